@@ -1,0 +1,163 @@
+"""Oracle (TEST INFRASTRUCTURE): golden-fixture generator.  Runs ONLY in the build
+container, where the read-only reference tree exists at /root/reference.
+
+It imports the *unmodified* reference modules (models.rfnet, utils.criterions) with the
+one-line `.cuda()` identity shim (criterions.py:153 hard-codes .cuda()), drives them with
+the deterministic synthetic weights/batches of oracle/synth.py, and
+  1. asserts that oracle/synth.rfnet_param_shapes() equals the reference state_dict layout;
+  2. asserts that the oracle restatement (oracle/rfnet_oracle.py, criterions_oracle.py,
+     train_step_oracle.py) reproduces the reference outputs, loss and gradients;
+  3. writes the REFERENCE's outputs to tests/golden/rfnet_passion_<case>.npz
+     (outputs in full; gradients as per-parameter L2 norm + a fixed random projection).
+Usage:  python -m oracle.gen_golden            (from the repo root)
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference/code"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (B, S, labels, mask_ids, mask_type, use_passion, temp, seed)
+    "idtU": (2, 16, "U", None, "idt", True, 4.0, 1037),
+    "idtS": (2, 16, "S", [3, 14], "idt", True, 4.0, 7),
+    "pdtU": (1, 16, "U", [12], "pdt", True, 4.0, 11),
+    "idtU_nopassion": (2, 16, "U", [10, 5], "idt", False, 4.0, 5),
+    "idtS24": (1, 24, "S", [11], "idt", True, 2.0, 3),
+}
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # CPU shim, see SURVEY.md §8(c)
+    from models import rfnet as ref_rfnet
+    from utils import criterions as ref_crit
+    return ref_rfnet, ref_crit
+
+
+def projection(name, n):
+    """Fixed ±1 vector per parameter (seeded by a stable hash of its name)."""
+    h = 0
+    for ch in name:
+        h = (h * 131 + ord(ch)) % (2 ** 31 - 1)
+    return np.random.RandomState(h).randint(0, 2, n).astype(np.float64) * 2 - 1
+
+
+def grad_summary(named_grads):
+    names = sorted(named_grads)
+    norms = np.array([float(named_grads[k].double().norm()) for k in names])
+    projs = np.array([float((named_grads[k].double().reshape(-1).numpy() * projection(k, named_grads[k].numel())).sum())
+                      for k in names])
+    return names, norms, projs
+
+
+def reference_mix(ref_crit, outs, target, mask, imb_beta, modal_weight, mask_type):
+    """train.py:228-280 applied to the reference's own outputs with the reference's own criterions."""
+    fuse_pred, prm_bs, sep_bs, kl_bs, proto_bs, dist_bs = outs
+    fuse = (ref_crit.softmax_weighted_loss_bs(fuse_pred, target, num_cls=4)
+            + ref_crit.dice_loss_bs(fuse_pred, target, num_cls=4)).sum()
+    prm = prm_bs.sum()
+    rp_iter = torch.zeros(4)
+    if mask_type == "pdt":
+        sep_m, kl_m, proto_m = sep_bs.sum(0), kl_bs.sum(0), proto_bs.sum(0)
+        for bs in range(fuse_pred.size(0)):
+            rp_iter += dist_bs[bs] / torch.mean(dist_bs[bs]) - 1
+        rp_mask = rp_iter > 0
+        kl, proto = (imb_beta * kl_m).sum(), (rp_mask * proto_m).sum()
+        sep = (rp_mask * imb_beta * sep_m).sum()
+    else:
+        sep_m, kl_m, proto_m = (sep_bs * mask).sum(0), (kl_bs * mask).sum(0), (proto_bs * mask).sum(0)
+        for bs in range(fuse_pred.size(0)):
+            rp_iter += mask[bs] * (dist_bs[bs] / (sum(dist_bs[bs]) / sum(mask[bs])) - 1)
+        rp_mask = rp_iter > 0
+        kl, proto = (imb_beta * modal_weight * kl_m).sum(), (rp_mask * modal_weight * proto_m).sum()
+        sep = (rp_mask * imb_beta * modal_weight * sep_m).sum()
+    return fuse + sep + prm + kl * 0.5 + proto * 0.1, rp_iter
+
+
+def main():
+    from oracle import rfnet_oracle, synth, train_step_oracle
+    ref_rfnet, ref_crit = import_reference()
+    os.makedirs(GOLD, exist_ok=True)
+    src_csv = "/root/reference/datasets/BraTS/brats_split/Brats2020_imb_split_mr2468.csv"
+    shutil.copy(src_csv, os.path.join(GOLD, "Brats2020_imb_split_mr2468.csv"))   # golden data table, not code
+    shutil.copy("/root/reference/datasets/BraTS/BRATS2020_Training_none_npy/train.txt",
+                os.path.join(GOLD, "brats2020_train.txt"))
+
+    torch.manual_seed(1037)
+    ref_model = ref_rfnet.Model(num_cls=4)
+    ref_sd = ref_model.state_dict()
+    shapes = synth.rfnet_param_shapes()
+    assert list(shapes.keys()) == list(ref_sd.keys()), "parameter order differs from reference"
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    sd = synth.make_state_dict(1037)
+    ref_model.load_state_dict(sd)
+    imb_beta = torch.tensor([1.1, 0.9, 1.3, 0.7])
+    modal_weight = torch.tensor([219 / 90.0, 219 / 135.0, 219 / 184.0, 219 / 43.0])   # iter_per_epoch/modal_num, mr2468
+
+    worst = 0.0
+    for case, (B, S, labels, mask_ids, mask_type, use_passion, temp, seed) in CASES.items():
+        x, target, mask, y = synth.make_batch(B, S, seed=seed, labels=labels, mask_ids=mask_ids)
+        ref_model.is_training, ref_model.use_passion, ref_model.mask_type = True, use_passion, mask_type
+        ref_model.zero_grad()
+        outs = ref_model(x, mask, target=target, temp=temp)
+        P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        o_outs = rfnet_oracle.forward(P, x, mask, target, temp, use_passion=use_passion, mask_type=mask_type)
+        save = {"B": B, "S": S, "temp": temp, "seed": seed, "mask": mask.numpy(), "labels_kind": labels,
+                "mask_type": mask_type, "use_passion": use_passion,
+                "imb_beta": imb_beta.numpy(), "modal_weight": modal_weight.numpy()}
+        names_out = ["fuse_prob", "prm_loss", "sep_loss", "kl_loss", "proto_loss", "dist"][:len(outs)]
+        for n, r, o in zip(names_out, outs, o_outs):
+            err = float((r - o).detach().abs().max())
+            worst = max(worst, err)
+            assert err < 2e-5, (case, n, err)
+            save[n] = r.detach().numpy()
+        if use_passion:
+            loss, rp_iter = reference_mix(ref_crit, outs, target, mask, imb_beta, modal_weight, mask_type)
+            o_loss, o_parts = train_step_oracle.loss_mix(o_outs, target, mask, imb_beta, modal_weight, mask_type=mask_type)
+            assert abs(float(loss) - float(o_loss)) < 1e-4 * max(1.0, abs(float(loss))), (case, float(loss), float(o_loss))
+            assert torch.allclose(rp_iter, o_parts["rp_iter"], atol=1e-4, equal_nan=True), (rp_iter, o_parts["rp_iter"])
+            save["rp_iter"] = rp_iter.detach().numpy()
+        else:
+            fuse = (ref_crit.softmax_weighted_loss_bs(outs[0], target, num_cls=4) + ref_crit.dice_loss_bs(outs[0], target, num_cls=4)).sum()
+            loss = fuse + outs[1].sum() + (outs[2] * mask).sum()
+            from oracle import criterions_oracle as oc
+            o_fuse = (oc.softmax_weighted_loss_bs(o_outs[0], target) + oc.dice_loss_bs(o_outs[0], target)).sum()
+            o_loss = o_fuse + o_outs[1].sum() + (o_outs[2] * mask).sum()
+        loss.backward()
+        o_loss.backward()
+        ref_g = {k: p.grad.detach().clone() for k, p in ref_model.named_parameters() if p.grad is not None}
+        names, norms, projs = grad_summary(ref_g)
+        for k in names:
+            # conv biases feeding an InstanceNorm have pure-rounding-noise grads
+            g_r, g_o = ref_g[k], P[k].grad
+            den = float(g_r.norm())
+            if den > 1e-5:
+                rel = float((g_r - g_o).norm()) / den
+                assert rel < 2e-4, (case, k, rel)
+                worst = max(worst, rel)
+        save["loss"] = float(loss)
+        save["grad_names"] = np.array(names)
+        save["grad_norms"] = norms
+        save["grad_projs"] = projs
+        # inference path (rfnet.py:403)
+        ref_model.is_training = False
+        with torch.no_grad():
+            inf = ref_model(x, mask)
+            o_inf = rfnet_oracle.forward({k: v for k, v in sd.items()}, x, mask, is_training=False, mask_type=mask_type)
+        assert float((inf - o_inf).abs().max()) < 2e-5
+        save["infer_prob"] = inf.numpy()
+        save["infer_argmax"] = inf.argmax(1).numpy().astype(np.int8)
+        np.savez_compressed(os.path.join(GOLD, f"rfnet_passion_{case}.npz"), **save)
+        print(f"{case}: loss {float(loss):.6f}  oracle {float(o_loss):.6f}  n_grads {len(names)}")
+    print("oracle-vs-reference worst abs/rel error:", worst)
+
+
+if __name__ == "__main__":
+    main()
