@@ -1,0 +1,117 @@
+/* passion_b200 — C ABI of the B200-native PASSION training hot path.
+ *
+ * The reference (Jun-Jie-Shi/PASSION) is pure Python/PyTorch and has no FFI layer; its hot
+ * path reaches the GPU through torch.nn library modules.  Each entry point below replaces one
+ * of those library call sites (cited as reference file:line) with a hand-written sm_100a
+ * kernel.  The Python host side (passion_b200/ops.py) binds these with ctypes and exposes them
+ * behind the reference's own module interface (Model.forward, criterions.*_bs).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PB_E* code otherwise;
+ *     pb_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch); no hidden allocation,
+ *     no hidden synchronisation; every kernel is enqueued on `stream` and is CUDA-graph
+ *     capture safe.  Scratch comes from caller-provided workspaces.
+ *   - activations are dense NDHWC ("channels last"): [N][D][H][W][C], C fastest.
+ *     dtype 0 = float32 (check mode), 1 = bfloat16 (storage only; all arithmetic accumulates in fp32).
+ *   - statistics buffers are float64 so that the atomically accumulated sums are order-insensitive
+ *     to ~1e-16 relative.
+ */
+#ifndef PASSION_B200_H
+#define PASSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pb_stream_t;            /* cudaStream_t */
+
+enum { PB_OK = 0, PB_EINVAL = -1, PB_ECUDA = -2, PB_EUNSUPPORTED = -3 };
+enum { PB_F32 = 0, PB_BF16 = 1 };
+enum { PB_PAD_ZERO = 0, PB_PAD_REFLECT = 1 };
+
+int         pb_version(void);
+const char* pb_last_error(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+long long   pb_launch_count(void);
+
+/* ---- 3-D convolution -------------------------------------------------------------------
+ * Replaces nn.Conv3d inside general_conv3d (models/blocks.py:354-370, conv at :357) and the plain
+ * heads (models/rfnet.py:69,107; models/blocks.py:407,455).
+ * Input = channel concatenation of x0 (C0 channels) and x1 (C1 channels, may be NULL/0):
+ * the torch.cat((a, b), dim=1) feeding a conv (rfnet.py:75,79,83,133,139,145; blocks.py:463) is
+ * never materialised.  Samples are split evenly into `groups` weight groups (the four
+ * modality encoders, rfnet.py:234-237, run as one launch with groups = 4).
+ * Weights are fp32 in the kernel layout [groups][k^3 taps][Cin][Cout] (fwd, wgrad output)
+ * or [groups][k^3 taps][Cout][Cin] (dgrad).  ksize in {1,3}; stride in {1,2}; padding = ksize/2.
+ */
+typedef struct pb_conv_desc {
+    int32_t dtype;                 /* PB_F32 | PB_BF16 : storage type of x, y, dy, dx        */
+    int32_t n;                     /* batch                                                   */
+    int32_t di, hi, wi;            /* input spatial size                                      */
+    int32_t dout, ho, wo;          /* output spatial size                                     */
+    int32_t c0, c1;                /* channels of the two concatenated inputs (c1 may be 0)   */
+    int32_t cout;
+    int32_t ksize, stride;
+    int32_t pad_mode;              /* PB_PAD_ZERO | PB_PAD_REFLECT                            */
+    int32_t groups;
+} pb_conv_desc;
+
+/* y = conv(cat(x0,x1)) (+bias).  If stats != NULL it must be zero-filled [n][cout][2] float64 and
+ * receives per-(sample,channel) sum and sum of squares of the fp32 accumulators (the
+ * InstanceNorm statistics, blocks.py:18) — fused into the conv epilogue. */
+int pb_conv3d_fwd(const pb_conv_desc* d, const void* x0, const void* x1, const float* w,
+                  const float* bias, void* y, double* stats, pb_stream_t stream);
+/* dx0/dx1 = gradient w.r.t. the two inputs (exact adjoint incl. reflect padding). wt is the
+ * [groups][taps][Cout][Cin] layout. */
+int pb_conv3d_dgrad(const pb_conv_desc* d, const void* dy, const float* wt, void* dx0, void* dx1,
+                    pb_stream_t stream);
+/* dw[groups][taps][Cin][Cout] += sum over samples/voxels; dw must be zero-filled by the caller. */
+int pb_conv3d_wgrad(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy,
+                    float* dw, pb_stream_t stream);
+
+/* ---- InstanceNorm3d(affine=False, eps) + LeakyReLU(slope) (+ residual) -----------------
+ * Replaces norm + activation of general_conv3d (blocks.py:18, :363, :367-369) and the encoder
+ * residual add (rfnet.py:37,40,43,46).
+ *   pb_inorm_finalize : stats (sum, sumsq) -> mr[n][c] = (mean, rstd) float32
+ *   pb_inorm_lrelu_fwd: out = lrelu((y-mean)*rstd) (+ res)
+ *   pb_inorm_lrelu_bwd: given dout, y, mr -> dy ; sums is a zero-filled [n][c][2] float64 scratch.
+ */
+int pb_inorm_finalize(const double* stats, float* mr, int n, int c, long long voxels, float eps,
+                      pb_stream_t stream);
+int pb_inorm_lrelu_fwd(int dtype, const void* y, const float* mr, const void* res, void* out,
+                       int n, long long voxels, int c, float slope, pb_stream_t stream);
+int pb_inorm_lrelu_bwd(int dtype, const void* dout, const void* y, const float* mr, double* sums,
+                       void* dy, int n, long long voxels, int c, float slope, pb_stream_t stream);
+
+/* ---- trilinear up-sampling, align_corners=True, integer scale ---------------------------
+ * Replaces nn.Upsample (rfnet.py:54,59,64,110-112,208-210). */
+int pb_upsample_fwd(int dtype, const void* x, void* y, int n, int d, int h, int w, int c, int scale,
+                    pb_stream_t stream);
+int pb_upsample_bwd(int dtype, const void* dy, void* dx, int n, int d, int h, int w, int c, int scale,
+                    pb_stream_t stream);
+
+/* ---- region-aware modal fusion (models/blocks.py:495-517, 597-616) ----------------------
+ * y  [n][v][K*C]  masked modality features (channel = k*C + c), storage dtype
+ * p  [n][v][4]    float32 class probabilities (softmax of the PRM logits, detached)
+ *   pool : S[n][i][k*C+c] = sum_v y*p_i   (float64, zero-filled), Psum[n][i] = sum_v p_i
+ *   mix  : R[n][v][i*C+c] = p_i * sum_k gate[n][i][k] * y[n][v][k*C+c]
+ *   mix_bwd_gate : dgate[n][i][k] = sum_{v,c} p_i * y[k*C+c] * dR[i*C+c]   (float64, zero-filled)
+ *   bwd_y : dy[n][v][k*C+c] = sum_i p_i * (gate[n][i][k]*dR[n][v][i*C+c] + dS[n][i][k*C+c])
+ */
+int pb_rfm_pool(int dtype, const void* y, const float* p, double* S, double* Psum,
+                int n, long long voxels, int kc, pb_stream_t stream);
+int pb_rfm_mix(int dtype, const void* y, const float* p, const float* gate, void* r,
+               int n, long long voxels, int k, int c, pb_stream_t stream);
+int pb_rfm_mix_bwd_gate(int dtype, const void* y, const float* p, const void* dr, double* dgate,
+                        int n, long long voxels, int k, int c, pb_stream_t stream);
+int pb_rfm_bwd_y(int dtype, const float* p, const float* gate, const void* dr, const float* dS,
+                 void* dy, int n, long long voxels, int k, int c, pb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASSION_B200_H */

@@ -1,0 +1,81 @@
+"""ctypes binding of libpassion_b200.so (the C ABI declared in include/passion_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a symbol is absent the
+import of any op raises, and every op refuses non-CUDA tensors.
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpassion_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "passion_b200.h")
+
+PB_F32, PB_BF16 = 0, 1
+PB_PAD_ZERO, PB_PAD_REFLECT = 0, 1
+
+_lib = None
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of pb_conv_desc."""
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "dtype", "n", "di", "hi", "wi", "dout", "ho", "wo", "c0", "c1", "cout", "ksize", "stride",
+        "pad_mode", "groups")]
+
+
+def declared_symbols():
+    """Every function name declared in include/passion_b200.h."""
+    with open(HEADER_PATH) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", src)))
+
+
+def load():
+    """dlopen the library and check that it exports every symbol of the header."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"passion_b200: CUDA library not built ({LIB_PATH}); run `python __graft_entry__.py`. "
+            "There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    if missing:
+        raise RuntimeError(f"passion_b200: library is missing symbols {missing}")
+    lib.pb_last_error.restype = ctypes.c_char_p
+    lib.pb_launch_count.restype = ctypes.c_longlong
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    cd = ctypes.POINTER(ConvDesc)
+    sig = {
+        "pb_conv3d_fwd": [cd, vp, vp, vp, vp, vp, vp, vp],
+        "pb_conv3d_dgrad": [cd, vp, vp, vp, vp, vp],
+        "pb_conv3d_wgrad": [cd, vp, vp, vp, vp, vp],
+        "pb_inorm_finalize": [vp, vp, i32, i32, i64, f32, vp],
+        "pb_inorm_lrelu_fwd": [i32, vp, vp, vp, vp, i32, i64, i32, f32, vp],
+        "pb_inorm_lrelu_bwd": [i32, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp],
+        "pb_upsample_fwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+        "pb_upsample_bwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+        "pb_rfm_pool": [i32, vp, vp, vp, vp, i32, i64, i32, vp],
+        "pb_rfm_mix": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
+        "pb_rfm_mix_bwd_gate": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
+        "pb_rfm_bwd_y": [i32, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],
+    }
+    for name, args in sig.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"passion_b200.{what} failed ({rc}): {load().pb_last_error().decode()}")
+
+
+def launch_count():
+    return int(load().pb_launch_count())

@@ -1,0 +1,507 @@
+// 3-D convolution, direct FFMA path (fp32 accumulate): forward, dgrad, wgrad.
+//
+// This is the precision-reference / small-channel path of the library: it serves the fp32
+// check mode (rel-L2 <= 1e-4 vs the CPU oracle) and every (Cin, Cout) class, including the
+// C in {1,2,4} layers that cannot feed a tensor-core tile.  The bf16 tcgen05 implicit-GEMM
+// path for the dominant classes lives in conv3d_tc.cu.
+//
+// Replaces nn.Conv3d of general_conv3d (reference models/blocks.py:357) incl. its
+// padding_mode='reflect', the torch.cat feeding decoder convs (models/rfnet.py:75,79,83,133,139,145)
+// and the four separate modality encoders (models/rfnet.py:234-237) as weight groups.
+#include "common.cuh"
+
+namespace {
+
+struct ConvK {
+    int N, Di, Hi, Wi, Do, Ho, Wo, C0, C1, Cin, Cout, K, S, pad, reflect, groups, npg;
+    long long Vi, Vo;
+};
+
+template <int N> __device__ __forceinline__ void lds_vec(const float* p, float* o) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            float4 v = reinterpret_cast<const float4*>(p)[i];
+            o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
+        }
+    } else if constexpr (N == 2) {
+        float2 v = *reinterpret_cast<const float2*>(p); o[0] = v.x; o[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) o[i] = p[i];
+    }
+}
+
+// acc[j] += sum_i xv[i] * wr[i*NO + j]
+template <int NI, int NO> __device__ __forceinline__ void fma_block(const float* xv, const float* wr, float* acc) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        float wv[NO];
+        lds_vec<NO>(wr + i * NO, wv);
+#pragma unroll
+        for (int j = 0; j < NO; ++j) acc[j] = fmaf(xv[i], wv[j], acc[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------ forward
+// one thread = one output voxel x CO_T output channels; weights of the (group, co-chunk) in smem.
+template <typename T, int CI_V, int CO_T>
+__global__ void __launch_bounds__(128) conv_fwd_kernel(ConvK p, const T* __restrict__ x0, const T* __restrict__ x1,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       T* __restrict__ y, double* __restrict__ stats) {
+    extern __shared__ __align__(16) float wsm[];              // [taps][Cin][CO_T]
+    __shared__ float red[4][CO_T * 2];
+    const int n = blockIdx.z, coc = blockIdx.y, g = n / p.npg;
+    const int taps = p.K * p.K * p.K;
+    const float* wg = w + (size_t)g * taps * p.Cin * p.Cout + coc * CO_T;
+    for (int i = threadIdx.x; i < taps * p.Cin * CO_T; i += 128) {
+        int j = i % CO_T, r = i / CO_T;
+        wsm[i] = wg[(size_t)r * p.Cout + j];
+    }
+    __syncthreads();
+
+    long long o = (long long)blockIdx.x * 128 + threadIdx.x;
+    const bool valid = o < p.Vo;
+    if (!valid) o = p.Vo - 1;
+    const int ow = (int)(o % p.Wo);
+    const int t1 = (int)(o / p.Wo);
+    const int oh = t1 % p.Ho, od = t1 / p.Ho;
+
+    float acc[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[j] = bias ? bias[(size_t)g * p.Cout + coc * CO_T + j] : 0.f;
+
+    for (int kd = 0; kd < p.K; ++kd) {
+        int id = od * p.S + kd - p.pad;
+        if (p.reflect) id = reflect_idx(id, p.Di); else if (id < 0 || id >= p.Di) continue;
+        for (int kh = 0; kh < p.K; ++kh) {
+            int ih = oh * p.S + kh - p.pad;
+            if (p.reflect) ih = reflect_idx(ih, p.Hi); else if (ih < 0 || ih >= p.Hi) continue;
+            for (int kw = 0; kw < p.K; ++kw) {
+                int iw = ow * p.S + kw - p.pad;
+                if (p.reflect) iw = reflect_idx(iw, p.Wi); else if (iw < 0 || iw >= p.Wi) continue;
+                const size_t vox = (((size_t)n * p.Di + id) * p.Hi + ih) * p.Wi + iw;
+                const float* wt = wsm + ((kd * p.K + kh) * p.K + kw) * p.Cin * CO_T;
+                const T* p0 = x0 + vox * p.C0;
+                for (int c = 0; c < p.C0; c += CI_V) {
+                    float xv[CI_V];
+                    VecIO<T, CI_V>::load(p0 + c, xv);
+                    fma_block<CI_V, CO_T>(xv, wt + c * CO_T, acc);
+                }
+                if (p.C1) {
+                    const T* p1 = x1 + vox * p.C1;
+                    const float* wt1 = wt + p.C0 * CO_T;
+                    for (int c = 0; c < p.C1; c += CI_V) {
+                        float xv[CI_V];
+                        VecIO<T, CI_V>::load(p1 + c, xv);
+                        fma_block<CI_V, CO_T>(xv, wt1 + c * CO_T, acc);
+                    }
+                }
+            }
+        }
+    }
+    if (valid) VecIO<T, CO_T>::store(y + ((size_t)n * p.Vo + o) * p.Cout + coc * CO_T, acc);
+    if (stats) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) {
+            float s = valid ? acc[j] : 0.f;
+            float q = s * s;
+            s = warp_sum(s); q = warp_sum(q);
+            if (lane == 0) { red[wid][2 * j] = s; red[wid][2 * j + 1] = q; }
+        }
+        __syncthreads();
+        if (threadIdx.x < CO_T * 2) {
+            float v = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+            atomicAdd(&stats[((size_t)n * p.Cout + coc * CO_T + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1)], (double)v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ dgrad
+// Exact adjoint of the forward gather, as a gather over dy: one thread = one INPUT voxel x CI_T
+// input channels.  For every padded position p that the forward's index map sends to this voxel
+// (p = i, plus the reflected twins -i / 2(D-1)-i next to the faces) and every tap k, the
+// contributing output is o = (p + pad - k) / stride when that is an in-range integer.
+__device__ __forceinline__ int dgrad_cand(int c, int i, int D, int pad, int reflect, bool& ok) {
+    if (c == 0) { ok = true; return i; }
+    if (c == 1) { ok = reflect && i >= 1 && i <= pad; return -i; }
+    int q = 2 * (D - 1) - i;
+    ok = reflect && q >= D && q <= D - 1 + pad;
+    return q;
+}
+
+template <typename T, int CO_V, int CI_T>
+__global__ void __launch_bounds__(128) conv_dgrad_kernel(ConvK p, const T* __restrict__ dy, const float* __restrict__ wt,
+                                                         T* __restrict__ dx0, T* __restrict__ dx1) {
+    extern __shared__ __align__(16) float wsm[];              // [taps][Cout][CI_T]
+    const int n = blockIdx.z, cic = blockIdx.y, g = n / p.npg;
+    const int taps = p.K * p.K * p.K;
+    const float* wg = wt + (size_t)g * taps * p.Cout * p.Cin + cic * CI_T;
+    for (int i = threadIdx.x; i < taps * p.Cout * CI_T; i += 128) {
+        int j = i % CI_T, r = i / CI_T;
+        wsm[i] = wg[(size_t)r * p.Cin + j];
+    }
+    __syncthreads();
+
+    long long iv = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (iv >= p.Vi) return;
+    const int iw = (int)(iv % p.Wi);
+    const int t1 = (int)(iv / p.Wi);
+    const int ih = t1 % p.Hi, id = t1 / p.Hi;
+
+    float acc[CI_T];
+#pragma unroll
+    for (int j = 0; j < CI_T; ++j) acc[j] = 0.f;
+    const int nc = p.reflect ? 3 : 1;
+
+    for (int cd = 0; cd < nc; ++cd) {
+        bool okd; const int pd = dgrad_cand(cd, id, p.Di, p.pad, p.reflect, okd);
+        if (!okd) continue;
+        for (int kd = 0; kd < p.K; ++kd) {
+            const int td = pd + p.pad - kd;
+            if (td < 0) continue;
+            const int od = td / p.S;
+            if (od * p.S != td || od >= p.Do) continue;
+            for (int ch = 0; ch < nc; ++ch) {
+                bool okh; const int ph = dgrad_cand(ch, ih, p.Hi, p.pad, p.reflect, okh);
+                if (!okh) continue;
+                for (int kh = 0; kh < p.K; ++kh) {
+                    const int th = ph + p.pad - kh;
+                    if (th < 0) continue;
+                    const int oh = th / p.S;
+                    if (oh * p.S != th || oh >= p.Ho) continue;
+                    for (int cw = 0; cw < nc; ++cw) {
+                        bool okw; const int pw = dgrad_cand(cw, iw, p.Wi, p.pad, p.reflect, okw);
+                        if (!okw) continue;
+                        for (int kw = 0; kw < p.K; ++kw) {
+                            const int tw = pw + p.pad - kw;
+                            if (tw < 0) continue;
+                            const int ow = tw / p.S;
+                            if (ow * p.S != tw || ow >= p.Wo) continue;
+                            const T* pdy = dy + ((((size_t)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout;
+                            const float* wr = wsm + ((kd * p.K + kh) * p.K + kw) * p.Cout * CI_T;
+                            for (int c = 0; c < p.Cout; c += CO_V) {
+                                float gv[CO_V];
+                                VecIO<T, CO_V>::load(pdy + c, gv);
+                                fma_block<CO_V, CI_T>(gv, wr + c * CI_T, acc);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const int ci0 = cic * CI_T;
+    const size_t vox = (size_t)n * p.Vi + iv;
+    if (ci0 < p.C0) VecIO<T, CI_T>::store(dx0 + vox * p.C0 + ci0, acc);
+    else            VecIO<T, CI_T>::store(dx1 + vox * p.C1 + (ci0 - p.C0), acc);
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+// Persistent blocks; each stages an input halo tile and a dy tile in smem (fp32) and every thread
+// owns one (tap, CIQ input channels) x CO_T slab of dw for a slice of the tile's voxels.
+struct WgK {
+    int td, th, tw;        // output tile
+    int hd, hh, hw;        // halo tile = (t-1)*S + K
+    int tiles_d, tiles_h, tiles_w;
+    int cic;               // input channels per chunk
+    int xs;                // smem voxel stride of the halo tile (floats)
+    int nitems, slices;
+    int n_cic, n_coc;
+};
+
+template <typename T, int CIQ, int CO_T, int LV>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(ConvK p, WgK q, const T* __restrict__ x0, const T* __restrict__ x1,
+                                                         const T* __restrict__ dy, float* __restrict__ dw) {
+    extern __shared__ __align__(16) float sm[];
+    float* xsm = sm;                                          // [halo voxels][xs]
+    const int halo = q.hd * q.hh * q.hw, tv = q.td * q.th * q.tw;
+    float* dsm = sm + (((size_t)halo * q.xs + 3) & ~(size_t)3);  // [tile voxels][CO_T], 16 B aligned
+    const int g = blockIdx.z;
+    const int cic_i = blockIdx.y % q.n_cic, coc = blockIdx.y / q.n_cic;
+    const int ci0 = cic_i * q.cic;                            // global input-channel offset of this chunk
+    const bool from1 = ci0 >= p.C0;
+    const T* xsrc = from1 ? x1 : x0;
+    const int csrc = from1 ? p.C1 : p.C0, coff = from1 ? ci0 - p.C0 : ci0;
+    const int tid = threadIdx.x;
+    const int item = tid % q.nitems, slice = tid / q.nitems;
+    const bool active = slice < q.slices;
+    const int nq = q.cic / CIQ;
+    const int tap = item / nq, ciq = item % nq;
+    const int kd = tap / (p.K * p.K), kh = (tap / p.K) % p.K, kw = tap % p.K;
+
+    float acc[CIQ][CO_T];
+#pragma unroll
+    for (int i = 0; i < CIQ; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[i][j] = 0.f;
+
+    const int tiles_ps = q.tiles_d * q.tiles_h * q.tiles_w;
+    const long long ntiles = (long long)p.npg * tiles_ps;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n = g * p.npg + (int)(t / tiles_ps);
+        int r = (int)(t % tiles_ps);
+        const int tw_i = r % q.tiles_w; r /= q.tiles_w;
+        const int th_i = r % q.tiles_h, td_i = r / q.tiles_h;
+        const int od0 = td_i * q.td, oh0 = th_i * q.th, ow0 = tw_i * q.tw;
+        __syncthreads();                                      // previous tile fully consumed
+        // ---- stage input halo tile (reflect / zero padding resolved here)
+        const int lpv = q.cic / LV;
+        for (int idx = tid; idx < halo * lpv; idx += 256) {
+            const int hv = idx / lpv, lc = idx % lpv;
+            const int hw_i = hv % q.hw, r2 = hv / q.hw;
+            const int hh_i = r2 % q.hh, hd_i = r2 / q.hh;
+            int id = od0 * p.S - p.pad + hd_i, ih = oh0 * p.S - p.pad + hh_i, iw = ow0 * p.S - p.pad + hw_i;
+            bool ok = true;
+            if (p.reflect) {
+                id = reflect_idx(id, p.Di); ih = reflect_idx(ih, p.Hi); iw = reflect_idx(iw, p.Wi);
+                ok = id >= 0 && id < p.Di && ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi;   // far overhang of partial tiles
+            } else {
+                ok = id >= 0 && id < p.Di && ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi;
+            }
+            float v[LV];
+            if (ok) VecIO<T, LV>::load(xsrc + ((((size_t)n * p.Di + id) * p.Hi + ih) * p.Wi + iw) * csrc + coff + lc * LV, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < LV; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < LV; ++i) xsm[(size_t)hv * q.xs + lc * LV + i] = v[i];
+        }
+        // ---- stage dy tile (zero outside the volume)
+        for (int idx = tid; idx < tv; idx += 256) {
+            const int vw = idx % q.tw, r2 = idx / q.tw;
+            const int vh = r2 % q.th, vd = r2 / q.th;
+            const int od = od0 + vd, oh = oh0 + vh, ow = ow0 + vw;
+            float v[CO_T];
+            if (od < p.Do && oh < p.Ho && ow < p.Wo)
+                VecIO<T, CO_T>::load(dy + ((((size_t)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + coc * CO_T, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < CO_T; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) dsm[(size_t)idx * CO_T + j] = v[j];
+        }
+        __syncthreads();
+        if (active) {
+            for (int v = slice; v < tv; v += q.slices) {
+                const int vw = v % q.tw, r2 = v / q.tw;
+                const int vh = r2 % q.th, vd = r2 / q.th;
+                const int hv = ((vd * p.S + kd) * q.hh + vh * p.S + kh) * q.hw + vw * p.S + kw;
+                float xv[CIQ], gv[CO_T];
+                lds_vec<CIQ>(xsm + (size_t)hv * q.xs + ciq * CIQ, xv);
+                lds_vec<CO_T>(dsm + (size_t)v * CO_T, gv);
+#pragma unroll
+                for (int i = 0; i < CIQ; ++i)
+#pragma unroll
+                    for (int j = 0; j < CO_T; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+            }
+        }
+    }
+    if (active) {
+        const int taps = p.K * p.K * p.K;
+#pragma unroll
+        for (int i = 0; i < CIQ; ++i) {
+            float* o = dw + (((size_t)g * taps + tap) * p.Cin + ci0 + ciq * CIQ + i) * p.Cout + coc * CO_T;
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) atomicAdd(o + j, acc[i][j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+int fill(const pb_conv_desc* d, ConvK& k) {
+    if (!d) return -1;
+    if (d->ksize != 1 && d->ksize != 3) return -1;
+    if (d->stride != 1 && d->stride != 2) return -1;
+    if (d->groups < 1 || d->n % d->groups) return -1;
+    if (d->c0 < 1 || d->c1 < 0 || d->cout < 1) return -1;
+    k.N = d->n; k.Di = d->di; k.Hi = d->hi; k.Wi = d->wi; k.Do = d->dout; k.Ho = d->ho; k.Wo = d->wo;
+    k.C0 = d->c0; k.C1 = d->c1; k.Cin = d->c0 + d->c1; k.Cout = d->cout; k.K = d->ksize; k.S = d->stride;
+    k.pad = d->ksize / 2; k.reflect = (d->pad_mode == PB_PAD_REFLECT && d->ksize == 3) ? 1 : 0;
+    k.groups = d->groups; k.npg = d->n / d->groups;
+    k.Vi = (long long)d->di * d->hi * d->wi; k.Vo = (long long)d->dout * d->ho * d->wo;
+    // output size must match the conv arithmetic
+    auto osz = [&](int i) { return (i + 2 * k.pad - k.K) / k.S + 1; };
+    if (osz(k.Di) != k.Do || osz(k.Hi) != k.Ho || osz(k.Wi) != k.Wo) return -1;
+    if (k.reflect && (k.Di < 2 || k.Hi < 2 || k.Wi < 2)) return -1;
+    return 0;
+}
+
+int chunk_of(int c, int cap) {           // largest power of two <= cap dividing c
+    int v = cap;
+    while (v > 1 && c % v) v >>= 1;
+    return v;
+}
+
+template <typename K> int set_smem(K kern, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) { pb_set_error("cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e)); return PB_ECUDA; }
+    }
+    return 0;
+}
+
+template <typename T, int CI_V, int CO_T>
+int launch_fwd(const ConvK& k, const void* x0, const void* x1, const float* w, const float* bias, void* y, double* stats,
+               cudaStream_t st) {
+    const size_t smem = (size_t)k.K * k.K * k.K * k.Cin * CO_T * sizeof(float);
+    auto kern = conv_fwd_kernel<T, CI_V, CO_T>;
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((unsigned)((k.Vo + 127) / 128), k.Cout / CO_T, k.N);
+    kern<<<grid, 128, smem, st>>>(k, (const T*)x0, (const T*)x1, w, bias, (T*)y, stats);
+    return 0;
+}
+
+template <typename T, int CI_V>
+int dispatch_fwd_co(int co_t, const ConvK& k, const void* x0, const void* x1, const float* w, const float* bias, void* y,
+                    double* stats, cudaStream_t st) {
+    switch (co_t) {
+        case 16: return launch_fwd<T, CI_V, 16>(k, x0, x1, w, bias, y, stats, st);
+        case 8:  return launch_fwd<T, CI_V, 8>(k, x0, x1, w, bias, y, stats, st);
+        case 4:  return launch_fwd<T, CI_V, 4>(k, x0, x1, w, bias, y, stats, st);
+        case 2:  return launch_fwd<T, CI_V, 2>(k, x0, x1, w, bias, y, stats, st);
+        default: return launch_fwd<T, CI_V, 1>(k, x0, x1, w, bias, y, stats, st);
+    }
+}
+
+template <typename T>
+int dispatch_fwd(const ConvK& k, const void* x0, const void* x1, const float* w, const float* bias, void* y, double* stats,
+                 cudaStream_t st) {
+    int ci_v = chunk_of(k.C0, 8);
+    if (k.C1) ci_v = chunk_of(k.C1, ci_v);
+    const int co_t = chunk_of(k.Cout, 16);
+    switch (ci_v) {
+        case 8:  return dispatch_fwd_co<T, 8>(co_t, k, x0, x1, w, bias, y, stats, st);
+        case 4:  return dispatch_fwd_co<T, 4>(co_t, k, x0, x1, w, bias, y, stats, st);
+        case 2:  return dispatch_fwd_co<T, 2>(co_t, k, x0, x1, w, bias, y, stats, st);
+        default: return dispatch_fwd_co<T, 1>(co_t, k, x0, x1, w, bias, y, stats, st);
+    }
+}
+
+template <typename T, int CO_V, int CI_T>
+int launch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st) {
+    const size_t smem = (size_t)k.K * k.K * k.K * k.Cout * CI_T * sizeof(float);
+    auto kern = conv_dgrad_kernel<T, CO_V, CI_T>;
+    if (int e = set_smem(kern, smem)) return e;
+    dim3 grid((unsigned)((k.Vi + 127) / 128), k.Cin / CI_T, k.N);
+    kern<<<grid, 128, smem, st>>>(k, (const T*)dy, wt, (T*)dx0, (T*)dx1);
+    return 0;
+}
+
+template <typename T, int CO_V>
+int dispatch_dgrad_ci(int ci_t, const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st) {
+    switch (ci_t) {
+        case 16: return launch_dgrad<T, CO_V, 16>(k, dy, wt, dx0, dx1, st);
+        case 8:  return launch_dgrad<T, CO_V, 8>(k, dy, wt, dx0, dx1, st);
+        case 4:  return launch_dgrad<T, CO_V, 4>(k, dy, wt, dx0, dx1, st);
+        case 2:  return launch_dgrad<T, CO_V, 2>(k, dy, wt, dx0, dx1, st);
+        default: return launch_dgrad<T, CO_V, 1>(k, dy, wt, dx0, dx1, st);
+    }
+}
+
+template <typename T>
+int dispatch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st) {
+    const int co_v = chunk_of(k.Cout, 8);
+    int ci_t = chunk_of(k.C0, 16);
+    if (k.C1) ci_t = chunk_of(k.C1, ci_t);
+    switch (co_v) {
+        case 8:  return dispatch_dgrad_ci<T, 8>(ci_t, k, dy, wt, dx0, dx1, st);
+        case 4:  return dispatch_dgrad_ci<T, 4>(ci_t, k, dy, wt, dx0, dx1, st);
+        case 2:  return dispatch_dgrad_ci<T, 2>(ci_t, k, dy, wt, dx0, dx1, st);
+        default: return dispatch_dgrad_ci<T, 1>(ci_t, k, dy, wt, dx0, dx1, st);
+    }
+}
+
+template <typename T, int CIQ, int CO_T, int LV>
+int launch_wgrad(const ConvK& k, WgK q, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
+    const size_t smem = ((((size_t)q.hd * q.hh * q.hw * q.xs + 3) & ~(size_t)3) + (size_t)q.td * q.th * q.tw * CO_T) * sizeof(float);
+    auto kern = conv_wgrad_kernel<T, CIQ, CO_T, LV>;
+    if (int e = set_smem(kern, smem)) return e;
+    const long long ntiles = (long long)k.npg * q.tiles_d * q.tiles_h * q.tiles_w;
+    const int pairs = q.n_cic * q.n_coc;
+    long long nblk = (148LL * 3 + (long long)pairs * k.groups - 1) / ((long long)pairs * k.groups);
+    if (nblk < 1) nblk = 1;
+    if (nblk > ntiles) nblk = ntiles;
+    dim3 grid((unsigned)nblk, pairs, k.groups);
+    kern<<<grid, 256, smem, st>>>(k, q, (const T*)x0, (const T*)x1, (const T*)dy, dw);
+    return 0;
+}
+
+template <typename T, int CIQ, int LV>
+int dispatch_wgrad_co(int co_t, const ConvK& k, const WgK& q, const void* x0, const void* x1, const void* dy, float* dw,
+                      cudaStream_t st) {
+    switch (co_t) {
+        case 16: return launch_wgrad<T, CIQ, 16, LV>(k, q, x0, x1, dy, dw, st);
+        case 8:  return launch_wgrad<T, CIQ, 8, LV>(k, q, x0, x1, dy, dw, st);
+        case 4:  return launch_wgrad<T, CIQ, 4, LV>(k, q, x0, x1, dy, dw, st);
+        case 2:  return launch_wgrad<T, CIQ, 2, LV>(k, q, x0, x1, dy, dw, st);
+        default: return launch_wgrad<T, CIQ, 1, LV>(k, q, x0, x1, dy, dw, st);
+    }
+}
+
+template <typename T>
+int dispatch_wgrad(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
+    WgK q;
+    if (k.S == 1) { q.td = 4; q.th = 4; q.tw = 8; } else { q.td = 2; q.th = 4; q.tw = 8; }
+    q.hd = (q.td - 1) * k.S + k.K; q.hh = (q.th - 1) * k.S + k.K; q.hw = (q.tw - 1) * k.S + k.K;
+    q.tiles_d = (k.Do + q.td - 1) / q.td; q.tiles_h = (k.Ho + q.th - 1) / q.th; q.tiles_w = (k.Wo + q.tw - 1) / q.tw;
+    int cic = chunk_of(k.C0, k.K == 3 ? 16 : 64);
+    if (k.C1) cic = chunk_of(k.C1, cic);
+    q.cic = cic;
+    const int ciq = chunk_of(cic, 4);
+    q.xs = cic + (cic >= 4 ? 4 : 0);                          // +4 floats: keeps 16 B alignment, spreads banks
+    const int taps = k.K * k.K * k.K;
+    q.nitems = taps * (cic / ciq);
+    if (q.nitems > 256) { pb_set_error("wgrad: nitems %d > 256", q.nitems); return PB_EUNSUPPORTED; }
+    q.slices = 256 / q.nitems;
+    const int co_t = chunk_of(k.Cout, 16);
+    q.n_cic = k.Cin / cic; q.n_coc = k.Cout / co_t;
+    switch (ciq) {
+        case 4:
+            if (cic % 8 == 0) return dispatch_wgrad_co<T, 4, 8>(co_t, k, q, x0, x1, dy, dw, st);
+            return dispatch_wgrad_co<T, 4, 4>(co_t, k, q, x0, x1, dy, dw, st);
+        case 2:  return dispatch_wgrad_co<T, 2, 2>(co_t, k, q, x0, x1, dy, dw, st);
+        default: return dispatch_wgrad_co<T, 1, 1>(co_t, k, q, x0, x1, dy, dw, st);
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_conv3d_fwd(const pb_conv_desc* d, const void* x0, const void* x1, const float* w, const float* bias,
+                             void* y, double* stats, pb_stream_t stream) {
+    ConvK k;
+    PB_CHECK_ARG(fill(d, k) == 0, "bad descriptor");
+    PB_CHECK_ARG(x0 && w && y && (d->c1 == 0 || x1), "null pointer");
+    int e = d->dtype == PB_BF16 ? dispatch_fwd<bf16>(k, x0, x1, w, bias, y, stats, (cudaStream_t)stream)
+                                : dispatch_fwd<float>(k, x0, x1, w, bias, y, stats, (cudaStream_t)stream);
+    if (e) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_conv3d_dgrad(const pb_conv_desc* d, const void* dy, const float* wt, void* dx0, void* dx1,
+                               pb_stream_t stream) {
+    ConvK k;
+    PB_CHECK_ARG(fill(d, k) == 0, "bad descriptor");
+    PB_CHECK_ARG(dy && wt && dx0 && (d->c1 == 0 || dx1), "null pointer");
+    int e = d->dtype == PB_BF16 ? dispatch_dgrad<bf16>(k, dy, wt, dx0, dx1, (cudaStream_t)stream)
+                                : dispatch_dgrad<float>(k, dy, wt, dx0, dx1, (cudaStream_t)stream);
+    if (e) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_conv3d_wgrad(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw,
+                               pb_stream_t stream) {
+    ConvK k;
+    PB_CHECK_ARG(fill(d, k) == 0, "bad descriptor");
+    PB_CHECK_ARG(x0 && dy && dw && (d->c1 == 0 || x1), "null pointer");
+    int e = d->dtype == PB_BF16 ? dispatch_wgrad<bf16>(k, x0, x1, dy, dw, (cudaStream_t)stream)
+                                : dispatch_wgrad<float>(k, x0, x1, dy, dw, (cudaStream_t)stream);
+    if (e) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

@@ -1,0 +1,180 @@
+// InstanceNorm3d(affine=False) + LeakyReLU (+ residual): finalize / apply / backward.
+// Memory-bound, vectorised (16 B per thread access), fp32 math, float64 cross-block sums.
+// Replaces reference models/blocks.py:18 (nn.InstanceNorm3d), :363 (LeakyReLU) and the encoder
+// residual adds models/rfnet.py:37,40,43,46.
+#include "common.cuh"
+
+namespace {
+
+__global__ void finalize_kernel(const double* __restrict__ stats, float* __restrict__ mr, int nc, double inv_v, float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    double mean = stats[2 * i] * inv_v;
+    double var = stats[2 * i + 1] * inv_v - mean * mean;     // biased variance, as InstanceNorm
+    if (var < 0.0) var = 0.0;
+    mr[2 * i] = (float)mean;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// out = lrelu((y - mean) * rstd) (+ res);  one thread = VEC channels of one voxel
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ mr,
+                                                        const T* __restrict__ res, T* __restrict__ out,
+                                                        long long total_vec, long long vox_c, int c, float slope) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * VEC;
+        const int n = (int)(e / vox_c);
+        const int c0 = (int)(e % c);
+        float v[VEC], r[VEC];
+        VecIO<T, VEC>::load(y + e, v);
+        if (res) VecIO<T, VEC>::load(res + e, r);
+        const float* m = mr + ((size_t)n * c + c0) * 2;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float xh = (v[j] - m[2 * j]) * m[2 * j + 1];
+            xh = xh > 0.f ? xh : xh * slope;
+            v[j] = res ? xh + r[j] : xh;
+        }
+        VecIO<T, VEC>::store(out + e, v);
+    }
+}
+
+// per-(n,c): sum g, sum g*xhat  with g = dout * lrelu'(xhat).  grid = (blocks_per_sample, n);
+// a thread keeps the same VEC channels for all its voxels (thread stride is a multiple of c/VEC).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
+                                                         const float* __restrict__ mr, double* __restrict__ sums,
+                                                         long long voxels, int c, float slope) {
+    extern __shared__ float ssum[];                           // [c][2]
+    const int n = blockIdx.y;
+    const int lanes = c / VEC;                                // threads per voxel
+    const int tpb = (256 / lanes) * lanes;                    // active threads
+    for (int i = threadIdx.x; i < 2 * c; i += 256) ssum[i] = 0.f;
+    __syncthreads();
+    if ((int)threadIdx.x < tpb) {
+        const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
+        const int vpb = tpb / lanes;                          // voxels per block-iteration
+        const int c0 = cl * VEC;
+        float mean[VEC], rstd[VEC], sg[VEC], sgx[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            mean[j] = mr[((size_t)n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)n * c + c0 + j) * 2 + 1];
+            sg[j] = 0.f; sgx[j] = 0.f;
+        }
+        const T* dn = dout + (size_t)n * voxels * c;
+        const T* yn = y + (size_t)n * voxels * c;
+        for (long long v = (long long)blockIdx.x * vpb + vl; v < voxels; v += (long long)gridDim.x * vpb) {
+            float g[VEC], yv[VEC];
+            VecIO<T, VEC>::load(dn + v * c + c0, g);
+            VecIO<T, VEC>::load(yn + v * c + c0, yv);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float xh = (yv[j] - mean[j]) * rstd[j];
+                float gg = xh > 0.f ? g[j] : g[j] * slope;
+                sg[j] += gg; sgx[j] += gg * xh;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { atomicAdd(&ssum[2 * (c0 + j)], sg[j]); atomicAdd(&ssum[2 * (c0 + j) + 1], sgx[j]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * c; i += 256) atomicAdd(&sums[(size_t)n * c * 2 + i], (double)ssum[i]);
+}
+
+// dy = rstd * (g - mean(g) - xhat * mean(g*xhat))
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y,
+                                                        const float* __restrict__ mr, const double* __restrict__ sums,
+                                                        T* __restrict__ dy, long long total_vec, long long vox_c, int c,
+                                                        float inv_v, float slope) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * VEC;
+        const int n = (int)(e / vox_c);
+        const int c0 = (int)(e % c);
+        float g[VEC], yv[VEC];
+        VecIO<T, VEC>::load(dout + e, g);
+        VecIO<T, VEC>::load(y + e, yv);
+        const float* m = mr + ((size_t)n * c + c0) * 2;
+        const double* s = sums + ((size_t)n * c + c0) * 2;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const float rstd = m[2 * j + 1];
+            float xh = (yv[j] - m[2 * j]) * rstd;
+            float gg = xh > 0.f ? g[j] : g[j] * slope;
+            g[j] = rstd * (gg - (float)s[2 * j] * inv_v - xh * ((float)s[2 * j + 1] * inv_v));
+        }
+        VecIO<T, VEC>::store(dy + e, g);
+    }
+}
+
+int grid_for(long long work, int per_block) {
+    long long b = (work + per_block - 1) / per_block;
+    const long long cap = 148LL * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <typename T, int VEC>
+int run_fwd(const void* y, const float* mr, const void* res, void* out, int n, long long voxels, int c, float slope, cudaStream_t st) {
+    const long long total_vec = (long long)n * voxels * c / VEC;
+    apply_fwd_kernel<T, VEC><<<grid_for(total_vec, 256), 256, 0, st>>>((const T*)y, mr, (const T*)res, (T*)out, total_vec,
+                                                                       voxels * c, c, slope);
+    return 0;
+}
+
+template <typename T, int VEC>
+int run_bwd(const void* dout, const void* y, const float* mr, double* sums, void* dy, int n, long long voxels, int c, float slope,
+            cudaStream_t st) {
+    const int lanes = c / VEC;
+    const int vpb = 256 / lanes;
+    int bps = (int)((voxels + (long long)vpb * 8 - 1) / ((long long)vpb * 8));   // >= 8 voxel-iterations per thread
+    const int cap = (148 * 8 + n - 1) / n;
+    if (bps > cap) bps = cap;
+    if (bps < 1) bps = 1;
+    bwd_reduce_kernel<T, VEC><<<dim3(bps, n), 256, 2 * c * sizeof(float), st>>>((const T*)dout, (const T*)y, mr, sums, voxels, c, slope);
+    pb_count_launch();
+    const long long total_vec = (long long)n * voxels * c / VEC;
+    bwd_apply_kernel<T, VEC><<<grid_for(total_vec, 256), 256, 0, st>>>((const T*)dout, (const T*)y, mr, sums, (T*)dy, total_vec,
+                                                                       voxels * c, c, 1.0f / (float)voxels, slope);
+    return 0;
+}
+
+#define VEC_SWITCH(T, c, CALL)                                   \
+    switch (pb_vec_width(c)) {                                   \
+        case 8: CALL(T, 8); break;                               \
+        case 4: CALL(T, 4); break;                               \
+        case 2: CALL(T, 2); break;                               \
+        default: CALL(T, 1); break;                              \
+    }
+
+}  // namespace
+
+extern "C" int pb_inorm_finalize(const double* stats, float* mr, int n, int c, long long voxels, float eps, pb_stream_t stream) {
+    PB_CHECK_ARG(stats && mr && n > 0 && c > 0 && voxels > 0, "bad argument");
+    const int nc = n * c;
+    finalize_kernel<<<(nc + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, mr, nc, 1.0 / (double)voxels, eps);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_inorm_lrelu_fwd(int dtype, const void* y, const float* mr, const void* res, void* out, int n,
+                                  long long voxels, int c, float slope, pb_stream_t stream) {
+    PB_CHECK_ARG(y && mr && out && n > 0 && c > 0 && voxels > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL_F(T, V) run_fwd<T, V>(y, mr, res, out, n, voxels, c, slope, st)
+    if (dtype == PB_BF16) { VEC_SWITCH(bf16, c, CALL_F) } else { VEC_SWITCH(float, c, CALL_F) }
+#undef CALL_F
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_inorm_lrelu_bwd(int dtype, const void* dout, const void* y, const float* mr, double* sums, void* dy, int n,
+                                  long long voxels, int c, float slope, pb_stream_t stream) {
+    PB_CHECK_ARG(dout && y && mr && sums && dy && n > 0 && c > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(c <= 256 * pb_vec_width(c), "too many channels");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL_B(T, V) run_bwd<T, V>(dout, y, mr, sums, dy, n, voxels, c, slope, st)
+    if (dtype == PB_BF16) { VEC_SWITCH(bf16, c, CALL_B) } else { VEC_SWITCH(float, c, CALL_B) }
+#undef CALL_B
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

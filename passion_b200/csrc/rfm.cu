@@ -1,0 +1,239 @@
+// Region-aware modal fusion, the part that is not a convolution:
+//   pooled region statistics, gated modality mixing, and their adjoints.
+// Replaces reference models/blocks.py:504-517 (modal_fusion.forward) and :597-616
+// (region_aware_modal_fusion.forward) without materialising the [B,K,cls,C,D,H,W]
+// broadcast product: with y[k] the (masked) modality features and p_i the class probabilities,
+//     feat_avg_i[k,c] = mean_v(y[k,c] p_i) / (mean_v p_i + 1e-7)        -> pb_rfm_pool (the two sums)
+//     region_i[c]     = p_i * sum_k gate_i[k] y[k,c]                     -> pb_rfm_mix
+// The 4C+1 -> 128 -> 4 gate MLP on the pooled vector is host-side glue on a [B, 4C+1] tensor.
+#include "common.cuh"
+
+namespace {
+
+// S[n][i][kc] += sum_v y[kc] p_i ; Psum[n][i] += sum_v p_i.   grid = (blocks_per_sample, n)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ y, const float* __restrict__ p, double* __restrict__ S,
+                                                   double* __restrict__ Psum, long long voxels, int kc) {
+    extern __shared__ float ssum[];                           // [4][kc] + [4]
+    const int n = blockIdx.y;
+    const int lanes = kc / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
+    for (int i = threadIdx.x; i < 4 * kc + 4; i += 256) ssum[i] = 0.f;
+    __syncthreads();
+    if ((int)threadIdx.x < tpb) {
+        const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes, c0 = cl * VEC;
+        float acc[4][VEC], pacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[i][j] = 0.f;
+        const T* yn = y + (size_t)n * voxels * kc + c0;
+        const float4* pn = reinterpret_cast<const float4*>(p) + (size_t)n * voxels;
+        for (long long v = (long long)blockIdx.x * vpb + vl; v < voxels; v += (long long)gridDim.x * vpb) {
+            float yv[VEC];
+            VecIO<T, VEC>::load(yn + v * kc, yv);
+            const float4 pv = __ldg(pn + v);
+            const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                pacc[i] += pp[i];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(yv[j], pp[i], acc[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) atomicAdd(&ssum[i * kc + c0 + j], acc[i][j]);
+            if (cl == 0) atomicAdd(&ssum[4 * kc + i], pacc[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * kc; i += 256) atomicAdd(&S[(size_t)n * 4 * kc + i], (double)ssum[i]);
+    if (threadIdx.x < 4) atomicAdd(&Psum[(size_t)n * 4 + threadIdx.x], (double)ssum[4 * kc + threadIdx.x]);
+}
+
+// R[n][v][i*C+c] = p_i * sum_k gate[n][i][k] y[n][v][k*C+c]   (K = 4 modalities, 4 classes)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ y, const float* __restrict__ p, const float* __restrict__ gate,
+                                                  T* __restrict__ r, long long voxels, int c, long long total) {
+    const int cv = c / VEC;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cl = (int)(t % cv);
+        const long long nv = t / cv;                          // n*voxels + v
+        const int n = (int)(nv / voxels);
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(p) + nv);
+        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+        const float* g = gate + (size_t)n * 16;
+        float yv[4][VEC];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) VecIO<T, VEC>::load(y + nv * 4 * c + k * c + cl * VEC, yv[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float o[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s = fmaf(__ldg(g + i * 4 + k), yv[k][j], s);
+                o[j] = s * pp[i];
+            }
+            VecIO<T, VEC>::store(r + nv * 4 * c + i * c + cl * VEC, o);
+        }
+    }
+}
+
+// dgate[n][i][k] += sum_{v,c} p_i y[k*C+c] dR[i*C+c].   grid = (blocks_per_sample, n)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) mix_bwd_gate_kernel(const T* __restrict__ y, const float* __restrict__ p, const T* __restrict__ dr,
+                                                           double* __restrict__ dgate, long long voxels, int c) {
+    __shared__ float red[8][16];
+    const int n = blockIdx.y, cv = c / VEC;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const long long total = voxels * cv;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+        const int cl = (int)(t % cv);
+        const long long nv = (size_t)n * voxels + t / cv;
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(p) + nv);
+        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+        float yv[4][VEC];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) VecIO<T, VEC>::load(y + nv * 4 * c + k * c + cl * VEC, yv[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float g[VEC];
+            VecIO<T, VEC>::load(dr + nv * 4 * c + i * c + cl * VEC, g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) s = fmaf(yv[k][j], g[j], s);
+                acc[i * 4 + k] = fmaf(s, pp[i], acc[i * 4 + k]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float s = warp_sum(acc[i]);
+        if (lane == 0) red[wid][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float s = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
+        atomicAdd(&dgate[(size_t)n * 16 + threadIdx.x], (double)s);
+    }
+}
+
+// dy[n][v][k*C+c] = sum_i p_i (gate[n][i][k] dR[n][v][i*C+c] + dS[n][i][k*C+c]).  grid = (blocks_per_sample, n)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bwd_y_kernel(const float* __restrict__ p, const float* __restrict__ gate, const T* __restrict__ dr,
+                                                    const float* __restrict__ dS, T* __restrict__ dy, long long voxels, int c) {
+    extern __shared__ __align__(16) float sds[];              // dS[n] : [4][4*c], then gate[16]
+    const int n = blockIdx.y, cv = c / VEC, kc = 4 * c;
+    for (int i = threadIdx.x; i < 4 * kc; i += 256) sds[i] = dS[(size_t)n * 4 * kc + i];
+    float* sg = sds + 4 * kc;
+    if (threadIdx.x < 16) sg[threadIdx.x] = gate[(size_t)n * 16 + threadIdx.x];
+    __syncthreads();
+    const long long total = voxels * cv;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+        const int cl = (int)(t % cv);
+        const long long nv = (size_t)n * voxels + t / cv;
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(p) + nv);
+        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+        float g[4][VEC];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) VecIO<T, VEC>::load(dr + nv * kc + i * c + cl * VEC, g[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float o[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s = fmaf(pp[i], fmaf(sg[i * 4 + k], g[i][j], sds[i * kc + k * c + cl * VEC + j]), s);
+                o[j] = s;
+            }
+            VecIO<T, VEC>::store(dy + nv * kc + k * c + cl * VEC, o);
+        }
+    }
+}
+
+int blocks_per_sample(long long work_items, int n) {
+    long long b = (work_items + 256 * 4 - 1) / (256 * 4);
+    const long long cap = (148LL * 8 + n - 1) / n;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+#define RFM_DISPATCH(c_expr, ...)                                                        \
+    do {                                                                                  \
+        const int vw_ = pb_vec_width(c_expr);                                             \
+        if (dtype == PB_BF16) {                                                           \
+            typedef bf16 T;                                                               \
+            if (vw_ == 8) { constexpr int VEC = 8; __VA_ARGS__ } else if (vw_ == 4) { constexpr int VEC = 4; __VA_ARGS__ } \
+            else if (vw_ == 2) { constexpr int VEC = 2; __VA_ARGS__ } else { constexpr int VEC = 1; __VA_ARGS__ }          \
+        } else {                                                                          \
+            typedef float T;                                                              \
+            if (vw_ == 8) { constexpr int VEC = 8; __VA_ARGS__ } else if (vw_ == 4) { constexpr int VEC = 4; __VA_ARGS__ } \
+            else if (vw_ == 2) { constexpr int VEC = 2; __VA_ARGS__ } else { constexpr int VEC = 1; __VA_ARGS__ }          \
+        }                                                                                 \
+    } while (0)
+
+extern "C" int pb_rfm_pool(int dtype, const void* y, const float* p, double* S, double* Psum, int n, long long voxels, int kc,
+                           pb_stream_t stream) {
+    PB_CHECK_ARG(y && p && S && Psum && n > 0 && voxels > 0 && kc > 0, "bad argument");
+    PB_CHECK_ARG(kc / pb_vec_width(kc) <= 256, "too many channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    RFM_DISPATCH(kc, {
+        const int lanes = kc / VEC, vpb = 256 / lanes;
+        int bps = blocks_per_sample(voxels * lanes / 2, n);
+        if ((long long)bps * vpb > voxels) bps = (int)((voxels + vpb - 1) / vpb);
+        pool_kernel<T, VEC><<<dim3(bps, n), 256, (4 * kc + 4) * sizeof(float), st>>>((const T*)y, p, S, Psum, voxels, kc);
+    });
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_rfm_mix(int dtype, const void* y, const float* p, const float* gate, void* r, int n, long long voxels, int k,
+                          int c, pb_stream_t stream) {
+    PB_CHECK_ARG(y && p && gate && r && n > 0 && voxels > 0 && k == 4 && c > 0, "bad argument (k must be 4)");
+    cudaStream_t st = (cudaStream_t)stream;
+    RFM_DISPATCH(c, {
+        const long long total = (long long)n * voxels * (c / VEC);
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 16) blocks = 148LL * 16;
+        mix_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)y, p, gate, (T*)r, voxels, c, total);
+    });
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_rfm_mix_bwd_gate(int dtype, const void* y, const float* p, const void* dr, double* dgate, int n,
+                                   long long voxels, int k, int c, pb_stream_t stream) {
+    PB_CHECK_ARG(y && p && dr && dgate && n > 0 && voxels > 0 && k == 4 && c > 0, "bad argument (k must be 4)");
+    cudaStream_t st = (cudaStream_t)stream;
+    RFM_DISPATCH(c, {
+        const int bps = blocks_per_sample(voxels * (c / VEC), n);
+        mix_bwd_gate_kernel<T, VEC><<<dim3(bps, n), 256, 0, st>>>((const T*)y, p, (const T*)dr, dgate, voxels, c);
+    });
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_rfm_bwd_y(int dtype, const float* p, const float* gate, const void* dr, const float* dS, void* dy, int n,
+                            long long voxels, int k, int c, pb_stream_t stream) {
+    PB_CHECK_ARG(p && gate && dr && dS && dy && n > 0 && voxels > 0 && k == 4 && c > 0, "bad argument (k must be 4)");
+    cudaStream_t st = (cudaStream_t)stream;
+    RFM_DISPATCH(c, {
+        const int bps = blocks_per_sample(voxels * (c / VEC), n);
+        bwd_y_kernel<T, VEC><<<dim3(bps, n), 256, (16 * c + 16) * sizeof(float), st>>>(p, gate, (const T*)dr, dS, (T*)dy, voxels, c);
+    });
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

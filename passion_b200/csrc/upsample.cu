@@ -1,0 +1,145 @@
+// Trilinear up-sampling with align_corners=True and an integer scale factor, NDHWC, fwd + exact adjoint.
+// Replaces nn.Upsample(scale_factor=s, mode='trilinear', align_corners=True)
+// (reference models/rfnet.py:54,59,64,110-112).  Index arithmetic mirrors ATen's
+// area_pixel_compute_source_index for align_corners: src = dst * (in-1)/(out-1) in float.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void src_index(int o, float ratio, int in, int& i0, int& i1, float& l1) {
+    const float s = ratio * (float)o;
+    i0 = (int)s;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) up_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int d, int h, int w, int c,
+                                                     int scale, float rd, float rh, float rw, long long total_vec) {
+    const int od_n = d * scale, oh_n = h * scale, ow_n = w * scale, cv = c / VEC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int cl = (int)(t % cv); t /= cv;
+        const int ow = (int)(t % ow_n); t /= ow_n;
+        const int oh = (int)(t % oh_n); t /= oh_n;
+        const int od = (int)(t % od_n);
+        const int nn = (int)(t / od_n);
+        int d0, d1, h0, h1, w0, w1; float ld, lh, lw;
+        src_index(od, rd, d, d0, d1, ld); src_index(oh, rh, h, h0, h1, lh); src_index(ow, rw, w, w0, w1, lw);
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        const T* xb = x + (size_t)nn * d * h * w * c + cl * VEC;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float wt = (a ? ld : 1.f - ld) * (b ? lh : 1.f - lh) * (e ? lw : 1.f - lw);
+                    float v[VEC];
+                    VecIO<T, VEC>::load(xb + ((((size_t)(a ? d1 : d0)) * h + (b ? h1 : h0)) * w + (e ? w1 : w0)) * c, v);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
+                }
+        VecIO<T, VEC>::store(y + i * VEC, acc);
+    }
+}
+
+// weight with which output index o reads input index i along one axis (0 if it does not)
+__device__ __forceinline__ float axis_weight(int o, int i, float ratio, int in) {
+    int i0, i1; float l1;
+    src_index(o, ratio, in, i0, i1, l1);
+    float wgt = 0.f;
+    if (i0 == i) wgt += 1.f - l1;
+    if (i1 == i) wgt += l1;
+    return wgt;
+}
+
+// gather form of the adjoint: dx[i] = sum_o w(o,i) dy[o]; candidates o in [(i-1)/ratio, (i+1)/ratio]
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) up_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int d, int h, int w, int c,
+                                                     int scale, float rd, float rh, float rw, long long total_vec) {
+    const int od_n = d * scale, oh_n = h * scale, ow_n = w * scale, cv = c / VEC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int cl = (int)(t % cv); t /= cv;
+        const int iw = (int)(t % w); t /= w;
+        const int ih = (int)(t % h); t /= h;
+        const int id = (int)(t % d);
+        const int nn = (int)(t / d);
+        // candidate ranges (one extra on each side guards float rounding; axis_weight rejects non-contributors)
+        int od_lo = 0, od_hi = od_n - 1, oh_lo = 0, oh_hi = oh_n - 1, ow_lo = 0, ow_hi = ow_n - 1;
+        if (rd > 0.f) { od_lo = max(0, (int)floorf((id - 1) / rd) - 1); od_hi = min(od_n - 1, (int)ceilf((id + 1) / rd) + 1); }
+        if (rh > 0.f) { oh_lo = max(0, (int)floorf((ih - 1) / rh) - 1); oh_hi = min(oh_n - 1, (int)ceilf((ih + 1) / rh) + 1); }
+        if (rw > 0.f) { ow_lo = max(0, (int)floorf((iw - 1) / rw) - 1); ow_hi = min(ow_n - 1, (int)ceilf((iw + 1) / rw) + 1); }
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        const T* gb = dy + (size_t)nn * od_n * oh_n * ow_n * c + cl * VEC;
+        for (int od = od_lo; od <= od_hi; ++od) {
+            const float wd = axis_weight(od, id, rd, d);
+            if (wd == 0.f) continue;
+            for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+                const float wh = axis_weight(oh, ih, rh, h);
+                if (wh == 0.f) continue;
+                for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+                    const float ww = axis_weight(ow, iw, rw, w);
+                    if (ww == 0.f) continue;
+                    float v[VEC];
+                    VecIO<T, VEC>::load(gb + (((size_t)od * oh_n + oh) * ow_n + ow) * c, v);
+                    const float wt = wd * wh * ww;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
+                }
+            }
+        }
+        VecIO<T, VEC>::store(dx + i * VEC, acc);
+    }
+}
+
+template <typename T, int VEC, bool FWD>
+int run(const void* a, void* b, int n, int d, int h, int w, int c, int scale, cudaStream_t st) {
+    const float rd = d * scale > 1 ? (float)(d - 1) / (float)(d * scale - 1) : 0.f;
+    const float rh = h * scale > 1 ? (float)(h - 1) / (float)(h * scale - 1) : 0.f;
+    const float rw = w * scale > 1 ? (float)(w - 1) / (float)(w * scale - 1) : 0.f;
+    const long long vox = FWD ? (long long)d * h * w * scale * scale * scale : (long long)d * h * w;
+    const long long total_vec = (long long)n * vox * c / VEC;
+    long long blocks = (total_vec + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks < 1) blocks = 1;
+    if (FWD) up_fwd_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)b, n, d, h, w, c, scale, rd, rh, rw, total_vec);
+    else     up_bwd_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)b, n, d, h, w, c, scale, rd, rh, rw, total_vec);
+    return 0;
+}
+
+template <bool FWD>
+int dispatch(int dtype, const void* a, void* b, int n, int d, int h, int w, int c, int scale, cudaStream_t st) {
+    const int v = pb_vec_width(c);
+#define UP_CASE(T)                                                     \
+    switch (v) {                                                       \
+        case 8: return run<T, 8, FWD>(a, b, n, d, h, w, c, scale, st); \
+        case 4: return run<T, 4, FWD>(a, b, n, d, h, w, c, scale, st); \
+        case 2: return run<T, 2, FWD>(a, b, n, d, h, w, c, scale, st); \
+        default: return run<T, 1, FWD>(a, b, n, d, h, w, c, scale, st); \
+    }
+    if (dtype == PB_BF16) { UP_CASE(bf16) } else { UP_CASE(float) }
+#undef UP_CASE
+}
+
+}  // namespace
+
+extern "C" int pb_upsample_fwd(int dtype, const void* x, void* y, int n, int d, int h, int w, int c, int scale, pb_stream_t stream) {
+    PB_CHECK_ARG(x && y && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && scale >= 1, "bad argument");
+    dispatch<true>(dtype, x, y, n, d, h, w, c, scale, (cudaStream_t)stream);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_upsample_bwd(int dtype, const void* dy, void* dx, int n, int d, int h, int w, int c, int scale, pb_stream_t stream) {
+    PB_CHECK_ARG(dy && dx && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && scale >= 1, "bad argument");
+    dispatch<false>(dtype, dy, dx, n, d, h, w, c, scale, (cudaStream_t)stream);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

@@ -1,0 +1,384 @@
+"""RFNet backbone + in-forward PASSION loss assembly on the passion_b200 CUDA kernels.
+
+Drop-in for the reference `models/rfnet.py`: same constructor, same attributes poked from the
+training script (`is_training`, `use_passion`, `mask_type`; train.py:91-92,212), same
+`forward(x, mask, target=None, temp=1.0)` and return tuples (rfnet.py:379, :402, :403), same
+state_dict names and shapes, so reference checkpoints load both ways.
+
+What is different underneath (B200-first):
+  * activations are channels-last [N,D,H,W,C] in `compute_dtype` (bf16 by default, fp32 = check mode);
+  * the four modality encoders (rfnet.py:234-237) run as ONE grouped launch per layer (4 weight groups);
+  * the five decoder_fuse passes (full mask + four single-modality masks, rfnet.py:244,269-275) share
+    weights and only use per-sample statistics, so they run as ONE pass at batch 5B; likewise the four
+    decoder_sep passes (rfnet.py:254-257) run at batch 4B;
+  * torch.cat feeding a conv is never materialised (two-source conv kernel), conv biases that feed an
+    InstanceNorm are dropped (they cancel exactly), missing-modality masking is a per-(sample, modality)
+    scale;
+  * the class-presence gate of the prototype loss (criterions.py:157) is evaluated on the device, so
+    the whole step is free of host synchronisation and CUDA-graph capturable.
+The nn.Conv3d / nn.Sequential objects below are parameter containers only (names, shapes, init);
+their torch forward is never called.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import criterions as crit
+from .. import ops
+
+basic_dims = 8
+num_modals = 4
+
+
+class general_conv3d(nn.Module):
+    """Parameter container for reference blocks.py:354-370 (conv -> InstanceNorm -> LeakyReLU)."""
+
+    def __init__(self, in_ch, out_ch, k_size=3, stride=1, padding=1, pad_type='reflect'):
+        super().__init__()
+        self.conv = nn.Conv3d(in_ch, out_ch, kernel_size=k_size, stride=stride, padding=padding,
+                              padding_mode=pad_type, bias=True)
+        self.k_size, self.stride, self.pad_type = k_size, stride, pad_type
+
+    def kernel_weight(self):
+        return ops.kernel_layout(self.conv.weight)[None]           # [1, taps, cin, cout]
+
+    def run(self, x0, x1=None, res=None):
+        y = ops.conv_in_lrelu(x0, self.kernel_weight(), x1=x1, ksize=self.k_size, stride=self.stride,
+                              pad_mode=self.pad_type, res=res)
+        # the bias cancels in InstanceNorm: give it an exact-zero gradient (keeps optimizer state shape)
+        return _ZeroGradTouch.apply(y, self.conv.bias)
+
+
+class _ZeroGradTouch(torch.autograd.Function):
+    """Identity on `y` that reports an all-zero gradient for `b` (a parameter with no influence on y)."""
+
+    @staticmethod
+    def forward(ctx, y, b):
+        ctx.shape, ctx.meta = b.shape, (b.dtype, b.device)
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, torch.zeros(ctx.shape, dtype=ctx.meta[0], device=ctx.meta[1])
+
+
+def _plain_conv1(conv, x):
+    """plain nn.Conv3d 1x1x1 head with bias (rfnet.py:69,107; blocks.py:407,455) -> logits."""
+    w = ops.kernel_layout(conv.weight)[None]
+    y, _ = ops.conv3d(x, w, conv.bias[None].contiguous(), ksize=1, pad_mode="zeros")
+    return y
+
+
+class Encoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        b = basic_dims
+        cin = 1
+        for lvl in (1, 2, 3, 4):
+            c = b * 2 ** (lvl - 1)
+            setattr(self, f"e{lvl}_c1", general_conv3d(cin, c, stride=1 if lvl == 1 else 2))
+            setattr(self, f"e{lvl}_c2", general_conv3d(c, c))
+            setattr(self, f"e{lvl}_c3", general_conv3d(c, c))
+            cin = c
+
+
+def _run_encoders(encoders, x):
+    """Four Encoders (rfnet.py:36-48) as one grouped pass.  x [4B,D,H,W,1] ordered modality-major."""
+    feats = []
+    for lvl in (1, 2, 3, 4):
+        def gw(name):
+            return torch.stack([ops.kernel_layout(getattr(e, name).conv.weight) for e in encoders])
+        stride = 1 if lvl == 1 else 2
+        x = ops.conv_in_lrelu(x, gw(f"e{lvl}_c1"), stride=stride, groups=4)
+        t = ops.conv_in_lrelu(x, gw(f"e{lvl}_c2"), groups=4)
+        x = ops.conv_in_lrelu(t, gw(f"e{lvl}_c3"), groups=4, res=x)       # x + c3(c2(x))
+        for e in encoders:                                                 # zero grads for the cancelled biases
+            for nm in ("c1", "c2", "c3"):
+                x = _ZeroGradTouch.apply(x, getattr(e, f"e{lvl}_{nm}").conv.bias)
+        feats.append(x)
+    return feats
+
+
+class _DecoderConvs(nn.Module):
+    def __init__(self, num_cls):
+        super().__init__()
+        b = basic_dims
+        for lvl, c in ((3, b * 4), (2, b * 2), (1, b)):
+            setattr(self, f"d{lvl}_c1", general_conv3d(c * 2, c))
+            setattr(self, f"d{lvl}_c2", general_conv3d(c * 2, c))
+            setattr(self, f"d{lvl}_out", general_conv3d(c, c, k_size=1, padding=0))
+        self.seg_layer = nn.Conv3d(b, num_cls, kernel_size=1, stride=1, padding=0, bias=True)
+
+
+class Decoder_sep(_DecoderConvs):
+    """rfnet.py:50-89.  Returns LOGITS (cl); the caller applies the softmax."""
+
+    def run(self, x1, x2, x3, x4):
+        de = self.d3_c1.run(ops.upsample(x4))
+        de = self.d3_out.run(self.d3_c2.run(de, x3))
+        de = self.d2_c1.run(ops.upsample(de))
+        de = self.d2_out.run(self.d2_c2.run(de, x2))
+        de = self.d1_c1.run(ops.upsample(de))
+        de = self.d1_out.run(self.d1_c2.run(de, x1))
+        return _plain_conv1(self.seg_layer, de)
+
+
+class modal_fusion(nn.Module):
+    """Parameter container for blocks.py:495-503."""
+
+    def __init__(self, in_channel):
+        super().__init__()
+        self.weight_layer = nn.Sequential(nn.Conv3d(4 * in_channel + 1, 128, 1, padding=0, bias=True),
+                                          nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                          nn.Conv3d(128, 4, 1, padding=0, bias=True))
+
+
+class region_fusion(nn.Module):
+    def __init__(self, in_channel, num_cls):
+        super().__init__()
+        self.fusion_layer = nn.Sequential(general_conv3d(in_channel * num_cls, in_channel, k_size=1, padding=0),
+                                          general_conv3d(in_channel, in_channel, k_size=3, padding=1),
+                                          general_conv3d(in_channel, in_channel // 2, k_size=1, padding=0))
+
+
+def _run_seq(seq, x):
+    for m in seq:
+        x = m.run(x)
+    return x
+
+
+class region_aware_modal_fusion(nn.Module):
+    """blocks.py:582-626."""
+
+    def __init__(self, in_channel, num_cls=4):
+        super().__init__()
+        self.modal_fusion = nn.ModuleList([modal_fusion(in_channel) for _ in range(num_cls)])
+        self.region_fusion = region_fusion(in_channel, num_cls)
+        self.short_cut = nn.Sequential(general_conv3d(in_channel * 4, in_channel, k_size=1, padding=0),
+                                       general_conv3d(in_channel, in_channel, k_size=3, padding=1),
+                                       general_conv3d(in_channel, in_channel // 2, k_size=1, padding=0))
+
+    def run(self, y, prm):
+        """y [N,D,H,W,4C] masked features (channel = modality*C + c); prm [N,D,H,W,4] fp32 detached probs."""
+        mf = self.modal_fusion
+        w0 = torch.stack([m.weight_layer[0].weight.flatten(1) for m in mf])     # [4,128,4C+1]
+        b0 = torch.stack([m.weight_layer[0].bias for m in mf])
+        w2 = torch.stack([m.weight_layer[2].weight.flatten(1) for m in mf])     # [4,4,128]
+        b2 = torch.stack([m.weight_layer[2].bias for m in mf])
+        region = ops.rfm_region(y, prm, w0, b0, w2, b2)
+        r = _run_seq(self.region_fusion.fusion_layer, region)
+        s = _run_seq(self.short_cut, y)
+        return torch.cat((r, s), -1)
+
+
+class prm_generator_pk(nn.Module):
+    """blocks.py:396-416 (laststage: no upper feature) and :443-464."""
+
+    def __init__(self, in_channel, num_cls=4, laststage=False):
+        super().__init__()
+        q = in_channel // 4
+        self.embedding_layer = nn.Sequential(general_conv3d(in_channel * 4, q, k_size=1, padding=0),
+                                             general_conv3d(q, q, k_size=3, padding=1),
+                                             general_conv3d(q, in_channel, k_size=1, padding=0))
+        self.prm_layer = nn.Sequential(general_conv3d(in_channel if laststage else in_channel * 2, 16, k_size=1, padding=0),
+                                       nn.Conv3d(16, num_cls, kernel_size=1, padding=0, stride=1, bias=True))
+
+    def run(self, y, upper=None):
+        e = _run_seq(self.embedding_layer, y)
+        h = self.prm_layer[0].run(e) if upper is None else self.prm_layer[0].run(upper, e)   # cat((x1, emb))
+        return _plain_conv1(self.prm_layer[1], h)
+
+
+class Decoder_fuse(_DecoderConvs):
+    """rfnet.py:91-152, batched over decoder passes."""
+
+    def __init__(self, num_cls=4):
+        super().__init__(num_cls)
+        b = basic_dims
+        self.RFM4 = region_aware_modal_fusion(b * 8, num_cls)
+        self.RFM3 = region_aware_modal_fusion(b * 4, num_cls)
+        self.RFM2 = region_aware_modal_fusion(b * 2, num_cls)
+        self.RFM1 = region_aware_modal_fusion(b * 1, num_cls)
+        self.prm_generator4 = prm_generator_pk(b * 8, num_cls, laststage=True)
+        self.prm_generator3 = prm_generator_pk(b * 4, num_cls)
+        self.prm_generator2 = prm_generator_pk(b * 2, num_cls)
+        self.prm_generator1 = prm_generator_pk(b * 1, num_cls)
+
+    @staticmethod
+    def _probs(logits):
+        return torch.softmax(logits.float(), -1).detach()
+
+    def run(self, y1, y2, y3, y4):
+        """y_l [N,D_l,H_l,W_l,4*C_l] masked encoder features.  Returns logits, (prm1..4), (de1..4), all cl."""
+        prm4 = self.prm_generator4.run(y4)
+        de4 = self.RFM4.run(y4, self._probs(prm4))
+        de4 = self.d3_c1.run(ops.upsample(de4))
+
+        prm3 = self.prm_generator3.run(y3, de4)
+        de3 = self.RFM3.run(y3, self._probs(prm3))
+        de3 = self.d3_out.run(self.d3_c2.run(de3, de4))
+        de3 = self.d2_c1.run(ops.upsample(de3))
+
+        prm2 = self.prm_generator2.run(y2, de3)
+        de2 = self.RFM2.run(y2, self._probs(prm2))
+        de2 = self.d2_out.run(self.d2_c2.run(de2, de3))
+        de2 = self.d1_c1.run(ops.upsample(de2))
+
+        prm1 = self.prm_generator1.run(y1, de2)
+        de1 = self.RFM1.run(y1, self._probs(prm1))
+        de1 = self.d1_out.run(self.d1_c2.run(de1, de2))
+
+        logits = _plain_conv1(self.seg_layer, de1)
+        return logits, (prm1, prm2, prm3, prm4), (de1, de2, de3, de4)
+
+
+class MaskModal(nn.Module):
+    """kept for state/attribute compatibility (rfnet.py:154-163); masking is a scale in this implementation."""
+
+    def forward(self, x, mask):
+        B, K = x.shape[:2]
+        return (x * mask.to(x.dtype).view(B, K, *([1] * (x.dim() - 2)))).reshape(B, -1, *x.shape[3:])
+
+
+class MaskModal_NoCat(nn.Module):
+    def forward(self, x, mask):
+        B, K = x.shape[:2]
+        return x * mask.to(x.dtype).view(B, K, *([1] * (x.dim() - 2)))
+
+
+UP_SCALES = (1, 2, 4, 8)          # rfnet.py:207-211
+
+
+class Model(nn.Module):
+    def __init__(self, num_cls=4):
+        super().__init__()
+        self.flair_encoder = Encoder()
+        self.t1ce_encoder = Encoder()
+        self.t1_encoder = Encoder()
+        self.t2_encoder = Encoder()
+        self.decoder_fuse = Decoder_fuse(num_cls=num_cls)
+        self.decoder_sep = Decoder_sep(num_cls=num_cls)
+        self.masker = MaskModal()
+        self.masker_nocat = MaskModal_NoCat()
+
+        self.is_training = False
+        self.use_passion = False
+        self.mask_type = 'idt'
+        self.num_cls = num_cls
+        self.compute_dtype = torch.bfloat16          # torch.float32 = check mode
+        self.last = {}                               # prediction tuples of the last forward (parity tests)
+
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                torch.nn.init.kaiming_normal_(m.weight)          # rfnet.py:213-215
+
+    # ------------------------------------------------------------------ feature extraction
+    def _features(self, x, mask):
+        """-> enc (4 levels of [4B,d,h,w,C], modality-major) and stacked [B,d,h,w,4C] per level."""
+        B = x.shape[0]
+        dt = self.compute_dtype
+        idt = self.mask_type != 'pdt'
+        fm = mask.to(torch.float32)
+        xin = x.to(torch.float32).permute(1, 0, 2, 3, 4)                       # [4,B,D,H,W]
+        if idt:
+            xin = xin * fm.t()[:, :, None, None, None]                         # rfnet.py:232-233
+        xe = xin.reshape(4 * B, *x.shape[2:], 1).to(dt).contiguous()
+        encs = (self.flair_encoder, self.t1ce_encoder, self.t1_encoder, self.t2_encoder)
+        enc = _run_encoders(encs, xe)
+        stacked = []
+        for f in enc:
+            _, d, h, w, c = f.shape
+            s = f.view(4, B, d, h, w, c).permute(1, 2, 3, 4, 0, 5)             # [B,d,h,w,4,C]
+            stacked.append(s)
+        return enc, stacked
+
+    @staticmethod
+    def _masked(stacked, ms):
+        """stacked [B,d,h,w,4,C] x pass masks ms [P,B,4] -> [P*B,d,h,w,4C]."""
+        P, B = ms.shape[:2]
+        out = []
+        for s in stacked:
+            _, d, h, w, k, c = s.shape
+            y = s[None] * ms.to(s.dtype).view(P, B, 1, 1, 1, k, 1)
+            out.append(y.reshape(P * B, d, h, w, k * c).contiguous())
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, mask, target=None, temp=1.0):
+        if not x.is_cuda:
+            raise RuntimeError("passion_b200.models.rfnet.Model runs on CUDA only (no CPU fallback)")
+        B = x.shape[0]
+        idt = self.mask_type != 'pdt'
+        enc, stacked = self._features(x, mask)
+        fm = mask.to(torch.float32)
+        train_passion = self.is_training and self.use_passion
+        eye = torch.eye(4, device=x.device, dtype=torch.float32)
+        if train_passion:
+            single = eye[:, None, :].expand(4, B, 4)                           # masks_mod0..3 (rfnet.py:262-265)
+            eff = fm if idt else torch.ones_like(fm)
+            # features are already masked by `mask` in idt mode (rfnet.py:239-242); the single-modality
+            # passes then see mask & masks_mod_m
+            ms = torch.cat((eff[None], single * eff[None]), 0)                 # [5,B,4]
+        else:
+            ms = (fm if idt else torch.ones_like(fm))[None]
+        # pdt: decoder_fuse still masks inside PRM/RFM with the pass mask (blocks.py:409-413,597-600)
+        if not idt:
+            ms = ms.clone()
+            ms[0] = fm
+            if train_passion:
+                ms[1:] = single
+        P = ms.shape[0]
+        ys = self._masked(stacked, ms)
+        logits, prms, des = self.decoder_fuse.run(*ys)
+        D, H, W = logits.shape[1:4]
+        fuse_logits = logits.view(P, B, D, H, W, -1)
+        fuse_prob = torch.softmax(fuse_logits[0].float(), -1).permute(0, 4, 1, 2, 3)   # [B,C,D,H,W]
+        self.last = {"fuse_logits": fuse_logits, "prm_logits": prms, "de_f": des, "passes": P}
+        if not self.is_training:
+            return fuse_prob
+
+        sep_logits = self.decoder_sep.run(*enc)                               # [4B,D,H,W,C], modality-major
+        sep_prob = torch.softmax(sep_logits.float(), -1).view(4, B, D, H, W, -1)
+        e = (fm if idt else torch.ones_like(fm)).t()                          # [4(m),B]
+        if idt:
+            sep_prob = sep_prob * e[:, :, None, None, None, None]             # rfnet.py:259-260
+        self.last["sep_prob"] = sep_prob
+
+        t_cl = target.permute(0, 2, 3, 4, 1).to(torch.float32).contiguous()   # [B,D,H,W,C]
+        cnt, wgt = crit.target_stats(t_cl)
+
+        # ---- prm loss (rfnet.py:284-288): full-mask pass only
+        prm_loss = torch.zeros(B, device=x.device)
+        wl = 1.0
+        for prm, s in zip(prms, UP_SCALES):
+            wl /= 2.0
+            p0 = torch.softmax(prm.view(P, B, *prm.shape[1:])[0].float(), -1)
+            ce, dice = crit.cedice_cl(crit.up_probs(p0, s)[None], t_cl, cnt, wgt)
+            prm_loss = prm_loss + wl * (ce[0] + dice[0])
+        # ---- sep loss (rfnet.py:336 ...)
+        ce, dice = crit.cedice_cl(sep_prob, t_cl, cnt, wgt)                   # [4,B]
+        sep_loss = (e * (ce + dice)).t()                                      # [B,4]
+        if not self.use_passion:
+            return fuse_prob, prm_loss[:, None], sep_loss                     # rfnet.py:402
+
+        # ---- PASSION terms: single-modality passes 1..4 vs the detached full-mask pass 0
+        V = D * H * W
+        ps = torch.softmax(fuse_logits[1:].float() / temp, -1)
+        pt = torch.softmax(fuse_logits[0].float().detach() / temp, -1)
+        kl = crit.kl_cl(ps, pt, temp)                                          # [4,B]
+        wl = 1.0
+        for prm, s in zip(prms, UP_SCALES):
+            wl /= 2.0
+            pr = prm.view(P, B, *prm.shape[1:]).float()
+            ps_l = torch.softmax(pr[1:] / temp, -1)
+            pt_l = torch.softmax(pr[0].detach() / temp, -1)
+            if s > 1:
+                ps_l = crit.up_probs(ps_l.reshape(4 * B, *ps_l.shape[2:]).contiguous(), s).view(4, B, D, H, W, -1)
+                pt_l = crit.up_probs(pt_l.contiguous(), s)
+            kl = kl + wl * crit.kl_cl(ps_l, pt_l, temp)
+        de1 = des[0].view(P, B, V, -1).float()
+        proto, dist = crit.proto_cl(de1[1:], de1[0].detach(), t_cl.view(B, V, -1), cnt)
+        kl_loss = (e * kl).t()
+        proto_loss = (e * proto).t()
+        dist_out = (e * dist).t()
+        return fuse_prob, prm_loss[:, None], sep_loss, kl_loss, proto_loss, dist_out     # rfnet.py:379

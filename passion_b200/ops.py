@@ -1,0 +1,237 @@
+"""torch.autograd wrappers around the C-ABI kernels (include/passion_b200.h).
+
+All activations are dense channels-last tensors of shape [N, D, H, W, C] ("cl"), dtype float32
+(check mode) or bfloat16.  Every op requires CUDA tensors; there is no eager/CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import PB_BF16, PB_F32, PB_PAD_REFLECT, PB_PAD_ZERO, ConvDesc
+
+LRELU_SLOPE = 0.2     # reference models/blocks.py:355 relufactor
+IN_EPS = 1e-5         # nn.InstanceNorm3d default (models/blocks.py:18)
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return PB_BF16
+    if t.dtype == torch.float32:
+        return PB_F32
+    raise TypeError(f"passion_b200: unsupported dtype {t.dtype}")
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("passion_b200 ops need CUDA tensors (no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("passion_b200 ops need contiguous tensors")
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
+    n, di, hi, wi, c0 = x0.shape
+    pad = ksize // 2
+    osz = lambda i: (i + 2 * pad - ksize) // stride + 1
+    d = ConvDesc(dtype=_dt(x0), n=n, di=di, hi=hi, wi=wi, dout=osz(di), ho=osz(hi), wo=osz(wi), c0=c0,
+                 c1=0 if x1 is None else x1.shape[-1], cout=cout, ksize=ksize, stride=stride,
+                 pad_mode=PB_PAD_REFLECT if pad_mode == "reflect" else PB_PAD_ZERO, groups=groups)
+    return d
+
+
+class _Conv3d(torch.autograd.Function):
+    """y = conv(cat(x0, x1), w) (+ bias); optionally also the per-(n,c) sum / sum-of-squares of y."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, w, bias, ksize, stride, pad_mode, groups, want_stats):
+        lib = _lib.load()
+        _chk(x0, x1, w, bias)
+        assert w.dtype == torch.float32 and w.dim() == 4, "w must be fp32 [groups, taps, cin, cout]"
+        cout = w.shape[-1]
+        d = _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups)
+        assert w.shape == (groups, ksize ** 3, d.c0 + d.c1, cout), (tuple(w.shape), groups, ksize, d.c0, d.c1, cout)
+        y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
+        stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
+        _lib.check(lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(w), _p(bias), _p(y), _p(stats), _stream()),
+                   "conv3d_fwd")
+        ctx.save_for_backward(x0, x1, w)
+        ctx.cfg = (ksize, stride, pad_mode, groups, bias is not None)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        lib = _lib.load()
+        x0, x1, w = ctx.saved_tensors
+        ksize, stride, pad_mode, groups, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        d = _conv_desc(x0, x1, w.shape[-1], ksize, stride, pad_mode, groups)
+        dx0 = dx1 = dw = db = None
+        need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
+        if need_dx:
+            wt = w.transpose(2, 3).contiguous()
+            dx0 = torch.empty_like(x0)
+            dx1 = torch.empty_like(x1) if x1 is not None else None
+            _lib.check(lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()), "conv3d_dgrad")
+        if ctx.needs_input_grad[2]:
+            dw = torch.zeros_like(w)
+            _lib.check(lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()), "conv3d_wgrad")
+        if has_bias and ctx.needs_input_grad[3]:
+            db = dy.float().reshape(groups, -1, dy.shape[-1]).sum(1)
+        return dx0, dx1, dw, db, None, None, None, None, None
+
+
+def conv3d(x0, w, bias=None, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=1, want_stats=False):
+    """w: fp32 kernel layout [groups, ksize^3, cin, cout]; bias: fp32 [groups, cout] or None."""
+    return _Conv3d.apply(x0, x1, w, bias, ksize, stride, pad_mode, groups, want_stats)
+
+
+def kernel_layout(w):
+    """reference Conv3d weight [cout, cin, kd, kh, kw] -> [taps, cin, cout] (differentiable)."""
+    cout, cin = w.shape[:2]
+    return w.permute(2, 3, 4, 1, 0).reshape(-1, cin, cout)
+
+
+def inorm_finalize(stats, voxels, eps=IN_EPS):
+    lib = _lib.load()
+    n, c, _ = stats.shape
+    mr = torch.empty((n, c, 2), dtype=torch.float32, device=stats.device)
+    _lib.check(lib.pb_inorm_finalize(_p(stats), _p(mr), n, c, voxels, eps, _stream()), "inorm_finalize")
+    return mr
+
+
+class _InormLrelu(torch.autograd.Function):
+    """out = LeakyReLU(InstanceNorm(y)) (+ res).  `mr` = (mean, rstd) of y; backward is the full
+    InstanceNorm adjoint (the dependence of the statistics on y is accounted for)."""
+
+    @staticmethod
+    def forward(ctx, y, mr, res):
+        lib = _lib.load()
+        _chk(y, mr, res)
+        n, c = y.shape[0], y.shape[-1]
+        voxels = y.numel() // (n * c)
+        out = torch.empty_like(y)
+        _lib.check(lib.pb_inorm_lrelu_fwd(_dt(y), _p(y), _p(mr), _p(res), _p(out), n, voxels, c, LRELU_SLOPE, _stream()),
+                   "inorm_lrelu_fwd")
+        ctx.save_for_backward(y, mr)
+        ctx.has_res = res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        y, mr = ctx.saved_tensors
+        dout = dout.contiguous()
+        n, c = y.shape[0], y.shape[-1]
+        voxels = y.numel() // (n * c)
+        sums = torch.zeros((n, c, 2), dtype=torch.float64, device=y.device)
+        dy = torch.empty_like(y)
+        _lib.check(lib.pb_inorm_lrelu_bwd(_dt(y), _p(dout), _p(y), _p(mr), _p(sums), _p(dy), n, voxels, c, LRELU_SLOPE,
+                                          _stream()), "inorm_lrelu_bwd")
+        return dy, None, (dout if ctx.has_res else None)
+
+
+def conv_in_lrelu(x0, w, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=1, res=None):
+    """general_conv3d (reference models/blocks.py:354-370): conv -> InstanceNorm -> LeakyReLU(0.2) (+ res).
+    The conv bias is dropped: InstanceNorm(affine=False) cancels it exactly."""
+    y, stats = conv3d(x0, w, None, x1, ksize, stride, pad_mode, groups, True)
+    voxels = y.shape[1] * y.shape[2] * y.shape[3]
+    mr = inorm_finalize(stats, voxels)
+    return _InormLrelu.apply(y, mr, res)
+
+
+class _Upsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        lib = _lib.load()
+        _chk(x)
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, d * scale, h * scale, w * scale, c), dtype=x.dtype, device=x.device)
+        _lib.check(lib.pb_upsample_fwd(_dt(x), _p(x), _p(y), n, d, h, w, c, scale, _stream()), "upsample_fwd")
+        ctx.shape, ctx.scale = (n, d, h, w, c), scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        dy = dy.contiguous()
+        n, d, h, w, c = ctx.shape
+        dx = torch.empty((n, d, h, w, c), dtype=dy.dtype, device=dy.device)
+        _lib.check(lib.pb_upsample_bwd(_dt(dy), _p(dy), _p(dx), n, d, h, w, c, ctx.scale, _stream()), "upsample_bwd")
+        return dx, None
+
+
+def upsample(x, scale=2):
+    """nn.Upsample(scale_factor=scale, mode='trilinear', align_corners=True) on a cl tensor."""
+    return _Upsample.apply(x, scale)
+
+
+def _gate_mlp(S, Psum, voxels, w0, b0, w2, b2):
+    """modal_fusion gate (reference models/blocks.py:507-513) on the pooled statistics.
+    S [N,4,KC] = sum_v y p_i, Psum [N,4] = sum_v p_i  ->  gate [N,4(class),4(modality)]."""
+    prm_avg = Psum / voxels + 1e-7                                  # [N,4]
+    feat = torch.cat((S / voxels / prm_avg[..., None], prm_avg[..., None]), -1)        # [N,4,KC+1]
+    h = torch.nn.functional.leaky_relu(torch.einsum("nif,ihf->nih", feat, w0) + b0, LRELU_SLOPE)
+    return torch.sigmoid(torch.einsum("nih,ikh->nik", h, w2) + b2)
+
+
+class _RfmRegion(torch.autograd.Function):
+    """Region-aware modality mixing: y [N,D,H,W,4C] (masked features, channel = k*C+c), p [N,D,H,W,4] fp32
+    (detached class probabilities) -> R [N,D,H,W,4C] (channel = class*C + c).
+    w0 [4,128,4C+1], b0 [4,128], w2 [4,4,128], b2 [4,4] are the four modal_fusion gate MLPs."""
+
+    @staticmethod
+    def forward(ctx, y, p, w0, b0, w2, b2):
+        lib = _lib.load()
+        _chk(y, p)
+        assert p.dtype == torch.float32 and p.shape[-1] == 4
+        n, kc = y.shape[0], y.shape[-1]
+        c = kc // 4
+        voxels = y.numel() // (n * kc)
+        S = torch.zeros((n, 4, kc), dtype=torch.float64, device=y.device)
+        Ps = torch.zeros((n, 4), dtype=torch.float64, device=y.device)
+        _lib.check(lib.pb_rfm_pool(_dt(y), _p(y), _p(p), _p(S), _p(Ps), n, voxels, kc, _stream()), "rfm_pool")
+        S, Ps = S.float(), Ps.float()
+        gate = _gate_mlp(S, Ps, voxels, w0, b0, w2, b2).contiguous()
+        r = torch.empty_like(y)
+        _lib.check(lib.pb_rfm_mix(_dt(y), _p(y), _p(p), _p(gate), _p(r), n, voxels, 4, c, _stream()), "rfm_mix")
+        ctx.save_for_backward(y, p, S, Ps, gate, w0, b0, w2, b2)
+        return r
+
+    @staticmethod
+    def backward(ctx, dr):
+        lib = _lib.load()
+        y, p, S, Ps, gate, w0, b0, w2, b2 = ctx.saved_tensors
+        dr = dr.contiguous()
+        n, kc = y.shape[0], y.shape[-1]
+        c = kc // 4
+        voxels = y.numel() // (n * kc)
+        dgate = torch.zeros((n, 4, 4), dtype=torch.float64, device=y.device)
+        _lib.check(lib.pb_rfm_mix_bwd_gate(_dt(y), _p(y), _p(p), _p(dr), _p(dgate), n, voxels, 4, c, _stream()),
+                   "rfm_mix_bwd_gate")
+        with torch.enable_grad():                       # tiny [N, 4C+1] MLP: recompute and let autograd transpose it
+            S_ = S.detach().requires_grad_(True)
+            params = [t.detach().requires_grad_(True) for t in (w0, b0, w2, b2)]
+            g = _gate_mlp(S_, Ps, voxels, *params)
+            dS, dw0, db0, dw2, db2 = torch.autograd.grad(g, [S_, *params], dgate.float())
+        dy = torch.empty_like(y)
+        _lib.check(lib.pb_rfm_bwd_y(_dt(y), _p(p), _p(gate), _p(dr), _p(dS.contiguous()), _p(dy), n, voxels, 4, c, _stream()),
+                   "rfm_bwd_y")
+        return dy, None, dw0, db0, dw2, db2
+
+
+def rfm_region(y, p, w0, b0, w2, b2):
+    return _RfmRegion.apply(y, p, w0, b0, w2, b2)

@@ -1,0 +1,187 @@
+"""GPU parity tests of the individual CUDA kernels (through the C ABI / ops.py) against plain PyTorch
+float64 references of the same op.  fp32 storage must agree to ~1e-5, bf16 storage to bf16 rounding."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def to_cl(t):           # NCDHW -> NDHWC contiguous
+    return t.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def to_nc(t):
+    return t.permute(0, 4, 1, 2, 3)
+
+
+TOL = {torch.float32: 2e-5, torch.bfloat16: 8e-3}
+
+CONV_CASES = [
+    # c0, c1, cout, k, stride, pad, groups, n, (d,h,w), bias
+    (1, 0, 8, 3, 1, "reflect", 4, 8, (12, 10, 14), False),
+    (8, 0, 8, 3, 1, "reflect", 1, 2, (10, 12, 9), False),
+    (8, 0, 16, 3, 2, "reflect", 4, 4, (12, 8, 10), False),
+    (16, 16, 8, 3, 1, "reflect", 1, 3, (9, 10, 11), False),
+    (32, 32, 16, 3, 1, "reflect", 1, 2, (6, 5, 7), False),
+    (64, 0, 64, 3, 1, "reflect", 1, 2, (5, 6, 4), False),
+    (64, 64, 32, 3, 1, "reflect", 1, 1, (4, 4, 4), False),
+    (32, 0, 64, 3, 2, "reflect", 2, 2, (4, 6, 4), False),
+    (2, 0, 2, 3, 1, "reflect", 1, 2, (8, 8, 8), False),
+    (4, 0, 4, 3, 1, "reflect", 1, 2, (7, 8, 9), False),
+    (8, 0, 8, 3, 1, "zeros", 1, 2, (6, 7, 8), False),
+    (16, 0, 16, 3, 1, "reflect", 1, 1, (2, 2, 2), False),
+    (32, 0, 2, 1, 1, "zeros", 1, 2, (8, 8, 8), False),
+    (256, 0, 16, 1, 1, "zeros", 1, 2, (3, 4, 5), False),
+    (16, 0, 4, 1, 1, "zeros", 1, 2, (6, 6, 6), True),
+    (8, 8, 16, 1, 1, "zeros", 1, 3, (5, 6, 7), False),
+    (2, 0, 8, 1, 1, "zeros", 1, 2, (6, 6, 6), False),
+    (128, 0, 32, 1, 1, "zeros", 1, 2, (4, 4, 4), False),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "c%d+%d_%d_k%d_s%d_%s_g%d" % c[:7])
+def test_conv3d(lib_built, case, dtype):
+    from passion_b200 import ops
+    c0, c1, cout, k, stride, pad, groups, n, (d, h, w), has_bias = case
+    g = torch.Generator(device="cpu").manual_seed(hash(case[:7]) % 2 ** 31)
+    dev = "cuda"
+    cin = c0 + c1
+    x = torch.randn(n, cin, d, h, w, generator=g).to(dev)
+    wt = (torch.randn(groups, cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5).to(dev)
+    bias = torch.randn(groups, cout, generator=g).to(dev) if has_bias else None
+    xq = x.to(dtype)                                   # the kernel sees dtype-rounded activations
+    # ---- float64 reference on the same (rounded) inputs
+    xr = xq.double().requires_grad_(True)
+    wr = wt.double().requires_grad_(True)
+    ys = []
+    npg = n // groups
+    for gi in range(groups):
+        xi = xr[gi * npg:(gi + 1) * npg]
+        if k == 3:
+            xi = F.pad(xi, (1,) * 6, mode="reflect" if pad == "reflect" else "constant")
+        ys.append(F.conv3d(xi, wr[gi], None if bias is None else bias[gi].double(), stride=stride))
+    yr = torch.cat(ys, 0)
+    gy = torch.randn(yr.shape, generator=g).to(dev).to(dtype)
+    yr.backward(gy.double())
+    # ---- kernel path
+    x_cl = to_cl(xq)
+    x0 = x_cl[..., :c0].contiguous().requires_grad_(True)
+    x1 = x_cl[..., c0:].contiguous().requires_grad_(True) if c1 else None
+    wk = torch.stack([ops.kernel_layout(wt[gi]) for gi in range(groups)]).contiguous().requires_grad_(True)
+    bk = bias.clone().requires_grad_(True) if has_bias else None
+    y, stats = ops.conv3d(x0, wk, bk, x1, ksize=k, stride=stride, pad_mode=pad, groups=groups, want_stats=True)
+    y.backward(to_cl(gy))
+    tol = TOL[dtype]
+    assert rel(to_nc(y), yr) < tol
+    # statistics come from the fp32 accumulators (before storage rounding)
+    assert rel(stats[..., 0], yr.sum((2, 3, 4))) < 1e-4 + (0 if dtype == torch.float32 else 0)
+    assert rel(stats[..., 1], (yr * yr).sum((2, 3, 4))) < 1e-4
+    dxr = to_cl(xr.grad)
+    assert rel(x0.grad, dxr[..., :c0]) < tol
+    if c1:
+        assert rel(x1.grad, dxr[..., c0:]) < tol
+    dwr = torch.stack([ops.kernel_layout(wr.grad[gi]) for gi in range(groups)])
+    assert rel(wk.grad, dwr) < (5e-5 if dtype == torch.float32 else tol)
+    if has_bias:
+        assert rel(bk.grad, gy.double().sum((0, 2, 3, 4))[None]) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,shape,with_res", [(8, (12, 10, 14), True), (16, (6, 7, 8), False), (2, (8, 8, 8), False),
+                                              (4, (5, 5, 5), True), (64, (2, 2, 2), False), (32, (4, 5, 6), True),
+                                              (1, (6, 6, 6), False)])
+def test_inorm_lrelu(lib_built, c, shape, with_res, dtype):
+    from passion_b200 import ops
+    g = torch.Generator().manual_seed(c * 131 + shape[0])
+    n = 3
+    y = (torch.randn(n, c, *shape, generator=g) * 2 + 0.7).cuda().to(dtype)
+    res = torch.randn(n, c, *shape, generator=g).cuda().to(dtype) if with_res else None
+    gy = torch.randn(n, c, *shape, generator=g).cuda().to(dtype)
+    yr = y.double().requires_grad_(True)
+    out_r = F.leaky_relu(F.instance_norm(yr, eps=1e-5), 0.2)
+    if with_res:
+        rr = res.double().requires_grad_(True)
+        out_r = out_r + rr
+    out_r.backward(gy.double())
+    y_cl = to_cl(y).requires_grad_(True)
+    res_cl = to_cl(res).requires_grad_(True) if with_res else None
+    yd = y.double()
+    stats = torch.stack((yd.sum((2, 3, 4)), (yd * yd).sum((2, 3, 4))), -1).contiguous()
+    voxels = shape[0] * shape[1] * shape[2]
+    mr = ops.inorm_finalize(stats, voxels)
+    out = ops._InormLrelu.apply(y_cl, mr, res_cl)
+    out.backward(to_cl(gy))
+    tol = TOL[dtype]
+    assert rel(to_nc(out), out_r) < tol
+    assert rel(to_nc(y_cl.grad), yr.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
+    if with_res:
+        assert rel(to_nc(res_cl.grad), rr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,shape,scale", [(8, (5, 6, 7), 2), (64, (2, 2, 2), 2), (4, (3, 4, 5), 4), (4, (2, 3, 2), 8),
+                                           (16, (10, 10, 10), 2), (2, (4, 4, 4), 2), (32, (5, 5, 5), 2)])
+def test_upsample(lib_built, c, shape, scale, dtype):
+    from passion_b200 import ops
+    g = torch.Generator().manual_seed(c + scale)
+    x = torch.randn(2, c, *shape, generator=g).cuda().to(dtype)
+    xr = x.double().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=scale, mode="trilinear", align_corners=True)
+    gy = torch.randn(yr.shape, generator=g).cuda().to(dtype)
+    yr.backward(gy.double())
+    x_cl = to_cl(x).requires_grad_(True)
+    y = ops.upsample(x_cl, scale)
+    y.backward(to_cl(gy))
+    tol = TOL[dtype]
+    assert rel(to_nc(y), yr) < tol
+    assert rel(to_nc(x_cl.grad), xr.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,shape", [(8, (6, 7, 8)), (16, (4, 5, 6)), (64, (2, 2, 2)), (32, (3, 4, 3))])
+def test_rfm_region(lib_built, c, shape, dtype):
+    from passion_b200 import ops
+    g = torch.Generator().manual_seed(c)
+    n = 3
+    kc = 4 * c
+    y = torch.randn(n, *shape, kc, generator=g).cuda().to(dtype)
+    y[0, ..., c:2 * c] = 0                                            # a missing modality
+    p = torch.softmax(torch.randn(n, *shape, 4, generator=g), -1).cuda()
+    w0 = (torch.randn(4, 128, kc + 1, generator=g) / kc ** 0.5).cuda()
+    b0 = (torch.randn(4, 128, generator=g) * 0.1).cuda()
+    w2 = (torch.randn(4, 4, 128, generator=g) / 128 ** 0.5).cuda()
+    b2 = (torch.randn(4, 4, generator=g) * 0.1).cuda()
+    gr = torch.randn(n, *shape, kc, generator=g).cuda().to(dtype)
+
+    def reference(y, w0, b0, w2, b2):
+        V = shape[0] * shape[1] * shape[2]
+        yv = y.reshape(n, V, 4, c)
+        pv = p.double().reshape(n, V, 4)
+        outs = []
+        for i in range(4):
+            yp = yv * pv[:, :, i, None, None]                         # [n,V,4,c]
+            prm_avg = pv[:, :, i].mean(1) + 1e-7
+            feat = torch.cat(((yp.mean(1) / prm_avg[:, None, None]).reshape(n, kc), prm_avg[:, None]), 1)
+            hdn = F.leaky_relu(feat @ w0[i].t() + b0[i], 0.2)
+            gate = torch.sigmoid(hdn @ w2[i].t() + b2[i])             # [n,4]
+            outs.append((yp * gate[:, None, :, None]).sum(2))         # [n,V,c]
+        return torch.stack(outs, 2).reshape(n, *shape, kc)
+
+    refs = [t.double().requires_grad_(True) for t in (y, w0, b0, w2, b2)]
+    rr = reference(*refs)
+    rr.backward(gr.double())
+    ins = [y.clone().requires_grad_(True)] + [t.clone().requires_grad_(True) for t in (w0, b0, w2, b2)]
+    r = ops.rfm_region(ins[0], p, *ins[1:])
+    r.backward(gr)
+    tol = TOL[dtype]
+    assert rel(r, rr) < tol
+    assert rel(ins[0].grad, refs[0].grad) < tol
+    for a, b in zip(ins[1:], refs[1:]):
+        assert rel(a.grad, b.grad) < (2e-4 if dtype == torch.float32 else 2e-2)
