@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Throughput bench of the PASSION training hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one forward + PASSION loss + backward + AdamW(amsgrad) update on one synthetic batch of
+BraTS-shaped 4x80^3 crops, B = 2 per GPU (BASELINE.json configs[1]); at N > 1 (torchrun, one rank per GPU,
+NCCL) each rank takes its own B = 2 shard of the global batch (weak scaling, configs[2]).
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same metric
+through the public API with pinned HOST buffers (H2D of x / one-hot target / mask and D2H of the loss inside
+the timed region).  `roofline` is the live CUDA-event measurement of the dominant kernel family.
+`--impl reference` times the reference algorithm's CPU port (oracle/, PyTorch fp32 on the host cores).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train samples/sec (4x80^3 crops, fwd+bwd+PASSION loss+AdamW)"
+S_CROP = 80
+B_PER_GPU = 2
+# algorithmic work per sample (dense as the reference executes it)
+FLOP_PER_SAMPLE = 557.8e9
+BYTES_PER_SAMPLE = 14.7e9
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        import statistics
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            parts = [t.strip() for t in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def mask_ids_for(n_samples, offset=0):
+    """Missing-modality masks drawn from the reference's imbalanced mr2468 table."""
+    import csv
+    import numpy as np
+    with open(os.path.join(ROOT, "tests", "golden", "Brats2020_imb_split_mr2468.csv")) as f:
+        table = [int(r["mask_id"]) for r in csv.DictReader(f)]
+    rs = np.random.RandomState(1037)
+    ids = [table[i] for i in rs.randint(0, len(table), offset + n_samples)]
+    return ids[offset:]
+
+
+MASK_ARRAY = [[False, False, False, True], [False, True, False, False], [False, False, True, False], [True, False, False, False],
+              [False, True, False, True], [False, True, True, False], [True, False, True, False], [False, False, True, True],
+              [True, False, False, True], [True, True, False, False], [True, True, True, False], [True, False, True, True],
+              [True, True, False, True], [False, True, True, True], [True, True, True, True]]     # datasets_nii.py:27-30
+
+
+def synth_host_batches(rank, n_batches, B, S):
+    """Pinned-host synthetic batches in the reference loader's format: x f32 [B,4,S,S,S], one-hot target f64, mask bool."""
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(1037 + rank)
+    out = []
+    for i in range(n_batches):
+        x = torch.from_numpy(rs.standard_normal((B, 4, S, S, S)).astype(np.float32))
+        y = rs.randint(0, 4, (B, S, S, S))
+        target = torch.from_numpy(np.ascontiguousarray(np.eye(4)[y].transpose(0, 4, 1, 2, 3)))
+        ids = mask_ids_for(B, offset=(rank * n_batches + i) * B)
+        mask = torch.tensor([MASK_ARRAY[j] for j in ids])
+        out.append(tuple(t.pin_memory() if torch.cuda.is_available() else t for t in (x, target, mask)))
+    return out
+
+
+def modal_weight():
+    """iter_per_epoch / modal_num of the mr2468 table (train.py:163-171): 219 / (90, 135, 184, 43)."""
+    import torch
+    return torch.tensor([219 / 90.0, 219 / 135.0, 219 / 184.0, 219 / 43.0])
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from passion_b200 import _lib, ops
+    from passion_b200.engine import Trainer
+    from passion_b200.models import rfnet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    torch.manual_seed(1037)
+    model = rfnet.Model(num_cls=4).to(dev)
+    model.compute_dtype = dtype
+    trainer = Trainer(model, lr=2e-4, weight_decay=1e-4, temp=4.0, mask_type="idt", use_passion=True,
+                      modal_weight=modal_weight())
+    B, S = args.batch, args.size
+    nb = 2
+    host = synth_host_batches(rank, nb, B, S)
+    devb = [tuple(t.to(dev) for t in b) for b in host]
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        trainer.step(*devb[i % nb])
+    sync()
+
+    # ---- timed region 1: inputs resident in HBM; every kernel launch timed with CUDA events
+    clocks = ClockSampler(local)
+    timer = ops.KernelTimer()
+    ops.TIMER = timer
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for i in range(args.steps):
+        loss, _ = trainer.step(*devb[i % nb])
+    e1.record()
+    sync()
+    ops.TIMER = None
+    launches = _lib.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+
+    # ---- timed region 2: end to end through the public API from pinned host buffers
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e2.record()
+    last = 0.0
+    for i in range(args.steps):
+        xb, tb, mb = (t.to(dev, non_blocking=True) for t in host[i % nb])
+        loss, _ = trainer.step(xb, tb, mb)
+        last = float(loss.item())                       # D2H read of the step's result
+    e3.record()
+    sync()
+    clk = clocks.stop()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2_total = float(ms2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    samples = args.steps * B * world
+    value = samples / (ms_total / 1e3)
+    e2e = samples / (ms2_total / 1e3)
+    hbm_peak, tc_peak, how = peaks()
+    summ = timer.summary()
+    fam = {}
+    for (name, key), d in summ.items():
+        f = fam.setdefault(name, dict(calls=0, ms=0.0, bytes=0, flops=0))
+        for k in f:
+            f[k] += d[k]
+    top_name = max(fam, key=lambda k: fam[k]["ms"])
+    top = fam[top_name]
+    top_cls = max(((k, d) for k, d in summ.items() if k[0] == top_name), key=lambda kv: kv[1]["ms"])
+    ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": how,
+                "launches": top["calls"], "avg_launch_ms": round(top["ms"] / top["calls"], 4),
+                "share_of_step": round(top["ms"] / ms_total, 3),
+                "top_class": {"key": top_cls[0][1], "ms_per_launch": round(top_cls[1]["ms"] / top_cls[1]["calls"], 4),
+                              "GBps": round(top_cls[1]["bytes"] / (top_cls[1]["ms"] / 1e3) / 1e9, 1),
+                              "TFLOPs": round(top_cls[1]["flops"] / (top_cls[1]["ms"] / 1e3) / 1e12, 2)},
+                "step_hbm_frac": round(value / world * BYTES_PER_SAMPLE / 1e9 / hbm_peak, 4),
+                "step_tc_frac": round(value / world * FLOP_PER_SAMPLE / 1e12 / tc_peak, 4),
+                "families_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+    out = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
+           "config": {"workload": f"RFNet+PASSION train step, B={B}/GPU, 4x{S}^3 crops, idt masks from mr2468, temp 4, AdamW amsgrad",
+                      "global_batch": B * world, "parallelism": f"dp{world}",
+                      "l2": "per-step working set (~6 GiB of activations) exceeds the 126 MB L2; no explicit flush"},
+           "clocks": clk,
+           "e2e": {"value": round(e2e, 3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "ms_per_step": round(ms2_total / args.steps, 3), "last_loss": last},
+           "gpu_launches": int(launches), "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(budget_s=30.0)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------- CPU reference arm
+def _oracle_step_fn(S, B=1):
+    """One training step of the reference algorithm's CPU port (oracle/, torch fp32 on the host cores)."""
+    import torch
+    from oracle import rfnet_oracle, synth, train_step_oracle
+    torch.set_num_threads(os.cpu_count())
+    sd = synth.make_state_dict(1037)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW([{"params": list(P.values()), "lr": 2e-4, "weight_decay": 1e-4}], betas=(0.9, 0.999),
+                            eps=1e-8, amsgrad=True)
+    x, target, mask, _ = synth.make_batch(B, S, seed=1037, labels="U", mask_ids=mask_ids_for(B))
+    beta, mw = torch.ones(4), modal_weight()
+
+    def step():
+        outs = rfnet_oracle.forward(P, x, mask, target, 4.0)
+        loss, _ = train_step_oracle.loss_mix(outs, target, mask, beta, mw)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def cpu_baseline(budget_s=30.0):
+    import torch
+    step16 = _oracle_step_fn(16)
+    step16()                                            # library warm-up at a tiny size
+    step = _oracle_step_fn(S_CROP, 1)
+    t0 = time.time()
+    step()
+    dt = time.time() - t0
+    return {"value": round(1.0 / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 step, B=1, 4x{S_CROP}^3, fp32, oracle/ (PyTorch-CPU restatement of the reference), {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores.  /root/reference does not exist on
+    the GPU box and the reference cannot be pip-installed (it is a script tree without setup.py), so the arm
+    runs the oracle port, which gen_golden.py pinned against the real reference modules."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    total = args.steps + args.warmup
+    step16 = _oracle_step_fn(16)
+    step16()
+    # size the per-step sample so that the whole run stays within ~4 minutes: full 80^3 costs ~10-14 s/step
+    probe = _oracle_step_fn(32)
+    t0 = time.time(); probe(); t32 = time.time() - t0
+    S = S_CROP
+    for cand in (80, 64, 48, 40, 32):
+        S = cand
+        if t32 * (cand / 32.0) ** 3 * total <= 240.0:
+            break
+    step = _oracle_step_fn(S, 1)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t0
+    frac = (S / float(S_CROP)) ** 3                      # conv work is linear in voxels
+    value = args.steps * frac / dt
+    cores = torch.get_num_threads()
+    sample = f"{args.steps} steps, B=1, 4x{S}^3 crop (= {frac:.3f} of an 80^3 sample each), fp32, {cores} threads"
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "samples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"RFNet+PASSION train step (CPU port of the reference algorithm), 4x{S}^3 crops scaled to 80^3-equivalent samples"},
+           "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--size", type=int, default=S_CROP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,20 +40,18 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
 }
 
 // per-(n,c): sum g, sum g*xhat  with g = dout * lrelu'(xhat).  grid = (blocks_per_sample, n);
-// a thread keeps the same VEC channels for all its voxels (thread stride is a multiple of c/VEC).
+// a thread keeps the same VEC channels for all its voxels; block reduction in a fixed order (deterministic).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                          const float* __restrict__ mr, double* __restrict__ sums,
                                                          long long voxels, int c, float slope) {
-    extern __shared__ float ssum[];                           // [c][2]
+    extern __shared__ float ssum[];                           // [vpb][2*c]
     const int n = blockIdx.y;
     const int lanes = c / VEC;                                // threads per voxel
     const int tpb = (256 / lanes) * lanes;                    // active threads
-    for (int i = threadIdx.x; i < 2 * c; i += 256) ssum[i] = 0.f;
-    __syncthreads();
+    const int vpb = tpb / lanes;                              // voxels per block-iteration
     if ((int)threadIdx.x < tpb) {
         const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
-        const int vpb = tpb / lanes;                          // voxels per block-iteration
         const int c0 = cl * VEC;
         float mean[VEC], rstd[VEC], sg[VEC], sgx[VEC];
 #pragma unroll
@@ -74,11 +72,16 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
                 sg[j] += gg; sgx[j] += gg * xh;
             }
         }
+        float* r = ssum + (size_t)vl * 2 * c;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { atomicAdd(&ssum[2 * (c0 + j)], sg[j]); atomicAdd(&ssum[2 * (c0 + j) + 1], sgx[j]); }
+        for (int j = 0; j < VEC; ++j) { r[2 * (c0 + j)] = sg[j]; r[2 * (c0 + j) + 1] = sgx[j]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * c; i += 256) atomicAdd(&sums[(size_t)n * c * 2 + i], (double)ssum[i]);
+    for (int i = threadIdx.x; i < 2 * c; i += 256) {
+        float s = 0.f;
+        for (int v = 0; v < vpb; ++v) s += ssum[(size_t)v * 2 * c + i];
+        atomicAdd(&sums[(size_t)n * c * 2 + i], (double)s);
+    }
 }
 
 // dy = rstd * (g - mean(g) - xhat * mean(g*xhat))
@@ -130,7 +133,7 @@ int run_bwd(const void* dout, const void* y, const float* mr, double* sums, void
     const int cap = (148 * 8 + n - 1) / n;
     if (bps > cap) bps = cap;
     if (bps < 1) bps = 1;
-    bwd_reduce_kernel<T, VEC><<<dim3(bps, n), 256, 2 * c * sizeof(float), st>>>((const T*)dout, (const T*)y, mr, sums, voxels, c, slope);
+    bwd_reduce_kernel<T, VEC><<<dim3(bps, n), 256, (size_t)vpb * 2 * c * sizeof(float), st>>>((const T*)dout, (const T*)y, mr, sums, voxels, c, slope);
     pb_count_launch();
     const long long total_vec = (long long)n * voxels * c / VEC;
     bwd_apply_kernel<T, VEC><<<grid_for(total_vec, 256), 256, 0, st>>>((const T*)dout, (const T*)y, mr, sums, (T*)dy, total_vec,

@@ -11,14 +11,15 @@
 namespace {
 
 // S[n][i][kc] += sum_v y[kc] p_i ; Psum[n][i] += sum_v p_i.   grid = (blocks_per_sample, n)
+// Block reduction is order-deterministic (per-thread partials in smem, summed in a fixed order), so two
+// samples with identical inputs produce bit-identical block partials.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ y, const float* __restrict__ p, double* __restrict__ S,
                                                    double* __restrict__ Psum, long long voxels, int kc) {
-    extern __shared__ float ssum[];                           // [4][kc] + [4]
+    extern __shared__ float ssum[];                           // [vpb][4*kc + 4]
     const int n = blockIdx.y;
     const int lanes = kc / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
-    for (int i = threadIdx.x; i < 4 * kc + 4; i += 256) ssum[i] = 0.f;
-    __syncthreads();
+    const int row = 4 * kc + 4;
     if ((int)threadIdx.x < tpb) {
         const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes, c0 = cl * VEC;
         float acc[4][VEC], pacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -40,16 +41,21 @@ __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ y, cons
                 for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(yv[j], pp[i], acc[i][j]);
             }
         }
+        float* r = ssum + (size_t)vl * row;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) atomicAdd(&ssum[i * kc + c0 + j], acc[i][j]);
-            if (cl == 0) atomicAdd(&ssum[4 * kc + i], pacc[i]);
+            for (int j = 0; j < VEC; ++j) r[i * kc + c0 + j] = acc[i][j];
+            if (cl == 0) r[4 * kc + i] = pacc[i];
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 4 * kc; i += 256) atomicAdd(&S[(size_t)n * 4 * kc + i], (double)ssum[i]);
-    if (threadIdx.x < 4) atomicAdd(&Psum[(size_t)n * 4 + threadIdx.x], (double)ssum[4 * kc + threadIdx.x]);
+    for (int i = threadIdx.x; i < row; i += 256) {
+        float s = 0.f;
+        for (int v = 0; v < vpb; ++v) s += ssum[(size_t)v * row + i];
+        if (i < 4 * kc) atomicAdd(&S[(size_t)n * 4 * kc + i], (double)s);
+        else            atomicAdd(&Psum[(size_t)n * 4 + (i - 4 * kc)], (double)s);
+    }
 }
 
 // R[n][v][i*C+c] = p_i * sum_k gate[n][i][k] y[n][v][k*C+c]   (K = 4 modalities, 4 classes)
@@ -194,7 +200,7 @@ extern "C" int pb_rfm_pool(int dtype, const void* y, const float* p, double* S, 
         const int lanes = kc / VEC, vpb = 256 / lanes;
         int bps = blocks_per_sample(voxels * lanes / 2, n);
         if ((long long)bps * vpb > voxels) bps = (int)((voxels + vpb - 1) / vpb);
-        pool_kernel<T, VEC><<<dim3(bps, n), 256, (4 * kc + 4) * sizeof(float), st>>>((const T*)y, p, S, Psum, voxels, kc);
+        pool_kernel<T, VEC><<<dim3(bps, n), 256, (size_t)vpb * (4 * kc + 4) * sizeof(float), st>>>((const T*)y, p, S, Psum, voxels, kc);
     });
     PB_CHECK_LAUNCH();
     return PB_OK;

@@ -1,0 +1,53 @@
+"""Training-step engine: what reference train.py:198-289 does per iteration, as one object.
+
+    trainer = Trainer(model, lr=2e-4, weight_decay=1e-4, temp=4.0, mask_type='idt', ...)
+    loss, parts = trainer.step(x, target, mask)
+
+One process per GPU.  With torch.distributed initialised (backend nccl) the step adds exactly two
+exchanges: a 4-float all-reduce of rp_iter before the loss mix (rp_mask is a global-batch
+statistic, train.py:265-268) and a SUM all-reduce of the gradients (the reference loss is a sum over
+samples, train.py:229,260-263 — averaging would change the effective LR), bucketed and launched from
+autograd hooks on a side stream so that it overlaps the rest of backward (passion_b200/ddp.py).
+"""
+import torch
+
+from . import ddp as _ddp
+from .train_step import loss_mix
+
+
+class Trainer:
+    def __init__(self, model, lr=2e-4, weight_decay=1e-4, temp=4.0, mask_type="idt", use_passion=True,
+                 modal_weight=None, imb_beta=None, warmup=False, distributed=None, bucket_mb=4.0):
+        self.model = model
+        dev = next(model.parameters()).device
+        self.dev = dev
+        model.is_training, model.use_passion, model.mask_type = True, use_passion, mask_type
+        self.temp, self.mask_type, self.warmup = temp, mask_type, warmup
+        self.modal_weight = (modal_weight if modal_weight is not None else torch.ones(4)).to(dev).float()
+        self.imb_beta = (imb_beta if imb_beta is not None else torch.ones(4)).to(dev).float()
+        # train.py:94-96
+        self.optimizer = torch.optim.AdamW([{"params": model.parameters(), "lr": lr, "weight_decay": weight_decay}],
+                                           betas=(0.9, 0.999), eps=1e-08, amsgrad=True)
+        if distributed is None:
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1
+        self.reducer = _ddp.GradReducer(model, bucket_mb=bucket_mb) if distributed else None
+        if self.reducer is not None:
+            self.reducer.broadcast_parameters()
+
+    def forward_loss(self, x, target, mask):
+        outs = self.model(x, mask, target=target, temp=self.temp)
+        rp_allreduce = self.reducer.allreduce_small if self.reducer is not None else None
+        return loss_mix(outs, target, mask, self.imb_beta, self.modal_weight, mask_type=self.mask_type,
+                        warmup=self.warmup, rp_allreduce=rp_allreduce)
+
+    def step(self, x, target, mask):
+        loss, parts = self.forward_loss(x, target, mask)
+        self.optimizer.zero_grad(set_to_none=True)
+        if self.reducer is not None:
+            self.reducer.prepare()
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.optimizer.step()
+        return loss.detach(), parts

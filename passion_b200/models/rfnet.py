@@ -378,6 +378,12 @@ class Model(nn.Module):
             kl = kl + wl * crit.kl_cl(ps_l, pt_l, temp)
         de1 = des[0].view(P, B, V, -1).float()
         proto, dist = crit.proto_cl(de1[1:], de1[0].detach(), t_cl.view(B, V, -1), cnt)
+        # A sample whose ONLY present modality is m makes pass 1+m identical to pass 0 (same inputs, same
+        # weights): the reference then gets kl = proto = dist = 0 EXACTLY (bit-identical passes), which is what
+        # turns rp_iter into 0/0 = NaN in train.py:265-268.  Reproduce the exact zeros structurally.
+        ident = (mask.to(torch.bool) & (fm.sum(1, keepdim=True) == 1)).t()   # [4(m),B]
+        zero = torch.zeros((), device=x.device)
+        kl, proto, dist = (torch.where(ident, zero, t) for t in (kl, proto, dist))
         kl_loss = (e * kl).t()
         proto_loss = (e * proto).t()
         dist_out = (e * dist).t()

@@ -40,6 +40,52 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the library's kernels (bench.py's live roofline numbers).
+    Events are recorded on the launching stream around each C-ABI call."""
+
+    def __init__(self):
+        self.records = []
+
+    def run(self, name, key, nbytes, flops, fn):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn()
+        e1.record()
+        self.records.append((name, key, nbytes, flops, e0, e1))
+        return rc
+
+    def summary(self):
+        """{(name, key): dict(calls, ms, bytes, flops)} — call after torch.cuda.synchronize()."""
+        out = {}
+        for name, key, nbytes, flops, e0, e1 in self.records:
+            d = out.setdefault((name, key), dict(calls=0, ms=0.0, bytes=0, flops=0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        return out
+
+
+TIMER = None          # set to a KernelTimer() to time every launch
+
+
+def _run(name, key, nbytes, flops, fn):
+    rc = TIMER.run(name, key, nbytes, flops, fn) if TIMER is not None else fn()
+    _lib.check(rc, name)
+
+
+def _conv_work(d, esize):
+    """algorithmic bytes (each activation tensor touched once) and FLOPs of one conv launch."""
+    cin = d.c0 + d.c1
+    vin, vout = d.di * d.hi * d.wi, d.dout * d.ho * d.wo
+    nbytes = d.n * (vin * cin + vout * d.cout) * esize
+    flops = 2 * d.n * vout * d.ksize ** 3 * cin * d.cout
+    key = f"c{cin}->{d.cout} k{d.ksize} s{d.stride} {d.dout}x{d.ho}x{d.wo} n{d.n} g{d.groups}"
+    return key, nbytes, flops
+
+
 def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
     n, di, hi, wi, c0 = x0.shape
     pad = ksize // 2
@@ -63,8 +109,9 @@ class _Conv3d(torch.autograd.Function):
         assert w.shape == (groups, ksize ** 3, d.c0 + d.c1, cout), (tuple(w.shape), groups, ksize, d.c0, d.c1, cout)
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
         stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
-        _lib.check(lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(w), _p(bias), _p(y), _p(stats), _stream()),
-                   "conv3d_fwd")
+        key, nb, fl = _conv_work(d, x0.element_size())
+        _run("conv3d_fwd", key, nb, fl,
+             lambda: lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(w), _p(bias), _p(y), _p(stats), _stream()))
         ctx.save_for_backward(x0, x1, w)
         ctx.cfg = (ksize, stride, pad_mode, groups, bias is not None)
         if want_stats:
@@ -80,15 +127,18 @@ class _Conv3d(torch.autograd.Function):
         dy = dy.contiguous()
         d = _conv_desc(x0, x1, w.shape[-1], ksize, stride, pad_mode, groups)
         dx0 = dx1 = dw = db = None
+        key, nb, fl = _conv_work(d, x0.element_size())
         need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
         if need_dx:
             wt = w.transpose(2, 3).contiguous()
             dx0 = torch.empty_like(x0)
             dx1 = torch.empty_like(x1) if x1 is not None else None
-            _lib.check(lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()), "conv3d_dgrad")
+            _run("conv3d_dgrad", key, nb, fl,
+                 lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
         if ctx.needs_input_grad[2]:
             dw = torch.zeros_like(w)
-            _lib.check(lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()), "conv3d_wgrad")
+            _run("conv3d_wgrad", key, nb, fl,
+                 lambda: lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()))
         if has_bias and ctx.needs_input_grad[3]:
             db = dy.float().reshape(groups, -1, dy.shape[-1]).sum(1)
         return dx0, dx1, dw, db, None, None, None, None, None
@@ -102,7 +152,7 @@ def conv3d(x0, w, bias=None, x1=None, ksize=3, stride=1, pad_mode="reflect", gro
 def kernel_layout(w):
     """reference Conv3d weight [cout, cin, kd, kh, kw] -> [taps, cin, cout] (differentiable)."""
     cout, cin = w.shape[:2]
-    return w.permute(2, 3, 4, 1, 0).reshape(-1, cin, cout)
+    return w.permute(2, 3, 4, 1, 0).reshape(-1, cin, cout).contiguous()
 
 
 def inorm_finalize(stats, voxels, eps=IN_EPS):
@@ -124,8 +174,9 @@ class _InormLrelu(torch.autograd.Function):
         n, c = y.shape[0], y.shape[-1]
         voxels = y.numel() // (n * c)
         out = torch.empty_like(y)
-        _lib.check(lib.pb_inorm_lrelu_fwd(_dt(y), _p(y), _p(mr), _p(res), _p(out), n, voxels, c, LRELU_SLOPE, _stream()),
-                   "inorm_lrelu_fwd")
+        nb = y.numel() * y.element_size() * (3 if res is not None else 2)
+        _run("inorm_lrelu_fwd", f"c{c}", nb, 0,
+             lambda: lib.pb_inorm_lrelu_fwd(_dt(y), _p(y), _p(mr), _p(res), _p(out), n, voxels, c, LRELU_SLOPE, _stream()))
         ctx.save_for_backward(y, mr)
         ctx.has_res = res is not None
         return out
@@ -139,8 +190,9 @@ class _InormLrelu(torch.autograd.Function):
         voxels = y.numel() // (n * c)
         sums = torch.zeros((n, c, 2), dtype=torch.float64, device=y.device)
         dy = torch.empty_like(y)
-        _lib.check(lib.pb_inorm_lrelu_bwd(_dt(y), _p(dout), _p(y), _p(mr), _p(sums), _p(dy), n, voxels, c, LRELU_SLOPE,
-                                          _stream()), "inorm_lrelu_bwd")
+        _run("inorm_lrelu_bwd", f"c{c}", y.numel() * y.element_size() * 3, 0,
+             lambda: lib.pb_inorm_lrelu_bwd(_dt(y), _p(dout), _p(y), _p(mr), _p(sums), _p(dy), n, voxels, c, LRELU_SLOPE,
+                                            _stream()))
         return dy, None, (dout if ctx.has_res else None)
 
 
@@ -160,7 +212,8 @@ class _Upsample(torch.autograd.Function):
         _chk(x)
         n, d, h, w, c = x.shape
         y = torch.empty((n, d * scale, h * scale, w * scale, c), dtype=x.dtype, device=x.device)
-        _lib.check(lib.pb_upsample_fwd(_dt(x), _p(x), _p(y), n, d, h, w, c, scale, _stream()), "upsample_fwd")
+        _run("upsample_fwd", f"c{c} x{scale}", (x.numel() + y.numel()) * x.element_size(), 0,
+             lambda: lib.pb_upsample_fwd(_dt(x), _p(x), _p(y), n, d, h, w, c, scale, _stream()))
         ctx.shape, ctx.scale = (n, d, h, w, c), scale
         return y
 
@@ -170,7 +223,8 @@ class _Upsample(torch.autograd.Function):
         dy = dy.contiguous()
         n, d, h, w, c = ctx.shape
         dx = torch.empty((n, d, h, w, c), dtype=dy.dtype, device=dy.device)
-        _lib.check(lib.pb_upsample_bwd(_dt(dy), _p(dy), _p(dx), n, d, h, w, c, ctx.scale, _stream()), "upsample_bwd")
+        _run("upsample_bwd", f"c{c} x{ctx.scale}", (dx.numel() + dy.numel()) * dy.element_size(), 0,
+             lambda: lib.pb_upsample_bwd(_dt(dy), _p(dy), _p(dx), n, d, h, w, c, ctx.scale, _stream()))
         return dx, None
 
 
