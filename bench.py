@@ -234,6 +234,14 @@ def run_ours(args):
            "e2e": {"value": round(e2e, 3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                    "ms_per_step": round(ms2_total / args.steps, 3), "last_loss": last},
            "gpu_launches": int(launches), "roofline": roofline}
+    dump = os.environ.get("PB_DUMP_KERNELS")
+    if dump:
+        rows = sorted(((k[0], k[1], d["calls"] // args.steps, d["ms"] / args.steps, d["bytes"] / (d["ms"] / 1e3) / 1e9,
+                       d["flops"] / (d["ms"] / 1e3) / 1e12) for k, d in summ.items()), key=lambda r: -r[3])
+        with open(dump, "w") as f:
+            f.write("kernel | class | launches/step | ms/step | GB/s (algorithmic) | TFLOP/s\n")
+            for r in rows:
+                f.write(f"{r[0]} | {r[1]} | {r[2]} | {r[3]:.3f} | {r[4]:.1f} | {r[5]:.2f}\n")
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(budget_s=30.0)
     print(json.dumps(out), flush=True)

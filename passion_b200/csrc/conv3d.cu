@@ -311,6 +311,52 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(ConvK p, WgK q, const T
     }
 }
 
+// ------------------------------------------------------------------------------------ wgrad, 1x1x1
+// dw[ci][co] = sum_v x[v][ci] * dy[v][co]: every thread streams a strided set of voxels and keeps a CI_B x CO_B
+// register tile; one shuffle + smem reduction per block, then fp32 atomics.  grid = (voxel blocks, ci/co tiles, groups)
+template <typename T, int CI_B, int CO_B>
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(ConvK p, const T* __restrict__ x0, const T* __restrict__ x1,
+                                                          const T* __restrict__ dy, float* __restrict__ dw) {
+    __shared__ float red[8][CI_B * CO_B];
+    const int g = blockIdx.z;
+    const int n_ci = p.Cin / CI_B;
+    const int ci0 = (blockIdx.y % n_ci) * CI_B, co0 = (blockIdx.y / n_ci) * CO_B;
+    const bool from1 = ci0 >= p.C0;
+    const T* xs = from1 ? x1 : x0;
+    const int cs = from1 ? p.C1 : p.C0, coff = from1 ? ci0 - p.C0 : ci0;
+    float acc[CI_B][CO_B];
+#pragma unroll
+    for (int i = 0; i < CI_B; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_B; ++j) acc[i][j] = 0.f;
+    const long long v_begin = (long long)g * p.npg * p.Vo, v_end = v_begin + (long long)p.npg * p.Vo;
+    for (long long v = v_begin + (long long)blockIdx.x * 256 + threadIdx.x; v < v_end; v += (long long)gridDim.x * 256) {
+        float xv[CI_B], gv[CO_B];
+        VecIO<T, CI_B>::load(xs + v * cs + coff, xv);
+        VecIO<T, CO_B>::load(dy + v * p.Cout + co0, gv);
+#pragma unroll
+        for (int i = 0; i < CI_B; ++i)
+#pragma unroll
+            for (int j = 0; j < CO_B; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < CI_B; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_B; ++j) {
+            const float s = warp_sum(acc[i][j]);
+            if (lane == 0) red[wid][i * CO_B + j] = s;
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < CI_B * CO_B; e += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) s += red[w8][e];
+        const int i = e / CO_B, j = e % CO_B;
+        atomicAdd(dw + ((size_t)g * p.Cin + ci0 + i) * p.Cout + co0 + j, s);
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 int fill(const pb_conv_desc* d, ConvK& k) {
     if (!d) return -1;
@@ -442,8 +488,38 @@ int dispatch_wgrad_co(int co_t, const ConvK& k, const WgK& q, const void* x0, co
     }
 }
 
+template <typename T, int CI_B, int CO_B>
+int launch_wgrad1(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
+    const int tiles = (k.Cin / CI_B) * (k.Cout / CO_B);
+    const long long vox = (long long)k.npg * k.Vo;
+    long long nblk = (148LL * 8 + (long long)tiles * k.groups - 1) / ((long long)tiles * k.groups);
+    const long long need = (vox + 256 * 4 - 1) / (256 * 4);            // >= 4 voxels per thread
+    if (nblk > need) nblk = need;
+    if (nblk < 1) nblk = 1;
+    conv1_wgrad_kernel<T, CI_B, CO_B><<<dim3((unsigned)nblk, tiles, k.groups), 256, 0, st>>>(k, (const T*)x0, (const T*)x1,
+                                                                                            (const T*)dy, dw);
+    return 0;
+}
+
+template <typename T>
+int dispatch_wgrad1(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
+    const int co_b = chunk_of(k.Cout, 16);
+    int ci_b = chunk_of(k.C0, 64 / co_b > 8 ? 8 : 64 / co_b);
+    if (k.C1) ci_b = chunk_of(k.C1, ci_b);
+#define W1(CI, CO) return launch_wgrad1<T, CI, CO>(k, x0, x1, dy, dw, st)
+    switch (co_b) {
+        case 16: switch (ci_b) { case 4: W1(4, 16); case 2: W1(2, 16); default: W1(1, 16); }
+        case 8:  switch (ci_b) { case 8: W1(8, 8); case 4: W1(4, 8); case 2: W1(2, 8); default: W1(1, 8); }
+        case 4:  switch (ci_b) { case 8: W1(8, 4); case 4: W1(4, 4); case 2: W1(2, 4); default: W1(1, 4); }
+        case 2:  switch (ci_b) { case 8: W1(8, 2); case 4: W1(4, 2); case 2: W1(2, 2); default: W1(1, 2); }
+        default: switch (ci_b) { case 8: W1(8, 1); case 4: W1(4, 1); case 2: W1(2, 1); default: W1(1, 1); }
+    }
+#undef W1
+}
+
 template <typename T>
 int dispatch_wgrad(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
+    if (k.K == 1) return dispatch_wgrad1<T>(k, x0, x1, dy, dw, st);
     WgK q;
     if (k.S == 1) { q.td = 4; q.th = 4; q.tw = 8; } else { q.td = 2; q.th = 4; q.tw = 8; }
     q.hd = (q.td - 1) * k.S + k.K; q.hh = (q.th - 1) * k.S + k.K; q.hw = (q.tw - 1) * k.S + k.K;

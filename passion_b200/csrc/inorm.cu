@@ -45,7 +45,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                          const float* __restrict__ mr, double* __restrict__ sums,
                                                          long long voxels, int c, float slope) {
-    extern __shared__ float ssum[];                           // [vpb][2*c]
+    extern __shared__ double ssum[];                          // [vpb][2*c]
     const int n = blockIdx.y;
     const int lanes = c / VEC;                                // threads per voxel
     const int tpb = (256 / lanes) * lanes;                    // active threads
@@ -53,11 +53,12 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
     if ((int)threadIdx.x < tpb) {
         const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
         const int c0 = cl * VEC;
-        float mean[VEC], rstd[VEC], sg[VEC], sgx[VEC];
+        float mean[VEC], rstd[VEC];
+        double sg[VEC], sgx[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             mean[j] = mr[((size_t)n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)n * c + c0 + j) * 2 + 1];
-            sg[j] = 0.f; sgx[j] = 0.f;
+            sg[j] = 0.0; sgx[j] = 0.0;
         }
         const T* dn = dout + (size_t)n * voxels * c;
         const T* yn = y + (size_t)n * voxels * c;
@@ -69,27 +70,29 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
             for (int j = 0; j < VEC; ++j) {
                 float xh = (yv[j] - mean[j]) * rstd[j];
                 float gg = xh > 0.f ? g[j] : g[j] * slope;
-                sg[j] += gg; sgx[j] += gg * xh;
+                sg[j] += (double)gg; sgx[j] += (double)gg * (((double)yv[j] - (double)mean[j]) * (double)rstd[j]);
             }
         }
-        float* r = ssum + (size_t)vl * 2 * c;
+        double* r = ssum + (size_t)vl * 2 * c;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { r[2 * (c0 + j)] = sg[j]; r[2 * (c0 + j) + 1] = sgx[j]; }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * c; i += 256) {
-        float s = 0.f;
+        double s = 0.0;
         for (int v = 0; v < vpb; ++v) s += ssum[(size_t)v * 2 * c + i];
-        atomicAdd(&sums[(size_t)n * c * 2 + i], (double)s);
+        atomicAdd(&sums[(size_t)n * c * 2 + i], s);
     }
 }
 
-// dy = rstd * (g - mean(g) - xhat * mean(g*xhat))
+// dy = rstd * (g - mean(g) - xhat * mean(g*xhat)).  The three-term difference cancels heavily when the incoming
+// gradient lies mostly in span{1, xhat} (typical right below the loss), so it is evaluated in float64 from the
+// float64 sums; the LeakyReLU branch uses the same fp32 xhat as the forward pass.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                         const float* __restrict__ mr, const double* __restrict__ sums,
                                                         T* __restrict__ dy, long long total_vec, long long vox_c, int c,
-                                                        float inv_v, float slope) {
+                                                        double inv_v, float slope) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * VEC;
         const int n = (int)(e / vox_c);
@@ -102,9 +105,10 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ do
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             const float rstd = m[2 * j + 1];
-            float xh = (yv[j] - m[2 * j]) * rstd;
-            float gg = xh > 0.f ? g[j] : g[j] * slope;
-            g[j] = rstd * (gg - (float)s[2 * j] * inv_v - xh * ((float)s[2 * j + 1] * inv_v));
+            const float xh = (yv[j] - m[2 * j]) * rstd;
+            const float gg = xh > 0.f ? g[j] : g[j] * slope;
+            const double xd = ((double)yv[j] - (double)m[2 * j]) * (double)rstd;
+            g[j] = (float)((double)rstd * ((double)gg - s[2 * j] * inv_v - xd * (s[2 * j + 1] * inv_v)));
         }
         VecIO<T, VEC>::store(dy + e, g);
     }
@@ -133,11 +137,11 @@ int run_bwd(const void* dout, const void* y, const float* mr, double* sums, void
     const int cap = (148 * 8 + n - 1) / n;
     if (bps > cap) bps = cap;
     if (bps < 1) bps = 1;
-    bwd_reduce_kernel<T, VEC><<<dim3(bps, n), 256, (size_t)vpb * 2 * c * sizeof(float), st>>>((const T*)dout, (const T*)y, mr, sums, voxels, c, slope);
+    bwd_reduce_kernel<T, VEC><<<dim3(bps, n), 256, (size_t)vpb * 2 * c * sizeof(double), st>>>((const T*)dout, (const T*)y, mr, sums, voxels, c, slope);
     pb_count_launch();
     const long long total_vec = (long long)n * voxels * c / VEC;
     bwd_apply_kernel<T, VEC><<<grid_for(total_vec, 256), 256, 0, st>>>((const T*)dout, (const T*)y, mr, sums, (T*)dy, total_vec,
-                                                                       voxels * c, c, 1.0f / (float)voxels, slope);
+                                                                       voxels * c, c, 1.0 / (double)voxels, slope);
     return 0;
 }
 

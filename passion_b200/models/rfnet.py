@@ -333,7 +333,7 @@ class Model(nn.Module):
         D, H, W = logits.shape[1:4]
         fuse_logits = logits.view(P, B, D, H, W, -1)
         fuse_prob = torch.softmax(fuse_logits[0].float(), -1).permute(0, 4, 1, 2, 3)   # [B,C,D,H,W]
-        self.last = {"fuse_logits": fuse_logits, "prm_logits": prms, "de_f": des, "passes": P}
+        self.last = {"fuse_logits": fuse_logits, "prm_logits": prms, "de_f": des, "passes": P, "enc": enc}
         if not self.is_training:
             return fuse_prob
 
