@@ -73,6 +73,21 @@ int pb_conv3d_dgrad(const pb_conv_desc* d, const void* dy, const float* wt, void
 int pb_conv3d_wgrad(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy,
                     float* dw, pb_stream_t stream);
 
+/* tcgen05 / TMEM implicit-GEMM path for the dominant class: bf16, 3x3x3, stride 1, same-size output, c0/c1/cout
+ * multiples of 8, c0 + c1 <= 64 (csrc/conv3d_tc.cu).  `wimg` is the bf16 weight image
+ * [groups][cout tiles][27][max(2,cin/8)][NT][8] with NT = pb_conv3d_tc_ntile(cin, cout) (0 = class unsupported).
+ * The output may be split channel-wise into y0 (co0 channels) | y1 (co1 channels) — used by the data gradient
+ * of a two-source conv, which is this same kernel run on dy with flipped/transposed weights and zero padding
+ * (pb_conv3d_dgrad_reflect_fix then adds the reflected-halo terms).  `err_flag` is a zero-initialised device
+ * int that receives a non-zero code if the kernel's internal pipeline ever times out. */
+int pb_conv3d_tc_ntile(int cin, int cout);
+int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, void* y0, void* y1,
+                 int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
+/* dx0/dx1 += the contributions that reach an input voxel through the reflect padding (voxels one step inside a
+ * face); completes a zero-padding data gradient into the exact adjoint of the reflect-padded forward conv. */
+int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy, const float* wt, void* dx0, void* dx1,
+                                pb_stream_t stream);
+
 /* ---- InstanceNorm3d(affine=False, eps) + LeakyReLU(slope) (+ residual) -----------------
  * Replaces norm + activation of general_conv3d (blocks.py:18, :363, :367-369) and the encoder
  * residual add (rfnet.py:37,40,43,46).

@@ -131,7 +131,7 @@ __device__ __forceinline__ int dgrad_cand(int c, int i, int D, int pad, int refl
     return q;
 }
 
-template <typename T, int CO_V, int CI_T>
+template <typename T, int CO_V, int CI_T, bool MIRROR_ONLY>
 __global__ void __launch_bounds__(128) conv_dgrad_kernel(ConvK p, const T* __restrict__ dy, const float* __restrict__ wt,
                                                          T* __restrict__ dx0, T* __restrict__ dx1) {
     extern __shared__ __align__(16) float wsm[];              // [taps][Cout][CI_T]
@@ -149,6 +149,10 @@ __global__ void __launch_bounds__(128) conv_dgrad_kernel(ConvK p, const T* __res
     const int iw = (int)(iv % p.Wi);
     const int t1 = (int)(iv / p.Wi);
     const int ih = t1 % p.Hi, id = t1 / p.Hi;
+    if (MIRROR_ONLY) {      // only voxels one step inside a face receive reflected-halo contributions
+        const bool edge = id == 1 || id == p.Di - 2 || ih == 1 || ih == p.Hi - 2 || iw == 1 || iw == p.Wi - 2;
+        if (!edge) return;
+    }
 
     float acc[CI_T];
 #pragma unroll
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(128) conv_dgrad_kernel(ConvK p, const T* __res
                     for (int cw = 0; cw < nc; ++cw) {
                         bool okw; const int pw = dgrad_cand(cw, iw, p.Wi, p.pad, p.reflect, okw);
                         if (!okw) continue;
+                        if (MIRROR_ONLY && cd == 0 && ch == 0 && cw == 0) continue;   // the zero-padding part is already there
                         for (int kw = 0; kw < p.K; ++kw) {
                             const int tw = pw + p.pad - kw;
                             if (tw < 0) continue;
@@ -194,8 +199,14 @@ __global__ void __launch_bounds__(128) conv_dgrad_kernel(ConvK p, const T* __res
     }
     const int ci0 = cic * CI_T;
     const size_t vox = (size_t)n * p.Vi + iv;
-    if (ci0 < p.C0) VecIO<T, CI_T>::store(dx0 + vox * p.C0 + ci0, acc);
-    else            VecIO<T, CI_T>::store(dx1 + vox * p.C1 + (ci0 - p.C0), acc);
+    T* dst = ci0 < p.C0 ? dx0 + vox * p.C0 + ci0 : dx1 + vox * p.C1 + (ci0 - p.C0);
+    if (MIRROR_ONLY) {
+        float old[CI_T];
+        VecIO<T, CI_T>::load(dst, old);
+#pragma unroll
+        for (int j = 0; j < CI_T; ++j) acc[j] += old[j];
+    }
+    VecIO<T, CI_T>::store(dst, acc);
 }
 
 // ------------------------------------------------------------------------------------ wgrad
@@ -428,9 +439,9 @@ int dispatch_fwd(const ConvK& k, const void* x0, const void* x1, const float* w,
 }
 
 template <typename T, int CO_V, int CI_T>
-int launch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st) {
+int launch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st, bool mirror_only) {
     const size_t smem = (size_t)k.K * k.K * k.K * k.Cout * CI_T * sizeof(float);
-    auto kern = conv_dgrad_kernel<T, CO_V, CI_T>;
+    auto kern = mirror_only ? conv_dgrad_kernel<T, CO_V, CI_T, true> : conv_dgrad_kernel<T, CO_V, CI_T, false>;
     if (int e = set_smem(kern, smem)) return e;
     dim3 grid((unsigned)((k.Vi + 127) / 128), k.Cin / CI_T, k.N);
     kern<<<grid, 128, smem, st>>>(k, (const T*)dy, wt, (T*)dx0, (T*)dx1);
@@ -438,26 +449,26 @@ int launch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, voi
 }
 
 template <typename T, int CO_V>
-int dispatch_dgrad_ci(int ci_t, const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st) {
+int dispatch_dgrad_ci(int ci_t, const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st, bool mo) {
     switch (ci_t) {
-        case 16: return launch_dgrad<T, CO_V, 16>(k, dy, wt, dx0, dx1, st);
-        case 8:  return launch_dgrad<T, CO_V, 8>(k, dy, wt, dx0, dx1, st);
-        case 4:  return launch_dgrad<T, CO_V, 4>(k, dy, wt, dx0, dx1, st);
-        case 2:  return launch_dgrad<T, CO_V, 2>(k, dy, wt, dx0, dx1, st);
-        default: return launch_dgrad<T, CO_V, 1>(k, dy, wt, dx0, dx1, st);
+        case 16: return launch_dgrad<T, CO_V, 16>(k, dy, wt, dx0, dx1, st, mo);
+        case 8:  return launch_dgrad<T, CO_V, 8>(k, dy, wt, dx0, dx1, st, mo);
+        case 4:  return launch_dgrad<T, CO_V, 4>(k, dy, wt, dx0, dx1, st, mo);
+        case 2:  return launch_dgrad<T, CO_V, 2>(k, dy, wt, dx0, dx1, st, mo);
+        default: return launch_dgrad<T, CO_V, 1>(k, dy, wt, dx0, dx1, st, mo);
     }
 }
 
 template <typename T>
-int dispatch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st) {
+int dispatch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st, bool mo = false) {
     const int co_v = chunk_of(k.Cout, 8);
     int ci_t = chunk_of(k.C0, 16);
     if (k.C1) ci_t = chunk_of(k.C1, ci_t);
     switch (co_v) {
-        case 8:  return dispatch_dgrad_ci<T, 8>(ci_t, k, dy, wt, dx0, dx1, st);
-        case 4:  return dispatch_dgrad_ci<T, 4>(ci_t, k, dy, wt, dx0, dx1, st);
-        case 2:  return dispatch_dgrad_ci<T, 2>(ci_t, k, dy, wt, dx0, dx1, st);
-        default: return dispatch_dgrad_ci<T, 1>(ci_t, k, dy, wt, dx0, dx1, st);
+        case 8:  return dispatch_dgrad_ci<T, 8>(ci_t, k, dy, wt, dx0, dx1, st, mo);
+        case 4:  return dispatch_dgrad_ci<T, 4>(ci_t, k, dy, wt, dx0, dx1, st, mo);
+        case 2:  return dispatch_dgrad_ci<T, 2>(ci_t, k, dy, wt, dx0, dx1, st, mo);
+        default: return dispatch_dgrad_ci<T, 1>(ci_t, k, dy, wt, dx0, dx1, st, mo);
     }
 }
 
@@ -565,6 +576,19 @@ extern "C" int pb_conv3d_dgrad(const pb_conv_desc* d, const void* dy, const floa
     PB_CHECK_ARG(dy && wt && dx0 && (d->c1 == 0 || dx1), "null pointer");
     int e = d->dtype == PB_BF16 ? dispatch_dgrad<bf16>(k, dy, wt, dx0, dx1, (cudaStream_t)stream)
                                 : dispatch_dgrad<float>(k, dy, wt, dx0, dx1, (cudaStream_t)stream);
+    if (e) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy, const float* wt, void* dx0, void* dx1,
+                                           pb_stream_t stream) {
+    ConvK k;
+    PB_CHECK_ARG(fill(d, k) == 0, "bad descriptor");
+    PB_CHECK_ARG(dy && wt && dx0 && (d->c1 == 0 || dx1), "null pointer");
+    if (!k.reflect) return PB_OK;
+    int e = d->dtype == PB_BF16 ? dispatch_dgrad<bf16>(k, dy, wt, dx0, dx1, (cudaStream_t)stream, true)
+                                : dispatch_dgrad<float>(k, dy, wt, dx0, dx1, (cudaStream_t)stream, true);
     if (e) return e;
     PB_CHECK_LAUNCH();
     return PB_OK;

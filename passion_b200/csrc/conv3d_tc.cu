@@ -1,0 +1,395 @@
+// 3x3x3 stride-1 convolution as a tcgen05 implicit GEMM (sm_100a), bf16 operands, fp32 accumulation in TMEM.
+//
+// Replaces nn.Conv3d(k=3, padding_mode='reflect') of general_conv3d (reference models/blocks.py:357) for the
+// channel classes that carry 95 % of the FLOPs, forward and (with flipped/transposed
+// weights and zero padding) the data gradient.
+//
+// GEMM view per output voxel tile:  D[128 voxels x NT] += A[128 x 16] * B[16 x NT]  for each of the 27 taps and each
+// 16-channel K step.  Tile = 128 CONSECUTIVE positions q = h*PW + w of the padded-pitch plane (PW = W + 2), so that for
+// every tap (kd,kh,kw) the A operand is simply the same 128-row window of the staged input plane d+kd shifted by
+// kh*PW + kw rows: no im2col expansion in shared memory, one staged copy serves all 27 taps.
+//   * smem A layout: channel-chunk planes [chunk of 8 ch][row] with 16 B per row -> the canonical no-swizzle K-major
+//     UMMA layout (8 rows x 16 B core matrices, SBO = 128 B between row groups, LBO = plane pitch between the two
+//     8-channel halves of a K=16 step); the UMMA descriptor's start address selects tap and plane.
+//   * a CTA sweeps along d: a ring of input planes lives in smem, each plane is fetched once per sweep
+//     (cp.async 16 B copies; reflect / zero padding and the two-source channel concat are resolved in the address
+//     computation), the weights of the CTA's (group, Cout tile) are fetched once with a TMA bulk copy.
+//   * warp roles: warps 0-3 epilogue (TMEM -> registers -> bf16 NDHWC stores + InstanceNorm partial sums),
+//     warp 4 single-thread tcgen05.mma issue + TMEM allocation, warps 5-7 producers.  Two TMEM accumulator stages
+//     overlap the epilogue of plane d with the MMAs of plane d+1.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kProducerThreads = 96;
+constexpr int kLag = 3;                 // cp.async plane groups in flight per producer thread
+constexpr int kSlots = kLag + 3;        // ring depth needed for deadlock freedom (see producer loop)
+constexpr int kTileM = 128;
+
+struct TcP {
+    int N, D, H, W, C0, C1, CO0, CO1;   // inputs x0|x1 (concat), outputs y0|y1 (split)
+    int reflect;
+    int PW, QT, DCH, ND, npg, groups;
+    int slab_need, slab_e;              // rows needed / padded rows per chunk plane of a slab
+    int nt_tiles;
+    long long w_tile_bytes;             // bytes of one (group, Cout tile) weight image
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU.  On timeout (~2 s) an error code is published and every
+// later wait returns immediately, so the kernel drains (with garbage results) and the host reports the failure.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (*err != 0) return;
+        if (clock64() - t0 > 4000000000LL) { atomicCAS((int*)err, 0, code); return; }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// UMMA shared-memory descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 | [46,48) version
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ULL << 46);
+}
+// instruction descriptor for kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// NCHR = real input chunks of 8 channels (1,2,4,8); NT = Cout tile (16 or 32)
+template <int NCHR, int NT>
+__global__ void __launch_bounds__(kThreads, 1) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                               const bf16* __restrict__ wimg, bf16* __restrict__ y0,
+                                                               bf16* __restrict__ y1, double* __restrict__ stats, int* err) {
+    constexpr int NCH = NCHR < 2 ? 2 : NCHR;             // a K=16 MMA step needs two 8-channel chunks (zero chunk if Cin = 8)
+    constexpr int KS = NCH / 2;
+    constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
+    constexpr uint32_t IDESC = umma_idesc(kTileM, NT);
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int w_bytes = 27 * NCH * NT * 16;
+    uint8_t* w_s = smem;
+    const int slot_bytes = NCH * p.slab_e * 16;
+    uint8_t* slab_s = smem + ((w_bytes + 127) & ~127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab_s + (size_t)kSlots * slot_bytes);
+    uint64_t* full = bars;                   // [kSlots]  producers -> MMA
+    uint64_t* empty = bars + kSlots;         // [kSlots]  MMA -> producers
+    uint64_t* acc_full = bars + 2 * kSlots;  // [2]       MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;      // [2]       epilogue -> MMA
+    uint64_t* wbar = acc_empty + 2;          // weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.y, nt = blockIdx.z;
+    const int items = p.npg * p.QT * p.ND;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kProducerThreads); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (NCHR < 2) {                          // zero the dummy chunk plane of every slot once
+        for (int i = threadIdx.x; i < kSlots * p.slab_e; i += kThreads) {
+            const int s = i / p.slab_e, e = i % p.slab_e;
+            *reinterpret_cast<uint4*>(slab_s + (size_t)s * slot_bytes + ((size_t)p.slab_e + e) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 5) {
+        // =============================== producers ===============================
+        const int pt = threadIdx.x - 5 * 32;
+        const int c0ch = p.C0 >> 3;
+        const int copies = p.slab_need * NCHR;
+        uint32_t k = 0;                                        // running plane counter (whole kernel)
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
+            const int d0 = dc * p.DCH, q0 = qt * kTileM;
+            const int nout = min(p.DCH, p.D - d0);
+            for (int pl = 0; pl < nout + 2; ++pl, ++k) {
+                const int slot = k % kSlots;
+                mbar_wait(&empty[slot], ((k / kSlots) & 1) ^ 1, err, 1);
+                int dp = d0 - 1 + pl;
+                bool plane_ok = true;
+                if (p.reflect) dp = reflect_idx(dp, p.D); else plane_ok = dp >= 0 && dp < p.D;
+                const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
+                for (int idx = pt; idx < copies; idx += kProducerThreads) {
+                    const int ch = idx % NCHR, e = idx / NCHR;
+                    const int f = q0 + e;
+                    const int hp = f / p.PW, wp = f - hp * p.PW;
+                    int h = hp - 1, w = wp - 1;
+                    bool ok = plane_ok && hp < p.H + 2;
+                    if (p.reflect) { h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); ok = ok && h >= 0 && h < p.H; }
+                    else ok = ok && h >= 0 && h < p.H && w >= 0 && w < p.W;
+                    const bf16* src = x0;
+                    if (ok) {
+                        const size_t vox = (((size_t)n * p.D + dp) * p.H + h) * p.W + w;
+                        src = ch < c0ch ? x0 + vox * p.C0 + ch * 8 : x1 + vox * p.C1 + (ch - c0ch) * 8;
+                    }
+                    cp_async16(sbase + (uint32_t)(ch * p.slab_e + e) * 16, src, ok ? 16u : 0u);
+                }
+                cp_async_commit();
+                if (k >= kLag) {
+                    cp_async_wait<kLag>();
+                    fence_proxy_async();
+                    mbar_arrive(&full[(k - kLag) % kSlots]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (uint32_t j = (k >= kLag ? k - kLag : 0); j < k; ++j) mbar_arrive(&full[j % kSlots]);
+    } else if (warp == 4) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const bf16* wsrc = wimg + ((size_t)(g * p.nt_tiles + nt) * w_bytes) / 2;
+            mbar_expect_tx(wbar, (uint32_t)w_bytes);
+            for (int off = 0; off < w_bytes; off += 16384) {
+                const int nb = min(16384, w_bytes - off);
+                bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
+            }
+            mbar_wait(wbar, 0, err, 2);
+            const uint32_t w_addr = smem_u32(w_s), slab_addr = smem_u32(slab_s);
+            uint32_t k = 0, j = 0;
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int dc = it % p.ND;
+                const int nout = min(p.DCH, p.D - dc * p.DCH);
+                for (int od = 0; od < nout; ++od, ++j) {
+                    const int first_wait = od == 0 ? 0 : 2;
+                    for (int kd = first_wait; kd < 3; ++kd) {
+                        const uint32_t kk = k + od + kd;
+                        mbar_wait(&full[kk % kSlots], (kk / kSlots) & 1, err, 3);
+                    }
+                    const int stage = j & 1;
+                    mbar_wait(&acc_empty[stage], ((j >> 1) & 1) ^ 1, err, 4);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + stage * NT;
+                    uint32_t acc = 0;
+#pragma unroll 1
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const uint32_t sb = slab_addr + ((k + od + kd) % kSlots) * slot_bytes;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const int tap = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+                                for (int ks = 0; ks < KS; ++ks) {
+                                    const uint64_t ad = umma_desc(sb + (uint32_t)(2 * ks * p.slab_e + kh * p.PW + kw) * 16,
+                                                                  (uint32_t)p.slab_e * 16, 128);
+                                    const uint64_t bd = umma_desc(w_addr + (uint32_t)((tap * NCH + 2 * ks) * NT) * 16, NT * 16, 128);
+                                    umma_f16(d_tmem, ad, bd, IDESC, acc);
+                                    acc = 1;
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(&acc_full[stage]);
+                    umma_commit(&empty[(k + od) % kSlots]);                 // plane od is not needed any more
+                    if (od == nout - 1) {
+                        umma_commit(&empty[(k + od + 1) % kSlots]);
+                        umma_commit(&empty[(k + od + 2) % kSlots]);
+                    }
+                }
+                k += nout + 2;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue (warps 0-3 = TMEM lane quadrants) ===============================
+        const int cout = p.CO0 + p.CO1;
+        const int cb0 = nt * NT;
+        const int creal = min(NT, cout - cb0);                 // real channels in this tile (multiple of 8)
+        uint32_t j = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
+            const int d0 = dc * p.DCH;
+            const int nout = min(p.DCH, p.D - d0);
+            const int f = qt * kTileM + warp * 32 + lane;
+            const int h = f / p.PW, w = f - h * p.PW;
+            const bool valid = h < p.H && w < p.W;
+            float s1[NT], s2[NT];
+#pragma unroll
+            for (int c = 0; c < NT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+            for (int od = 0; od < nout; ++od, ++j) {
+                const int stage = j & 1;
+                mbar_wait(&acc_full[stage], (j >> 1) & 1, err, 5);
+                tc_fence_after();
+                float v[NT];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * NT;
+#pragma unroll
+                for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, v + c);
+                tc_fence_before();
+                mbar_arrive(&acc_empty[stage]);
+                if (valid) {
+                    const size_t vox = (((size_t)n * p.D + d0 + od) * p.H + h) * p.W + w;
+#pragma unroll
+                    for (int c8 = 0; c8 < NT / 8; ++c8) {
+                        if (c8 * 8 < creal) {
+                            const int cb = cb0 + c8 * 8;
+                            bf16* dst = cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0);
+                            VecIO<bf16, 8>::store(dst, v + c8 * 8);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) { s1[c8 * 8 + c] += v[c8 * 8 + c]; s2[c8 * 8 + c] += v[c8 * 8 + c] * v[c8 * 8 + c]; }
+                        }
+                    }
+                }
+            }
+            if (stats != nullptr) {
+#pragma unroll
+                for (int c = 0; c < NT; ++c) {
+                    const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+                    if (lane == 0 && c < creal) {
+                        atomicAdd(&stats[((size_t)n * cout + cb0 + c) * 2], (double)a);
+                        atomicAdd(&stats[((size_t)n * cout + cb0 + c) * 2 + 1], (double)b);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+template <int NCHR, int NT>
+int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, void* y0, void* y1, double* stats, int* err,
+              cudaStream_t st) {
+    constexpr int NCH = NCHR < 2 ? 2 : NCHR;
+    const size_t w_bytes = (size_t)27 * NCH * NT * 16;
+    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 5) * 8 + 16;
+    auto kern = conv3_tc_kernel<NCHR, NT>;
+    if (smem > 227 * 1024) { pb_set_error("conv3d_tc: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pb_set_error("conv3d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
+    const int items = p.npg * p.QT * p.ND;
+    int ctas = 148 / (p.groups * p.nt_tiles);
+    if (smem <= 110 * 1024) ctas *= 2;
+    if (ctas < 1) ctas = 1;
+    if (ctas > items) ctas = items;
+    kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg,
+                                                                    (bf16*)y0, (bf16*)y1, stats, err);
+    return 0;
+}
+
+}  // namespace
+
+// Weight image layout expected by the kernel: [groups][cout tiles][27 taps][NCH chunks][NT rows][8 channels] bf16,
+// NCH = max(2, (c0+c1)/8), NT = pb_conv3d_tc_ntile(cout); rows beyond Cout and the padding chunk are zero.
+extern "C" int pb_conv3d_tc_ntile(int cin, int cout) {
+    if (cin % 8 || cout % 8 || cin > 64 || cin < 8 || cout < 8) return 0;
+    if (cout >= 32 && cin <= 32) return 32;      // cin = 64 keeps NT = 16: weights + plane ring must fit 227 KB
+    return 16;
+}
+
+extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, void* y0, void* y1,
+                            int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
+    PB_CHECK_ARG(d && x0 && wimg && y0 && err_flag, "null pointer");
+    PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 3 && d->stride == 1, "bf16, 3x3x3, stride 1 only");
+    PB_CHECK_ARG(d->di == d->dout && d->hi == d->ho && d->wi == d->wo, "same-size output only");
+    const int cin = d->c0 + d->c1, cout = co0 + co1;
+    PB_CHECK_ARG(cout == d->cout && co0 % 8 == 0 && co1 % 8 == 0 && (co1 == 0 || y1), "bad output split");
+    PB_CHECK_ARG(d->c0 % 8 == 0 && d->c1 % 8 == 0 && (d->c1 == 0 || x1), "channels must be multiples of 8");
+    const int NT = pb_conv3d_tc_ntile(cin, cout);
+    PB_CHECK_ARG(NT != 0, "unsupported channel class");
+    PB_CHECK_ARG(d->groups >= 1 && d->n % d->groups == 0, "bad groups");
+    TcP p;
+    p.N = d->n; p.D = d->di; p.H = d->hi; p.W = d->wi; p.C0 = d->c0; p.C1 = d->c1; p.CO0 = co0; p.CO1 = co1;
+    p.reflect = d->pad_mode == PB_PAD_REFLECT;
+    PB_CHECK_ARG(!p.reflect || (p.D >= 2 && p.H >= 2 && p.W >= 2), "reflect padding needs size >= 2");
+    p.PW = p.W + 2;
+    p.QT = (p.H * p.PW + kTileM - 1) / kTileM;
+    p.npg = d->n / d->groups; p.groups = d->groups;
+    p.nt_tiles = (cout + NT - 1) / NT;
+    // depth chunking: enough work items to balance ~2 waves of CTAs, chunks of at least 8 planes
+    const int target = 148 * 4 / (p.groups * p.nt_tiles);
+    int nd = 1;
+    while (p.npg * p.QT * nd < target && (p.D + nd) / (nd + 1) >= 8) ++nd;
+    p.DCH = (p.D + nd - 1) / nd;
+    p.ND = (p.D + p.DCH - 1) / p.DCH;
+    p.slab_need = kTileM + 2 * p.PW + 2;
+    const int nchr = cin / 8, nch = nchr < 2 ? 2 : nchr;
+    // pad the plane pitch so that the nch chunk planes start in different shared-memory banks
+    const int want = nch >= 8 ? 1 : 8 / nch;
+    int se = p.slab_need;
+    while (se % 8 != want % 8) ++se;
+    p.slab_e = se;
+    p.w_tile_bytes = (long long)27 * nch * NT * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = PB_EUNSUPPORTED;
+#define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, y0, y1, stats, err_flag, st)
+    TC_CASE(1, 16); TC_CASE(2, 16); TC_CASE(4, 16); TC_CASE(8, 16);
+    TC_CASE(1, 32); TC_CASE(2, 32); TC_CASE(4, 32); TC_CASE(8, 32);
+#undef TC_CASE
+    if (rc) { if (rc == PB_EUNSUPPORTED) pb_set_error("conv3d_tc: no kernel for cin %d cout %d", cin, cout); return rc; }
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

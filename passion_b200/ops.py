@@ -4,6 +4,7 @@ All activations are dense channels-last tensors of shape [N, D, H, W, C] ("cl"),
 (check mode) or bfloat16.  Every op requires CUDA tensors; there is no eager/CPU fallback.
 """
 import ctypes
+import os
 
 import torch
 
@@ -96,6 +97,49 @@ def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
     return d
 
 
+# ---- tcgen05 implicit-GEMM path (csrc/conv3d_tc.cu) ------------------------------------------------------
+TC_ENABLED = os.environ.get("PB_TC", "1") != "0"
+_tc_err = {}
+
+
+def _tc_err_flag(device):
+    t = _tc_err.get(device)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _tc_err[device] = t
+    return t
+
+
+def check_tc_errors():
+    """Synchronises and raises if any tcgen05 conv launch reported an internal pipeline time-out."""
+    for dev, t in _tc_err.items():
+        code = int(t.item())
+        if code:
+            t.zero_()
+            raise RuntimeError(f"passion_b200: conv3d_tc pipeline time-out (code {code}) on {dev}")
+
+
+def _tc_ntile(cin, cout):
+    return int(_lib.load().pb_conv3d_tc_ntile(cin, cout))
+
+
+def _tc_eligible(dtype, ksize, stride, c0, c1, cout):
+    return (TC_ENABLED and dtype == torch.bfloat16 and ksize == 3 and stride == 1 and c0 % 8 == 0 and c1 % 8 == 0
+            and cout % 8 == 0 and _tc_ntile(c0 + c1, cout) != 0)
+
+
+def tc_weight_image(w, nt):
+    """fp32 [G, 27, cin, cout] -> bf16 image [G, cout tiles, 27, max(2, cin/8), nt, 8] (zero padded)."""
+    G, taps, cin, cout = w.shape
+    nchr = cin // 8
+    nch = max(2, nchr)
+    tiles = (cout + nt - 1) // nt
+    img = torch.zeros((G, taps, nch, 8, tiles * nt), dtype=torch.float32, device=w.device)
+    img[:, :, :nchr, :, :cout] = w.reshape(G, taps, nchr, 8, cout)
+    img = img.view(G, taps, nch, 8, tiles, nt).permute(0, 4, 1, 2, 5, 3)
+    return img.to(torch.bfloat16).contiguous()
+
+
 class _Conv3d(torch.autograd.Function):
     """y = conv(cat(x0, x1), w) (+ bias); optionally also the per-(n,c) sum / sum-of-squares of y."""
 
@@ -110,8 +154,15 @@ class _Conv3d(torch.autograd.Function):
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
         stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
         key, nb, fl = _conv_work(d, x0.element_size())
-        _run("conv3d_fwd", key, nb, fl,
-             lambda: lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(w), _p(bias), _p(y), _p(stats), _stream()))
+        if bias is None and _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
+            img = tc_weight_image(w, _tc_ntile(d.c0 + d.c1, cout))
+            err = _tc_err_flag(x0.device)
+            _run("conv3d_fwd_tc", key, nb, fl,
+                 lambda: lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y), None, cout, 0, _p(stats),
+                                          _p(err), _stream()))
+        else:
+            _run("conv3d_fwd", key, nb, fl,
+                 lambda: lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(w), _p(bias), _p(y), _p(stats), _stream()))
         ctx.save_for_backward(x0, x1, w)
         ctx.cfg = (ksize, stride, pad_mode, groups, bias is not None)
         if want_stats:
@@ -133,8 +184,23 @@ class _Conv3d(torch.autograd.Function):
             wt = w.transpose(2, 3).contiguous()
             dx0 = torch.empty_like(x0)
             dx1 = torch.empty_like(x1) if x1 is not None else None
-            _run("conv3d_dgrad", key, nb, fl,
-                 lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
+            if _tc_eligible(dy.dtype, ksize, stride, d.cout, 0, d.c0 + d.c1) and d.c0 % 8 == 0 and d.c1 % 8 == 0:
+                # data gradient = the same implicit GEMM on dy with flipped taps / transposed channels and zero
+                # padding; the reflected-halo terms are added by a thin boundary kernel
+                wflip = w.flip(1).transpose(2, 3)
+                img = tc_weight_image(wflip, _tc_ntile(d.cout, d.c0 + d.c1))
+                dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0,
+                              cout=d.c0 + d.c1, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
+                err = _tc_err_flag(dy.device)
+                _run("conv3d_dgrad_tc", key, nb, fl,
+                     lambda: lib.pb_conv3d_tc(ctypes.byref(dd), _p(dy), None, _p(img), _p(dx0), _p(dx1), d.c0, d.c1, None,
+                                              _p(err), _stream()))
+                if pad_mode == "reflect":
+                    _run("conv3d_dgrad_fix", key, 0, 0,
+                         lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
+            else:
+                _run("conv3d_dgrad", key, nb, fl,
+                     lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
         if ctx.needs_input_grad[2]:
             dw = torch.zeros_like(w)
             _run("conv3d_wgrad", key, nb, fl,

@@ -42,6 +42,14 @@ CONV_CASES = [
     (8, 8, 16, 1, 1, "zeros", 1, 3, (5, 6, 7), False),
     (2, 0, 8, 1, 1, "zeros", 1, 2, (6, 6, 6), False),
     (128, 0, 32, 1, 1, "zeros", 1, 2, (4, 4, 4), False),
+    # larger volumes: several q-tiles / depth chunks of the tcgen05 path (bf16) and of the wgrad tiling
+    (16, 0, 8, 3, 1, "reflect", 1, 3, (24, 20, 22), False),
+    (8, 0, 8, 3, 1, "reflect", 4, 4, (18, 16, 20), False),
+    (8, 8, 8, 3, 1, "reflect", 1, 2, (17, 13, 19), False),
+    (32, 0, 32, 3, 1, "reflect", 1, 2, (10, 12, 10), False),
+    (16, 16, 16, 3, 1, "zeros", 1, 2, (12, 10, 14), False),
+    (64, 0, 32, 3, 1, "reflect", 1, 2, (8, 10, 6), False),
+    (16, 0, 64, 3, 1, "reflect", 2, 2, (6, 8, 10), False),
 ]
 
 
@@ -59,7 +67,9 @@ def test_conv3d(lib_built, case, dtype):
     xq = x.to(dtype)                                   # the kernel sees dtype-rounded activations
     # ---- float64 reference on the same (rounded) inputs
     xr = xq.double().requires_grad_(True)
-    wr = wt.double().requires_grad_(True)
+    # the tcgen05 path multiplies bf16 weights (fp32 accumulate); give the reference the same rounded operands
+    uses_tc = ops._tc_eligible(dtype, k, stride, c0, c1, cout) and not has_bias
+    wr = (wt.to(torch.bfloat16) if uses_tc else wt).double().requires_grad_(True)
     ys = []
     npg = n // groups
     for gi in range(groups):
@@ -91,6 +101,7 @@ def test_conv3d(lib_built, case, dtype):
     assert rel(wk.grad, dwr) < (5e-5 if dtype == torch.float32 else tol)
     if has_bias:
         assert rel(bk.grad, gy.double().sum((0, 2, 3, 4))[None]) < 1e-3
+    ops.check_tc_errors()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
