@@ -126,6 +126,41 @@ int pb_rfm_mix_bwd_gate(int dtype, const void* y, const float* p, const void* dr
 int pb_rfm_bwd_y(int dtype, const float* p, const float* gate, const void* dr, const float* dS,
                  void* dy, int n, long long voxels, int k, int c, pb_stream_t stream);
 
+/* ---- PASSION objective (utils/criterions.py:25-38, 59-76, 92-103, 144-180), csrc/loss.cu --------------------
+ * The loss kernels read class LABELS (uint8 [b][V]) instead of the float64 one-hot target; sample n of a prediction
+ * batch uses the labels / teacher of sample n % b (the 5B / 4B batched decoder passes).  Probabilities are float32
+ * [n][V][4] at label resolution (low-resolution PRM heads are first brought there by pb_upsample_fwd, the
+ * reference's up_op).  All sums are float64 and must be zero-filled by the caller.
+ *   pb_softmax4      probs = softmax(logits * inv_temp) over the 4 classes (storage dtype in, f32 out)   (:93-94)
+ *   pb_cedice_fwd    sums[n][12]: A_c = sum p_c t_c | L_c = sum p_c | E_c = sum t_c log(clamp(p_c,.005,1)) (:30-32, :69)
+ *   pb_cedice_bwd    dprobs[n][V][4] = coef[n][4+c] + [t==c](coef[n][c] + coef[n][8+c] * d log clamp / dp)
+ *   pb_kl_fwd/bwd    sums[n] = sum_{v,c} pt (log pt - log ps), both clamped to [.005, 1]; dps = coef[n] * d/dps (:98-101)
+ *   pb_proto_sums    P[n][4][8] = sum_v f[v] [t_v == i]                                                  (:158-159)
+ *   pb_proto_fwd     out[n][2] = sum over present classes and voxels of (d^2, |d|), d = cos(fs,Ps_i) - cos(ft,Pt_i) (:161-178)
+ *   pb_proto_bwd1    dfs (direct term) and dPs[n][4][8] given coef[n] = dL/d(sum d^2)
+ *   pb_proto_bwd2    dfs[v] += dproto[n][t_v]  (gradient through the masked class means)
+ */
+int pb_softmax4(int dtype, const void* logits, float* probs, long long rows, float inv_temp, pb_stream_t stream);
+int pb_softmax4_bwd(int dtype, const float* probs, const float* dprobs, void* dlogits, long long rows,
+                    float inv_temp, pb_stream_t stream);
+int pb_cedice_fwd(const float* probs, const uint8_t* labels, double* sums, int n, int b, long long voxels,
+                  pb_stream_t stream);
+int pb_cedice_bwd(const float* probs, const uint8_t* labels, const float* coef, float* dprobs, int n, int b,
+                  long long voxels, pb_stream_t stream);
+int pb_kl_fwd(const float* ps, const float* pt, double* sums, int n, int b, long long voxels, pb_stream_t stream);
+int pb_kl_bwd(const float* ps, const float* pt, const float* coef, float* dps, int n, int b, long long voxels,
+              pb_stream_t stream);
+int pb_proto_sums(int dtype, const void* f, const uint8_t* labels, double* P, int n, int b, long long voxels, int c,
+                  pb_stream_t stream);
+int pb_proto_fwd(int dtype, const void* fs, const void* ft, const float* protos, const float* protot,
+                 const float* present, double* out, int n, int b, long long voxels, int c, float eps,
+                 pb_stream_t stream);
+int pb_proto_bwd1(int dtype, const void* fs, const void* ft, const float* protos, const float* protot,
+                  const float* present, const float* coef, void* dfs, double* dprotos, int n, int b,
+                  long long voxels, int c, float eps, pb_stream_t stream);
+int pb_proto_bwd2(int dtype, const uint8_t* labels, const float* dproto, void* dfs, int n, int b, long long voxels,
+                  int c, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,16 @@ def load():
         "pb_inorm_lrelu_bwd": [i32, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp],
         "pb_upsample_fwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "pb_upsample_bwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+        "pb_softmax4": [i32, vp, vp, i64, f32, vp],
+        "pb_softmax4_bwd": [i32, vp, vp, vp, i64, f32, vp],
+        "pb_cedice_fwd": [vp, vp, vp, i32, i32, i64, vp],
+        "pb_cedice_bwd": [vp, vp, vp, vp, i32, i32, i64, vp],
+        "pb_kl_fwd": [vp, vp, vp, i32, i32, i64, vp],
+        "pb_kl_bwd": [vp, vp, vp, vp, i32, i32, i64, vp],
+        "pb_proto_sums": [i32, vp, vp, vp, i32, i32, i64, i32, vp],
+        "pb_proto_fwd": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, vp],
+        "pb_proto_bwd1": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, vp],
+        "pb_proto_bwd2": [i32, vp, vp, vp, i32, i32, i64, i32, vp],
         "pb_rfm_pool": [i32, vp, vp, vp, vp, i32, i64, i32, vp],
         "pb_rfm_mix": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
         "pb_rfm_mix_bwd_gate": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],

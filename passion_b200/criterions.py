@@ -1,21 +1,24 @@
-"""PASSION loss library with the reference's signatures (utils/criterions.py) on CUDA tensors.
+"""PASSION loss library with the reference's signatures (utils/criterions.py) on the fused CUDA kernels of
+csrc/loss.cu.
 
 Public, reference-compatible entry points (all return [B,1] float32, as the reference):
-    dice_loss_bs(output, target, num_cls, eps, up_op)              criterions.py:25-38
-    softmax_weighted_loss_bs(output, target, num_cls, up_op)       criterions.py:59-76
-    temp_kl_loss_bs(logit_s, logit_t, target, num_cls, temp, up_op) criterions.py:92-103
-    prototype_passion_loss_bs(feature_s, feature_t, target, logit_s, logit_t, num_cls, temp, up_op)  :144-180
-`output`/`logit_*`/`feature_*` are [B,C,D,H,W]; `target` is the one-hot [B,num_cls,D,H,W] tensor.
-`up_op` is either None or an integer scale factor / nn.Upsample-like object with .scale_factor.
+    dice_loss_bs(output, target, num_cls, eps, up_op)                                   criterions.py:25-38
+    softmax_weighted_loss_bs(output, target, num_cls, up_op)                            criterions.py:59-76
+    temp_kl_loss_bs(logit_s, logit_t, target, num_cls, temp, up_op)                     criterions.py:92-103
+    prototype_passion_loss_bs(feature_s, feature_t, target, logit_s, logit_t, ...)      criterions.py:144-180
+`output` / `logit_*` / `feature_*` are [B,C,D,H,W]; `target` is the one-hot [B,num_cls,D,H,W] tensor; `up_op` is
+None, an integer scale factor or an nn.Upsample-like object with .scale_factor.
 
-The model does not go through these wrappers: it calls the channels-last (`*_cl`) kernels below
-directly on its internal [N,D,H,W,C] tensors, batched over the five decoder passes.
+The model does not go through these wrappers: it calls the channels-last helpers below directly on its
+internal [N,D,H,W,C] tensors, batched over the decoder passes (prediction sample n pairs with label sample n % B).
+Only tiny [N,4]-sized arithmetic (dice ratio, class weights, means) is left to torch; everything that touches a
+volume is one of: ops.softmax4, ops.upsample, ops.cedice_sums, ops.kl_sums, ops.proto_sums.
 """
 import torch
 
 from . import ops
 
-CLAMP_MIN = 0.005        # criterions.py:69, 98-99
+CLAMP_MIN = 0.005        # criterions.py:69, 98-99 (applied inside the kernels)
 __all__ = ["dice_loss_bs", "softmax_weighted_loss_bs", "temp_kl_loss_bs", "prototype_passion_loss_bs"]
 
 
@@ -35,93 +38,68 @@ def _to_cl(t):
 
 
 def up_probs(p, scale):
-    """trilinear align_corners up-sampling of a cl fp32 tensor by an integer factor (own kernel)."""
+    """trilinear align_corners up-sampling of a channels-last fp32 tensor by an integer factor."""
     return p if scale == 1 else ops.upsample(p, scale)
 
 
-# ------------------------------------------------------------------ channels-last internals
-def target_stats(target_cl):
-    """per-sample class voxel counts [B,C] and CE class weights 1 - count/total (criterions.py:67)."""
-    cnt = target_cl.sum((1, 2, 3))
-    return cnt, 1.0 - cnt / cnt.sum(1, keepdim=True)
+# ------------------------------------------------------------------ channels-last helpers used by the model
+def label_stats(target):
+    """one-hot target [B,C,D,H,W] -> (labels uint8 [B,D,H,W], class voxel counts [B,C] fp32,
+    CE class weights 1 - count/total [B,C] (criterions.py:67))."""
+    labels = target.argmax(1).to(torch.uint8).contiguous()
+    cnt = target.sum((2, 3, 4)).to(torch.float32)
+    return labels, cnt, 1.0 - cnt / cnt.sum(1, keepdim=True)
 
 
-def cedice_cl(prob, target_cl, cnt, wgt, eps=1e-7):
-    """prob [P,B,D,H,W,C] (any leading pass dim) fp32 at label resolution; target_cl [B,D,H,W,C].
-    Returns (ce [P,B], dice [P,B]) following criterions.py:25-38 and :59-76."""
-    t = target_cl[None]
-    dims = (2, 3, 4)
-    num = (prob * t).sum(dims)                                     # [P,B,C]
-    den = prob.sum(dims) + cnt[None] + eps
-    dice = 1.0 - (2.0 * num / den).sum(-1) / prob.shape[-1]
-    logp = torch.log(torch.clamp(prob, CLAMP_MIN, 1.0))
-    voxels = prob.shape[2] * prob.shape[3] * prob.shape[4]
-    ce = -((logp * t).sum(dims) * wgt[None]).sum(-1) / voxels
+def cedice(prob, labels, cnt, wgt, eps=1e-7):
+    """prob [N,D,H,W,4] fp32 at label resolution (N a multiple of B).  Returns (ce [N], dice [N]) following
+    criterions.py:25-38 and :59-76."""
+    n, b = prob.shape[0], labels.shape[0]
+    voxels = labels.numel() // b
+    s = ops.cedice_sums(prob.contiguous(), labels)                     # [N,3,4]: A, L, E
+    cnt_n, wgt_n = cnt.repeat(n // b, 1), wgt.repeat(n // b, 1)
+    dice = 1.0 - (2.0 * s[:, 0] / (s[:, 1] + cnt_n + eps)).sum(1) / prob.shape[-1]
+    ce = -(wgt_n * s[:, 2]).sum(1) / voxels
     return ce, dice
 
 
-def kl_cl(ps, pt, temp):
-    """ps [P,B,D,H,W,C], pt [B,D,H,W,C] (already soft-maxed at temperature and up-sampled).  [P,B]."""
-    ps = torch.clamp(ps, CLAMP_MIN, 1.0)
-    pt = torch.clamp(pt, CLAMP_MIN, 1.0)[None]
-    kl = temp * temp * pt * (torch.log(pt) - torch.log(ps))
-    return kl.mean((2, 3, 4, 5))
+def kl(ps, pt, temp):
+    """ps [N,D,H,W,4], pt [B,D,H,W,4]: fp32 probabilities at temperature `temp`, same resolution.  Returns [N]
+    = T^2 * mean_{c,v} clamp(pt) (log clamp(pt) - log clamp(ps))   (criterions.py:98-102)."""
+    per = ps.numel() // ps.shape[0]
+    return (temp * temp / per) * ops.kl_sums(ps.contiguous(), pt.contiguous())
 
 
-def _cos(f, proto, eps):
-    """F.cosine_similarity(f, proto[..., None], dim=channel, eps) for cl tensors. f [..., V, C], proto [..., 1, C]."""
-    fn = f.norm(dim=-1).clamp_min(eps)
-    pn = proto.norm(dim=-1).clamp_min(eps)
-    return (f * proto).sum(-1) / (fn * pn)
-
-
-def proto_cl(fs, ft, target_cl, cnt, eps=1e-5):
-    """fs [P,B,V,C] student features, ft [B,V,C] teacher features (detached), target_cl [B,V,K] one-hot.
-    Returns proto [P,B], dist [P,B] (criterions.py:144-180; class used iff present in every local sample)."""
-    present = (cnt > 0).all(0).to(fs.dtype)                        # [K]  (:157) — stays on device, no sync
-    n_present = present.sum()
-    den = cnt + eps                                                # [B,K]
-    proto_s = torch.einsum("pbvc,bvk->pbkc", fs, target_cl) / den[None, :, :, None]
-    proto_t = torch.einsum("bvc,bvk->bkc", ft, target_cl) / den[:, :, None]
-    V = fs.shape[2]
-    se = torch.zeros(fs.shape[:2], dtype=fs.dtype, device=fs.device)
-    ab = torch.zeros_like(se)
-    for k in range(target_cl.shape[-1]):
-        s = _cos(fs, proto_s[:, :, k:k + 1, :], eps)              # [P,B,V]
-        t = _cos(ft, proto_t[:, k:k + 1, :], eps)[None]
-        d = s - t
-        se = se + present[k] * (d * d).sum(-1)
-        ab = ab + present[k] * d.abs().sum(-1)
-    return se / (n_present * V), ab / (n_present * V)
+def proto(fs, ft, labels, cnt, eps=1e-5):
+    """fs [N,V,C] student / ft [B,V,C] teacher features -> (proto [N], dist [N])  (criterions.py:144-180)."""
+    se, ab, present = ops.proto_sums(fs.contiguous(), ft.contiguous(), labels, cnt, eps)
+    denom = present.sum() * fs.shape[1]
+    return se / denom, ab / denom
 
 
 # ------------------------------------------------------------------ reference-signature wrappers
 def dice_loss_bs(output, target, num_cls=5, eps=1e-7, up_op=None):
     p = up_probs(_to_cl(output.float()), _scale_of(up_op))
-    t = _to_cl(target.float())
-    cnt, wgt = target_stats(t)
-    return cedice_cl(p[None], t, cnt, wgt, eps)[1][0].unsqueeze(1)
+    labels, cnt, wgt = label_stats(target)
+    return cedice(p, labels, cnt, wgt, eps)[1].unsqueeze(1)
 
 
 def softmax_weighted_loss_bs(output, target, num_cls=5, up_op=None):
     p = up_probs(_to_cl(output.float()), _scale_of(up_op))
-    t = _to_cl(target.float())
-    cnt, wgt = target_stats(t)
-    return cedice_cl(p[None], t, cnt, wgt)[0][0].unsqueeze(1)
+    labels, cnt, wgt = label_stats(target)
+    return cedice(p, labels, cnt, wgt)[0].unsqueeze(1)
 
 
 def temp_kl_loss_bs(logit_s, logit_t, target=None, num_cls=5, temp=1.0, up_op=None):
     s = _scale_of(up_op)
-    ps = up_probs(torch.softmax(_to_cl(logit_s.float()) / temp, -1), s)
-    pt = up_probs(torch.softmax(_to_cl(logit_t.float()) / temp, -1), s)
-    return kl_cl(ps[None], pt, temp)[0].unsqueeze(1)
+    ps = up_probs(ops.softmax4(_to_cl(logit_s), temp), s)
+    pt = up_probs(ops.softmax4(_to_cl(logit_t), temp), s)
+    return kl(ps, pt, temp).unsqueeze(1)
 
 
 def prototype_passion_loss_bs(feature_s, feature_t, target, logit_s=None, logit_t=None, num_cls=5, temp=1.0, up_op=None):
-    fs = _to_cl(feature_s.float())
-    ft = _to_cl(feature_t.float())
-    t = _to_cl(target.float())
+    fs, ft = _to_cl(feature_s), _to_cl(feature_t)
     B, C = fs.shape[0], fs.shape[-1]
-    cnt, _ = target_stats(t)
-    proto, dist = proto_cl(fs.reshape(1, B, -1, C), ft.reshape(B, -1, C), t.reshape(B, -1, t.shape[-1]), cnt)
-    return proto[0].unsqueeze(1), dist[0].unsqueeze(1)
+    labels, cnt, _ = label_stats(target)
+    pl, dist = proto(fs.reshape(B, -1, C), ft.reshape(B, -1, C), labels, cnt)
+    return pl.unsqueeze(1), dist.unsqueeze(1)

@@ -145,13 +145,35 @@ __global__ void __launch_bounds__(128) conv_dgrad_kernel(ConvK p, const T* __res
     __syncthreads();
 
     long long iv = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (iv >= p.Vi) return;
-    const int iw = (int)(iv % p.Wi);
-    const int t1 = (int)(iv / p.Wi);
-    const int ih = t1 % p.Hi, id = t1 / p.Hi;
-    if (MIRROR_ONLY) {      // only voxels one step inside a face receive reflected-halo contributions
-        const bool edge = id == 1 || id == p.Di - 2 || ih == 1 || ih == p.Hi - 2 || iw == 1 || iw == p.Wi - 2;
-        if (!edge) return;
+    int iw, ih, id;
+    if (MIRROR_ONLY) {
+        // Only voxels one step inside a face receive reflected-halo contributions.  Threads enumerate exactly that
+        // shell: (A) id in {1, D-2}; (B) id elsewhere, ih in {1, H-2}; (C) id, ih elsewhere, iw in {1, W-2}.
+        // (host guarantees D, H, W >= 4 for this mode)
+        const long long nA = 2LL * p.Hi * p.Wi, nB = (long long)(p.Di - 2) * 2 * p.Wi, nC = (long long)(p.Di - 2) * (p.Hi - 2) * 2;
+        if (iv >= nA + nB + nC) return;
+        auto inner = [](int j, int D) { return j == 0 ? 0 : (j == D - 3 ? D - 1 : j + 1); };   // j-th index not in {1, D-2}
+        if (iv < nA) {
+            id = iv < (long long)p.Hi * p.Wi ? 1 : p.Di - 2;
+            const int r = (int)(iv % ((long long)p.Hi * p.Wi));
+            ih = r / p.Wi; iw = r % p.Wi;
+        } else if (iv < nA + nB) {
+            const long long r = iv - nA;
+            id = inner((int)(r / (2 * p.Wi)), p.Di);
+            const int r2 = (int)(r % (2 * p.Wi));
+            ih = r2 < p.Wi ? 1 : p.Hi - 2; iw = r2 % p.Wi;
+        } else {
+            const long long r = iv - nA - nB;
+            id = inner((int)(r / (2 * (p.Hi - 2))), p.Di);
+            const int r2 = (int)(r % (2 * (p.Hi - 2)));
+            ih = inner(r2 >> 1, p.Hi); iw = (r2 & 1) ? p.Wi - 2 : 1;
+        }
+        iv = ((long long)id * p.Hi + ih) * p.Wi + iw;
+    } else {
+        if (iv >= p.Vi) return;
+        iw = (int)(iv % p.Wi);
+        const int t1 = (int)(iv / p.Wi);
+        ih = t1 % p.Hi; id = t1 / p.Hi;
     }
 
     float acc[CI_T];
@@ -443,7 +465,9 @@ int launch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, voi
     const size_t smem = (size_t)k.K * k.K * k.K * k.Cout * CI_T * sizeof(float);
     auto kern = mirror_only ? conv_dgrad_kernel<T, CO_V, CI_T, true> : conv_dgrad_kernel<T, CO_V, CI_T, false>;
     if (int e = set_smem(kern, smem)) return e;
-    dim3 grid((unsigned)((k.Vi + 127) / 128), k.Cin / CI_T, k.N);
+    long long work = k.Vi;
+    if (mirror_only) work = 2LL * k.Hi * k.Wi + (long long)(k.Di - 2) * 2 * k.Wi + (long long)(k.Di - 2) * (k.Hi - 2) * 2;
+    dim3 grid((unsigned)((work + 127) / 128), k.Cin / CI_T, k.N);
     kern<<<grid, 128, smem, st>>>(k, (const T*)dy, wt, (T*)dx0, (T*)dx1);
     return 0;
 }
@@ -587,6 +611,7 @@ extern "C" int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy
     PB_CHECK_ARG(fill(d, k) == 0, "bad descriptor");
     PB_CHECK_ARG(dy && wt && dx0 && (d->c1 == 0 || dx1), "null pointer");
     if (!k.reflect) return PB_OK;
+    if (k.Di < 4 || k.Hi < 4 || k.Wi < 4 || k.S != 1) { pb_set_error("reflect_fix: needs stride 1 and sizes >= 4"); return PB_EUNSUPPORTED; }
     int e = d->dtype == PB_BF16 ? dispatch_dgrad<bf16>(k, dy, wt, dx0, dx1, (cudaStream_t)stream, true)
                                 : dispatch_dgrad<float>(k, dy, wt, dx0, dx1, (cudaStream_t)stream, true);
     if (e) return e;

@@ -23,8 +23,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kProducerThreads = 96;
-constexpr int kLag = 3;                 // cp.async plane groups in flight per producer thread
-constexpr int kSlots = kLag + 3;        // ring depth needed for deadlock freedom (see producer loop)
+constexpr int kSlots = 6;               // input-plane ring: 3 planes in use by the MMAs + 3 planes of prefetch
+constexpr int kMaxCopies = 16;          // 16-B copies per producer thread and plane
 constexpr int kTileM = 128;
 
 struct TcP {
@@ -61,17 +61,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err, int code) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (*err != 0) return;
-        if (clock64() - t0 > 4000000000LL) { atomicCAS((int*)err, 0, code); return; }
+        if ((++spins & 255u) == 0) {
+            if (*err != 0) return;
+            if (clock64() - t0 > 4000000000LL) { atomicCAS((int*)err, 0, code); return; }
+        }
     }
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// arrive on `bar` once all cp.async copies issued so far by this thread have landed (counts as one expected arrival)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -114,7 +121,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 // NCHR = real input chunks of 8 channels (1,2,4,8); NT = Cout tile (16 or 32)
 template <int NCHR, int NT>
-__global__ void __launch_bounds__(kThreads, 1) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+__global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                                const bf16* __restrict__ wimg, bf16* __restrict__ y0,
                                                                bf16* __restrict__ y1, double* __restrict__ stats, int* err) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;             // a K=16 MMA step needs two 8-channel chunks (zero chunk if Cin = 8)
@@ -162,6 +169,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_tc_kernel(TcP p, const bf16
 
     if (warp >= 5) {
         // =============================== producers ===============================
+        // The (h, w) geometry of a slab row depends only on the q-tile, so each thread resolves its <= kMaxCopies
+        // copies (source offset inside a plane, padding, destination) once per work item and then streams planes.
         const int pt = threadIdx.x - 5 * 32;
         const int c0ch = p.C0 >> 3;
         const int copies = p.slab_need * NCHR;
@@ -171,39 +180,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_tc_kernel(TcP p, const bf16
             const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
             const int d0 = dc * p.DCH, q0 = qt * kTileM;
             const int nout = min(p.DCH, p.D - d0);
+            int soff[kMaxCopies];                              // element offset inside the source plane, -1 = zero fill
+            uint32_t doff[kMaxCopies];                         // byte offset inside the slot
+            uint32_t from1 = 0;
+#pragma unroll
+            for (int i = 0; i < kMaxCopies; ++i) {
+                const int idx = pt + i * kProducerThreads;
+                soff[i] = -1; doff[i] = 0;
+                if (idx < copies) {
+                    const int ch = idx % NCHR, e = idx / NCHR;
+                    const int f = q0 + e;
+                    const int hp = f / p.PW, wp = f - hp * p.PW;
+                    int h = hp - 1, w = wp - 1;
+                    bool ok = hp < p.H + 2;
+                    if (p.reflect) { h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); ok = ok && h >= 0 && h < p.H; }
+                    else ok = ok && h >= 0 && h < p.H && w >= 0 && w < p.W;
+                    doff[i] = (uint32_t)(ch * p.slab_e + e) * 16;
+                    if (ok) {
+                        if (ch < c0ch) soff[i] = (h * p.W + w) * p.C0 + ch * 8;
+                        else { soff[i] = (h * p.W + w) * p.C1 + (ch - c0ch) * 8; from1 |= 1u << i; }
+                    }
+                }
+            }
             for (int pl = 0; pl < nout + 2; ++pl, ++k) {
                 const int slot = k % kSlots;
                 mbar_wait(&empty[slot], ((k / kSlots) & 1) ^ 1, err, 1);
                 int dp = d0 - 1 + pl;
                 bool plane_ok = true;
                 if (p.reflect) dp = reflect_idx(dp, p.D); else plane_ok = dp >= 0 && dp < p.D;
+                if (!plane_ok) dp = 0;
+                const size_t plane = ((size_t)n * p.D + dp) * p.H * p.W;
+                const bf16* p0 = x0 + plane * p.C0;
+                const bf16* p1 = x1 + plane * p.C1;
                 const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
-                for (int idx = pt; idx < copies; idx += kProducerThreads) {
-                    const int ch = idx % NCHR, e = idx / NCHR;
-                    const int f = q0 + e;
-                    const int hp = f / p.PW, wp = f - hp * p.PW;
-                    int h = hp - 1, w = wp - 1;
-                    bool ok = plane_ok && hp < p.H + 2;
-                    if (p.reflect) { h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); ok = ok && h >= 0 && h < p.H; }
-                    else ok = ok && h >= 0 && h < p.H && w >= 0 && w < p.W;
-                    const bf16* src = x0;
-                    if (ok) {
-                        const size_t vox = (((size_t)n * p.D + dp) * p.H + h) * p.W + w;
-                        src = ch < c0ch ? x0 + vox * p.C0 + ch * 8 : x1 + vox * p.C1 + (ch - c0ch) * 8;
+#pragma unroll
+                for (int i = 0; i < kMaxCopies; ++i) {
+                    if (pt + i * kProducerThreads < copies) {
+                        const bool ok = plane_ok && soff[i] >= 0;
+                        const bf16* src = ((from1 >> i) & 1u) ? p1 : p0;
+                        cp_async16(sbase + doff[i], ok ? src + soff[i] : x0, ok ? 16u : 0u);
                     }
-                    cp_async16(sbase + (uint32_t)(ch * p.slab_e + e) * 16, src, ok ? 16u : 0u);
                 }
-                cp_async_commit();
-                if (k >= kLag) {
-                    cp_async_wait<kLag>();
-                    fence_proxy_async();
-                    mbar_arrive(&full[(k - kLag) % kSlots]);
-                }
+                cp_async_arrive_noinc(&full[slot]);
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (uint32_t j = (k >= kLag ? k - kLag : 0); j < k; ++j) mbar_arrive(&full[j % kSlots]);
+        cp_async_wait_all();
     } else if (warp == 4) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
@@ -214,7 +235,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_tc_kernel(TcP p, const bf16
                 bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
             }
             mbar_wait(wbar, 0, err, 2);
-            const uint32_t w_addr = smem_u32(w_s), slab_addr = smem_u32(slab_s);
+            const uint32_t slab_addr = smem_u32(slab_s);
+            const uint64_t b0 = umma_desc(smem_u32(w_s), NT * 16, 128);
             uint32_t k = 0, j = 0;
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
@@ -227,22 +249,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_tc_kernel(TcP p, const bf16
                     }
                     const int stage = j & 1;
                     mbar_wait(&acc_empty[stage], ((j >> 1) & 1) ^ 1, err, 4);
+                    fence_proxy_async();                       // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + stage * NT;
                     uint32_t acc = 0;
 #pragma unroll 1
                     for (int kd = 0; kd < 3; ++kd) {
                         const uint32_t sb = slab_addr + ((k + od + kd) % kSlots) * slot_bytes;
+                        const uint64_t a0 = umma_desc(sb, (uint32_t)p.slab_e * 16, 128);
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
                             for (int kw = 0; kw < 3; ++kw) {
                                 const int tap = (kd * 3 + kh) * 3 + kw;
+                                const uint64_t a1 = a0 + (uint64_t)(uint32_t)(kh * p.PW + kw);       // address field is in 16 B units
 #pragma unroll
                                 for (int ks = 0; ks < KS; ++ks) {
-                                    const uint64_t ad = umma_desc(sb + (uint32_t)(2 * ks * p.slab_e + kh * p.PW + kw) * 16,
-                                                                  (uint32_t)p.slab_e * 16, 128);
-                                    const uint64_t bd = umma_desc(w_addr + (uint32_t)((tap * NCH + 2 * ks) * NT) * 16, NT * 16, 128);
+                                    const uint64_t ad = a1 + (uint64_t)(uint32_t)(2 * ks * p.slab_e);
+                                    const uint64_t bd = b0 + (uint64_t)(uint32_t)((tap * NCH + 2 * ks) * NT);
                                     umma_f16(d_tmem, ad, bd, IDESC, acc);
                                     acc = 1;
                                 }
@@ -383,6 +407,10 @@ extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x
     while (se % 8 != want % 8) ++se;
     p.slab_e = se;
     p.w_tile_bytes = (long long)27 * nch * NT * 16;
+    if (p.slab_need * nchr > kMaxCopies * kProducerThreads) {
+        pb_set_error("conv3d_tc: plane slab of %d x %d copies exceeds the producer budget", p.slab_need, nchr);
+        return PB_EUNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
 #define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, y0, y1, stats, err_flag, st)

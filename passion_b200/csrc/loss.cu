@@ -1,0 +1,402 @@
+// PASSION objective kernels (reference utils/criterions.py), channels-last, fp32 math, float64 cross-block sums.
+//   softmax4      : F.softmax(logit / T, dim=1) over the 4 classes                           (:93-94, rfnet.py:286,379)
+//   cedice        : the three per-class sums behind dice_loss_bs (:25-38) and softmax_weighted_loss_bs (:59-76)
+//   kl            : sum_v,c pt (log pt - log ps) with both clamped to [0.005, 1]                (:98-101)
+//   proto_*       : masked class-mean prototypes, cosine-similarity maps, (s-t)^2 and |s-t|      (:144-180)
+// All of them read class LABELS (uint8) instead of the float64 one-hot target; prediction sample n uses the
+// labels of sample n % b (batched decoder passes).  Reductions: per-thread registers -> warp shuffle -> smem ->
+// one float64 atomic per block and quantity.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kClampMin = 0.005f;
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, float* o) { VecIO<T, 4>::load(p, o); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax4_kernel(const T* __restrict__ logits, float* __restrict__ probs, long long rows, float inv_temp) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows; i += (long long)gridDim.x * 256) {
+        float v[4];
+        load4(logits + i * 4, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] *= inv_temp;
+        const float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { v[c] = expf(v[c] - m); s += v[c]; }
+        const float r = 1.f / s;
+        reinterpret_cast<float4*>(probs)[i] = make_float4(v[0] * r, v[1] * r, v[2] * r, v[3] * r);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax4_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ dprobs,
+                                                           T* __restrict__ dlogits, long long rows, float inv_temp) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows; i += (long long)gridDim.x * 256) {
+        const float4 p = reinterpret_cast<const float4*>(probs)[i], g = reinterpret_cast<const float4*>(dprobs)[i];
+        const float dot = p.x * g.x + p.y * g.y + p.z * g.z + p.w * g.w;
+        float o[4] = {inv_temp * p.x * (g.x - dot), inv_temp * p.y * (g.y - dot), inv_temp * p.z * (g.z - dot), inv_temp * p.w * (g.w - dot)};
+        VecIO<T, 4>::store(dlogits + i * 4, o);
+    }
+}
+
+// block-wide sum of NV per-thread values, result valid in threads < NV of warp 0 ... returned through smem `red`
+template <int NV>
+__device__ __forceinline__ void block_reduce_atomic(float* vals, double* dst) {
+    __shared__ float red[8][NV];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float s = warp_sum(vals[i]);
+        if (lane == 0) red[wid][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        atomicAdd(dst + threadIdx.x, (double)s);
+    }
+}
+
+// sums[n][0..3] = A_c = sum p_c t_c ; [4..7] = L_c = sum p_c ; [8..11] = E_c = sum t_c log(clamp(p_c))
+__global__ void __launch_bounds__(256) cedice_fwd_kernel(const float* __restrict__ probs, const uint8_t* __restrict__ labels,
+                                                         double* __restrict__ sums, long long voxels, int b) {
+    const int n = blockIdx.y;
+    const float4* pn = reinterpret_cast<const float4*>(probs) + (size_t)n * voxels;
+    const uint8_t* ln = labels + (size_t)(n % b) * voxels;
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < voxels; v += (long long)gridDim.x * 256) {
+        const float4 p4 = __ldg(pn + v);
+        const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+        const int t = ln[v];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            acc[4 + c] += p[c];
+            if (t == c) { acc[c] += p[c]; acc[8 + c] += logf(fminf(fmaxf(p[c], kClampMin), 1.f)); }
+        }
+    }
+    block_reduce_atomic<12>(acc, sums + (size_t)n * 12);
+}
+
+// dP[n][v][c] = coef[n][4+c] + [t==c] (coef[n][c] + coef[n][8+c] * (clamp passes ? 1/p_c : 0))
+__global__ void __launch_bounds__(256) cedice_bwd_kernel(const float* __restrict__ probs, const uint8_t* __restrict__ labels,
+                                                         const float* __restrict__ coef, float* __restrict__ dprobs,
+                                                         long long voxels, int b, long long total) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int n = (int)(i / voxels);
+        const long long v = i - (long long)n * voxels;
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(probs) + i);
+        const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+        const int t = labels[(size_t)(n % b) * voxels + v];
+        const float* cf = coef + (size_t)n * 12;
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float g = cf[4 + c];
+            if (t == c) g += cf[c] + ((p[c] >= kClampMin && p[c] <= 1.f) ? cf[8 + c] / p[c] : 0.f);
+            o[c] = g;
+        }
+        reinterpret_cast<float4*>(dprobs)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// sums[n] = sum_{v,c} pt (log pt - log ps), both clamped to [0.005, 1]; teacher sample = n % b
+__global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ ps, const float* __restrict__ pt, double* __restrict__ sums,
+                                                     long long voxels, int b) {
+    const int n = blockIdx.y;
+    const float4* sn = reinterpret_cast<const float4*>(ps) + (size_t)n * voxels;
+    const float4* tn = reinterpret_cast<const float4*>(pt) + (size_t)(n % b) * voxels;
+    float acc[1] = {0.f};
+    for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < voxels; v += (long long)gridDim.x * 256) {
+        const float4 s4 = __ldg(sn + v), t4 = __ldg(tn + v);
+        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float tc = fminf(fmaxf(t[c], kClampMin), 1.f), sc = fminf(fmaxf(s[c], kClampMin), 1.f);
+            acc[0] += tc * (logf(tc) - logf(sc));
+        }
+    }
+    block_reduce_atomic<1>(acc, sums + n);
+}
+
+__global__ void __launch_bounds__(256) kl_bwd_kernel(const float* __restrict__ ps, const float* __restrict__ pt, const float* __restrict__ coef,
+                                                     float* __restrict__ dps, long long voxels, int b, long long total) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int n = (int)(i / voxels);
+        const long long v = i - (long long)n * voxels;
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(ps) + i);
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(pt) + (size_t)(n % b) * voxels + v);
+        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, t[4] = {t4.x, t4.y, t4.z, t4.w};
+        const float cf = coef[n];
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float tc = fminf(fmaxf(t[c], kClampMin), 1.f);
+            o[c] = (s[c] >= kClampMin && s[c] <= 1.f) ? -cf * tc / s[c] : 0.f;
+        }
+        reinterpret_cast<float4*>(dps)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------ prototype loss, C = 8 features
+constexpr int PC = 8;
+
+// P[n][i][c] += sum_v f[v][c] [t_v == i]
+template <typename T>
+__global__ void __launch_bounds__(256) proto_sums_kernel(const T* __restrict__ f, const uint8_t* __restrict__ labels, double* __restrict__ P,
+                                                         long long voxels, int b) {
+    const int n = blockIdx.y;
+    const T* fn = f + (size_t)n * voxels * PC;
+    const uint8_t* ln = labels + (size_t)(n % b) * voxels;
+    float acc[4 * PC];
+#pragma unroll
+    for (int i = 0; i < 4 * PC; ++i) acc[i] = 0.f;
+    for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < voxels; v += (long long)gridDim.x * 256) {
+        float x[PC];
+        VecIO<T, PC>::load(fn + v * PC, x);
+        const int t = ln[v];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (t == i) {
+#pragma unroll
+                for (int c = 0; c < PC; ++c) acc[i * PC + c] += x[c];
+            }
+    }
+    block_reduce_atomic<4 * PC>(acc, P + (size_t)n * 4 * PC);
+}
+
+__device__ __forceinline__ float dot8(const float* a, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < PC; ++c) s = fmaf(a[c], b[c], s);
+    return s;
+}
+
+// out[n][0] += sum over present classes, voxels of d^2 ; out[n][1] += |d| ; d = cos(fs, Ps_i) - cos(ft, Pt_i)
+template <typename T>
+__global__ void __launch_bounds__(256) proto_fwd_kernel(const T* __restrict__ fs, const T* __restrict__ ft, const float* __restrict__ protos,
+                                                        const float* __restrict__ protot, const float* __restrict__ present,
+                                                        double* __restrict__ out, long long voxels, int b, float eps) {
+    __shared__ float sp[2][4][PC + 1];                        // prototypes and their clamped norms
+    const int n = blockIdx.y, nb = n % b;
+    if (threadIdx.x < 4 * PC) {
+        sp[0][threadIdx.x / PC][threadIdx.x % PC] = protos[(size_t)n * 4 * PC + threadIdx.x];
+        sp[1][threadIdx.x / PC][threadIdx.x % PC] = protot[(size_t)nb * 4 * PC + threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float* q = sp[threadIdx.x >> 2][threadIdx.x & 3];
+        q[PC] = fmaxf(sqrtf(dot8(q, q)), eps);
+    }
+    __syncthreads();
+    float acc[2] = {0.f, 0.f};
+    const T* fsn = fs + (size_t)n * voxels * PC;
+    const T* ftn = ft + (size_t)nb * voxels * PC;
+    for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < voxels; v += (long long)gridDim.x * 256) {
+        float a[PC], t[PC];
+        VecIO<T, PC>::load(fsn + v * PC, a);
+        VecIO<T, PC>::load(ftn + v * PC, t);
+        const float na = fmaxf(sqrtf(dot8(a, a)), eps), nt = fmaxf(sqrtf(dot8(t, t)), eps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float d = dot8(a, sp[0][i]) / (na * sp[0][i][PC]) - dot8(t, sp[1][i]) / (nt * sp[1][i][PC]);
+            const float w = present[i];
+            acc[0] += w * d * d;
+            acc[1] += w * fabsf(d);
+        }
+    }
+    block_reduce_atomic<2>(acc, out + (size_t)n * 2);
+}
+
+// direct gradient wrt the student features and the reduction for the prototype gradient:
+//   g_i = 2 d_i coef[n] present_i ;  dfs = sum_i g_i (Ps_i/(na nP) - cos_i fs / na^2 [|fs| > eps])
+//   dPs[n][i] += sum_v g_i (fs/(na nP) - cos_i Ps_i / nP^2 [|Ps_i| > eps])
+template <typename T>
+__global__ void __launch_bounds__(256) proto_bwd1_kernel(const T* __restrict__ fs, const T* __restrict__ ft, const float* __restrict__ protos,
+                                                         const float* __restrict__ protot, const float* __restrict__ present,
+                                                         const float* __restrict__ coef, T* __restrict__ dfs, double* __restrict__ dprotos,
+                                                         long long voxels, int b, float eps) {
+    __shared__ float sp[2][4][PC + 2];                        // prototype, clamped norm, raw norm
+    const int n = blockIdx.y, nb = n % b;
+    if (threadIdx.x < 4 * PC) {
+        sp[0][threadIdx.x / PC][threadIdx.x % PC] = protos[(size_t)n * 4 * PC + threadIdx.x];
+        sp[1][threadIdx.x / PC][threadIdx.x % PC] = protot[(size_t)nb * 4 * PC + threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float* q = sp[threadIdx.x >> 2][threadIdx.x & 3];
+        const float r = sqrtf(dot8(q, q));
+        q[PC] = fmaxf(r, eps); q[PC + 1] = r;
+    }
+    __syncthreads();
+    const float cf = coef[n];
+    float dP[4 * PC];
+#pragma unroll
+    for (int i = 0; i < 4 * PC; ++i) dP[i] = 0.f;
+    const T* fsn = fs + (size_t)n * voxels * PC;
+    const T* ftn = ft + (size_t)nb * voxels * PC;
+    T* dn = dfs + (size_t)n * voxels * PC;
+    for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < voxels; v += (long long)gridDim.x * 256) {
+        float a[PC], t[PC], g[PC];
+        VecIO<T, PC>::load(fsn + v * PC, a);
+        VecIO<T, PC>::load(ftn + v * PC, t);
+        const float ra = sqrtf(dot8(a, a));
+        const float na = fmaxf(ra, eps), nt = fmaxf(sqrtf(dot8(t, t)), eps);
+#pragma unroll
+        for (int c = 0; c < PC; ++c) g[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float nP = sp[0][i][PC];
+            const float cs = dot8(a, sp[0][i]) / (na * nP);
+            const float d = cs - dot8(t, sp[1][i]) / (nt * sp[1][i][PC]);
+            const float gi = 2.f * d * cf * present[i];
+            const float k1 = gi / (na * nP);
+            const float k2 = ra > eps ? gi * cs / (na * na) : 0.f;
+            const float k3 = sp[0][i][PC + 1] > eps ? gi * cs / (nP * nP) : 0.f;
+#pragma unroll
+            for (int c = 0; c < PC; ++c) {
+                g[c] += k1 * sp[0][i][c] - k2 * a[c];
+                dP[i * PC + c] += k1 * a[c] - k3 * sp[0][i][c];
+            }
+        }
+        VecIO<T, PC>::store(dn + v * PC, g);
+    }
+    block_reduce_atomic<4 * PC>(dP, dprotos + (size_t)n * 4 * PC);
+}
+
+// dfs[v] += dproto[n][t_v]   (gradient through the masked class means)
+template <typename T>
+__global__ void __launch_bounds__(256) proto_bwd2_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ dproto, T* __restrict__ dfs,
+                                                         long long voxels, int b, long long total) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int n = (int)(i / voxels);
+        const long long v = i - (long long)n * voxels;
+        const int t = labels[(size_t)(n % b) * voxels + v];
+        float g[PC];
+        VecIO<T, PC>::load(dfs + i * PC, g);
+        const float* dp = dproto + ((size_t)n * 4 + t) * PC;
+#pragma unroll
+        for (int c = 0; c < PC; ++c) g[c] += dp[c];
+        VecIO<T, PC>::store(dfs + i * PC, g);
+    }
+}
+
+int ew_blocks(long long work) {
+    long long bl = (work + 255) / 256;
+    if (bl > 148LL * 16) bl = 148LL * 16;
+    return (int)(bl < 1 ? 1 : bl);
+}
+int red_blocks(long long voxels, int n) {
+    long long bl = (voxels + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (148LL * 8 + n - 1) / n;
+    if (bl > cap) bl = cap;
+    return (int)(bl < 1 ? 1 : bl);
+}
+
+}  // namespace
+
+extern "C" int pb_softmax4(int dtype, const void* logits, float* probs, long long rows, float inv_temp, pb_stream_t stream) {
+    PB_CHECK_ARG(logits && probs && rows > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PB_BF16) softmax4_kernel<bf16><<<ew_blocks(rows), 256, 0, st>>>((const bf16*)logits, probs, rows, inv_temp);
+    else softmax4_kernel<float><<<ew_blocks(rows), 256, 0, st>>>((const float*)logits, probs, rows, inv_temp);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_softmax4_bwd(int dtype, const float* probs, const float* dprobs, void* dlogits, long long rows, float inv_temp,
+                               pb_stream_t stream) {
+    PB_CHECK_ARG(probs && dprobs && dlogits && rows > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PB_BF16) softmax4_bwd_kernel<bf16><<<ew_blocks(rows), 256, 0, st>>>(probs, dprobs, (bf16*)dlogits, rows, inv_temp);
+    else softmax4_bwd_kernel<float><<<ew_blocks(rows), 256, 0, st>>>(probs, dprobs, (float*)dlogits, rows, inv_temp);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_cedice_fwd(const float* probs, const uint8_t* labels, double* sums, int n, int b, long long voxels, pb_stream_t stream) {
+    PB_CHECK_ARG(probs && labels && sums && n > 0 && b > 0 && voxels > 0, "bad argument");
+    cedice_fwd_kernel<<<dim3(red_blocks(voxels, n), n), 256, 0, (cudaStream_t)stream>>>(probs, labels, sums, voxels, b);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_cedice_bwd(const float* probs, const uint8_t* labels, const float* coef, float* dprobs, int n, int b,
+                             long long voxels, pb_stream_t stream) {
+    PB_CHECK_ARG(probs && labels && coef && dprobs && n > 0 && b > 0 && voxels > 0, "bad argument");
+    const long long total = (long long)n * voxels;
+    cedice_bwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(probs, labels, coef, dprobs, voxels, b, total);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_kl_fwd(const float* ps, const float* pt, double* sums, int n, int b, long long voxels, pb_stream_t stream) {
+    PB_CHECK_ARG(ps && pt && sums && n > 0 && b > 0 && voxels > 0, "bad argument");
+    kl_fwd_kernel<<<dim3(red_blocks(voxels, n), n), 256, 0, (cudaStream_t)stream>>>(ps, pt, sums, voxels, b);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_kl_bwd(const float* ps, const float* pt, const float* coef, float* dps, int n, int b, long long voxels,
+                         pb_stream_t stream) {
+    PB_CHECK_ARG(ps && pt && coef && dps && n > 0 && b > 0 && voxels > 0, "bad argument");
+    const long long total = (long long)n * voxels;
+    kl_bwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(ps, pt, coef, dps, voxels, b, total);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_proto_sums(int dtype, const void* f, const uint8_t* labels, double* P, int n, int b, long long voxels, int c,
+                             pb_stream_t stream) {
+    PB_CHECK_ARG(f && labels && P && n > 0 && b > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(c == PC, "prototype kernels are specialised for 8 feature channels (basic_dims)");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(red_blocks(voxels, n), n);
+    if (dtype == PB_BF16) proto_sums_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)f, labels, P, voxels, b);
+    else proto_sums_kernel<float><<<grid, 256, 0, st>>>((const float*)f, labels, P, voxels, b);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_proto_fwd(int dtype, const void* fs, const void* ft, const float* protos, const float* protot, const float* present,
+                            double* out, int n, int b, long long voxels, int c, float eps, pb_stream_t stream) {
+    PB_CHECK_ARG(fs && ft && protos && protot && present && out && n > 0 && b > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(c == PC, "prototype kernels are specialised for 8 feature channels (basic_dims)");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(red_blocks(voxels, n), n);
+    if (dtype == PB_BF16) proto_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)fs, (const bf16*)ft, protos, protot, present, out, voxels, b, eps);
+    else proto_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)fs, (const float*)ft, protos, protot, present, out, voxels, b, eps);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_proto_bwd1(int dtype, const void* fs, const void* ft, const float* protos, const float* protot, const float* present,
+                             const float* coef, void* dfs, double* dprotos, int n, int b, long long voxels, int c, float eps,
+                             pb_stream_t stream) {
+    PB_CHECK_ARG(fs && ft && protos && protot && present && coef && dfs && dprotos && n > 0 && b > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(c == PC, "prototype kernels are specialised for 8 feature channels (basic_dims)");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(red_blocks(voxels, n), n);
+    if (dtype == PB_BF16)
+        proto_bwd1_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)fs, (const bf16*)ft, protos, protot, present, coef, (bf16*)dfs, dprotos, voxels, b, eps);
+    else
+        proto_bwd1_kernel<float><<<grid, 256, 0, st>>>((const float*)fs, (const float*)ft, protos, protot, present, coef, (float*)dfs, dprotos, voxels, b, eps);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_proto_bwd2(int dtype, const uint8_t* labels, const float* dproto, void* dfs, int n, int b, long long voxels, int c,
+                             pb_stream_t stream) {
+    PB_CHECK_ARG(labels && dproto && dfs && n > 0 && b > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(c == PC, "prototype kernels are specialised for 8 feature channels (basic_dims)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n * voxels;
+    if (dtype == PB_BF16) proto_bwd2_kernel<bf16><<<ew_blocks(total), 256, 0, st>>>(labels, dproto, (bf16*)dfs, voxels, b, total);
+    else proto_bwd2_kernel<float><<<ew_blocks(total), 256, 0, st>>>(labels, dproto, (float*)dfs, voxels, b, total);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

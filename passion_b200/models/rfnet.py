@@ -332,52 +332,50 @@ class Model(nn.Module):
         logits, prms, des = self.decoder_fuse.run(*ys)
         D, H, W = logits.shape[1:4]
         fuse_logits = logits.view(P, B, D, H, W, -1)
-        fuse_prob = torch.softmax(fuse_logits[0].float(), -1).permute(0, 4, 1, 2, 3)   # [B,C,D,H,W]
+        fuse_prob = ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)                  # [B,C,D,H,W]
         self.last = {"fuse_logits": fuse_logits, "prm_logits": prms, "de_f": des, "passes": P, "enc": enc}
         if not self.is_training:
             return fuse_prob
 
         sep_logits = self.decoder_sep.run(*enc)                               # [4B,D,H,W,C], modality-major
-        sep_prob = torch.softmax(sep_logits.float(), -1).view(4, B, D, H, W, -1)
+        sep_prob = ops.softmax4(sep_logits).view(4, B, D, H, W, -1)
         e = (fm if idt else torch.ones_like(fm)).t()                          # [4(m),B]
         if idt:
             sep_prob = sep_prob * e[:, :, None, None, None, None]             # rfnet.py:259-260
         self.last["sep_prob"] = sep_prob
 
-        t_cl = target.permute(0, 2, 3, 4, 1).to(torch.float32).contiguous()   # [B,D,H,W,C]
-        cnt, wgt = crit.target_stats(t_cl)
+        labels, cnt, wgt = crit.label_stats(target)
 
         # ---- prm loss (rfnet.py:284-288): full-mask pass only
         prm_loss = torch.zeros(B, device=x.device)
         wl = 1.0
         for prm, s in zip(prms, UP_SCALES):
             wl /= 2.0
-            p0 = torch.softmax(prm.view(P, B, *prm.shape[1:])[0].float(), -1)
-            ce, dice = crit.cedice_cl(crit.up_probs(p0, s)[None], t_cl, cnt, wgt)
-            prm_loss = prm_loss + wl * (ce[0] + dice[0])
+            p0 = ops.softmax4(prm.view(P, B, *prm.shape[1:])[0])
+            ce, dice = crit.cedice(crit.up_probs(p0, s), labels, cnt, wgt)
+            prm_loss = prm_loss + wl * (ce + dice)
         # ---- sep loss (rfnet.py:336 ...)
-        ce, dice = crit.cedice_cl(sep_prob, t_cl, cnt, wgt)                   # [4,B]
-        sep_loss = (e * (ce + dice)).t()                                      # [B,4]
+        ce, dice = crit.cedice(sep_prob.view(4 * B, D, H, W, -1), labels, cnt, wgt)
+        sep_loss = (e * (ce + dice).view(4, B)).t()                           # [B,4]
         if not self.use_passion:
             return fuse_prob, prm_loss[:, None], sep_loss                     # rfnet.py:402
 
         # ---- PASSION terms: single-modality passes 1..4 vs the detached full-mask pass 0
         V = D * H * W
-        ps = torch.softmax(fuse_logits[1:].float() / temp, -1)
-        pt = torch.softmax(fuse_logits[0].float().detach() / temp, -1)
-        kl = crit.kl_cl(ps, pt, temp)                                          # [4,B]
+        ps = ops.softmax4(fuse_logits[1:].reshape(4 * B, D, H, W, -1), temp)
+        pt = ops.softmax4(fuse_logits[0].detach(), temp)
+        kl = crit.kl(ps, pt, temp)                                             # [4B]
         wl = 1.0
         for prm, s in zip(prms, UP_SCALES):
             wl /= 2.0
-            pr = prm.view(P, B, *prm.shape[1:]).float()
-            ps_l = torch.softmax(pr[1:] / temp, -1)
-            pt_l = torch.softmax(pr[0].detach() / temp, -1)
-            if s > 1:
-                ps_l = crit.up_probs(ps_l.reshape(4 * B, *ps_l.shape[2:]).contiguous(), s).view(4, B, D, H, W, -1)
-                pt_l = crit.up_probs(pt_l.contiguous(), s)
-            kl = kl + wl * crit.kl_cl(ps_l, pt_l, temp)
-        de1 = des[0].view(P, B, V, -1).float()
-        proto, dist = crit.proto_cl(de1[1:], de1[0].detach(), t_cl.view(B, V, -1), cnt)
+            pr = prm.view(P, B, *prm.shape[1:])
+            ps_l = crit.up_probs(ops.softmax4(pr[1:].reshape(4 * B, *prm.shape[1:]), temp), s)
+            pt_l = crit.up_probs(ops.softmax4(pr[0].detach(), temp), s)
+            kl = kl + wl * crit.kl(ps_l, pt_l, temp)
+        kl = kl.view(4, B)
+        de1 = des[0].view(P, B, V, -1)
+        proto, dist = crit.proto(de1[1:].reshape(4 * B, V, -1), de1[0].detach(), labels.view(B, V), cnt)
+        proto, dist = proto.view(4, B), dist.view(4, B)
         # A sample whose ONLY present modality is m makes pass 1+m identical to pass 0 (same inputs, same
         # weights): the reference then gets kl = proto = dist = 0 EXACTLY (bit-identical passes), which is what
         # turns rp_iter into 0/0 = NaN in train.py:265-268.  Reproduce the exact zeros structurally.

@@ -72,9 +72,12 @@ class KernelTimer:
 TIMER = None          # set to a KernelTimer() to time every launch
 
 
-def _run(name, key, nbytes, flops, fn):
+def _run(name, key, nbytes, flops, fn, allow_unsupported=False):
     rc = TIMER.run(name, key, nbytes, flops, fn) if TIMER is not None else fn()
+    if allow_unsupported and rc == -3:          # PB_EUNSUPPORTED: caller falls back to the generic kernel
+        return False
     _lib.check(rc, name)
+    return True
 
 
 def _conv_work(d, esize):
@@ -157,10 +160,12 @@ class _Conv3d(torch.autograd.Function):
         if bias is None and _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
             img = tc_weight_image(w, _tc_ntile(d.c0 + d.c1, cout))
             err = _tc_err_flag(x0.device)
-            _run("conv3d_fwd_tc", key, nb, fl,
-                 lambda: lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y), None, cout, 0, _p(stats),
-                                          _p(err), _stream()))
+            done = _run("conv3d_fwd_tc", key, nb, fl,
+                        lambda: lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y), None, cout, 0, _p(stats),
+                                                 _p(err), _stream()), allow_unsupported=True)
         else:
+            done = False
+        if not done:
             _run("conv3d_fwd", key, nb, fl,
                  lambda: lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(w), _p(bias), _p(y), _p(stats), _stream()))
         ctx.save_for_backward(x0, x1, w)
@@ -184,7 +189,8 @@ class _Conv3d(torch.autograd.Function):
             wt = w.transpose(2, 3).contiguous()
             dx0 = torch.empty_like(x0)
             dx1 = torch.empty_like(x1) if x1 is not None else None
-            if _tc_eligible(dy.dtype, ksize, stride, d.cout, 0, d.c0 + d.c1) and d.c0 % 8 == 0 and d.c1 % 8 == 0:
+            if (_tc_eligible(dy.dtype, ksize, stride, d.cout, 0, d.c0 + d.c1) and d.c0 % 8 == 0 and d.c1 % 8 == 0
+                    and (pad_mode != "reflect" or min(d.di, d.hi, d.wi) >= 4)):
                 # data gradient = the same implicit GEMM on dy with flipped taps / transposed channels and zero
                 # padding; the reflected-halo terms are added by a thin boundary kernel
                 wflip = w.flip(1).transpose(2, 3)
@@ -192,13 +198,15 @@ class _Conv3d(torch.autograd.Function):
                 dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0,
                               cout=d.c0 + d.c1, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
                 err = _tc_err_flag(dy.device)
-                _run("conv3d_dgrad_tc", key, nb, fl,
-                     lambda: lib.pb_conv3d_tc(ctypes.byref(dd), _p(dy), None, _p(img), _p(dx0), _p(dx1), d.c0, d.c1, None,
-                                              _p(err), _stream()))
-                if pad_mode == "reflect":
+                done = _run("conv3d_dgrad_tc", key, nb, fl,
+                            lambda: lib.pb_conv3d_tc(ctypes.byref(dd), _p(dy), None, _p(img), _p(dx0), _p(dx1), d.c0, d.c1, None,
+                                                     _p(err), _stream()), allow_unsupported=True)
+                if done and pad_mode == "reflect":
                     _run("conv3d_dgrad_fix", key, 0, 0,
                          lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
             else:
+                done = False
+            if not done:
                 _run("conv3d_dgrad", key, nb, fl,
                      lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
         if ctx.needs_input_grad[2]:
@@ -355,3 +363,160 @@ class _RfmRegion(torch.autograd.Function):
 
 def rfm_region(y, p, w0, b0, w2, b2):
     return _RfmRegion.apply(y, p, w0, b0, w2, b2)
+
+
+# ---- PASSION objective kernels (csrc/loss.cu) ----------------------------------------------------------------
+class _Softmax4(torch.autograd.Function):
+    """probs[..., 4] (fp32) = softmax(logits[..., 4] / temp)."""
+
+    @staticmethod
+    def forward(ctx, logits, temp):
+        lib = _lib.load()
+        _chk(logits)
+        assert logits.shape[-1] == 4
+        rows = logits.numel() // 4
+        probs = torch.empty(logits.shape, dtype=torch.float32, device=logits.device)
+        _run("softmax4", "", logits.numel() * (logits.element_size() + 4), 0,
+             lambda: lib.pb_softmax4(_dt(logits), _p(logits), _p(probs), rows, 1.0 / temp, _stream()))
+        ctx.save_for_backward(probs)
+        ctx.meta = (logits.dtype, temp)
+        return probs
+
+    @staticmethod
+    def backward(ctx, dprobs):
+        lib = _lib.load()
+        probs, = ctx.saved_tensors
+        dtype, temp = ctx.meta
+        dprobs = dprobs.contiguous().float()
+        dlogits = torch.empty(probs.shape, dtype=dtype, device=probs.device)
+        rows = probs.numel() // 4
+        _run("softmax4_bwd", "", probs.numel() * (8 + dlogits.element_size()), 0,
+             lambda: lib.pb_softmax4_bwd(_dt(dlogits), _p(probs), _p(dprobs), _p(dlogits), rows, 1.0 / temp, _stream()))
+        return dlogits, None
+
+
+def softmax4(logits, temp=1.0):
+    return _Softmax4.apply(logits, float(temp))
+
+
+class _CeDiceSums(torch.autograd.Function):
+    """probs [N, V.., 4] fp32 at label resolution, labels uint8 [B, V..] -> sums [N, 3, 4] fp32:
+    A_c = sum p_c t_c, L_c = sum p_c, E_c = sum t_c log(clamp(p_c, .005, 1)).  Sample n uses labels n % B."""
+
+    @staticmethod
+    def forward(ctx, probs, labels):
+        lib = _lib.load()
+        _chk(probs, labels)
+        n, b = probs.shape[0], labels.shape[0]
+        voxels = labels.numel() // b
+        assert probs.dtype == torch.float32 and probs.numel() == n * voxels * 4 and labels.dtype == torch.uint8
+        sums = torch.zeros((n, 12), dtype=torch.float64, device=probs.device)
+        _run("cedice_fwd", "", probs.numel() * 4 + n * voxels, 0,
+             lambda: lib.pb_cedice_fwd(_p(probs), _p(labels), _p(sums), n, b, voxels, _stream()))
+        ctx.save_for_backward(probs, labels)
+        return sums.float().view(n, 3, 4)
+
+    @staticmethod
+    def backward(ctx, dsums):
+        lib = _lib.load()
+        probs, labels = ctx.saved_tensors
+        n, b = probs.shape[0], labels.shape[0]
+        voxels = labels.numel() // b
+        coef = dsums.reshape(n, 12).contiguous().float()
+        dprobs = torch.empty_like(probs)
+        _run("cedice_bwd", "", probs.numel() * 8 + n * voxels, 0,
+             lambda: lib.pb_cedice_bwd(_p(probs), _p(labels), _p(coef), _p(dprobs), n, b, voxels, _stream()))
+        return dprobs, None
+
+
+def cedice_sums(probs, labels):
+    return _CeDiceSums.apply(probs, labels)
+
+
+class _KlSums(torch.autograd.Function):
+    """ps [N, V.., 4], pt [B, V.., 4] fp32 (already at temperature, same resolution) -> [N] sums of
+    clamp(pt) (log clamp(pt) - log clamp(ps)); no gradient to the teacher."""
+
+    @staticmethod
+    def forward(ctx, ps, pt):
+        lib = _lib.load()
+        _chk(ps, pt)
+        n, b = ps.shape[0], pt.shape[0]
+        voxels = pt.numel() // (b * 4)
+        assert ps.numel() == n * voxels * 4
+        sums = torch.zeros(n, dtype=torch.float64, device=ps.device)
+        _run("kl_fwd", "", (ps.numel() + pt.numel()) * 4, 0,
+             lambda: lib.pb_kl_fwd(_p(ps), _p(pt), _p(sums), n, b, voxels, _stream()))
+        ctx.save_for_backward(ps, pt)
+        return sums.float()
+
+    @staticmethod
+    def backward(ctx, dsums):
+        lib = _lib.load()
+        ps, pt = ctx.saved_tensors
+        n, b = ps.shape[0], pt.shape[0]
+        voxels = pt.numel() // (b * 4)
+        coef = dsums.contiguous().float()
+        dps = torch.empty_like(ps)
+        _run("kl_bwd", "", ps.numel() * 12, 0,
+             lambda: lib.pb_kl_bwd(_p(ps), _p(pt), _p(coef), _p(dps), n, b, voxels, _stream()))
+        return dps, None
+
+
+def kl_sums(ps, pt):
+    return _KlSums.apply(ps, pt.detach())
+
+
+class _ProtoSums(torch.autograd.Function):
+    """fs [N, V, 8] student features, ft [B, V, 8] teacher features (detached), labels uint8 [B, V], cnt [B, 4] class
+    voxel counts -> (sum d^2 [N], sum |d| [N]) over the classes present in every sample of the local batch."""
+
+    @staticmethod
+    def forward(ctx, fs, ft, labels, cnt, eps):
+        lib = _lib.load()
+        _chk(fs, ft, labels)
+        n, b, c = fs.shape[0], ft.shape[0], fs.shape[-1]
+        voxels = labels.numel() // b
+        dev = fs.device
+        Ps = torch.zeros((n, 4, c), dtype=torch.float64, device=dev)
+        Pt = torch.zeros((b, 4, c), dtype=torch.float64, device=dev)
+        dt = _dt(fs)
+        _run("proto_sums", "s", fs.numel() * fs.element_size(), 0,
+             lambda: lib.pb_proto_sums(dt, _p(fs), _p(labels), _p(Ps), n, b, voxels, c, _stream()))
+        _run("proto_sums", "t", ft.numel() * ft.element_size(), 0,
+             lambda: lib.pb_proto_sums(dt, _p(ft), _p(labels), _p(Pt), b, b, voxels, c, _stream()))
+        den = (cnt.float() + eps)                                         # [B,4]   (criterions.py:158-159)
+        present = (cnt > 0).all(0).float().contiguous()                   # class used iff present in EVERY sample (:157)
+        protos = (Ps.float() / den.repeat(n // b, 1)[..., None]).contiguous()
+        protot = (Pt.float() / den[..., None]).contiguous()
+        out = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+        _run("proto_fwd", "", (fs.numel() + fs.numel()) * fs.element_size(), 0,
+             lambda: lib.pb_proto_fwd(dt, _p(fs), _p(ft), _p(protos), _p(protot), _p(present), _p(out), n, b, voxels, c, eps,
+                                      _stream()))
+        ctx.save_for_backward(fs, ft, labels, protos, protot, present, den)
+        ctx.eps = eps
+        out = out.float()
+        ctx.mark_non_differentiable(present)
+        return out[:, 0].contiguous(), out[:, 1].contiguous(), present
+
+    @staticmethod
+    def backward(ctx, dse, _dab, _dpresent):
+        lib = _lib.load()
+        fs, ft, labels, protos, protot, present, den = ctx.saved_tensors
+        n, b, c = fs.shape[0], ft.shape[0], fs.shape[-1]
+        voxels = labels.numel() // b
+        coef = dse.contiguous().float()
+        dfs = torch.empty_like(fs)
+        dP = torch.zeros((n, 4, c), dtype=torch.float64, device=fs.device)
+        dt = _dt(fs)
+        _run("proto_bwd1", "", fs.numel() * fs.element_size() * 3, 0,
+             lambda: lib.pb_proto_bwd1(dt, _p(fs), _p(ft), _p(protos), _p(protot), _p(present), _p(coef), _p(dfs), _p(dP), n, b,
+                                       voxels, c, ctx.eps, _stream()))
+        dproto = (dP.float() / den.repeat(n // b, 1)[..., None]).contiguous()
+        _run("proto_bwd2", "", fs.numel() * fs.element_size() * 2, 0,
+             lambda: lib.pb_proto_bwd2(dt, _p(labels), _p(dproto), _p(dfs), n, b, voxels, c, _stream()))
+        return dfs, None, None, None, None
+
+
+def proto_sums(fs, ft, labels, cnt, eps=1e-5):
+    return _ProtoSums.apply(fs, ft.detach(), labels, cnt, eps)

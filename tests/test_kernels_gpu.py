@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 def rel(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
@@ -196,3 +196,65 @@ def test_rfm_region(lib_built, c, shape, dtype):
     assert rel(ins[0].grad, refs[0].grad) < tol
     for a, b in zip(ins[1:], refs[1:]):
         assert rel(a.grad, b.grad) < (2e-4 if dtype == torch.float32 else 2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ loss kernels
+def _onehot_target(labels, num_cls=4):
+    return F.one_hot(labels.long(), num_cls).permute(0, 4, 1, 2, 3).double()
+
+
+@pytest.mark.parametrize("scale", [1, 2, 4])
+def test_criterions_match_oracle(lib_built, scale):
+    """The reference-signature loss wrappers (fused kernels) against the CPU oracle's restatement, values and
+    gradients, including the trilinear up_op and the batched n % B label pairing."""
+    from oracle import criterions_oracle as oc
+    from passion_b200 import criterions as crit
+    g = torch.Generator().manual_seed(scale)
+    B, S = 2, 16
+    s = S // scale
+    labels = torch.randint(0, 4, (B, S, S, S), generator=g)
+    labels[1][labels[1] == 3] = 0                                     # class 3 absent from sample 1 -> presence gate
+    target = _onehot_target(labels)
+    logit_s = torch.randn(B, 4, s, s, s, generator=g) * 3
+    logit_t = torch.randn(B, 4, s, s, s, generator=g) * 3
+    up = (lambda t: F.interpolate(t, scale_factor=scale, mode="trilinear", align_corners=True)) if scale > 1 else None
+    for name in ("dice", "ce", "kl"):
+        a = logit_s.clone().requires_grad_(True)
+        ac = logit_s.cuda().requires_grad_(True)
+        if name == "dice":
+            ref = oc.dice_loss_bs(torch.softmax(a, 1), target, 4, up_op=up)
+            out = crit.dice_loss_bs(torch.softmax(ac, 1), target.cuda(), num_cls=4, up_op=scale)
+        elif name == "ce":
+            ref = oc.softmax_weighted_loss_bs(torch.softmax(a, 1), target, 4, up_op=up)
+            out = crit.softmax_weighted_loss_bs(torch.softmax(ac, 1), target.cuda(), num_cls=4, up_op=scale)
+        else:
+            ref = oc.temp_kl_loss_bs(a, logit_t, 4.0, up_op=up)
+            out = crit.temp_kl_loss_bs(ac, logit_t.cuda(), target.cuda(), num_cls=4, temp=4.0, up_op=scale)
+        assert out.shape == ref.shape == (B, 1)
+        assert rel(out, ref) < 1e-5, name
+        wv = torch.tensor([[0.7], [1.3]])
+        (ref * wv).sum().backward()
+        (out * wv.cuda()).sum().backward()
+        assert rel(ac.grad, a.grad) < 1e-4, name
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_prototype_loss_matches_oracle(lib_built, dtype):
+    from oracle import criterions_oracle as oc
+    from passion_b200 import criterions as crit
+    g = torch.Generator().manual_seed(5)
+    B, S, C = 2, 12, 8
+    labels = torch.randint(0, 4, (B, S, S, S), generator=g)
+    labels[0][labels[0] == 2] = 1                                     # class 2 absent from sample 0
+    target = _onehot_target(labels)
+    fs = torch.randn(B, C, S, S, S, generator=g).to(dtype)
+    ft = (fs.float() + 0.5 * torch.randn(B, C, S, S, S, generator=g)).to(dtype)
+    a = fs.float().clone().requires_grad_(True)
+    ref_p, ref_d = oc.prototype_passion_loss_bs(a, ft.float(), target, 4)
+    ac = fs.cuda().requires_grad_(True)
+    out_p, out_d = crit.prototype_passion_loss_bs(ac, ft.cuda(), target.cuda(), None, None, num_cls=4)
+    assert rel(out_p, ref_p) < 1e-4 and rel(out_d, ref_d) < 1e-4
+    wv = torch.tensor([[0.7], [1.3]])
+    (ref_p * wv).sum().backward()
+    (out_p * wv.cuda()).sum().backward()
+    assert rel(ac.grad, a.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
