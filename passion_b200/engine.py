@@ -17,7 +17,7 @@ from .train_step import loss_mix
 
 class Trainer:
     def __init__(self, model, lr=2e-4, weight_decay=1e-4, temp=4.0, mask_type="idt", use_passion=True,
-                 modal_weight=None, imb_beta=None, warmup=False, distributed=None, bucket_mb=4.0):
+                 modal_weight=None, imb_beta=None, warmup=False, distributed=None, bucket_mb=4.0, use_graph=False):
         self.model = model
         dev = next(model.parameters()).device
         self.dev = dev
@@ -26,11 +26,15 @@ class Trainer:
         self.modal_weight = (modal_weight if modal_weight is not None else torch.ones(4)).to(dev).float()
         self.imb_beta = (imb_beta if imb_beta is not None else torch.ones(4)).to(dev).float()
         # train.py:94-96
-        self.optimizer = torch.optim.AdamW([{"params": model.parameters(), "lr": lr, "weight_decay": weight_decay}],
-                                           betas=(0.9, 0.999), eps=1e-08, amsgrad=True)
         if distributed is None:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
+        # The whole step (forward, loss mix, backward, AdamW) is sync-free and shape-static, so at N = 1 it can be
+        # replayed as ONE CUDA graph; the optimizer then keeps its step counter on the device (capturable).
+        self.use_graph = bool(use_graph) and not distributed
+        self.optimizer = torch.optim.AdamW([{"params": model.parameters(), "lr": lr, "weight_decay": weight_decay}],
+                                           betas=(0.9, 0.999), eps=1e-08, amsgrad=True, capturable=self.use_graph)
+        self._graph = None
         self.reducer = _ddp.GradReducer(model, bucket_mb=bucket_mb) if distributed else None
         if self.reducer is not None:
             self.reducer.broadcast_parameters()
@@ -41,7 +45,7 @@ class Trainer:
         return loss_mix(outs, target, mask, self.imb_beta, self.modal_weight, mask_type=self.mask_type,
                         warmup=self.warmup, rp_allreduce=rp_allreduce)
 
-    def step(self, x, target, mask):
+    def _eager_step(self, x, target, mask):
         loss, parts = self.forward_loss(x, target, mask)
         self.optimizer.zero_grad(set_to_none=True)
         if self.reducer is not None:
@@ -51,3 +55,28 @@ class Trainer:
             self.reducer.finish()
         self.optimizer.step()
         return loss.detach(), parts
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def _capture(self, x, target, mask):
+        self._static = tuple(t.clone() for t in (x, target, mask))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                    # warm-up on a side stream (allocator, lazy inits, autotune-free)
+            for _ in range(2):
+                self._eager_step(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            loss, parts = self._eager_step(*self._static)
+        self._out = (loss, {k: v.detach() for k, v in parts.items()})
+
+    def step(self, x, target, mask):
+        if not self.use_graph:
+            return self._eager_step(x, target, mask)
+        if self._graph is None:
+            self._capture(x, target, mask)
+        for dst, src in zip(self._static, (x, target, mask)):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._out

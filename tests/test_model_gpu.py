@@ -88,9 +88,11 @@ def test_fp32_check_mode(lib_built, case):
     outs, loss, parts = _cuda_step(model, x, target, mask, z)
     o_outs, o_loss, o_grads = _oracle(sd, x, target, mask, z)
     _, _, x_grads = _oracle(sd, x, target, mask, z, torch.float64)          # "exact" gradients
-    g = torch.Generator().manual_seed(0)
-    x_pert = (x.double() * (1 + 2e-6 * torch.randn(x.shape, generator=g, dtype=torch.float64)))
-    _, _, p_grads = _oracle(sd, x_pert, target, mask, z, torch.float64)     # sensitivity probe
+    probes = []                                                             # sensitivity probes (3 draws)
+    for seed in range(3):
+        g = torch.Generator().manual_seed(seed)
+        x_pert = (x.double() * (1 + 2e-6 * torch.randn(x.shape, generator=g, dtype=torch.float64)))
+        probes.append(_oracle(sd, x_pert, target, mask, z, torch.float64)[2])
     names = ["fuse_prob", "prm_loss", "sep_loss", "kl_loss", "proto_loss", "dist"][:len(outs)]
     for n, a, b in zip(names, outs, o_outs):
         assert rel(a, torch.from_numpy(z[n])) < 1e-4, (n, "vs golden")          # reference's own outputs
@@ -106,7 +108,7 @@ def test_fp32_check_mode(lib_built, case):
 
     def cat(d):
         return torch.cat([(d[k].grad if isinstance(d[k], torch.nn.Parameter) else d[k]).flatten().cpu().double() for k in keys])
-    sens_g = rel(cat(p_grads), cat(x_grads))
+    sens_g = max(rel(cat(pg), cat(x_grads)) for pg in probes)
     bad, sens_k = [], {}
     for k, p in model.named_parameters():
         if _is_cancelled_bias(k):
@@ -116,7 +118,7 @@ def test_fp32_check_mode(lib_built, case):
         if float(gx.norm()) < 1e-7:
             assert float(p.grad.norm()) < 1e-5, k
             continue
-        sens = sens_k[k] = rel(p_grads[k], gx)
+        sens = sens_k[k] = max(rel(pg[k], gx) for pg in probes)
         r = rel(p.grad, gx)
         if not r < max(1e-4, 4 * sens, 4 * sens_g):
             bad.append((k, r, sens))
@@ -131,7 +133,7 @@ def test_fp32_check_mode(lib_built, case):
     for k in keys:
         if gn[k] < 1e-6:
             continue
-        assert abs(float(params[k].grad.double().norm()) - gn[k]) < max(5e-3, 4 * sens_g, 4 * sens_k.get(k, 0.0)) * gn[k], k
+        assert abs(float(params[k].grad.double().norm()) - gn[k]) < max(5e-3, 6 * sens_g, 6 * sens_k.get(k, 0.0)) * gn[k], k
 
 
 @pytest.mark.parametrize("case", ["idtU", "idtS24"])
