@@ -83,6 +83,11 @@ int pb_conv3d_wgrad(const pb_conv_desc* d, const void* x0, const void* x1, const
 int pb_conv3d_tc_ntile(int cin, int cout);
 int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, void* y0, void* y1,
                  int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
+/* Weight gradient of the same class on tcgen05: voxels are the GEMM K dimension, the nine (kd,kh) accumulators of one
+ * 8-channel input chunk stay resident in TMEM for the CTA's whole sweep.  dw is the fp32 [groups][27][cin][cout]
+ * layout of pb_conv3d_wgrad and must be zero-filled; cout in {8,16,32,64}. */
+int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw,
+                       int* err_flag, pb_stream_t stream);
 /* dx0/dx1 += the contributions that reach an input voxel through the reflect padding (voxels one step inside a
  * face); completes a zero-padding data gradient into the exact adjoint of the reflect-padded forward conv. */
 int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy, const float* wt, void* dx0, void* dx1,

@@ -364,6 +364,236 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, vo
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------ weight gradient on tcgen05
+// dw[tap][ci][co] = sum_{n,q} x[n, q + off(tap)][ci] * dy[n, q][co]  (reflect / zero padding resolved when staging x).
+// GEMM view with the VOXEL index as K:  D[co, (kw, ci)] += A[co, q] * B[(kw, ci), q]  for every (kd, kh), where
+//   A = dy tile  [128 rows q][co]  read as an MN-major operand (co contiguous, q strided by 16 B),
+//   B = x slab   rows q + kh*PW + kw + ...  read as an MN-major operand whose N-groups are the kw = 0..3 shifts of the
+//       same 8-channel plane (SBO = 16 B: a one-row shift) — again no im2col copy in shared memory.
+// One CTA owns one 8-channel chunk of the input and keeps all nine (kd,kh) accumulators (128 lanes x 32 columns each)
+// resident in TMEM while it sweeps its share of the volume; they are read out once at the end and added to dw with fp32
+// atomics.  M is 128 although only `co` rows are meaningful: rows beyond co read don't-care shared memory and are never
+// stored (each D row depends on its own A row only).
+constexpr int kWgSlotsX = 6, kWgSlotsY = 3;
+constexpr int kWgYSlotBytes = 16 * kTileM * 16;      // 16 M-groups x 128 rows x 16 B
+
+struct WgP {
+    int N, D, H, W, C0, C1, Cout, reflect;
+    int PW, QT, DCH, ND, npg, groups, nchunks;
+    int slab_need, slab_e;
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {       // both operands MN-major
+    return umma_idesc(M, N) | (1u << 15) | (1u << 16);
+}
+
+template <int NCO>   // NCO = Cout / 8
+__global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                                     const bf16* __restrict__ dy, float* __restrict__ dw, int* err) {
+    constexpr uint32_t IDESC = umma_idesc_mn(kTileM, 32);
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* y_s = smem;                                              // [kWgSlotsY][16 planes][128 rows][16 B]
+    uint8_t* x_s = smem + kWgSlotsY * kWgYSlotBytes;                  // [kWgSlotsX][slab_e rows][16 B]
+    const int xslot_bytes = p.slab_e * 16;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + (size_t)kWgSlotsX * xslot_bytes);
+    uint64_t* fullx = bars;
+    uint64_t* emptyx = bars + kWgSlotsX;
+    uint64_t* fully = bars + 2 * kWgSlotsX;
+    uint64_t* emptyy = fully + kWgSlotsY;
+    uint64_t* done = emptyy + kWgSlotsY;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.y / p.nchunks, chunk = blockIdx.y % p.nchunks;
+    const int items = p.npg * p.QT * p.ND;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWgSlotsX; ++i) { mbar_init(&fullx[i], kProducerThreads); mbar_init(&emptyx[i], 1); }
+        for (int i = 0; i < kWgSlotsY; ++i) { mbar_init(&fully[i], kProducerThreads); mbar_init(&emptyy[i], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 5) {
+        // =============================== producers ===============================
+        const int pt = threadIdx.x - 5 * 32;
+        const int c0ch = p.C0 >> 3;
+        const bool from1 = chunk >= c0ch;
+        const bf16* xsrc = from1 ? x1 : x0;
+        const int cs = from1 ? p.C1 : p.C0, coff = (from1 ? chunk - c0ch : chunk) * 8;
+        uint32_t kx = 0, ky = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
+            const int d0 = dc * p.DCH, q0 = qt * kTileM;
+            const int nout = min(p.DCH, p.D - d0);
+            int soff[4];                                   // x slab rows of this thread (slab_need <= 4 * 96)
+            int yoff[2 * NCO];                             // dy copies of this thread (128 * NCO <= 2 * NCO * 96)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = pt + i * kProducerThreads;
+                soff[i] = -1;
+                if (e < p.slab_need) {
+                    const int f = q0 + e;
+                    const int hp = f / p.PW, wp = f - hp * p.PW;
+                    int h = hp - 1, w = wp - 1;
+                    bool ok = hp < p.H + 2;
+                    if (p.reflect) { h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); ok = ok && h >= 0 && h < p.H && w >= 0 && w < p.W; }
+                    else ok = ok && h >= 0 && h < p.H && w >= 0 && w < p.W;
+                    if (ok) soff[i] = (h * p.W + w) * cs + coff;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2 * NCO; ++i) {
+                const int idx = pt + i * kProducerThreads;
+                yoff[i] = -1;
+                if (idx < kTileM * NCO) {
+                    const int c = idx % NCO, r = idx / NCO;
+                    const int f = q0 + r;
+                    const int h = f / p.PW, w = f - h * p.PW;
+                    if (h < p.H && w < p.W) yoff[i] = (h * p.W + w) * p.Cout + c * 8;
+                }
+            }
+            for (int pl = 0; pl < nout + 2; ++pl, ++kx) {
+                const int slot = kx % kWgSlotsX;
+                mbar_wait(&emptyx[slot], ((kx / kWgSlotsX) & 1) ^ 1, err, 11);
+                int dp = d0 - 1 + pl;
+                bool plane_ok = true;
+                if (p.reflect) dp = reflect_idx(dp, p.D); else plane_ok = dp >= 0 && dp < p.D;
+                if (!plane_ok) dp = 0;
+                const bf16* pp = xsrc + ((size_t)n * p.D + dp) * p.H * p.W * cs;
+                const uint32_t sbase = smem_u32(x_s + (size_t)slot * xslot_bytes);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = pt + i * kProducerThreads;
+                    if (e < p.slab_need) {
+                        const bool ok = plane_ok && soff[i] >= 0;
+                        cp_async16(sbase + (uint32_t)e * 16, ok ? pp + soff[i] : x0, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive_noinc(&fullx[slot]);
+                // the dy plane that pairs with x planes pl-1, pl, pl+1 is output plane d0 + pl - 1: stage it one step late
+                if (pl >= 1 && pl <= nout) {
+                    const int ys = ky % kWgSlotsY;
+                    mbar_wait(&emptyy[ys], ((ky / kWgSlotsY) & 1) ^ 1, err, 12);
+                    const bf16* py = dy + ((size_t)n * p.D + d0 + pl - 1) * p.H * p.W * p.Cout;
+                    const uint32_t ybase = smem_u32(y_s + (size_t)ys * kWgYSlotBytes);
+#pragma unroll
+                    for (int i = 0; i < 2 * NCO; ++i) {
+                        const int idx = pt + i * kProducerThreads;
+                        if (idx < kTileM * NCO) {
+                            const int c = idx % NCO, r = idx / NCO;
+                            const bool ok = yoff[i] >= 0;
+                            cp_async16(ybase + (uint32_t)(c * kTileM + r) * 16, ok ? py + yoff[i] : dy, ok ? 16u : 0u);
+                        }
+                    }
+                    cp_async_arrive_noinc(&fully[ys]);
+                    ++ky;
+                }
+            }
+        }
+        cp_async_wait_all();
+    } else if (warp == 4) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t x_addr = smem_u32(x_s), y_addr = smem_u32(y_s);
+            uint32_t kx = 0, ky = 0;
+            bool first = true;
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int dc = it % p.ND;
+                const int nout = min(p.DCH, p.D - dc * p.DCH);
+                for (int od = 0; od < nout; ++od, ++ky) {
+                    for (int kd = (od == 0 ? 0 : 2); kd < 3; ++kd) {
+                        const uint32_t kk = kx + od + kd;
+                        mbar_wait(&fullx[kk % kWgSlotsX], (kk / kWgSlotsX) & 1, err, 13);
+                    }
+                    mbar_wait(&fully[ky % kWgSlotsY], (ky / kWgSlotsY) & 1, err, 14);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint64_t a0 = umma_desc(y_addr + (ky % kWgSlotsY) * kWgYSlotBytes, 128, kTileM * 16);   // LBO = 8 rows, SBO = co-chunk plane
+#pragma unroll 1
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const uint32_t sb = x_addr + ((kx + od + kd) % kWgSlotsX) * xslot_bytes;
+                        const uint64_t b0 = umma_desc(sb, 128, 16);                                            // LBO = 8 rows, SBO = one-row (kw) shift
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint32_t d_tmem = tmem_base + (kd * 3 + kh) * 32;
+                            const uint64_t b1 = b0 + (uint64_t)(uint32_t)(kh * p.PW);
+#pragma unroll
+                            for (int ks = 0; ks < kTileM / 16; ++ks) {
+                                umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b1 + (uint64_t)(16 * ks), IDESC, (first && ks == 0) ? 0u : 1u);
+                            }
+                        }
+                    }
+                    first = false;
+                    umma_commit(&emptyy[ky % kWgSlotsY]);
+                    umma_commit(&emptyx[(kx + od) % kWgSlotsX]);
+                    if (od == nout - 1) {
+                        umma_commit(&emptyx[(kx + od + 1) % kWgSlotsX]);
+                        umma_commit(&emptyx[(kx + od + 2) % kWgSlotsX]);
+                    }
+                }
+                kx += nout + 2;
+            }
+            umma_commit(done);
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue: TMEM -> fp32 atomics into dw ===============================
+        if (blockIdx.x < items) {
+            mbar_wait(done, 0, err, 15);
+            tc_fence_after();
+            const int co = warp * 32 + lane;
+            const int cin = p.C0 + p.C1;
+            for (int a = 0; a < 9; ++a) {
+                float v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + a * 32;
+                tmem_ld16(taddr, v);
+                tmem_ld16(taddr + 16, v + 16);
+                if (co < p.Cout) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int tap = a * 3 + kw;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            atomicAdd(dw + (((size_t)g * 27 + tap) * cin + chunk * 8 + j) * p.Cout + co, v[kw * 8 + j]);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <int NCO>
+int launch_wgrad_tc(const WgP& p, const void* x0, const void* x1, const void* dy, float* dw, int* err, cudaStream_t st) {
+    const size_t smem = (size_t)kWgSlotsY * kWgYSlotBytes + (size_t)kWgSlotsX * p.slab_e * 16 + (2 * kWgSlotsX + 2 * kWgSlotsY + 1) * 8 + 16;
+    auto kern = conv3_wgrad_tc_kernel<NCO>;
+    if (smem > 227 * 1024) { pb_set_error("conv3d_wgrad_tc: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pb_set_error("conv3d_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
+    const int items = p.npg * p.QT * p.ND;
+    int ctas = 148 / (p.groups * p.nchunks);
+    if (ctas < 1) ctas = 1;
+    if (ctas > items) ctas = items;
+    kern<<<dim3(ctas, p.groups * p.nchunks), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)dy, dw, err);
+    return 0;
+}
+
 }  // namespace
 
 // Weight image layout expected by the kernel: [groups][cout tiles][27 taps][NCH chunks][NT rows][8 channels] bf16,
@@ -418,6 +648,44 @@ extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x
     TC_CASE(1, 32); TC_CASE(2, 32); TC_CASE(4, 32); TC_CASE(8, 32);
 #undef TC_CASE
     if (rc) { if (rc == PB_EUNSUPPORTED) pb_set_error("conv3d_tc: no kernel for cin %d cout %d", cin, cout); return rc; }
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw, int* err_flag,
+                                  pb_stream_t stream) {
+    PB_CHECK_ARG(d && x0 && dy && dw && err_flag, "null pointer");
+    PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 3 && d->stride == 1, "bf16, 3x3x3, stride 1 only");
+    PB_CHECK_ARG(d->di == d->dout && d->hi == d->ho && d->wi == d->wo, "same-size output only");
+    PB_CHECK_ARG(d->c0 % 8 == 0 && d->c1 % 8 == 0 && d->c0 >= 8 && (d->c1 == 0 || x1), "input channels must be multiples of 8");
+    PB_CHECK_ARG(d->cout % 8 == 0 && d->cout >= 8 && d->cout <= 64, "cout must be a multiple of 8 in [8, 64]");
+    PB_CHECK_ARG(d->groups >= 1 && d->n % d->groups == 0, "bad groups");
+    WgP p;
+    p.N = d->n; p.D = d->di; p.H = d->hi; p.W = d->wi; p.C0 = d->c0; p.C1 = d->c1; p.Cout = d->cout;
+    p.reflect = d->pad_mode == PB_PAD_REFLECT;
+    PB_CHECK_ARG(!p.reflect || (p.D >= 2 && p.H >= 2 && p.W >= 2), "reflect padding needs size >= 2");
+    p.PW = p.W + 2;
+    p.QT = (p.H * p.PW + kTileM - 1) / kTileM;
+    p.npg = d->n / d->groups; p.groups = d->groups;
+    p.nchunks = (d->c0 + d->c1) / 8;
+    const int target = 148 * 2 / (p.groups * p.nchunks) + 1;
+    int nd = 1;
+    while (p.npg * p.QT * nd < target && (p.D + nd) / (nd + 1) >= 8) ++nd;
+    p.DCH = (p.D + nd - 1) / nd;
+    p.ND = (p.D + p.DCH - 1) / p.DCH;
+    p.slab_need = kTileM + 2 * p.PW + 3;
+    p.slab_e = (p.slab_need + 7) & ~7;
+    if (p.slab_need > 4 * kProducerThreads) { pb_set_error("conv3d_wgrad_tc: plane slab of %d rows exceeds the producer budget", p.slab_need); return PB_EUNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = PB_EUNSUPPORTED;
+    switch (d->cout / 8) {
+        case 1: rc = launch_wgrad_tc<1>(p, x0, x1, dy, dw, err_flag, st); break;
+        case 2: rc = launch_wgrad_tc<2>(p, x0, x1, dy, dw, err_flag, st); break;
+        case 4: rc = launch_wgrad_tc<4>(p, x0, x1, dy, dw, err_flag, st); break;
+        case 8: rc = launch_wgrad_tc<8>(p, x0, x1, dy, dw, err_flag, st); break;
+        default: pb_set_error("conv3d_wgrad_tc: cout %d not supported", d->cout); break;
+    }
+    if (rc) return rc;
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

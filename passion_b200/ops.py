@@ -102,6 +102,7 @@ def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
 
 # ---- tcgen05 implicit-GEMM path (csrc/conv3d_tc.cu) ------------------------------------------------------
 TC_ENABLED = os.environ.get("PB_TC", "1") != "0"
+WGRAD_TC = os.environ.get("PB_WGRAD_TC", "1") != "0"
 _tc_err = {}
 
 
@@ -211,8 +212,16 @@ class _Conv3d(torch.autograd.Function):
                      lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
         if ctx.needs_input_grad[2]:
             dw = torch.zeros_like(w)
-            _run("conv3d_wgrad", key, nb, fl,
-                 lambda: lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()))
+            done = False
+            if (TC_ENABLED and WGRAD_TC and dy.dtype == torch.bfloat16 and ksize == 3 and stride == 1 and d.c0 % 8 == 0
+                    and d.c1 % 8 == 0 and d.cout % 8 == 0 and d.cout <= 64):
+                err = _tc_err_flag(dy.device)
+                done = _run("conv3d_wgrad_tc", key, nb, fl,
+                            lambda: lib.pb_conv3d_wgrad_tc(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _p(err), _stream()),
+                            allow_unsupported=True)
+            if not done:
+                _run("conv3d_wgrad", key, nb, fl,
+                     lambda: lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()))
         if has_bias and ctx.needs_input_grad[3]:
             db = dy.float().reshape(groups, -1, dy.shape[-1]).sum(1)
         return dx0, dx1, dw, db, None, None, None, None, None
