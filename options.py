@@ -1,0 +1,45 @@
+"""Command-line flags of the training entry point — same names, defaults and derived fields as the reference
+`code/options.py:4-52` (argparse is the reference's only config mechanism), plus two additions that do not exist
+there: --synthetic (no dataset on disk) and --dtype."""
+import argparse
+import os
+
+
+def args_parser(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--model', default='rfnet', type=str, help='model name (rfnet is the B200-native path)')
+    parser.add_argument('-batch_size', '--batch_size', default=1, type=int, help='Batch size (per GPU)')
+    parser.add_argument('--lr', default=2e-4, type=float, help='base learning rate')
+    parser.add_argument('--weight_decay', default=1e-4, type=float)
+    parser.add_argument('--num_epochs', default=300, type=int, help='training epochs')
+    parser.add_argument('--temp', default=4.0, type=float, help='knowledge-distillation temperature')
+    parser.add_argument('--region_fusion_start_epoch', default=0, type=int, help='warm-up epochs used in rfnet')
+    # system
+    parser.add_argument('--seed', default=1037, type=int, help='random seed')
+    parser.add_argument('--gpu', type=str, default='0', help='GPU to use (ignored under torchrun: one rank per GPU)')
+    # options
+    parser.add_argument('--mask_type', default='idt', type=str, help='training settings: pdt idt or idt_drop')
+    parser.add_argument('--use_pretrain', action='store_true', default=False, help='whether use pretrained model')
+    parser.add_argument('--use_passion', action='store_true', default=False, help='whether use passion')
+    parser.add_argument('--use_valid', action='store_true', default=False, help='whether use validation')
+    # paths
+    parser.add_argument('--dataname', default='BraTS/BRATS2020', type=str)
+    parser.add_argument('--datapath', default='BraTS/BRATS2020_Training_none_npy', type=str)
+    parser.add_argument('--imbmrpath', default='BraTS/brats_split/Brats2020_imb_split_mr2468.csv', type=str, help='csv path')
+    parser.add_argument('--savepath', default='outputs/idt_mr2468_rfnet_passion', type=str, help='output path')
+    parser.add_argument('--resume', default=None, type=str, help='pretrained model path')
+    parser.add_argument('--datarootPath', default=None, type=str, help='dataset root (default: ./datasets)')
+    # additions (not in the reference)
+    parser.add_argument('--synthetic', action='store_true', help='train on synthetic BraTS-shaped batches (no dataset needed)')
+    parser.add_argument('--iters_per_epoch', default=0, type=int, help='with --synthetic: iterations per epoch (default 219 / global batch)')
+    parser.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'], help='activation storage (f32 = check mode)')
+    parser.add_argument('--no_graph', action='store_true', help='do not replay the step as a CUDA graph (N = 1)')
+    args = parser.parse_args(argv)
+
+    root = args.datarootPath or os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'datasets'))
+    args.datarootPath = root
+    args.datasetPath = os.path.abspath(os.path.join(root, args.datapath))
+    # kept for interface parity (options.py:50-51); this repository's loader implements the random 80^3 crop only
+    args.train_transforms = 'Compose([RandCrop3D((80,80,80)), RandomRotion(10), RandomIntensityChange((0.1,0.1)), RandomFlip(0), NumpyType((np.float32, np.int64)),])'
+    args.test_transforms = 'Compose([NumpyType((np.float32, np.int64)),])'
+    return args

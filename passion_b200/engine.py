@@ -35,9 +35,20 @@ class Trainer:
         self.optimizer = torch.optim.AdamW([{"params": model.parameters(), "lr": lr, "weight_decay": weight_decay}],
                                            betas=(0.9, 0.999), eps=1e-08, amsgrad=True, capturable=self.use_graph)
         self._graph = None
+        self._captured_warmup = None
+        if self.use_graph:                       # the LR lives in a device tensor so that a replayed graph sees updates
+            self._lr_t = torch.tensor(float(lr), device=dev)
+            self.optimizer.param_groups[0]["lr"] = self._lr_t
         self.reducer = _ddp.GradReducer(model, bucket_mb=bucket_mb) if distributed else None
         if self.reducer is not None:
             self.reducer.broadcast_parameters()
+
+    def set_lr(self, lr):
+        """lr_scheduler.py:42-43 (_adjust_learning_rate)."""
+        if self.use_graph:
+            self._lr_t.fill_(float(lr))
+        else:
+            self.optimizer.param_groups[0]["lr"] = lr
 
     def forward_loss(self, x, target, mask):
         outs = self.model(x, mask, target=target, temp=self.temp)
@@ -70,11 +81,12 @@ class Trainer:
         with torch.cuda.graph(self._graph):
             loss, parts = self._eager_step(*self._static)
         self._out = (loss, {k: v.detach() for k, v in parts.items()})
+        self._captured_warmup = self.warmup
 
     def step(self, x, target, mask):
         if not self.use_graph:
             return self._eager_step(x, target, mask)
-        if self._graph is None:
+        if self._graph is None or self._captured_warmup != self.warmup:     # the warm-up branch is baked into a capture
             self._capture(x, target, mask)
         for dst, src in zip(self._static, (x, target, mask)):
             dst.copy_(src, non_blocking=True)

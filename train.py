@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Training entry point with the reference's flags and loop shape (code/train.py:69-373), on the B200-native path.
+
+    python train.py --use_passion --model rfnet --batch_size 2 --synthetic --num_epochs 1
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 train.py --use_passion --batch_size 2 ...
+
+One process per GPU (torchrun) replaces torch.nn.DataParallel (train.py:90).  Per iteration the work is
+passion_b200.engine.Trainer.step (train.py:198-289); per epoch the LR schedule (lr_scheduler.py:15-17), the
+relative-preference update of imb_beta (train.py:325-335) and the reference-format checkpoint (train.py:358-364).
+Data: `<datasetPath>/vol/*_vol.npy` + `seg/*_seg.npy` with a random 80^3 crop (the numpy/scipy augmentation
+pipeline of the reference is CPU code outside this hot path), or --synthetic.
+"""
+import csv
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from options import args_parser
+from passion_b200.engine import Trainer
+from passion_b200.models import rfnet
+from passion_b200.train_step import poly_lr, preference_update
+
+MASK_ARRAY = np.array([[False, False, False, True], [False, True, False, False], [False, False, True, False],
+                       [True, False, False, False], [False, True, False, True], [False, True, True, False],
+                       [True, False, True, False], [False, False, True, True], [True, False, False, True],
+                       [True, True, False, False], [True, True, True, False], [True, False, True, True],
+                       [True, True, False, True], [False, True, True, True], [True, True, True, True]])   # train.py:42-45
+
+
+def read_split(path):
+    with open(path) as f:
+        return list(csv.DictReader(f))
+
+
+class Source:
+    """Yields (x f32 [B,4,80,80,80], one-hot target f64 [B,4,80,80,80], mask bool [B,4]) like the reference loader."""
+
+    def __init__(self, args, rows, rank, world):
+        self.args, self.rows, self.rank, self.world = args, rows, rank, world
+        self.rs = np.random.RandomState(args.seed + rank)
+        per_step = args.batch_size * world
+        self.iters = args.iters_per_epoch or max(1, len(rows) // per_step)
+
+    def _mask_id(self, row):
+        if self.args.mask_type == 'idt':
+            return int(row['mask_id'])
+        if self.args.mask_type == 'idt_drop':
+            return int(self.rs.choice(eval(row['pos_mask_ids']), 1)[0])
+        return int(self.rs.choice(15, 1)[0])
+
+    def batch(self, it):
+        B, S = self.args.batch_size, 80
+        xs, ys, ms = [], [], []
+        for b in range(B):
+            row = self.rows[(it * self.world * B + self.rank * B + b) % len(self.rows)]
+            if self.args.synthetic:
+                x = self.rs.standard_normal((4, S, S, S)).astype(np.float32)
+                y = self.rs.randint(0, 4, (S, S, S))
+            else:
+                vol = np.load(os.path.join(self.args.datasetPath, 'vol', row['data_name'] + '_vol.npy'))   # [H,W,Z,4]
+                seg = np.load(os.path.join(self.args.datasetPath, 'seg', row['data_name'] + '_seg.npy'))
+                o = [self.rs.randint(0, max(1, vol.shape[i] - S + 1)) for i in range(3)]
+                x = np.ascontiguousarray(vol[o[0]:o[0] + S, o[1]:o[1] + S, o[2]:o[2] + S].transpose(3, 0, 1, 2)).astype(np.float32)
+                y = seg[o[0]:o[0] + S, o[1]:o[1] + S, o[2]:o[2] + S].astype(np.int64)
+            xs.append(x)
+            ys.append(np.eye(4)[y].transpose(3, 0, 1, 2))                       # datasets_nii.py:150-153
+            ms.append(MASK_ARRAY[self._mask_id(row)])
+        return (torch.from_numpy(np.stack(xs)), torch.from_numpy(np.ascontiguousarray(np.stack(ys))),
+                torch.from_numpy(np.stack(ms)))
+
+
+def main():
+    args = args_parser()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.model != 'rfnet':
+        raise SystemExit('only --model rfnet is implemented on the B200-native path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    os.makedirs(args.savepath, exist_ok=True)
+    logging.basicConfig(level=logging.INFO if rank == 0 else logging.WARNING, format='%(asctime)s %(message)s',
+                        handlers=[logging.StreamHandler(), logging.FileHandler(os.path.join(args.savepath, f'{args.mask_type}_training.txt'))])
+    torch.manual_seed(args.seed)
+    np.random.seed(args.seed)
+
+    csv_path = os.path.join(args.datarootPath, args.imbmrpath)
+    if not os.path.exists(csv_path):
+        csv_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tests', 'golden', os.path.basename(args.imbmrpath))
+    rows = read_split(csv_path)
+    src = Source(args, rows, rank, world)
+    modal_num = torch.tensor(np.sum([eval(r['mask']) for r in rows], 0), dtype=torch.float32)      # train.py:163-166
+    logging.info('Training Imperfect Datasets with Mod.Flair-%d, Mod.T1c-%d, Mod.T1-%d, Mod.T2-%d', *modal_num.int().tolist())
+    iter_per_epoch = src.iters
+    modal_weight = iter_per_epoch / modal_num                                                       # train.py:171
+
+    model = rfnet.Model(num_cls=4).to(dev)
+    model.compute_dtype = torch.float32 if args.dtype == 'f32' else torch.bfloat16
+    if args.resume is not None and args.use_pretrain:                                               # train.py:144-152
+        sd = torch.load(args.resume, map_location=dev)['state_dict']
+        sd = {k[len('module.'):] if k.startswith('module.') else k: v for k, v in sd.items()}
+        model.load_state_dict({**model.state_dict(), **{k: v for k, v in sd.items() if k in model.state_dict()}})
+        logging.info('load ok')
+    trainer = Trainer(model, lr=args.lr, weight_decay=args.weight_decay, temp=args.temp, mask_type=args.mask_type,
+                      use_passion=args.use_passion, modal_weight=modal_weight, use_graph=not args.no_graph)
+    eta, eta_ext = 0.01, 1.5
+    for epoch in range(args.num_epochs):
+        lr = poly_lr(args.lr, epoch, args.num_epochs)
+        trainer.set_lr(lr)
+        trainer.warmup = epoch < args.region_fusion_start_epoch
+        acc = torch.zeros(4, device=dev)
+        t0 = time.time()
+        for i in range(iter_per_epoch):
+            x, target, mask = (t.to(dev, non_blocking=True) for t in src.batch(epoch * iter_per_epoch + i))
+            loss, parts = trainer.step(x, target, mask)
+            dist_m = parts['dist_m'].clone()
+            if world > 1:
+                dist.all_reduce(dist_m)
+            acc += dist_m / (modal_num.to(dev) if args.mask_type == 'idt' else iter_per_epoch)      # train.py:299-308
+            if rank == 0 and (i % 10 == 0 or i == iter_per_epoch - 1):
+                vals = torch.stack([loss, parts['fuse'], parts['prm'], parts['sep'], parts['kl'], parts['proto']]).tolist()   # one D2H
+                logging.info('Epoch %d/%d, Iter %d/%d, Loss %.4f, fuse_loss:%.4f, prm_loss:%.4f, sep_loss:%.4f, kl_loss:%.4f, proto_loss:%.4f',
+                             epoch + 1, args.num_epochs, i + 1, iter_per_epoch, *vals)
+        torch.cuda.synchronize()
+        logging.info('train time per epoch: %.2f s (%.2f samples/s)', time.time() - t0,
+                     iter_per_epoch * args.batch_size * world / (time.time() - t0))
+        if args.use_passion and epoch >= args.region_fusion_start_epoch:                            # train.py:325-335
+            beta, eta, rp_epoch = preference_update(trainer.imb_beta.cpu(), acc.cpu(), eta, epoch, eta_ext)
+            trainer.imb_beta.copy_(beta.to(dev))
+            logging.info('rp_epoch:%s imb_beta:%s', [round(v, 4) for v in rp_epoch.tolist()], [round(v, 4) for v in beta.tolist()])
+        if rank == 0:                                                                               # train.py:358-364
+            torch.save({'epoch': epoch, 'state_dict': {'module.' + k: v for k, v in model.state_dict().items()},
+                        'optim_dict': trainer.optimizer.state_dict()}, os.path.join(args.savepath, 'model_last.pth'))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
