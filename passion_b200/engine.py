@@ -29,9 +29,9 @@ class Trainer:
         if distributed is None:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
-        # The whole step (forward, loss mix, backward, AdamW) is sync-free and shape-static, so at N = 1 it can be
-        # replayed as ONE CUDA graph; the optimizer then keeps its step counter on the device (capturable).
-        self.use_graph = bool(use_graph) and not distributed
+        # The whole step (forward, loss mix, backward incl. the NCCL bucket all-reduces, AdamW) is sync-free and
+        # shape-static, so it is replayed as ONE CUDA graph; the optimizer keeps its step counter on the device.
+        self.use_graph = bool(use_graph)
         self.optimizer = torch.optim.AdamW([{"params": model.parameters(), "lr": lr, "weight_decay": weight_decay}],
                                            betas=(0.9, 0.999), eps=1e-08, amsgrad=True, capturable=self.use_graph)
         self._graph = None
