@@ -339,7 +339,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "samples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"RFNet+PASSION train step (CPU port of the reference algorithm), 4x{S}^3 crops scaled to 80^3-equivalent samples"},
+           "config": {"workload": f"RFNet+PASSION train step, B={B_PER_GPU}/GPU, 4x{S_CROP}^3 crops, idt masks from mr2468, temp 4, AdamW amsgrad",
+                      "sample": sample, "implementation": "CPU port of the reference algorithm (oracle/, PyTorch fp32, all host threads)"},
            "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}

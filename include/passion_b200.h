@@ -113,6 +113,10 @@ int pb_upsample_fwd(int dtype, const void* x, void* y, int n, int d, int h, int 
                     pb_stream_t stream);
 int pb_upsample_bwd(int dtype, const void* dy, void* dx, int n, int d, int h, int w, int c, int scale,
                     pb_stream_t stream);
+/* one axis of the separable adjoint: in [outer][n_big][inner] -> out [outer][n_small][inner] (inner % c == 0, c = the
+ * channel count that fixes the vector width); the host composes W, H, D with caller-allocated intermediates. */
+int pb_upsample_bwd_axis(int dtype, const void* in, void* out, long long outer, int n_big, int n_small,
+                         long long inner, int c, pb_stream_t stream);
 
 /* ---- region-aware modal fusion (models/blocks.py:495-517, 597-616) ----------------------
  * y  [n][v][K*C]  masked modality features (channel = k*C + c), storage dtype

@@ -51,6 +51,15 @@ def loss_mix(outputs, target, mask, imb_beta, modal_weight, *, mask_type="idt",
     return loss, parts
 
 
+def loss_mix_baseline(outputs, target, mask, *, mask_type="idt", num_cls=4):
+    """train.py:410-437 — the non-PASSION loss: fuse + sum_m sep_m + prm."""
+    fuse_pred, prm_bs, sep_bs = outputs
+    fuse_loss = (crit.softmax_weighted_loss_bs(fuse_pred, target, num_cls)
+                 + crit.dice_loss_bs(fuse_pred, target, num_cls)).sum()
+    sep_m = sep_bs.sum(0) if mask_type == "pdt" else (sep_bs * mask.float()).sum(0)
+    return fuse_loss + sep_m.sum() + prm_bs.sum(), dict(fuse=fuse_loss, prm=prm_bs.sum(), sep=sep_m.sum(), sep_m=sep_m)
+
+
 def preference_update(imb_beta, epoch_dist_m, eta, epoch, eta_ext=1.5):
     """train.py:325-335 (the non-warm-up branch).  Returns (new imb_beta, new eta, rp_epoch)."""
     avg = epoch_dist_m.sum() / 4.0

@@ -62,6 +62,7 @@ def load():
         "pb_inorm_lrelu_bwd": [i32, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp],
         "pb_upsample_fwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "pb_upsample_bwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+        "pb_upsample_bwd_axis": [i32, vp, vp, i64, i32, i32, i64, i32, vp],
         "pb_softmax4": [i32, vp, vp, i64, f32, vp],
         "pb_softmax4_bwd": [i32, vp, vp, vp, i64, f32, vp],
         "pb_cedice_fwd": [vp, vp, vp, i32, i32, i64, vp],

@@ -372,11 +372,13 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, vo
 //   B = x slab   rows q + kh*PW + kw + ...  read as an MN-major operand whose N-groups are the kw = 0..3 shifts of the
 //       same 8-channel plane (SBO = 16 B: a one-row shift) — again no im2col copy in shared memory.
 // One CTA owns one 8-channel chunk of the input and keeps all nine (kd,kh) accumulators (128 lanes x 32 columns each)
-// resident in TMEM while it sweeps its share of the volume; they are read out once at the end and added to dw with fp32
-// atomics.  M is 128 although only `co` rows are meaningful: rows beyond co read don't-care shared memory and are never
+// resident in TMEM (M = 64: rows 16w..16w+15 in lanes 32w..32w+15) while it sweeps its share of the volume; they are read out once at the end and added to dw with fp32
+// atomics.  M is 64 although only `co` rows are meaningful: rows beyond co read don't-care shared memory and are never
 // stored (each D row depends on its own A row only).
 constexpr int kWgSlotsX = 6, kWgSlotsY = 3;
-constexpr int kWgYSlotBytes = 16 * kTileM * 16;      // 16 M-groups x 128 rows x 16 B
+constexpr int kWgM = 64;                              // UMMA M: Cout <= 64 rows are meaningful, M = 64 halves the A-operand fetch
+constexpr int kWgYPlane = (kTileM + 1) * 16;          // co-chunk plane pitch: 129 rows, so the 8 M-groups of one K row hit 8 different banks
+constexpr int kWgYSlotBytes = (kWgM / 8) * kWgYPlane;  // 8 M-groups (co chunks)
 
 struct WgP {
     int N, D, H, W, C0, C1, Cout, reflect;
@@ -391,9 +393,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {       // bo
 template <int NCO>   // NCO = Cout / 8
 __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                                      const bf16* __restrict__ dy, float* __restrict__ dw, int* err) {
-    constexpr uint32_t IDESC = umma_idesc_mn(kTileM, 32);
+    constexpr uint32_t IDESC = umma_idesc_mn(kWgM, 32);
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* y_s = smem;                                              // [kWgSlotsY][16 planes][128 rows][16 B]
+    uint8_t* y_s = smem;                                              // [kWgSlotsY][8 planes][128 rows][16 B]
     uint8_t* x_s = smem + kWgSlotsY * kWgYSlotBytes;                  // [kWgSlotsX][slab_e rows][16 B]
     const int xslot_bytes = p.slab_e * 16;
     uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + (size_t)kWgSlotsX * xslot_bytes);
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
                         if (idx < kTileM * NCO) {
                             const int c = idx % NCO, r = idx / NCO;
                             const bool ok = yoff[i] >= 0;
-                            cp_async16(ybase + (uint32_t)(c * kTileM + r) * 16, ok ? py + yoff[i] : dy, ok ? 16u : 0u);
+                            cp_async16(ybase + (uint32_t)(c * kWgYPlane + r * 16), ok ? py + yoff[i] : dy, ok ? 16u : 0u);
                         }
                     }
                     cp_async_arrive_noinc(&fully[ys]);
@@ -519,18 +521,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
                     mbar_wait(&fully[ky % kWgSlotsY], (ky / kWgSlotsY) & 1, err, 14);
                     fence_proxy_async();
                     tc_fence_after();
-                    const uint64_t a0 = umma_desc(y_addr + (ky % kWgSlotsY) * kWgYSlotBytes, 128, kTileM * 16);   // LBO = 8 rows, SBO = co-chunk plane
+                    const uint64_t a0 = umma_desc(y_addr + (ky % kWgSlotsY) * kWgYSlotBytes, 128, kWgYPlane);   // LBO = 8 rows, SBO = co-chunk plane
+                    // consecutive MMAs go to DIFFERENT accumulators (9 independent (kd,kh) tiles per K step), so the
+                    // operand fetch of one overlaps the math of the previous instead of queueing behind a dependent chain
+                    uint64_t b0[3];
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd)
+                        b0[kd] = umma_desc(x_addr + ((kx + od + kd) % kWgSlotsX) * xslot_bytes, 128, 16);      // LBO = 8 rows, SBO = one-row (kw) shift
 #pragma unroll 1
-                    for (int kd = 0; kd < 3; ++kd) {
-                        const uint32_t sb = x_addr + ((kx + od + kd) % kWgSlotsX) * xslot_bytes;
-                        const uint64_t b0 = umma_desc(sb, 128, 16);                                            // LBO = 8 rows, SBO = one-row (kw) shift
+                    for (int ks = 0; ks < kTileM / 16; ++ks) {
 #pragma unroll
-                        for (int kh = 0; kh < 3; ++kh) {
-                            const uint32_t d_tmem = tmem_base + (kd * 3 + kh) * 32;
-                            const uint64_t b1 = b0 + (uint64_t)(uint32_t)(kh * p.PW);
+                        for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-                            for (int ks = 0; ks < kTileM / 16; ++ks) {
-                                umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b1 + (uint64_t)(16 * ks), IDESC, (first && ks == 0) ? 0u : 1u);
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const uint32_t d_tmem = tmem_base + (kd * 3 + kh) * 32;
+                                umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b0[kd] + (uint64_t)(uint32_t)(kh * p.PW + 16 * ks), IDESC,
+                                         (first && ks == 0) ? 0u : 1u);
                             }
                         }
                     }
@@ -552,7 +558,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
         if (blockIdx.x < items) {
             mbar_wait(done, 0, err, 15);
             tc_fence_after();
-            const int co = warp * 32 + lane;
+            // M = 64 accumulator layout (cute tmem_frg, "half subpartitions"): row m lives in lane (m % 16) + 32 * (m / 16)
+            const int co = lane < 16 ? warp * 16 + lane : p.Cout;
             const int cin = p.C0 + p.C1;
             for (int a = 0; a < 9; ++a) {
                 float v[32];

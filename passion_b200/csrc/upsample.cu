@@ -99,6 +99,47 @@ __global__ void __launch_bounds__(256) up_bwd_kernel(const T* __restrict__ dy, T
     }
 }
 
+// One axis of the (separable) adjoint: in [outer][n_big][inner] -> out [outer][n_small][inner],
+// out[i] = sum_o w(o, i) in[o].  The 3-D adjoint is the composition over W, H, D; the intermediates shrink by the
+// scale factor after every pass, so for x4 / x8 this replaces a (2s)^3-term gather per voxel by three 2s-term ones.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) up_bwd_axis_kernel(const T* __restrict__ in, T* __restrict__ out, long long outer, int n_big,
+                                                          int n_small, long long inner_vec, float ratio, long long total_vec) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total_vec; t += (long long)gridDim.x * blockDim.x) {
+        const long long iv = t % inner_vec;
+        const long long r = t / inner_vec;
+        const int i = (int)(r % n_small);
+        const long long o_idx = r / n_small;
+        int lo = 0, hi = n_big - 1;
+        if (ratio > 0.f) { lo = max(0, (int)floorf((i - 1) / ratio) - 1); hi = min(n_big - 1, (int)ceilf((i + 1) / ratio) + 1); }
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        const T* base = in + (o_idx * n_big) * inner_vec * VEC + iv * VEC;
+        for (int o = lo; o <= hi; ++o) {
+            const float wgt = axis_weight(o, i, ratio, n_small);
+            if (wgt == 0.f) continue;
+            float v[VEC];
+            VecIO<T, VEC>::load(base + (long long)o * inner_vec * VEC, v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
+        }
+        VecIO<T, VEC>::store(out + t * VEC, acc);
+    }
+}
+
+template <typename T, int VEC>
+int run_axis(const void* in, void* out, long long outer, int n_big, int n_small, long long inner, cudaStream_t st) {
+    const float ratio = n_big > 1 ? (float)(n_small - 1) / (float)(n_big - 1) : 0.f;
+    const long long inner_vec = inner / VEC;
+    const long long total_vec = outer * n_small * inner_vec;
+    long long blocks = (total_vec + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks < 1) blocks = 1;
+    up_bwd_axis_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)in, (T*)out, outer, n_big, n_small, inner_vec, ratio, total_vec);
+    return 0;
+}
+
 template <typename T, int VEC, bool FWD>
 int run(const void* a, void* b, int n, int d, int h, int w, int c, int scale, cudaStream_t st) {
     const float rd = d * scale > 1 ? (float)(d - 1) / (float)(d * scale - 1) : 0.f;
@@ -140,6 +181,24 @@ extern "C" int pb_upsample_fwd(int dtype, const void* x, void* y, int n, int d, 
 extern "C" int pb_upsample_bwd(int dtype, const void* dy, void* dx, int n, int d, int h, int w, int c, int scale, pb_stream_t stream) {
     PB_CHECK_ARG(dy && dx && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && scale >= 1, "bad argument");
     dispatch<false>(dtype, dy, dx, n, d, h, w, c, scale, (cudaStream_t)stream);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_upsample_bwd_axis(int dtype, const void* in, void* out, long long outer, int n_big, int n_small, long long inner,
+                                    int c, pb_stream_t stream) {
+    PB_CHECK_ARG(in && out && outer > 0 && n_big > 0 && n_small > 0 && inner > 0 && c > 0 && inner % c == 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int v = pb_vec_width(c);
+#define AX_CASE(T)                                                                      \
+    switch (v) {                                                                        \
+        case 8: run_axis<T, 8>(in, out, outer, n_big, n_small, inner, st); break;       \
+        case 4: run_axis<T, 4>(in, out, outer, n_big, n_small, inner, st); break;       \
+        case 2: run_axis<T, 2>(in, out, outer, n_big, n_small, inner, st); break;       \
+        default: run_axis<T, 1>(in, out, outer, n_big, n_small, inner, st); break;      \
+    }
+    if (dtype == PB_BF16) { AX_CASE(bf16) } else { AX_CASE(float) }
+#undef AX_CASE
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

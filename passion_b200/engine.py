@@ -12,7 +12,7 @@ autograd hooks on a side stream so that it overlaps the rest of backward (passio
 import torch
 
 from . import ddp as _ddp
-from .train_step import loss_mix
+from .train_step import loss_mix, loss_mix_baseline
 
 
 class Trainer:
@@ -52,6 +52,8 @@ class Trainer:
 
     def forward_loss(self, x, target, mask):
         outs = self.model(x, mask, target=target, temp=self.temp)
+        if len(outs) == 3:                   # use_passion = False (train.py:374-573)
+            return loss_mix_baseline(outs, target, mask, mask_type=self.mask_type, warmup=self.warmup)
         rp_allreduce = self.reducer.allreduce_small if self.reducer is not None else None
         return loss_mix(outs, target, mask, self.imb_beta, self.modal_weight, mask_type=self.mask_type,
                         warmup=self.warmup, rp_allreduce=rp_allreduce)

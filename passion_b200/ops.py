@@ -305,9 +305,22 @@ class _Upsample(torch.autograd.Function):
         lib = _lib.load()
         dy = dy.contiguous()
         n, d, h, w, c = ctx.shape
+        s = ctx.scale
         dx = torch.empty((n, d, h, w, c), dtype=dy.dtype, device=dy.device)
-        _run("upsample_bwd", f"c{c} x{ctx.scale}", (dx.numel() + dy.numel()) * dy.element_size(), 0,
-             lambda: lib.pb_upsample_bwd(_dt(dy), _p(dy), _p(dx), n, d, h, w, c, ctx.scale, _stream()))
+        if s <= 2:
+            _run("upsample_bwd", f"c{c} x{s}", (dx.numel() + dy.numel()) * dy.element_size(), 0,
+                 lambda: lib.pb_upsample_bwd(_dt(dy), _p(dy), _p(dx), n, d, h, w, c, s, _stream()))
+            return dx, None
+        # separable adjoint (W, then H, then D): the intermediates shrink by `s` after every pass
+        t1 = torch.empty((n, d * s, h * s, w, c), dtype=dy.dtype, device=dy.device)
+        t2 = torch.empty((n, d * s, h, w, c), dtype=dy.dtype, device=dy.device)
+        nb = (dy.numel() + 2 * t1.numel() + 2 * t2.numel() + dx.numel()) * dy.element_size()
+        _run("upsample_bwd", f"c{c} x{s} W", nb, 0,
+             lambda: lib.pb_upsample_bwd_axis(_dt(dy), _p(dy), _p(t1), n * d * s * h * s, w * s, w, c, c, _stream()))
+        _run("upsample_bwd", f"c{c} x{s} H", 0, 0,
+             lambda: lib.pb_upsample_bwd_axis(_dt(dy), _p(t1), _p(t2), n * d * s, h * s, h, w * c, c, _stream()))
+        _run("upsample_bwd", f"c{c} x{s} D", 0, 0,
+             lambda: lib.pb_upsample_bwd_axis(_dt(dy), _p(t2), _p(dx), n, d * s, d, h * w * c, c, _stream()))
         return dx, None
 
 

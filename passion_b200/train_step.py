@@ -45,6 +45,18 @@ def loss_mix(outputs, target, mask, imb_beta, modal_weight, *, mask_type="idt", 
     return loss, parts
 
 
+def loss_mix_baseline(outputs, target, mask, *, mask_type="idt", warmup=False, num_cls=4):
+    """The non-PASSION loop's loss (train.py:410-437): fuse + sum_m sep_m + prm, no preference gating."""
+    fuse_pred, prm_bs, sep_bs = outputs
+    fuse_loss = (criterions.softmax_weighted_loss_bs(fuse_pred, target, num_cls=num_cls)
+                 + criterions.dice_loss_bs(fuse_pred, target, num_cls=num_cls)).sum()
+    prm_loss = prm_bs.sum()
+    sep_m = sep_bs.sum(0) if mask_type == "pdt" else (sep_bs * mask.to(torch.float32)).sum(0)
+    sep_loss = sep_m.sum()
+    loss = fuse_loss * 0.0 + sep_loss + prm_loss * 0.0 if warmup else fuse_loss + sep_loss + prm_loss
+    return loss, dict(fuse=fuse_loss, prm=prm_loss, sep=sep_loss, sep_m=sep_m)
+
+
 def preference_update(imb_beta, epoch_dist_m, eta, epoch, eta_ext=1.5):
     """train.py:325-335 (non-warm-up branch), same order of operations, on CPU tensors."""
     avg = sum(epoch_dist_m) / 4.0

@@ -138,8 +138,11 @@ def main():
         if rank == 0:                                                                               # train.py:358-364
             torch.save({'epoch': epoch, 'state_dict': {'module.' + k: v for k, v in model.state_dict().items()},
                         'optim_dict': trainer.optimizer.state_dict()}, os.path.join(args.savepath, 'model_last.pth'))
-    if world > 1:
-        dist.destroy_process_group()
+    if world > 1:                     # captured graphs still hold the NCCL communicator: leave without tearing it down
+        torch.cuda.synchronize()
+        dist.barrier()
+        logging.shutdown()
+        os._exit(0)
 
 
 if __name__ == '__main__':
