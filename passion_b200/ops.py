@@ -103,6 +103,7 @@ def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
 # ---- tcgen05 implicit-GEMM path (csrc/conv3d_tc.cu) ------------------------------------------------------
 TC_ENABLED = os.environ.get("PB_TC", "1") != "0"
 WGRAD_TC = os.environ.get("PB_WGRAD_TC", "1") != "0"
+TC_STACKED = os.environ.get("PB_TCS", "0") != "0"        # kw-stacked variant of the fwd / dgrad implicit GEMM (measured: not faster)
 _tc_err = {}
 
 
@@ -144,6 +145,35 @@ def tc_weight_image(w, nt):
     return img.to(torch.bfloat16).contiguous()
 
 
+def _tcs_geom(cin, cout):
+    ntp, npad = ctypes.c_int(0), ctypes.c_int(0)
+    ok = _lib.load().pb_conv3d_tcs_geom(cin, cout, ctypes.byref(ntp), ctypes.byref(npad))
+    return (ntp.value, npad.value) if ok else None
+
+
+def tcs_weight_image(w, ntp, npad):
+    """fp32 [G, 27, cin, cout] -> bf16 kw-stacked image [G, cout/ntp, 9, max(2, cin/8), npad, 8]; row = kw*ntp + co."""
+    G, taps, cin, cout = w.shape
+    nchr = cin // 8
+    nch = max(2, nchr)
+    tiles = cout // ntp
+    w6 = w.reshape(G, 9, 3, nchr, 8, tiles, ntp)                       # [G, (kd,kh), kw, chunk, 8, tile, co]
+    img = torch.zeros((G, tiles, 9, nch, npad, 8), dtype=torch.float32, device=w.device)
+    img[:, :, :, :nchr, :3 * ntp, :] = w6.permute(0, 5, 1, 3, 2, 6, 4).reshape(G, tiles, 9, nchr, 3 * ntp, 8)
+    return img.to(torch.bfloat16).contiguous()
+
+
+def _tc_conv_call(lib, d, x0, x1, w, y0, y1, co0, co1, stats, err):
+    """Launch the tensor-core implicit GEMM (kw-stacked variant when enabled); returns the C status code."""
+    cin, cout = d.c0 + d.c1, co0 + co1
+    geom = _tcs_geom(cin, cout) if TC_STACKED else None
+    if geom is not None:
+        img = tcs_weight_image(w, *geom)
+        return lib.pb_conv3d_tcs(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
+    img = tc_weight_image(w, _tc_ntile(cin, cout))
+    return lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
+
+
 class _Conv3d(torch.autograd.Function):
     """y = conv(cat(x0, x1), w) (+ bias); optionally also the per-(n,c) sum / sum-of-squares of y."""
 
@@ -159,11 +189,9 @@ class _Conv3d(torch.autograd.Function):
         stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
         key, nb, fl = _conv_work(d, x0.element_size())
         if bias is None and _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
-            img = tc_weight_image(w, _tc_ntile(d.c0 + d.c1, cout))
             err = _tc_err_flag(x0.device)
             done = _run("conv3d_fwd_tc", key, nb, fl,
-                        lambda: lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y), None, cout, 0, _p(stats),
-                                                 _p(err), _stream()), allow_unsupported=True)
+                        lambda: _tc_conv_call(lib, d, x0, x1, w, y, None, cout, 0, stats, err), allow_unsupported=True)
         else:
             done = False
         if not done:
@@ -195,13 +223,12 @@ class _Conv3d(torch.autograd.Function):
                 # data gradient = the same implicit GEMM on dy with flipped taps / transposed channels and zero
                 # padding; the reflected-halo terms are added by a thin boundary kernel
                 wflip = w.flip(1).transpose(2, 3)
-                img = tc_weight_image(wflip, _tc_ntile(d.cout, d.c0 + d.c1))
                 dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0,
                               cout=d.c0 + d.c1, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
                 err = _tc_err_flag(dy.device)
                 done = _run("conv3d_dgrad_tc", key, nb, fl,
-                            lambda: lib.pb_conv3d_tc(ctypes.byref(dd), _p(dy), None, _p(img), _p(dx0), _p(dx1), d.c0, d.c1, None,
-                                                     _p(err), _stream()), allow_unsupported=True)
+                            lambda: _tc_conv_call(lib, dd, dy, None, wflip, dx0, dx1, d.c0, d.c1, None, err),
+                            allow_unsupported=True)
                 if done and pad_mode == "reflect":
                     _run("conv3d_dgrad_fix", key, 0, 0,
                          lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
