@@ -30,6 +30,14 @@ FLOP_PER_SAMPLE = 557.8e9
 BYTES_PER_SAMPLE = 14.7e9
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01_*_metrics.txt), keyed by kernel family; None = not captured yet.
+NCU_TRAFFIC_BYTES = {
+    "conv3d_fwd_tc": {"class": "c8->8 k3 s1 80x80x80 n8 g4", "bytes": 65.74e6 + 28.23e6, "source": "profiles/r01_conv_tc_metrics.txt"},
+    "conv3d_wgrad_tc": {"class": "c8->8 k3 s1 80x80x80 n8 g4", "bytes": 196.66e6 + 3.48e6, "source": "profiles/r01_wgrad_tc_metrics.txt"},
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -177,7 +185,11 @@ def run_ours(args):
     l0 = _lib.launch_count()
     n_prof = min(args.steps, 3)
     for i in range(n_prof):
+        # park the GPU behind a ~150 ms spin so the host enqueues the whole step ahead of it: the event pairs then
+        # bracket back-to-back kernel executions instead of host launch latency
+        torch.cuda._sleep(int(3e8))
         trainer._eager_step(*devb[i % nb])
+        torch.cuda.synchronize()
     sync()
     ops.TIMER = None
     launches = (_lib.launch_count() - l0) // n_prof * args.steps
@@ -236,7 +248,7 @@ def run_ours(args):
     top_cls = max(((k, d) for k, d in summ.items() if k[0] == top_name), key=lambda kv: kv[1]["ms"])
     ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": how,
+                "frac": round(ach / hbm_peak, 4), "traffic": NCU_TRAFFIC_BYTES.get(top_name), "peak_source": how,
                 "launches": int(top["calls"]), "avg_launch_ms": round(top["ms"] / top["calls"], 4),
                 "share_of_step": round(top["ms"] / ms_total, 3),
                 "top_class": {"key": top_cls[0][1], "ms_per_launch": round(top_cls[1]["ms"] / top_cls[1]["calls"], 4),
