@@ -16,26 +16,34 @@ __global__ void finalize_kernel(const double* __restrict__ stats, float* __restr
     mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// out = lrelu((y - mean) * rstd) (+ res);  one thread = VEC channels of one voxel
+// out = lrelu((y - mean) * rstd) (+ res);  one thread = VEC channels of one voxel, two independent vectors per
+// iteration (all loads are issued before the first use, doubling the bytes in flight per thread)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ mr,
                                                         const T* __restrict__ res, T* __restrict__ out,
                                                         long long total_vec, long long vox_c, int c, float slope) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-        const long long e = i * VEC;
-        const int n = (int)(e / vox_c);
-        const int c0 = (int)(e % c);
-        float v[VEC], r[VEC];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += 2 * stride) {
+        const long long i2 = i + stride;
+        const bool has2 = i2 < total_vec;
+        const long long e = i * VEC, e2 = (has2 ? i2 : i) * VEC;
+        float v[VEC], r[VEC], v2[VEC], r2[VEC];
         VecIO<T, VEC>::load(y + e, v);
-        if (res) VecIO<T, VEC>::load(res + e, r);
-        const float* m = mr + ((size_t)n * c + c0) * 2;
+        VecIO<T, VEC>::load(y + e2, v2);
+        if (res) { VecIO<T, VEC>::load(res + e, r); VecIO<T, VEC>::load(res + e2, r2); }
+        const float* m = mr + ((size_t)(e / vox_c) * c + (int)(e % c)) * 2;
+        const float* m2 = mr + ((size_t)(e2 / vox_c) * c + (int)(e2 % c)) * 2;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float xh = (v[j] - m[2 * j]) * m[2 * j + 1];
             xh = xh > 0.f ? xh : xh * slope;
             v[j] = res ? xh + r[j] : xh;
+            float xg = (v2[j] - m2[2 * j]) * m2[2 * j + 1];
+            xg = xg > 0.f ? xg : xg * slope;
+            v2[j] = res ? xg + r2[j] : xg;
         }
         VecIO<T, VEC>::store(out + e, v);
+        if (has2) VecIO<T, VEC>::store(out + e2, v2);
     }
 }
 
