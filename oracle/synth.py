@@ -75,21 +75,33 @@ def rfnet_param_shapes(num_cls=4):
 
 
 def make_state_dict(seed=1037, shapes=None, bias_scale=1.0):
-    """Kaiming-normal weights / uniform biases from numpy RandomState(seed), fp32 torch tensors."""
+    """Kaiming-normal weights / uniform biases from numpy RandomState(seed), fp32 torch tensors.
+    `shapes` = OrderedDict name -> shape (default: the RFNet table).  Rules by name/rank: conv / linear weights
+    N(0, 2/fan_in); their biases U(+-1/sqrt(fan_in)); 1-D "weight" (LayerNorm gain) 1 + 0.1 N; LayerNorm bias 0.1 N;
+    "*_pos" position embeddings 0.02 N (zeros in the reference — randomised so that the tests exercise them)."""
     rs = np.random.RandomState(seed)
     shapes = shapes or rfnet_param_shapes()
     sd = OrderedDict()
     fan = {}
     for name, shp in shapes.items():
-        if name.endswith("weight"):
+        shp = tuple(shp)
+        if name.endswith("_pos"):
+            sd[name] = torch.from_numpy((0.02 * rs.standard_normal(shp)).astype(np.float32))
+        elif name.endswith("weight") and len(shp) == 1:
+            fan[name[:-len("weight")]] = None
+            sd[name] = torch.from_numpy((1.0 + 0.1 * rs.standard_normal(shp)).astype(np.float32))
+        elif name.endswith("weight"):
             fan_in = int(np.prod(shp[1:]))
             fan[name[:-len("weight")]] = fan_in
             w = rs.standard_normal(shp).astype(np.float32) * np.float32(np.sqrt(2.0 / fan_in))
             sd[name] = torch.from_numpy(w)
         else:
-            fan_in = fan[name[:-len("bias")]]
-            bound = bias_scale / np.sqrt(fan_in)
-            sd[name] = torch.from_numpy(rs.uniform(-bound, bound, shp).astype(np.float32))
+            fan_in = fan.get(name[:-len("bias")])
+            if fan_in is None:
+                sd[name] = torch.from_numpy((0.1 * rs.standard_normal(shp)).astype(np.float32))
+            else:
+                bound = bias_scale / np.sqrt(fan_in)
+                sd[name] = torch.from_numpy(rs.uniform(-bound, bound, shp).astype(np.float32))
     return sd
 
 

@@ -54,11 +54,12 @@ def load():
         "pb_conv3d_dgrad": [cd, vp, vp, vp, vp, vp],
         "pb_conv3d_wgrad": [cd, vp, vp, vp, vp, vp],
         "pb_conv3d_tc_ntile": [i32, i32],
-        "pb_conv3d_tc": [cd, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
+        "pb_conv3d_tc": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_tcs_geom": [i32, i32, vp, vp],
-        "pb_conv3d_tcs": [cd, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
+        "pb_conv3d_tcs": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv3d_dgrad_reflect_fix": [cd, vp, vp, vp, vp, vp],
+        "pb_channel_stats": [i32, vp, vp, i32, i64, i32, vp],
         "pb_inorm_finalize": [vp, vp, i32, i32, i64, f32, vp],
         "pb_inorm_lrelu_fwd": [i32, vp, vp, vp, vp, i32, i64, i32, f32, vp],
         "pb_inorm_lrelu_bwd": [i32, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp],

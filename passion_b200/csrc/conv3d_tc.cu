@@ -122,8 +122,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // NCHR = real input chunks of 8 channels (1,2,4,8); NT = Cout tile (16 or 32)
 template <int NCHR, int NT>
 __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
-                                                               const bf16* __restrict__ wimg, bf16* __restrict__ y0,
-                                                               bf16* __restrict__ y1, double* __restrict__ stats, int* err) {
+                                                               const bf16* __restrict__ wimg, const float* __restrict__ bias,
+                                                               bf16* __restrict__ y0, bf16* __restrict__ y1,
+                                                               double* __restrict__ stats, int* err) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;             // a K=16 MMA step needs two 8-channel chunks (zero chunk if Cin = 8)
     constexpr int KS = NCH / 2;
     constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
@@ -289,6 +290,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
         const int cout = p.CO0 + p.CO1;
         const int cb0 = nt * NT;
         const int creal = min(NT, cout - cb0);                 // real channels in this tile (multiple of 8)
+        float bv[NT];
+#pragma unroll
+        for (int c = 0; c < NT; ++c) bv[c] = (bias != nullptr && c < creal) ? bias[(size_t)g * cout + cb0 + c] : 0.f;
         uint32_t j = 0;
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int dc = it % p.ND, r1 = it / p.ND;
@@ -311,6 +315,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
                 for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, v + c);
                 tc_fence_before();
                 mbar_arrive(&acc_empty[stage]);
+#pragma unroll
+                for (int c = 0; c < NT; ++c) v[c] += bv[c];
                 if (valid) {
                     const size_t vox = (((size_t)n * p.D + d0 + od) * p.H + h) * p.W + w;
 #pragma unroll
@@ -345,8 +351,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
 }
 
 template <int NCHR, int NT>
-int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, void* y0, void* y1, double* stats, int* err,
-              cudaStream_t st) {
+int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
+              double* stats, int* err, cudaStream_t st) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     const size_t w_bytes = (size_t)27 * NCH * NT * 16;
     const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 5) * 8 + 16;
@@ -359,7 +365,7 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, vo
     if (smem <= 110 * 1024) ctas *= 2;
     if (ctas < 1) ctas = 1;
     if (ctas > items) ctas = items;
-    kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg,
+    kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
                                                                     (bf16*)y0, (bf16*)y1, stats, err);
     return 0;
 }
@@ -395,8 +401,9 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 
 template <int NCHR>
 __global__ void __launch_bounds__(kThreads, 2) conv3_tcs_kernel(TcsP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
-                                                                const bf16* __restrict__ wimg, bf16* __restrict__ y0,
-                                                                bf16* __restrict__ y1, double* __restrict__ stats, int* err) {
+                                                                const bf16* __restrict__ wimg, const float* __restrict__ bias,
+                                                                bf16* __restrict__ y0, bf16* __restrict__ y1,
+                                                                double* __restrict__ stats, int* err) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     constexpr int KS = NCH / 2;
     const uint32_t idesc = umma_idesc(kTileM, p.np_);
@@ -596,6 +603,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tcs_kernel(TcsP p, const bf
                         a[4] += b1v.x + c1v.x; a[5] += b1v.y + c1v.y; a[6] += b1v.z + c1v.z; a[7] += b1v.w + c1v.w;
                     }
                     if (creal <= 8) epi_bar();                 // single chunk: the one buffer is rewritten next plane
+                    if (bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a[i] += bias[(size_t)g * cout + cb0 + c8 + i];
+                    }
                     if (valid) {
                         const int cb = cb0 + c8;
                         bf16* dst = cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0);
@@ -629,8 +640,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tcs_kernel(TcsP p, const bf
 }
 
 template <int NCHR>
-int launch_tcs(const TcsP& p, const void* x0, const void* x1, const void* wimg, void* y0, void* y1, double* stats, int* err,
-               cudaStream_t st) {
+int launch_tcs(const TcsP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
+               double* stats, int* err, cudaStream_t st) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     const size_t w_bytes = (size_t)9 * NCH * p.np_ * 16;
     const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kTileM * 16 + 128) * 4 +
@@ -644,7 +655,7 @@ int launch_tcs(const TcsP& p, const void* x0, const void* x1, const void* wimg, 
     if (smem <= 110 * 1024 && p.tmem_cols <= 256) ctas *= 2;
     if (ctas < 1) ctas = 1;
     if (ctas > items) ctas = items;
-    kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg,
+    kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
                                                                     (bf16*)y0, (bf16*)y1, stats, err);
     return 0;
 }
@@ -1116,8 +1127,8 @@ extern "C" int pb_conv3d_tc_ntile(int cin, int cout) {
     return 16;
 }
 
-extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, void* y0, void* y1,
-                            int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
+extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias,
+                            void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
     PB_CHECK_ARG(d && x0 && wimg && y0 && err_flag, "null pointer");
     PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 3 && d->stride == 1, "bf16, 3x3x3, stride 1 only");
     PB_CHECK_ARG(d->di == d->dout && d->hi == d->ho && d->wi == d->wo, "same-size output only");
@@ -1155,7 +1166,7 @@ extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
-#define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, y0, y1, stats, err_flag, st)
+#define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st)
     TC_CASE(1, 16); TC_CASE(2, 16); TC_CASE(4, 16); TC_CASE(8, 16);
     TC_CASE(1, 32); TC_CASE(2, 32); TC_CASE(4, 32); TC_CASE(8, 32);
 #undef TC_CASE
@@ -1215,8 +1226,8 @@ extern "C" int pb_conv3d_tcs_geom(int cin, int cout, int* ntp, int* np) {
     return 1;
 }
 
-extern "C" int pb_conv3d_tcs(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, void* y0, void* y1,
-                             int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
+extern "C" int pb_conv3d_tcs(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias,
+                             void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
     PB_CHECK_ARG(d && x0 && wimg && y0 && err_flag, "null pointer");
     PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 3 && d->stride == 1, "bf16, 3x3x3, stride 1 only");
     PB_CHECK_ARG(d->di == d->dout && d->hi == d->ho && d->wi == d->wo, "same-size output only");
@@ -1254,10 +1265,10 @@ extern "C" int pb_conv3d_tcs(const pb_conv_desc* d, const void* x0, const void* 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
     switch (nchr) {
-        case 1: rc = launch_tcs<1>(p, x0, x1, wimg, y0, y1, stats, err_flag, st); break;
-        case 2: rc = launch_tcs<2>(p, x0, x1, wimg, y0, y1, stats, err_flag, st); break;
-        case 4: rc = launch_tcs<4>(p, x0, x1, wimg, y0, y1, stats, err_flag, st); break;
-        case 8: rc = launch_tcs<8>(p, x0, x1, wimg, y0, y1, stats, err_flag, st); break;
+        case 1: rc = launch_tcs<1>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
+        case 2: rc = launch_tcs<2>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
+        case 4: rc = launch_tcs<4>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
+        case 8: rc = launch_tcs<8>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
         default: pb_set_error("conv3d_tcs: cin %d not supported", cin); break;
     }
     if (rc) return rc;

@@ -47,6 +47,37 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
     }
 }
 
+// per-(n,c) sum and sum of squares of an arbitrary tensor (statistics for a PRE-norm block, reference
+// models/blocks.py:312-316, where the normalised tensor is not a conv output of ours).  grid = (blocks_per_sample, n)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) channel_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, long long voxels, int c) {
+    extern __shared__ double ssum[];                          // [vpb][2*c]
+    const int n = blockIdx.y;
+    const int lanes = c / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
+    if ((int)threadIdx.x < tpb) {
+        const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes, c0 = cl * VEC;
+        double s1[VEC], s2[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
+        const T* xn = x + (size_t)n * voxels * c;
+        for (long long v = (long long)blockIdx.x * vpb + vl; v < voxels; v += (long long)gridDim.x * vpb) {
+            float xv[VEC];
+            VecIO<T, VEC>::load(xn + v * c + c0, xv);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { s1[j] += (double)xv[j]; s2[j] += (double)xv[j] * (double)xv[j]; }
+        }
+        double* r = ssum + (size_t)vl * 2 * c;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { r[2 * (c0 + j)] = s1[j]; r[2 * (c0 + j) + 1] = s2[j]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * c; i += 256) {
+        double s = 0.0;
+        for (int v = 0; v < vpb; ++v) s += ssum[(size_t)v * 2 * c + i];
+        atomicAdd(&stats[(size_t)n * c * 2 + i], s);
+    }
+}
+
 // per-(n,c): sum g, sum g*xhat  with g = dout * lrelu'(xhat).  grid = (blocks_per_sample, n);
 // a thread keeps the same VEC channels for all its voxels; block reduction in a fixed order (deterministic).
 template <typename T, int VEC>
@@ -182,6 +213,24 @@ extern "C" int pb_inorm_finalize(const double* stats, float* mr, int n, int c, l
     PB_CHECK_ARG(stats && mr && n > 0 && c > 0 && voxels > 0, "bad argument");
     const int nc = n * c;
     finalize_kernel<<<(nc + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, mr, nc, 1.0 / (double)voxels, eps);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_channel_stats(int dtype, const void* x, double* stats, int n, long long voxels, int c, pb_stream_t stream) {
+    PB_CHECK_ARG(x && stats && n > 0 && c > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(c <= 256 * pb_vec_width(c), "too many channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vw = pb_vec_width(c);
+    const int lanes = c / vw, vpb = 256 / lanes;
+    int bps = (int)((voxels + (long long)vpb * 8 - 1) / ((long long)vpb * 8));
+    const int cap = (148 * 8 + n - 1) / n;
+    if (bps > cap) bps = cap;
+    if (bps < 1) bps = 1;
+    const size_t smem = (size_t)vpb * 2 * c * sizeof(double);
+#define CS_CALL(T, V) channel_stats_kernel<T, V><<<dim3(bps, n), 256, smem, st>>>((const T*)x, stats, voxels, c)
+    if (dtype == PB_BF16) { VEC_SWITCH(bf16, c, CS_CALL) } else { VEC_SWITCH(float, c, CS_CALL) }
+#undef CS_CALL
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

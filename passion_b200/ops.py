@@ -163,15 +163,16 @@ def tcs_weight_image(w, ntp, npad):
     return img.to(torch.bfloat16).contiguous()
 
 
-def _tc_conv_call(lib, d, x0, x1, w, y0, y1, co0, co1, stats, err):
+def _tc_conv_call(lib, d, x0, x1, w, y0, y1, co0, co1, stats, err, bias=None):
     """Launch the tensor-core implicit GEMM (kw-stacked variant when enabled); returns the C status code."""
     cin, cout = d.c0 + d.c1, co0 + co1
     geom = _tcs_geom(cin, cout) if TC_STACKED else None
     if geom is not None:
         img = tcs_weight_image(w, *geom)
-        return lib.pb_conv3d_tcs(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
+        return lib.pb_conv3d_tcs(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y0), _p(y1), co0, co1, _p(stats), _p(err),
+                                 _stream())
     img = tc_weight_image(w, _tc_ntile(cin, cout))
-    return lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
+    return lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
 
 
 class _Conv3d(torch.autograd.Function):
@@ -188,10 +189,10 @@ class _Conv3d(torch.autograd.Function):
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
         stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
         key, nb, fl = _conv_work(d, x0.element_size())
-        if bias is None and _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
+        if _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
             err = _tc_err_flag(x0.device)
             done = _run("conv3d_fwd_tc", key, nb, fl,
-                        lambda: _tc_conv_call(lib, d, x0, x1, w, y, None, cout, 0, stats, err), allow_unsupported=True)
+                        lambda: _tc_conv_call(lib, d, x0, x1, w, y, None, cout, 0, stats, err, bias), allow_unsupported=True)
         else:
             done = False
         if not done:
@@ -313,6 +314,27 @@ def conv_in_lrelu(x0, w, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=
     voxels = y.shape[1] * y.shape[2] * y.shape[3]
     mr = inorm_finalize(stats, voxels)
     return _InormLrelu.apply(y, mr, res)
+
+
+def channel_stats(x):
+    """float64 [N, C, 2] (sum, sum of squares over the voxels) of a cl tensor; not differentiable by itself — the
+    InstanceNorm adjoint in _InormLrelu accounts for the dependence of the statistics on x."""
+    lib = _lib.load()
+    x = x.detach()
+    _chk(x)
+    n, c = x.shape[0], x.shape[-1]
+    voxels = x.numel() // (n * c)
+    stats = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    _run("channel_stats", f"c{c}", x.numel() * x.element_size(), 0,
+         lambda: lib.pb_channel_stats(_dt(x), _p(x), _p(stats), n, voxels, c, _stream()))
+    return stats
+
+
+def prenorm(x):
+    """InstanceNorm3d(affine=False) -> LeakyReLU(0.2) of an arbitrary cl tensor (the first half of
+    general_conv3d_prenorm, reference models/blocks.py:312-314)."""
+    voxels = x.numel() // (x.shape[0] * x.shape[-1])
+    return _InormLrelu.apply(x, inorm_finalize(channel_stats(x), voxels), None)
 
 
 class _Upsample(torch.autograd.Function):

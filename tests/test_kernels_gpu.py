@@ -50,6 +50,11 @@ CONV_CASES = [
     (16, 16, 16, 3, 1, "zeros", 1, 2, (12, 10, 14), False),
     (64, 0, 32, 3, 1, "reflect", 1, 2, (8, 10, 6), False),
     (16, 0, 64, 3, 1, "reflect", 2, 2, (6, 8, 10), False),
+    # biased 3x3 (pre-norm blocks of the mmFormer backbone) and wide channels
+    (16, 0, 16, 3, 1, "reflect", 1, 2, (10, 9, 12), True),
+    (8, 8, 8, 3, 1, "zeros", 2, 4, (8, 10, 9), True),
+    (128, 0, 64, 3, 1, "reflect", 1, 1, (4, 4, 4), True),
+    (64, 0, 128, 3, 2, "reflect", 1, 1, (4, 4, 4), True),
 ]
 
 
@@ -68,7 +73,7 @@ def test_conv3d(lib_built, case, dtype):
     # ---- float64 reference on the same (rounded) inputs
     xr = xq.double().requires_grad_(True)
     # the tcgen05 path multiplies bf16 weights (fp32 accumulate); give the reference the same rounded operands
-    uses_tc = ops._tc_eligible(dtype, k, stride, c0, c1, cout) and not has_bias
+    uses_tc = ops._tc_eligible(dtype, k, stride, c0, c1, cout)
     wr = (wt.to(torch.bfloat16) if uses_tc else wt).double().requires_grad_(True)
     ys = []
     npg = n // groups
@@ -100,7 +105,9 @@ def test_conv3d(lib_built, case, dtype):
     dwr = torch.stack([ops.kernel_layout(wr.grad[gi]) for gi in range(groups)])
     assert rel(wk.grad, dwr) < (5e-5 if dtype == torch.float32 else tol)
     if has_bias:
-        assert rel(bk.grad, gy.double().sum((0, 2, 3, 4))[None]) < 1e-3
+        npg_ = n // groups
+        ref_db = torch.stack([gy.double()[gi * npg_:(gi + 1) * npg_].sum((0, 2, 3, 4)) for gi in range(groups)])
+        assert rel(bk.grad, ref_db) < 1e-3
     ops.check_tc_errors()
 
 
