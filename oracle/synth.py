@@ -74,6 +74,74 @@ def rfnet_param_shapes(num_cls=4):
     return d
 
 
+def mmformer_param_shapes(num_cls=4, patch=5, basic=8, tdim=512, mlp=4096):
+    """state_dict names/shapes of mmformer.Model (mmformer.py:24-189, 329-379) in registration order
+    (a module's own Parameters — the four *_pos — come before its sub-modules)."""
+    d = OrderedDict()
+    mods = ("flair", "t1ce", "t1", "t2")
+    for m in mods:
+        d[f"{m}_pos"] = (1, patch ** 3, tdim)
+    for m in mods:
+        pre = f"{m}_encoder"
+        d[f"{pre}.e1_c1.weight"] = (basic, 1, 3, 3, 3)
+        d[f"{pre}.e1_c1.bias"] = (basic,)
+        _gc(d, f"{pre}.e1_c2", basic, basic, 3)
+        _gc(d, f"{pre}.e1_c3", basic, basic, 3)
+        for lvl in (2, 3, 4, 5):
+            c = basic * 2 ** (lvl - 1)
+            _gc(d, f"{pre}.e{lvl}_c1", c // 2, c, 3)
+            _gc(d, f"{pre}.e{lvl}_c2", c, c, 3)
+            _gc(d, f"{pre}.e{lvl}_c3", c, c, 3)
+    for m in mods:
+        d[f"{m}_encode_conv.weight"] = (tdim, basic * 16, 1, 1, 1)
+        d[f"{m}_encode_conv.bias"] = (tdim,)
+
+    def transformer(pre):
+        a = f"{pre}.cross_attention_list.0.fn"
+        d[f"{a}.norm.weight"] = (tdim,)
+        d[f"{a}.norm.bias"] = (tdim,)
+        d[f"{a}.fn.qkv.weight"] = (3 * tdim, tdim)
+        d[f"{a}.fn.proj.weight"] = (tdim, tdim)
+        d[f"{a}.fn.proj.bias"] = (tdim,)
+        f = f"{pre}.cross_ffn_list.0.fn"
+        d[f"{f}.norm.weight"] = (tdim,)
+        d[f"{f}.norm.bias"] = (tdim,)
+        d[f"{f}.fn.net.0.weight"] = (mlp, tdim)
+        d[f"{f}.fn.net.0.bias"] = (mlp,)
+        d[f"{f}.fn.net.3.weight"] = (tdim, mlp)
+        d[f"{f}.fn.net.3.bias"] = (tdim,)
+
+    for m in mods:
+        transformer(f"{m}_transformer")
+    transformer("multimodal_transformer")
+    d["multimodal_decode_conv.weight"] = (basic * 16 * 4, tdim * 4, 1, 1, 1)
+    d["multimodal_decode_conv.bias"] = (basic * 16 * 4,)
+
+    def dec_convs(pre):
+        for lvl in (4, 3, 2, 1):
+            c = basic * 2 ** (lvl - 1)
+            _gc(d, f"{pre}.d{lvl}_c1", c * 2, c, 3)
+            _gc(d, f"{pre}.d{lvl}_c2", c * 2, c, 3)
+            _gc(d, f"{pre}.d{lvl}_out", c, c, 1)
+
+    dec_convs("decoder_fuse")
+    for lvl in (4, 3, 2, 1):
+        d[f"decoder_fuse.seg_d{lvl}.weight"] = (num_cls, basic * 2 ** lvl, 1, 1, 1)
+        d[f"decoder_fuse.seg_d{lvl}.bias"] = (num_cls,)
+    d["decoder_fuse.seg_layer.weight"] = (num_cls, basic, 1, 1, 1)
+    d["decoder_fuse.seg_layer.bias"] = (num_cls,)
+    for lvl in (5, 4, 3, 2, 1):
+        c = basic * 2 ** (lvl - 1)
+        pre = f"decoder_fuse.RFM{lvl}.fusion_layer"
+        _gc(d, f"{pre}.0", c * num_cls, c, 1)
+        _gc(d, f"{pre}.1", c, c, 3)
+        _gc(d, f"{pre}.2", c, c, 1)
+    dec_convs("decoder_sep")
+    d["decoder_sep.seg_layer.weight"] = (num_cls, basic, 1, 1, 1)
+    d["decoder_sep.seg_layer.bias"] = (num_cls,)
+    return d
+
+
 def make_state_dict(seed=1037, shapes=None, bias_scale=1.0):
     """Kaiming-normal weights / uniform biases from numpy RandomState(seed), fp32 torch tensors.
     `shapes` = OrderedDict name -> shape (default: the RFNet table).  Rules by name/rank: conv / linear weights

@@ -409,6 +409,8 @@ int fill(const pb_conv_desc* d, ConvK& k) {
     return 0;
 }
 
+constexpr size_t kSmemBudget = 200 * 1024;   // dynamic shared memory the FFMA kernels may ask for (227 KB per CTA on sm_100a)
+
 int chunk_of(int c, int cap) {           // largest power of two <= cap dividing c
     int v = cap;
     while (v > 1 && c % v) v >>= 1;
@@ -451,7 +453,9 @@ int dispatch_fwd(const ConvK& k, const void* x0, const void* x1, const float* w,
                  cudaStream_t st) {
     int ci_v = chunk_of(k.C0, 8);
     if (k.C1) ci_v = chunk_of(k.C1, ci_v);
-    const int co_t = chunk_of(k.Cout, 16);
+    int co_t = chunk_of(k.Cout, 16);
+    // the CTA's weight slice (taps x Cin x co_t floats) lives in shared memory: narrow the tile for wide layers
+    while (co_t > 1 && (size_t)k.K * k.K * k.K * k.Cin * co_t * sizeof(float) > kSmemBudget) co_t >>= 1;
     switch (ci_v) {
         case 8:  return dispatch_fwd_co<T, 8>(co_t, k, x0, x1, w, bias, y, stats, st);
         case 4:  return dispatch_fwd_co<T, 4>(co_t, k, x0, x1, w, bias, y, stats, st);
@@ -488,6 +492,7 @@ int dispatch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, v
     const int co_v = chunk_of(k.Cout, 8);
     int ci_t = chunk_of(k.C0, 16);
     if (k.C1) ci_t = chunk_of(k.C1, ci_t);
+    while (ci_t > 1 && (size_t)k.K * k.K * k.K * k.Cout * ci_t * sizeof(float) > kSmemBudget) ci_t >>= 1;
     switch (co_v) {
         case 8:  return dispatch_dgrad_ci<T, 8>(ci_t, k, dy, wt, dx0, dx1, st, mo);
         case 4:  return dispatch_dgrad_ci<T, 4>(ci_t, k, dy, wt, dx0, dx1, st, mo);

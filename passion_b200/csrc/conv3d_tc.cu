@@ -290,9 +290,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
         const int cout = p.CO0 + p.CO1;
         const int cb0 = nt * NT;
         const int creal = min(NT, cout - cb0);                 // real channels in this tile (multiple of 8)
-        float bv[NT];
-#pragma unroll
-        for (int c = 0; c < NT; ++c) bv[c] = (bias != nullptr && c < creal) ? bias[(size_t)g * cout + cb0 + c] : 0.f;
+        const float4* bias4 = bias != nullptr ? reinterpret_cast<const float4*>(bias + (size_t)g * cout + cb0) : nullptr;
         uint32_t j = 0;
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int dc = it % p.ND, r1 = it / p.ND;
@@ -315,8 +313,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
                 for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, v + c);
                 tc_fence_before();
                 mbar_arrive(&acc_empty[stage]);
+                if (bias4 != nullptr) {                       // L1-resident broadcast loads; not kept in registers
 #pragma unroll
-                for (int c = 0; c < NT; ++c) v[c] += bv[c];
+                    for (int c4 = 0; c4 < NT / 4; ++c4) {
+                        if (c4 * 4 < creal) {
+                            const float4 b = __ldg(bias4 + c4);
+                            v[c4 * 4] += b.x; v[c4 * 4 + 1] += b.y; v[c4 * 4 + 2] += b.z; v[c4 * 4 + 3] += b.w;
+                        }
+                    }
+                }
                 if (valid) {
                     const size_t vox = (((size_t)n * p.D + d0 + od) * p.H + h) * p.W + w;
 #pragma unroll

@@ -55,6 +55,10 @@ CONV_CASES = [
     (8, 8, 8, 3, 1, "zeros", 2, 4, (8, 10, 9), True),
     (128, 0, 64, 3, 1, "reflect", 1, 1, (4, 4, 4), True),
     (64, 0, 128, 3, 2, "reflect", 1, 1, (4, 4, 4), True),
+    (128, 128, 64, 3, 1, "reflect", 1, 1, (5, 5, 5), True),
+    (128, 0, 128, 3, 1, "zeros", 1, 2, (5, 5, 5), True),
+    (512, 0, 128, 1, 1, "zeros", 1, 2, (5, 5, 5), True),
+    (32, 0, 8, 1, 1, "zeros", 1, 2, (6, 7, 8), True),
 ]
 
 

@@ -60,6 +60,17 @@ def test_state_dict_layout_matches_reference_table():
     m.load_state_dict(synth.make_state_dict(3))
 
 
+def test_mmformer_state_dict_layout_matches_reference_table():
+    from oracle import synth
+    from passion_b200.models import mmformer
+    m = mmformer.Model(4)
+    sd = m.state_dict()
+    shapes = synth.mmformer_param_shapes()
+    assert list(sd.keys()) == list(shapes.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+
+
 def test_preference_update_and_lr_match_oracle():
     from oracle import train_step_oracle as o
     from passion_b200 import train_step as t

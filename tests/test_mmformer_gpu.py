@@ -1,0 +1,169 @@
+"""End-to-end GPU parity of passion_b200.models.mmformer.Model (BASELINE.json configs[3]) against the
+CPU oracle (oracle/mmformer_oracle.py) and the committed golden fixtures written from the unmodified reference
+(oracle/gen_golden.py mmformer: 32^3 crops, patch_size 2, dropout off).  Same bars and the same calibration of the
+gradient bound by float64 sensitivity probes as tests/test_model_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["idtU", "idtS_t2only", "idtU_nopassion"]
+NAMES = ["fuse_prob", "prm_loss", "sep_loss", "kl_loss", "proto_loss", "dist"]
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _setup(case, dtype):
+    from oracle import synth
+    from oracle.masks import mask_id_of
+    from passion_b200.models import mmformer
+    z = np.load(os.path.join(GOLD, f"mmformer_passion_{case}.npz"), allow_pickle=True)
+    B, S = int(z["B"]), int(z["S"])
+    ids = [mask_id_of(m) for m in z["mask"]]
+    x, target, mask, _ = synth.make_batch(B, S, seed=int(z["seed"]), labels=str(z["labels_kind"]), mask_ids=ids)
+    sd = synth.make_state_dict(2051, synth.mmformer_param_shapes(patch=2))
+    old = mmformer.patch_size
+    mmformer.patch_size = 2                              # the reference's module-level constant (mmformer.py:21)
+    try:
+        model = mmformer.Model(num_cls=4).cuda()
+    finally:
+        mmformer.patch_size = old
+    model.load_state_dict(sd)
+    model.eval()                                         # dropout off, as in the fixtures
+    model.is_training, model.use_passion, model.mask_type = True, bool(z["use_passion"]), "idt"
+    model.compute_dtype = dtype
+    return z, model, sd, x, target, mask
+
+
+def _oracle(sd, x, target, mask, z, dtype=torch.float32):
+    from oracle import mmformer_oracle, train_step_oracle
+    P = {k: v.clone().to(dtype).requires_grad_(True) for k, v in sd.items()}
+    outs = mmformer_oracle.forward(P, x.to(dtype), mask, target, float(z["temp"]), use_passion=bool(z["use_passion"]))
+    if bool(z["use_passion"]):
+        loss, _ = train_step_oracle.loss_mix(outs, target, mask, torch.from_numpy(z["imb_beta"]).to(dtype),
+                                             torch.from_numpy(z["modal_weight"]).to(dtype))
+    else:
+        loss, _ = train_step_oracle.loss_mix_baseline(outs, target, mask)
+    loss.backward()
+    return outs, loss, {k: p.grad for k, p in P.items()}
+
+
+def _cuda_step(model, x, target, mask, z):
+    from passion_b200.train_step import loss_mix, loss_mix_baseline
+    dev = "cuda"
+    outs = model(x.to(dev), mask.to(dev), target=target.to(dev), temp=float(z["temp"]))
+    if bool(z["use_passion"]):
+        loss, parts = loss_mix(outs, target.to(dev), mask.to(dev), torch.from_numpy(z["imb_beta"]).to(dev),
+                               torch.from_numpy(z["modal_weight"]).to(dev))
+    else:
+        loss, parts = loss_mix_baseline(outs, target.to(dev), mask.to(dev))
+    loss.backward()
+    return outs, loss, parts
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fp32_check_mode(lib_built, case):
+    """Forward quantities within 1e-4 rel-L2 of the fp32 oracle and of the reference's golden outputs, argmax bit-exact;
+    gradients within 4x the float64 oracle's own sensitivity to a 2e-6 input perturbation (see test_model_gpu.py)."""
+    z, model, sd, x, target, mask = _setup(case, torch.float32)
+    outs, loss, parts = _cuda_step(model, x, target, mask, z)
+    o_outs, o_loss, o_grads = _oracle(sd, x, target, mask, z)
+    _, _, x_grads = _oracle(sd, x, target, mask, z, torch.float64)
+    probes = []
+    for seed in range(2):
+        g = torch.Generator().manual_seed(seed)
+        x_pert = x.double() * (1 + 2e-6 * torch.randn(x.shape, generator=g, dtype=torch.float64))
+        probes.append(_oracle(sd, x_pert, target, mask, z, torch.float64)[2])
+    for n, a, b in zip(NAMES, outs, o_outs):
+        assert rel(a, b.detach()) < 1e-4, (n, "vs oracle", rel(a, b.detach()))
+        gold = torch.from_numpy(z[n])
+        assert rel(a[:, :, ::2, ::2, ::2] if n == "fuse_prob" else a, gold) < 1e-4, (n, "vs golden")
+    assert abs(float(loss) - float(z["loss"])) < 1e-4 * max(1.0, abs(float(z["loss"])))
+    if "rp_iter" in z.files:
+        assert np.allclose(parts["rp_iter"].detach().cpu().numpy(), z["rp_iter"], atol=1e-3, equal_nan=True)
+    assert np.array_equal(outs[0].argmax(1).cpu().numpy().astype(np.int8), z["fuse_argmax"])
+    keys = [k for k, _ in model.named_parameters()]
+    params = dict(model.named_parameters())
+
+    def cat(d):
+        return torch.cat([(d[k].grad if isinstance(d[k], torch.nn.Parameter) else d[k]).flatten().cpu().double() for k in keys])
+    gx_all = cat(x_grads)
+    sens_g = max(rel(cat(pg), gx_all) for pg in probes)
+    scale = float(gx_all.norm())
+    bad = []
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        gx = x_grads[k]
+        if float(gx.norm()) < 1e-6 * scale:
+            # a conv bias whose output only ever feeds InstanceNorms: mathematically zero, rounding noise in fp32
+            assert float(p.grad.double().norm()) < 1e-4 * scale, (k, float(p.grad.norm()))
+            continue
+        sens = max(rel(pg[k], gx) for pg in probes)
+        r = rel(p.grad, gx)
+        if not r < max(1e-4, 4 * sens, 4 * sens_g):
+            bad.append((k, r, sens))
+    r_g = rel(cat(params), gx_all)
+    r_o = rel(cat(o_grads), gx_all)
+    print(f"mmformer {case}: global grad rel-L2 vs fp64 oracle: cuda fp32 {r_g:.2e} | cpu fp32 oracle {r_o:.2e} | "
+          f"fp64 sensitivity to 2e-6 input noise {sens_g:.2e}; violations {bad[:6]}")
+    assert not bad, bad[:8]
+    assert r_g < max(1e-4, 4 * sens_g)
+
+
+@pytest.mark.parametrize("case", ["idtU", "idtS_t2only"])
+def test_bf16(lib_built, case):
+    """bf16 storage of activations / gradients and bf16 tensor-core operands (fp32 accumulate, fp32 statistics and loss
+    math).  Bounds = the bf16 noise floor of this IN-normalised network with head-room (tests/test_model_gpu.py)."""
+    z, model, sd, x, target, mask = _setup(case, torch.bfloat16)
+    outs, loss, parts = _cuda_step(model, x, target, mask, z)
+    o_outs, o_loss, o_grads = _oracle(sd, x, target, mask, z)
+    r_p = rel(outs[0], o_outs[0].detach())
+    flat = torch.cat([p.grad.flatten().cpu() for k, p in model.named_parameters()])
+    flat_o = torch.cat([o_grads[k].flatten() for k, p in model.named_parameters()])
+    r = rel(flat, flat_o)
+    agree = float((outs[0].argmax(1).cpu() == o_outs[0].argmax(1)).float().mean())
+    print(f"mmformer {case}: bf16 global grad rel-L2 {r:.3e}; fuse_prob rel {r_p:.3e}; argmax agreement {agree:.4f}; "
+          f"losses {[round(rel(a, b.detach()), 4) for a, b in zip(outs[1:], o_outs[1:])]}")
+    assert r_p < 6e-2
+    for a, b in zip(outs[1:], o_outs[1:]):
+        assert rel(a, b.detach()) < 3e-2
+    assert abs(float(loss) - float(o_loss)) < 1e-2 * abs(float(o_loss))
+    assert r < 0.45
+    assert agree > 0.95, agree
+
+
+def test_inference_argmax(lib_built):
+    z, model, sd, x, target, mask = _setup("idtU", torch.float32)
+    model.is_training = False
+    with torch.no_grad():
+        prob = model(x.cuda(), mask.cuda())
+    assert np.array_equal(prob.argmax(1).cpu().numpy().astype(np.int8), z["infer_argmax"])
+
+
+def test_dropout_is_active_in_train_mode(lib_built):
+    """The reference's Transformer uses dropout 0.1 in .train() mode (mmformer.py:282): two forwards differ, and .eval()
+    restores determinism."""
+    z, model, sd, x, target, mask = _setup("idtU_nopassion", torch.float32)
+    model.is_training = False
+    with torch.no_grad():
+        model.train()
+        a = model(x.cuda(), mask.cuda())
+        b = model(x.cuda(), mask.cuda())
+        model.eval()
+        c = model(x.cuda(), mask.cuda())
+        d = model(x.cuda(), mask.cuda())
+    assert float((a - b).abs().max()) > 0
+    assert rel(c, d) < 1e-6
+
+
+def test_pdt_is_rejected(lib_built):
+    z, model, sd, x, target, mask = _setup("idtU_nopassion", torch.float32)
+    model.mask_type = "pdt"
+    with pytest.raises(NotImplementedError):
+        model(x.cuda(), mask.cuda())
