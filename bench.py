@@ -134,7 +134,7 @@ def run_ours(args):
     import torch.distributed as dist
     from passion_b200 import _lib, ops
     from passion_b200.engine import Trainer
-    from passion_b200.models import rfnet
+    from passion_b200.models import build_model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -149,7 +149,7 @@ def run_ours(args):
     _lib.load()
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     torch.manual_seed(1037)
-    model = rfnet.Model(num_cls=4).to(dev)
+    model = build_model(args.model, num_cls=4, crop=args.size).to(dev)
     model.compute_dtype = dtype
     use_graph = not args.no_graph
     trainer = Trainer(model, lr=2e-4, weight_decay=1e-4, temp=4.0, mask_type="idt", use_passion=True,
@@ -180,6 +180,8 @@ def run_ours(args):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     # ---- the same steps once more, eagerly, with every kernel launch bracketed by CUDA events on the launching
     #      stream: per-kernel durations for the roofline block and the launch count (events cannot sit inside a graph)
+    trainer._eager_step(*devb[0])                       # untimed: lets the caching allocator settle for eager execution
+    torch.cuda.synchronize()
     timer = ops.KernelTimer()
     ops.TIMER = timer
     l0 = _lib.launch_count()
@@ -257,10 +259,12 @@ def run_ours(args):
                 "step_hbm_frac": round(value / world * BYTES_PER_SAMPLE / 1e9 / hbm_peak, 4),
                 "step_tc_frac": round(value / world * FLOP_PER_SAMPLE / 1e12 / tc_peak, 4),
                 "families_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
-    out = {"metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+    label = {"rfnet": "RFNet", "mmformer": "mmFormer"}[args.model]
+    metric = METRIC if S == S_CROP else METRIC.replace("4x80^3", f"4x{S}^3")
+    out = {"metric": metric, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
-           "config": {"workload": f"RFNet+PASSION train step, B={B}/GPU, 4x{S}^3 crops, idt masks from mr2468, temp 4, AdamW amsgrad",
+           "config": {"workload": f"{label}+PASSION train step, B={B}/GPU, 4x{S}^3 crops, idt masks from mr2468, temp 4, AdamW amsgrad",
                       "global_batch": B * world, "parallelism": f"dp{world}",
                       "step_execution": "one CUDA graph replay per step" if use_graph else "eager launches",
                       "roofline_region": "eager re-run of the same steps with CUDA events around every kernel launch",
@@ -277,19 +281,23 @@ def run_ours(args):
             f.write("kernel | class | launches/step | ms/step | GB/s (algorithmic) | TFLOP/s\n")
             for r in rows:
                 f.write(f"{r[0]} | {r[1]} | {int(r[2])} | {r[3]:.3f} | {r[4]:.1f} | {r[5]:.2f}\n")
+    if args.model != "rfnet":
+        # SURVEY.md §8d's per-sample flop / byte figures are RFNet's; the secondary backbone reports kernel families only
+        roofline.pop("step_hbm_frac"); roofline.pop("step_tc_frac")
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(budget_s=30.0)
+        out["cpu_baseline"] = cpu_baseline(budget_s=30.0, model=args.model, S=S)
     print(json.dumps(out), flush=True)
     finish()
 
 
 # ----------------------------------------------------------------------------------------- CPU reference arm
-def _oracle_step_fn(S, B=1):
+def _oracle_step_fn(S, B=1, model="rfnet"):
     """One training step of the reference algorithm's CPU port (oracle/, torch fp32 on the host cores)."""
     import torch
-    from oracle import rfnet_oracle, synth, train_step_oracle
+    from oracle import mmformer_oracle, rfnet_oracle, synth, train_step_oracle
     torch.set_num_threads(os.cpu_count())
-    sd = synth.make_state_dict(1037)
+    fwd = rfnet_oracle.forward if model == "rfnet" else mmformer_oracle.forward
+    sd = synth.make_state_dict(1037, None if model == "rfnet" else synth.mmformer_param_shapes(patch=S // 16))
     P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     opt = torch.optim.AdamW([{"params": list(P.values()), "lr": 2e-4, "weight_decay": 1e-4}], betas=(0.9, 0.999),
                             eps=1e-8, amsgrad=True)
@@ -297,7 +305,7 @@ def _oracle_step_fn(S, B=1):
     beta, mw = torch.ones(4), modal_weight()
 
     def step():
-        outs = rfnet_oracle.forward(P, x, mask, target, 4.0)
+        outs = fwd(P, x, mask, target, 4.0)
         loss, _ = train_step_oracle.loss_mix(outs, target, mask, beta, mw)
         opt.zero_grad()
         loss.backward()
@@ -306,16 +314,16 @@ def _oracle_step_fn(S, B=1):
     return step
 
 
-def cpu_baseline(budget_s=30.0):
+def cpu_baseline(budget_s=30.0, model="rfnet", S=S_CROP):
     import torch
-    step16 = _oracle_step_fn(16)
+    step16 = _oracle_step_fn(16, 1, model)
     step16()                                            # library warm-up at a tiny size
-    step = _oracle_step_fn(S_CROP, 1)
+    step = _oracle_step_fn(S, 1, model)
     t0 = time.time()
     step()
     dt = time.time() - t0
     return {"value": round(1.0 / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 step, B=1, 4x{S_CROP}^3, fp32, oracle/ (PyTorch-CPU restatement of the reference), {dt:.1f} s"}
+            "sample": f"1 step, B=1, 4x{S}^3, fp32, oracle/ (PyTorch-CPU restatement of the reference), {dt:.1f} s"}
 
 
 def run_reference(args):
@@ -368,6 +376,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--size", type=int, default=S_CROP)
+    ap.add_argument("--model", default="rfnet", choices=["rfnet", "mmformer"],
+                    help="backbone; the headline metric (BASELINE.json configs[1]) is rfnet")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one CUDA graph")
     args = ap.parse_args()

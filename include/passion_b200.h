@@ -98,6 +98,16 @@ int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const void* x1, co
  * face); completes a zero-padding data gradient into the exact adjoint of the reflect-padded forward conv. */
 int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy, const float* wt, void* dx0, void* dx1,
                                 pb_stream_t stream);
+/* Data gradient of a REFLECT-padded 3x3x3 conv on the tensor cores (replaces the same autograd node as pb_conv3d_dgrad):
+ *   pb_conv3d_tc_full : "full" correlation of dy [n,di,hi,wi,c0] with the flipped/transposed weight image on the domain
+ *                       grown by one voxel per side (d->dout = di+2 ...).  Voxels whose value is final (not within two
+ *                       voxels' reach of a reflection: interior coordinate not in {1, size-2} on any axis) are written
+ *                       straight into y0|y1 [n,di,hi,wi,co0|co1]; all others into yext [n,di+2,hi+2,wi+2,co0+co1].
+ *   pb_reflect_fold   : y0|y1[v] = sum of the yext voxels that the reflect padding maps onto v, for the remaining voxels
+ *                       (per axis: {i+1} U {0 if i == 1} U {size+1 if i == size-2}).  bf16, sizes >= 4. */
+int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, void* y0, void* y1, int co0, int co1,
+                      void* yext, int* err_flag, pb_stream_t stream);
+int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int d, int h, int w, int co0, int co1, pb_stream_t stream);
 
 /* ---- InstanceNorm3d(affine=False, eps) + LeakyReLU(slope) (+ residual) -----------------
  * Replaces norm + activation of general_conv3d (blocks.py:18, :363, :367-369) and the encoder

@@ -7,7 +7,7 @@ import os
 
 def args_parser(argv=None):
     parser = argparse.ArgumentParser()
-    parser.add_argument('--model', default='rfnet', type=str, help='model name (rfnet is the B200-native path)')
+    parser.add_argument('--model', default='rfnet', type=str, help='model name: rfnet | mmformer (both on the B200-native kernels)')
     parser.add_argument('-batch_size', '--batch_size', default=1, type=int, help='Batch size (per GPU)')
     parser.add_argument('--lr', default=2e-4, type=float, help='base learning rate')
     parser.add_argument('--weight_decay', default=1e-4, type=float)
@@ -33,6 +33,7 @@ def args_parser(argv=None):
     parser.add_argument('--synthetic', action='store_true', help='train on synthetic BraTS-shaped batches (no dataset needed)')
     parser.add_argument('--iters_per_epoch', default=0, type=int, help='with --synthetic: iterations per epoch (default 219 / global batch)')
     parser.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'], help='activation storage (f32 = check mode)')
+    parser.add_argument('--crop_size', default=80, type=int, help='edge of the random training crop (reference: 80; mmformer needs a multiple of 16)')
     parser.add_argument('--no_graph', action='store_true', help='do not replay the step as a CUDA graph (N = 1)')
     args = parser.parse_args(argv)
 

@@ -24,12 +24,17 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kProducerThreads = 96;
 constexpr int kSlots = 6;               // input-plane ring: 3 planes in use by the MMAs + 3 planes of prefetch
-constexpr int kMaxCopies = 16;          // 16-B copies per producer thread and plane
+constexpr int kMaxCopies = 16;          // 16-B copies per producer thread and plane ...
+constexpr int kMaxCopiesWide = 20;      // ... and for the 64-channel variants (NCHR = 8, which have registers to spare)
+__host__ __device__ constexpr int max_copies(int nchr) { return nchr >= 8 ? kMaxCopiesWide : kMaxCopies; }
+constexpr int kWgCopies = 5;            // weight-gradient kernels: slab rows per producer thread (planes up to W = 174)
 constexpr int kTileM = 128;
 
 struct TcP {
     int N, D, H, W, C0, C1, CO0, CO1;   // inputs x0|x1 (concat), outputs y0|y1 (split)
     int reflect;
+    int inset;                          // 1: the output domain is the input grown by one voxel per side ("full" correlation,
+                                        // zero padding 2) — the data-gradient of a reflect-padded conv before folding
     int PW, QT, DCH, ND, npg, groups;
     int slab_need, slab_e;              // rows needed / padded rows per chunk plane of a slab
     int nt_tiles;
@@ -123,12 +128,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 template <int NCHR, int NT>
 __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                                const bf16* __restrict__ wimg, const float* __restrict__ bias,
-                                                               bf16* __restrict__ y0, bf16* __restrict__ y1,
+                                                               bf16* __restrict__ y0, bf16* __restrict__ y1, bf16* __restrict__ yext,
                                                                double* __restrict__ stats, int* err) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;             // a K=16 MMA step needs two 8-channel chunks (zero chunk if Cin = 8)
     constexpr int KS = NCH / 2;
     constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
     constexpr uint32_t IDESC = umma_idesc(kTileM, NT);
+    // input extent (= output extent unless p.inset)
+    const int Di = p.D - 2 * p.inset, Hi = p.H - 2 * p.inset, Wi = p.W - 2 * p.inset;
     extern __shared__ __align__(128) uint8_t smem[];
     const int w_bytes = 27 * NCH * NT * 16;
     uint8_t* w_s = smem;
@@ -181,41 +188,41 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
             const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
             const int d0 = dc * p.DCH, q0 = qt * kTileM;
             const int nout = min(p.DCH, p.D - d0);
-            int soff[kMaxCopies];                              // element offset inside the source plane, -1 = zero fill
-            uint32_t doff[kMaxCopies];                         // byte offset inside the slot
+            int soff[max_copies(NCHR)];                              // element offset inside the source plane, -1 = zero fill
+            uint32_t doff[max_copies(NCHR)];                         // byte offset inside the slot
             uint32_t from1 = 0;
 #pragma unroll
-            for (int i = 0; i < kMaxCopies; ++i) {
+            for (int i = 0; i < max_copies(NCHR); ++i) {
                 const int idx = pt + i * kProducerThreads;
                 soff[i] = -1; doff[i] = 0;
                 if (idx < copies) {
                     const int ch = idx % NCHR, e = idx / NCHR;
                     const int f = q0 + e;
                     const int hp = f / p.PW, wp = f - hp * p.PW;
-                    int h = hp - 1, w = wp - 1;
+                    int h = hp - 1 - p.inset, w = wp - 1 - p.inset;
                     bool ok = hp < p.H + 2;
-                    if (p.reflect) { h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); ok = ok && h >= 0 && h < p.H; }
-                    else ok = ok && h >= 0 && h < p.H && w >= 0 && w < p.W;
+                    if (p.reflect) { h = reflect_idx(h, Hi); w = reflect_idx(w, Wi); ok = ok && h >= 0 && h < Hi; }
+                    else ok = ok && h >= 0 && h < Hi && w >= 0 && w < Wi;
                     doff[i] = (uint32_t)(ch * p.slab_e + e) * 16;
                     if (ok) {
-                        if (ch < c0ch) soff[i] = (h * p.W + w) * p.C0 + ch * 8;
-                        else { soff[i] = (h * p.W + w) * p.C1 + (ch - c0ch) * 8; from1 |= 1u << i; }
+                        if (ch < c0ch) soff[i] = (h * Wi + w) * p.C0 + ch * 8;
+                        else { soff[i] = (h * Wi + w) * p.C1 + (ch - c0ch) * 8; from1 |= 1u << i; }
                     }
                 }
             }
             for (int pl = 0; pl < nout + 2; ++pl, ++k) {
                 const int slot = k % kSlots;
                 mbar_wait(&empty[slot], ((k / kSlots) & 1) ^ 1, err, 1);
-                int dp = d0 - 1 + pl;
+                int dp = d0 - 1 + pl - p.inset;
                 bool plane_ok = true;
-                if (p.reflect) dp = reflect_idx(dp, p.D); else plane_ok = dp >= 0 && dp < p.D;
+                if (p.reflect) dp = reflect_idx(dp, Di); else plane_ok = dp >= 0 && dp < Di;
                 if (!plane_ok) dp = 0;
-                const size_t plane = ((size_t)n * p.D + dp) * p.H * p.W;
+                const size_t plane = ((size_t)n * Di + dp) * Hi * Wi;
                 const bf16* p0 = x0 + plane * p.C0;
                 const bf16* p1 = x1 + plane * p.C1;
                 const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
 #pragma unroll
-                for (int i = 0; i < kMaxCopies; ++i) {
+                for (int i = 0; i < max_copies(NCHR); ++i) {
                     if (pt + i * kProducerThreads < copies) {
                         const bool ok = plane_ok && soff[i] >= 0;
                         const bf16* src = ((from1 >> i) & 1u) ? p1 : p0;
@@ -300,6 +307,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
             const int f = qt * kTileM + warp * 32 + lane;
             const int h = f / p.PW, w = f - h * p.PW;
             const bool valid = h < p.H && w < p.W;
+            // inset mode: voxels that need no folding go straight to their final place, the rest to the extended buffer
+            const int hi = h - 1, wi = w - 1;
+            const bool hw_inside = hi >= 0 && hi < Hi && wi >= 0 && wi < Wi;
+            const bool hw_shell = hi == 1 || hi == Hi - 2 || wi == 1 || wi == Wi - 2;
             float s1[NT], s2[NT];
 #pragma unroll
             for (int c = 0; c < NT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
@@ -323,12 +334,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
                     }
                 }
                 if (valid) {
-                    const size_t vox = (((size_t)n * p.D + d0 + od) * p.H + h) * p.W + w;
+                    size_t vox = (((size_t)n * p.D + d0 + od) * p.H + h) * p.W + w;
+                    bool to_ext = false;
+                    if (p.inset) {
+                        const int di = d0 + od - 1;
+                        if (hw_inside && di >= 0 && di < Di && !(hw_shell || di == 1 || di == Di - 2))
+                            vox = (((size_t)n * Di + di) * Hi + hi) * Wi + wi;
+                        else
+                            to_ext = true;
+                    }
 #pragma unroll
                     for (int c8 = 0; c8 < NT / 8; ++c8) {
                         if (c8 * 8 < creal) {
                             const int cb = cb0 + c8 * 8;
-                            bf16* dst = cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0);
+                            bf16* dst = to_ext ? yext + vox * cout + cb
+                                               : (cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0));
                             VecIO<bf16, 8>::store(dst, v + c8 * 8);
 #pragma unroll
                             for (int c = 0; c < 8; ++c) { s1[c8 * 8 + c] += v[c8 * 8 + c]; s2[c8 * 8 + c] += v[c8 * 8 + c] * v[c8 * 8 + c]; }
@@ -356,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
 }
 
 template <int NCHR, int NT>
-int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
+int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1, void* yext,
               double* stats, int* err, cudaStream_t st) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     const size_t w_bytes = (size_t)27 * NCH * NT * 16;
@@ -371,7 +391,7 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, co
     if (ctas < 1) ctas = 1;
     if (ctas > items) ctas = items;
     kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
-                                                                    (bf16*)y0, (bf16*)y1, stats, err);
+                                                                    (bf16*)y0, (bf16*)y1, (bf16*)yext, stats, err);
     return 0;
 }
 
@@ -465,11 +485,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tcs_kernel(TcsP p, const bf
             const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
             const int d0 = dc * p.DCH, q0 = qt * kTileOut;
             const int nout = min(p.DCH, p.D - d0);
-            int soff[kMaxCopies];
-            uint32_t doff[kMaxCopies];
+            int soff[max_copies(NCHR)];
+            uint32_t doff[max_copies(NCHR)];
             uint32_t from1 = 0;
 #pragma unroll
-            for (int i = 0; i < kMaxCopies; ++i) {
+            for (int i = 0; i < max_copies(NCHR); ++i) {
                 const int idx = pt + i * kProducerThreads;
                 soff[i] = -1; doff[i] = 0;
                 if (idx < copies) {
@@ -499,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tcs_kernel(TcsP p, const bf
                 const bf16* p1 = x1 + plane * p.C1;
                 const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
 #pragma unroll
-                for (int i = 0; i < kMaxCopies; ++i) {
+                for (int i = 0; i < max_copies(NCHR); ++i) {
                     if (pt + i * kProducerThreads < copies) {
                         const bool ok = plane_ok && soff[i] >= 0;
                         const bf16* src = ((from1 >> i) & 1u) ? p1 : p0;
@@ -738,10 +758,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
             const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
             const int d0 = dc * p.DCH, q0 = qt * kTileM;
             const int nout = min(p.DCH, p.D - d0);
-            int soff[4];                                   // x slab rows of this thread (slab_need <= 4 * 96)
+            int soff[kWgCopies];                           // x slab rows of this thread (slab_need <= kWgCopies * 96)
             int yoff[2 * NCO];                             // dy copies of this thread (128 * NCO <= 2 * NCO * 96)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kWgCopies; ++i) {
                 const int e = pt + i * kProducerThreads;
                 soff[i] = -1;
                 if (e < p.slab_need) {
@@ -775,7 +795,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
                 const bf16* pp = xsrc + ((size_t)n * p.D + dp) * p.H * p.W * cs;
                 const uint32_t sbase = smem_u32(x_s + (size_t)slot * xslot_bytes);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < kWgCopies; ++i) {
                     const int e = pt + i * kProducerThreads;
                     if (e < p.slab_need) {
                         const bool ok = plane_ok && soff[i] >= 0;
@@ -944,7 +964,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_wgrad_tc8_kernel(WgP p, con
             const int d0 = dc * p.DCH, u0 = qt * kTileM;
             const int nout = min(p.DCH, p.D - d0);
             int soff[2];                                   // x slab rows of this thread (131 <= 2 * 96)
-            int yoff[4];                                   // dy slab rows of this thread (128 + 2*PW <= 4 * 96)
+            int yoff[kWgCopies];                           // dy slab rows of this thread (128 + 2*PW <= kWgCopies * 96)
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int e = pt + i * kProducerThreads;
@@ -960,7 +980,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_wgrad_tc8_kernel(WgP p, con
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kWgCopies; ++i) {
                 const int e = pt + i * kProducerThreads;
                 yoff[i] = -1;
                 if (e < yrows) {
@@ -995,7 +1015,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_wgrad_tc8_kernel(WgP p, con
                     const bf16* py = dy + ((size_t)n * p.D + d0 + pl - 1) * p.H * p.W * p.Cout;
                     const uint32_t ybase = smem_u32(y_s + (size_t)ys * yslot_bytes);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < kWgCopies; ++i) {
                         const int e = pt + i * kProducerThreads;
                         if (e < yrows) {
                             const bool ok = yoff[i] >= 0;
@@ -1087,7 +1107,7 @@ int launch_wgrad_tc8(WgP p, const void* x0, const void* x1, const void* dy, floa
     p.slab_need = kTileM + 3;
     p.slab_e = (p.slab_need + 7) & ~7;
     const int yrows = kTileM + 2 * p.PW;
-    if (yrows > 4 * kProducerThreads) { pb_set_error("conv3d_wgrad_tc8: dy slab of %d rows exceeds the producer budget", yrows); return PB_EUNSUPPORTED; }
+    if (yrows > kWgCopies * kProducerThreads) { pb_set_error("conv3d_wgrad_tc8: dy slab of %d rows exceeds the producer budget", yrows); return PB_EUNSUPPORTED; }
     const int target = 148 * 4 / (p.groups * p.nchunks) + 1;
     int nd = 1;
     while (p.npg * p.QT * nd < target && (p.D + nd) / (nd + 1) >= 8) ++nd;
@@ -1132,11 +1152,88 @@ extern "C" int pb_conv3d_tc_ntile(int cin, int cout) {
     return 16;
 }
 
+namespace {
+int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
+             void* yext, int inset, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
+}
+
 extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias,
                             void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
     PB_CHECK_ARG(d && x0 && wimg && y0 && err_flag, "null pointer");
-    PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 3 && d->stride == 1, "bf16, 3x3x3, stride 1 only");
     PB_CHECK_ARG(d->di == d->dout && d->hi == d->ho && d->wi == d->wo, "same-size output only");
+    return tc_entry(d, x0, x1, wimg, bias, y0, y1, nullptr, 0, co0, co1, stats, err_flag, stream);
+}
+
+extern "C" int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, void* y0, void* y1, int co0, int co1,
+                                 void* yext, int* err_flag, pb_stream_t stream) {
+    PB_CHECK_ARG(d && x && wimg && y0 && yext && err_flag, "null pointer");
+    PB_CHECK_ARG(d->dout == d->di + 2 && d->ho == d->hi + 2 && d->wo == d->wi + 2, "output must be the input grown by one voxel per side");
+    PB_CHECK_ARG(d->pad_mode == PB_PAD_ZERO && d->c1 == 0, "zero padding, single source");
+    PB_CHECK_ARG(d->di >= 4 && d->hi >= 4 && d->wi >= 4, "sizes >= 4");
+    return tc_entry(d, x, nullptr, wimg, nullptr, y0, y1, yext, 1, co0, co1, nullptr, err_flag, stream);
+}
+
+namespace {
+
+// dx[i] = sum of the extended-domain values that reflect onto i: per axis {i+1} U {0 if i == 1} U {size+1 if i == size-2}
+__device__ __forceinline__ int fold_sources(int i, int size, int* src) {
+    int n = 0;
+    src[n++] = i + 1;
+    if (i == 1) src[n++] = 0;
+    if (i == size - 2) src[n++] = size + 1;
+    return n;
+}
+
+__global__ void reflect_fold_kernel(const bf16* __restrict__ ext, bf16* __restrict__ y0, bf16* __restrict__ y1, int N, int D, int H,
+                                    int W, int CO0, int CO1) {
+    const int C = CO0 + CO1, C8 = C >> 3;
+    const long long total = (long long)N * D * H * W * C8;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % C8);
+        long long v = t / C8;
+        const int w = (int)(v % W); v /= W;
+        const int h = (int)(v % H); v /= H;
+        const int d = (int)(v % D);
+        const int n = (int)(v / D);
+        if (!(d == 1 || d == D - 2 || h == 1 || h == H - 2 || w == 1 || w == W - 2)) continue;
+        int sd[3], sh[3], sw[3];
+        const int nd = fold_sources(d, D, sd), nh = fold_sources(h, H, sh), nw = fold_sources(w, W, sw);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int a = 0; a < nd; ++a)
+            for (int b = 0; b < nh; ++b)
+                for (int c = 0; c < nw; ++c) {
+                    float x[8];
+                    VecIO<bf16, 8>::load(ext + ((((size_t)n * (D + 2) + sd[a]) * (H + 2) + sh[b]) * (W + 2) + sw[c]) * C + c8 * 8, x);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] += x[i];
+                }
+        const size_t vox = (((size_t)n * D + d) * H + h) * W + w;
+        const int cb = c8 * 8;
+        bf16* dst = cb < CO0 ? y0 + vox * CO0 + cb : y1 + vox * CO1 + (cb - CO0);
+        VecIO<bf16, 8>::store(dst, acc);
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int d, int h, int w, int co0, int co1,
+                               pb_stream_t stream) {
+    PB_CHECK_ARG(yext && y0 && (co1 == 0 || y1), "null pointer");
+    PB_CHECK_ARG(co0 % 8 == 0 && co1 % 8 == 0 && co0 > 0 && d >= 4 && h >= 4 && w >= 4, "bad shape");
+    const long long total = (long long)n * d * h * w * ((co0 + co1) / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    reflect_fold_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)yext, (bf16*)y0, (bf16*)y1, n, d, h, w, co0, co1);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+namespace {
+int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
+             void* yext, int inset, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
+    PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 3 && d->stride == 1, "bf16, 3x3x3, stride 1 only");
     const int cin = d->c0 + d->c1, cout = co0 + co1;
     PB_CHECK_ARG(cout == d->cout && co0 % 8 == 0 && co1 % 8 == 0 && (co1 == 0 || y1), "bad output split");
     PB_CHECK_ARG(d->c0 % 8 == 0 && d->c1 % 8 == 0 && (d->c1 == 0 || x1), "channels must be multiples of 8");
@@ -1144,8 +1241,9 @@ extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x
     PB_CHECK_ARG(NT != 0, "unsupported channel class");
     PB_CHECK_ARG(d->groups >= 1 && d->n % d->groups == 0, "bad groups");
     TcP p;
-    p.N = d->n; p.D = d->di; p.H = d->hi; p.W = d->wi; p.C0 = d->c0; p.C1 = d->c1; p.CO0 = co0; p.CO1 = co1;
+    p.N = d->n; p.D = d->dout; p.H = d->ho; p.W = d->wo; p.C0 = d->c0; p.C1 = d->c1; p.CO0 = co0; p.CO1 = co1;
     p.reflect = d->pad_mode == PB_PAD_REFLECT;
+    p.inset = inset;
     PB_CHECK_ARG(!p.reflect || (p.D >= 2 && p.H >= 2 && p.W >= 2), "reflect padding needs size >= 2");
     p.PW = p.W + 2;
     p.QT = (p.H * p.PW + kTileM - 1) / kTileM;
@@ -1165,13 +1263,13 @@ extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x
     while (se % 8 != want % 8) ++se;
     p.slab_e = se;
     p.w_tile_bytes = (long long)27 * nch * NT * 16;
-    if (p.slab_need * nchr > kMaxCopies * kProducerThreads) {
+    if (p.slab_need * nchr > max_copies(nchr) * kProducerThreads) {
         pb_set_error("conv3d_tc: plane slab of %d x %d copies exceeds the producer budget", p.slab_need, nchr);
         return PB_EUNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
-#define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st)
+#define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
     TC_CASE(1, 16); TC_CASE(2, 16); TC_CASE(4, 16); TC_CASE(8, 16);
     TC_CASE(1, 32); TC_CASE(2, 32); TC_CASE(4, 32); TC_CASE(8, 32);
 #undef TC_CASE
@@ -1179,6 +1277,7 @@ extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x
     PB_CHECK_LAUNCH();
     return PB_OK;
 }
+}  // namespace
 
 extern "C" int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw, int* err_flag,
                                   pb_stream_t stream) {
@@ -1203,7 +1302,7 @@ extern "C" int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const v
     p.ND = (p.D + p.DCH - 1) / p.DCH;
     p.slab_need = kTileM + 2 * p.PW + 3;
     p.slab_e = (p.slab_need + 7) & ~7;
-    if (p.slab_need > 4 * kProducerThreads) { pb_set_error("conv3d_wgrad_tc: plane slab of %d rows exceeds the producer budget", p.slab_need); return PB_EUNSUPPORTED; }
+    if (p.slab_need > kWgCopies * kProducerThreads) { pb_set_error("conv3d_wgrad_tc: plane slab of %d rows exceeds the producer budget", p.slab_need); return PB_EUNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
     switch (d->cout / 8) {
@@ -1263,7 +1362,7 @@ extern "C" int pb_conv3d_tcs(const pb_conv_desc* d, const void* x0, const void* 
     int se = p.slab_need;
     while (se % 8 != want % 8) ++se;
     p.slab_e = se;
-    if (p.slab_need * nchr > kMaxCopies * kProducerThreads) {
+    if (p.slab_need * nchr > max_copies(nchr) * kProducerThreads) {
         pb_set_error("conv3d_tcs: plane slab of %d x %d copies exceeds the producer budget", p.slab_need, nchr);
         return PB_EUNSUPPORTED;
     }

@@ -103,6 +103,7 @@ def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
 # ---- tcgen05 implicit-GEMM path (csrc/conv3d_tc.cu) ------------------------------------------------------
 TC_ENABLED = os.environ.get("PB_TC", "1") != "0"
 WGRAD_TC = os.environ.get("PB_WGRAD_TC", "1") != "0"
+DGRAD_FOLD = os.environ.get("PB_DGRAD_FOLD", "1") != "0"      # reflect-pad data gradient: extended-domain tc pass + fold
 TC_STACKED = os.environ.get("PB_TCS", "0") != "0"        # kw-stacked variant of the fwd / dgrad implicit GEMM (measured: not faster)
 _tc_err = {}
 
@@ -224,15 +225,29 @@ class _Conv3d(torch.autograd.Function):
                 # data gradient = the same implicit GEMM on dy with flipped taps / transposed channels and zero
                 # padding; the reflected-halo terms are added by a thin boundary kernel
                 wflip = w.flip(1).transpose(2, 3)
-                dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0,
-                              cout=d.c0 + d.c1, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
                 err = _tc_err_flag(dy.device)
-                done = _run("conv3d_dgrad_tc", key, nb, fl,
-                            lambda: _tc_conv_call(lib, dd, dy, None, wflip, dx0, dx1, d.c0, d.c1, None, err),
-                            allow_unsupported=True)
-                if done and pad_mode == "reflect":
-                    _run("conv3d_dgrad_fix", key, 0, 0,
-                         lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
+                cin = d.c0 + d.c1
+                if pad_mode == "reflect" and DGRAD_FOLD:
+                    # "full" correlation on the domain grown by one voxel, then fold the halo back along the reflections
+                    dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di + 2, ho=d.hi + 2, wo=d.wi + 2,
+                                  c0=d.cout, c1=0, cout=cin, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
+                    ext = torch.empty((d.n, d.di + 2, d.hi + 2, d.wi + 2, cin), dtype=dy.dtype, device=dy.device)
+                    img = tc_weight_image(wflip, _tc_ntile(d.cout, cin))
+                    done = _run("conv3d_dgrad_tc", key, nb, fl,
+                                lambda: lib.pb_conv3d_tc_full(ctypes.byref(dd), _p(dy), _p(img), _p(dx0), _p(dx1), d.c0, d.c1,
+                                                              _p(ext), _p(err), _stream()), allow_unsupported=True)
+                    if done:
+                        _run("reflect_fold", key, 0, 0,
+                             lambda: lib.pb_reflect_fold(_p(ext), _p(dx0), _p(dx1), d.n, d.di, d.hi, d.wi, d.c0, d.c1, _stream()))
+                else:
+                    dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0,
+                                  cout=cin, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
+                    done = _run("conv3d_dgrad_tc", key, nb, fl,
+                                lambda: _tc_conv_call(lib, dd, dy, None, wflip, dx0, dx1, d.c0, d.c1, None, err),
+                                allow_unsupported=True)
+                    if done and pad_mode == "reflect":
+                        _run("conv3d_dgrad_fix", key, 0, 0,
+                             lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
             else:
                 done = False
             if not done:

@@ -59,6 +59,11 @@ CONV_CASES = [
     (128, 0, 128, 3, 1, "zeros", 1, 2, (5, 5, 5), True),
     (512, 0, 128, 1, 1, "zeros", 1, 2, (5, 5, 5), True),
     (32, 0, 8, 1, 1, "zeros", 1, 2, (6, 7, 8), True),
+    # 128-wide planes (128^3 crops): producer budgets of the tcgen05 kernels
+    (16, 0, 8, 3, 1, "reflect", 1, 1, (4, 6, 128), False),
+    (8, 0, 8, 3, 1, "reflect", 1, 1, (3, 5, 128), True),
+    (16, 0, 16, 3, 1, "zeros", 1, 1, (3, 4, 128), True),
+    (64, 0, 32, 3, 1, "reflect", 1, 1, (4, 5, 32), True),
 ]
 
 

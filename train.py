@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from options import args_parser
 from passion_b200.engine import Trainer
-from passion_b200.models import rfnet
+from passion_b200.models import build_model
 from passion_b200.train_step import poly_lr, preference_update
 
 MASK_ARRAY = np.array([[False, False, False, True], [False, True, False, False], [False, False, True, False],
@@ -53,7 +53,7 @@ class Source:
         return int(self.rs.choice(15, 1)[0])
 
     def batch(self, it):
-        B, S = self.args.batch_size, 80
+        B, S = self.args.batch_size, self.args.crop_size
         xs, ys, ms = [], [], []
         for b in range(B):
             row = self.rows[(it * self.world * B + self.rank * B + b) % len(self.rows)]
@@ -78,8 +78,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    if args.model != 'rfnet':
-        raise SystemExit('only --model rfnet is implemented on the B200-native path')
+    if args.model not in ('rfnet', 'mmformer'):
+        raise SystemExit('--model rfnet | mmformer are implemented on the B200-native path')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -101,7 +101,7 @@ def main():
     iter_per_epoch = src.iters
     modal_weight = iter_per_epoch / modal_num                                                       # train.py:171
 
-    model = rfnet.Model(num_cls=4).to(dev)
+    model = build_model(args.model, num_cls=4, crop=args.crop_size).to(dev)
     model.compute_dtype = torch.float32 if args.dtype == 'f32' else torch.bfloat16
     if args.resume is not None and args.use_pretrain:                                               # train.py:144-152
         sd = torch.load(args.resume, map_location=dev)['state_dict']
