@@ -109,6 +109,40 @@ int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, vo
                       void* yext, int* err_flag, pb_stream_t stream);
 int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int d, int h, int w, int co0, int co1, pb_stream_t stream);
 
+/* ---- weight layout conversion ------------------------------------------------------------
+ * The parameters stay in nn.Conv3d's layout [cout][cin][k][k][k] fp32 (models/blocks.py:357, state_dict compatible);
+ * pb_weight_prep gathers, for up to 4 weight groups (the four modality encoders, rfnet.py:234-237), every layout the
+ * conv kernels of one layer need in ONE launch (NULL output = skip):
+ *   wk  [G][taps][cin][cout] f32 (pb_conv3d_fwd / _wgrad)      wt   [G][taps][cout][cin] f32 (pb_conv3d_dgrad)
+ *   img  = pb_conv3d_tc weight image, nt  = pb_conv3d_tc_ntile(cin, cout)
+ *   imgT = weight image of the data gradient (taps mirrored, channels transposed), ntT = pb_conv3d_tc_ntile(cout, cin)
+ *   bias [G][cout] f32 gathered from b[g]
+ * pb_weight_grad_unpack scatters a kernel-layout weight gradient dw [G][taps][cin][cout] (and the bias gradient, given
+ * either as db [G][cout] or as the channel sums of dy) back into per-group gradients in the parameter layout. */
+typedef struct {
+    const float* w[4];
+    const float* b[4];
+    int groups, cin, cout, ksize;
+    float* wk;
+    float* wt;
+    void* img;
+    int nt;
+    void* imgT;
+    int ntT;
+    float* bias;
+} pb_weight_prep_desc;
+typedef struct {
+    const float* dw;
+    const float* db;        /* bias gradient [G][cout], or NULL ... */
+    const double* dy_stats; /* ... or the pb_channel_stats of dy [n][cout][2]: db[g][c] = sum over the group's npg samples */
+    int npg;
+    float* gw[4];
+    float* gb[4];
+    int groups, cin, cout, ksize;
+} pb_weight_unpack_desc;
+int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream);
+int pb_weight_grad_unpack(const pb_weight_unpack_desc* d, pb_stream_t stream);
+
 /* ---- InstanceNorm3d(affine=False, eps) + LeakyReLU(slope) (+ residual) -----------------
  * Replaces norm + activation of general_conv3d (blocks.py:18, :363, :367-369) and the encoder
  * residual add (rfnet.py:37,40,43,46).

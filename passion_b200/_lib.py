@@ -24,6 +24,21 @@ class ConvDesc(ctypes.Structure):
         "pad_mode", "groups")]
 
 
+class WeightPrepDesc(ctypes.Structure):
+    """Mirror of pb_weight_prep_desc."""
+    _fields_ = [("w", ctypes.c_void_p * 4), ("b", ctypes.c_void_p * 4),
+                ("groups", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32),
+                ("wk", ctypes.c_void_p), ("wt", ctypes.c_void_p), ("img", ctypes.c_void_p), ("nt", ctypes.c_int32),
+                ("imgT", ctypes.c_void_p), ("ntT", ctypes.c_int32), ("bias", ctypes.c_void_p)]
+
+
+class WeightUnpackDesc(ctypes.Structure):
+    """Mirror of pb_weight_unpack_desc."""
+    _fields_ = [("dw", ctypes.c_void_p), ("db", ctypes.c_void_p), ("dy_stats", ctypes.c_void_p), ("npg", ctypes.c_int32),
+                ("gw", ctypes.c_void_p * 4), ("gb", ctypes.c_void_p * 4),
+                ("groups", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32)]
+
+
 def declared_symbols():
     """Every function name declared in include/passion_b200.h."""
     with open(HEADER_PATH) as f:
@@ -61,6 +76,8 @@ def load():
         "pb_conv3d_tcs": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv3d_dgrad_reflect_fix": [cd, vp, vp, vp, vp, vp],
+        "pb_weight_prep": [ctypes.POINTER(WeightPrepDesc), vp],
+        "pb_weight_grad_unpack": [ctypes.POINTER(WeightUnpackDesc), vp],
         "pb_channel_stats": [i32, vp, vp, i32, i64, i32, vp],
         "pb_inorm_finalize": [vp, vp, i32, i32, i64, f32, vp],
         "pb_inorm_lrelu_fwd": [i32, vp, vp, vp, vp, i32, i64, i32, f32, vp],

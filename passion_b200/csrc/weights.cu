@@ -1,0 +1,178 @@
+// Weight layout conversions, one launch per conv layer and direction.
+//
+// The model keeps its parameters in the reference's nn.Conv3d layout [Cout][Cin][kd][kh][kw] fp32 (state_dict
+// compatibility, reference models/blocks.py:357).  The kernels want
+//   wk   fp32 [G][taps][Cin][Cout]                 FFMA forward / weight-gradient layout
+//   wt   fp32 [G][taps][Cout][Cin]                 FFMA data-gradient layout
+//   img  bf16 [G][Cout tiles][27][NCH][NT][8]      tcgen05 forward weight image (zero padded)
+//   imgT bf16 [G][Cin tiles][27][NCH'][NT'][8]     the same for the data gradient: taps flipped, channels transposed
+// Doing this with tensor ops costs ~10 tiny launches per layer and step (permute / stack / zeros / copy / cast); here
+// it is one gather kernel before the layer runs and one scatter kernel after its weight gradient.
+#include "common.cuh"
+
+namespace {
+
+struct PrepK {
+    const float* w[4];
+    const float* b[4];
+    int G, cin, cout, taps;
+    float* wk; float* wt; bf16* img; bf16* imgT; float* bias;
+    int nt, ntT;
+    long long n_wk, n_wt, n_img, n_imgT, n_bias;
+    int nch, tiles, nchT, tilesT;
+};
+
+__device__ __forceinline__ float ref_w(const PrepK& k, int g, int co, int ci, int tap) {
+    return __ldg(k.w[g] + ((size_t)co * k.cin + ci) * k.taps + tap);
+}
+
+__global__ void weight_prep_kernel(PrepK k) {
+    const long long total = k.n_wk + k.n_wt + k.n_img + k.n_imgT + k.n_bias;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long i = t;
+        if (i < k.n_wk) {                                   // [g][tap][ci][co]
+            const int co = (int)(i % k.cout); i /= k.cout;
+            const int ci = (int)(i % k.cin); i /= k.cin;
+            const int tap = (int)(i % k.taps);
+            const int g = (int)(i / k.taps);
+            k.wk[t] = ref_w(k, g, co, ci, tap);
+            continue;
+        }
+        i -= k.n_wk;
+        if (i < k.n_wt) {                                   // [g][tap][co][ci]
+            const long long o = i;
+            const int ci = (int)(i % k.cin); i /= k.cin;
+            const int co = (int)(i % k.cout); i /= k.cout;
+            const int tap = (int)(i % k.taps);
+            const int g = (int)(i / k.taps);
+            k.wt[o] = ref_w(k, g, co, ci, tap);
+            continue;
+        }
+        i -= k.n_wt;
+        if (i < k.n_img) {                                  // [g][tile][tap][chunk][row][8]
+            const long long o = i;
+            const int e = (int)(i % 8); i /= 8;
+            const int row = (int)(i % k.nt); i /= k.nt;
+            const int chunk = (int)(i % k.nch); i /= k.nch;
+            const int tap = (int)(i % 27); i /= 27;
+            const int tile = (int)(i % k.tiles);
+            const int g = (int)(i / k.tiles);
+            const int ci = chunk * 8 + e, co = tile * k.nt + row;
+            k.img[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, tap) : 0.f);
+            continue;
+        }
+        i -= k.n_img;
+        if (i < k.n_imgT) {                                 // roles of Cin / Cout swapped, taps mirrored
+            const long long o = i;
+            const int e = (int)(i % 8); i /= 8;
+            const int row = (int)(i % k.ntT); i /= k.ntT;
+            const int chunk = (int)(i % k.nchT); i /= k.nchT;
+            const int tap = (int)(i % 27); i /= 27;
+            const int tile = (int)(i % k.tilesT);
+            const int g = (int)(i / k.tilesT);
+            const int co = chunk * 8 + e, ci = tile * k.ntT + row;
+            k.imgT[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, 26 - tap) : 0.f);
+            continue;
+        }
+        i -= k.n_imgT;
+        {
+            const int co = (int)(i % k.cout);
+            const int g = (int)(i / k.cout);
+            k.bias[i] = __ldg(k.b[g] + co);
+        }
+    }
+}
+
+struct UnpackK {
+    const float* dw; const float* db; const double* dy_stats; int npg;
+    float* gw[4]; float* gb[4];
+    int G, cin, cout, taps;
+};
+
+__global__ void weight_unpack_kernel(UnpackK k) {
+    const long long per = (long long)k.cout * k.cin * k.taps;
+    const long long n_w = per * k.G;
+    const long long total = n_w + ((k.db || k.dy_stats) ? (long long)k.G * k.cout : 0);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        if (t < n_w) {
+            const int g = (int)(t / per);
+            long long i = t - (long long)g * per;
+            const long long o = i;
+            const int tap = (int)(i % k.taps); i /= k.taps;
+            const int ci = (int)(i % k.cin);
+            const int co = (int)(i / k.cin);
+            k.gw[g][o] = __ldg(k.dw + (((size_t)g * k.taps + tap) * k.cin + ci) * k.cout + co);
+        } else {
+            const long long i = t - n_w;
+            const int g = (int)(i / k.cout), co = (int)(i % k.cout);
+            if (k.db) k.gb[g][co] = __ldg(k.db + i);
+            else {
+                double acc = 0.0;
+                for (int n = 0; n < k.npg; ++n) acc += k.dy_stats[(((size_t)g * k.npg + n) * k.cout + co) * 2];
+                k.gb[g][co] = (float)acc;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream) {
+    PB_CHECK_ARG(d && d->groups >= 1 && d->groups <= 4, "1..4 weight groups");
+    PB_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "ksize 1 or 3");
+    PB_CHECK_ARG(d->cin >= 1 && d->cout >= 1, "bad channels");
+    PrepK k;
+    k.G = d->groups; k.cin = d->cin; k.cout = d->cout; k.taps = d->ksize * d->ksize * d->ksize;
+    for (int g = 0; g < 4; ++g) {
+        k.w[g] = g < k.G ? d->w[g] : nullptr;
+        k.b[g] = g < k.G ? d->b[g] : nullptr;
+        PB_CHECK_ARG(g >= k.G || k.w[g], "null weight");
+        PB_CHECK_ARG(g >= k.G || !d->bias || k.b[g], "null bias");
+    }
+    k.wk = d->wk; k.wt = d->wt; k.img = (bf16*)d->img; k.imgT = (bf16*)d->imgT; k.bias = d->bias;
+    k.nt = d->nt; k.ntT = d->ntT;
+    const long long nw = (long long)k.G * k.taps * k.cin * k.cout;
+    k.n_wk = k.wk ? nw : 0;
+    k.n_wt = k.wt ? nw : 0;
+    k.nch = k.tiles = k.nchT = k.tilesT = 1;
+    k.n_img = k.n_imgT = 0;
+    if (k.img) {
+        PB_CHECK_ARG(k.taps == 27 && k.nt > 0 && k.cin % 8 == 0, "forward image needs a 3x3x3 conv, cin % 8 == 0");
+        k.nch = k.cin / 8 < 2 ? 2 : k.cin / 8;
+        k.tiles = (k.cout + k.nt - 1) / k.nt;
+        k.n_img = (long long)k.G * k.tiles * 27 * k.nch * k.nt * 8;
+    }
+    if (k.imgT) {
+        PB_CHECK_ARG(k.taps == 27 && k.ntT > 0 && k.cout % 8 == 0, "data-gradient image needs a 3x3x3 conv, cout % 8 == 0");
+        k.nchT = k.cout / 8 < 2 ? 2 : k.cout / 8;
+        k.tilesT = (k.cin + k.ntT - 1) / k.ntT;
+        k.n_imgT = (long long)k.G * k.tilesT * 27 * k.nchT * k.ntT * 8;
+    }
+    k.n_bias = k.bias ? (long long)k.G * k.cout : 0;
+    const long long total = k.n_wk + k.n_wt + k.n_img + k.n_imgT + k.n_bias;
+    if (total == 0) return PB_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    weight_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_weight_grad_unpack(const pb_weight_unpack_desc* d, pb_stream_t stream) {
+    PB_CHECK_ARG(d && d->dw && d->groups >= 1 && d->groups <= 4, "1..4 weight groups");
+    UnpackK k;
+    k.dw = d->dw; k.db = d->db; k.dy_stats = d->dy_stats; k.npg = d->npg;
+    k.G = d->groups; k.cin = d->cin; k.cout = d->cout; k.taps = d->ksize * d->ksize * d->ksize;
+    for (int g = 0; g < 4; ++g) {
+        k.gw[g] = g < k.G ? d->gw[g] : nullptr;
+        k.gb[g] = g < k.G ? d->gb[g] : nullptr;
+        PB_CHECK_ARG(g >= k.G || k.gw[g], "null gradient pointer");
+        PB_CHECK_ARG(g >= k.G || !(d->db || d->dy_stats) || k.gb[g], "null bias-gradient pointer");
+    }
+    const long long total = (long long)k.G * k.cout * (k.cin * k.taps + ((k.db || k.dy_stats) ? 1 : 0));
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    weight_unpack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

@@ -50,15 +50,14 @@ class general_conv3d_prenorm(nn.Module):
     def run(self, x0, x1=None):
         a0 = ops.prenorm(x0)
         a1 = ops.prenorm(x1) if x1 is not None else None
-        w = ops.kernel_layout(self.conv.weight)[None]
-        y, _ = ops.conv3d(a0, w, self.conv.bias[None], a1, ksize=self.k_size, stride=self.stride, pad_mode=self.pad_type)
+        y, _ = ops.conv3d_ref(a0, [self.conv.weight], [self.conv.bias], a1, ksize=self.k_size, stride=self.stride,
+                              pad_mode=self.pad_type)
         return y
 
 
 def _plain_conv1(conv, x):
     """nn.Conv3d 1x1x1 head with bias -> logits (mmformer.py:90, 135-139)."""
-    w = ops.kernel_layout(conv.weight)[None]
-    y, _ = ops.conv3d(x, w, conv.bias[None], ksize=1, pad_mode="zeros")
+    y, _ = ops.conv3d_ref(x, [conv.weight], [conv.bias], ksize=1, pad_mode="zeros")
     return y
 
 
@@ -84,9 +83,8 @@ def _run_encoders(encoders, x):
     def gconv(name, t, stride=1, norm=True):
         convs = [getattr(e, name) for e in encoders]
         convs = [c.conv if norm else c for c in convs]
-        w = torch.stack([ops.kernel_layout(c.weight) for c in convs])
-        b = torch.stack([c.bias for c in convs])
-        y, _ = ops.conv3d(ops.prenorm(t) if norm else t, w, b, ksize=3, stride=stride, pad_mode="reflect", groups=4)
+        y, _ = ops.conv3d_ref(ops.prenorm(t) if norm else t, [c.weight for c in convs], [c.bias for c in convs], ksize=3,
+                              stride=stride, pad_mode="reflect")
         return y
 
     feats = []

@@ -39,12 +39,9 @@ class general_conv3d(nn.Module):
                               padding_mode=pad_type, bias=True)
         self.k_size, self.stride, self.pad_type = k_size, stride, pad_type
 
-    def kernel_weight(self):
-        return ops.kernel_layout(self.conv.weight)[None]           # [1, taps, cin, cout]
-
     def run(self, x0, x1=None, res=None):
-        y = ops.conv_in_lrelu(x0, self.kernel_weight(), x1=x1, ksize=self.k_size, stride=self.stride,
-                              pad_mode=self.pad_type, res=res)
+        y = ops.conv_in_lrelu_ref(x0, [self.conv.weight], x1=x1, ksize=self.k_size, stride=self.stride,
+                                  pad_mode=self.pad_type, res=res)
         # the bias cancels in InstanceNorm: give it an exact-zero gradient (keeps optimizer state shape)
         return _ZeroGradTouch.apply(y, self.conv.bias)
 
@@ -59,13 +56,12 @@ class _ZeroGradTouch(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        return dy, torch.zeros(ctx.shape, dtype=ctx.meta[0], device=ctx.meta[1])
+        return dy, ops.zero_grad_like(ctx.shape, *ctx.meta)
 
 
 def _plain_conv1(conv, x):
     """plain nn.Conv3d 1x1x1 head with bias (rfnet.py:69,107; blocks.py:407,455) -> logits."""
-    w = ops.kernel_layout(conv.weight)[None]
-    y, _ = ops.conv3d(x, w, conv.bias[None].contiguous(), ksize=1, pad_mode="zeros")
+    y, _ = ops.conv3d_ref(x, [conv.weight], [conv.bias], ksize=1, pad_mode="zeros")
     return y
 
 
@@ -87,11 +83,11 @@ def _run_encoders(encoders, x):
     feats = []
     for lvl in (1, 2, 3, 4):
         def gw(name):
-            return torch.stack([ops.kernel_layout(getattr(e, name).conv.weight) for e in encoders])
+            return [getattr(e, name).conv.weight for e in encoders]
         stride = 1 if lvl == 1 else 2
-        x = ops.conv_in_lrelu(x, gw(f"e{lvl}_c1"), stride=stride, groups=4)
-        t = ops.conv_in_lrelu(x, gw(f"e{lvl}_c2"), groups=4)
-        x = ops.conv_in_lrelu(t, gw(f"e{lvl}_c3"), groups=4, res=x)       # x + c3(c2(x))
+        x = ops.conv_in_lrelu_ref(x, gw(f"e{lvl}_c1"), stride=stride)
+        t = ops.conv_in_lrelu_ref(x, gw(f"e{lvl}_c2"))
+        x = ops.conv_in_lrelu_ref(t, gw(f"e{lvl}_c3"), res=x)             # x + c3(c2(x))
         for e in encoders:                                                 # zero grads for the cancelled biases
             for nm in ("c1", "c2", "c3"):
                 x = _ZeroGradTouch.apply(x, getattr(e, f"e{lvl}_{nm}").conv.bias)

@@ -176,8 +176,83 @@ def _tc_conv_call(lib, d, x0, x1, w, y0, y1, co0, co1, stats, err, bias=None):
     return lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
 
 
+def _conv_fwd_launch(lib, d, x0, x1, get_wk, tc_call, bias, y, stats):
+    """Forward launch: the tcgen05 implicit GEMM when `tc_call` is given (and supports the shape), else the FFMA kernel
+    with the fp32 kernel-layout weights returned by get_wk()."""
+    key, nb, fl = _conv_work(d, x0.element_size())
+    done = False
+    if tc_call is not None:
+        done = _run("conv3d_fwd_tc", key, nb, fl, tc_call, allow_unsupported=True)
+    if not done:
+        wk = get_wk()
+        _run("conv3d_fwd", key, nb, fl,
+             lambda: lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(wk), _p(bias), _p(y), _p(stats), _stream()))
+
+
+def _dgrad_tc_ok(d, dtype, ksize, stride, pad_mode):
+    return (_tc_eligible(dtype, ksize, stride, d.cout, 0, d.c0 + d.c1) and d.c0 % 8 == 0 and d.c1 % 8 == 0
+            and (pad_mode != "reflect" or min(d.di, d.hi, d.wi) >= 4))
+
+
+def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, need_dw):
+    """Data and weight gradient launches.  get_imgT() -> bf16 image of the flipped / transposed weights (None = class
+    not on the tensor-core path), get_wt() -> fp32 [G][taps][cout][cin] for the FFMA kernels.
+    Returns dx0, dx1, dw (kernel layout [G][taps][cin][cout] fp32)."""
+    groups = d.groups
+    cin = d.c0 + d.c1
+    dx0 = dx1 = dw = None
+    key, nb, fl = _conv_work(d, x0.element_size())
+    if need_dx:
+        dx0 = torch.empty_like(x0)
+        dx1 = torch.empty_like(x1) if x1 is not None else None
+        done = False
+        imgT = get_imgT()
+        if imgT is not None:
+            # data gradient = the same implicit GEMM on dy with flipped taps / transposed channels
+            err = _tc_err_flag(dy.device)
+            if pad_mode == "reflect" and DGRAD_FOLD:
+                # "full" correlation on the domain grown by one voxel, then fold the halo back along the reflections
+                dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di + 2, ho=d.hi + 2, wo=d.wi + 2,
+                              c0=d.cout, c1=0, cout=cin, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
+                ext = torch.empty((d.n, d.di + 2, d.hi + 2, d.wi + 2, cin), dtype=dy.dtype, device=dy.device)
+                done = _run("conv3d_dgrad_tc", key, nb, fl,
+                            lambda: lib.pb_conv3d_tc_full(ctypes.byref(dd), _p(dy), _p(imgT), _p(dx0), _p(dx1), d.c0, d.c1,
+                                                          _p(ext), _p(err), _stream()), allow_unsupported=True)
+                if done:
+                    _run("reflect_fold", key, 0, 0,
+                         lambda: lib.pb_reflect_fold(_p(ext), _p(dx0), _p(dx1), d.n, d.di, d.hi, d.wi, d.c0, d.c1, _stream()))
+            else:
+                dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0,
+                              cout=cin, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
+                done = _run("conv3d_dgrad_tc", key, nb, fl,
+                            lambda: lib.pb_conv3d_tc(ctypes.byref(dd), _p(dy), None, _p(imgT), None, _p(dx0), _p(dx1), d.c0, d.c1,
+                                                     None, _p(err), _stream()), allow_unsupported=True)
+                if done and pad_mode == "reflect":
+                    wt = get_wt()
+                    _run("conv3d_dgrad_fix", key, 0, 0,
+                         lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
+        if not done:
+            wt = get_wt()
+            _run("conv3d_dgrad", key, nb, fl,
+                 lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
+    if need_dw:
+        dw = torch.zeros((groups, d.ksize ** 3, cin, d.cout), dtype=torch.float32, device=dy.device)
+        done = False
+        if (TC_ENABLED and WGRAD_TC and dy.dtype == torch.bfloat16 and d.ksize == 3 and d.stride == 1 and d.c0 % 8 == 0
+                and d.c1 % 8 == 0 and d.cout % 8 == 0 and d.cout <= 64):
+            err = _tc_err_flag(dy.device)
+            done = _run("conv3d_wgrad_tc", key, nb, fl,
+                        lambda: lib.pb_conv3d_wgrad_tc(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _p(err), _stream()),
+                        allow_unsupported=True)
+        if not done:
+            _run("conv3d_wgrad", key, nb, fl,
+                 lambda: lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()))
+    return dx0, dx1, dw
+
+
 class _Conv3d(torch.autograd.Function):
-    """y = conv(cat(x0, x1), w) (+ bias); optionally also the per-(n,c) sum / sum-of-squares of y."""
+    """y = conv(cat(x0, x1), w) (+ bias) with KERNEL-layout weights [groups, taps, cin, cout]; optionally also the
+    per-(n,c) sum / sum-of-squares of y.  (The models use _Conv3dRef, which takes the parameters as they are.)"""
 
     @staticmethod
     def forward(ctx, x0, x1, w, bias, ksize, stride, pad_mode, groups, want_stats):
@@ -189,16 +264,11 @@ class _Conv3d(torch.autograd.Function):
         assert w.shape == (groups, ksize ** 3, d.c0 + d.c1, cout), (tuple(w.shape), groups, ksize, d.c0, d.c1, cout)
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
         stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
-        key, nb, fl = _conv_work(d, x0.element_size())
+        tc_call = None
         if _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
             err = _tc_err_flag(x0.device)
-            done = _run("conv3d_fwd_tc", key, nb, fl,
-                        lambda: _tc_conv_call(lib, d, x0, x1, w, y, None, cout, 0, stats, err, bias), allow_unsupported=True)
-        else:
-            done = False
-        if not done:
-            _run("conv3d_fwd", key, nb, fl,
-                 lambda: lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(w), _p(bias), _p(y), _p(stats), _stream()))
+            tc_call = lambda: _tc_conv_call(lib, d, x0, x1, w, y, None, cout, 0, stats, err, bias)
+        _conv_fwd_launch(lib, d, x0, x1, lambda: w, tc_call, bias, y, stats)
         ctx.save_for_backward(x0, x1, w)
         ctx.cfg = (ksize, stride, pad_mode, groups, bias is not None)
         if want_stats:
@@ -213,61 +283,116 @@ class _Conv3d(torch.autograd.Function):
         ksize, stride, pad_mode, groups, has_bias = ctx.cfg
         dy = dy.contiguous()
         d = _conv_desc(x0, x1, w.shape[-1], ksize, stride, pad_mode, groups)
-        dx0 = dx1 = dw = db = None
-        key, nb, fl = _conv_work(d, x0.element_size())
         need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
-        if need_dx:
-            wt = w.transpose(2, 3).contiguous()
-            dx0 = torch.empty_like(x0)
-            dx1 = torch.empty_like(x1) if x1 is not None else None
-            if (_tc_eligible(dy.dtype, ksize, stride, d.cout, 0, d.c0 + d.c1) and d.c0 % 8 == 0 and d.c1 % 8 == 0
-                    and (pad_mode != "reflect" or min(d.di, d.hi, d.wi) >= 4)):
-                # data gradient = the same implicit GEMM on dy with flipped taps / transposed channels and zero
-                # padding; the reflected-halo terms are added by a thin boundary kernel
-                wflip = w.flip(1).transpose(2, 3)
-                err = _tc_err_flag(dy.device)
-                cin = d.c0 + d.c1
-                if pad_mode == "reflect" and DGRAD_FOLD:
-                    # "full" correlation on the domain grown by one voxel, then fold the halo back along the reflections
-                    dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di + 2, ho=d.hi + 2, wo=d.wi + 2,
-                                  c0=d.cout, c1=0, cout=cin, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
-                    ext = torch.empty((d.n, d.di + 2, d.hi + 2, d.wi + 2, cin), dtype=dy.dtype, device=dy.device)
-                    img = tc_weight_image(wflip, _tc_ntile(d.cout, cin))
-                    done = _run("conv3d_dgrad_tc", key, nb, fl,
-                                lambda: lib.pb_conv3d_tc_full(ctypes.byref(dd), _p(dy), _p(img), _p(dx0), _p(dx1), d.c0, d.c1,
-                                                              _p(ext), _p(err), _stream()), allow_unsupported=True)
-                    if done:
-                        _run("reflect_fold", key, 0, 0,
-                             lambda: lib.pb_reflect_fold(_p(ext), _p(dx0), _p(dx1), d.n, d.di, d.hi, d.wi, d.c0, d.c1, _stream()))
-                else:
-                    dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0,
-                                  cout=cin, ksize=3, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
-                    done = _run("conv3d_dgrad_tc", key, nb, fl,
-                                lambda: _tc_conv_call(lib, dd, dy, None, wflip, dx0, dx1, d.c0, d.c1, None, err),
-                                allow_unsupported=True)
-                    if done and pad_mode == "reflect":
-                        _run("conv3d_dgrad_fix", key, 0, 0,
-                             lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
-            else:
-                done = False
-            if not done:
-                _run("conv3d_dgrad", key, nb, fl,
-                     lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
-        if ctx.needs_input_grad[2]:
-            dw = torch.zeros_like(w)
-            done = False
-            if (TC_ENABLED and WGRAD_TC and dy.dtype == torch.bfloat16 and ksize == 3 and stride == 1 and d.c0 % 8 == 0
-                    and d.c1 % 8 == 0 and d.cout % 8 == 0 and d.cout <= 64):
-                err = _tc_err_flag(dy.device)
-                done = _run("conv3d_wgrad_tc", key, nb, fl,
-                            lambda: lib.pb_conv3d_wgrad_tc(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _p(err), _stream()),
-                            allow_unsupported=True)
-            if not done:
-                _run("conv3d_wgrad", key, nb, fl,
-                     lambda: lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()))
+
+        def get_imgT():
+            if not _dgrad_tc_ok(d, dy.dtype, ksize, stride, pad_mode):
+                return None
+            return tc_weight_image(w.flip(1).transpose(2, 3), _tc_ntile(d.cout, d.c0 + d.c1))
+
+        dx0, dx1, dw = _conv_bwd_launch(lib, d, x0, x1, dy, lambda: w.transpose(2, 3).contiguous(), get_imgT, pad_mode,
+                                        need_dx, ctx.needs_input_grad[2])
+        db = None
         if has_bias and ctx.needs_input_grad[3]:
             db = dy.float().reshape(groups, -1, dy.shape[-1]).sum(1)
         return dx0, dx1, dw, db, None, None, None, None, None
+
+
+def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt=0, ntT=0, want_bias=False):
+    """One pb_weight_prep launch: parameter-layout weights of G groups -> the layouts asked for."""
+    G = len(ws)
+    dev = ws[0].device
+    taps = ksize ** 3
+    f32 = dict(dtype=torch.float32, device=dev)
+    wk = torch.empty((G, taps, cin, cout), **f32) if want_wk else None
+    wt = torch.empty((G, taps, cout, cin), **f32) if want_wt else None
+    img = torch.empty((G, (cout + nt - 1) // nt, 27, max(2, cin // 8), nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
+    imgT = torch.empty((G, (cin + ntT - 1) // ntT, 27, max(2, cout // 8), ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
+    bias = torch.empty((G, cout), **f32) if want_bias else None
+    desc = _lib.WeightPrepDesc(groups=G, cin=cin, cout=cout, ksize=ksize, wk=_p(wk), wt=_p(wt), img=_p(img), nt=nt,
+                               imgT=_p(imgT), ntT=ntT, bias=_p(bias))
+    for g in range(G):
+        desc.w[g] = ws[g].data_ptr()
+        desc.b[g] = bs[g].data_ptr() if want_bias else None
+    _run("weight_prep", f"c{cin}->{cout} k{ksize} g{G}", 0, 0, lambda: lib.pb_weight_prep(ctypes.byref(desc), _stream()))
+    return wk, wt, img, imgT, bias
+
+
+class _Conv3dRef(torch.autograd.Function):
+    """Same op as _Conv3d, but on the PARAMETERS as the reference stores them: G weights [cout, cin, k, k, k] (one per
+    weight group) and optionally G biases [cout].  All layout work is one gather launch in forward (pb_weight_prep)
+    and one scatter launch in backward (pb_weight_grad_unpack) instead of ~10 tensor-op launches per layer."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, ksize, stride, pad_mode, want_stats, has_bias, *params):
+        lib = _lib.load()
+        G = len(params) // 2 if has_bias else len(params)
+        ws, bs = params[:G], params[G:]
+        _chk(x0, x1, *params)
+        cout, cin = ws[0].shape[0], ws[0].shape[1]
+        d = _conv_desc(x0, x1, cout, ksize, stride, pad_mode, G)
+        assert cin == d.c0 + d.c1 and all(w.dtype == torch.float32 and tuple(w.shape) == (cout, cin, ksize, ksize, ksize) for w in ws)
+        need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
+        fwd_tc = _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout)
+        dgrad_tc = need_dx and _dgrad_tc_ok(d, x0.dtype, ksize, stride, pad_mode)
+        want_wt = need_dx and (not dgrad_tc or (pad_mode == "reflect" and not DGRAD_FOLD))
+        wk, wt, img, imgT, bias = _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=not fwd_tc, want_wt=want_wt,
+                                               nt=_tc_ntile(cin, cout) if fwd_tc else 0,
+                                               ntT=_tc_ntile(cout, cin) if dgrad_tc else 0, want_bias=has_bias)
+        y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
+        stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
+        tc_call = None
+        if fwd_tc:
+            err = _tc_err_flag(x0.device)
+            tc_call = lambda: lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y), None, cout, 0,
+                                               _p(stats), _p(err), _stream())
+        _conv_fwd_launch(lib, d, x0, x1, lambda: wk if wk is not None else _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=True)[0],
+                         tc_call, bias, y, stats)
+        ctx.save_for_backward(x0, x1, *ws)
+        ctx.bwd_w = (wt, imgT)
+        ctx.cfg = (ksize, stride, pad_mode, G, has_bias)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        lib = _lib.load()
+        ksize, stride, pad_mode, G, has_bias = ctx.cfg
+        x0, x1 = ctx.saved_tensors[:2]
+        ws = ctx.saved_tensors[2:]
+        wt, imgT = ctx.bwd_w
+        cout, cin = ws[0].shape[0], ws[0].shape[1]
+        dy = dy.contiguous()
+        d = _conv_desc(x0, x1, cout, ksize, stride, pad_mode, G)
+        need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
+        need_dw = any(ctx.needs_input_grad[7:7 + G])
+        need_db = has_bias and any(ctx.needs_input_grad[7 + G:])
+        get_wt = lambda: wt if wt is not None else _weight_prep(lib, ws, (), cin, cout, ksize, want_wt=True)[1]
+        dx0, dx1, dw = _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, lambda: imgT, pad_mode, need_dx, need_dw or need_db)
+        gws = [None] * G
+        gbs = [None] * G if has_bias else []
+        if need_dw or need_db:
+            gws = [torch.empty_like(w) for w in ws]
+            desc = _lib.WeightUnpackDesc(dw=_p(dw), db=None, dy_stats=None, npg=d.n // G, groups=G, cin=cin, cout=cout, ksize=ksize)
+            if need_db:
+                st = channel_stats(dy)
+                desc.dy_stats = st.data_ptr()
+                gbs = [torch.empty((cout,), dtype=torch.float32, device=dy.device) for _ in range(G)]
+            for g in range(G):
+                desc.gw[g] = gws[g].data_ptr()
+                desc.gb[g] = gbs[g].data_ptr() if need_db else None
+            _run("weight_grad_unpack", f"c{cin}->{cout} k{ksize} g{G}", 0, 0,
+                 lambda: lib.pb_weight_grad_unpack(ctypes.byref(desc), _stream()))
+        return (dx0, dx1, None, None, None, None, None, *gws, *gbs)
+
+
+def conv3d_ref(x0, weights, biases=None, x1=None, ksize=3, stride=1, pad_mode="reflect", want_stats=False):
+    """Conv on the parameters in nn.Conv3d layout: `weights` = list of G tensors [cout, cin, k, k, k] (G weight groups
+    over a modality-major batch), `biases` = list of G tensors [cout] or None.  Returns (y, stats or None)."""
+    params = list(weights) + (list(biases) if biases is not None else [])
+    return _Conv3dRef.apply(x0, x1, ksize, stride, pad_mode, want_stats, biases is not None, *params)
 
 
 def conv3d(x0, w, bias=None, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=1, want_stats=False):
@@ -329,6 +454,29 @@ def conv_in_lrelu(x0, w, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=
     voxels = y.shape[1] * y.shape[2] * y.shape[3]
     mr = inorm_finalize(stats, voxels)
     return _InormLrelu.apply(y, mr, res)
+
+
+def conv_in_lrelu_ref(x0, weights, x1=None, ksize=3, stride=1, pad_mode="reflect", res=None):
+    """conv_in_lrelu on parameter-layout weights (list of G tensors, see conv3d_ref)."""
+    y, stats = conv3d_ref(x0, weights, None, x1, ksize, stride, pad_mode, True)
+    voxels = y.shape[1] * y.shape[2] * y.shape[3]
+    return _InormLrelu.apply(y, inorm_finalize(stats, voxels), res)
+
+
+_zero_arena = {}
+
+
+def zero_grad_like(shape, dtype, device):
+    """A read-only all-zero tensor of the given shape without a launch: a view into a persistent zero buffer (used as the
+    gradient of parameters that provably do not influence the output)."""
+    n = 1
+    for v in shape:
+        n *= v
+    buf = _zero_arena.get((dtype, device))
+    if buf is None or buf.numel() < n:
+        buf = torch.zeros(max(n, 1 << 16), dtype=dtype, device=device)
+        _zero_arena[(dtype, device)] = buf
+    return buf[:n].view(shape)
 
 
 def channel_stats(x):

@@ -121,6 +121,51 @@ def test_conv3d(lib_built, case, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", [(8, 0, 16, 3, 1, "reflect", 4, 4, (9, 8, 10), True), (16, 16, 8, 3, 1, "reflect", 1, 2, (8, 9, 10), False),
+                                  (32, 0, 4, 1, 1, "zeros", 1, 2, (5, 6, 7), True), (8, 0, 16, 3, 2, "reflect", 4, 4, (8, 8, 6), True),
+                                  (1, 0, 8, 3, 1, "reflect", 4, 4, (6, 7, 8), True), (64, 0, 32, 3, 1, "zeros", 1, 1, (4, 5, 6), True)],
+                         ids=lambda c: "c%d+%d_%d_k%d_s%d_%s_g%d" % c[:7])
+def test_conv3d_on_parameter_layout(lib_built, case, dtype):
+    """ops.conv3d_ref (weights as nn.Conv3d stores them; one gather / one scatter launch for the layout work) must equal
+    ops.conv3d on the kernel-layout copies bit for bit: same kernels, same operands."""
+    from passion_b200 import ops
+    c0, c1, cout, k, stride, pad, groups, n, (d, h, w), has_bias = case
+    g = torch.Generator(device="cpu").manual_seed(7 + c0 + cout)
+    cin = c0 + c1
+    x = torch.randn(n, d, h, w, cin, generator=g).cuda().to(dtype)
+    ws = [(torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5).cuda().requires_grad_(True) for _ in range(groups)]
+    bs = [torch.randn(cout, generator=g).cuda().requires_grad_(True) for _ in range(groups)] if has_bias else None
+    gy = None
+    res = []
+    for ref_path in (True, False):
+        x0 = x[..., :c0].contiguous().requires_grad_(True)
+        x1 = x[..., c0:].contiguous().requires_grad_(True) if c1 else None
+        for t in ws + (bs or []):
+            t.grad = None
+        if ref_path:
+            y, st = ops.conv3d_ref(x0, ws, bs, x1, ksize=k, stride=stride, pad_mode=pad, want_stats=True)
+        else:
+            wk = torch.stack([ops.kernel_layout(wi) for wi in ws])
+            bk = torch.stack(bs) if has_bias else None
+            y, st = ops.conv3d(x0, wk, bk, x1, ksize=k, stride=stride, pad_mode=pad, groups=groups, want_stats=True)
+        if gy is None:
+            gy = torch.randn(y.shape, generator=g).cuda().to(dtype)
+        y.backward(gy)
+        res.append((y.detach(), st, x0.grad, None if x1 is None else x1.grad, [t.grad.clone() for t in ws],
+                    [t.grad.clone() for t in bs] if has_bias else []))
+    a, b = res
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    assert rel(a[1], b[1]) < 1e-12                       # float64 atomics: order may differ
+    if c1:
+        assert torch.equal(a[3], b[3])
+    for ga, gb in zip(a[4], b[4]):
+        assert rel(ga, gb) < 1e-6                        # weight-gradient kernels accumulate with atomics
+    for ga, gb in zip(a[5], b[5]):
+        assert rel(ga, gb) < (1e-6 if dtype == torch.float32 else 2e-3)      # float64 sums vs torch's fp32 reduction
+    ops.check_tc_errors()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("c,shape,with_res", [(8, (12, 10, 14), True), (16, (6, 7, 8), False), (2, (8, 8, 8), False),
                                               (4, (5, 5, 5), True), (64, (2, 2, 2), False), (32, (4, 5, 6), True),
                                               (1, (6, 6, 6), False)])
