@@ -179,6 +179,13 @@ int pb_upsample_bwd_axis(int dtype, const void* in, void* out, long long outer, 
  *   mix_bwd_gate : dgate[n][i][k] = sum_{v,c} p_i * y[k*C+c] * dR[i*C+c]   (float64, zero-filled)
  *   bwd_y : dy[n][v][k*C+c] = sum_i p_i * (gate[n][i][k]*dR[n][v][i*C+c] + dS[n][i][k*C+c])
  */
+/* MaskModal (rfnet.py:154-163, 239-242; mmformer.py:316-326) for `passes` decoder passes in one launch:
+ *   out[p*b + i][v][m*c + ch] = enc[m*b + i][v][ch] * ms[p][i][m]     (enc: modality-major output of the grouped encoders)
+ * and its adjoint denc[m*b + i][v][ch] = sum_p ms[p][i][m] * dout[p*b + i][v][m*c + ch]. */
+int pb_masked_stack_fwd(int dtype, const void* enc, const float* ms, void* out, int passes, int b, long long voxels, int c,
+                        pb_stream_t stream);
+int pb_masked_stack_bwd(int dtype, const void* dout, const float* ms, void* denc, int passes, int b, long long voxels, int c,
+                        pb_stream_t stream);
 int pb_rfm_pool(int dtype, const void* y, const float* p, double* S, double* Psum,
                 int n, long long voxels, int kc, pb_stream_t stream);
 int pb_rfm_mix(int dtype, const void* y, const float* p, const float* gate, void* r,

@@ -95,6 +95,8 @@ def load():
         "pb_proto_fwd": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, vp],
         "pb_proto_bwd1": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, vp],
         "pb_proto_bwd2": [i32, vp, vp, vp, i32, i32, i64, i32, vp],
+        "pb_masked_stack_fwd": [i32, vp, vp, vp, i32, i32, i64, i32, vp],
+        "pb_masked_stack_bwd": [i32, vp, vp, vp, i32, i32, i64, i32, vp],
         "pb_rfm_pool": [i32, vp, vp, vp, vp, i32, i64, i32, vp],
         "pb_rfm_mix": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
         "pb_rfm_mix_bwd_gate": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],

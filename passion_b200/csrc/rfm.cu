@@ -243,3 +243,90 @@ extern "C" int pb_rfm_bwd_y(int dtype, const float* p, const float* gate, const 
     PB_CHECK_LAUNCH();
     return PB_OK;
 }
+
+
+// ------------------------------------------------------------------------------------ masked modality stacking
+// MaskModal of the reference (models/rfnet.py:154-163, 239-242; mmformer.py:316-326) for P decoder passes at once:
+//   out[p*B + b][v][m*C + c] = enc[m*B + b][v][c] * ms[p][b][m]
+// enc is the modality-major encoder output of the grouped pass; each element is read once and written P times.
+namespace {
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) masked_stack_fwd_kernel(const T* __restrict__ enc, const float* __restrict__ ms,
+                                                               T* __restrict__ out, int P, int B, long long V, int C) {
+    const int cl = C / VEC;
+    const long long total = 4LL * B * V * cl;
+    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+        const int c = (int)(t % cl) * VEC;
+        long long r = t / cl;
+        const long long v = r % V; r /= V;
+        const int b = (int)(r % B), m = (int)(r / B);
+        float x[VEC], y[VEC];
+        VecIO<T, VEC>::load(enc + (((size_t)m * B + b) * V + v) * C + c, x);
+        for (int p = 0; p < P; ++p) {
+            const float s = __ldg(ms + ((size_t)p * B + b) * 4 + m);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) y[i] = x[i] * s;
+            VecIO<T, VEC>::store(out + (((size_t)p * B + b) * V + v) * (4 * C) + m * C + c, y);
+        }
+    }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) masked_stack_bwd_kernel(const T* __restrict__ dout, const float* __restrict__ ms,
+                                                               T* __restrict__ denc, int P, int B, long long V, int C) {
+    const int cl = C / VEC;
+    const long long total = 4LL * B * V * cl;
+    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+        const int c = (int)(t % cl) * VEC;
+        long long r = t / cl;
+        const long long v = r % V; r /= V;
+        const int b = (int)(r % B), m = (int)(r / B);
+        float acc[VEC], g[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int p = 0; p < P; ++p) {
+            const float s = __ldg(ms + ((size_t)p * B + b) * 4 + m);
+            if (s == 0.f) continue;
+            VecIO<T, VEC>::load(dout + (((size_t)p * B + b) * V + v) * (4 * C) + m * C + c, g);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(g[i], s, acc[i]);
+        }
+        VecIO<T, VEC>::store(denc + (((size_t)m * B + b) * V + v) * C + c, acc);
+    }
+}
+
+template <bool BWD>
+int masked_stack_launch(int dtype, const void* in, const float* ms, void* out, int P, int B, long long V, int C, cudaStream_t st) {
+    const int vec = dtype == PB_BF16 ? 8 : 4;
+    if (C % vec) { pb_set_error("masked_stack: C %d not a multiple of %d", C, vec); return PB_EUNSUPPORTED; }
+    const long long total = 4LL * B * V * (C / vec);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (dtype == PB_BF16) {
+        if (BWD) masked_stack_bwd_kernel<bf16, 8><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)in, ms, (bf16*)out, P, B, V, C);
+        else masked_stack_fwd_kernel<bf16, 8><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)in, ms, (bf16*)out, P, B, V, C);
+    } else {
+        if (BWD) masked_stack_bwd_kernel<float, 4><<<(unsigned)blocks, 256, 0, st>>>((const float*)in, ms, (float*)out, P, B, V, C);
+        else masked_stack_fwd_kernel<float, 4><<<(unsigned)blocks, 256, 0, st>>>((const float*)in, ms, (float*)out, P, B, V, C);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pb_masked_stack_fwd(int dtype, const void* enc, const float* ms, void* out, int passes, int b, long long voxels,
+                                   int c, pb_stream_t stream) {
+    PB_CHECK_ARG(enc && ms && out && passes >= 1 && b >= 1 && voxels >= 1 && c >= 1, "bad arguments");
+    if (int e = masked_stack_launch<false>(dtype, enc, ms, out, passes, b, voxels, c, (cudaStream_t)stream)) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_masked_stack_bwd(int dtype, const void* dout, const float* ms, void* denc, int passes, int b, long long voxels,
+                                   int c, pb_stream_t stream) {
+    PB_CHECK_ARG(dout && ms && denc && passes >= 1 && b >= 1 && voxels >= 1 && c >= 1, "bad arguments");
+    if (int e = masked_stack_launch<true>(dtype, dout, ms, denc, passes, b, voxels, c, (cudaStream_t)stream)) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}

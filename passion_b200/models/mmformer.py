@@ -319,6 +319,7 @@ class Model(nn.Module):
     def forward(self, x, mask, target=None, temp=1.0):
         if not x.is_cuda:
             raise RuntimeError("passion_b200.models.mmformer.Model runs on CUDA only (no CPU fallback)")
+        ops.begin_step(x.device)
         if self.mask_type == 'pdt':
             raise NotImplementedError("the reference's 'pdt' branch of mmformer.Model.forward reads x5 before it is "
                                       "defined (mmformer.py:449-470); only 'idt' masking is defined for this backbone")
@@ -332,10 +333,6 @@ class Model(nn.Module):
         enc = _run_encoders(self._encoders(), xe)                             # 5 levels of [4B,d,h,w,C], modality-major
         escale = e.reshape(4 * B, 1, 1, 1, 1).to(dt)
         feat = [f * escale for f in enc]                                      # masked per-modality features (:406-416)
-        stacked = []
-        for f in feat[:4]:
-            _, d, h, w, c = f.shape
-            stacked.append(f.view(4, B, d, h, w, c).permute(1, 2, 3, 4, 0, 5))            # [B,d,h,w,4,C]
         p = feat[4].shape[1]
         intra = self._intra(feat[4].view(4, B, p ** 3, -1), fm)
 
@@ -349,10 +346,8 @@ class Model(nn.Module):
         else:
             ms = ms5 = fm[None]
         P = ms.shape[0]
-        ys = []
-        for s in stacked:
-            _, d, h, w, k, c = s.shape
-            ys.append((s[None] * ms.to(dt).view(P, B, 1, 1, 1, k, 1)).reshape(P * B, d, h, w, k * c).contiguous())
+        # masks are 0/1, so masking the already-masked features again (mask & pass mask) is the product of the two
+        ys = [ops.masked_stack(f, ms) for f in enc[:4]]
         x5 = self._inter(intra, ms5, p)
         logits, preds, des = self.decoder_fuse.run(*ys, x5)
         D, H, W = logits.shape[1:4]

@@ -270,7 +270,7 @@ class Model(nn.Module):
 
     # ------------------------------------------------------------------ feature extraction
     def _features(self, x, mask):
-        """-> enc (4 levels of [4B,d,h,w,C], modality-major) and stacked [B,d,h,w,4C] per level."""
+        """-> enc: 4 levels of [4B,d,h,w,C], modality-major."""
         B = x.shape[0]
         dt = self.compute_dtype
         idt = self.mask_type != 'pdt'
@@ -280,32 +280,21 @@ class Model(nn.Module):
             xin = xin * fm.t()[:, :, None, None, None]                         # rfnet.py:232-233
         xe = xin.reshape(4 * B, *x.shape[2:], 1).to(dt).contiguous()
         encs = (self.flair_encoder, self.t1ce_encoder, self.t1_encoder, self.t2_encoder)
-        enc = _run_encoders(encs, xe)
-        stacked = []
-        for f in enc:
-            _, d, h, w, c = f.shape
-            s = f.view(4, B, d, h, w, c).permute(1, 2, 3, 4, 0, 5)             # [B,d,h,w,4,C]
-            stacked.append(s)
-        return enc, stacked
+        return _run_encoders(encs, xe)
 
     @staticmethod
-    def _masked(stacked, ms):
-        """stacked [B,d,h,w,4,C] x pass masks ms [P,B,4] -> [P*B,d,h,w,4C]."""
-        P, B = ms.shape[:2]
-        out = []
-        for s in stacked:
-            _, d, h, w, k, c = s.shape
-            y = s[None] * ms.to(s.dtype).view(P, B, 1, 1, 1, k, 1)
-            out.append(y.reshape(P * B, d, h, w, k * c).contiguous())
-        return out
+    def _masked(enc, ms):
+        """enc: per-level [4B,d,h,w,C] (modality-major) x pass masks ms [P,B,4] -> per-level [P*B,d,h,w,4C]."""
+        return [ops.masked_stack(f, ms) for f in enc]
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, mask, target=None, temp=1.0):
         if not x.is_cuda:
             raise RuntimeError("passion_b200.models.rfnet.Model runs on CUDA only (no CPU fallback)")
+        ops.begin_step(x.device)
         B = x.shape[0]
         idt = self.mask_type != 'pdt'
-        enc, stacked = self._features(x, mask)
+        enc = self._features(x, mask)
         fm = mask.to(torch.float32)
         train_passion = self.is_training and self.use_passion
         eye = torch.eye(4, device=x.device, dtype=torch.float32)
@@ -324,7 +313,7 @@ class Model(nn.Module):
             if train_passion:
                 ms[1:] = single
         P = ms.shape[0]
-        ys = self._masked(stacked, ms)
+        ys = self._masked(enc, ms)
         logits, prms, des = self.decoder_fuse.run(*ys)
         D, H, W = logits.shape[1:4]
         fuse_logits = logits.view(P, B, D, H, W, -1)

@@ -80,6 +80,44 @@ def _run(name, key, nbytes, flops, fn, allow_unsupported=False):
     return True
 
 
+class _ZeroScratch:
+    """Zero-initialised short-lived scratch (statistics / weight-gradient accumulators that kernels fill with atomics and
+    the very next launch consumes).  Slices of one arena per device, handed out linearly; `begin_step()` re-zeroes the
+    used part with ONE memset instead of one fill launch per buffer (~350 per training step)."""
+    MIN_BYTES = 8 << 20
+
+    def __init__(self):
+        self.arenas = {}
+
+    def begin_step(self, device):
+        a = self.arenas.get(device)
+        if a is not None and a[1] > 0:
+            a[0][:a[1]].zero_()
+            a[1] = 0
+
+    def zeros(self, shape, dtype, device):
+        n = 1
+        for v in shape:
+            n *= int(v)
+        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 255) & ~255
+        a = self.arenas.get(device)
+        if a is None or a[1] + nbytes > a[0].numel():
+            size = max(self.MIN_BYTES, 2 * nbytes, 2 * (a[0].numel() if a is not None else 0))
+            a = [torch.zeros(size, dtype=torch.uint8, device=device), 0]
+            self.arenas[device] = a
+        off = a[1]
+        a[1] = off + nbytes
+        return a[0][off:off + nbytes].view(dtype)[:n].view(shape)
+
+
+_scratch = _ZeroScratch()
+
+
+def begin_step(device):
+    """Call once at the start of a forward pass: recycles the zero scratch of the previous step."""
+    _scratch.begin_step(torch.device(device))
+
+
 def _conv_work(d, esize):
     """algorithmic bytes (each activation tensor touched once) and FLOPs of one conv launch."""
     cin = d.c0 + d.c1
@@ -236,7 +274,7 @@ def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, ne
             _run("conv3d_dgrad", key, nb, fl,
                  lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
     if need_dw:
-        dw = torch.zeros((groups, d.ksize ** 3, cin, d.cout), dtype=torch.float32, device=dy.device)
+        dw = _scratch.zeros((groups, d.ksize ** 3, cin, d.cout), torch.float32, dy.device)
         done = False
         if (TC_ENABLED and WGRAD_TC and dy.dtype == torch.bfloat16 and d.ksize == 3 and d.stride == 1 and d.c0 % 8 == 0
                 and d.c1 % 8 == 0 and d.cout % 8 == 0 and d.cout <= 64):
@@ -263,7 +301,7 @@ class _Conv3d(torch.autograd.Function):
         d = _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups)
         assert w.shape == (groups, ksize ** 3, d.c0 + d.c1, cout), (tuple(w.shape), groups, ksize, d.c0, d.c1, cout)
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
-        stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
+        stats = _scratch.zeros((d.n, cout, 2), torch.float64, x0.device) if want_stats else None
         tc_call = None
         if _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
             err = _tc_err_flag(x0.device)
@@ -295,6 +333,8 @@ class _Conv3d(torch.autograd.Function):
         db = None
         if has_bias and ctx.needs_input_grad[3]:
             db = dy.float().reshape(groups, -1, dy.shape[-1]).sum(1)
+        if dw is not None:
+            dw = dw.clone()                      # the accumulator is recycled scratch
         return dx0, dx1, dw, db, None, None, None, None, None
 
 
@@ -340,7 +380,7 @@ class _Conv3dRef(torch.autograd.Function):
                                                nt=_tc_ntile(cin, cout) if fwd_tc else 0,
                                                ntT=_tc_ntile(cout, cin) if dgrad_tc else 0, want_bias=has_bias)
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
-        stats = torch.zeros((d.n, cout, 2), dtype=torch.float64, device=x0.device) if want_stats else None
+        stats = _scratch.zeros((d.n, cout, 2), torch.float64, x0.device) if want_stats else None
         tc_call = None
         if fwd_tc:
             err = _tc_err_flag(x0.device)
@@ -439,7 +479,7 @@ class _InormLrelu(torch.autograd.Function):
         dout = dout.contiguous()
         n, c = y.shape[0], y.shape[-1]
         voxels = y.numel() // (n * c)
-        sums = torch.zeros((n, c, 2), dtype=torch.float64, device=y.device)
+        sums = _scratch.zeros((n, c, 2), torch.float64, y.device)
         dy = torch.empty_like(y)
         _run("inorm_lrelu_bwd", f"c{c}", y.numel() * y.element_size() * 3, 0,
              lambda: lib.pb_inorm_lrelu_bwd(_dt(y), _p(dout), _p(y), _p(mr), _p(sums), _p(dy), n, voxels, c, LRELU_SLOPE,
@@ -487,7 +527,7 @@ def channel_stats(x):
     _chk(x)
     n, c = x.shape[0], x.shape[-1]
     voxels = x.numel() // (n * c)
-    stats = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    stats = _scratch.zeros((n, c, 2), torch.float64, x.device)
     _run("channel_stats", f"c{c}", x.numel() * x.element_size(), 0,
          lambda: lib.pb_channel_stats(_dt(x), _p(x), _p(stats), n, voxels, c, _stream()))
     return stats
@@ -548,6 +588,44 @@ def _gate_mlp(S, Psum, voxels, w0, b0, w2, b2):
     feat = torch.cat((S / voxels / prm_avg[..., None], prm_avg[..., None]), -1)        # [N,4,KC+1]
     h = torch.nn.functional.leaky_relu(torch.einsum("nif,ihf->nih", feat, w0) + b0, LRELU_SLOPE)
     return torch.sigmoid(torch.einsum("nih,ikh->nik", h, w2) + b2)
+
+
+class _MaskedStack(torch.autograd.Function):
+    """out[p*B+b, ..., m*C+c] = enc[m*B+b, ..., c] * ms[p, b, m]  (MaskModal for P decoder passes in one launch)."""
+
+    @staticmethod
+    def forward(ctx, enc, ms):
+        lib = _lib.load()
+        ms = ms.to(torch.float32).contiguous()
+        _chk(enc, ms)
+        P, B = ms.shape[:2]
+        assert ms.shape[2] == 4 and enc.shape[0] == 4 * B
+        C = enc.shape[-1]
+        V = enc.numel() // (4 * B * C)
+        out = torch.empty((P * B,) + tuple(enc.shape[1:-1]) + (4 * C,), dtype=enc.dtype, device=enc.device)
+        nb = (enc.numel() + out.numel()) * enc.element_size()
+        _run("masked_stack_fwd", f"c{C} p{P}", nb, 0,
+             lambda: lib.pb_masked_stack_fwd(_dt(enc), _p(enc), _p(ms), _p(out), P, B, V, C, _stream()))
+        ctx.save_for_backward(ms)
+        ctx.meta = (tuple(enc.shape), P, B, V, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        (ms,) = ctx.saved_tensors
+        shape, P, B, V, C = ctx.meta
+        dout = dout.contiguous()
+        denc = torch.empty(shape, dtype=dout.dtype, device=dout.device)
+        nb = (denc.numel() + dout.numel()) * dout.element_size()
+        _run("masked_stack_bwd", f"c{C} p{P}", nb, 0,
+             lambda: lib.pb_masked_stack_bwd(_dt(dout), _p(dout), _p(ms), _p(denc), P, B, V, C, _stream()))
+        return denc, None
+
+
+def masked_stack(enc, ms):
+    """enc [4B,D,H,W,C] (modality-major), ms [P,B,4] -> [P*B,D,H,W,4C]."""
+    return _MaskedStack.apply(enc, ms)
 
 
 class _RfmRegion(torch.autograd.Function):

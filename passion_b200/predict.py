@@ -79,8 +79,9 @@ def predict_all_masks(model, x, masks=None, patch_size=80):
     ms = mt.to(torch.float32)[:, None, :]                                              # [M, B=1, 4] pass masks
     for h, w, z in _windows(shape, patch_size):
         xw = x[:, :, h:h + patch_size, w:w + patch_size, z:z + patch_size].contiguous()
-        _, stacked = model._features(xw, all_present)                                  # encoders once
-        ys = model._masked(stacked, ms)                                                # 15 masked copies
+        ops.begin_step(x.device)
+        enc = model._features(xw, all_present)                                         # encoders once
+        ys = model._masked(enc, ms)                                                    # 15 masked copies
         logits, _, _ = model.decoder_fuse.run(*ys)                                     # one batch-15 decoder pass
         prob = ops.softmax4(logits).permute(0, 4, 1, 2, 3)                             # [M,C,p,p,p]
         pred[:, :, h:h + patch_size, w:w + patch_size, z:z + patch_size] += prob

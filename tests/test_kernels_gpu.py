@@ -166,6 +166,25 @@ def test_conv3d_on_parameter_layout(lib_built, case, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,P,B,shape", [(8, 5, 2, (6, 5, 7)), (16, 1, 3, (4, 4, 4)), (64, 15, 1, (2, 3, 2))])
+def test_masked_stack(lib_built, C, P, B, shape, dtype):
+    """MaskModal for P passes in one launch (rfnet.py:154-163): out[p*B+b, ..., m*C+c] = enc[m*B+b, ..., c] * ms[p,b,m]."""
+    from passion_b200 import ops
+    g = torch.Generator().manual_seed(C + P)
+    enc = torch.randn(4 * B, *shape, C, generator=g).cuda().to(dtype).requires_grad_(True)
+    ms = (torch.rand(P, B, 4, generator=g) > 0.4).float().cuda()
+    out = ops.masked_stack(enc, ms)
+    ref_in = enc.detach().double().requires_grad_(True)
+    st = ref_in.view(4, B, *shape, C).permute(1, 2, 3, 4, 0, 5)                       # [B,d,h,w,4,C]
+    ref = (st[None] * ms.double().view(P, B, 1, 1, 1, 4, 1)).reshape(P * B, *shape, 4 * C)
+    assert torch.equal(out.double(), ref.detach())                                   # masks are 0/1: exact
+    gy = torch.randn(out.shape, generator=g).cuda().to(dtype)
+    out.backward(gy)
+    ref.backward(gy.double())
+    assert rel(enc.grad, ref_in.grad) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("c,shape,with_res", [(8, (12, 10, 14), True), (16, (6, 7, 8), False), (2, (8, 8, 8), False),
                                               (4, (5, 5, 5), True), (64, (2, 2, 2), False), (32, (4, 5, 6), True),
                                               (1, (6, 6, 6), False)])
