@@ -118,6 +118,101 @@ __global__ void __launch_bounds__(128) conv_fwd_kernel(ConvK p, const T* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------ 1x1x1 forward / data gradient
+// Pointwise conv: y[v][co] = b[co] + sum_ci x[v][ci] w[ci][co].  HBM-bound, so the kernel is built around the memory
+// system: a fixed grid of CTAs strides over the voxels of one sample, every thread keeps UNR voxels (independent 16-byte
+// loads) in flight, the statistics are accumulated in registers over the whole stride loop and reduced ONCE per CTA.
+// The data gradient of a 1x1x1 conv is the same operation on dy with the transposed weights and the output split
+// across the two sources (y0 | y1).
+struct PwK {
+    int N, C0, C1, Cin, CO0, CO1, Cout, npg;
+    long long V;
+};
+
+template <typename T, int CI_V, int CO_T, int UNR>
+__global__ void __launch_bounds__(256) pw_conv_kernel(PwK p, const T* __restrict__ x0, const T* __restrict__ x1,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      T* __restrict__ y0, T* __restrict__ y1, double* __restrict__ stats) {
+    extern __shared__ __align__(16) float wsm[];              // [Cin][CO_T]
+    __shared__ float red[8][CO_T * 2];
+    const int n = blockIdx.z, coc = blockIdx.y, g = n / p.npg;
+    const float* wg = w + (size_t)g * p.Cin * p.Cout + coc * CO_T;
+    for (int i = threadIdx.x; i < p.Cin * CO_T; i += 256) wsm[i] = wg[(size_t)(i / CO_T) * p.Cout + (i % CO_T)];
+    __syncthreads();
+    float b[CO_T], s1[CO_T], s2[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) { b[j] = bias ? bias[(size_t)g * p.Cout + coc * CO_T + j] : 0.f; s1[j] = 0.f; s2[j] = 0.f; }
+    const long long stride = (long long)gridDim.x * 256;
+    const int co0 = coc * CO_T;
+    const T* xs0 = x0 + (size_t)n * p.V * p.C0;
+    const T* xs1 = p.C1 ? x1 + (size_t)n * p.V * p.C1 : nullptr;
+    for (long long v0 = (long long)blockIdx.x * 256 + threadIdx.x; v0 < p.V; v0 += stride * UNR) {
+        float acc[UNR][CO_T];
+        long long vv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long v = v0 + u * stride;
+            vv[u] = v < p.V ? v : v0;                         // tail: recompute voxel v0, the store is skipped
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) acc[u][j] = b[j];
+        }
+        for (int c = 0; c < p.C0; c += CI_V) {
+            float xv[UNR][CI_V];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) VecIO<T, CI_V>::load(xs0 + vv[u] * p.C0 + c, xv[u]);
+#pragma unroll
+            for (int i = 0; i < CI_V; ++i) {
+                float wv[CO_T];
+                lds_vec<CO_T>(wsm + (c + i) * CO_T, wv);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                    for (int j = 0; j < CO_T; ++j) acc[u][j] = fmaf(xv[u][i], wv[j], acc[u][j]);
+            }
+        }
+        for (int c = 0; c < p.C1; c += CI_V) {
+            float xv[UNR][CI_V];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) VecIO<T, CI_V>::load(xs1 + vv[u] * p.C1 + c, xv[u]);
+#pragma unroll
+            for (int i = 0; i < CI_V; ++i) {
+                float wv[CO_T];
+                lds_vec<CO_T>(wsm + (p.C0 + c + i) * CO_T, wv);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                    for (int j = 0; j < CO_T; ++j) acc[u][j] = fmaf(xv[u][i], wv[j], acc[u][j]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long v = v0 + u * stride;
+            if (v < p.V) {
+                const size_t vox = (size_t)n * p.V + v;
+                T* dst = co0 < p.CO0 ? y0 + vox * p.CO0 + co0 : y1 + vox * p.CO1 + (co0 - p.CO0);
+                VecIO<T, CO_T>::store(dst, acc[u]);
+#pragma unroll
+                for (int j = 0; j < CO_T; ++j) { s1[j] += acc[u][j]; s2[j] += acc[u][j] * acc[u][j]; }
+            }
+        }
+    }
+    if (stats) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) {
+            const float s = warp_sum(s1[j]), q = warp_sum(s2[j]);
+            if (lane == 0) { red[wid][2 * j] = s; red[wid][2 * j + 1] = q; }
+        }
+        __syncthreads();
+        if (threadIdx.x < CO_T * 2) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += (double)red[k][threadIdx.x];
+            atomicAdd(&stats[((size_t)n * p.Cout + co0 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1)], v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ dgrad
 // Exact adjoint of the forward gather, as a gather over dy: one thread = one INPUT voxel x CI_T
 // input channels.  For every padded position p that the forward's index map sends to this voxel
@@ -448,9 +543,57 @@ int dispatch_fwd_co(int co_t, const ConvK& k, const void* x0, const void* x1, co
     }
 }
 
+template <typename T, int CI_V, int CO_T>
+int launch_pw(const PwK& p, const void* x0, const void* x1, const float* w, const float* bias, void* y0, void* y1, double* stats,
+              cudaStream_t st) {
+    constexpr int UNR = (CO_T >= 16 || CI_V * CO_T > 64) ? 2 : 4;
+    const size_t smem = (size_t)p.Cin * CO_T * sizeof(float);
+    auto kern = pw_conv_kernel<T, CI_V, CO_T, UNR>;
+    if (int e = set_smem(kern, smem)) return e;
+    const int chunks = p.Cout / CO_T;
+    long long bx = (p.V + 256LL * UNR - 1) / (256LL * UNR);
+    const long long cap = (148LL * 8 + (long long)p.N * chunks - 1) / ((long long)p.N * chunks);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    kern<<<dim3((unsigned)bx, chunks, p.N), 256, smem, st>>>(p, (const T*)x0, (const T*)x1, w, bias, (T*)y0, (T*)y1, stats);
+    return 0;
+}
+
+template <typename T, int CI_V>
+int dispatch_pw_co(int co_t, const PwK& p, const void* x0, const void* x1, const float* w, const float* bias, void* y0, void* y1,
+                   double* stats, cudaStream_t st) {
+    switch (co_t) {
+        case 16: return launch_pw<T, CI_V, 16>(p, x0, x1, w, bias, y0, y1, stats, st);
+        case 8:  return launch_pw<T, CI_V, 8>(p, x0, x1, w, bias, y0, y1, stats, st);
+        case 4:  return launch_pw<T, CI_V, 4>(p, x0, x1, w, bias, y0, y1, stats, st);
+        case 2:  return launch_pw<T, CI_V, 2>(p, x0, x1, w, bias, y0, y1, stats, st);
+        default: return launch_pw<T, CI_V, 1>(p, x0, x1, w, bias, y0, y1, stats, st);
+    }
+}
+
+// p.C0|C1 = input split, p.CO0|CO1 = output split
+template <typename T>
+int dispatch_pw(const PwK& p, const void* x0, const void* x1, const float* w, const float* bias, void* y0, void* y1,
+                double* stats, cudaStream_t st) {
+    int ci_v = chunk_of(p.C0, 8);
+    if (p.C1) ci_v = chunk_of(p.C1, ci_v);
+    int co_t = chunk_of(p.CO0, 16);
+    if (p.CO1) co_t = chunk_of(p.CO1, co_t);
+    switch (ci_v) {
+        case 8:  return dispatch_pw_co<T, 8>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);
+        case 4:  return dispatch_pw_co<T, 4>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);
+        case 2:  return dispatch_pw_co<T, 2>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);
+        default: return dispatch_pw_co<T, 1>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);
+    }
+}
+
 template <typename T>
 int dispatch_fwd(const ConvK& k, const void* x0, const void* x1, const float* w, const float* bias, void* y, double* stats,
                  cudaStream_t st) {
+    if (k.K == 1 && k.S == 1) {
+        PwK p{k.N, k.C0, k.C1, k.Cin, k.Cout, 0, k.Cout, k.npg, k.Vo};
+        return dispatch_pw<T>(p, x0, x1, w, bias, y, nullptr, stats, st);
+    }
     int ci_v = chunk_of(k.C0, 8);
     if (k.C1) ci_v = chunk_of(k.C1, ci_v);
     int co_t = chunk_of(k.Cout, 16);
@@ -489,6 +632,11 @@ int dispatch_dgrad_ci(int ci_t, const ConvK& k, const void* dy, const float* wt,
 
 template <typename T>
 int dispatch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, void* dx1, cudaStream_t st, bool mo = false) {
+    if (k.K == 1 && k.S == 1 && !mo) {
+        // dx[v][ci] = sum_co dy[v][co] wt[co][ci]: the pointwise kernel with the roles of the channels swapped
+        PwK p{k.N, k.Cout, 0, k.Cout, k.C0, k.C1, k.Cin, k.npg, k.Vi};
+        return dispatch_pw<T>(p, dy, nullptr, wt, nullptr, dx0, dx1, nullptr, st);
+    }
     const int co_v = chunk_of(k.Cout, 8);
     int ci_t = chunk_of(k.C0, 16);
     if (k.C1) ci_t = chunk_of(k.C1, ci_t);
@@ -528,6 +676,86 @@ int dispatch_wgrad_co(int co_t, const ConvK& k, const WgK& q, const void* x0, co
     }
 }
 
+// Row-cooperative variant: the L = Cin/CI_B lanes of a lane group share one voxel, each owning one CI_B-channel chunk
+// of its x row (so a warp reads whole rows, every sector fully used) and all reading the same CO_B dy values (one
+// broadcast sector).  x and dy are read exactly once per Cout tile.  Accumulators are combined by xor-shuffles across
+// the lane groups, then across the 8 warps through shared memory, then one atomicAdd per element and CTA.
+template <typename T, int CI_B, int CO_B, int UNR>
+__global__ void __launch_bounds__(256) conv1_wgrad_rows_kernel(ConvK p, int L, const T* __restrict__ x0, const T* __restrict__ x1,
+                                                               const T* __restrict__ dy, float* __restrict__ dw) {
+    extern __shared__ float red[];                            // [8][Cin * CO_B]
+    const int g = blockIdx.z, co0 = blockIdx.y * CO_B;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sub = lane % L, vl = lane / L, vpw = 32 / L;
+    const int ci0 = sub * CI_B;
+    const bool from1 = ci0 >= p.C0;
+    const T* xs = from1 ? x1 : x0;
+    const int cs = from1 ? p.C1 : p.C0, coff = from1 ? ci0 - p.C0 : ci0;
+    float acc[CI_B][CO_B];
+#pragma unroll
+    for (int i = 0; i < CI_B; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_B; ++j) acc[i][j] = 0.f;
+    const long long v_begin = (long long)g * p.npg * p.Vo, v_end = v_begin + (long long)p.npg * p.Vo;
+    const long long stride = (long long)gridDim.x * 8 * vpw;
+    for (long long v0 = v_begin + ((long long)blockIdx.x * 8 + wid) * vpw + vl; v0 < v_end; v0 += stride * UNR) {
+        float xv[UNR][CI_B], gv[UNR][CO_B];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long v = v0 + u * stride;
+            if (v < v_end) {
+                VecIO<T, CI_B>::load(xs + v * cs + coff, xv[u]);
+                VecIO<T, CO_B>::load(dy + v * p.Cout + co0, gv[u]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < CI_B; ++i) xv[u][i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < CO_B; ++j) gv[u][j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int i = 0; i < CI_B; ++i)
+#pragma unroll
+                for (int j = 0; j < CO_B; ++j) acc[i][j] = fmaf(xv[u][i], gv[u][j], acc[i][j]);
+    }
+    const int row = p.Cin * CO_B;
+#pragma unroll
+    for (int i = 0; i < CI_B; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_B; ++j) {
+            float s = acc[i][j];
+            for (int off = L; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane < L) red[wid * row + (ci0 + i) * CO_B + j] = s;
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < row; e += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * row + e];
+        const int ci = e / CO_B, j = e % CO_B;
+        atomicAdd(dw + ((size_t)g * p.Cin + ci) * p.Cout + co0 + j, s);
+    }
+}
+
+template <typename T, int CI_B, int CO_B>
+int launch_wgrad1_rows(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
+    constexpr int UNR = CI_B * CO_B >= 64 ? 2 : 4;
+    const int L = k.Cin / CI_B;
+    const int tiles = k.Cout / CO_B;
+    const size_t smem = (size_t)8 * k.Cin * CO_B * sizeof(float);
+    auto kern = conv1_wgrad_rows_kernel<T, CI_B, CO_B, UNR>;
+    if (int e = set_smem(kern, smem)) return e;
+    const long long vox = (long long)k.npg * k.Vo;
+    long long nblk = (148LL * 6 + (long long)tiles * k.groups - 1) / ((long long)tiles * k.groups);
+    const long long need = (vox * L + 256 * 8 - 1) / (256 * 8);         // >= 8 voxels per lane group
+    if (nblk > need) nblk = need;
+    if (nblk < 1) nblk = 1;
+    kern<<<dim3((unsigned)nblk, tiles, k.groups), 256, smem, st>>>(k, L, (const T*)x0, (const T*)x1, (const T*)dy, dw);
+    return 0;
+}
+
 template <typename T, int CI_B, int CO_B>
 int launch_wgrad1(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
     const int tiles = (k.Cin / CI_B) * (k.Cout / CO_B);
@@ -543,6 +771,26 @@ int launch_wgrad1(const ConvK& k, const void* x0, const void* x1, const void* dy
 
 template <typename T>
 int dispatch_wgrad1(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
+    {
+        // row-cooperative kernel: needs Cin / CI_B to be a power of two <= 32 and the reduction buffer to fit; measured
+        // faster than the tile kernel below only for rows of >= 4 chunks (c32->8 80^3: 0.27 -> 0.23 ms)
+        const int co_r = chunk_of(k.Cout, 8);
+        int ci_r = chunk_of(k.C0, 8);
+        if (k.C1) ci_r = chunk_of(k.C1, ci_r);
+        while (k.Cin / ci_r > 32 && ci_r < 8) ci_r <<= 1;
+        const int L = k.Cin / ci_r;
+        const bool pow2 = L >= 1 && L <= 32 && (L & (L - 1)) == 0 && L * ci_r == k.Cin && k.C0 % ci_r == 0 && k.C1 % ci_r == 0;
+        if (pow2 && L >= 4 && (size_t)8 * k.Cin * co_r * sizeof(float) <= 96 * 1024 && (ci_r == 8 || ci_r == 4 || ci_r == 2 || ci_r == 1)) {
+#define W1R(CI, CO) return launch_wgrad1_rows<T, CI, CO>(k, x0, x1, dy, dw, st)
+            switch (co_r) {
+                case 8:  switch (ci_r) { case 8: W1R(8, 8); case 4: W1R(4, 8); case 2: W1R(2, 8); default: W1R(1, 8); }
+                case 4:  switch (ci_r) { case 8: W1R(8, 4); case 4: W1R(4, 4); case 2: W1R(2, 4); default: W1R(1, 4); }
+                case 2:  switch (ci_r) { case 8: W1R(8, 2); case 4: W1R(4, 2); case 2: W1R(2, 2); default: W1R(1, 2); }
+                default: switch (ci_r) { case 8: W1R(8, 1); case 4: W1R(4, 1); case 2: W1R(2, 1); default: W1R(1, 1); }
+            }
+#undef W1R
+        }
+    }
     const int co_b = chunk_of(k.Cout, 16);
     int ci_b = chunk_of(k.C0, 64 / co_b > 8 ? 8 : 64 / co_b);
     if (k.C1) ci_b = chunk_of(k.C1, ci_b);

@@ -60,11 +60,32 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const T* __restrict_
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
         const T* xn = x + (size_t)n * voxels * c;
-        for (long long v = (long long)blockIdx.x * vpb + vl; v < voxels; v += (long long)gridDim.x * vpb) {
-            float xv[VEC];
-            VecIO<T, VEC>::load(xn + v * c + c0, xv);
+        const long long stride = (long long)gridDim.x * vpb;
+        for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * 4) {
+            float xv[4][VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) { s1[j] += (double)xv[j]; s2[j] += (double)xv[j] * (double)xv[j]; }
+            for (int u = 0; u < 4; ++u) {
+                const long long v = v0 + u * stride;
+                if (v < voxels) VecIO<T, VEC>::load(xn + v * c + c0, xv[u]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) xv[u][j] = 0.f;
+                }
+            }
+            if (sizeof(T) == 4) {                             // fp32 check mode: every element in float64
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) { s1[j] += (double)xv[u][j]; s2[j] += (double)xv[u][j] * (double)xv[u][j]; }
+            } else {                                          // bf16 storage: fp32 over a run of 4, float64 across runs
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { a += xv[u][j]; b = fmaf(xv[u][j], xv[u][j], b); }
+                    s1[j] += (double)a; s2[j] += (double)b;
+                }
+            }
         }
         double* r = ssum + (size_t)vl * 2 * c;
 #pragma unroll
@@ -80,10 +101,16 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const T* __restrict_
 
 // per-(n,c): sum g, sum g*xhat  with g = dout * lrelu'(xhat).  grid = (blocks_per_sample, n);
 // a thread keeps the same VEC channels for all its voxels; block reduction in a fixed order (deterministic).
+// Precision: the fp32 check mode (T = float) accumulates every element in float64.  Under bf16 storage the inputs carry
+// 2^-9 relative rounding already, so runs of kRun voxels are summed in fp32 and only the run totals go to the float64
+// accumulators — per-element float64 conversions would otherwise make this memory-bound pass conversion-bound.
+constexpr int kRun = 4;
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                          const float* __restrict__ mr, double* __restrict__ sums,
                                                          long long voxels, int c, float slope) {
+    constexpr bool kExact = sizeof(T) == 4;
     extern __shared__ double ssum[];                          // [vpb][2*c]
     const int n = blockIdx.y;
     const int lanes = c / VEC;                                // threads per voxel
@@ -99,17 +126,47 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
             mean[j] = mr[((size_t)n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)n * c + c0 + j) * 2 + 1];
             sg[j] = 0.0; sgx[j] = 0.0;
         }
-        const T* dn = dout + (size_t)n * voxels * c;
-        const T* yn = y + (size_t)n * voxels * c;
-        for (long long v = (long long)blockIdx.x * vpb + vl; v < voxels; v += (long long)gridDim.x * vpb) {
-            float g[VEC], yv[VEC];
-            VecIO<T, VEC>::load(dn + v * c + c0, g);
-            VecIO<T, VEC>::load(yn + v * c + c0, yv);
+        const T* dn = dout + (size_t)n * voxels * c + c0;
+        const T* yn = y + (size_t)n * voxels * c + c0;
+        const long long stride = (long long)gridDim.x * vpb;
+        for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * kRun) {
+            float g[kRun][VEC], yv[kRun][VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                float xh = (yv[j] - mean[j]) * rstd[j];
-                float gg = xh > 0.f ? g[j] : g[j] * slope;
-                sg[j] += (double)gg; sgx[j] += (double)gg * (((double)yv[j] - (double)mean[j]) * (double)rstd[j]);
+            for (int u = 0; u < kRun; ++u) {                  // all loads of the run are in flight together
+                const long long v = v0 + u * stride;
+                if (v < voxels) {
+                    VecIO<T, VEC>::load(dn + v * c, g[u]);
+                    VecIO<T, VEC>::load(yn + v * c, yv[u]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) { g[u][j] = 0.f; yv[u][j] = mean[j]; }
+                }
+            }
+            if (kExact) {
+#pragma unroll
+                for (int u = 0; u < kRun; ++u)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const float xh = (yv[u][j] - mean[j]) * rstd[j];
+                        const float gg = xh > 0.f ? g[u][j] : g[u][j] * slope;
+                        sg[j] += (double)gg;
+                        sgx[j] += (double)gg * (((double)yv[u][j] - (double)mean[j]) * (double)rstd[j]);
+                    }
+            } else {
+                float pg[VEC], pgx[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { pg[j] = 0.f; pgx[j] = 0.f; }
+#pragma unroll
+                for (int u = 0; u < kRun; ++u)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const float xh = (yv[u][j] - mean[j]) * rstd[j];
+                        const float gg = xh > 0.f ? g[u][j] : g[u][j] * slope;
+                        pg[j] += gg;
+                        pgx[j] = fmaf(gg, xh, pgx[j]);
+                    }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { sg[j] += (double)pg[j]; sgx[j] += (double)pgx[j]; }
             }
         }
         double* r = ssum + (size_t)vl * 2 * c;
@@ -125,31 +182,51 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
 }
 
 // dy = rstd * (g - mean(g) - xhat * mean(g*xhat)).  The three-term difference cancels heavily when the incoming
-// gradient lies mostly in span{1, xhat} (typical right below the loss), so it is evaluated in float64 from the
-// float64 sums; the LeakyReLU branch uses the same fp32 xhat as the forward pass.
+// gradient lies mostly in span{1, xhat} (typical right below the loss); in the fp32 check mode it is evaluated in
+// float64 from the float64 sums.  Under bf16 storage fp32 arithmetic is already ~2^15 finer than the operands.
+// Same thread -> channel mapping as the reduce pass, so the per-channel coefficients are loaded once per thread.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                         const float* __restrict__ mr, const double* __restrict__ sums,
-                                                        T* __restrict__ dy, long long total_vec, long long vox_c, int c,
-                                                        double inv_v, float slope) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-        const long long e = i * VEC;
-        const int n = (int)(e / vox_c);
-        const int c0 = (int)(e % c);
-        float g[VEC], yv[VEC];
-        VecIO<T, VEC>::load(dout + e, g);
-        VecIO<T, VEC>::load(y + e, yv);
-        const float* m = mr + ((size_t)n * c + c0) * 2;
-        const double* s = sums + ((size_t)n * c + c0) * 2;
+                                                        T* __restrict__ dy, long long voxels, int c, double inv_v, float slope) {
+    constexpr bool kExact = sizeof(T) == 4;
+    const int n = blockIdx.y;
+    const int lanes = c / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
+    if ((int)threadIdx.x >= tpb) return;
+    const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
+    const int c0 = cl * VEC;
+    float mean[VEC], rstd[VEC], af[VEC], bf[VEC];
+    double ad[VEC], bd[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const float rstd = m[2 * j + 1];
-            const float xh = (yv[j] - m[2 * j]) * rstd;
-            const float gg = xh > 0.f ? g[j] : g[j] * slope;
-            const double xd = ((double)yv[j] - (double)m[2 * j]) * (double)rstd;
-            g[j] = (float)((double)rstd * ((double)gg - s[2 * j] * inv_v - xd * (s[2 * j + 1] * inv_v)));
-        }
-        VecIO<T, VEC>::store(dy + e, g);
+    for (int j = 0; j < VEC; ++j) {
+        mean[j] = mr[((size_t)n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)n * c + c0 + j) * 2 + 1];
+        ad[j] = sums[((size_t)n * c + c0 + j) * 2] * inv_v; bd[j] = sums[((size_t)n * c + c0 + j) * 2 + 1] * inv_v;
+        af[j] = (float)ad[j]; bf[j] = (float)bd[j];
+    }
+    const size_t base = (size_t)n * voxels * c + c0;
+    const long long stride = (long long)gridDim.x * vpb;
+    for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * 2) {
+        const long long v1 = v0 + stride;
+        const bool has1 = v1 < voxels;
+        float g[2][VEC], yv[2][VEC];
+        VecIO<T, VEC>::load(dout + base + v0 * c, g[0]);
+        VecIO<T, VEC>::load(y + base + v0 * c, yv[0]);
+        if (has1) { VecIO<T, VEC>::load(dout + base + v1 * c, g[1]); VecIO<T, VEC>::load(y + base + v1 * c, yv[1]); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float xh = (yv[u][j] - mean[j]) * rstd[j];
+                const float gg = xh > 0.f ? g[u][j] : g[u][j] * slope;
+                if (kExact) {
+                    const double xd = ((double)yv[u][j] - (double)mean[j]) * (double)rstd[j];
+                    g[u][j] = (float)((double)rstd[j] * ((double)gg - ad[j] - xd * bd[j]));
+                } else {
+                    g[u][j] = rstd[j] * (gg - af[j] - xh * bf[j]);
+                }
+            }
+        VecIO<T, VEC>::store(dy + base + v0 * c, g[0]);
+        if (has1) VecIO<T, VEC>::store(dy + base + v1 * c, g[1]);
     }
 }
 
@@ -191,9 +268,11 @@ int run_bwd(const void* dout, const void* y, const float* mr, double* sums, void
         if (bps < 1) bps = 1;
         bwd_reduce_kernel<T, VEC><<<dim3(bps, nn), 256, (size_t)vpb * 2 * c * sizeof(double), st>>>(d_, y_, mr_, s_, voxels, c, slope);
         pb_count_launch();
-        const long long total_vec = (long long)nn * voxels * c / VEC;
-        bwd_apply_kernel<T, VEC><<<grid_for(total_vec, 256), 256, 0, st>>>(d_, y_, mr_, s_, o_, total_vec, voxels * c, c,
-                                                                          1.0 / (double)voxels, slope);
+        int bpa = (int)((voxels + (long long)vpb * 4 - 1) / ((long long)vpb * 4));     // >= 4 voxels per thread
+        const int capa = (148 * 16 + nn - 1) / nn;
+        if (bpa > capa) bpa = capa;
+        if (bpa < 1) bpa = 1;
+        bwd_apply_kernel<T, VEC><<<dim3(bpa, nn), 256, 0, st>>>(d_, y_, mr_, s_, o_, voxels, c, 1.0 / (double)voxels, slope);
         if (n0 + group < n) pb_count_launch();
     }
     return 0;
