@@ -142,6 +142,7 @@ def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
 TC_ENABLED = os.environ.get("PB_TC", "1") != "0"
 WGRAD_TC = os.environ.get("PB_WGRAD_TC", "1") != "0"
 DGRAD_FOLD = os.environ.get("PB_DGRAD_FOLD", "1") != "0"      # reflect-pad data gradient: extended-domain tc pass + fold
+UPSAMPLE_SEPARABLE_FROM = int(os.environ.get("PB_UPS_SEP", "2"))     # trilinear adjoint: three 1-D passes from this scale on
 TC_STACKED = os.environ.get("PB_TCS", "0") != "0"        # kw-stacked variant of the fwd / dgrad implicit GEMM (measured: not faster)
 _tc_err = {}
 
@@ -559,7 +560,7 @@ class _Upsample(torch.autograd.Function):
         n, d, h, w, c = ctx.shape
         s = ctx.scale
         dx = torch.empty((n, d, h, w, c), dtype=dy.dtype, device=dy.device)
-        if s <= 2:
+        if s < UPSAMPLE_SEPARABLE_FROM:
             _run("upsample_bwd", f"c{c} x{s}", (dx.numel() + dy.numel()) * dy.element_size(), 0,
                  lambda: lib.pb_upsample_bwd(_dt(dy), _p(dy), _p(dx), n, d, h, w, c, s, _stream()))
             return dx, None
