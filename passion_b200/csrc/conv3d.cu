@@ -579,6 +579,8 @@ int dispatch_pw(const PwK& p, const void* x0, const void* x1, const float* w, co
     if (p.C1) ci_v = chunk_of(p.C1, ci_v);
     int co_t = chunk_of(p.CO0, 16);
     if (p.CO1) co_t = chunk_of(p.CO1, co_t);
+    // small volumes (deep levels): narrower Cout tiles give more CTAs; x is re-read from L2, which is cheap at these sizes
+    while (co_t > 4 && ((p.V + 511) / 512) * (p.Cout / co_t) * p.N < 148) co_t >>= 1;
     switch (ci_v) {
         case 8:  return dispatch_pw_co<T, 8>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);
         case 4:  return dispatch_pw_co<T, 4>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);

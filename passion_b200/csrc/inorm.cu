@@ -16,6 +16,50 @@ __global__ void finalize_kernel(const double* __restrict__ stats, float* __restr
     mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Block-level finish of per-thread float64 partials (thread = VEC channels of one voxel lane).  When the lanes-per-voxel
+// count is a power of two <= 32 the voxel lanes of a warp are combined by xor-shuffles and only the 8 warp totals go
+// through shared memory; otherwise every voxel lane writes its partials and 2c threads sum them (the old, slow tail:
+// it made the reduce pass 1.7x slower than the apply pass on the same tensor).
+template <int VEC>
+__device__ __forceinline__ void block_finish(const double* s1, const double* s2, double* ssum, double* __restrict__ out,
+                                             int lanes, int vpb, int c, int c0, int vl, bool active) {
+    const bool pow2 = lanes <= 32 && (lanes & (lanes - 1)) == 0;
+    if (pow2) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            double a = active ? s1[j] : 0.0, b = active ? s2[j] : 0.0;
+            for (int off = lanes; off < 32; off <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, off);
+                b += __shfl_xor_sync(0xffffffffu, b, off);
+            }
+            if (lane < lanes) {                               // lanes divides 32: lane % lanes is this thread's channel lane
+                ssum[(size_t)wid * 2 * c + 2 * (c0 + j)] = a;
+                ssum[(size_t)wid * 2 * c + 2 * (c0 + j) + 1] = b;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * c; i += 256) {
+            double t = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) t += ssum[(size_t)w8 * 2 * c + i];
+            atomicAdd(&out[i], t);
+        }
+    } else {
+        if (active) {
+            double* r = ssum + (size_t)vl * 2 * c;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { r[2 * (c0 + j)] = s1[j]; r[2 * (c0 + j) + 1] = s2[j]; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * c; i += 256) {
+            double t = 0.0;
+            for (int v = 0; v < vpb; ++v) t += ssum[(size_t)v * 2 * c + i];
+            atomicAdd(&out[i], t);
+        }
+    }
+}
+
 // out = lrelu((y - mean) * rstd) (+ res);  one thread = VEC channels of one voxel, two independent vectors per
 // iteration (all loads are issued before the first use, doubling the bytes in flight per thread)
 template <typename T, int VEC>
@@ -50,15 +94,16 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
 // per-(n,c) sum and sum of squares of an arbitrary tensor (statistics for a PRE-norm block, reference
 // models/blocks.py:312-316, where the normalised tensor is not a conv output of ours).  grid = (blocks_per_sample, n)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) channel_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, long long voxels, int c) {
+__global__ void __launch_bounds__(256, 2) channel_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, long long voxels, int c) {
     extern __shared__ double ssum[];                          // [vpb][2*c]
     const int n = blockIdx.y;
     const int lanes = c / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
-    if ((int)threadIdx.x < tpb) {
-        const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes, c0 = cl * VEC;
-        double s1[VEC], s2[VEC];
+    const bool active = (int)threadIdx.x < tpb;
+    const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes, c0 = cl * VEC;
+    double s1[VEC], s2[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
+    for (int j = 0; j < VEC; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
+    if (active) {
         const T* xn = x + (size_t)n * voxels * c;
         const long long stride = (long long)gridDim.x * vpb;
         for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * 4) {
@@ -87,16 +132,8 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const T* __restrict_
                 }
             }
         }
-        double* r = ssum + (size_t)vl * 2 * c;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { r[2 * (c0 + j)] = s1[j]; r[2 * (c0 + j) + 1] = s2[j]; }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * c; i += 256) {
-        double s = 0.0;
-        for (int v = 0; v < vpb; ++v) s += ssum[(size_t)v * 2 * c + i];
-        atomicAdd(&stats[(size_t)n * c * 2 + i], s);
-    }
+    block_finish<VEC>(s1, s2, ssum, stats + (size_t)n * c * 2, lanes, vpb, c, c0, vl, active);
 }
 
 // per-(n,c): sum g, sum g*xhat  with g = dout * lrelu'(xhat).  grid = (blocks_per_sample, n);
@@ -107,7 +144,7 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const T* __restrict_
 constexpr int kRun = 4;
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                          const float* __restrict__ mr, double* __restrict__ sums,
                                                          long long voxels, int c, float slope) {
     constexpr bool kExact = sizeof(T) == 4;
@@ -116,15 +153,17 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
     const int lanes = c / VEC;                                // threads per voxel
     const int tpb = (256 / lanes) * lanes;                    // active threads
     const int vpb = tpb / lanes;                              // voxels per block-iteration
-    if ((int)threadIdx.x < tpb) {
-        const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
-        const int c0 = cl * VEC;
+    const bool active = (int)threadIdx.x < tpb;
+    const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
+    const int c0 = cl * VEC;
+    double sg[VEC], sgx[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { sg[j] = 0.0; sgx[j] = 0.0; }
+    if (active) {
         float mean[VEC], rstd[VEC];
-        double sg[VEC], sgx[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             mean[j] = mr[((size_t)n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)n * c + c0 + j) * 2 + 1];
-            sg[j] = 0.0; sgx[j] = 0.0;
         }
         const T* dn = dout + (size_t)n * voxels * c + c0;
         const T* yn = y + (size_t)n * voxels * c + c0;
@@ -169,16 +208,8 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* __restrict__ d
                 for (int j = 0; j < VEC; ++j) { sg[j] += (double)pg[j]; sgx[j] += (double)pgx[j]; }
             }
         }
-        double* r = ssum + (size_t)vl * 2 * c;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { r[2 * (c0 + j)] = sg[j]; r[2 * (c0 + j) + 1] = sgx[j]; }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * c; i += 256) {
-        double s = 0.0;
-        for (int v = 0; v < vpb; ++v) s += ssum[(size_t)v * 2 * c + i];
-        atomicAdd(&sums[(size_t)n * c * 2 + i], s);
-    }
+    block_finish<VEC>(sg, sgx, ssum, sums + (size_t)n * c * 2, lanes, vpb, c, c0, vl, active);
 }
 
 // dy = rstd * (g - mean(g) - xhat * mean(g*xhat)).  The three-term difference cancels heavily when the incoming

@@ -224,7 +224,7 @@ def _conv_fwd_launch(lib, d, x0, x1, get_wk, tc_call, bias, y, stats):
         done = _run("conv3d_fwd_tc", key, nb, fl, tc_call, allow_unsupported=True)
     if not done:
         wk = get_wk()
-        _run("conv3d_fwd", key, nb, fl,
+        _run("conv1_fwd" if d.ksize == 1 else "conv3d_fwd", key, nb, fl,
              lambda: lib.pb_conv3d_fwd(ctypes.byref(d), _p(x0), _p(x1), _p(wk), _p(bias), _p(y), _p(stats), _stream()))
 
 
@@ -272,7 +272,7 @@ def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, ne
                          lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
         if not done:
             wt = get_wt()
-            _run("conv3d_dgrad", key, nb, fl,
+            _run("conv1_dgrad" if d.ksize == 1 else "conv3d_dgrad", key, nb, fl,
                  lambda: lib.pb_conv3d_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
     if need_dw:
         dw = _scratch.zeros((groups, d.ksize ** 3, cin, d.cout), torch.float32, dy.device)
@@ -284,7 +284,7 @@ def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, ne
                         lambda: lib.pb_conv3d_wgrad_tc(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _p(err), _stream()),
                         allow_unsupported=True)
         if not done:
-            _run("conv3d_wgrad", key, nb, fl,
+            _run("conv1_wgrad" if d.ksize == 1 else "conv3d_wgrad", key, nb, fl,
                  lambda: lib.pb_conv3d_wgrad(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _stream()))
     return dx0, dx1, dw
 
