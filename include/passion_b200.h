@@ -109,6 +109,18 @@ int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, vo
                       void* yext, int* err_flag, pb_stream_t stream);
 int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int d, int h, int w, int co0, int co1, pb_stream_t stream);
 
+/* ---- 3x3x3 stride-1 convs with very few channels (csrc/conv3d_small.cu): shared-memory tiled FFMA kernels for the
+ * classes pb_conv3d_small_supported(cin, cout) reports (1->8: first encoder conv, rfnet.py:24 / mmformer.py:28;
+ * 2->2 and 4->4: PRM embedding layers, blocks.py:399-401).  Single source (c1 = 0), fp32 or bf16 storage.
+ *   fwd   : w = [G][27][cin][cout] f32, optional bias [G][cout], optional stats as pb_conv3d_fwd
+ *   dgrad : wt = [G][27][cout][cin] f32; reflect padding needs `ext`, a scratch of n*(di+2)*(hi+2)*(wi+2)*cin elements
+ *   wgrad : dw [G][27][cin][cout] f32, accumulated with atomics (zero-filled by the caller) */
+int pb_conv3d_small_supported(int cin, int cout);
+int pb_conv3d_small_fwd(const pb_conv_desc* d, const void* x, const float* w, const float* bias, void* y, double* stats,
+                        pb_stream_t stream);
+int pb_conv3d_small_dgrad(const pb_conv_desc* d, const void* dy, const float* wt, void* dx, void* ext, pb_stream_t stream);
+int pb_conv3d_small_wgrad(const pb_conv_desc* d, const void* x, const void* dy, float* dw, pb_stream_t stream);
+
 /* ---- weight layout conversion ------------------------------------------------------------
  * The parameters stay in nn.Conv3d's layout [cout][cin][k][k][k] fp32 (models/blocks.py:357, state_dict compatible);
  * pb_weight_prep gathers, for up to 4 weight groups (the four modality encoders, rfnet.py:234-237), every layout the

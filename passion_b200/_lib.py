@@ -76,6 +76,10 @@ def load():
         "pb_conv3d_tcs": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv3d_dgrad_reflect_fix": [cd, vp, vp, vp, vp, vp],
+        "pb_conv3d_small_supported": [i32, i32],
+        "pb_conv3d_small_fwd": [cd, vp, vp, vp, vp, vp, vp],
+        "pb_conv3d_small_dgrad": [cd, vp, vp, vp, vp, vp],
+        "pb_conv3d_small_wgrad": [cd, vp, vp, vp, vp],
         "pb_weight_prep": [ctypes.POINTER(WeightPrepDesc), vp],
         "pb_weight_grad_unpack": [ctypes.POINTER(WeightUnpackDesc), vp],
         "pb_channel_stats": [i32, vp, vp, i32, i64, i32, vp],

@@ -144,10 +144,11 @@ __global__ void __launch_bounds__(256, 2) channel_stats_kernel(const T* __restri
 constexpr int kRun = 4;
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                          const float* __restrict__ mr, double* __restrict__ sums,
                                                          long long voxels, int c, float slope) {
     constexpr bool kExact = sizeof(T) == 4;
+    constexpr int RUN = (sizeof(T) == 2 && VEC == 8) ? 2 : kRun;   // keeps the bf16 x8 variant at 3 CTAs per SM without spills
     extern __shared__ double ssum[];                          // [vpb][2*c]
     const int n = blockIdx.y;
     const int lanes = c / VEC;                                // threads per voxel
@@ -168,10 +169,13 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const T* __restrict_
         const T* dn = dout + (size_t)n * voxels * c + c0;
         const T* yn = y + (size_t)n * voxels * c + c0;
         const long long stride = (long long)gridDim.x * vpb;
-        for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * kRun) {
-            float g[kRun][VEC], yv[kRun][VEC];
+        float fg[VEC], fgx[VEC];                               // bf16 mode: a thread sums a few dozen voxels, fp32 is ample
 #pragma unroll
-            for (int u = 0; u < kRun; ++u) {                  // all loads of the run are in flight together
+        for (int j = 0; j < VEC; ++j) { fg[j] = 0.f; fgx[j] = 0.f; }
+        for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * RUN) {
+            float g[RUN][VEC], yv[RUN][VEC];
+#pragma unroll
+            for (int u = 0; u < RUN; ++u) {                  // all loads of the run are in flight together
                 const long long v = v0 + u * stride;
                 if (v < voxels) {
                     VecIO<T, VEC>::load(dn + v * c, g[u]);
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const T* __restrict_
             }
             if (kExact) {
 #pragma unroll
-                for (int u = 0; u < kRun; ++u)
+                for (int u = 0; u < RUN; ++u)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
                         const float xh = (yv[u][j] - mean[j]) * rstd[j];
@@ -192,21 +196,20 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const T* __restrict_
                         sgx[j] += (double)gg * (((double)yv[u][j] - (double)mean[j]) * (double)rstd[j]);
                     }
             } else {
-                float pg[VEC], pgx[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) { pg[j] = 0.f; pgx[j] = 0.f; }
-#pragma unroll
-                for (int u = 0; u < kRun; ++u)
+                for (int u = 0; u < RUN; ++u)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
                         const float xh = (yv[u][j] - mean[j]) * rstd[j];
                         const float gg = xh > 0.f ? g[u][j] : g[u][j] * slope;
-                        pg[j] += gg;
-                        pgx[j] = fmaf(gg, xh, pgx[j]);
+                        fg[j] += gg;
+                        fgx[j] = fmaf(gg, xh, fgx[j]);
                     }
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) { sg[j] += (double)pg[j]; sgx[j] += (double)pgx[j]; }
             }
+        }
+        if (!kExact) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { sg[j] += (double)fg[j]; sgx[j] += (double)fgx[j]; }
         }
     }
     block_finish<VEC>(sg, sgx, ssum, sums + (size_t)n * c * 2, lanes, vpb, c, c0, vl, active);

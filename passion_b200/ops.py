@@ -215,6 +215,14 @@ def _tc_conv_call(lib, d, x0, x1, w, y0, y1, co0, co1, stats, err, bias=None):
     return lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
 
 
+SMALL_ENABLED = os.environ.get("PB_SMALL", "1") != "0"       # shared-memory tiled kernels for the C <= 8 3x3x3 classes
+
+
+def _small_ok(d):
+    return (SMALL_ENABLED and d.ksize == 3 and d.stride == 1 and d.c1 == 0
+            and bool(_lib.load().pb_conv3d_small_supported(d.c0, d.cout)))
+
+
 def _conv_fwd_launch(lib, d, x0, x1, get_wk, tc_call, bias, y, stats):
     """Forward launch: the tcgen05 implicit GEMM when `tc_call` is given (and supports the shape), else the FFMA kernel
     with the fp32 kernel-layout weights returned by get_wk()."""
@@ -222,6 +230,11 @@ def _conv_fwd_launch(lib, d, x0, x1, get_wk, tc_call, bias, y, stats):
     done = False
     if tc_call is not None:
         done = _run("conv3d_fwd_tc", key, nb, fl, tc_call, allow_unsupported=True)
+    if not done and _small_ok(d):
+        wk = get_wk()
+        done = _run("conv3d_small_fwd", key, nb, fl,
+                    lambda: lib.pb_conv3d_small_fwd(ctypes.byref(d), _p(x0), _p(wk), _p(bias), _p(y), _p(stats), _stream()),
+                    allow_unsupported=True)
     if not done:
         wk = get_wk()
         _run("conv1_fwd" if d.ksize == 1 else "conv3d_fwd", key, nb, fl,
@@ -270,6 +283,13 @@ def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, ne
                     wt = get_wt()
                     _run("conv3d_dgrad_fix", key, 0, 0,
                          lambda: lib.pb_conv3d_dgrad_reflect_fix(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(dx1), _stream()))
+        if not done and _small_ok(d) and (pad_mode != "reflect" or min(d.di, d.hi, d.wi) >= 4):
+            wt = get_wt()
+            ext = (torch.empty((d.n, d.di + 2, d.hi + 2, d.wi + 2, cin), dtype=dy.dtype, device=dy.device)
+                   if pad_mode == "reflect" else None)
+            done = _run("conv3d_small_dgrad", key, nb, fl,
+                        lambda: lib.pb_conv3d_small_dgrad(ctypes.byref(d), _p(dy), _p(wt), _p(dx0), _p(ext), _stream()),
+                        allow_unsupported=True)
         if not done:
             wt = get_wt()
             _run("conv1_dgrad" if d.ksize == 1 else "conv3d_dgrad", key, nb, fl,
@@ -282,6 +302,10 @@ def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, ne
             err = _tc_err_flag(dy.device)
             done = _run("conv3d_wgrad_tc", key, nb, fl,
                         lambda: lib.pb_conv3d_wgrad_tc(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _p(err), _stream()),
+                        allow_unsupported=True)
+        if not done and _small_ok(d):
+            done = _run("conv3d_small_wgrad", key, nb, fl,
+                        lambda: lib.pb_conv3d_small_wgrad(ctypes.byref(d), _p(x0), _p(dy), _p(dw), _stream()),
                         allow_unsupported=True)
         if not done:
             _run("conv1_wgrad" if d.ksize == 1 else "conv3d_wgrad", key, nb, fl,

@@ -64,6 +64,12 @@ CONV_CASES = [
     (8, 0, 8, 3, 1, "reflect", 1, 1, (3, 5, 128), True),
     (16, 0, 16, 3, 1, "zeros", 1, 1, (3, 4, 128), True),
     (64, 0, 32, 3, 1, "reflect", 1, 1, (4, 5, 32), True),
+    # very few channels: shared-memory tiled kernels (several tiles in d and in the plane, ragged edges, zero padding)
+    (2, 0, 2, 3, 1, "reflect", 1, 2, (20, 18, 22), False),
+    (2, 0, 2, 3, 1, "zeros", 1, 2, (6, 7, 8), True),
+    (4, 0, 4, 3, 1, "reflect", 1, 1, (10, 33, 9), True),
+    (4, 0, 4, 3, 1, "zeros", 1, 2, (9, 5, 6), False),
+    (1, 0, 8, 3, 1, "reflect", 4, 4, (17, 20, 24), True),
 ]
 
 
