@@ -206,9 +206,11 @@ def run_ours(args):
     sync()
     e2.record()
     last = 0.0
-    for i in range(args.steps):
-        xb, tb, mb = (t.to(dev, non_blocking=True) for t in host[i % nb])
-        loss, _ = trainer.step(xb, tb, mb)
+    from passion_b200.engine import DevicePrefetcher
+    feed = DevicePrefetcher((host[i % nb] for i in range(args.steps)), dev)     # H2D of batch i+1 overlaps step i
+    for batch in feed:
+        loss, _ = trainer.step(*batch)
+        feed.release(batch)
         last = float(loss.item())                       # D2H read of the step's result
     e3.record()
     sync()

@@ -1200,15 +1200,33 @@ __device__ __forceinline__ int fold_sources(int i, int size, int* src) {
 __global__ void reflect_fold_kernel(const bf16* __restrict__ ext, bf16* __restrict__ y0, bf16* __restrict__ y1, int N, int D, int H,
                                     int W, int CO0, int CO1) {
     const int C = CO0 + CO1, C8 = C >> 3;
-    const long long total = (long long)N * D * H * W * C8;
+    // Threads enumerate exactly the voxels one step inside a face (sizes >= 4): (A) d in {1, D-2}; (B) d elsewhere,
+    // h in {1, H-2}; (C) d, h elsewhere, w in {1, W-2}.
+    const long long nA = 2LL * H * W, nB = (long long)(D - 2) * 2 * W, nC = (long long)(D - 2) * (H - 2) * 2;
+    const long long per_n = nA + nB + nC;
+    const long long total = (long long)N * per_n * C8;
+    auto inner = [](int j, int S) { return j == 0 ? 0 : (j == S - 3 ? S - 1 : j + 1); };      // j-th index not in {1, S-2}
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int c8 = (int)(t % C8);
         long long v = t / C8;
-        const int w = (int)(v % W); v /= W;
-        const int h = (int)(v % H); v /= H;
-        const int d = (int)(v % D);
-        const int n = (int)(v / D);
-        if (!(d == 1 || d == D - 2 || h == 1 || h == H - 2 || w == 1 || w == W - 2)) continue;
+        const int n = (int)(v / per_n);
+        const long long iv = v - (long long)n * per_n;
+        int d, h, w;
+        if (iv < nA) {
+            d = iv < (long long)H * W ? 1 : D - 2;
+            const int r = (int)(iv % ((long long)H * W));
+            h = r / W; w = r % W;
+        } else if (iv < nA + nB) {
+            const long long r = iv - nA;
+            d = inner((int)(r / (2 * W)), D);
+            const int r2 = (int)(r % (2 * W));
+            h = r2 < W ? 1 : H - 2; w = r2 % W;
+        } else {
+            const long long r = iv - nA - nB;
+            d = inner((int)(r / (2 * (H - 2))), D);
+            const int r2 = (int)(r % (2 * (H - 2)));
+            h = inner(r2 >> 1, H); w = (r2 & 1) ? W - 2 : 1;
+        }
         int sd[3], sh[3], sw[3];
         const int nd = fold_sources(d, D, sd), nh = fold_sources(h, H, sh), nw = fold_sources(w, W, sw);
         float acc[8];
@@ -1235,7 +1253,8 @@ extern "C" int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int 
                                pb_stream_t stream) {
     PB_CHECK_ARG(yext && y0 && (co1 == 0 || y1), "null pointer");
     PB_CHECK_ARG(co0 % 8 == 0 && co1 % 8 == 0 && co0 > 0 && d >= 4 && h >= 4 && w >= 4, "bad shape");
-    const long long total = (long long)n * d * h * w * ((co0 + co1) / 8);
+    const long long shell = 2LL * h * w + (long long)(d - 2) * 2 * w + (long long)(d - 2) * (h - 2) * 2;
+    const long long total = (long long)n * shell * ((co0 + co1) / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     reflect_fold_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)yext, (bf16*)y0, (bf16*)y1, n, d, h, w, co0, co1);

@@ -32,8 +32,10 @@ class Trainer:
         # The whole step (forward, loss mix, backward incl. the NCCL bucket all-reduces, AdamW) is sync-free and
         # shape-static, so it is replayed as ONE CUDA graph; the optimizer keeps its step counter on the device.
         self.use_graph = bool(use_graph)
+        # fused=True: one multi-tensor kernel per parameter group instead of ~a dozen foreach passes (same update rule)
         self.optimizer = torch.optim.AdamW([{"params": model.parameters(), "lr": lr, "weight_decay": weight_decay}],
-                                           betas=(0.9, 0.999), eps=1e-08, amsgrad=True, capturable=self.use_graph)
+                                           betas=(0.9, 0.999), eps=1e-08, amsgrad=True, capturable=self.use_graph,
+                                           fused=dev.type == "cuda")
         self._graph = None
         self._captured_warmup = None
         if self.use_graph:                       # the LR lives in a device tensor so that a replayed graph sees updates
@@ -94,3 +96,59 @@ class Trainer:
             dst.copy_(src, non_blocking=True)
         self._graph.replay()
         return self._out
+
+
+class DevicePrefetcher:
+    """Iterates over (x, target, mask) batches that live in pinned host memory and yields them on the device, copying
+    batch i+1 on a side stream while step i computes (what the reference gets from its DataLoader workers + `.cuda()`,
+    train.py:200-203, minus the serialisation).  Two device buffers per tensor are reused in turn; a batch handed out is
+    valid until the next-but-one `next()`."""
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [None, None]
+        self.k = 0
+        self.pending = None
+        self._issue()
+
+    def _issue(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.pending = None
+            return
+        slot = self.k % 2
+        with torch.cuda.stream(self.stream):
+            if self.consumed[slot] is not None:
+                self.stream.wait_event(self.consumed[slot])          # the step that read this slot has finished
+            if self.slots[slot] is None or any(a.shape != b.shape or a.dtype != b.dtype for a, b in zip(self.slots[slot], host)):
+                self.slots[slot] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
+            for dst, src in zip(self.slots[slot], host):
+                dst.copy_(src, non_blocking=True)
+            self.ready[slot].record(self.stream)
+        self.pending = slot
+        self.k += 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.pending is None:
+            raise StopIteration
+        slot = self.pending
+        torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
+        batch = self.slots[slot]
+        self._issue()                                               # start copying the following batch right away
+        return batch
+
+    def release(self, batch):
+        """Call after the step that consumed `batch` has been enqueued: its buffers may then be overwritten."""
+        for slot in (0, 1):
+            if self.slots[slot] is batch:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self.consumed[slot] = ev

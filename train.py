@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from options import args_parser
-from passion_b200.engine import Trainer
+from passion_b200.engine import DevicePrefetcher, Trainer
 from passion_b200.models import build_model
 from passion_b200.train_step import poly_lr, preference_update
 
@@ -117,9 +117,11 @@ def main():
         trainer.warmup = epoch < args.region_fusion_start_epoch
         acc = torch.zeros(4, device=dev)
         t0 = time.time()
-        for i in range(iter_per_epoch):
-            x, target, mask = (t.to(dev, non_blocking=True) for t in src.batch(epoch * iter_per_epoch + i))
-            loss, parts = trainer.step(x, target, mask)
+        feed = DevicePrefetcher((tuple(t.pin_memory() for t in src.batch(epoch * iter_per_epoch + i))
+                                 for i in range(iter_per_epoch)), dev)            # H2D of batch i+1 overlaps step i
+        for i, batch in enumerate(feed):
+            loss, parts = trainer.step(*batch)
+            feed.release(batch)
             dist_m = parts['dist_m'].clone()
             if world > 1:
                 dist.all_reduce(dist_m)
