@@ -201,13 +201,15 @@ def run_ours(args):
     ms_total = float(ms)
 
     # ---- timed region 2: end to end through the public API from pinned host buffers
+    from passion_b200.engine import DevicePrefetcher
     h2d = sum(t.numel() * t.element_size() for t in host[0])
+    for batch in DevicePrefetcher((host[i % nb] for i in range(2)), dev, like=host[0]):      # untimed: one-time setup of the path
+        trainer.step(*batch)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    feed = DevicePrefetcher((host[i % nb] for i in range(args.steps)), dev, like=host[0])   # H2D of batch i+1 overlaps step i
     sync()
     e2.record()
     last = 0.0
-    from passion_b200.engine import DevicePrefetcher
-    feed = DevicePrefetcher((host[i % nb] for i in range(args.steps)), dev)     # H2D of batch i+1 overlaps step i
     for batch in feed:
         loss, _ = trainer.step(*batch)
         feed.release(batch)

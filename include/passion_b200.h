@@ -94,6 +94,10 @@ int pb_conv3d_tcs(const pb_conv_desc* d, const void* x0, const void* x1, const v
  * layout of pb_conv3d_wgrad and must be zero-filled; cout in {8,16,32,64}. */
 int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw,
                        int* err_flag, pb_stream_t stream);
+/* 1x1x1 weight gradient on the tensor cores: dw [groups][cin][cout] += sum_v x[v][ci] dy[v][co] (bf16, c0, c1, cout
+ * multiples of 8, cin <= 256, cout <= 64; PB_EUNSUPPORTED otherwise).  Same autograd node as pb_conv3d_wgrad. */
+int pb_conv1_wgrad_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw,
+                      int* err_flag, pb_stream_t stream);
 /* dx0/dx1 += the contributions that reach an input voxel through the reflect padding (voxels one step inside a
  * face); completes a zero-padding data gradient into the exact adjoint of the reflect-padded forward conv. */
 int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy, const float* wt, void* dx0, void* dx1,

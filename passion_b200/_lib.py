@@ -75,6 +75,7 @@ def load():
         "pb_reflect_fold": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "pb_conv3d_tcs": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
+        "pb_conv1_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv3d_dgrad_reflect_fix": [cd, vp, vp, vp, vp, vp],
         "pb_conv3d_small_supported": [i32, i32],
         "pb_conv3d_small_fwd": [cd, vp, vp, vp, vp, vp, vp],

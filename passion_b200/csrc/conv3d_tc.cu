@@ -1140,6 +1140,155 @@ int launch_wgrad_tc8(WgP p, const void* x0, const void* x1, const void* dy, floa
     return 0;
 }
 
+// ---- 1x1x1 weight gradient on tcgen05 ----------------------------------------------------------------------------
+// dw[ci][co] = sum_v x[v][ci] * dy[v][co]: a skinny GEMM whose K is the voxel count, HBM-bound (the FFMA kernels for it are
+// FP32-pipe bound at 3.2 FMA per byte).  A = dy tile (MN-major: M = co, 8-channel chunk planes), B = x tile (MN-major:
+// N = ci, chunk planes), 128 voxels per tile = 8 K-steps; the [64 x Cin] fp32 accumulator stays in TMEM for the CTA's
+// whole stream of tiles.  Tiles are plain contiguous row ranges of the two tensors (no halo), staged by cp.async into a
+// ring of slots; one atomic flush per CTA.
+constexpr int kW1Plane = (kTileM + 1) * 16;               // chunk-plane pitch (129 rows: spreads the MN-groups over the banks)
+constexpr int kW1Producers = kThreads - 32;               // all warps except the MMA issuer stage tiles
+
+struct W1P {
+    int C0, C1, Cout;
+    long long VT;                                         // voxels per weight group (samples of a group are contiguous)
+    int slots, tiles;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) conv1_wgrad_tc_kernel(W1P p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                                     const bf16* __restrict__ dy, float* __restrict__ dw, int* err) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int cin = p.C0 + p.C1;
+    const int nci = cin >> 3, nco = p.Cout >> 3, nch = nci + nco;
+    const int slot_bytes = nch * kW1Plane;                // [co chunk planes][ci chunk planes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.slots * slot_bytes + 8 * kW1Plane);   // tail pad: don't-care M-groups
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.slots;
+    uint64_t* done = empty + p.slots;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    // copy table, one packed word per 16-byte piece of a tile: [0,16) source element offset from the tile's first row in its
+    // tensor, [16,29) destination offset / 16 inside the slot, [29,31) source tensor (0 dy, 1 x0, 2 x1).  Built once; the
+    // producers then issue a copy with a handful of instructions (a per-copy division / 64-bit address chain made the three
+    // producer warps of this 1-CTA-per-SM kernel latency-bound at ~1 TB/s).
+    uint32_t* table = tmem_slot + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.y;
+    {
+        const int c0ch = p.C0 >> 3;
+        for (int idx = threadIdx.x; idx < kTileM * nch; idx += kThreads) {
+            const int r = idx / nch, ch = idx - r * nch;
+            uint32_t src, dst, sel;
+            if (ch < nco) { sel = 0; src = r * p.Cout + ch * 8; dst = (ch * kW1Plane) / 16 + r; }
+            else {
+                const int ci = ch - nco;
+                if (ci < c0ch) { sel = 1; src = r * p.C0 + ci * 8; } else { sel = 2; src = r * p.C1 + (ci - c0ch) * 8; }
+                dst = ((nco + ci) * kW1Plane) / 16 + r;
+            }
+            table[idx] = src | (dst << 16) | (sel << 29);
+        }
+    }
+    // NACC independent accumulators (K-step ks of every tile goes to accumulator ks % NACC): a chain of dependent
+    // tcgen05.mma on ONE accumulator runs at the MMA latency (~0.2 us each, 1.6 us per tile measured), not at its throughput
+    const int acc_stride = ((cin + 15) / 16) * 16;
+    const int nacc = 2;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < nacc * acc_stride) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.slots; ++i) { mbar_init(&full[i], kW1Producers); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const bf16* xg0 = x0 + (size_t)g * p.VT * p.C0;
+    const bf16* xg1 = p.C1 ? x1 + (size_t)g * p.VT * p.C1 : nullptr;
+    const bf16* dyg = dy + (size_t)g * p.VT * p.Cout;
+
+    if (warp != 4) {
+        // =============================== producers: every warp but the MMA issuer ===============================
+        const int pt = warp < 4 ? threadIdx.x : threadIdx.x - 32;
+        const int copies = kTileM * nch;
+        uint32_t k = 0;
+        for (int it = blockIdx.x; it < p.tiles; it += gridDim.x, ++k) {
+            const int slot = k % p.slots;
+            mbar_wait(&empty[slot], ((k / p.slots) & 1) ^ 1, err, 41);
+            const long long v0 = (long long)it * kTileM;
+            const uint32_t sbase = smem_u32(smem + (size_t)slot * slot_bytes);
+            const bf16* base[3] = {dyg + v0 * p.Cout, xg0 + v0 * p.C0, p.C1 ? xg1 + v0 * p.C1 : xg0};
+            const int rows_ok = (int)min((long long)kTileM, p.VT - v0);       // < 128 only in the last tile
+            // consecutive threads take consecutive 16-byte pieces of a row: first the dy row, then the x row(s)
+            for (int idx = pt; idx < copies; idx += kW1Producers) {
+                const uint32_t e = table[idx];
+                const uint32_t dst16 = (e >> 16) & 0x1FFFu;
+                const bool ok = rows_ok == kTileM || (int)(idx / nch) < rows_ok;
+                cp_async16(sbase + dst16 * 16, ok ? base[e >> 29] + (e & 0xFFFFu) : dy, ok ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(&full[slot]);
+        }
+        cp_async_wait_all();
+    }
+    if (warp == 4) {
+        // =============================== MMA issuer: 8 K-steps per tile ===============================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_mn(kWgM, cin);
+            uint32_t k = 0;
+            bool first = true;
+            for (int it = blockIdx.x; it < p.tiles; it += gridDim.x, ++k) {
+                const int slot = k % p.slots;
+                mbar_wait(&full[slot], (k / p.slots) & 1, err, 42);
+                fence_proxy_async();
+                tc_fence_after();
+                const uint32_t sbase = smem_u32(smem + (size_t)slot * slot_bytes);
+                const uint64_t a0 = umma_desc(sbase, 128, kW1Plane);                      // M-groups = co chunk planes
+                const uint64_t b0 = umma_desc(sbase + nco * kW1Plane, 128, kW1Plane);     // N-groups = ci chunk planes
+#pragma unroll
+                for (int ks = 0; ks < kTileM / 16; ++ks)
+                    umma_f16(tmem_base + (uint32_t)((ks % nacc) * acc_stride), a0 + (uint64_t)(16 * ks), b0 + (uint64_t)(16 * ks), idesc,
+                             (first && ks < nacc) ? 0u : 1u);
+                first = false;
+                umma_commit(&empty[slot]);
+            }
+            umma_commit(done);
+        }
+        __syncwarp();
+    } else if (warp < 4) {
+        // =============================== epilogue: TMEM -> fp32 atomics into dw [g][cin][cout] ===============================
+        if ((int)blockIdx.x < p.tiles) {
+            mbar_wait(done, 0, err, 43);
+            tc_fence_after();
+            const int co = lane < 16 ? warp * 16 + lane : p.Cout;            // M = 64 layout: row m in lane (m % 16) + 32 * (m / 16)
+            for (int c0 = 0; c0 < cin; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+                for (int a = 1; a < nacc; ++a) {
+                    float u[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + a * acc_stride + c0, u);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += u[j];
+                }
+                if (co < p.Cout) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < cin) atomicAdd(dw + ((size_t)g * cin + c0 + j) * p.Cout + co, v[j]);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
 template <int NCO>
 int launch_wgrad_tc(const WgP& p, const void* x0, const void* x1, const void* dy, float* dw, int* err, cudaStream_t st) {
     const size_t smem = (size_t)kWgSlotsY * kWgYSlotBytes + (size_t)kWgSlotsX * p.slab_e * 16 + (2 * kWgSlotsX + 2 * kWgSlotsY + 1) * 8 + 16;
@@ -1345,6 +1494,41 @@ extern "C" int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const v
         default: pb_set_error("conv3d_wgrad_tc: cout %d not supported", d->cout); break;
     }
     if (rc) return rc;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_conv1_wgrad_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw, int* err_flag,
+                                 pb_stream_t stream) {
+    PB_CHECK_ARG(d && x0 && dy && dw && err_flag, "null pointer");
+    PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 1 && d->stride == 1, "bf16, 1x1x1, stride 1 only");
+    PB_CHECK_ARG(d->c0 % 8 == 0 && d->c1 % 8 == 0 && d->c0 >= 8 && (d->c1 == 0 || x1), "input channels must be multiples of 8");
+    PB_CHECK_ARG(d->cout % 8 == 0 && d->cout >= 8 && d->cout <= 64, "cout must be a multiple of 8 in [8, 64]");
+    PB_CHECK_ARG(d->groups >= 1 && d->n % d->groups == 0, "bad groups");
+    const int cin = d->c0 + d->c1;
+    if (cin > 256) { pb_set_error("conv1_wgrad_tc: cin %d > 256", cin); return PB_EUNSUPPORTED; }
+    W1P p;
+    p.C0 = d->c0; p.C1 = d->c1; p.Cout = d->cout;
+    p.VT = (long long)(d->n / d->groups) * d->dout * d->ho * d->wo;
+    const long long tiles = (p.VT + kTileM - 1) / kTileM;
+    if (tiles > 0x7fffffffLL) { pb_set_error("conv1_wgrad_tc: too many tiles"); return PB_EUNSUPPORTED; }
+    p.tiles = (int)tiles;
+    const int slot_bytes = (cin / 8 + d->cout / 8) * kW1Plane;
+    const int table_bytes = kTileM * (cin / 8 + d->cout / 8) * 4;
+    // two CTAs per SM when the accumulators (2 x cin columns each) and two rings fit, else one
+    const bool two = cin <= 128 && 2 * slot_bytes + 8 * kW1Plane + table_bytes <= 100 * 1024;
+    int slots = ((two ? 100 : 200) * 1024 - 8 * kW1Plane - table_bytes) / slot_bytes;
+    if (slots > 8) slots = 8;
+    if (slots < 2) { pb_set_error("conv1_wgrad_tc: a tile of %d B does not leave room for two slots", slot_bytes); return PB_EUNSUPPORTED; }
+    p.slots = slots;
+    const size_t smem = (size_t)slots * slot_bytes + 8 * kW1Plane + (2 * slots + 1) * 8 + 16 + table_bytes;
+    cudaError_t e = cudaFuncSetAttribute(conv1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pb_set_error("conv1_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
+    int ctas = (two ? 296 : 148) / d->groups;
+    if (ctas < 1) ctas = 1;
+    if (ctas > p.tiles) ctas = p.tiles;
+    conv1_wgrad_tc_kernel<<<dim3(ctas, d->groups), kThreads, smem, (cudaStream_t)stream>>>(p, (const bf16*)x0, (const bf16*)x1,
+                                                                                         (const bf16*)dy, dw, err_flag);
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

@@ -104,16 +104,20 @@ class DevicePrefetcher:
     train.py:200-203, minus the serialisation).  Two device buffers per tensor are reused in turn; a batch handed out is
     valid until the next-but-one `next()`."""
 
-    def __init__(self, batches, device):
+    def __init__(self, batches, device, like=None):
+        """`like`: an example host batch; the two device buffer sets are then allocated right away (one-time setup)
+        instead of on first use.  Copies start with the first `next()`."""
         self.it = iter(batches)
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
         self.slots = [None, None]
+        if like is not None:
+            self.slots = [tuple(torch.empty(t.shape, dtype=t.dtype, device=device) for t in like) for _ in range(2)]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.consumed = [None, None]
         self.k = 0
         self.pending = None
-        self._issue()
+        self.started = False
 
     def _issue(self):
         try:
@@ -137,6 +141,9 @@ class DevicePrefetcher:
         return self
 
     def __next__(self):
+        if not self.started:
+            self.started = True
+            self._issue()
         if self.pending is None:
             raise StopIteration
         slot = self.pending

@@ -141,6 +141,7 @@ def _conv_desc(x0, x1, cout, ksize, stride, pad_mode, groups):
 # ---- tcgen05 implicit-GEMM path (csrc/conv3d_tc.cu) ------------------------------------------------------
 TC_ENABLED = os.environ.get("PB_TC", "1") != "0"
 WGRAD_TC = os.environ.get("PB_WGRAD_TC", "1") != "0"
+WGRAD1_TC = os.environ.get("PB_WGRAD1_TC", "1") != "0"        # 1x1x1 weight gradient on tcgen05
 DGRAD_FOLD = os.environ.get("PB_DGRAD_FOLD", "1") != "0"      # reflect-pad data gradient: extended-domain tc pass + fold
 UPSAMPLE_SEPARABLE_FROM = int(os.environ.get("PB_UPS_SEP", "2"))     # trilinear adjoint: three 1-D passes from this scale on
 TC_STACKED = os.environ.get("PB_TCS", "0") != "0"        # kw-stacked variant of the fwd / dgrad implicit GEMM (measured: not faster)
@@ -302,6 +303,12 @@ def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, ne
             err = _tc_err_flag(dy.device)
             done = _run("conv3d_wgrad_tc", key, nb, fl,
                         lambda: lib.pb_conv3d_wgrad_tc(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _p(err), _stream()),
+                        allow_unsupported=True)
+        if (not done and TC_ENABLED and WGRAD1_TC and dy.dtype == torch.bfloat16 and d.ksize == 1 and d.stride == 1
+                and d.c0 % 8 == 0 and d.c1 % 8 == 0 and d.cout % 8 == 0 and d.cout <= 64 and cin <= 256):
+            err = _tc_err_flag(dy.device)
+            done = _run("conv1_wgrad_tc", key, nb, fl,
+                        lambda: lib.pb_conv1_wgrad_tc(ctypes.byref(d), _p(x0), _p(x1), _p(dy), _p(dw), _p(err), _stream()),
                         allow_unsupported=True)
         if not done and _small_ok(d):
             done = _run("conv3d_small_wgrad", key, nb, fl,
