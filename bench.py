@@ -145,6 +145,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")            # keeps NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "nccl_bench_%h_%p.log"))
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
