@@ -48,11 +48,16 @@ class general_conv3d_prenorm(nn.Module):
         self.k_size, self.stride, self.pad_type = k_size, stride, pad_type
 
     def run(self, x0, x1=None):
-        a0 = ops.prenorm(x0)
-        a1 = ops.prenorm(x1) if x1 is not None else None
-        y, _ = ops.conv3d_ref(a0, [self.conv.weight], [self.conv.bias], a1, ksize=self.k_size, stride=self.stride,
-                              pad_mode=self.pad_type)
-        return y
+        """x0 / x1: a cl tensor, or a (tensor, stats) pair when its producer already accumulated the InstanceNorm sums.
+        Returns (y, stats of y): the conv epilogue accumulates the sums the NEXT pre-norm block needs."""
+        a0 = ops.prenorm(*_pair(x0))
+        a1 = ops.prenorm(*_pair(x1)) if x1 is not None else None
+        return ops.conv3d_ref(a0, [self.conv.weight], [self.conv.bias], a1, ksize=self.k_size, stride=self.stride,
+                              pad_mode=self.pad_type, want_stats=True)
+
+
+def _pair(a):
+    return a if isinstance(a, tuple) else (a, None)
 
 
 def _plain_conv1(conv, x):
@@ -81,18 +86,20 @@ def _run_encoders(encoders, x):
     """Four Encoders as one grouped pass.  x [4B,D,H,W,1] ordered modality-major."""
 
     def gconv(name, t, stride=1, norm=True):
+        """t: tensor or (tensor, stats); returns (y, stats of y)."""
         convs = [getattr(e, name) for e in encoders]
         convs = [c.conv if norm else c for c in convs]
-        y, _ = ops.conv3d_ref(ops.prenorm(t) if norm else t, [c.weight for c in convs], [c.bias for c in convs], ksize=3,
-                              stride=stride, pad_mode="reflect")
-        return y
+        a = ops.prenorm(*_pair(t)) if norm else _pair(t)[0]
+        return ops.conv3d_ref(a, [c.weight for c in convs], [c.bias for c in convs], ksize=3, stride=stride,
+                              pad_mode="reflect", want_stats=True)
 
     feats = []
-    x = gconv("e1_c1", x, norm=False)
+    x = gconv("e1_c1", x, norm=False)                              # (tensor, stats)
     for lvl in (1, 2, 3, 4, 5):
         if lvl > 1:
             x = gconv(f"e{lvl}_c1", x, stride=2)
-        x = x + gconv(f"e{lvl}_c3", gconv(f"e{lvl}_c2", x))
+        t = x[0] + gconv(f"e{lvl}_c3", gconv(f"e{lvl}_c2", x))[0]   # residual sum: its statistics need their own pass,
+        x = (t, ops.channel_stats(t))                              # shared by every consumer of this level's features
         feats.append(x)
     return feats
 
@@ -111,10 +118,10 @@ class Decoder_sep(nn.Module):
         self.seg_layer = nn.Conv3d(b, num_cls, kernel_size=1, stride=1, padding=0, bias=True)
 
     def run(self, x1, x2, x3, x4, x5):
-        de = x5
+        de = _pair(x5)[0]
         for lvl, skip in ((4, x4), (3, x3), (2, x2), (1, x1)):
             de = getattr(self, f"d{lvl}_c1").run(ops.upsample(de))
-            de = getattr(self, f"d{lvl}_out").run(getattr(self, f"d{lvl}_c2").run(de, skip))     # cat((de, skip))
+            de = getattr(self, f"d{lvl}_out").run(getattr(self, f"d{lvl}_c2").run(de, skip))[0]  # cat((de, skip))
         return _plain_conv1(self.seg_layer, de)
 
 
@@ -130,7 +137,7 @@ class fusion_prenorm(nn.Module):
     def run(self, x):
         for m in self.fusion_layer:
             x = m.run(x)
-        return x
+        return x                                                   # (tensor, stats)
 
 
 class Decoder_fuse(nn.Module):
@@ -153,12 +160,12 @@ class Decoder_fuse(nn.Module):
     def run(self, x1, x2, x3, x4, x5):
         """x_l [N,...,4*C_l] masked encoder features (x5: the inter-modal transformer output).
         Returns logits, (pred1..4) deep-supervision logits at levels 2..5, (de_x1_f..de_x5_f), all cl."""
-        f = self.RFM5.run(x5)
+        f = self.RFM5.run(x5)[0]
         preds, feats = [_plain_conv1(self.seg_d4, f)], [f]
         for lvl, xl in ((4, x4), (3, x3), (2, x2), (1, x1)):
             de = getattr(self, f"d{lvl}_c1").run(ops.upsample(f))
             r = getattr(self, f"RFM{lvl}").run(xl)
-            f = getattr(self, f"d{lvl}_out").run(getattr(self, f"d{lvl}_c2").run(r, de))          # cat((RFM, de))
+            f = getattr(self, f"d{lvl}_out").run(getattr(self, f"d{lvl}_c2").run(r, de))[0]       # cat((RFM, de))
             feats.append(f)
             if lvl > 1:
                 preds.append(_plain_conv1(getattr(self, f"seg_d{lvl - 1}"), f))
@@ -330,11 +337,13 @@ class Model(nn.Module):
         e = fm.t().contiguous()                                               # [4(m),B]
         xin = x.to(torch.float32).permute(1, 0, 2, 3, 4) * e[:, :, None, None, None]     # mmformer.py:397-398
         xe = xin.reshape(4 * B, *x.shape[2:], 1).to(dt).contiguous()
-        enc = _run_encoders(self._encoders(), xe)                             # 5 levels of [4B,d,h,w,C], modality-major
+        enc_s = _run_encoders(self._encoders(), xe)                           # 5 levels of ([4B,d,h,w,C], sums), modality-major
+        enc = [f for f, _ in enc_s]
         escale = e.reshape(4 * B, 1, 1, 1, 1).to(dt)
-        feat = [f * escale for f in enc]                                      # masked per-modality features (:406-416)
-        p = feat[4].shape[1]
-        intra = self._intra(feat[4].view(4, B, p ** 3, -1), fm)
+        # masked per-modality features (:406-416); masks are 0/1, so their InstanceNorm sums are the masked sums
+        feat = [(f * escale, st * e.reshape(4 * B, 1, 1).double()) for f, st in enc_s]
+        p = enc[4].shape[1]
+        intra = self._intra(feat[4][0].view(4, B, p ** 3, -1), fm)
 
         train_passion = self.is_training and self.use_passion
         eye = torch.eye(4, device=dev, dtype=torch.float32)
@@ -347,7 +356,11 @@ class Model(nn.Module):
             ms = ms5 = fm[None]
         P = ms.shape[0]
         # masks are 0/1, so masking the already-masked features again (mask & pass mask) is the product of the two
-        ys = [ops.masked_stack(f, ms) for f in enc[:4]]
+        ys = []
+        for f, st in enc_s[:4]:
+            C = f.shape[-1]
+            st_p = st.view(4, B, C, 2).permute(1, 0, 2, 3)[None] * ms.double()[:, :, :, None, None]      # [P,B,4,C,2]
+            ys.append((ops.masked_stack(f, ms), st_p.reshape(P * B, 4 * C, 2).contiguous()))
         x5 = self._inter(intra, ms5, p)
         logits, preds, des = self.decoder_fuse.run(*ys, x5)
         D, H, W = logits.shape[1:4]

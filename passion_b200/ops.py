@@ -565,11 +565,12 @@ def channel_stats(x):
     return stats
 
 
-def prenorm(x):
+def prenorm(x, stats=None):
     """InstanceNorm3d(affine=False) -> LeakyReLU(0.2) of an arbitrary cl tensor (the first half of
-    general_conv3d_prenorm, reference models/blocks.py:312-314)."""
+    general_conv3d_prenorm, reference models/blocks.py:312-314).  `stats`: the float64 [N, C, 2] sums of x when the kernel
+    that produced x already accumulated them in its epilogue (conv3d_ref(..., want_stats=True)); else one extra pass."""
     voxels = x.numel() // (x.shape[0] * x.shape[-1])
-    return _InormLrelu.apply(x, inorm_finalize(channel_stats(x), voxels), None)
+    return _InormLrelu.apply(x, inorm_finalize(stats if stats is not None else channel_stats(x), voxels), None)
 
 
 class _Upsample(torch.autograd.Function):
