@@ -257,10 +257,13 @@ __global__ void __launch_bounds__(256) masked_stack_fwd_kernel(const T* __restri
     const int cl = C / VEC;
     const long long total = 4LL * B * V * cl;
     for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+        // channel chunk fastest, then the modality: the threads of a warp cover whole 4C-channel rows of the stacked tensor
+        // (full sectors on the 5x larger side of this op); the per-modality reads stay 16 B x consecutive voxels per warp
         const int c = (int)(t % cl) * VEC;
         long long r = t / cl;
-        const long long v = r % V; r /= V;
-        const int b = (int)(r % B), m = (int)(r / B);
+        const int m = (int)(r & 3); r >>= 2;
+        const long long v = r % V;
+        const int b = (int)(r / V);
         float x[VEC], y[VEC];
         VecIO<T, VEC>::load(enc + (((size_t)m * B + b) * V + v) * C + c, x);
         for (int p = 0; p < P; ++p) {
@@ -278,10 +281,13 @@ __global__ void __launch_bounds__(256) masked_stack_bwd_kernel(const T* __restri
     const int cl = C / VEC;
     const long long total = 4LL * B * V * cl;
     for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+        // channel chunk fastest, then the modality: the threads of a warp cover whole 4C-channel rows of the stacked tensor
+        // (full sectors on the 5x larger side of this op); the per-modality reads stay 16 B x consecutive voxels per warp
         const int c = (int)(t % cl) * VEC;
         long long r = t / cl;
-        const long long v = r % V; r /= V;
-        const int b = (int)(r % B), m = (int)(r / B);
+        const int m = (int)(r & 3); r >>= 2;
+        const long long v = r % V;
+        const int b = (int)(r / V);
         float acc[VEC], g[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;

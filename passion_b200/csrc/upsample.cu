@@ -14,19 +14,23 @@ __device__ __forceinline__ void src_index(int o, float ratio, int in, int& i0, i
     l1 = s - (float)i0;
 }
 
+// grid = (blocks per output plane, 1, n * output planes): the plane / sample indices and the d interpolation are uniform
+// per CTA, a thread resolves only its (oh, ow, channel chunk) — the flat version spent most of its time in five 64-bit
+// divisions per 16-byte output vector (1.1 TB/s).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) up_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int d, int h, int w, int c,
                                                      int scale, float rd, float rh, float rw, long long total_vec) {
     const int od_n = d * scale, oh_n = h * scale, ow_n = w * scale, cv = c / VEC;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i;
-        const int cl = (int)(t % cv); t /= cv;
-        const int ow = (int)(t % ow_n); t /= ow_n;
-        const int oh = (int)(t % oh_n); t /= oh_n;
-        const int od = (int)(t % od_n);
-        const int nn = (int)(t / od_n);
-        int d0, d1, h0, h1, w0, w1; float ld, lh, lw;
-        src_index(od, rd, d, d0, d1, ld); src_index(oh, rh, h, h0, h1, lh); src_index(ow, rw, w, w0, w1, lw);
+    const int nn = blockIdx.z / od_n, od = blockIdx.z - nn * od_n;
+    int d0, d1; float ld;
+    src_index(od, rd, d, d0, d1, ld);
+    const int plane_vec = oh_n * ow_n * cv;
+    for (int pi = blockIdx.x * blockDim.x + threadIdx.x; pi < plane_vec; pi += gridDim.x * blockDim.x) {
+        const int r = pi / cv, cl = pi - r * cv;
+        const int oh = r / ow_n, ow = r - oh * ow_n;
+        const long long i = (long long)blockIdx.z * plane_vec + pi;
+        int h0, h1, w0, w1; float lh, lw;
+        src_index(oh, rh, h, h0, h1, lh); src_index(ow, rw, w, w0, w1, lw);
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
@@ -150,7 +154,15 @@ int run(const void* a, void* b, int n, int d, int h, int w, int c, int scale, cu
     long long blocks = (total_vec + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     if (blocks < 1) blocks = 1;
-    if (FWD) up_fwd_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)b, n, d, h, w, c, scale, rd, rh, rw, total_vec);
+    if (FWD) {
+        const long long plane_vec = (long long)h * scale * w * scale * (c / VEC);
+        long long bx = (plane_vec + 255) / 256;
+        if (bx > 1024) bx = 1024;
+        const long long planes = (long long)n * d * scale;
+        if (planes > 65535 || plane_vec > 0x7fffffffLL) { pb_set_error("upsample_fwd: volume too large"); return PB_EUNSUPPORTED; }
+        up_fwd_kernel<T, VEC><<<dim3((unsigned)bx, 1, (unsigned)planes), 256, 0, st>>>((const T*)a, (T*)b, n, d, h, w, c, scale, rd, rh,
+                                                                                          rw, total_vec);
+    }
     else     up_bwd_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)b, n, d, h, w, c, scale, rd, rh, rw, total_vec);
     return 0;
 }
@@ -173,7 +185,7 @@ int dispatch(int dtype, const void* a, void* b, int n, int d, int h, int w, int 
 
 extern "C" int pb_upsample_fwd(int dtype, const void* x, void* y, int n, int d, int h, int w, int c, int scale, pb_stream_t stream) {
     PB_CHECK_ARG(x && y && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && scale >= 1, "bad argument");
-    dispatch<true>(dtype, x, y, n, d, h, w, c, scale, (cudaStream_t)stream);
+    if (int e = dispatch<true>(dtype, x, y, n, d, h, w, c, scale, (cudaStream_t)stream)) return e;
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

@@ -8,8 +8,9 @@ Two entry points:
   (SURVEY.md §8 f-2): each encoder only sees its own modality channel (rfnet.py:222-225, 234-237), so its output for a
   PRESENT modality is the same for every mask and is zeroed otherwise (rfnet.py:239-242).  The four encoders therefore
   run once per window (4 encoder passes instead of 60) and the fused decoder runs once on a batch of 15 masked
-  copies; overlap-add, division and argmax stay on the device.  Results are identical to 15 calls of
-  `predict_volume` (same kernels, same per-sample arithmetic).
+  copies; overlap-add, division and argmax stay on the device.  Same kernels and the same per-sample arithmetic as 15
+  calls of `predict_volume`; the only difference is the summation order of the float64 statistics atomics, i.e. the
+  probabilities agree to ~1e-5 in fp32 (tests/test_predict_gpu.py) and the label maps differ only at bf16 near-ties.
 """
 import numpy as np
 import torch
