@@ -257,8 +257,16 @@ def run_ours(args):
     top = fam[top_name]
     top_cls = max(((k, d) for k, d in summ.items() if k[0] == top_name), key=lambda kv: kv[1]["ms"])
     ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": top_name, "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(ach / hbm_peak, 4), "traffic": NCU_TRAFFIC_BYTES.get(top_name), "peak_source": how,
+    ach_tf = top["flops"] / (top["ms"] / 1e3) / 1e12
+    # the tcgen05 conv kernels are limited by the tensor pipe (ncu: pipe 65-90 % busy, dram bytes = algorithmic bytes), every
+    # other family streams: report the family against the roof that actually bounds it, and the other figure beside it
+    tensor_bound = top_name.endswith("_tc")
+    roofline = {"bound": "tensor" if tensor_bound else "hbm", "kernel": top_name,
+                "achieved": round(ach_tf, 2) if tensor_bound else round(ach, 1),
+                "peak": tc_peak if tensor_bound else hbm_peak, "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                "frac": round(ach_tf / tc_peak, 4) if tensor_bound else round(ach / hbm_peak, 4),
+                "hbm_GBps": round(ach, 1), "hbm_frac": round(ach / hbm_peak, 4),
+                "traffic": NCU_TRAFFIC_BYTES.get(top_name), "peak_source": how,
                 "launches": int(top["calls"]), "avg_launch_ms": round(top["ms"] / top["calls"], 4),
                 "share_of_step": round(top["ms"] / ms_total, 3),
                 "top_class": {"key": top_cls[0][1], "ms_per_launch": round(top_cls[1]["ms"] / top_cls[1]["calls"], 4),
