@@ -302,7 +302,7 @@ def run_ours(args):
         roofline.pop("step_hbm_frac"); roofline.pop("step_tc_frac")
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(budget_s=30.0, model=args.model, S=S)
-    print(json.dumps(out), flush=True)
+    emit(out)
     finish()
 
 
@@ -380,10 +380,34 @@ def run_reference(args):
            "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything that native libraries print on fd 1 (NCCL's version banner, for one) goes to stderr from here on; the ONE
+    JSON line is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -406,7 +430,7 @@ def main():
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_ours(args)
 
 
