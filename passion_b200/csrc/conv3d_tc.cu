@@ -942,9 +942,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_wgrad_tc8_kernel(WgP p, con
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kWg8SlotsX; ++i) { mbar_init(&fullx[i], kProducerThreads); mbar_init(&emptyx[i], 1); }
-        for (int i = 0; i < kWg8SlotsY; ++i) { mbar_init(&fully[i], kProducerThreads); mbar_init(&emptyy[i], 1); }
-        mbar_init(done, 1);
+        // three MMA issuers (one per kd, see below): every consumer-side barrier expects one arrival from each of them
+        for (int i = 0; i < kWg8SlotsX; ++i) { mbar_init(&fullx[i], kProducerThreads); mbar_init(&emptyx[i], 3); }
+        for (int i = 0; i < kWg8SlotsY; ++i) { mbar_init(&fully[i], kProducerThreads); mbar_init(&emptyy[i], 3); }
+        mbar_init(done, 3);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -1036,8 +1037,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_wgrad_tc8_kernel(WgP p, con
             }
         }
         cp_async_wait_all();
-    } else if (warp == 4) {
-        // =============================== MMA issuer: 3 (kd) x 8 (K steps) instructions per plane ===============================
+    }
+    // =============================== MMA issuers ===============================
+    // A tcgen05.mma with N <= 32 occupies the tensor pipe for ~40-45 cycles however small it is, and ONE thread cannot issue
+    // them faster than every ~45-60 cycles (scripts/microbench/umma_rate.cu: 61 -> 31 -> 23 cycles per M=64 MMA with 1 -> 2 -> 4
+    // issuing warps).  The three kd taps accumulate into different TMEM tiles, so each gets its own issuing thread: lane 0 of
+    // warp 4 (kd = 0) and of the otherwise idle epilogue warps 0 and 1 (kd = 1, 2).  Every issuer walks the input planes in
+    // order, waits for each plane (also the ones only the other issuers read: an arrival on `empty` is only legal once the
+    // plane's `full` phase has been seen) and releases it with its own tcgen05.commit.
+    const int my_kd = warp == 4 ? 0 : (warp == 0 ? 1 : (warp == 1 ? 2 : -1));
+    if (my_kd >= 0) {
         if (lane == 0) {
             const uint32_t x_addr = smem_u32(x_s), y_addr = smem_u32(y_s);
             uint32_t kx = 0, ky = 0;
@@ -1045,41 +1054,38 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_wgrad_tc8_kernel(WgP p, con
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
                 const int nout = min(p.DCH, p.D - dc * p.DCH);
-                for (int od = 0; od < nout; ++od, ++ky) {
-                    for (int kd = (od == 0 ? 0 : 2); kd < 3; ++kd) {
-                        const uint32_t kk = kx + od + kd;
-                        mbar_wait(&fullx[kk % kWg8SlotsX], (kk / kWg8SlotsX) & 1, err, 33);
-                    }
-                    mbar_wait(&fully[ky % kWg8SlotsY], (ky / kWg8SlotsY) & 1, err, 34);
-                    fence_proxy_async();
-                    tc_fence_after();
-                    // A: M-group g' (= 2 - kh) starts g' padded rows further into the dy slab
+                for (int pl = 0; pl < nout + 2; ++pl) {
+                    const uint32_t kk = kx + pl;
+                    mbar_wait(&fullx[kk % kWg8SlotsX], (kk / kWg8SlotsX) & 1, err, 33);
+                    const int od = pl - my_kd;                           // the output plane this issuer pairs with x plane pl
+                    if (od >= 0 && od < nout) {
+                        const uint32_t ko = ky + od;
+                        mbar_wait(&fully[ko % kWg8SlotsY], (ko / kWg8SlotsY) & 1, err, 34);
+                        fence_proxy_async();
+                        tc_fence_after();
+                        const uint64_t b0 = umma_desc(x_addr + (kk % kWg8SlotsX) * xslot_bytes, 128, 16);
 #pragma unroll
-                    for (int cc = 0; cc < NCO; ++cc) {
-                        const uint64_t a0 = umma_desc(y_addr + (ky % kWg8SlotsY) * yslot_bytes + cc * yplane_bytes, 128, (uint32_t)p.PW * 16);
-#pragma unroll
-                        for (int kd = 0; kd < 3; ++kd) {
-                            const uint64_t b0 = umma_desc(x_addr + ((kx + od + kd) % kWg8SlotsX) * xslot_bytes, 128, 16);
-                            const uint32_t d_tmem = tmem_base + (cc * 3 + kd) * 32;
+                        for (int cc = 0; cc < NCO; ++cc) {
+                            // A: M-group g' (= 2 - kh) starts g' padded rows further into the dy slab
+                            const uint64_t a0 = umma_desc(y_addr + (ko % kWg8SlotsY) * yslot_bytes + cc * yplane_bytes, 128, (uint32_t)p.PW * 16);
+                            const uint32_t d_tmem = tmem_base + (cc * 3 + my_kd) * 32;
 #pragma unroll
                             for (int ks = 0; ks < kTileM / 16; ++ks)
                                 umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b0 + (uint64_t)(16 * ks), IDESC, (first && ks == 0) ? 0u : 1u);
                         }
+                        first = false;
+                        umma_commit(&emptyy[ko % kWg8SlotsY]);
                     }
-                    first = false;
-                    umma_commit(&emptyy[ky % kWg8SlotsY]);
-                    umma_commit(&emptyx[(kx + od) % kWg8SlotsX]);
-                    if (od == nout - 1) {
-                        umma_commit(&emptyx[(kx + od + 1) % kWg8SlotsX]);
-                        umma_commit(&emptyx[(kx + od + 2) % kWg8SlotsX]);
-                    }
+                    umma_commit(&emptyx[kk % kWg8SlotsX]);
                 }
                 kx += nout + 2;
+                ky += nout;
             }
             umma_commit(done);
         }
         __syncwarp();
-    } else {
+    }
+    if (warp < 4) {
         // =============================== epilogue ===============================
         if (blockIdx.x < items) {
             mbar_wait(done, 0, err, 35);
