@@ -23,6 +23,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kProducerThreads = 96;
+constexpr int kTcThreads = 288;         // conv3_tc_kernel: 4 epilogue warps, 2 MMA-issuer warps, 3 producer warps
 constexpr int kSlots = 6;               // input-plane ring: 3 planes in use by the MMAs + 3 planes of prefetch
 constexpr int kMaxCopies = 16;          // 16-B copies per producer thread and plane ...
 constexpr int kMaxCopiesWide = 20;      // ... and for the 64-channel variants (NCHR = 8, which have registers to spare)
@@ -124,15 +125,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// taps [T0, T1) of one output plane, fully unrolled: every descriptor is one 64-bit add away from a register
+template <int T0, int T1, int KS, int NCH, int NT>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, const uint64_t (&sdesc)[3], uint64_t b0, const uint32_t (&toff)[9],
+                                           int ks_stride, uint32_t idesc) {
+#pragma unroll
+    for (int tap = T0; tap < T1; ++tap) {
+        const uint64_t a1 = sdesc[tap / 9] + (uint64_t)toff[tap % 9];                   // address field is in 16 B units
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            umma_f16(d_tmem, a1 + (uint64_t)(uint32_t)(ks * ks_stride), b0 + (uint64_t)(uint32_t)((tap * NCH + 2 * ks) * NT), idesc,
+                     (tap == T0 && ks == 0) ? 0u : 1u);
+    }
+}
+
 // NCHR = real input chunks of 8 channels (1,2,4,8); NT = Cout tile (16 or 32)
 template <int NCHR, int NT>
-__global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+__global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                                const bf16* __restrict__ wimg, const float* __restrict__ bias,
                                                                bf16* __restrict__ y0, bf16* __restrict__ y1, bf16* __restrict__ yext,
                                                                double* __restrict__ stats, int* err) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;             // a K=16 MMA step needs two 8-channel chunks (zero chunk if Cin = 8)
     constexpr int KS = NCH / 2;
-    constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
+    constexpr int TMEM_COLS = 4 * NT < 32 ? 32 : 4 * NT;  // 2 stages x 2 partial accumulators (one per issuer)
     constexpr uint32_t IDESC = umma_idesc(kTileM, NT);
     // input extent (= output extent unless p.inset)
     const int Di = p.D - 2 * p.inset, Hi = p.H - 2 * p.inset, Wi = p.W - 2 * p.inset;
@@ -154,13 +169,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kProducerThreads); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        // two MMA issuers: each arrives once on every consumer-side barrier
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kProducerThreads); mbar_init(&empty[i], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 128); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (NCHR < 2) {                          // zero the dummy chunk plane of every slot once
-        for (int i = threadIdx.x; i < kSlots * p.slab_e; i += kThreads) {
+        for (int i = threadIdx.x; i < kSlots * p.slab_e; i += kTcThreads) {
             const int s = i / p.slab_e, e = i % p.slab_e;
             *reinterpret_cast<uint4*>(slab_s + (size_t)s * slot_bytes + ((size_t)p.slab_e + e) * 16) = make_uint4(0, 0, 0, 0);
         }
@@ -175,11 +191,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 5) {
+    if (warp >= 6) {
         // =============================== producers ===============================
         // The (h, w) geometry of a slab row depends only on the q-tile, so each thread resolves its <= kMaxCopies
         // copies (source offset inside a plane, padding, destination) once per work item and then streams planes.
-        const int pt = threadIdx.x - 5 * 32;
+        const int pt = threadIdx.x - 6 * 32;
         const int c0ch = p.C0 >> 3;
         const int copies = p.slab_need * NCHR;
         uint32_t k = 0;                                        // running plane counter (whole kernel)
@@ -233,18 +249,28 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
             }
         }
         cp_async_wait_all();
-    } else if (warp == 4) {
-        // =============================== MMA issuer ===============================
+    } else if (warp >= 4) {
+        // =============================== MMA issuers (lane 0 of warps 4 and 5) ===============================
+        // A tcgen05.mma this small (N = 16 / 32) holds the tensor pipe for ~40 cycles regardless of N, and one thread cannot
+        // issue them faster than every ~45-60 cycles (scripts/microbench/umma_rate.cu), so the 27 taps of an output plane are
+        // split between two issuing threads — taps 0-13 and 14-26 — that accumulate into two partial TMEM tiles; the epilogue
+        // adds the partials.  Each issuer releases an input plane after ITS last use of it.
         if (lane == 0) {
-            const bf16* wsrc = wimg + ((size_t)(g * p.nt_tiles + nt) * w_bytes) / 2;
-            mbar_expect_tx(wbar, (uint32_t)w_bytes);
-            for (int off = 0; off < w_bytes; off += 16384) {
-                const int nb = min(16384, w_bytes - off);
-                bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
+            const int half = warp - 4;
+            if (half == 0) {
+                const bf16* wsrc = wimg + ((size_t)(g * p.nt_tiles + nt) * w_bytes) / 2;
+                mbar_expect_tx(wbar, (uint32_t)w_bytes);
+                for (int off = 0; off < w_bytes; off += 16384) {
+                    const int nb = min(16384, w_bytes - off);
+                    bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
+                }
             }
             mbar_wait(wbar, 0, err, 2);
             const uint32_t slab_addr = smem_u32(slab_s);
             const uint64_t b0 = umma_desc(smem_u32(w_s), NT * 16, 128);
+            uint32_t toff[9];                                  // (kh, kw) start-address shifts, in 16 B units
+#pragma unroll
+            for (int r = 0; r < 9; ++r) toff[r] = (uint32_t)((r / 3) * p.PW + (r % 3));
             uint32_t k = 0, j = 0;
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
@@ -259,33 +285,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
                     mbar_wait(&acc_empty[stage], ((j >> 1) & 1) ^ 1, err, 4);
                     fence_proxy_async();                       // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + stage * NT;
-                    uint32_t acc = 0;
-#pragma unroll 1
-                    for (int kd = 0; kd < 3; ++kd) {
-                        const uint32_t sb = slab_addr + ((k + od + kd) % kSlots) * slot_bytes;
-                        const uint64_t a0 = umma_desc(sb, (uint32_t)p.slab_e * 16, 128);
+                    const uint32_t d_tmem = tmem_base + (stage * 2 + half) * NT;
+                    uint64_t sdesc[3];
 #pragma unroll
-                        for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                            for (int kw = 0; kw < 3; ++kw) {
-                                const int tap = (kd * 3 + kh) * 3 + kw;
-                                const uint64_t a1 = a0 + (uint64_t)(uint32_t)(kh * p.PW + kw);       // address field is in 16 B units
-#pragma unroll
-                                for (int ks = 0; ks < KS; ++ks) {
-                                    const uint64_t ad = a1 + (uint64_t)(uint32_t)(2 * ks * p.slab_e);
-                                    const uint64_t bd = b0 + (uint64_t)(uint32_t)((tap * NCH + 2 * ks) * NT);
-                                    umma_f16(d_tmem, ad, bd, IDESC, acc);
-                                    acc = 1;
-                                }
-                            }
-                        }
-                    }
+                    for (int kd = 0; kd < 3; ++kd)
+                        sdesc[kd] = umma_desc(slab_addr + ((k + od + kd) % kSlots) * slot_bytes, (uint32_t)p.slab_e * 16, 128);
+                    if (half == 0) issue_taps<0, 14, KS, NCH, NT>(d_tmem, sdesc, b0, toff, 2 * p.slab_e, IDESC);
+                    else           issue_taps<14, 27, KS, NCH, NT>(d_tmem, sdesc, b0, toff, 2 * p.slab_e, IDESC);
                     umma_commit(&acc_full[stage]);
-                    umma_commit(&empty[(k + od) % kSlots]);                 // plane od is not needed any more
-                    if (od == nout - 1) {
+                    // plane releases: issuer 0's last use of plane P is as kd = 0 of output P, issuer 1's as kd = 1 of output P-1
+                    if (half == 0) {
+                        umma_commit(&empty[(k + od) % kSlots]);
+                        if (od == nout - 1) {
+                            umma_commit(&empty[(k + od + 1) % kSlots]);
+                            umma_commit(&empty[(k + od + 2) % kSlots]);
+                        }
+                    } else {
+                        if (od == 0) umma_commit(&empty[k % kSlots]);
                         umma_commit(&empty[(k + od + 1) % kSlots]);
-                        umma_commit(&empty[(k + od + 2) % kSlots]);
+                        if (od == nout - 1) umma_commit(&empty[(k + od + 2) % kSlots]);
                     }
                 }
                 k += nout + 2;
@@ -319,9 +337,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_tc_kernel(TcP p, const bf16
                 mbar_wait(&acc_full[stage], (j >> 1) & 1, err, 5);
                 tc_fence_after();
                 float v[NT];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * NT;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * 2 * NT;
 #pragma unroll
-                for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, v + c);
+                for (int c = 0; c < NT; c += 16) {
+                    float u[16];
+                    tmem_ld16(taddr + c, v + c);
+                    tmem_ld16(taddr + NT + c, u);               // the second issuer's partial sum
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[c + i] += u[i];
+                }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[stage]);
                 if (bias4 != nullptr) {                       // L1-resident broadcast loads; not kept in registers
@@ -390,7 +414,7 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, co
     if (smem <= 110 * 1024) ctas *= 2;
     if (ctas < 1) ctas = 1;
     if (ctas > items) ctas = items;
-    kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
+    kern<<<dim3(ctas, p.groups, p.nt_tiles), kTcThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
                                                                     (bf16*)y0, (bf16*)y1, (bf16*)yext, stats, err);
     return 0;
 }
