@@ -23,7 +23,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kProducerThreads = 96;
-constexpr int kTcThreads = 288;         // conv3_tc_kernel: 4 epilogue warps, 2 MMA-issuer warps, 3 producer warps
+constexpr int kTcThreads = 288;         // conv3_tc_kernel: 4 epilogue warps, 1 MMA-issuer warp, 4 producer warps
+constexpr int kTcProducers = 128;
 constexpr int kSlots = 6;               // input-plane ring: 3 planes in use by the MMAs + 3 planes of prefetch
 constexpr int kMaxCopies = 16;          // 16-B copies per producer thread and plane ...
 constexpr int kMaxCopiesWide = 20;      // ... and for the 64-channel variants (NCHR = 8, which have registers to spare)
@@ -125,20 +126,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// taps [T0, T1) of one output plane, fully unrolled: every descriptor is one 64-bit add away from a register
-template <int T0, int T1, int KS, int NCH, int NT>
-__device__ __forceinline__ void issue_taps(uint32_t d_tmem, const uint64_t (&sdesc)[3], uint64_t b0, const uint32_t (&toff)[9],
-                                           int ks_stride, uint32_t idesc) {
-#pragma unroll
-    for (int tap = T0; tap < T1; ++tap) {
-        const uint64_t a1 = sdesc[tap / 9] + (uint64_t)toff[tap % 9];                   // address field is in 16 B units
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-            umma_f16(d_tmem, a1 + (uint64_t)(uint32_t)(ks * ks_stride), b0 + (uint64_t)(uint32_t)((tap * NCH + 2 * ks) * NT), idesc,
-                     (tap == T0 && ks == 0) ? 0u : 1u);
-    }
+// zero 16 consecutive TMEM columns of this warp's 32 lanes
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+        ::"r"(taddr), "r"(0u) : "memory");
 }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// The three kd taps are stacked along N: the MMAs of INPUT plane pl (9 x K-steps of them, N = 3 NT) add its contribution
+// to the three output planes pl-2, pl-1, pl at once, whose accumulators are adjacent blocks of a ring of TMEM column blocks.
+// Why: a tcgen05.mma with N <= 48 holds the tensor pipe for ~40-45 cycles however small it is
+// (scripts/microbench/umma_rate.cu), so the pipe time of this kernel is (number of MMA instructions) x 40 cycles; stacking
+// cuts the instruction count per output plane from 27 to ~10 without any shifted summation in the epilogue (the shifts are
+// between planes, i.e. between accumulator blocks).  All MMAs accumulate; the epilogue zeroes a block after draining it.
 // NCHR = real input chunks of 8 channels (1,2,4,8); NT = Cout tile (16 or 32)
 template <int NCHR, int NT>
 __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
@@ -147,21 +148,21 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
                                                                double* __restrict__ stats, int* err) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;             // a K=16 MMA step needs two 8-channel chunks (zero chunk if Cin = 8)
     constexpr int KS = NCH / 2;
-    constexpr int TMEM_COLS = 4 * NT < 32 ? 32 : 4 * NT;  // 2 stages x 2 partial accumulators (one per issuer)
-    constexpr uint32_t IDESC = umma_idesc(kTileM, NT);
+    constexpr int TMEM_COLS = 256;                        // two CTAs per SM share the 512 columns
+    constexpr int R = TMEM_COLS / NT;                     // accumulator ring: one block of NT columns per output plane in flight
     // input extent (= output extent unless p.inset)
     const int Di = p.D - 2 * p.inset, Hi = p.H - 2 * p.inset, Wi = p.W - 2 * p.inset;
     extern __shared__ __align__(128) uint8_t smem[];
-    const int w_bytes = 27 * NCH * NT * 16;
+    const int w_bytes = 27 * NCH * NT * 16;              // [9 (kh,kw)][NCH chunks][3 NT rows: kd = 2,1,0][8 channels]
     uint8_t* w_s = smem;
     const int slot_bytes = NCH * p.slab_e * 16;
     uint8_t* slab_s = smem + ((w_bytes + 127) & ~127);
     uint64_t* bars = reinterpret_cast<uint64_t*>(slab_s + (size_t)kSlots * slot_bytes);
     uint64_t* full = bars;                   // [kSlots]  producers -> MMA
     uint64_t* empty = bars + kSlots;         // [kSlots]  MMA -> producers
-    uint64_t* acc_full = bars + 2 * kSlots;  // [2]       MMA -> epilogue
-    uint64_t* acc_empty = acc_full + 2;      // [2]       epilogue -> MMA
-    uint64_t* wbar = acc_empty + 2;          // weights landed
+    uint64_t* blk_full = bars + 2 * kSlots;  // [R]       MMA -> epilogue: output plane complete
+    uint64_t* blk_empty = blk_full + R;      // [R]       epilogue -> MMA: block drained and zeroed
+    uint64_t* wbar = blk_empty + R;          // weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,9 +170,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        // two MMA issuers: each arrives once on every consumer-side barrier
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kProducerThreads); mbar_init(&empty[i], 2); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kTcProducers); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < R; ++i) { mbar_init(&blk_full[i], 1); mbar_init(&blk_empty[i], 128); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -190,12 +190,20 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp < 4) {                          // every accumulator block starts from zero
+#pragma unroll 1
+        for (int c = 0; c < TMEM_COLS; c += 16) tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
-    if (warp >= 6) {
+    if (warp >= 5) {
         // =============================== producers ===============================
         // The (h, w) geometry of a slab row depends only on the q-tile, so each thread resolves its <= kMaxCopies
         // copies (source offset inside a plane, padding, destination) once per work item and then streams planes.
-        const int pt = threadIdx.x - 6 * 32;
+        const int pt = threadIdx.x - 5 * 32;
         const int c0ch = p.C0 >> 3;
         const int copies = p.slab_need * NCHR;
         uint32_t k = 0;                                        // running plane counter (whole kernel)
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
             uint32_t from1 = 0;
 #pragma unroll
             for (int i = 0; i < max_copies(NCHR); ++i) {
-                const int idx = pt + i * kProducerThreads;
+                const int idx = pt + i * kTcProducers;
                 soff[i] = -1; doff[i] = 0;
                 if (idx < copies) {
                     const int ch = idx % NCHR, e = idx / NCHR;
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
                 const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
 #pragma unroll
                 for (int i = 0; i < max_copies(NCHR); ++i) {
-                    if (pt + i * kProducerThreads < copies) {
+                    if (pt + i * kTcProducers < copies) {
                         const bool ok = plane_ok && soff[i] >= 0;
                         const bf16* src = ((from1 >> i) & 1u) ? p1 : p0;
                         cp_async16(sbase + doff[i], ok ? src + soff[i] : x0, ok ? 16u : 0u);
@@ -249,64 +257,54 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
             }
         }
         cp_async_wait_all();
-    } else if (warp >= 4) {
-        // =============================== MMA issuers (lane 0 of warps 4 and 5) ===============================
-        // A tcgen05.mma this small (N = 16 / 32) holds the tensor pipe for ~40 cycles regardless of N, and one thread cannot
-        // issue them faster than every ~45-60 cycles (scripts/microbench/umma_rate.cu), so the 27 taps of an output plane are
-        // split between two issuing threads — taps 0-13 and 14-26 — that accumulate into two partial TMEM tiles; the epilogue
-        // adds the partials.  Each issuer releases an input plane after ITS last use of it.
+    } else if (warp == 4) {
+        // =============================== MMA issuer ===============================
         if (lane == 0) {
-            const int half = warp - 4;
-            if (half == 0) {
-                const bf16* wsrc = wimg + ((size_t)(g * p.nt_tiles + nt) * w_bytes) / 2;
-                mbar_expect_tx(wbar, (uint32_t)w_bytes);
-                for (int off = 0; off < w_bytes; off += 16384) {
-                    const int nb = min(16384, w_bytes - off);
-                    bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
-                }
+            const bf16* wsrc = wimg + ((size_t)(g * p.nt_tiles + nt) * w_bytes) / 2;
+            mbar_expect_tx(wbar, (uint32_t)w_bytes);
+            for (int off = 0; off < w_bytes; off += 16384) {
+                const int nb = min(16384, w_bytes - off);
+                bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
             }
             mbar_wait(wbar, 0, err, 2);
             const uint32_t slab_addr = smem_u32(slab_s);
-            const uint64_t b0 = umma_desc(smem_u32(w_s), NT * 16, 128);
+            const uint64_t b0 = umma_desc(smem_u32(w_s), 3 * NT * 16, 128);      // LBO = one chunk plane of 3 NT rows
             uint32_t toff[9];                                  // (kh, kw) start-address shifts, in 16 B units
 #pragma unroll
             for (int r = 0; r < 9; ++r) toff[r] = (uint32_t)((r / 3) * p.PW + (r % 3));
-            uint32_t k = 0, j = 0;
+            uint32_t k = 0, j0 = 0;                            // running input-plane / output-plane counters (whole kernel)
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
                 const int nout = min(p.DCH, p.D - dc * p.DCH);
-                for (int od = 0; od < nout; ++od, ++j) {
-                    const int first_wait = od == 0 ? 0 : 2;
-                    for (int kd = first_wait; kd < 3; ++kd) {
-                        const uint32_t kk = k + od + kd;
-                        mbar_wait(&full[kk % kSlots], (kk / kSlots) & 1, err, 3);
+                for (int pl = 0; pl < nout + 2; ++pl, ++k) {
+                    mbar_wait(&full[k % kSlots], (k / kSlots) & 1, err, 3);
+                    if (pl < nout) {                           // output plane pl gets its first contribution: its block must be free
+                        const uint32_t jn = j0 + pl;
+                        mbar_wait(&blk_empty[jn % R], ((jn / R) & 1) ^ 1, err, 4);
                     }
-                    const int stage = j & 1;
-                    mbar_wait(&acc_empty[stage], ((j >> 1) & 1) ^ 1, err, 4);
                     fence_proxy_async();                       // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (stage * 2 + half) * NT;
-                    uint64_t sdesc[3];
+                    const int od_lo = pl >= 2 ? pl - 2 : 0, od_hi = pl < nout ? pl : nout - 1;
+                    const int nb = od_hi - od_lo + 1;                          // output planes this input plane feeds (1..3)
+                    const int row0 = (2 - (pl - od_lo)) * NT;                  // weight rows are ordered kd = 2, 1, 0
+                    const int blk0 = (int)((j0 + od_lo) % R);
+                    const int n1 = blk0 + nb > R ? R - blk0 : nb;              // blocks before the ring wraps
+                    const uint64_t a0 = umma_desc(slab_addr + (k % kSlots) * slot_bytes, (uint32_t)p.slab_e * 16, 128);
 #pragma unroll
-                    for (int kd = 0; kd < 3; ++kd)
-                        sdesc[kd] = umma_desc(slab_addr + ((k + od + kd) % kSlots) * slot_bytes, (uint32_t)p.slab_e * 16, 128);
-                    if (half == 0) issue_taps<0, 14, KS, NCH, NT>(d_tmem, sdesc, b0, toff, 2 * p.slab_e, IDESC);
-                    else           issue_taps<14, 27, KS, NCH, NT>(d_tmem, sdesc, b0, toff, 2 * p.slab_e, IDESC);
-                    umma_commit(&acc_full[stage]);
-                    // plane releases: issuer 0's last use of plane P is as kd = 0 of output P, issuer 1's as kd = 1 of output P-1
-                    if (half == 0) {
-                        umma_commit(&empty[(k + od) % kSlots]);
-                        if (od == nout - 1) {
-                            umma_commit(&empty[(k + od + 1) % kSlots]);
-                            umma_commit(&empty[(k + od + 2) % kSlots]);
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        const uint64_t a1 = a0 + (uint64_t)toff[t9];           // address field is in 16 B units
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint64_t ad = a1 + (uint64_t)(uint32_t)(2 * ks * p.slab_e);
+                            const uint64_t bd = b0 + (uint64_t)(uint32_t)((t9 * NCH + 2 * ks) * 3 * NT + row0);
+                            umma_f16(tmem_base + blk0 * NT, ad, bd, umma_idesc(kTileM, n1 * NT), 1u);
+                            if (n1 < nb) umma_f16(tmem_base, ad, bd + (uint64_t)(uint32_t)(n1 * NT), umma_idesc(kTileM, (nb - n1) * NT), 1u);
                         }
-                    } else {
-                        if (od == 0) umma_commit(&empty[k % kSlots]);
-                        umma_commit(&empty[(k + od + 1) % kSlots]);
-                        if (od == nout - 1) umma_commit(&empty[(k + od + 2) % kSlots]);
                     }
+                    umma_commit(&empty[k % kSlots]);           // every input plane is consumed exactly once
+                    if (pl >= 2) umma_commit(&blk_full[(j0 + pl - 2) % R]);    // output plane pl-2 is complete
                 }
-                k += nout + 2;
+                j0 += nout;
             }
         }
         __syncwarp();
@@ -333,21 +331,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
 #pragma unroll
             for (int c = 0; c < NT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
             for (int od = 0; od < nout; ++od, ++j) {
-                const int stage = j & 1;
-                mbar_wait(&acc_full[stage], (j >> 1) & 1, err, 5);
+                const uint32_t blk = j % R;
+                mbar_wait(&blk_full[blk], (j / R) & 1, err, 5);
                 tc_fence_after();
                 float v[NT];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * 2 * NT;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + blk * NT;
 #pragma unroll
-                for (int c = 0; c < NT; c += 16) {
-                    float u[16];
-                    tmem_ld16(taddr + c, v + c);
-                    tmem_ld16(taddr + NT + c, u);               // the second issuer's partial sum
+                for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, v + c);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[c + i] += u[i];
-                }
+                for (int c = 0; c < NT; c += 16) tmem_zero16(taddr + c);       // ready for the output plane R planes later
+                tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(&acc_empty[stage]);
+                mbar_arrive(&blk_empty[blk]);
                 if (bias4 != nullptr) {                       // L1-resident broadcast loads; not kept in registers
 #pragma unroll
                     for (int c4 = 0; c4 < NT / 4; ++c4) {
@@ -404,7 +399,7 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, co
               double* stats, int* err, cudaStream_t st) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     const size_t w_bytes = (size_t)27 * NCH * NT * 16;
-    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 5) * 8 + 16;
+    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 2 * 16 + 1) * 8 + 16;
     auto kern = conv3_tc_kernel<NCHR, NT>;
     if (smem > 227 * 1024) { pb_set_error("conv3d_tc: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1474,7 +1469,7 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     while (se % 8 != want % 8) ++se;
     p.slab_e = se;
     p.w_tile_bytes = (long long)27 * nch * NT * 16;
-    if (p.slab_need * nchr > max_copies(nchr) * kProducerThreads) {
+    if (p.slab_need * nchr > max_copies(nchr) * kTcProducers) {
         pb_set_error("conv3d_tc: plane slab of %d x %d copies exceeds the producer budget", p.slab_need, nchr);
         return PB_EUNSUPPORTED;
     }

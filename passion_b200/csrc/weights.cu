@@ -4,7 +4,7 @@
 // compatibility, reference models/blocks.py:357).  The kernels want
 //   wk   fp32 [G][taps][Cin][Cout]                 FFMA forward / weight-gradient layout
 //   wt   fp32 [G][taps][Cout][Cin]                 FFMA data-gradient layout
-//   img  bf16 [G][Cout tiles][27][NCH][NT][8]      tcgen05 forward weight image (zero padded)
+//   img  bf16 [G][Cout tiles][9][NCH][3 NT][8]     tcgen05 forward weight image: (kh,kw) taps, rows kd = 2,1,0 (zero padded)
 //   imgT bf16 [G][Cin tiles][27][NCH'][NT'][8]     the same for the data gradient: taps flipped, channels transposed
 // Doing this with tensor ops costs ~10 tiny launches per layer and step (permute / stack / zeros / copy / cast); here
 // it is one gather kernel before the layer runs and one scatter kernel after its weight gradient.
@@ -49,15 +49,16 @@ __global__ void weight_prep_kernel(PrepK k) {
             continue;
         }
         i -= k.n_wt;
-        if (i < k.n_img) {                                  // [g][tile][tap][chunk][row][8]
+        if (i < k.n_img) {                                  // [g][tile][9 (kh,kw)][chunk][3 nt rows: kd = 2,1,0][8]
             const long long o = i;
             const int e = (int)(i % 8); i /= 8;
-            const int row = (int)(i % k.nt); i /= k.nt;
+            const int row = (int)(i % (3 * k.nt)); i /= 3 * k.nt;
             const int chunk = (int)(i % k.nch); i /= k.nch;
-            const int tap = (int)(i % 27); i /= 27;
+            const int t9 = (int)(i % 9); i /= 9;
             const int tile = (int)(i % k.tiles);
             const int g = (int)(i / k.tiles);
-            const int ci = chunk * 8 + e, co = tile * k.nt + row;
+            const int tap = (2 - row / k.nt) * 9 + t9;
+            const int ci = chunk * 8 + e, co = tile * k.nt + row % k.nt;
             k.img[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, tap) : 0.f);
             continue;
         }
@@ -65,12 +66,13 @@ __global__ void weight_prep_kernel(PrepK k) {
         if (i < k.n_imgT) {                                 // roles of Cin / Cout swapped, taps mirrored
             const long long o = i;
             const int e = (int)(i % 8); i /= 8;
-            const int row = (int)(i % k.ntT); i /= k.ntT;
+            const int row = (int)(i % (3 * k.ntT)); i /= 3 * k.ntT;
             const int chunk = (int)(i % k.nchT); i /= k.nchT;
-            const int tap = (int)(i % 27); i /= 27;
+            const int t9 = (int)(i % 9); i /= 9;
             const int tile = (int)(i % k.tilesT);
             const int g = (int)(i / k.tilesT);
-            const int co = chunk * 8 + e, ci = tile * k.ntT + row;
+            const int tap = (2 - row / k.ntT) * 9 + t9;
+            const int co = chunk * 8 + e, ci = tile * k.ntT + row % k.ntT;
             k.imgT[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, 26 - tap) : 0.f);
             continue;
         }

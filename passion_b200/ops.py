@@ -175,15 +175,16 @@ def _tc_eligible(dtype, ksize, stride, c0, c1, cout):
 
 
 def tc_weight_image(w, nt):
-    """fp32 [G, 27, cin, cout] -> bf16 image [G, cout tiles, 27, max(2, cin/8), nt, 8] (zero padded)."""
+    """fp32 [G, 27, cin, cout] -> bf16 image [G, cout tiles, 9, max(2, cin/8), 3 nt, 8] (zero padded)."""
     G, taps, cin, cout = w.shape
     nchr = cin // 8
     nch = max(2, nchr)
     tiles = (cout + nt - 1) // nt
     img = torch.zeros((G, taps, nch, 8, tiles * nt), dtype=torch.float32, device=w.device)
     img[:, :, :nchr, :, :cout] = w.reshape(G, taps, nchr, 8, cout)
-    img = img.view(G, taps, nch, 8, tiles, nt).permute(0, 4, 1, 2, 5, 3)
-    return img.to(torch.bfloat16).contiguous()
+    # kernel layout: [G][tile][9 (kh,kw)][chunk][3 nt rows, kd = 2,1,0][8 channels]
+    img = img.view(G, 3, 9, nch, 8, tiles, nt).flip(1).permute(0, 5, 2, 3, 1, 6, 4)
+    return img.to(torch.bfloat16).reshape(G, tiles, 9, nch, 3 * nt, 8).contiguous()
 
 
 def _tcs_geom(cin, cout):
@@ -378,8 +379,8 @@ def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt
     f32 = dict(dtype=torch.float32, device=dev)
     wk = torch.empty((G, taps, cin, cout), **f32) if want_wk else None
     wt = torch.empty((G, taps, cout, cin), **f32) if want_wt else None
-    img = torch.empty((G, (cout + nt - 1) // nt, 27, max(2, cin // 8), nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
-    imgT = torch.empty((G, (cin + ntT - 1) // ntT, 27, max(2, cout // 8), ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
+    img = torch.empty((G, (cout + nt - 1) // nt, 9, max(2, cin // 8), 3 * nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
+    imgT = torch.empty((G, (cin + ntT - 1) // ntT, 9, max(2, cout // 8), 3 * ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
     bias = torch.empty((G, cout), **f32) if want_bias else None
     desc = _lib.WeightPrepDesc(groups=G, cin=cin, cout=cout, ksize=ksize, wk=_p(wk), wt=_p(wt), img=_p(img), nt=nt,
                                imgT=_p(imgT), ntT=ntT, bias=_p(bias))
