@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
         const int cb0 = nt * NT;
         const int creal = min(NT, cout - cb0);                 // real channels in this tile (multiple of 8)
         const float4* bias4 = bias != nullptr ? reinterpret_cast<const float4*>(bias + (size_t)g * cout + cb0) : nullptr;
-        uint32_t j = 0;
+        uint32_t j = 0, prev_blk = 0;
+        bool have_prev = false;
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int dc = it % p.ND, r1 = it / p.ND;
             const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
@@ -338,11 +339,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + blk * NT;
 #pragma unroll
                 for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, v + c);
+                // hand the PREVIOUS block back now: its zero-fill (issued one plane ago) has had a whole plane of epilogue work
+                // to land, so the wait below is free; the ring is R = 256 / NT blocks deep, one plane of delay costs nothing
+                if (have_prev) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&blk_empty[prev_blk]);
+                }
 #pragma unroll
                 for (int c = 0; c < NT; c += 16) tmem_zero16(taddr + c);       // ready for the output plane R planes later
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&blk_empty[blk]);
+                prev_blk = blk; have_prev = true;
                 if (bias4 != nullptr) {                       // L1-resident broadcast loads; not kept in registers
 #pragma unroll
                     for (int c4 = 0; c4 < NT / 4; ++c4) {
@@ -386,6 +392,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
                 }
             }
         }
+        if (have_prev) tmem_wait_st();                         // the last zero-fill must land before the columns are released
     }
     tc_fence_before();
     __syncthreads();
