@@ -757,9 +757,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kWgSlotsX; ++i) { mbar_init(&fullx[i], kProducerThreads); mbar_init(&emptyx[i], 1); }
-        for (int i = 0; i < kWgSlotsY; ++i) { mbar_init(&fully[i], kProducerThreads); mbar_init(&emptyy[i], 1); }
-        mbar_init(done, 1);
+        // three MMA issuers (one per kd, as in conv3_wgrad_tc8_kernel): one arrival from each on the consumer-side barriers
+        for (int i = 0; i < kWgSlotsX; ++i) { mbar_init(&fullx[i], kProducerThreads); mbar_init(&emptyx[i], 3); }
+        for (int i = 0; i < kWgSlotsY; ++i) { mbar_init(&fully[i], kProducerThreads); mbar_init(&emptyy[i], 3); }
+        mbar_init(done, 3);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -850,8 +851,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
             }
         }
         cp_async_wait_all();
-    } else if (warp == 4) {
-        // =============================== MMA issuer ===============================
+    }
+    // =============================== MMA issuers: lane 0 of warp 4 (kd = 0) and of the idle epilogue warps 0, 1 (kd = 1, 2) ===
+    // (see conv3_wgrad_tc8_kernel for the protocol: every issuer sees every x plane's `full` phase and releases it itself)
+    const int my_kd = warp == 4 ? 0 : (warp == 0 ? 1 : (warp == 1 ? 2 : -1));
+    if (my_kd >= 0) {
         if (lane == 0) {
             const uint32_t x_addr = smem_u32(x_s), y_addr = smem_u32(y_s);
             uint32_t kx = 0, ky = 0;
@@ -859,47 +863,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_wgrad_tc_kernel(WgP p, cons
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
                 const int nout = min(p.DCH, p.D - dc * p.DCH);
-                for (int od = 0; od < nout; ++od, ++ky) {
-                    for (int kd = (od == 0 ? 0 : 2); kd < 3; ++kd) {
-                        const uint32_t kk = kx + od + kd;
-                        mbar_wait(&fullx[kk % kWgSlotsX], (kk / kWgSlotsX) & 1, err, 13);
-                    }
-                    mbar_wait(&fully[ky % kWgSlotsY], (ky / kWgSlotsY) & 1, err, 14);
-                    fence_proxy_async();
-                    tc_fence_after();
-                    const uint64_t a0 = umma_desc(y_addr + (ky % kWgSlotsY) * kWgYSlotBytes, 128, kWgYPlane);   // LBO = 8 rows, SBO = co-chunk plane
-                    // consecutive MMAs go to DIFFERENT accumulators (9 independent (kd,kh) tiles per K step), so the
-                    // operand fetch of one overlaps the math of the previous instead of queueing behind a dependent chain
-                    uint64_t b0[3];
-#pragma unroll
-                    for (int kd = 0; kd < 3; ++kd)
-                        b0[kd] = umma_desc(x_addr + ((kx + od + kd) % kWgSlotsX) * xslot_bytes, 128, 16);      // LBO = 8 rows, SBO = one-row (kw) shift
+                for (int pl = 0; pl < nout + 2; ++pl) {
+                    const uint32_t kk = kx + pl;
+                    mbar_wait(&fullx[kk % kWgSlotsX], (kk / kWgSlotsX) & 1, err, 13);
+                    const int od = pl - my_kd;
+                    if (od >= 0 && od < nout) {
+                        const uint32_t ko = ky + od;
+                        mbar_wait(&fully[ko % kWgSlotsY], (ko / kWgSlotsY) & 1, err, 14);
+                        fence_proxy_async();
+                        tc_fence_after();
+                        const uint64_t a0 = umma_desc(y_addr + (ko % kWgSlotsY) * kWgYSlotBytes, 128, kWgYPlane);   // LBO = 8 rows, SBO = co-chunk plane
+                        const uint64_t b0 = umma_desc(x_addr + (kk % kWgSlotsX) * xslot_bytes, 128, 16);            // LBO = 8 rows, SBO = one-row (kw) shift
+                        // consecutive MMAs go to DIFFERENT accumulators (the three kh tiles of this kd)
 #pragma unroll 1
-                    for (int ks = 0; ks < kTileM / 16; ++ks) {
-#pragma unroll
-                        for (int kd = 0; kd < 3; ++kd) {
+                        for (int ks = 0; ks < kTileM / 16; ++ks) {
 #pragma unroll
                             for (int kh = 0; kh < 3; ++kh) {
-                                const uint32_t d_tmem = tmem_base + (kd * 3 + kh) * 32;
-                                umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b0[kd] + (uint64_t)(uint32_t)(kh * p.PW + 16 * ks), IDESC,
+                                const uint32_t d_tmem = tmem_base + (my_kd * 3 + kh) * 32;
+                                umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b0 + (uint64_t)(uint32_t)(kh * p.PW + 16 * ks), IDESC,
                                          (first && ks == 0) ? 0u : 1u);
                             }
                         }
+                        first = false;
+                        umma_commit(&emptyy[ko % kWgSlotsY]);
                     }
-                    first = false;
-                    umma_commit(&emptyy[ky % kWgSlotsY]);
-                    umma_commit(&emptyx[(kx + od) % kWgSlotsX]);
-                    if (od == nout - 1) {
-                        umma_commit(&emptyx[(kx + od + 1) % kWgSlotsX]);
-                        umma_commit(&emptyx[(kx + od + 2) % kWgSlotsX]);
-                    }
+                    umma_commit(&emptyx[kk % kWgSlotsX]);
                 }
                 kx += nout + 2;
+                ky += nout;
             }
             umma_commit(done);
         }
         __syncwarp();
-    } else {
+    }
+    if (warp < 4) {
         // =============================== epilogue: TMEM -> fp32 atomics into dw ===============================
         if (blockIdx.x < items) {
             mbar_wait(done, 0, err, 15);
