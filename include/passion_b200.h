@@ -83,12 +83,6 @@ int pb_conv3d_wgrad(const pb_conv_desc* d, const void* x0, const void* x1, const
 int pb_conv3d_tc_ntile(int cin, int cout);
 int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias /* [groups][cout] or NULL */,
                  void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
-/* kw-stacked variant of pb_conv3d_tc (same arguments): the three kw taps of a (kd,kh) pair share one tcgen05.mma
- * (N = 3 x channel tile), the one-/two-row shifted sum happens in the epilogue.  pb_conv3d_tcs_geom returns the per-kw
- * channel tile `ntp` and the padded MMA N `np`; weight image = [groups][cout/ntp][9][max(2,cin/8)][np rows kw*ntp+co][8] bf16. */
-int pb_conv3d_tcs_geom(int cin, int cout, int* ntp, int* np);
-int pb_conv3d_tcs(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias,
-                  void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
 /* Weight gradient of the same class on tcgen05: voxels are the GEMM K dimension, the nine (kd,kh) accumulators of one
  * 8-channel input chunk stay resident in TMEM for the CTA's whole sweep.  dw is the fp32 [groups][27][cin][cout]
  * layout of pb_conv3d_wgrad and must be zero-filled; cout in {8,16,32,64}. */

@@ -70,10 +70,8 @@ def load():
         "pb_conv3d_wgrad": [cd, vp, vp, vp, vp, vp],
         "pb_conv3d_tc_ntile": [i32, i32],
         "pb_conv3d_tc": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
-        "pb_conv3d_tcs_geom": [i32, i32, vp, vp],
         "pb_conv3d_tc_full": [cd, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_reflect_fold": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
-        "pb_conv3d_tcs": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv1_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv3d_dgrad_reflect_fix": [cd, vp, vp, vp, vp, vp],

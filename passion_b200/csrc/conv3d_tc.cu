@@ -422,295 +422,6 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, co
 }
 
 
-// ------------------------------------------------------------------------------------ kw-stacked variant
-// Same implicit GEMM, but the three kw taps of a (kd,kh) pair are stacked along N:
-//     E[q, (kw, co)] = sum_{kd,kh,ci} X[plane d+kd, q + kh*PW, ci] * W[kd,kh,kw,ci,co]        (9 MMAs per K step instead of 27)
-//     D[q, co]       = E[q, (0,co)] + E[q+1, (1,co)] + E[q+2, (2,co)]                        (shifted sum in the epilogue)
-// Every tcgen05.mma occupies the tensor pipe for ~50 cycles regardless of N when N is this small (the 128 x 16 A tile
-// has to be fetched from shared memory each time), so tripling N per instruction cuts the pipe time ~3x.  A tile
-// therefore produces 126 output rows (tiles overlap by 2 rows); the row shift goes through a small smem buffer.
-struct TcsP {
-    int N, D, H, W, C0, C1, CO0, CO1;
-    int reflect;
-    int PW, QT, DCH, ND, npg, groups;
-    int slab_need, slab_e;
-    int ntp, np_, nt_tiles;              // per-kw channel tile, padded N of the MMA (>= 3*ntp, multiple of 16), Cout tiles
-    int tmem_cols;
-};
-constexpr int kTileOut = kTileM - 2;
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }      // the 4 epilogue warps only
-
-template <int NCHR>
-__global__ void __launch_bounds__(kThreads, 2) conv3_tcs_kernel(TcsP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
-                                                                const bf16* __restrict__ wimg, const float* __restrict__ bias,
-                                                                bf16* __restrict__ y0, bf16* __restrict__ y1,
-                                                                double* __restrict__ stats, int* err) {
-    constexpr int NCH = NCHR < 2 ? 2 : NCHR;
-    constexpr int KS = NCH / 2;
-    const uint32_t idesc = umma_idesc(kTileM, p.np_);
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int w_bytes = 9 * NCH * p.np_ * 16;
-    uint8_t* w_s = smem;
-    const int slot_bytes = NCH * p.slab_e * 16;
-    uint8_t* slab_s = smem + ((w_bytes + 127) & ~127);
-    float* xch = reinterpret_cast<float*>(slab_s + (size_t)kSlots * slot_bytes);      // [2 buffers][128 rows][16] kw=1 / kw=2 parts
-    float* sstat = xch + 2 * kTileM * 16;                                             // [2 * 64] per-item InstanceNorm partial sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 128);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + kSlots;
-    uint64_t* acc_full = bars + 2 * kSlots;
-    uint64_t* acc_empty = acc_full + 2;
-    uint64_t* wbar = acc_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.y, nt = blockIdx.z;
-    const int items = p.npg * p.QT * p.ND;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kProducerThreads); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-        mbar_init(wbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x < 128) sstat[threadIdx.x] = 0.f;
-    if (NCHR < 2) {
-        for (int i = threadIdx.x; i < kSlots * p.slab_e; i += kThreads) {
-            const int s = i / p.slab_e, e = i % p.slab_e;
-            *reinterpret_cast<uint4*>(slab_s + (size_t)s * slot_bytes + ((size_t)p.slab_e + e) * 16) = make_uint4(0, 0, 0, 0);
-        }
-        fence_proxy_async();
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp >= 5) {
-        // =============================== producers (as conv3_tc_kernel; rows q0 .. q0 + 127 + 2*PW) ===============================
-        const int pt = threadIdx.x - 5 * 32;
-        const int c0ch = p.C0 >> 3;
-        const int copies = p.slab_need * NCHR;
-        uint32_t k = 0;
-        for (int it = blockIdx.x; it < items; it += gridDim.x) {
-            const int dc = it % p.ND, r1 = it / p.ND;
-            const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
-            const int d0 = dc * p.DCH, q0 = qt * kTileOut;
-            const int nout = min(p.DCH, p.D - d0);
-            int soff[max_copies(NCHR)];
-            uint32_t doff[max_copies(NCHR)];
-            uint32_t from1 = 0;
-#pragma unroll
-            for (int i = 0; i < max_copies(NCHR); ++i) {
-                const int idx = pt + i * kProducerThreads;
-                soff[i] = -1; doff[i] = 0;
-                if (idx < copies) {
-                    const int ch = idx % NCHR, e = idx / NCHR;
-                    const int f = q0 + e;
-                    const int hp = f / p.PW, wp = f - hp * p.PW;
-                    int h = hp - 1, w = wp - 1;
-                    bool ok = hp < p.H + 2;
-                    if (p.reflect) { h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); ok = ok && h >= 0 && h < p.H; }
-                    else ok = ok && h >= 0 && h < p.H && w >= 0 && w < p.W;
-                    doff[i] = (uint32_t)(ch * p.slab_e + e) * 16;
-                    if (ok) {
-                        if (ch < c0ch) soff[i] = (h * p.W + w) * p.C0 + ch * 8;
-                        else { soff[i] = (h * p.W + w) * p.C1 + (ch - c0ch) * 8; from1 |= 1u << i; }
-                    }
-                }
-            }
-            for (int pl = 0; pl < nout + 2; ++pl, ++k) {
-                const int slot = k % kSlots;
-                mbar_wait(&empty[slot], ((k / kSlots) & 1) ^ 1, err, 21);
-                int dp = d0 - 1 + pl;
-                bool plane_ok = true;
-                if (p.reflect) dp = reflect_idx(dp, p.D); else plane_ok = dp >= 0 && dp < p.D;
-                if (!plane_ok) dp = 0;
-                const size_t plane = ((size_t)n * p.D + dp) * p.H * p.W;
-                const bf16* p0 = x0 + plane * p.C0;
-                const bf16* p1 = x1 + plane * p.C1;
-                const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
-#pragma unroll
-                for (int i = 0; i < max_copies(NCHR); ++i) {
-                    if (pt + i * kProducerThreads < copies) {
-                        const bool ok = plane_ok && soff[i] >= 0;
-                        const bf16* src = ((from1 >> i) & 1u) ? p1 : p0;
-                        cp_async16(sbase + doff[i], ok ? src + soff[i] : x0, ok ? 16u : 0u);
-                    }
-                }
-                cp_async_arrive_noinc(&full[slot]);
-            }
-        }
-        cp_async_wait_all();
-    } else if (warp == 4) {
-        // =============================== MMA issuer: 9 * KS instructions per plane ===============================
-        if (lane == 0) {
-            const bf16* wsrc = wimg + ((size_t)(g * p.nt_tiles + nt) * w_bytes) / 2;
-            mbar_expect_tx(wbar, (uint32_t)w_bytes);
-            for (int off = 0; off < w_bytes; off += 16384) {
-                const int nb = min(16384, w_bytes - off);
-                bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
-            }
-            mbar_wait(wbar, 0, err, 22);
-            const uint32_t slab_addr = smem_u32(slab_s);
-            const uint64_t b0 = umma_desc(smem_u32(w_s), (uint32_t)p.np_ * 16, 128);
-            uint32_t k = 0, j = 0;
-            for (int it = blockIdx.x; it < items; it += gridDim.x) {
-                const int dc = it % p.ND;
-                const int nout = min(p.DCH, p.D - dc * p.DCH);
-                for (int od = 0; od < nout; ++od, ++j) {
-                    for (int kd = (od == 0 ? 0 : 2); kd < 3; ++kd) {
-                        const uint32_t kk = k + od + kd;
-                        mbar_wait(&full[kk % kSlots], (kk / kSlots) & 1, err, 23);
-                    }
-                    const int stage = j & 1;
-                    mbar_wait(&acc_empty[stage], ((j >> 1) & 1) ^ 1, err, 24);
-                    fence_proxy_async();
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + stage * p.np_;
-                    uint32_t acc = 0;
-#pragma unroll 1
-                    for (int kd = 0; kd < 3; ++kd) {
-                        const uint32_t sb = slab_addr + ((k + od + kd) % kSlots) * slot_bytes;
-                        const uint64_t a0 = umma_desc(sb, (uint32_t)p.slab_e * 16, 128);
-#pragma unroll
-                        for (int kh = 0; kh < 3; ++kh) {
-                            const uint64_t a1 = a0 + (uint64_t)(uint32_t)(kh * p.PW);
-#pragma unroll
-                            for (int ks = 0; ks < KS; ++ks) {
-                                const uint64_t ad = a1 + (uint64_t)(uint32_t)(2 * ks * p.slab_e);
-                                const uint64_t bd = b0 + (uint64_t)(uint32_t)(((kd * 3 + kh) * NCH + 2 * ks) * p.np_);
-                                umma_f16(d_tmem, ad, bd, idesc, acc);
-                                acc = 1;
-                            }
-                        }
-                    }
-                    umma_commit(&acc_full[stage]);
-                    umma_commit(&empty[(k + od) % kSlots]);
-                    if (od == nout - 1) {
-                        umma_commit(&empty[(k + od + 1) % kSlots]);
-                        umma_commit(&empty[(k + od + 2) % kSlots]);
-                    }
-                }
-                k += nout + 2;
-            }
-        }
-        __syncwarp();
-    } else {
-        // =============================== epilogue ===============================
-        const int cout = p.CO0 + p.CO1;
-        const int cb0 = nt * p.ntp;
-        const int creal = min(p.ntp, cout - cb0);
-        const int r = warp * 32 + lane;                        // tile row = TMEM lane
-        uint32_t j = 0;
-        for (int it = blockIdx.x; it < items; it += gridDim.x) {
-            const int dc = it % p.ND, r1 = it / p.ND;
-            const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
-            const int d0 = dc * p.DCH;
-            const int nout = min(p.DCH, p.D - d0);
-            const int f = qt * kTileOut + r;
-            const int h = f / p.PW, w = f - h * p.PW;
-            const bool valid = r < kTileOut && h < p.H && w < p.W;
-            for (int od = 0; od < nout; ++od, ++j) {
-                const int stage = j & 1;
-                mbar_wait(&acc_full[stage], (j >> 1) & 1, err, 25);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * p.np_;
-                const size_t vox = (((size_t)n * p.D + d0 + od) * p.H + h) * p.W + w;
-                for (int c8 = 0; c8 < creal; c8 += 8) {
-                    float a[8], b[8], c[8];
-                    tmem_ld8(taddr + c8, a);
-                    tmem_ld8(taddr + p.ntp + c8, b);
-                    tmem_ld8(taddr + 2 * p.ntp + c8, c);
-                    tmem_ld_wait();
-                    if (c8 + 8 >= creal) {                     // last read of this accumulator stage: hand it back to the MMA warp
-                        tc_fence_before();
-                        mbar_arrive(&acc_empty[stage]);
-                    }
-                    float* xb = xch + (size_t)((c8 >> 3) & 1) * kTileM * 16;
-                    float4* xr = reinterpret_cast<float4*>(xb + (size_t)r * 16);
-                    xr[0] = make_float4(b[0], b[1], b[2], b[3]); xr[1] = make_float4(b[4], b[5], b[6], b[7]);
-                    xr[2] = make_float4(c[0], c[1], c[2], c[3]); xr[3] = make_float4(c[4], c[5], c[6], c[7]);
-                    epi_bar();
-                    if (r < kTileOut) {
-                        const float4* x1r = reinterpret_cast<const float4*>(xb + (size_t)(r + 1) * 16);
-                        const float4* x2r = reinterpret_cast<const float4*>(xb + (size_t)(r + 2) * 16);
-                        const float4 b0v = x1r[0], b1v = x1r[1], c0v = x2r[2], c1v = x2r[3];
-                        a[0] += b0v.x + c0v.x; a[1] += b0v.y + c0v.y; a[2] += b0v.z + c0v.z; a[3] += b0v.w + c0v.w;
-                        a[4] += b1v.x + c1v.x; a[5] += b1v.y + c1v.y; a[6] += b1v.z + c1v.z; a[7] += b1v.w + c1v.w;
-                    }
-                    if (creal <= 8) epi_bar();                 // single chunk: the one buffer is rewritten next plane
-                    if (bias != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) a[i] += bias[(size_t)g * cout + cb0 + c8 + i];
-                    }
-                    if (valid) {
-                        const int cb = cb0 + c8;
-                        bf16* dst = cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0);
-                        VecIO<bf16, 8>::store(dst, a);
-                    }
-                    if (stats != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float v = valid ? a[i] : 0.f;
-                            const float s1 = warp_sum(v), s2 = warp_sum(v * v);
-                            if (lane == 0) { atomicAdd(&sstat[2 * (c8 + i)], s1); atomicAdd(&sstat[2 * (c8 + i) + 1], s2); }
-                        }
-                    }
-                }
-            }
-            if (stats != nullptr) {                            // flush the item's partial sums (one sample per item)
-                epi_bar();
-                if (threadIdx.x < 2 * creal) {
-                    atomicAdd(&stats[((size_t)n * cout + cb0) * 2 + threadIdx.x], (double)sstat[threadIdx.x]);
-                    sstat[threadIdx.x] = 0.f;
-                }
-                epi_bar();
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
-    }
-}
-
-template <int NCHR>
-int launch_tcs(const TcsP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
-               double* stats, int* err, cudaStream_t st) {
-    constexpr int NCH = NCHR < 2 ? 2 : NCHR;
-    const size_t w_bytes = (size_t)9 * NCH * p.np_ * 16;
-    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kTileM * 16 + 128) * 4 +
-                        (2 * kSlots + 5) * 8 + 16;
-    auto kern = conv3_tcs_kernel<NCHR>;
-    if (smem > 227 * 1024) { pb_set_error("conv3d_tcs: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { pb_set_error("conv3d_tcs: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
-    const int items = p.npg * p.QT * p.ND;
-    int ctas = 148 / (p.groups * p.nt_tiles);
-    if (smem <= 110 * 1024 && p.tmem_cols <= 256) ctas *= 2;
-    if (ctas < 1) ctas = 1;
-    if (ctas > items) ctas = items;
-    kern<<<dim3(ctas, p.groups, p.nt_tiles), kThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
-                                                                    (bf16*)y0, (bf16*)y1, stats, err);
-    return 0;
-}
-
 // ------------------------------------------------------------------------------------ weight gradient on tcgen05
 // dw[tap][ci][co] = sum_{n,q} x[n, q + off(tap)][ci] * dy[n, q][co]  (reflect / zero padding resolved when staging x).
 // GEMM view with the VOXEL index as K:  D[co, (kw, ci)] += A[co, q] * B[(kw, ci), q]  for every (kd, kh), where
@@ -1562,65 +1273,3 @@ extern "C" int pb_conv1_wgrad_tc(const pb_conv_desc* d, const void* x0, const vo
     return PB_OK;
 }
 
-// Geometry of the kw-stacked weight image: per-kw channel tile `ntp`, padded MMA N `np` (>= 3*ntp, multiple of 16).
-// Image layout: [groups][cout tiles][9 (kd,kh)][max(2,cin/8) chunks][np rows: kw*ntp + co][8 channels] bf16, zero padded.
-extern "C" int pb_conv3d_tcs_geom(int cin, int cout, int* ntp, int* np) {
-    if (cin % 8 || cout % 8 || cin > 64 || cin < 8 || cout < 8) return 0;
-    int t = cout;
-    if (t > 64) t = 64;
-    if (cin > 32 && t > 16) t = 16;                      // weights (9 * cin/8 * 3t * 16 B) + the 6-plane ring must fit 227 KB
-    while (cout % t) t -= 8;
-    *ntp = t;
-    *np = (3 * t + 15) / 16 * 16;
-    return 1;
-}
-
-extern "C" int pb_conv3d_tcs(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias,
-                             void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
-    PB_CHECK_ARG(d && x0 && wimg && y0 && err_flag, "null pointer");
-    PB_CHECK_ARG(d->dtype == PB_BF16 && d->ksize == 3 && d->stride == 1, "bf16, 3x3x3, stride 1 only");
-    PB_CHECK_ARG(d->di == d->dout && d->hi == d->ho && d->wi == d->wo, "same-size output only");
-    const int cin = d->c0 + d->c1, cout = co0 + co1;
-    PB_CHECK_ARG(cout == d->cout && co0 % 8 == 0 && co1 % 8 == 0 && (co1 == 0 || y1), "bad output split");
-    PB_CHECK_ARG(d->c0 % 8 == 0 && d->c1 % 8 == 0 && (d->c1 == 0 || x1), "channels must be multiples of 8");
-    PB_CHECK_ARG(d->groups >= 1 && d->n % d->groups == 0, "bad groups");
-    TcsP p;
-    PB_CHECK_ARG(pb_conv3d_tcs_geom(cin, cout, &p.ntp, &p.np_) != 0, "unsupported channel class");
-    p.N = d->n; p.D = d->di; p.H = d->hi; p.W = d->wi; p.C0 = d->c0; p.C1 = d->c1; p.CO0 = co0; p.CO1 = co1;
-    p.reflect = d->pad_mode == PB_PAD_REFLECT;
-    PB_CHECK_ARG(!p.reflect || (p.D >= 2 && p.H >= 2 && p.W >= 2), "reflect padding needs size >= 2");
-    p.PW = p.W + 2;
-    p.QT = (p.H * p.PW + kTileOut - 1) / kTileOut;
-    p.npg = d->n / d->groups; p.groups = d->groups;
-    p.nt_tiles = cout / p.ntp;
-    int tc = 32;
-    while (tc < 2 * p.np_) tc <<= 1;
-    p.tmem_cols = tc;
-    const int target = 148 * 4 / (p.groups * p.nt_tiles);
-    int nd = 1;
-    while (p.npg * p.QT * nd < target && (p.D + nd) / (nd + 1) >= 8) ++nd;
-    p.DCH = (p.D + nd - 1) / nd;
-    p.ND = (p.D + p.DCH - 1) / p.DCH;
-    p.slab_need = kTileM + 2 * p.PW;
-    const int nchr = cin / 8, nch = nchr < 2 ? 2 : nchr;
-    const int want = nch >= 8 ? 1 : 8 / nch;
-    int se = p.slab_need;
-    while (se % 8 != want % 8) ++se;
-    p.slab_e = se;
-    if (p.slab_need * nchr > max_copies(nchr) * kProducerThreads) {
-        pb_set_error("conv3d_tcs: plane slab of %d x %d copies exceeds the producer budget", p.slab_need, nchr);
-        return PB_EUNSUPPORTED;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc = PB_EUNSUPPORTED;
-    switch (nchr) {
-        case 1: rc = launch_tcs<1>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
-        case 2: rc = launch_tcs<2>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
-        case 4: rc = launch_tcs<4>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
-        case 8: rc = launch_tcs<8>(p, x0, x1, wimg, bias, y0, y1, stats, err_flag, st); break;
-        default: pb_set_error("conv3d_tcs: cin %d not supported", cin); break;
-    }
-    if (rc) return rc;
-    PB_CHECK_LAUNCH();
-    return PB_OK;
-}

@@ -144,7 +144,6 @@ WGRAD_TC = os.environ.get("PB_WGRAD_TC", "1") != "0"
 WGRAD1_TC = os.environ.get("PB_WGRAD1_TC", "1") != "0"        # 1x1x1 weight gradient on tcgen05
 DGRAD_FOLD = os.environ.get("PB_DGRAD_FOLD", "1") != "0"      # reflect-pad data gradient: extended-domain tc pass + fold
 UPSAMPLE_SEPARABLE_FROM = int(os.environ.get("PB_UPS_SEP", "2"))     # trilinear adjoint: three 1-D passes from this scale on
-TC_STACKED = os.environ.get("PB_TCS", "0") != "0"        # kw-stacked variant of the fwd / dgrad implicit GEMM (measured: not faster)
 _tc_err = {}
 
 
@@ -187,32 +186,9 @@ def tc_weight_image(w, nt):
     return img.to(torch.bfloat16).reshape(G, tiles, 9, nch, 3 * nt, 8).contiguous()
 
 
-def _tcs_geom(cin, cout):
-    ntp, npad = ctypes.c_int(0), ctypes.c_int(0)
-    ok = _lib.load().pb_conv3d_tcs_geom(cin, cout, ctypes.byref(ntp), ctypes.byref(npad))
-    return (ntp.value, npad.value) if ok else None
-
-
-def tcs_weight_image(w, ntp, npad):
-    """fp32 [G, 27, cin, cout] -> bf16 kw-stacked image [G, cout/ntp, 9, max(2, cin/8), npad, 8]; row = kw*ntp + co."""
-    G, taps, cin, cout = w.shape
-    nchr = cin // 8
-    nch = max(2, nchr)
-    tiles = cout // ntp
-    w6 = w.reshape(G, 9, 3, nchr, 8, tiles, ntp)                       # [G, (kd,kh), kw, chunk, 8, tile, co]
-    img = torch.zeros((G, tiles, 9, nch, npad, 8), dtype=torch.float32, device=w.device)
-    img[:, :, :, :nchr, :3 * ntp, :] = w6.permute(0, 5, 1, 3, 2, 6, 4).reshape(G, tiles, 9, nchr, 3 * ntp, 8)
-    return img.to(torch.bfloat16).contiguous()
-
-
 def _tc_conv_call(lib, d, x0, x1, w, y0, y1, co0, co1, stats, err, bias=None):
-    """Launch the tensor-core implicit GEMM (kw-stacked variant when enabled); returns the C status code."""
+    """Launch the tensor-core implicit GEMM on kernel-layout weights; returns the C status code."""
     cin, cout = d.c0 + d.c1, co0 + co1
-    geom = _tcs_geom(cin, cout) if TC_STACKED else None
-    if geom is not None:
-        img = tcs_weight_image(w, *geom)
-        return lib.pb_conv3d_tcs(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y0), _p(y1), co0, co1, _p(stats), _p(err),
-                                 _stream())
     img = tc_weight_image(w, _tc_ntile(cin, cout))
     return lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y0), _p(y1), co0, co1, _p(stats), _p(err), _stream())
 
