@@ -60,9 +60,11 @@ __global__ void __launch_bounds__(128) conv_fwd_kernel(ConvK p, const T* __restr
     }
     __syncthreads();
 
-    long long o = (long long)blockIdx.x * 128 + threadIdx.x;
-    const bool valid = o < p.Vo;
-    if (!valid) o = p.Vo - 1;
+    // persistent over the voxel blocks: the weight slice above (up to 200 KB for the wide layers) is staged once per CTA
+    float ssum[CO_T], ssq[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+    for (long long o = (long long)blockIdx.x * 128 + threadIdx.x; o < p.Vo; o += (long long)gridDim.x * 128) {
     const int ow = (int)(o % p.Wo);
     const int t1 = (int)(o / p.Wo);
     const int oh = t1 % p.Ho, od = t1 / p.Ho;
@@ -100,13 +102,16 @@ __global__ void __launch_bounds__(128) conv_fwd_kernel(ConvK p, const T* __restr
             }
         }
     }
-    if (valid) VecIO<T, CO_T>::store(y + ((size_t)n * p.Vo + o) * p.Cout + coc * CO_T, acc);
+    VecIO<T, CO_T>::store(y + ((size_t)n * p.Vo + o) * p.Cout + coc * CO_T, acc);
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) { ssum[j] += acc[j]; ssq[j] += acc[j] * acc[j]; }
+    }
     if (stats) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
         for (int j = 0; j < CO_T; ++j) {
-            float s = valid ? acc[j] : 0.f;
-            float q = s * s;
+            float s = ssum[j];
+            float q = ssq[j];
             s = warp_sum(s); q = warp_sum(q);
             if (lane == 0) { red[wid][2 * j] = s; red[wid][2 * j + 1] = q; }
         }
@@ -599,7 +604,10 @@ int launch_fwd(const ConvK& k, const void* x0, const void* x1, const float* w, c
     const size_t smem = (size_t)k.K * k.K * k.K * k.Cin * CO_T * sizeof(float);
     auto kern = conv_fwd_kernel<T, CI_V, CO_T>;
     if (int e = set_smem(kern, smem)) return e;
-    dim3 grid((unsigned)((k.Vo + 127) / 128), k.Cout / CO_T, k.N);
+    long long bx = (k.Vo + 127) / 128;
+    const long long cap = (148LL * 8 + (long long)(k.Cout / CO_T) * k.N - 1) / ((long long)(k.Cout / CO_T) * k.N);
+    if (smem > 16 * 1024 && bx > cap) bx = cap;                 // wide layers: amortise the weight staging over many voxels
+    dim3 grid((unsigned)bx, k.Cout / CO_T, k.N);
     kern<<<grid, 128, smem, st>>>(k, (const T*)x0, (const T*)x1, w, bias, (T*)y, stats);
     return 0;
 }
