@@ -25,7 +25,6 @@ constexpr int kThreads = 256;
 constexpr int kProducerThreads = 96;
 constexpr int kTcThreads = 288;         // conv3_tc_kernel: 4 epilogue warps, 1 MMA-issuer warp, 4 producer warps
 constexpr int kTcProducers = 128;
-constexpr int kSlots = 6;               // input-plane ring: 3 planes in use by the MMAs + 3 planes of prefetch
 constexpr int kMaxCopies = 16;          // 16-B copies per producer thread and plane ...
 constexpr int kMaxCopiesWide = 20;      // ... and for the 64-channel variants (NCHR = 8, which have registers to spare)
 __host__ __device__ constexpr int max_copies(int nchr) { return nchr >= 8 ? kMaxCopiesWide : kMaxCopies; }
@@ -140,7 +139,8 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // (scripts/microbench/umma_rate.cu), so the pipe time of this kernel is (number of MMA instructions) x 40 cycles; stacking
 // cuts the instruction count per output plane from 27 to ~10 without any shifted summation in the epilogue (the shifts are
 // between planes, i.e. between accumulator blocks).  All MMAs accumulate; the epilogue zeroes a block after draining it.
-// NCHR = real input chunks of 8 channels (1,2,4,8); NT = Cout tile (16 or 32)
+// NCHR = real input chunks of 8 channels (1,2,4,8,16); NT = Cout tile (16 or 32); the 128-channel variant (NCHR = 16) has
+// room for a 2-plane ring only (110 KB of weights + 2 x 40 KB planes, one CTA per SM) — its layers are the small deep ones
 template <int NCHR, int NT>
 __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                                const bf16* __restrict__ wimg, const float* __restrict__ bias,
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
                                                                double* __restrict__ stats, int* err) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;             // a K=16 MMA step needs two 8-channel chunks (zero chunk if Cin = 8)
     constexpr int KS = NCH / 2;
+    constexpr int kSlots = NCHR >= 16 ? 2 : 6;           // input-plane ring (every plane is consumed exactly once)
     constexpr int TMEM_COLS = 256;                        // two CTAs per SM share the 512 columns
     constexpr int R = TMEM_COLS / NT;                     // accumulator ring: one block of NT columns per output plane in flight
     // input extent (= output extent unless p.inset)
@@ -405,6 +406,7 @@ template <int NCHR, int NT>
 int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1, void* yext,
               double* stats, int* err, cudaStream_t st) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
+    constexpr int kSlots = NCHR >= 16 ? 2 : 6;
     const size_t w_bytes = (size_t)27 * NCH * NT * 16;
     const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 2 * 16 + 1) * 8 + 16;
     auto kern = conv3_tc_kernel<NCHR, NT>;
@@ -1049,8 +1051,10 @@ int launch_wgrad_tc(const WgP& p, const void* x0, const void* x1, const void* dy
 // Weight image layout expected by the kernel: [groups][cout tiles][27 taps][NCH chunks][NT rows][8 channels] bf16,
 // NCH = max(2, (c0+c1)/8), NT = pb_conv3d_tc_ntile(cout); rows beyond Cout and the padding chunk are zero.
 extern "C" int pb_conv3d_tc_ntile(int cin, int cout) {
-    if (cin % 8 || cout % 8 || cin > 64 || cin < 8 || cout < 8) return 0;
-    if (cout >= 32 && cin <= 32) return 32;      // cin = 64 keeps NT = 16: weights + plane ring must fit 227 KB
+    if (cin % 8 || cout % 8 || cin < 8 || cout < 8) return 0;
+    if (cin > 64 && cin != 128) return 0;        // 8-channel chunk counts the kernel is built for: 1, 2, 4, 8, 16
+    if (cin != 8 && cin != 16 && cin != 32 && cin != 64 && cin != 128) return 0;
+    if (cout >= 32 && cin <= 32) return 32;      // cin >= 64 keeps NT = 16: weights + plane ring must fit 227 KB
     return 16;
 }
 
@@ -1191,7 +1195,7 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
 #define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
-    TC_CASE(1, 16); TC_CASE(2, 16); TC_CASE(4, 16); TC_CASE(8, 16);
+    TC_CASE(1, 16); TC_CASE(2, 16); TC_CASE(4, 16); TC_CASE(8, 16); TC_CASE(16, 16);
     TC_CASE(1, 32); TC_CASE(2, 32); TC_CASE(4, 32); TC_CASE(8, 32);
 #undef TC_CASE
     if (rc) { if (rc == PB_EUNSUPPORTED) pb_set_error("conv3d_tc: no kernel for cin %d cout %d", cin, cout); return rc; }
