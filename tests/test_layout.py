@@ -85,3 +85,36 @@ def test_preference_update_and_lr_match_oracle():
         beta = bt
     for e in (0, 1, 150, 299):
         assert o.poly_lr(2e-4, e, 300) == t.poly_lr(2e-4, e, 300)
+
+
+def test_build_model_sets_token_grid():
+    from passion_b200.models import build_model
+    m = build_model("mmformer", crop=128)
+    assert tuple(m.flair_pos.shape) == (1, 8 ** 3, 512)          # 128 / 16 tokens per axis
+    m = build_model("mmformer", crop=80)
+    assert tuple(m.t2_pos.shape) == (1, 5 ** 3, 512)             # the reference's patch_size = 5
+    with pytest.raises(ValueError):
+        build_model("mmformer", crop=72)
+    with pytest.raises(ValueError):
+        build_model("m2ftrans")
+    assert type(build_model("rfnet")).__name__ == "Model"
+
+
+def test_zero_scratch_arena_hands_out_disjoint_zeroed_slices():
+    """ops._ZeroScratch: linear hand-out, one re-zero per step, growth keeps earlier slices valid."""
+    from passion_b200 import ops
+    sc = ops._ZeroScratch()
+    dev = torch.device("cpu")
+    a = sc.zeros((3, 5, 2), torch.float64, dev)
+    b = sc.zeros((7,), torch.float32, dev)
+    assert a.shape == (3, 5, 2) and a.dtype == torch.float64 and b.dtype == torch.float32
+    a += 1.0
+    b += 2.0
+    assert float(a.sum()) == 30.0 and float(b.sum()) == 14.0       # disjoint
+    sc.begin_step(dev)
+    a2 = sc.zeros((3, 5, 2), torch.float64, dev)
+    assert a2.data_ptr() == a.data_ptr() and float(a2.abs().sum()) == 0.0          # recycled and re-zeroed
+    big = sc.zeros((sc.MIN_BYTES // 4 + 10,), torch.float32, dev)                  # forces a new arena
+    assert float(big.abs().sum()) == 0.0
+    a2 += 3.0
+    assert float(a2.sum()) == 90.0                                                 # old slice still alive
