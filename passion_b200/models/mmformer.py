@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from .. import criterions as crit
 from .. import ops
+from . import rfnet as _rf
 
 basic_dims = 8
 transformer_basic_dims = 512
@@ -361,6 +362,15 @@ class Model(nn.Module):
             C = f.shape[-1]
             st_p = st.view(4, B, C, 2).permute(1, 0, 2, 3)[None] * ms.double()[:, :, :, None, None]      # [P,B,4,C,2]
             ys.append((ops.masked_stack(f, ms), st_p.reshape(P * B, 4 * C, 2).contiguous()))
+        sep_logits = None
+        if self.is_training and _rf.SEP_STREAM:
+            # decoder_sep only needs the masked encoder features: second stream, as in models/rfnet.py
+            main = torch.cuda.current_stream(dev)
+            side = _rf._side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                sep_logits = self.decoder_sep.run(*feat)
+                sep_logits.record_stream(main)
         x5 = self._inter(intra, ms5, p)
         logits, preds, des = self.decoder_fuse.run(*ys, x5)
         D, H, W = logits.shape[1:4]
@@ -370,7 +380,10 @@ class Model(nn.Module):
         if not self.is_training:
             return fuse_prob
 
-        sep_logits = self.decoder_sep.run(*feat)                              # [4B,D,H,W,C], modality-major
+        if sep_logits is None:
+            sep_logits = self.decoder_sep.run(*feat)                          # [4B,D,H,W,C], modality-major
+        else:
+            torch.cuda.current_stream(dev).wait_stream(_rf._side_stream(dev))
         sep_prob = ops.softmax4(sep_logits).view(4, B, D, H, W, -1) * e[:, :, None, None, None, None]     # :480-483
         self.last["sep_prob"] = sep_prob
         labels, cnt, wgt = crit.label_stats(target)
