@@ -80,6 +80,14 @@ def _run(name, key, nbytes, flops, fn, allow_unsupported=False):
     return True
 
 
+def _publish_to_all_streams(device):
+    """A buffer that was just created and filled on the CURRENT stream is about to be shared by ops on other streams (the
+    models run decoder_sep on a side stream): make the fill visible everywhere.  Only happens while the arenas grow, i.e.
+    in the first eager steps; never inside a CUDA-graph capture (the trainer's warm-up steps have sized everything by then)."""
+    if device.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.current_stream(device).synchronize()
+
+
 class _ZeroScratch:
     """Zero-initialised short-lived scratch (statistics / weight-gradient accumulators that kernels fill with atomics and
     the very next launch consumes).  Slices of one arena per device, handed out linearly; `begin_step()` re-zeroes the
@@ -105,6 +113,7 @@ class _ZeroScratch:
             size = max(self.MIN_BYTES, 2 * nbytes, 2 * (a[0].numel() if a is not None else 0))
             a = [torch.zeros(size, dtype=torch.uint8, device=device), 0]
             self.arenas[device] = a
+            _publish_to_all_streams(device)
         off = a[1]
         a[1] = off + nbytes
         return a[0][off:off + nbytes].view(dtype)[:n].view(shape)
@@ -152,6 +161,7 @@ def _tc_err_flag(device):
     if t is None:
         t = torch.zeros(1, dtype=torch.int32, device=device)
         _tc_err[device] = t
+        _publish_to_all_streams(torch.device(device))
     return t
 
 
@@ -525,6 +535,7 @@ def zero_grad_like(shape, dtype, device):
     if buf is None or buf.numel() < n:
         buf = torch.zeros(max(n, 1 << 16), dtype=dtype, device=device)
         _zero_arena[(dtype, device)] = buf
+        _publish_to_all_streams(torch.device(device))
     return buf[:n].view(shape)
 
 
