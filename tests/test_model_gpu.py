@@ -186,6 +186,29 @@ def test_inference_and_argmax(lib_built):
     assert_labels_match(prob, z["infer_argmax"], torch.from_numpy(z["infer_prob"]))
 
 
+def test_side_stream_does_not_change_results(lib_built):
+    """decoder_sep runs on a second CUDA stream (models/rfnet.py SEP_STREAM): same numbers as the single-stream order, up
+    to the summation order of the atomics."""
+    from passion_b200.models import rfnet
+    res = []
+    old = rfnet.SEP_STREAM
+    try:
+        for flag in (False, True):
+            rfnet.SEP_STREAM = flag
+            z, model, sd, x, target, mask = _setup("idtU", torch.float32)
+            outs, loss, parts = _cuda_step(model, x, target, mask, z)
+            torch.cuda.synchronize()
+            res.append((float(loss), [o.detach().clone() for o in outs],
+                        torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None]).clone()))
+    finally:
+        rfnet.SEP_STREAM = old
+    (l0, o0, g0), (l1, o1, g1) = res
+    assert abs(l0 - l1) < 1e-5 * abs(l0)
+    for a, b in zip(o0, o1):
+        assert rel(a, b) < 1e-5
+    assert rel(g0, g1) < 1e-4
+
+
 def test_requires_cuda(lib_built):
     from passion_b200.models import rfnet
     m = rfnet.Model(4)
