@@ -240,6 +240,36 @@ int pb_proto_bwd1(int dtype, const void* fs, const void* ft, const float* protos
 int pb_proto_bwd2(int dtype, const uint8_t* labels, const float* dproto, void* dfs, int n, int b, long long voxels,
                   int c, pb_stream_t stream);
 
+/* ---- training-sample pipeline on the device, csrc/augment.cu ------------------------------
+ * Replaces, for one batch and in ONE launch, what the reference's DataLoader workers do per item on the CPU with
+ * numpy / scipy: options.py:50's Compose([RandCrop3D, RandomRotion(10), RandomIntensityChange, RandomFlip, NumpyType])
+ * (data/transforms.py:407-418, 86-120, 133-155, 217-240, 378-390) and the transposes / one-hot of
+ * data/datasets_nii.py:141-160.  The random DRAWS stay on the host, in the reference's order (passion_b200/data.py);
+ * the kernel applies them bit-exactly:
+ *   out position (i,j,k) -> undo the flips -> p;  rotation (scipy.ndimage.rotate, order 0, mode 'constant',
+ *   cval -1, reshape False): in = M (p[a0], p[a1]) + off in float64 with separate multiplies and adds in scipy's order;
+ *   a coordinate outside [0, n-1] yields -1 for the image and 0 for the uint8 label, else the voxel floor(in + 0.5)
+ *   of the crop at `start`;  x = float32(float64(v) * scale[p0][c] + shift[p0][c]).
+ * vol: [H][W][Z][4] float32 (preprocessing/preprocess_brats.py:71-83), seg: [H][W][Z] uint8; both DEVICE pointers,
+ * the struct array and the factor tables are DEVICE memory too.
+ * Outputs: x [b][4][s0][s1][s2] float32 (Model.forward's input), labels [b][s0][s1][s2] uint8 (may be NULL),
+ * onehot [b][4][s0][s1][s2] float64 (the reference's target format, may be NULL).
+ */
+typedef struct pb_augment_sample {
+    const float*   vol;
+    const uint8_t* seg;
+    int32_t shape[3];              /* H, W, Z of the volume                                   */
+    int32_t start[3];              /* crop origin (RandCrop3D.buffer)                         */
+    int32_t flip[3];               /* RandomFlip x / y / z buffers                            */
+    int32_t rot_axes[2];           /* sorted rotation plane a0 < a1, axes of the crop         */
+    int32_t _pad;
+    double  rot_m[4];              /* [[c, s], [-s, c]], c/s = cosdg/sindg(angle)             */
+    double  rot_off[2];            /* centre - M centre, centre = (n - 1) / 2                 */
+} pb_augment_sample;
+int pb_augment_sample_size(void);  /* sizeof(pb_augment_sample), for the host-side packer's layout check */
+int pb_augment_batch(const pb_augment_sample* samples, const double* scale, const double* shift, int b, int s0, int s1,
+                     int s2, float* x, uint8_t* labels, double* onehot, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,6 @@
 """Command-line flags of the training entry point — same names, defaults and derived fields as the reference
-`code/options.py:4-52` (argparse is the reference's only config mechanism), plus two additions that do not exist
-there: --synthetic (no dataset on disk) and --dtype."""
+`code/options.py:4-52` (argparse is the reference's only config mechanism), plus a few additions that do not exist
+there: --synthetic (no dataset on disk), --dtype, --crop_size, --no_graph and --device_aug."""
 import argparse
 import os
 
@@ -35,12 +35,16 @@ def args_parser(argv=None):
     parser.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'], help='activation storage (f32 = check mode)')
     parser.add_argument('--crop_size', default=80, type=int, help='edge of the random training crop (reference: 80; mmformer needs a multiple of 16)')
     parser.add_argument('--no_graph', action='store_true', help='do not replay the step as a CUDA graph (N = 1)')
+    parser.add_argument('--device_aug', action='store_true',
+                        help='keep the preprocessed cases resident in HBM and run train_transforms (crop, rotation, intensity, flip) '
+                             'and the label encoding as one kernel per batch (passion_b200/data.py) instead of on the host')
     args = parser.parse_args(argv)
 
     root = args.datarootPath or os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'datasets'))
     args.datarootPath = root
     args.datasetPath = os.path.abspath(os.path.join(root, args.datapath))
-    # kept for interface parity (options.py:50-51); this repository's loader implements the random 80^3 crop only
+    # kept for interface parity (options.py:50-51): --device_aug implements exactly this chain on the device
+    # (passion_b200/data.py); the host loader of train.py without it does the random crop only
     args.train_transforms = 'Compose([RandCrop3D((80,80,80)), RandomRotion(10), RandomIntensityChange((0.1,0.1)), RandomFlip(0), NumpyType((np.float32, np.int64)),])'
     args.test_transforms = 'Compose([NumpyType((np.float32, np.int64)),])'
     return args

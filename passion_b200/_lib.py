@@ -39,6 +39,13 @@ class WeightUnpackDesc(ctypes.Structure):
                 ("groups", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32)]
 
 
+class AugmentSample(ctypes.Structure):
+    """Mirror of pb_augment_sample (112 bytes; checked against pb_augment_sample_size() at load)."""
+    _fields_ = [("vol", ctypes.c_void_p), ("seg", ctypes.c_void_p), ("shape", ctypes.c_int32 * 3), ("start", ctypes.c_int32 * 3),
+                ("flip", ctypes.c_int32 * 3), ("rot_axes", ctypes.c_int32 * 2), ("_pad", ctypes.c_int32),
+                ("rot_m", ctypes.c_double * 4), ("rot_off", ctypes.c_double * 2)]
+
+
 def declared_symbols():
     """Every function name declared in include/passion_b200.h."""
     with open(HEADER_PATH) as f:
@@ -104,12 +111,16 @@ def load():
         "pb_rfm_mix": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
         "pb_rfm_mix_bwd_gate": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
         "pb_rfm_bwd_y": [i32, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],
+        "pb_augment_sample_size": [],
+        "pb_augment_batch": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         if hasattr(lib, name):
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
+    if lib.pb_augment_sample_size() != ctypes.sizeof(AugmentSample):
+        raise RuntimeError("passion_b200: pb_augment_sample layout mismatch between the header and _lib.AugmentSample")
     _lib = lib
     return lib
 

@@ -6,7 +6,8 @@ Public, reference-compatible entry points (all return [B,1] float32, as the refe
     softmax_weighted_loss_bs(output, target, num_cls, up_op)                            criterions.py:59-76
     temp_kl_loss_bs(logit_s, logit_t, target, num_cls, temp, up_op)                     criterions.py:92-103
     prototype_passion_loss_bs(feature_s, feature_t, target, logit_s, logit_t, ...)      criterions.py:144-180
-`output` / `logit_*` / `feature_*` are [B,C,D,H,W]; `target` is the one-hot [B,num_cls,D,H,W] tensor; `up_op` is
+`output` / `logit_*` / `feature_*` are [B,C,D,H,W]; `target` is the one-hot [B,num_cls,D,H,W] tensor (or, as an extension, the
+uint8 label map [B,D,H,W]); `up_op` is
 None, an integer scale factor or an nn.Upsample-like object with .scale_factor.
 
 The model does not go through these wrappers: it calls the channels-last helpers below directly on its
@@ -43,11 +44,17 @@ def up_probs(p, scale):
 
 
 # ------------------------------------------------------------------ channels-last helpers used by the model
-def label_stats(target):
-    """one-hot target [B,C,D,H,W] -> (labels uint8 [B,D,H,W], class voxel counts [B,C] fp32,
-    CE class weights 1 - count/total [B,C] (criterions.py:67))."""
-    labels = target.argmax(1).to(torch.uint8).contiguous()
-    cnt = target.sum((2, 3, 4)).to(torch.float32)
+def label_stats(target, num_cls=4):
+    """target -> (labels uint8 [B,D,H,W], class voxel counts [B,C] fp32, CE class weights 1 - count/total [B,C]
+    (criterions.py:67)).  `target` is the reference's one-hot [B,C,D,H,W] (float64, datasets_nii.py:150-153) or — the
+    compact form passion_b200.data.DeviceAugment produces — the uint8 label map [B,D,H,W] itself (33x fewer bytes)."""
+    if target.dtype == torch.uint8 and target.dim() == 4:
+        labels = target.contiguous()
+        cls = torch.arange(num_cls, device=target.device, dtype=torch.uint8).view(1, num_cls, 1)
+        cnt = (labels.view(labels.shape[0], 1, -1) == cls).sum(-1).to(torch.float32)
+    else:
+        labels = target.argmax(1).to(torch.uint8).contiguous()
+        cnt = target.sum((2, 3, 4)).to(torch.float32)
     return labels, cnt, 1.0 - cnt / cnt.sum(1, keepdim=True)
 
 

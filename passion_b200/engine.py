@@ -38,6 +38,7 @@ class Trainer:
                                            fused=dev.type == "cuda")
         self._graph = None
         self._captured_warmup = None
+        self._sig = None
         if self.use_graph:                       # the LR lives in a device tensor so that a replayed graph sees updates
             self._lr_t = torch.tensor(float(lr), device=dev)
             self.optimizer.param_groups[0]["lr"] = self._lr_t
@@ -72,8 +73,14 @@ class Trainer:
         return loss.detach(), parts
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    @staticmethod
+    def _signature(*tensors):
+        return tuple((tuple(t.shape), t.dtype) for t in tensors)
+
     def _capture(self, x, target, mask):
+        self._graph = None                               # drop a previous capture (other input format) first
         self._static = tuple(t.clone() for t in (x, target, mask))
+        self._sig = self._signature(x, target, mask)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                    # warm-up on a side stream (allocator, lazy inits, autotune-free)
@@ -90,7 +97,9 @@ class Trainer:
     def step(self, x, target, mask):
         if not self.use_graph:
             return self._eager_step(x, target, mask)
-        if self._graph is None or self._captured_warmup != self.warmup:     # the warm-up branch is baked into a capture
+        # the warm-up branch and the input format (one-hot float64 target or uint8 label map, batch / crop size) are baked
+        # into a capture: re-capture when either changes
+        if self._graph is None or self._captured_warmup != self.warmup or self._sig != self._signature(x, target, mask):
             self._capture(x, target, mask)
         for dst, src in zip(self._static, (x, target, mask)):
             dst.copy_(src, non_blocking=True)

@@ -7,12 +7,15 @@
 One process per GPU (torchrun) replaces torch.nn.DataParallel (train.py:90).  Per iteration the work is
 passion_b200.engine.Trainer.step (train.py:198-289); per epoch the LR schedule (lr_scheduler.py:15-17), the
 relative-preference update of imb_beta (train.py:325-335) and the reference-format checkpoint (train.py:358-364).
-Data: `<datasetPath>/vol/*_vol.npy` + `seg/*_seg.npy` with a random 80^3 crop (the numpy/scipy augmentation
-pipeline of the reference is CPU code outside this hot path), or --synthetic.
+Data: `<datasetPath>/vol/*_vol.npy` + `seg/*_seg.npy` with a random 80^3 crop on the host, or --synthetic; with
+--device_aug the cases stay resident in HBM and the reference's whole transform chain (options.py:50: crop, rotation,
+intensity change, flips) plus the label encoding run as one kernel per batch, bit-exact against the numpy / scipy
+original (passion_b200/data.py).
 """
 import csv
 import logging
 import os
+import random
 import time
 
 import numpy as np
@@ -20,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from options import args_parser
+from passion_b200.data import AugmentSampler, DeviceAugment, ResidentCases
 from passion_b200.engine import DevicePrefetcher, Trainer
 from passion_b200.models import build_model
 from passion_b200.train_step import poly_lr, preference_update
@@ -73,6 +77,38 @@ class Source:
                 torch.from_numpy(np.stack(ms)))
 
 
+class ResidentSource(Source):
+    """--device_aug: yields DEVICE batches (x f32 [B,4,S,S,S], labels uint8 [B,S,S,S], mask bool [B,4]).  The cases live in
+    HBM; per step the host draws the transform parameters in the reference's order and sends ~10 KB."""
+
+    def __init__(self, args, rows, rank, world, dev):
+        super().__init__(args, rows, rank, world)
+        self.dev = dev
+        S = args.crop_size
+        self.cases = ResidentCases(dev)
+        if args.synthetic:
+            for i in range(4):
+                self.cases.add(self.rs.standard_normal((S + 40, S + 40, S + 24, 4)).astype(np.float32),
+                               self.rs.randint(0, 4, (S + 40, S + 40, S + 24)).astype(np.uint8))
+        else:
+            self.cases.add_files(args.datasetPath, [r['data_name'] for r in rows])
+        logging.info('%d cases resident in HBM (%.1f GB)', len(self.cases), self.cases.nbytes() / 1e9)
+        self.sampler = AugmentSampler((S, S, S), py_rng=random.Random(args.seed + rank), np_rng=np.random.RandomState(args.seed + rank))
+        self.aug = DeviceAugment(dev, size=(S, S, S), batch=args.batch_size)
+
+    def batch(self, it):
+        B = self.args.batch_size
+        ids, ps, ms = [], [], []
+        for b in range(B):
+            k = (it * self.world * B + self.rank * B + b) % len(self.rows)
+            cid = k % len(self.cases) if self.args.synthetic else k
+            ids.append(cid)
+            ps.append(self.sampler.sample(tuple(self.cases.vols[cid].shape[:3])))
+            ms.append(MASK_ARRAY[self._mask_id(self.rows[k])])
+        x, labels, _ = self.aug(self.cases, ids, ps)
+        return x, labels, torch.from_numpy(np.stack(ms)).to(self.dev)
+
+
 def main():
     args = args_parser()
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -95,7 +131,7 @@ def main():
     if not os.path.exists(csv_path):
         csv_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tests', 'golden', os.path.basename(args.imbmrpath))
     rows = read_split(csv_path)
-    src = Source(args, rows, rank, world)
+    src = ResidentSource(args, rows, rank, world, dev) if args.device_aug else Source(args, rows, rank, world)
     modal_num = torch.tensor(np.sum([eval(r['mask']) for r in rows], 0), dtype=torch.float32)      # train.py:163-166
     logging.info('Training Imperfect Datasets with Mod.Flair-%d, Mod.T1c-%d, Mod.T1-%d, Mod.T2-%d', *modal_num.int().tolist())
     iter_per_epoch = src.iters
@@ -117,11 +153,15 @@ def main():
         trainer.warmup = epoch < args.region_fusion_start_epoch
         acc = torch.zeros(4, device=dev)
         t0 = time.time()
-        feed = DevicePrefetcher((tuple(t.pin_memory() for t in src.batch(epoch * iter_per_epoch + i))
-                                 for i in range(iter_per_epoch)), dev)            # H2D of batch i+1 overlaps step i
+        if args.device_aug:
+            feed = (src.batch(epoch * iter_per_epoch + i) for i in range(iter_per_epoch))
+        else:
+            feed = DevicePrefetcher((tuple(t.pin_memory() for t in src.batch(epoch * iter_per_epoch + i))
+                                     for i in range(iter_per_epoch)), dev)        # H2D of batch i+1 overlaps step i
         for i, batch in enumerate(feed):
             loss, parts = trainer.step(*batch)
-            feed.release(batch)
+            if not args.device_aug:
+                feed.release(batch)
             dist_m = parts['dist_m'].clone()
             if world > 1:
                 dist.all_reduce(dist_m)
