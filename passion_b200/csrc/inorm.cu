@@ -3,8 +3,11 @@
 // Replaces reference models/blocks.py:18 (nn.InstanceNorm3d), :363 (LeakyReLU) and the encoder
 // residual adds models/rfnet.py:37,40,43,46.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
+
+constexpr int kDefaultInormOrder = 5;     // measured: 24.45 (0) -> 24.32 ms/step (5); 1, 4, 2, 3, 7 in between
 
 __global__ void finalize_kernel(const double* __restrict__ stats, float* __restrict__ mr, int nc, double inv_v, float eps) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,34 +63,76 @@ __device__ __forceinline__ void block_finish(const double* s1, const double* s2,
     }
 }
 
-// out = lrelu((y - mean) * rstd) (+ res);  one thread = VEC channels of one voxel, two independent vectors per
-// iteration (all loads are issued before the first use, doubling the bytes in flight per thread)
-template <typename T, int VEC>
+// Traversal order of the streaming passes.  Consecutive kernels of the step sweep the same 65-82 MB tensors; a pass that
+// walks its tensor in the OPPOSITE direction of the pass before it starts on the data that pass touched last, i.e. on what
+// is still resident in the 126 MB L2.  PB_INORM_ORDER is a bit mask: 1 = forward apply reversed, 2 = backward reduce
+// reversed, 4 = backward apply reversed (default chosen by measurement).
+int inorm_order() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PB_INORM_ORDER");
+        v = e ? atoi(e) : kDefaultInormOrder;
+    }
+    return v;
+}
+
+// Voxel walk shared by the passes: grid = (blocks per sample, n); a thread owns VEC channels (c0) and visits the voxels
+// first + k * stride, k = 0..K-1 — in increasing order, or (rev) blocks, samples and k all in decreasing order.
+struct Walk {
+    int n, first, stride, K;                                  // voxels per sample < 2^31 (checked by the host wrappers)
+    __device__ __forceinline__ Walk(long long voxels, int vpb, int vl, bool rev) {
+        n = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+        const int bx = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+        stride = (int)gridDim.x * vpb;
+        first = bx * vpb + vl;
+        K = first < (int)voxels ? ((int)voxels - 1 - first) / stride + 1 : 0;
+    }
+    // voxel of the it-th visit (it < K)
+    __device__ __forceinline__ long long at(int it, bool rev) const { return first + (long long)(rev ? K - 1 - it : it) * stride; }
+};
+
+// out = lrelu((y - mean) * rstd) (+ res).  One thread = VEC channels of one voxel lane with its mean / rstd in registers
+// (the first version recomputed sample and channel with two 64-bit divisions per vector and fetched the statistics from
+// memory per element: 158 instructions per 16-byte vector, issue-bound at 4.0 TB/s); four independent vectors in flight.
+template <typename T, int VEC, bool RES>
 __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ mr,
                                                         const T* __restrict__ res, T* __restrict__ out,
-                                                        long long total_vec, long long vox_c, int c, float slope) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += 2 * stride) {
-        const long long i2 = i + stride;
-        const bool has2 = i2 < total_vec;
-        const long long e = i * VEC, e2 = (has2 ? i2 : i) * VEC;
-        float v[VEC], r[VEC], v2[VEC], r2[VEC];
-        VecIO<T, VEC>::load(y + e, v);
-        VecIO<T, VEC>::load(y + e2, v2);
-        if (res) { VecIO<T, VEC>::load(res + e, r); VecIO<T, VEC>::load(res + e2, r2); }
-        const float* m = mr + ((size_t)(e / vox_c) * c + (int)(e % c)) * 2;
-        const float* m2 = mr + ((size_t)(e2 / vox_c) * c + (int)(e2 % c)) * 2;
+                                                        long long voxels, int c, float slope, int rev) {
+    constexpr int UNR = 4;
+    const int lanes = c / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
+    if ((int)threadIdx.x >= tpb) return;
+    const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
+    const int c0 = cl * VEC;
+    const Walk wk(voxels, vpb, vl, rev != 0);
+    float mean[VEC], rstd[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            float xh = (v[j] - m[2 * j]) * m[2 * j + 1];
-            xh = xh > 0.f ? xh : xh * slope;
-            v[j] = res ? xh + r[j] : xh;
-            float xg = (v2[j] - m2[2 * j]) * m2[2 * j + 1];
-            xg = xg > 0.f ? xg : xg * slope;
-            v2[j] = res ? xg + r2[j] : xg;
+    for (int j = 0; j < VEC; ++j) {
+        mean[j] = mr[((size_t)wk.n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)wk.n * c + c0 + j) * 2 + 1];
+    }
+    const size_t base = (size_t)wk.n * voxels * c + c0;
+    for (int it = 0; it < wk.K; it += UNR) {
+        float v[UNR][VEC], r[RES ? UNR : 1][VEC];
+        size_t off[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int k = it + u < wk.K ? it + u : it;                // tail: re-load the first vector, its store is skipped
+            off[u] = base + (size_t)wk.at(k, rev != 0) * c;
+            VecIO<T, VEC>::load(y + off[u], v[u]);
         }
-        VecIO<T, VEC>::store(out + e, v);
-        if (has2) VecIO<T, VEC>::store(out + e2, v2);
+        if (RES) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) VecIO<T, VEC>::load(res + off[u], r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float xh = (v[u][j] - mean[j]) * rstd[j];
+                xh = xh > 0.f ? xh : xh * slope;
+                v[u][j] = RES ? xh + r[RES ? u : 0][j] : xh;
+            }
+            if (it + u < wk.K) VecIO<T, VEC>::store(out + off[u], v[u]);
+        }
     }
 }
 
@@ -146,17 +191,18 @@ constexpr int kRun = 4;
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                          const float* __restrict__ mr, double* __restrict__ sums,
-                                                         long long voxels, int c, float slope) {
+                                                         long long voxels, int c, float slope, int rev) {
     constexpr bool kExact = sizeof(T) == 4;
     constexpr int RUN = (sizeof(T) == 2 && VEC == 8) ? 2 : kRun;   // keeps the bf16 x8 variant at 3 CTAs per SM without spills
     extern __shared__ double ssum[];                          // [vpb][2*c]
-    const int n = blockIdx.y;
     const int lanes = c / VEC;                                // threads per voxel
     const int tpb = (256 / lanes) * lanes;                    // active threads
     const int vpb = tpb / lanes;                              // voxels per block-iteration
     const bool active = (int)threadIdx.x < tpb;
     const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
     const int c0 = cl * VEC;
+    const Walk wk(voxels, vpb, vl, rev != 0);
+    const int n = wk.n;
     double sg[VEC], sgx[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { sg[j] = 0.0; sgx[j] = 0.0; }
@@ -168,16 +214,15 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bwd_reduce_kernel
         }
         const T* dn = dout + (size_t)n * voxels * c + c0;
         const T* yn = y + (size_t)n * voxels * c + c0;
-        const long long stride = (long long)gridDim.x * vpb;
         float fg[VEC], fgx[VEC];                               // bf16 mode: a thread sums a few dozen voxels, fp32 is ample
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { fg[j] = 0.f; fgx[j] = 0.f; }
-        for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * RUN) {
+        for (int it = 0; it < wk.K; it += RUN) {
             float g[RUN][VEC], yv[RUN][VEC];
 #pragma unroll
             for (int u = 0; u < RUN; ++u) {                  // all loads of the run are in flight together
-                const long long v = v0 + u * stride;
-                if (v < voxels) {
+                if (it + u < wk.K) {
+                    const long long v = wk.at(it + u, rev != 0);
                     VecIO<T, VEC>::load(dn + v * c, g[u]);
                     VecIO<T, VEC>::load(yn + v * c, yv[u]);
                 } else {
@@ -222,13 +267,15 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bwd_reduce_kernel
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                         const float* __restrict__ mr, const double* __restrict__ sums,
-                                                        T* __restrict__ dy, long long voxels, int c, double inv_v, float slope) {
+                                                        T* __restrict__ dy, long long voxels, int c, double inv_v, float slope,
+                                                        int rev) {
     constexpr bool kExact = sizeof(T) == 4;
-    const int n = blockIdx.y;
     const int lanes = c / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
     if ((int)threadIdx.x >= tpb) return;
     const int cl = threadIdx.x % lanes, vl = threadIdx.x / lanes;
     const int c0 = cl * VEC;
+    const Walk wk(voxels, vpb, vl, rev != 0);
+    const int n = wk.n;
     float mean[VEC], rstd[VEC], af[VEC], bf[VEC];
     double ad[VEC], bd[VEC];
 #pragma unroll
@@ -238,10 +285,9 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ do
         af[j] = (float)ad[j]; bf[j] = (float)bd[j];
     }
     const size_t base = (size_t)n * voxels * c + c0;
-    const long long stride = (long long)gridDim.x * vpb;
-    for (long long v0 = (long long)blockIdx.x * vpb + vl; v0 < voxels; v0 += stride * 2) {
-        const long long v1 = v0 + stride;
-        const bool has1 = v1 < voxels;
+    for (int it = 0; it < wk.K; it += 2) {
+        const bool has1 = it + 1 < wk.K;
+        const long long v0 = wk.at(it, rev != 0), v1 = has1 ? wk.at(it + 1, rev != 0) : v0;
         float g[2][VEC], yv[2][VEC];
         VecIO<T, VEC>::load(dout + base + v0 * c, g[0]);
         VecIO<T, VEC>::load(y + base + v0 * c, yv[0]);
@@ -264,17 +310,19 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ do
     }
 }
 
-int grid_for(long long work, int per_block) {
-    long long b = (work + per_block - 1) / per_block;
-    const long long cap = 148LL * 16;
-    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
-}
-
 template <typename T, int VEC>
 int run_fwd(const void* y, const float* mr, const void* res, void* out, int n, long long voxels, int c, float slope, cudaStream_t st) {
-    const long long total_vec = (long long)n * voxels * c / VEC;
-    apply_fwd_kernel<T, VEC><<<grid_for(total_vec, 256), 256, 0, st>>>((const T*)y, mr, (const T*)res, (T*)out, total_vec,
-                                                                       voxels * c, c, slope);
+    const int lanes = c / VEC, vpb = 256 / lanes;
+    int bps = (int)((voxels + (long long)vpb * 8 - 1) / ((long long)vpb * 8));       // >= 8 voxels per thread
+    const int cap = (148 * 8 + n - 1) / n;
+    if (bps > cap) bps = cap;
+    if (bps < 1) bps = 1;
+    if (res)
+        apply_fwd_kernel<T, VEC, true><<<dim3(bps, n), 256, 0, st>>>((const T*)y, mr, (const T*)res, (T*)out, voxels, c, slope,
+                                                                     inorm_order() & 1);
+    else
+        apply_fwd_kernel<T, VEC, false><<<dim3(bps, n), 256, 0, st>>>((const T*)y, mr, nullptr, (T*)out, voxels, c, slope,
+                                                                      inorm_order() & 1);
     return 0;
 }
 
@@ -300,13 +348,14 @@ int run_bwd(const void* dout, const void* y, const float* mr, double* sums, void
         const int cap = (148 * 8 + nn - 1) / nn;
         if (bps > cap) bps = cap;
         if (bps < 1) bps = 1;
-        bwd_reduce_kernel<T, VEC><<<dim3(bps, nn), 256, (size_t)vpb * 2 * c * sizeof(double), st>>>(d_, y_, mr_, s_, voxels, c, slope);
+        bwd_reduce_kernel<T, VEC><<<dim3(bps, nn), 256, (size_t)vpb * 2 * c * sizeof(double), st>>>(d_, y_, mr_, s_, voxels, c, slope, inorm_order() & 2);
         pb_count_launch();
         int bpa = (int)((voxels + (long long)vpb * 4 - 1) / ((long long)vpb * 4));     // >= 4 voxels per thread
         const int capa = (148 * 16 + nn - 1) / nn;
         if (bpa > capa) bpa = capa;
         if (bpa < 1) bpa = 1;
-        bwd_apply_kernel<T, VEC><<<dim3(bpa, nn), 256, 0, st>>>(d_, y_, mr_, s_, o_, voxels, c, 1.0 / (double)voxels, slope);
+        bwd_apply_kernel<T, VEC><<<dim3(bpa, nn), 256, 0, st>>>(d_, y_, mr_, s_, o_, voxels, c, 1.0 / (double)voxels, slope,
+                                                              inorm_order() & 4);
         if (n0 + group < n) pb_count_launch();
     }
     return 0;
@@ -350,7 +399,8 @@ extern "C" int pb_channel_stats(int dtype, const void* x, double* stats, int n, 
 
 extern "C" int pb_inorm_lrelu_fwd(int dtype, const void* y, const float* mr, const void* res, void* out, int n,
                                   long long voxels, int c, float slope, pb_stream_t stream) {
-    PB_CHECK_ARG(y && mr && out && n > 0 && c > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(y && mr && out && n > 0 && c > 0 && voxels > 0 && voxels < (1LL << 31), "bad argument");
+    PB_CHECK_ARG(c <= 256 * pb_vec_width(c), "too many channels");
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_F(T, V) run_fwd<T, V>(y, mr, res, out, n, voxels, c, slope, st)
     if (dtype == PB_BF16) { VEC_SWITCH(bf16, c, CALL_F) } else { VEC_SWITCH(float, c, CALL_F) }
@@ -361,7 +411,7 @@ extern "C" int pb_inorm_lrelu_fwd(int dtype, const void* y, const float* mr, con
 
 extern "C" int pb_inorm_lrelu_bwd(int dtype, const void* dout, const void* y, const float* mr, double* sums, void* dy, int n,
                                   long long voxels, int c, float slope, pb_stream_t stream) {
-    PB_CHECK_ARG(dout && y && mr && sums && dy && n > 0 && c > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(dout && y && mr && sums && dy && n > 0 && c > 0 && voxels > 0 && voxels < (1LL << 31), "bad argument");
     PB_CHECK_ARG(c <= 256 * pb_vec_width(c), "too many channels");
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_B(T, V) run_bwd<T, V>(dout, y, mr, sums, dy, n, voxels, c, slope, st)

@@ -193,7 +193,7 @@ def test_masked_stack(lib_built, C, P, B, shape, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("c,shape,with_res", [(8, (12, 10, 14), True), (16, (6, 7, 8), False), (2, (8, 8, 8), False),
                                               (4, (5, 5, 5), True), (64, (2, 2, 2), False), (32, (4, 5, 6), True),
-                                              (1, (6, 6, 6), False)])
+                                              (1, (6, 6, 6), False), (8, (40, 44, 36), True), (16, (30, 20, 28), False)])
 def test_inorm_lrelu(lib_built, c, shape, with_res, dtype):
     from passion_b200 import ops
     g = torch.Generator().manual_seed(c * 131 + shape[0])
