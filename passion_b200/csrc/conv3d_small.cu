@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kTQ) conv3_small_fwd_kernel(SmK p, const T* __
 // dw[g][tap][ci][co] += sum_v x[v + tap - 1][ci] * dy[v][co].  grid = (ctas, 3 / KDS, groups); a CTA owns the taps with
 // kd in [kd0, kd0 + KDS) and strides over the tiles of its group.
 template <typename T, int CIN, int COUT, int KDS>
-__global__ void __launch_bounds__(kTQ, 1) conv3_small_wgrad_kernel(SmK p, const T* __restrict__ x, const T* __restrict__ dy,
-                                                                   float* __restrict__ dw) {
+__global__ void __launch_bounds__(kTQ, (KDS * 9 * CIN * COUT <= 80) ? 2 : 1)
+conv3_small_wgrad_kernel(SmK p, const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw) {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;                                         // [kTD+2][rows][W+2][CIN]
     constexpr int NACC = KDS * 9 * CIN * COUT;
@@ -196,36 +196,46 @@ __global__ void __launch_bounds__(kTQ, 1) conv3_small_wgrad_kernel(SmK p, const 
         const int q = q0 + threadIdx.x;
         const bool valid = q < p.H * p.W;
         const int h = valid ? q / p.W : hb, wq = valid ? q - h * p.W : 0;
-        float g_[kTD][COUT];
+        // One output plane at a time, the next plane's dy vector already in flight: the accumulators plus two dy vectors
+        // fit 128 registers, so two CTAs share an SM (the version that held all kTD dy vectors ran one 8-warp CTA per SM
+        // and was bound by its own load -> sync -> compute latency chain: 0.41 ms for the 73 MB of the 1 -> 8 layer).
+        const T* dyp = dy + ((((size_t)n * p.D + d0) * p.H + h) * p.W + wq) * COUT;
+        const size_t plane = (size_t)p.H * p.W * COUT;
+        float gc[COUT], gn[COUT];
+        if (valid && d0 < p.D) VecIO<T, COUT>::load(dyp, gc);
+        else {
 #pragma unroll
-        for (int o = 0; o < kTD; ++o) {
-            const int d = d0 + o;
-            if (valid && d < p.D) VecIO<T, COUT>::load(dy + ((((size_t)n * p.D + d) * p.H + h) * p.W + wq) * COUT, g_[o]);
-            else {
-#pragma unroll
-                for (int j = 0; j < COUT; ++j) g_[o][j] = 0.f;
-            }
+            for (int j = 0; j < COUT; ++j) gc[j] = 0.f;
         }
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+        for (int o = 0; o < kTD; ++o) {
+            if (o + 1 < kTD) {
+                if (valid && d0 + o + 1 < p.D) VecIO<T, COUT>::load(dyp + (size_t)(o + 1) * plane, gn);
+                else {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float* tp = tile + ((size_t)(h - hb + kh) * WP + wq + kw) * CIN;
+                    for (int j = 0; j < COUT; ++j) gn[j] = 0.f;
+                }
+            }
 #pragma unroll
-                for (int k = 0; k < KDS; ++k) {
+            for (int k = 0; k < KDS; ++k)
 #pragma unroll
-                    for (int o = 0; o < kTD; ++o) {
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
                         float xv[CIN];
-                        lds_vecN<CIN>(tp + (size_t)(o + kd0 + k) * p.rows * WP * CIN, xv);
+                        lds_vecN<CIN>(tile + (((size_t)(o + kd0 + k) * p.rows + (h - hb + kh)) * WP + wq + kw) * CIN, xv);
 #pragma unroll
                         for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
                             for (int j = 0; j < COUT; ++j)
                                 acc[((k * 3 + kh) * 3 + kw) * CIN * COUT + ci * COUT + j] =
-                                    fmaf(xv[ci], g_[o][j], acc[((k * 3 + kh) * 3 + kw) * CIN * COUT + ci * COUT + j]);
+                                    fmaf(xv[ci], gc[j], acc[((k * 3 + kh) * 3 + kw) * CIN * COUT + ci * COUT + j]);
                     }
-                }
+            if (o + 1 < kTD) {
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) gc[j] = gn[j];
             }
+        }
     }
     // block reduction: shuffles inside the warps, the 8 warp totals through shared memory (reusing the tile buffer)
     __syncthreads();
