@@ -76,6 +76,30 @@ int inorm_order() {
     return v;
 }
 
+// A VEC-channel vector as it sits in memory: loads of several vectors are issued back to back in their packed form (one
+// register per two bf16 values) and unpacked to fp32 only when consumed, which doubles the bytes a thread keeps in flight
+// for the same register budget.
+template <typename T, int VEC> struct RawVec {
+    float v[VEC];
+    __device__ __forceinline__ void load(const T* p) { VecIO<T, VEC>::load(p, v); }
+    __device__ __forceinline__ void unpack(float* o) const {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = v[j];
+    }
+};
+template <> struct RawVec<bf16, 8> {
+    uint4 r;
+    __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void unpack(float* o) const {
+        bf2_unpack(r.x, o[0], o[1]); bf2_unpack(r.y, o[2], o[3]); bf2_unpack(r.z, o[4], o[5]); bf2_unpack(r.w, o[6], o[7]);
+    }
+};
+template <> struct RawVec<bf16, 4> {
+    uint2 r;
+    __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint2*>(p)); }
+    __device__ __forceinline__ void unpack(float* o) const { bf2_unpack(r.x, o[0], o[1]); bf2_unpack(r.y, o[2], o[3]); }
+};
+
 // Voxel walk shared by the passes: grid = (blocks per sample, n); a thread owns VEC channels (c0) and visits the voxels
 // first + k * stride, k = 0..K-1 — in increasing order, or (rev) blocks, samples and k all in decreasing order.
 struct Walk {
@@ -193,7 +217,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bwd_reduce_kernel
                                                          const float* __restrict__ mr, double* __restrict__ sums,
                                                          long long voxels, int c, float slope, int rev) {
     constexpr bool kExact = sizeof(T) == 4;
-    constexpr int RUN = (sizeof(T) == 2 && VEC == 8) ? 2 : kRun;   // keeps the bf16 x8 variant at 3 CTAs per SM without spills
+    constexpr int RUN = kRun;
     extern __shared__ double ssum[];                          // [vpb][2*c]
     const int lanes = c / VEC;                                // threads per voxel
     const int tpb = (256 / lanes) * lanes;                    // active threads
@@ -218,38 +242,30 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bwd_reduce_kernel
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { fg[j] = 0.f; fgx[j] = 0.f; }
         for (int it = 0; it < wk.K; it += RUN) {
-            float g[RUN][VEC], yv[RUN][VEC];
+            RawVec<T, VEC> rg[RUN], ry[RUN];
 #pragma unroll
-            for (int u = 0; u < RUN; ++u) {                  // all loads of the run are in flight together
-                if (it + u < wk.K) {
-                    const long long v = wk.at(it + u, rev != 0);
-                    VecIO<T, VEC>::load(dn + v * c, g[u]);
-                    VecIO<T, VEC>::load(yn + v * c, yv[u]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) { g[u][j] = 0.f; yv[u][j] = mean[j]; }
-                }
+            for (int u = 0; u < RUN; ++u) {                  // all loads of the run are in flight together, still packed
+                const long long v = wk.at(it + u < wk.K ? it + u : it, rev != 0);   // tail: a valid address, weight 0 below
+                rg[u].load(dn + v * c);
+                ry[u].load(yn + v * c);
             }
-            if (kExact) {
 #pragma unroll
-                for (int u = 0; u < RUN; ++u)
+            for (int u = 0; u < RUN; ++u) {
+                float g[VEC], yv[VEC];
+                rg[u].unpack(g); ry[u].unpack(yv);
+                const float live = it + u < wk.K ? 1.f : 0.f;
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const float xh = (yv[u][j] - mean[j]) * rstd[j];
-                        const float gg = xh > 0.f ? g[u][j] : g[u][j] * slope;
+                for (int j = 0; j < VEC; ++j) {
+                    const float xh = (yv[j] - mean[j]) * rstd[j];
+                    const float gg = (xh > 0.f ? g[j] : g[j] * slope) * live;
+                    if (kExact) {
                         sg[j] += (double)gg;
-                        sgx[j] += (double)gg * (((double)yv[u][j] - (double)mean[j]) * (double)rstd[j]);
-                    }
-            } else {
-#pragma unroll
-                for (int u = 0; u < RUN; ++u)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const float xh = (yv[u][j] - mean[j]) * rstd[j];
-                        const float gg = xh > 0.f ? g[u][j] : g[u][j] * slope;
+                        sgx[j] += (double)gg * (((double)yv[j] - (double)mean[j]) * (double)rstd[j]);
+                    } else {
                         fg[j] += gg;
                         fgx[j] = fmaf(gg, xh, fgx[j]);
                     }
+                }
             }
         }
         if (!kExact) {
