@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bwd_reduce_kernel
 // float64 from the float64 sums.  Under bf16 storage fp32 arithmetic is already ~2^15 finer than the operands.
 // Same thread -> channel mapping as the reduce pass, so the per-channel coefficients are loaded once per thread.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 1) bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y,
                                                         const float* __restrict__ mr, const double* __restrict__ sums,
                                                         T* __restrict__ dy, long long voxels, int c, double inv_v, float slope,
                                                         int rev) {
@@ -301,28 +301,33 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* __restrict__ do
         af[j] = (float)ad[j]; bf[j] = (float)bd[j];
     }
     const size_t base = (size_t)n * voxels * c + c0;
-    for (int it = 0; it < wk.K; it += 2) {
-        const bool has1 = it + 1 < wk.K;
-        const long long v0 = wk.at(it, rev != 0), v1 = has1 ? wk.at(it + 1, rev != 0) : v0;
-        float g[2][VEC], yv[2][VEC];
-        VecIO<T, VEC>::load(dout + base + v0 * c, g[0]);
-        VecIO<T, VEC>::load(y + base + v0 * c, yv[0]);
-        if (has1) { VecIO<T, VEC>::load(dout + base + v1 * c, g[1]); VecIO<T, VEC>::load(y + base + v1 * c, yv[1]); }
+    constexpr int RUN = sizeof(T) == 2 ? 3 : 2;                // packed bf16: three vector pairs in flight per thread, 3 CTAs per SM
+    for (int it = 0; it < wk.K; it += RUN) {
+        RawVec<T, VEC> rg[RUN], ry[RUN];
+        size_t off[RUN];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < RUN; ++u) {
+            off[u] = base + (size_t)wk.at(it + u < wk.K ? it + u : it, rev != 0) * c;      // tail: re-load, store skipped
+            rg[u].load(dout + off[u]);
+            ry[u].load(y + off[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < RUN; ++u) {
+            float g[VEC], yv[VEC];
+            rg[u].unpack(g); ry[u].unpack(yv);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const float xh = (yv[u][j] - mean[j]) * rstd[j];
-                const float gg = xh > 0.f ? g[u][j] : g[u][j] * slope;
+                const float xh = (yv[j] - mean[j]) * rstd[j];
+                const float gg = xh > 0.f ? g[j] : g[j] * slope;
                 if (kExact) {
-                    const double xd = ((double)yv[u][j] - (double)mean[j]) * (double)rstd[j];
-                    g[u][j] = (float)((double)rstd[j] * ((double)gg - ad[j] - xd * bd[j]));
+                    const double xd = ((double)yv[j] - (double)mean[j]) * (double)rstd[j];
+                    g[j] = (float)((double)rstd[j] * ((double)gg - ad[j] - xd * bd[j]));
                 } else {
-                    g[u][j] = rstd[j] * (gg - af[j] - xh * bf[j]);
+                    g[j] = rstd[j] * (gg - af[j] - xh * bf[j]);
                 }
             }
-        VecIO<T, VEC>::store(dy + base + v0 * c, g[0]);
-        if (has1) VecIO<T, VEC>::store(dy + base + v1 * c, g[1]);
+            if (it + u < wk.K) VecIO<T, VEC>::store(dy + off[u], g);
+        }
     }
 }
 
