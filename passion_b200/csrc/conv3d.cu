@@ -783,7 +783,11 @@ int launch_wgrad(const ConvK& k, WgK q, const void* x0, const void* x1, const vo
     if (int e = set_smem(kern, smem)) return e;
     const long long ntiles = (long long)k.npg * q.tiles_d * q.tiles_h * q.tiles_w;
     const int pairs = q.n_cic * q.n_coc;
-    long long nblk = (148LL * 3 + (long long)pairs * k.groups - 1) / ((long long)pairs * k.groups);
+    // persistent CTAs: exactly as many as are resident at once (registers / shared memory allow 2-3 per SM); 1.5 waves of
+    // 444 CTAs left every SM half idle for the last third of the kernel
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 2;
+    long long nblk = (148LL * occ) / ((long long)pairs * k.groups);
     if (nblk < 1) nblk = 1;
     if (nblk > ntiles) nblk = ntiles;
     dim3 grid((unsigned)nblk, pairs, k.groups);
