@@ -365,14 +365,19 @@ int run_bwd(const void* dout, const void* y, const float* mr, double* sums, void
         T* o_ = (T*)dy + eoff;
         const float* mr_ = mr + (size_t)n0 * c * 2;
         double* s_ = sums + (size_t)n0 * c * 2;
+        // grids are capped at whole waves of resident CTAs (the reduce pass ran 1184 CTAs on 444 slots: 2.67 waves)
+        const size_t rsmem = (size_t)vpb * 2 * c * sizeof(double);
+        static int occ_r = 0, occ_a = 0;                       // per template instantiation
+        if (!occ_r && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, bwd_reduce_kernel<T, VEC>, 256, rsmem) != cudaSuccess || occ_r < 1)) occ_r = 2;
+        if (!occ_a && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, bwd_apply_kernel<T, VEC>, 256, 0) != cudaSuccess || occ_a < 1)) occ_a = 2;
         int bps = (int)((voxels + (long long)vpb * 8 - 1) / ((long long)vpb * 8));   // >= 8 voxel-iterations per thread
-        const int cap = (148 * 8 + nn - 1) / nn;
+        const int cap = 148 * occ_r / nn;                      // one wave
         if (bps > cap) bps = cap;
         if (bps < 1) bps = 1;
-        bwd_reduce_kernel<T, VEC><<<dim3(bps, nn), 256, (size_t)vpb * 2 * c * sizeof(double), st>>>(d_, y_, mr_, s_, voxels, c, slope, inorm_order() & 2);
+        bwd_reduce_kernel<T, VEC><<<dim3(bps, nn), 256, rsmem, st>>>(d_, y_, mr_, s_, voxels, c, slope, inorm_order() & 2);
         pb_count_launch();
         int bpa = (int)((voxels + (long long)vpb * 4 - 1) / ((long long)vpb * 4));     // >= 4 voxels per thread
-        const int capa = (148 * 16 + nn - 1) / nn;
+        const int capa = 148 * occ_a * 2 / nn;                 // two waves
         if (bpa > capa) bpa = capa;
         if (bpa < 1) bpa = 1;
         bwd_apply_kernel<T, VEC><<<dim3(bpa, nn), 256, 0, st>>>(d_, y_, mr_, s_, o_, voxels, c, 1.0 / (double)voxels, slope,
