@@ -36,8 +36,8 @@ NCU_TRAFFIC_BYTES = {
     "conv3d_fwd_tc": {"class": "c16->8 k3 s1 80x80x80 n8 g1", "bytes": 131.29e6 + 40.21e6, "source": "profiles/r01_conv_tc_kdstack_metrics.txt"},
     "conv3d_dgrad_tc": {"class": "c16->8 k3 s1 80x80x80 n8 g1", "bytes": 131.29e6 + 40.21e6, "source": "profiles/r01_conv_tc_kdstack_metrics.txt"},
     "conv3d_wgrad_tc": {"class": "c16->8 k3 s1 80x80x80 n10 g1", "bytes": 245.90e6 + 5.17e6, "source": "profiles/r01_wgrad_tc8_3issuer_metrics.txt"},
-    "inorm_lrelu_bwd": {"class": "c8 (n8, 80^3): reduce pass 131.09e6 + 5.12e6, apply pass 131.08e6 + 38.28e6 (write-back partly deferred)",
-                        "bytes": 131.09e6 + 5.12e6 + 131.08e6 + 38.28e6, "source": "profiles/r01_inorm_bwd_metrics.txt"},
+    "inorm_lrelu_bwd": {"class": "c8 (n10, 80^3): reduce pass 163.86e6 + 4.24e6, apply pass 163.86e6 + 46.95e6 (write-back partly deferred)",
+                        "bytes": 163.86e6 + 4.24e6 + 163.86e6 + 46.95e6, "source": "profiles/r01_final_tuned_kernels_metrics.txt"},
 }
 
 
