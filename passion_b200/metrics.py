@@ -73,10 +73,12 @@ def evaluate_all_masks(model, x, target, patch_size=80, masks=None, mask_names=N
     from . import predict
     masks = predict.MASKS_TEST if masks is None else masks
     names = mask_names if mask_names is not None else [str(i) for i in range(len(masks))]
-    labels, _ = predict.predict_all_masks(model, x, masks, patch_size)
-    _, ev = dice_class4(labels, target.expand(labels.shape[0], *target.shape[1:]).to(labels.device))
-    # dice_class4's post-processing threshold is per CALL in the reference (batch 1, one mask per call): redo it per mask
-    cm = confusion_counts(labels, target.expand(labels.shape[0], *target.shape[1:]).to(labels.device))
-    keep = (cm.sum(2)[:, 3] >= POSTPRO_MIN_VOXELS).to(cm.dtype)
-    ev[:, 3] = _dice(cm[:, 3, 3] * keep, cm.sum(2)[:, 3] * keep, cm.sum(1)[:, 3])
-    return {names[i]: ev[i] for i in reversed(range(len(masks)))}
+    if hasattr(model, "_features") and getattr(model, "mask_type", "idt") != "pdt":
+        labels, _ = predict.predict_all_masks(model, x, masks, patch_size)             # shared-encoder sweep (RFNet)
+    else:                                                                              # one sliding-window pass per mask
+        labels = torch.cat([predict.predict_volume(model, x, torch.tensor([m], dtype=torch.bool, device=x.device), patch_size)[0]
+                            for m in masks])
+    tgt = target.expand(labels.shape[0], *target.shape[1:]).to(labels.device)
+    # the reference scores one mask per call (batch 1), so its < 500-voxel post-processing rule applies per mask
+    rows = [dice_class4(labels[i:i + 1], tgt[i:i + 1])[1][0] for i in range(labels.shape[0])]
+    return {names[i]: rows[i] for i in reversed(range(len(masks)))}

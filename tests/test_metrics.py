@@ -61,8 +61,60 @@ def test_evaluate_all_masks_scores_each_mask_like_a_separate_reference_call(monk
     maps[3][maps[3] == 3] = 0                                            # one mask predicts no enhancing tumour at all
     monkeypatch.setattr(predict, "predict_all_masks", lambda model, x, masks, patch: (torch.from_numpy(maps), None))
     names = [f"m{i}" for i in range(15)]
-    res = metrics.evaluate_all_masks(None, None, torch.from_numpy(target), mask_names=names)
+    class SharedEncoderModel:                                            # has the shared-encoder API -> predict_all_masks
+        mask_type = "idt"
+
+        def _features(self):
+            pass
+    res = metrics.evaluate_all_masks(SharedEncoderModel(), None, torch.from_numpy(target), mask_names=names)
     assert list(res) == names[::-1]
     for i, n in enumerate(names):
         _, ev = metrics.dice_class4(torch.from_numpy(maps[i:i + 1]), torch.from_numpy(target))
         assert torch.equal(res[n], ev[0])
+
+
+def test_evaluate_all_masks_falls_back_to_one_sweep_per_mask(monkeypatch):
+    """A model without the shared-encoder API (mmFormer) is scored through predict_volume, one mask at a time."""
+    from passion_b200 import predict
+    rs = np.random.RandomState(1)
+    shape = (8, 8, 8)
+    target = rs.randint(0, 4, (1,) + shape)
+    calls = []
+
+    def fake_volume(model, x, mask, patch):
+        calls.append(mask.tolist())
+        return torch.from_numpy(rs.randint(0, 4, (1,) + shape)), None
+    monkeypatch.setattr(predict, "predict_volume", fake_volume)
+    res = metrics.evaluate_all_masks(object(), torch.zeros(1), torch.from_numpy(target))
+    assert len(calls) == 15 and calls[0] == [predict.MASKS_TEST[0]] and len(res) == 15
+
+
+def test_eval_report_layout(tmp_path):
+    """eval.py writes the reference's CSV (header, masks in reversed table order, one row per case) and averages like
+    the reference's nested AverageMeters (mean over the cases per mask, then mean over the masks)."""
+    import csv
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("pb_eval", os.path.join(os.path.dirname(os.path.dirname(__file__)), "eval.py"))
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    rs = np.random.RandomState(0)
+    names = ["caseA", "caseB", "caseC"]
+    scores = {m: rs.rand(3, 4).astype(np.float32) for m in ev.MASK_NAME}
+    path = str(tmp_path / "report.csv")
+    per_mask, overall = ev.write_report(path, names, scores)
+    rows = list(csv.reader(open(path)))
+    assert rows[0][:4] == ["WT Dice", "TC Dice", "ET Dice", "ETPro Dice"] and len(rows) == 1 + 15 * 4
+    assert rows[1] == ["flairt1cet1t2"] and rows[5] == ["t1cet1t2"] and rows[-4] == ["t2"]
+    assert np.allclose([float(v) for v in rows[2][:4]], scores["flairt1cet1t2"][0]) and rows[2][4:] == [""] * 4
+    meter = metrics.AverageMeter()
+    for m in ev.MASK_NAME[::-1]:
+        inner = metrics.AverageMeter()
+        for k in range(3):
+            inner.update(scores[m][k].astype(np.float64))
+        assert np.allclose(inner.avg, per_mask[m])
+        meter.update(inner.avg)
+    assert np.allclose(meter.avg, overall)
+    args = ev.args_parser(["--model", "rfnet_passion", "--synthetic", "2"])
+    cases = list(ev.test_cases(args))
+    assert len(cases) == 2 and cases[0][1].shape == (1, 4, 96, 96, 88) and cases[0][2].dtype == np.uint8
