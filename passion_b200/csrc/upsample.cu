@@ -224,7 +224,7 @@ int run(const void* a, void* b, int n, int d, int h, int w, int c, int scale, cu
             // fp32 = check mode: the point-wise kernel, whose 8-corner summation order is the one the check-mode parity
             // runs were validated with.  The network's gradient is not continuous in round-off (LeakyReLU kinks behind
             // InstanceNorms over as few as 8 voxels): another fp32 summation order here moved single encoder gradients of
-            // the mmFormer fixture by percents (oracle study: DESIGN.md §2), so the bit pattern of this path is kept stable.
+            // the mmFormer fixture by percents (tests/study_grad_discontinuity.py), so the bit pattern of this path is kept stable.
             const long long plane_vec = (long long)h * scale * w * scale * (c / VEC);
             long long bx = (plane_vec + 255) / 256;
             if (bx > 1024) bx = 1024;
