@@ -9,6 +9,7 @@
 // padding_mode='reflect', the torch.cat feeding decoder convs (models/rfnet.py:75,79,83,133,139,145)
 // and the four separate modality encoders (models/rfnet.py:234-237) as weight groups.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -183,6 +184,94 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(PwK p, const T* __restrict
             for (int i = 0; i < CI_V; ++i) {
                 float wv[CO_T];
                 lds_vec<CO_T>(wsm + (p.C0 + c + i) * CO_T, wv);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                    for (int j = 0; j < CO_T; ++j) acc[u][j] = fmaf(xv[u][i], wv[j], acc[u][j]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long v = v0 + u * stride;
+            if (v < p.V) {
+                const size_t vox = (size_t)n * p.V + v;
+                T* dst = co0 < p.CO0 ? y0 + vox * p.CO0 + co0 : y1 + vox * p.CO1 + (co0 - p.CO0);
+                VecIO<T, CO_T>::store(dst, acc[u]);
+#pragma unroll
+                for (int j = 0; j < CO_T; ++j) { s1[j] += acc[u][j]; s2[j] += acc[u][j] * acc[u][j]; }
+            }
+        }
+    }
+    if (stats) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) {
+            const float s = warp_sum(s1[j]), q = warp_sum(s2[j]);
+            if (lane == 0) { red[wid][2 * j] = s; red[wid][2 * j + 1] = q; }
+        }
+        __syncthreads();
+        if (threadIdx.x < CO_T * 2) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += (double)red[k][threadIdx.x];
+            atomicAdd(&stats[((size_t)n * p.Cout + co0 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1)], v);
+        }
+    }
+}
+
+// EXPERIMENTAL (off unless PB_PW2=1; bf16 only; not yet run on a B200 — round-2 candidate, see DESIGN.md §4 "remaining levers").
+// Same operation and thread mapping as pw_conv_kernel, built for more bytes in flight: the channel-chunk counts of the two
+// sources are template parameters, so a thread first issues ALL the 16-byte loads of its UNR voxels (packed: one register
+// per two bf16 values) and only then unpacks chunk by chunk.  ncu on pw_conv_kernel: 127 registers -> two CTAs per SM with
+// 2-4 loads per thread in flight (16-32 KB per SM), 2.5-3.5 TB/s.
+template <typename T, int CO_T, int NCH0, int NCH1, int UNR, int MINB>
+__global__ void __launch_bounds__(256, MINB) pw_conv2_kernel(PwK p, const T* __restrict__ x0, const T* __restrict__ x1,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             T* __restrict__ y0, T* __restrict__ y1, double* __restrict__ stats) {
+    constexpr int CI_V = 8;
+    extern __shared__ __align__(16) float wsm[];              // [Cin][CO_T]
+    __shared__ float red[8][CO_T * 2];
+    __shared__ float bsm[CO_T];
+    const int n = blockIdx.z, coc = blockIdx.y, g = n / p.npg;
+    const float* wg = w + (size_t)g * p.Cin * p.Cout + coc * CO_T;
+    for (int i = threadIdx.x; i < p.Cin * CO_T; i += 256) wsm[i] = wg[(size_t)(i / CO_T) * p.Cout + (i % CO_T)];
+    if (threadIdx.x < CO_T) bsm[threadIdx.x] = bias ? bias[(size_t)g * p.Cout + coc * CO_T + threadIdx.x] : 0.f;
+    __syncthreads();
+    float s1[CO_T], s2[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    const long long stride = (long long)gridDim.x * 256;
+    const int co0 = coc * CO_T;
+    const T* xs0 = x0 + (size_t)n * p.V * (NCH0 * CI_V);
+    const T* xs1 = NCH1 ? x1 + (size_t)n * p.V * (NCH1 * CI_V) : nullptr;
+    for (long long v0 = (long long)blockIdx.x * 256 + threadIdx.x; v0 < p.V; v0 += stride * UNR) {
+        RawVec<T, CI_V> r0[UNR][NCH0], r1[UNR][NCH1 ? NCH1 : 1];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long v = v0 + u * stride;
+            const long long vv = v < p.V ? v : v0;            // tail: recompute voxel v0, the store is skipped
+#pragma unroll
+            for (int k = 0; k < NCH0; ++k) r0[u][k].load(xs0 + vv * (NCH0 * CI_V) + k * CI_V);
+#pragma unroll
+            for (int k = 0; k < NCH1; ++k) r1[u][k].load(xs1 + vv * (NCH1 * CI_V) + k * CI_V);
+        }
+        float acc[UNR][CO_T];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) acc[u][j] = bsm[j];
+#pragma unroll
+        for (int k = 0; k < NCH0 + NCH1; ++k) {
+            float xv[UNR][CI_V];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (k < NCH0) r0[u][k < NCH0 ? k : 0].unpack(xv[u]);
+                else r1[u][k >= NCH0 ? k - NCH0 : 0].unpack(xv[u]);
+            }
+#pragma unroll
+            for (int i = 0; i < CI_V; ++i) {
+                float wv[CO_T];
+                lds_vec<CO_T>(wsm + (k * CI_V + i) * CO_T, wv);
 #pragma unroll
                 for (int u = 0; u < UNR; ++u)
 #pragma unroll
@@ -681,6 +770,44 @@ int dispatch_pw_co(int co_t, const PwK& p, const void* x0, const void* x1, const
     }
 }
 
+template <int CO_T, int NCH0, int NCH1>
+int launch_pw2(const PwK& p, const void* x0, const void* x1, const float* w, const float* bias, void* y0, void* y1, double* stats,
+               cudaStream_t st) {
+    constexpr int NCH = NCH0 + NCH1;
+    // register budgets checked with ptxas -v: no spills at 80 registers (3 CTAs/SM) for CO_T <= 8, 128 (2 CTAs/SM) for CO_T = 16
+    constexpr int UNR = (CO_T >= 8 || NCH >= 4) ? 2 : 4;
+    constexpr int MINB = CO_T >= 16 ? 2 : 3;
+    const size_t smem = (size_t)p.Cin * CO_T * sizeof(float);
+    auto kern = pw_conv2_kernel<bf16, CO_T, NCH0, NCH1, UNR, MINB>;
+    if (int e = set_smem(kern, smem)) return e;
+    const int chunks = p.Cout / CO_T;
+    long long bx = (p.V + 256LL * UNR - 1) / (256LL * UNR);
+    const long long cap = (148LL * MINB * 2) / ((long long)p.N * chunks);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    kern<<<dim3((unsigned)bx, chunks, p.N), 256, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, w, bias, (bf16*)y0, (bf16*)y1, stats);
+    return 0;
+}
+
+// PB_PW2=1: route the bf16 classes the experimental kernel was instantiated for to it (returns -1 when the class is not covered)
+template <int CO_T>
+int dispatch_pw2(const PwK& p, const void* x0, const void* x1, const float* w, const float* bias, void* y0, void* y1, double* stats,
+                 cudaStream_t st) {
+    const int a = p.C0 / 8, b = p.C1 / 8;
+    if (a == 1 && b == 0) return launch_pw2<CO_T, 1, 0>(p, x0, x1, w, bias, y0, y1, stats, st);
+    if (a == 2 && b == 0) return launch_pw2<CO_T, 2, 0>(p, x0, x1, w, bias, y0, y1, stats, st);
+    if (a == 4 && b == 0) return launch_pw2<CO_T, 4, 0>(p, x0, x1, w, bias, y0, y1, stats, st);
+    if (a == 1 && b == 1) return launch_pw2<CO_T, 1, 1>(p, x0, x1, w, bias, y0, y1, stats, st);
+    if (a == 2 && b == 2) return launch_pw2<CO_T, 2, 2>(p, x0, x1, w, bias, y0, y1, stats, st);
+    return -1;
+}
+
+bool pw2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PB_PW2"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 // p.C0|C1 = input split, p.CO0|CO1 = output split
 template <typename T>
 int dispatch_pw(const PwK& p, const void* x0, const void* x1, const float* w, const float* bias, void* y0, void* y1,
@@ -691,6 +818,13 @@ int dispatch_pw(const PwK& p, const void* x0, const void* x1, const float* w, co
     if (p.CO1) co_t = chunk_of(p.CO1, co_t);
     // small volumes (deep levels): narrower Cout tiles give more CTAs; x is re-read from L2, which is cheap at these sizes
     while (co_t > 4 && ((p.V + 511) / 512) * (p.Cout / co_t) * p.N < 148) co_t >>= 1;
+    if (sizeof(T) == 2 && ci_v == 8 && pw2_enabled()) {
+        int e = -1;
+        if (co_t == 16) e = dispatch_pw2<16>(p, x0, x1, w, bias, y0, y1, stats, st);
+        else if (co_t == 8) e = dispatch_pw2<8>(p, x0, x1, w, bias, y0, y1, stats, st);
+        else if (co_t == 4) e = dispatch_pw2<4>(p, x0, x1, w, bias, y0, y1, stats, st);
+        if (e >= 0) return e;
+    }
     switch (ci_v) {
         case 8:  return dispatch_pw_co<T, 8>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);
         case 4:  return dispatch_pw_co<T, 4>(co_t, p, x0, x1, w, bias, y0, y1, stats, st);

@@ -76,30 +76,6 @@ int inorm_order() {
     return v;
 }
 
-// A VEC-channel vector as it sits in memory: loads of several vectors are issued back to back in their packed form (one
-// register per two bf16 values) and unpacked to fp32 only when consumed, which doubles the bytes a thread keeps in flight
-// for the same register budget.
-template <typename T, int VEC> struct RawVec {
-    float v[VEC];
-    __device__ __forceinline__ void load(const T* p) { VecIO<T, VEC>::load(p, v); }
-    __device__ __forceinline__ void unpack(float* o) const {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) o[j] = v[j];
-    }
-};
-template <> struct RawVec<bf16, 8> {
-    uint4 r;
-    __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
-    __device__ __forceinline__ void unpack(float* o) const {
-        bf2_unpack(r.x, o[0], o[1]); bf2_unpack(r.y, o[2], o[3]); bf2_unpack(r.z, o[4], o[5]); bf2_unpack(r.w, o[6], o[7]);
-    }
-};
-template <> struct RawVec<bf16, 4> {
-    uint2 r;
-    __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint2*>(p)); }
-    __device__ __forceinline__ void unpack(float* o) const { bf2_unpack(r.x, o[0], o[1]); bf2_unpack(r.y, o[2], o[3]); }
-};
-
 // Voxel walk shared by the passes: grid = (blocks per sample, n); a thread owns VEC channels (c0) and visits the voxels
 // first + k * stride, k = 0..K-1 — in increasing order, or (rev) blocks, samples and k all in decreasing order.
 struct Walk {
