@@ -2,6 +2,7 @@
 // Replaces nn.Upsample(scale_factor=s, mode='trilinear', align_corners=True)
 // (reference models/rfnet.py:54,59,64,110-112).  Index arithmetic mirrors ATen's
 // area_pixel_compute_source_index for align_corners: src = dst * (in-1)/(out-1) in float.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -220,11 +221,8 @@ int run(const void* a, void* b, int n, int d, int h, int w, int c, int scale, cu
     if (blocks < 1) blocks = 1;
     if (FWD) {
         const long long planes = (long long)n * d * scale;
-        if (sizeof(T) == 4) {
-            // fp32 = check mode: the point-wise kernel, whose 8-corner summation order is the one the check-mode parity
-            // runs were validated with.  The network's gradient is not continuous in round-off (LeakyReLU kinks behind
-            // InstanceNorms over as few as 8 voxels): another fp32 summation order here moved single encoder gradients of
-            // the mmFormer fixture by percents (tests/study_grad_discontinuity.py), so the bit pattern of this path is kept stable.
+        static const bool point = [] { const char* e = getenv("PB_UP_POINT"); return e != nullptr && e[0] == '1'; }();
+        if (point) {                                                 // one output vector per thread (kept for A/B measurements)
             const long long plane_vec = (long long)h * scale * w * scale * (c / VEC);
             long long bx = (plane_vec + 255) / 256;
             if (bx > 1024) bx = 1024;

@@ -368,6 +368,7 @@ class Model(nn.Module):
             main = torch.cuda.current_stream(dev)
             side = _rf._side_stream(dev)
             side.wait_stream(main)
+            _rf._lend_to_stream(feat, side)              # `feat` is referenced by nothing but decoder_sep's saved tensors
             with torch.cuda.stream(side):
                 sep_logits = self.decoder_sep.run(*feat)
                 sep_logits.record_stream(main)

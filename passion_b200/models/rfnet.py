@@ -31,6 +31,7 @@ from .. import ops
 basic_dims = 8
 num_modals = 4
 SEP_STREAM = os.environ.get("PB_SEP_STREAM", "1") != "0"     # run decoder_sep concurrently with decoder_fuse (measured: -0.9 ms/step)
+SIDE_RECORD = os.environ.get("PB_SIDE_RECORD", "1") != "0"   # debugging switch for _lend_to_stream (keep on)
 _side = {}
 
 
@@ -39,6 +40,21 @@ def _side_stream(device):
     if st is None:
         st = _side[device] = torch.cuda.Stream(device=device)
     return st
+
+
+def _lend_to_stream(tensors, stream):
+    """Tensors allocated on the current stream are about to be read by kernels on `stream`, forward AND (as tensors saved
+    for backward) by the backward of those ops, which autograd replays on `stream` too.  The caching allocator only knows
+    the allocating stream: without this, a block whose last reference dies while a side-stream kernel is still reading it
+    goes straight back to the main stream's pool and the next main-stream allocation overwrites it (the round-1 mmFormer
+    t1_encoder gradient error: the masked level features were only referenced by decoder_sep's saved tensors)."""
+    if not SIDE_RECORD:
+        return
+    for t in tensors:
+        if isinstance(t, (tuple, list)):
+            _lend_to_stream(t, stream)
+        elif isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(stream)
 
 
 class general_conv3d(nn.Module):
@@ -332,6 +348,7 @@ class Model(nn.Module):
             main = torch.cuda.current_stream(x.device)
             side = _side_stream(x.device)
             side.wait_stream(main)
+            _lend_to_stream(enc, side)
             with torch.cuda.stream(side):
                 sep_logits = self.decoder_sep.run(*enc)
                 sep_logits.record_stream(main)
