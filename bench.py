@@ -125,6 +125,13 @@ def synth_host_batches(rank, n_batches, B, S):
     return out
 
 
+def workload_config(model, B, S, world):
+    """The `config` block, identical in both arms (the driver compares them)."""
+    label = {"rfnet": "RFNet", "mmformer": "mmFormer"}[model]
+    return {"workload": f"{label}+PASSION train step, B={B}/GPU, 4x{S}^3 crops, idt masks from mr2468, temp 4, AdamW amsgrad",
+            "global_batch": B * world, "parallelism": f"dp{world}"}
+
+
 def modal_weight():
     """iter_per_epoch / modal_num of the mr2468 table (train.py:163-171): 219 / (90, 135, 184, 43)."""
     import torch
@@ -206,10 +213,13 @@ def run_ours(args):
     ms_total = float(ms)
 
     # ---- timed region 2: end to end through the public API from pinned host buffers
+    #      The target travels as the uint8 label map [B,S,S,S] (the compact form Model.forward / criterions accept next to the
+    #      reference loader's float64 one-hot, which is np.eye(4)[label] of the same map: 1 MB instead of 33 MB per batch).
     from passion_b200.engine import DevicePrefetcher
+    host = [(x, t.argmax(1).to(torch.uint8).contiguous().pin_memory(), m) for x, t, m in host]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     for batch in DevicePrefetcher((host[i % nb] for i in range(2)), dev, like=host[0]):      # untimed: one-time setup of the path
-        trainer.step(*batch)
+        trainer.step(*batch)                                                                 # (re-captures the step for this target format)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     feed = DevicePrefetcher((host[i % nb] for i in range(args.steps)), dev, like=host[0])   # H2D of batch i+1 overlaps step i
     sync()
@@ -324,19 +334,18 @@ def run_ours(args):
                 "step_hbm_frac": round(value / world * BYTES_PER_SAMPLE / 1e9 / hbm_peak, 4),
                 "step_tc_frac": round(value / world * FLOP_PER_SAMPLE / 1e12 / tc_peak, 4),
                 "families_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
-    label = {"rfnet": "RFNet", "mmformer": "mmFormer"}[args.model]
     metric = METRIC if S == S_CROP else METRIC.replace("4x80^3", f"4x{S}^3")
     out = {"metric": metric, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
-           "config": {"workload": f"{label}+PASSION train step, B={B}/GPU, 4x{S}^3 crops, idt masks from mr2468, temp 4, AdamW amsgrad",
-                      "global_batch": B * world, "parallelism": f"dp{world}",
-                      "step_execution": "one CUDA graph replay per step" if use_graph else "eager launches",
-                      "roofline_region": "eager re-run of the same steps with CUDA events around every kernel launch",
-                      "l2": "per-step working set (~6 GiB of activations) exceeds the 126 MB L2; no explicit flush"},
+           "config": workload_config(args.model, B, S, world),
+           "notes": {"step_execution": "one CUDA graph replay per step" if use_graph else "eager launches",
+                     "roofline_region": "eager re-run of the same steps with CUDA events around every kernel launch",
+                     "l2": "per-step working set (~6 GiB of activations) exceeds the 126 MB L2; no explicit flush"},
            "clocks": clk,
            "e2e": {"value": round(e2e, 3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                   "ms_per_step": round(ms2_total / args.steps, 3), "last_loss": last},
+                   "ms_per_step": round(ms2_total / args.steps, 3), "last_loss": last,
+                   "target_format": "uint8 label map (x f32 + labels u8 + mask from pinned host memory every step)"},
            "e2e_resident_cases": resident,
            "gpu_launches": int(launches), "roofline": roofline}
     dump = os.environ.get("PB_DUMP_KERNELS")
@@ -351,7 +360,11 @@ def run_ours(args):
         # SURVEY.md §8d's per-sample flop / byte figures are RFNet's; the secondary backbone reports kernel families only
         roofline.pop("step_hbm_frac"); roofline.pop("step_tc_frac")
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(budget_s=30.0, model=args.model, S=S)
+        out["cpu_baseline"], ref_first = cpu_baseline(budget_s=30.0, model=args.model, S=S)
+        try:
+            out["parity"] = parity_block(ref_first, args.model, S)
+        except Exception as exc:                         # an additional block must never take the headline line down
+            out["parity"] = {"error": repr(exc)[:300]}
     emit(out)
     finish()
 
@@ -376,58 +389,115 @@ def _oracle_step_fn(S, B=1, model="rfnet"):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        return float(loss)
-    return step
+        return float(loss), outs
+    return step, sd
+
+
+def _reference_step_fn(S, B, model="rfnet"):
+    """-> (step, state_dict, kind).  kind = "reference": the UNMODIFIED reference model + criterions staged under
+    baseline/_ref (baseline/run_cpu_reference.py); "port": the oracle restatement, when the staged tree is absent or for the
+    secondary backbone."""
+    import torch
+    from oracle import synth
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import run_cpu_reference as rcr
+    if model == "rfnet" and rcr.available():
+        x, target, mask, _ = synth.make_batch(B, S, seed=1037, labels="U", mask_ids=mask_ids_for(B))
+        sd = synth.make_state_dict(1037)
+        step, _ = rcr.step_fn(x, target, mask, torch.ones(4), modal_weight(), temp=4.0, state_dict=sd)
+        return step, sd, "reference"
+    step, sd = _oracle_step_fn(S, B, model)
+    return step, sd, "port"
 
 
 def cpu_baseline(budget_s=30.0, model="rfnet", S=S_CROP):
+    """One sample (B = 1) of the bench workload per step on the host cores: 1 warm-up + up to 3 timed steps inside the
+    budget, median reported.  Returns (json block, first-step outputs for the parity block)."""
     import torch
-    step16 = _oracle_step_fn(16, 1, model)
-    step16()                                            # library warm-up at a tiny size
-    step = _oracle_step_fn(S, 1, model)
+    t_start = time.time()
+    step, sd, kind = _reference_step_fn(S, 1, model)
     t0 = time.time()
-    step()
-    dt = time.time() - t0
-    return {"value": round(1.0 / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 step, B=1, 4x{S}^3, fp32, oracle/ (PyTorch-CPU restatement of the reference), {dt:.1f} s"}
+    loss0, outs0 = step()                               # warm-up (library initialisation); its loss is at the initial weights
+    first = time.time() - t0
+    ts = []
+    while len(ts) < 3 and (not ts or time.time() - t_start + first < budget_s):
+        t0 = time.time()
+        step()
+        ts.append(time.time() - t0)
+    ts.sort()
+    dt = ts[len(ts) // 2]
+    what = ("the unmodified reference model + criterions (baseline/_ref), train.py's step restated" if kind == "reference"
+            else "oracle/ (PyTorch-CPU restatement of the reference)")
+    blk = {"value": round(1.0 / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+           "sample": f"median of {len(ts)} steps after 1 warm-up ({first:.1f} s), B=1, 4x{S}^3, fp32, {what}, {dt:.2f} s/step"}
+    return blk, (loss0, [o.detach() for o in outs0], sd)
+
+
+def parity_block(ref_first, model_name, S):
+    """First-step quantities of OUR arm (bf16 production mode and fp32 check mode) against the CPU arm's first step on the
+    same weights and the same B = 1 batch, at the bench's crop size."""
+    import torch
+    from oracle import synth
+    from passion_b200.models import build_model
+    from passion_b200.train_step import loss_mix
+    loss_ref, outs_ref, sd = ref_first
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    x, target, mask, _ = synth.make_batch(1, S, seed=1037, labels="U", mask_ids=mask_ids_for(1))
+    names = ["fuse_prob", "prm_loss", "sep_loss", "kl_loss", "proto_loss", "dist"]
+    out = {"what": f"first step, B=1, 4x{S}^3, same weights/batch as cpu_baseline; rel-L2 of Model.forward outputs and |dloss|/loss",
+           "loss_cpu": round(loss_ref, 6)}
+    for tag, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        model = build_model(model_name, num_cls=4, crop=S).to(dev)
+        model.load_state_dict(sd)
+        model.is_training, model.use_passion, model.mask_type = True, True, "idt"
+        model.compute_dtype = dt
+        with torch.no_grad():
+            outs = model(x.to(dev), mask.to(dev), target=target.to(dev), temp=4.0)
+            loss, _ = loss_mix(outs, target.to(dev), mask.to(dev), torch.ones(4, device=dev), modal_weight().to(dev), mask_type="idt")
+        rels = {}
+        for n, a, b in zip(names, outs, outs_ref):
+            a, b = a.double().cpu(), b.double()
+            rels[n] = float(f"{float((a - b).norm() / b.norm().clamp_min(1e-30)):.3e}")
+        out[tag] = {"loss": round(float(loss), 6), "loss_rel": float(f"{abs(float(loss) - loss_ref) / abs(loss_ref):.3e}"), "outputs_rel_l2": rels}
+        del model
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host cores.  /root/reference does not exist on
-    the GPU box and the reference cannot be pip-installed (it is a script tree without setup.py), so the arm
-    runs the oracle port, which gen_golden.py pinned against the real reference modules."""
+    """--impl reference: the reference's own CPU implementation of the step on the host cores — the unmodified reference
+    model + criterions from baseline/_ref (staged by __graft_entry__.build(); /root/reference itself does not exist on the GPU
+    box), same config as our arm: B = 2, 4x80^3.  If a full batch per step would push the whole --steps/--warmup run past
+    ~5 minutes, each step is a bounded sample (B = 1, half a batch) and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     total = args.steps + args.warmup
-    step16 = _oracle_step_fn(16)
-    step16()
-    # size the per-step sample so that the whole run stays within ~4 minutes: full 80^3 costs ~10-14 s/step
-    probe = _oracle_step_fn(32)
-    t0 = time.time(); probe(); t32 = time.time() - t0
-    S = S_CROP
-    for cand in (80, 64, 48, 40, 32):
-        S = cand
-        if t32 * (cand / 32.0) ** 3 * total <= 240.0:
-            break
-    step = _oracle_step_fn(S, 1)
+    S, B = args.size, args.batch
+    step1, _, kind = _reference_step_fn(S, 1, args.model)
+    step1()                                              # library warm-up
+    t0 = time.time(); step1(); t1 = time.time() - t0     # one B = 1 step: the probe that sizes the run
+    del step1
+    b_run = B if t1 * B * total <= 330.0 else 1
+    step, _, kind = _reference_step_fn(S, b_run, args.model)
     for _ in range(args.warmup):
         step()
     t0 = time.time()
     for _ in range(args.steps):
         step()
     dt = time.time() - t0
-    frac = (S / float(S_CROP)) ** 3                      # conv work is linear in voxels
-    value = args.steps * frac / dt
+    value = args.steps * b_run / dt
     cores = torch.get_num_threads()
-    sample = f"{args.steps} steps, B=1, 4x{S}^3 crop (= {frac:.3f} of an 80^3 sample each), fp32, {cores} threads"
-    out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "samples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+    impl = ("unmodified reference model + criterions (baseline/_ref/code: models/rfnet.py, utils/criterions.py), train.py:228-280 "
+            "step restated, PyTorch fp32 CPU" if kind == "reference" else "CPU port of the reference algorithm (oracle/, PyTorch fp32)")
+    sample = (f"{args.steps} steps of B={b_run} x 4x{S}^3 (" + ("the full per-GPU batch" if b_run == B else f"a bounded sample: {b_run} of the {B} samples of a batch")
+              + f"), fp32, {cores} threads; {impl}")
+    out = {"impl": "reference", "metric": METRIC if S == S_CROP else METRIC.replace("4x80^3", f"4x{S}^3"), "value": round(value, 4),
+           "unit": "samples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"RFNet+PASSION train step, B={B_PER_GPU}/GPU, 4x{S_CROP}^3 crops, idt masks from mr2468, temp 4, AdamW amsgrad",
-                      "sample": sample, "implementation": "CPU port of the reference algorithm (oracle/, PyTorch fp32, all host threads)"},
-           "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": workload_config(args.model, B, S, 1),
+           "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
