@@ -81,6 +81,10 @@ int pb_conv3d_wgrad(const pb_conv_desc* d, const void* x0, const void* x1, const
  * (pb_conv3d_dgrad_reflect_fix then adds the reflected-halo terms).  `err_flag` is a zero-initialised device
  * int that receives a non-zero code if the kernel's internal pipeline ever times out. */
 int pb_conv3d_tc_ntile(int cin, int cout);
+/* 1 = the class runs on the kw-stacked variant (Cout <= 16: 3 MMAs of N = 144 per input plane instead of 9 of N = 48) and its
+ * weight image is laid out [groups][cout tiles][3 kh][max(2,cin/8)][rows: kd = 2,1,0 | kw | 16 co][8]; else the layout above
+ * ([9 (kh,kw)][chunk][rows: kd = 2,1,0 | NT co][8]).  pb_weight_prep writes whichever applies. */
+int pb_conv3d_tc_kws(int cin, int cout);
 int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias /* [groups][cout] or NULL */,
                  void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
 /* Weight gradient of the same class on tcgen05: voxels are the GEMM K dimension, the nine (kd,kh) accumulators of one

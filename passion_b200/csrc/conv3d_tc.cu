@@ -17,6 +17,7 @@
 //   * warp roles: warps 0-3 epilogue (TMEM -> registers -> bf16 NDHWC stores + InstanceNorm partial sums),
 //     warp 4 single-thread tcgen05.mma issue + TMEM allocation, warps 5-7 producers.  Two TMEM accumulator stages
 //     overlap the epilogue of plane d with the MMAs of plane d+1.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -413,6 +414,325 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, co
     if (smem > 227 * 1024) { pb_set_error("conv3d_tc: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { pb_set_error("conv3d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
+    const int items = p.npg * p.QT * p.ND;
+    int ctas = 148 / (p.groups * p.nt_tiles);
+    if (smem <= 110 * 1024) ctas *= 2;
+    if (ctas < 1) ctas = 1;
+    if (ctas > items) ctas = items;
+    kern<<<dim3(ctas, p.groups, p.nt_tiles), kTcThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
+                                                                    (bf16*)y0, (bf16*)y1, (bf16*)yext, stats, err);
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------ kw-stacked variant (Cout <= 16)
+// Same sweep as conv3_tc_kernel, but the three kw taps are stacked along N as well: the MMAs of one input plane are
+// 3 (kh) x K-steps instructions with N = 3 (kd) x 3 (kw) x 16 = 144 instead of 9 x K-steps with N = 48 — an MMA with N <= 48
+// costs the tensor pipe the same ~40-75 cycles as one with N = 144 (scripts/microbench/umma_rate.cu), so the pipe time per
+// plane drops ~3x.  The price is a shifted sum in the epilogue: accumulator row l holds, per kw, the contribution of INPUT
+// position l as tap kw, which belongs to output position l - kw, i.e.
+//     y[l] = D[l][kw=0] + D[l+1][kw=1] + D[l+2][kw=2].
+// A one/two-row shift is a warp shuffle; the two rows a warp needs from its right neighbour (TMEM lane quadrants are private to
+// a warp) travel through 1.5 KB of shared memory, double-buffered, one named barrier per plane among the four epilogue warps.
+// Rows 126/127 of a tile only serve as right neighbours: tiles advance by 126 positions.
+// Ring block of one output plane = 48 columns [kw][16 co]; weight image [3 kh][chunk][rows: kd = 2,1,0 | kw | co][8].
+constexpr int kKwsStride = 126;
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int NCHR, int CR>       // CR = real output channels of the tile / 8 (1 or 2)
+__global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                                   const bf16* __restrict__ wimg, const float* __restrict__ bias,
+                                                                   bf16* __restrict__ y0, bf16* __restrict__ y1, bf16* __restrict__ yext,
+                                                                   double* __restrict__ stats, int* err) {
+    constexpr int NT = 16, NB = 3 * NT, CRE = 8 * CR;
+    constexpr int NCH = NCHR < 2 ? 2 : NCHR;
+    constexpr int KS = NCH / 2;
+    constexpr int kSlots = NCHR >= 16 ? 2 : 6;
+    constexpr int TMEM_COLS = 256;
+    constexpr int R = TMEM_COLS / NB;                     // 5 accumulator blocks: 3 being written, 2 draining
+    const int Di = p.D - 2 * p.inset, Hi = p.H - 2 * p.inset, Wi = p.W - 2 * p.inset;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int w_bytes = 27 * NCH * NT * 16;
+    uint8_t* w_s = smem;
+    const int slot_bytes = NCH * p.slab_e * 16;
+    uint8_t* slab_s = smem + ((w_bytes + 127) & ~127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab_s + (size_t)kSlots * slot_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kSlots;
+    uint64_t* blk_full = bars + 2 * kSlots;
+    uint64_t* blk_empty = blk_full + R;
+    uint64_t* wbar = blk_empty + R;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* xch = reinterpret_cast<float*>(tmem_slot + 4);          // [2][4 warps][3][NT]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.y, nt = blockIdx.z;
+    const int items = p.npg * p.QT * p.ND;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kTcProducers); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < R; ++i) { mbar_init(&blk_full[i], 1); mbar_init(&blk_empty[i], 128); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (NCHR < 2) {
+        for (int i = threadIdx.x; i < kSlots * p.slab_e; i += kTcThreads) {
+            const int s = i / p.slab_e, e = i % p.slab_e;
+            *reinterpret_cast<uint4*>(slab_s + (size_t)s * slot_bytes + ((size_t)p.slab_e + e) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp < 4) {
+#pragma unroll 1
+        for (int c = 0; c < TMEM_COLS; c += 16) tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp >= 5) {
+        // =============================== producers (as conv3_tc_kernel; tiles advance by kKwsStride) ===============================
+        const int pt = threadIdx.x - 5 * 32;
+        const int c0ch = p.C0 >> 3;
+        const int copies = p.slab_need * NCHR;
+        uint32_t k = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
+            const int d0 = dc * p.DCH, q0 = qt * kKwsStride;
+            const int nout = min(p.DCH, p.D - d0);
+            int soff[max_copies(NCHR)];
+            uint32_t doff[max_copies(NCHR)];
+            uint32_t from1 = 0;
+#pragma unroll
+            for (int i = 0; i < max_copies(NCHR); ++i) {
+                const int idx = pt + i * kTcProducers;
+                soff[i] = -1; doff[i] = 0;
+                if (idx < copies) {
+                    const int ch = idx % NCHR, e = idx / NCHR;
+                    const int f = q0 + e;
+                    const int hp = f / p.PW, wp = f - hp * p.PW;
+                    int h = hp - 1 - p.inset, w = wp - 1 - p.inset;
+                    bool ok = hp < p.H + 2;
+                    if (p.reflect) { h = reflect_idx(h, Hi); w = reflect_idx(w, Wi); ok = ok && h >= 0 && h < Hi; }
+                    else ok = ok && h >= 0 && h < Hi && w >= 0 && w < Wi;
+                    doff[i] = (uint32_t)(ch * p.slab_e + e) * 16;
+                    if (ok) {
+                        if (ch < c0ch) soff[i] = (h * Wi + w) * p.C0 + ch * 8;
+                        else { soff[i] = (h * Wi + w) * p.C1 + (ch - c0ch) * 8; from1 |= 1u << i; }
+                    }
+                }
+            }
+            for (int pl = 0; pl < nout + 2; ++pl, ++k) {
+                const int slot = k % kSlots;
+                mbar_wait(&empty[slot], ((k / kSlots) & 1) ^ 1, err, 1);
+                int dp = d0 - 1 + pl - p.inset;
+                bool plane_ok = true;
+                if (p.reflect) dp = reflect_idx(dp, Di); else plane_ok = dp >= 0 && dp < Di;
+                if (!plane_ok) dp = 0;
+                const size_t plane = ((size_t)n * Di + dp) * Hi * Wi;
+                const bf16* p0 = x0 + plane * p.C0;
+                const bf16* p1 = x1 + plane * p.C1;
+                const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
+#pragma unroll
+                for (int i = 0; i < max_copies(NCHR); ++i) {
+                    if (pt + i * kTcProducers < copies) {
+                        const bool ok = plane_ok && soff[i] >= 0;
+                        const bf16* src = ((from1 >> i) & 1u) ? p1 : p0;
+                        cp_async16(sbase + doff[i], ok ? src + soff[i] : x0, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive_noinc(&full[slot]);
+            }
+        }
+        cp_async_wait_all();
+    } else if (warp == 4) {
+        // =============================== MMA issuer: 3 (kh) x KS instructions per input plane ===============================
+        if (lane == 0) {
+            const bf16* wsrc = wimg + ((size_t)(g * p.nt_tiles + nt) * w_bytes) / 2;
+            mbar_expect_tx(wbar, (uint32_t)w_bytes);
+            for (int off = 0; off < w_bytes; off += 16384) {
+                const int nb = min(16384, w_bytes - off);
+                bulk_g2s(smem_u32(w_s + off), reinterpret_cast<const uint8_t*>(wsrc) + off, (uint32_t)nb, wbar);
+            }
+            mbar_wait(wbar, 0, err, 2);
+            const uint32_t slab_addr = smem_u32(slab_s);
+            const uint64_t b0 = umma_desc(smem_u32(w_s), 9 * NT * 16, 128);      // LBO = one chunk plane of 9 NT rows
+            uint32_t k = 0, j0 = 0;
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int dc = it % p.ND;
+                const int nout = min(p.DCH, p.D - dc * p.DCH);
+                for (int pl = 0; pl < nout + 2; ++pl, ++k) {
+                    mbar_wait(&full[k % kSlots], (k / kSlots) & 1, err, 3);
+                    if (pl < nout) {
+                        const uint32_t jn = j0 + pl;
+                        mbar_wait(&blk_empty[jn % R], ((jn / R) & 1) ^ 1, err, 4);
+                    }
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const int od_lo = pl >= 2 ? pl - 2 : 0, od_hi = pl < nout ? pl : nout - 1;
+                    const int nb = od_hi - od_lo + 1;
+                    const int row0 = (2 - (pl - od_lo)) * NB;                  // weight rows: kd = 2, 1, 0 blocks of [kw][co]
+                    const int blk0 = (int)((j0 + od_lo) % R);
+                    const int n1 = blk0 + nb > R ? R - blk0 : nb;
+                    const uint64_t a0 = umma_desc(slab_addr + (k % kSlots) * slot_bytes, (uint32_t)p.slab_e * 16, 128);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t a1 = a0 + (uint64_t)(uint32_t)(kh * p.PW);
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint64_t ad = a1 + (uint64_t)(uint32_t)(2 * ks * p.slab_e);
+                            const uint64_t bd = b0 + (uint64_t)(uint32_t)((kh * NCH + 2 * ks) * 9 * NT + row0);
+                            umma_f16(tmem_base + blk0 * NB, ad, bd, umma_idesc(kTileM, n1 * NB), 1u);
+                            if (n1 < nb) umma_f16(tmem_base, ad, bd + (uint64_t)(uint32_t)(n1 * NB), umma_idesc(kTileM, (nb - n1) * NB), 1u);
+                        }
+                    }
+                    umma_commit(&empty[k % kSlots]);
+                    if (pl >= 2) umma_commit(&blk_full[(j0 + pl - 2) % R]);
+                }
+                j0 += nout;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue ===============================
+        const int cout = p.CO0 + p.CO1;
+        const int cb0 = nt * NT;
+        const float4* bias4 = bias != nullptr ? reinterpret_cast<const float4*>(bias + (size_t)g * cout + cb0) : nullptr;
+        uint32_t j = 0, prev_blk = 0;
+        bool have_prev = false;
+        const int tl = warp * 32 + lane;
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
+            const int d0 = dc * p.DCH;
+            const int nout = min(p.DCH, p.D - d0);
+            const int f = qt * kKwsStride + tl;
+            const int h = f / p.PW, w = f - h * p.PW;
+            const bool valid = tl < kKwsStride && h < p.H && w < p.W;
+            const int hi = h - 1, wi = w - 1;
+            const bool hw_inside = hi >= 0 && hi < Hi && wi >= 0 && wi < Wi;
+            const bool hw_shell = hi == 1 || hi == Hi - 2 || wi == 1 || wi == Wi - 2;
+            float s1[CRE], s2[CRE];
+#pragma unroll
+            for (int c = 0; c < CRE; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+            for (int od = 0; od < nout; ++od, ++j) {
+                const uint32_t blk = j % R;
+                mbar_wait(&blk_full[blk], (j / R) & 1, err, 5);
+                tc_fence_after();
+                float v0[CRE], v1[CRE], v2[CRE];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + blk * NB;
+#pragma unroll
+                for (int c = 0; c < CRE; c += 8) {
+                    tmem_ld8(taddr + c, v0 + c); tmem_ld8(taddr + NT + c, v1 + c); tmem_ld8(taddr + 2 * NT + c, v2 + c);
+                }
+                tmem_wait_ld();
+                if (have_prev) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&blk_empty[prev_blk]);
+                }
+#pragma unroll
+                for (int c = 0; c < NB; c += 16) tmem_zero16(taddr + c);
+                prev_blk = blk; have_prev = true;
+                // rows 0 / 1 of this warp are rows 32 / 33 of its left neighbour
+                float* xw = xch + ((j & 1) * 4 + warp) * 3 * NT;
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < CRE; ++c) { xw[c] = v1[c]; xw[NT + c] = v2[c]; }
+                } else if (lane == 1) {
+#pragma unroll
+                    for (int c = 0; c < CRE; ++c) xw[2 * NT + c] = v2[c];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const float* xn = xch + ((j & 1) * 4 + ((warp + 1) & 3)) * 3 * NT;
+                float y[CRE];
+#pragma unroll
+                for (int c = 0; c < CRE; ++c) {
+                    float a1 = __shfl_down_sync(0xffffffffu, v1[c], 1);
+                    float a2 = __shfl_down_sync(0xffffffffu, v2[c], 2);
+                    if (lane == 31) { a1 = xn[c]; a2 = xn[2 * NT + c]; }
+                    else if (lane == 30) a2 = xn[NT + c];
+                    y[c] = v0[c] + a1 + a2;
+                }
+                if (bias4 != nullptr) {
+#pragma unroll
+                    for (int c4 = 0; c4 < CRE / 4; ++c4) {
+                        const float4 b = __ldg(bias4 + c4);
+                        y[c4 * 4] += b.x; y[c4 * 4 + 1] += b.y; y[c4 * 4 + 2] += b.z; y[c4 * 4 + 3] += b.w;
+                    }
+                }
+                if (valid) {
+                    size_t vox = (((size_t)n * p.D + d0 + od) * p.H + h) * p.W + w;
+                    bool to_ext = false;
+                    if (p.inset) {
+                        const int di = d0 + od - 1;
+                        if (hw_inside && di >= 0 && di < Di && !(hw_shell || di == 1 || di == Di - 2))
+                            vox = (((size_t)n * Di + di) * Hi + hi) * Wi + wi;
+                        else
+                            to_ext = true;
+                    }
+#pragma unroll
+                    for (int c8 = 0; c8 < CR; ++c8) {
+                        const int cb = cb0 + c8 * 8;
+                        bf16* dst = to_ext ? yext + vox * cout + cb
+                                           : (cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0));
+                        VecIO<bf16, 8>::store(dst, y + c8 * 8);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) { s1[c8 * 8 + c] += y[c8 * 8 + c]; s2[c8 * 8 + c] += y[c8 * 8 + c] * y[c8 * 8 + c]; }
+                    }
+                }
+            }
+            if (stats != nullptr) {
+#pragma unroll
+                for (int c = 0; c < CRE; ++c) {
+                    const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+                    if (lane == 0) {
+                        atomicAdd(&stats[((size_t)n * cout + cb0 + c) * 2], (double)a);
+                        atomicAdd(&stats[((size_t)n * cout + cb0 + c) * 2 + 1], (double)b);
+                    }
+                }
+            }
+        }
+        if (have_prev) tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+template <int NCHR, int CR>
+int launch_tc_kws(const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1, void* yext,
+                  double* stats, int* err, cudaStream_t st) {
+    constexpr int NCH = NCHR < 2 ? 2 : NCHR;
+    constexpr int kSlots = NCHR >= 16 ? 2 : 6;
+    const size_t w_bytes = (size_t)27 * NCH * 16 * 16;
+    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 2 * 16 + 1) * 8 + 16
+                        + 2 * 4 * 3 * 16 * sizeof(float);
+    auto kern = conv3_tc_kws_kernel<NCHR, CR>;
+    if (smem > 227 * 1024) { pb_set_error("conv3d_tc_kws: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pb_set_error("conv3d_tc_kws: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
     const int items = p.npg * p.QT * p.ND;
     int ctas = 148 / (p.groups * p.nt_tiles);
     if (smem <= 110 * 1024) ctas *= 2;
@@ -1058,6 +1378,13 @@ extern "C" int pb_conv3d_tc_ntile(int cin, int cout) {
     return 16;
 }
 
+// 1 = the (cin, cout) class runs on the kw-stacked kernel (conv3_tc_kws_kernel) and its weight image uses that kernel's
+// layout [G][tile][3 kh][chunk][rows: kd = 2,1,0 | kw | 16 co][8]; PB_TC_KWS=0 switches the variant off (A/B measurements).
+extern "C" int pb_conv3d_tc_kws(int cin, int cout) {
+    static const bool on = [] { const char* e = getenv("PB_TC_KWS"); return !(e != nullptr && e[0] == '0'); }();
+    return on && pb_conv3d_tc_ntile(cin, cout) == 16 && cout <= 16 ? 1 : 0;
+}
+
 namespace {
 int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
              void* yext, int inset, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
@@ -1171,7 +1498,8 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     p.inset = inset;
     PB_CHECK_ARG(!p.reflect || (p.D >= 2 && p.H >= 2 && p.W >= 2), "reflect padding needs size >= 2");
     p.PW = p.W + 2;
-    p.QT = (p.H * p.PW + kTileM - 1) / kTileM;
+    const bool kws = pb_conv3d_tc_kws(cin, cout) != 0;
+    p.QT = kws ? (p.H * p.PW + kKwsStride - 1) / kKwsStride : (p.H * p.PW + kTileM - 1) / kTileM;
     p.npg = d->n / d->groups; p.groups = d->groups;
     p.nt_tiles = (cout + NT - 1) / NT;
     // depth chunking: enough work items to balance ~2 waves of CTAs, chunks of at least 8 planes
@@ -1180,7 +1508,7 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     while (p.npg * p.QT * nd < target && (p.D + nd) / (nd + 1) >= 8) ++nd;
     p.DCH = (p.D + nd - 1) / nd;
     p.ND = (p.D + p.DCH - 1) / p.DCH;
-    p.slab_need = kTileM + 2 * p.PW + 2;
+    p.slab_need = kws ? kTileM + 2 * p.PW : kTileM + 2 * p.PW + 2;
     const int nchr = cin / 8, nch = nchr < 2 ? 2 : nchr;
     // pad the plane pitch so that the nch chunk planes start in different shared-memory banks
     const int want = nch >= 8 ? 1 : 8 / nch;
@@ -1194,7 +1522,11 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
-#define TC_CASE(NCHR_, NT_) if (nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
+#define KWS_CASE(NCHR_, CR_) if (kws && nchr == NCHR_ && cout == 8 * CR_) rc = launch_tc_kws<NCHR_, CR_>(p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
+    KWS_CASE(1, 1); KWS_CASE(2, 1); KWS_CASE(4, 1); KWS_CASE(8, 1); KWS_CASE(16, 1);
+    KWS_CASE(1, 2); KWS_CASE(2, 2); KWS_CASE(4, 2); KWS_CASE(8, 2); KWS_CASE(16, 2);
+#undef KWS_CASE
+#define TC_CASE(NCHR_, NT_) if (!kws && nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
     TC_CASE(1, 16); TC_CASE(2, 16); TC_CASE(4, 16); TC_CASE(8, 16); TC_CASE(16, 16);
     TC_CASE(1, 32); TC_CASE(2, 32); TC_CASE(4, 32); TC_CASE(8, 32);
 #undef TC_CASE

@@ -20,7 +20,14 @@ struct PrepK {
     int nt, ntT;
     long long n_wk, n_wt, n_img, n_imgT, n_bias;
     int nch, tiles, nchT, tilesT;
+    int kws, kwsT;          // image layout of the kw-stacked kernel: [g][tile][3 kh][chunk][rows: kd = 2,1,0 | kw | nt co][8]
 };
+
+// (tap, local output row) of image row `row` of the (kh,kw)-plane / kh-plane `t`
+__device__ __forceinline__ void img_row(int kws, int nt, int t, int row, int& tap, int& col) {
+    if (kws) { tap = (2 - row / (3 * nt)) * 9 + t * 3 + (row / nt) % 3; col = row % nt; }
+    else { tap = (2 - row / nt) * 9 + t; col = row % nt; }
+}
 
 __device__ __forceinline__ float ref_w(const PrepK& k, int g, int co, int ci, int tap) {
     return __ldg(k.w[g] + ((size_t)co * k.cin + ci) * k.taps + tap);
@@ -51,28 +58,32 @@ __global__ void weight_prep_kernel(PrepK k) {
         i -= k.n_wt;
         if (i < k.n_img) {                                  // [g][tile][9 (kh,kw)][chunk][3 nt rows: kd = 2,1,0][8]
             const long long o = i;
+            const int rows = k.kws ? 9 * k.nt : 3 * k.nt, planes = k.kws ? 3 : 9;
             const int e = (int)(i % 8); i /= 8;
-            const int row = (int)(i % (3 * k.nt)); i /= 3 * k.nt;
+            const int row = (int)(i % rows); i /= rows;
             const int chunk = (int)(i % k.nch); i /= k.nch;
-            const int t9 = (int)(i % 9); i /= 9;
+            const int t9 = (int)(i % planes); i /= planes;
             const int tile = (int)(i % k.tiles);
             const int g = (int)(i / k.tiles);
-            const int tap = (2 - row / k.nt) * 9 + t9;
-            const int ci = chunk * 8 + e, co = tile * k.nt + row % k.nt;
+            int tap, col;
+            img_row(k.kws, k.nt, t9, row, tap, col);
+            const int ci = chunk * 8 + e, co = tile * k.nt + col;
             k.img[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, tap) : 0.f);
             continue;
         }
         i -= k.n_img;
         if (i < k.n_imgT) {                                 // roles of Cin / Cout swapped, taps mirrored
             const long long o = i;
+            const int rows = k.kwsT ? 9 * k.ntT : 3 * k.ntT, planes = k.kwsT ? 3 : 9;
             const int e = (int)(i % 8); i /= 8;
-            const int row = (int)(i % (3 * k.ntT)); i /= 3 * k.ntT;
+            const int row = (int)(i % rows); i /= rows;
             const int chunk = (int)(i % k.nchT); i /= k.nchT;
-            const int t9 = (int)(i % 9); i /= 9;
+            const int t9 = (int)(i % planes); i /= planes;
             const int tile = (int)(i % k.tilesT);
             const int g = (int)(i / k.tilesT);
-            const int tap = (2 - row / k.ntT) * 9 + t9;
-            const int co = chunk * 8 + e, ci = tile * k.ntT + row % k.ntT;
+            int tap, col;
+            img_row(k.kwsT, k.ntT, t9, row, tap, col);
+            const int co = chunk * 8 + e, ci = tile * k.ntT + col;
             k.imgT[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, 26 - tap) : 0.f);
             continue;
         }
@@ -137,6 +148,8 @@ extern "C" int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream) 
     k.n_wk = k.wk ? nw : 0;
     k.n_wt = k.wt ? nw : 0;
     k.nch = k.tiles = k.nchT = k.tilesT = 1;
+    k.kws = k.img ? pb_conv3d_tc_kws(k.cin, k.cout) : 0;
+    k.kwsT = k.imgT ? pb_conv3d_tc_kws(k.cout, k.cin) : 0;
     k.n_img = k.n_imgT = 0;
     if (k.img) {
         PB_CHECK_ARG(k.taps == 27 && k.nt > 0 && k.cin % 8 == 0, "forward image needs a 3x3x3 conv, cin % 8 == 0");

@@ -184,13 +184,18 @@ def _tc_eligible(dtype, ksize, stride, c0, c1, cout):
 
 
 def tc_weight_image(w, nt):
-    """fp32 [G, 27, cin, cout] -> bf16 image [G, cout tiles, 9, max(2, cin/8), 3 nt, 8] (zero padded)."""
+    """fp32 [G, 27, cin, cout] -> bf16 image [G, cout tiles, 9, max(2, cin/8), 3 nt, 8] (zero padded); for the classes of
+    the kw-stacked kernel (pb_conv3d_tc_kws) [G, cout tiles, 3 (kh), max(2, cin/8), 9 nt (kd = 2,1,0 | kw | co), 8]."""
     G, taps, cin, cout = w.shape
     nchr = cin // 8
     nch = max(2, nchr)
     tiles = (cout + nt - 1) // nt
     img = torch.zeros((G, taps, nch, 8, tiles * nt), dtype=torch.float32, device=w.device)
     img[:, :, :nchr, :, :cout] = w.reshape(G, taps, nchr, 8, cout)
+    if _lib.load().pb_conv3d_tc_kws(cin, cout):
+        # [G, kd, kh, kw, chunk, 8, tile, nt] -> [G, tile, kh, chunk, kd (flipped), kw, nt, 8]
+        img = img.view(G, 3, 3, 3, nch, 8, tiles, nt).flip(1).permute(0, 6, 2, 4, 1, 3, 7, 5)
+        return img.to(torch.bfloat16).reshape(G, tiles, 3, nch, 9 * nt, 8).contiguous()
     # kernel layout: [G][tile][9 (kh,kw)][chunk][3 nt rows, kd = 2,1,0][8 channels]
     img = img.view(G, 3, 9, nch, 8, tiles, nt).flip(1).permute(0, 5, 2, 3, 1, 6, 4)
     return img.to(torch.bfloat16).reshape(G, tiles, 9, nch, 3 * nt, 8).contiguous()
