@@ -20,7 +20,7 @@ import os
 import numpy as np
 import torch
 
-from passion_b200 import metrics
+from passion_b200 import metrics, ops
 from passion_b200.models import build_model
 from passion_b200.predict import MASKS_TEST
 
@@ -88,6 +88,7 @@ def evaluate(model, cases, patch_size=80, device='cuda'):
     for name, x, y in cases:
         res = metrics.evaluate_all_masks(model, torch.from_numpy(x).to(device), torch.from_numpy(y).to(device),
                                          patch_size=patch_size, masks=MASKS_TEST, mask_names=MASK_NAME)
+        ops.check_tc_errors()                          # once per case: a tcgen05 pipeline time-out must not pass silently
         names.append(name)
         msg = []
         for m in MASK_NAME[::-1]:
@@ -117,6 +118,7 @@ def main(argv=None):
         model.load_state_dict(sd)
         logging.info('last epoch: %d', ck.get('epoch', -1) + 1)
     model.is_training = False
+    model.eval()                                                                       # reference utils/predict.py:154
     names, scores = evaluate(model, test_cases(args), args.patch_size, dev)
     csv_name = os.path.join(args.savepath, f'{args.model}.csv')
     per_mask, overall = write_report(csv_name, names, scores)

@@ -38,7 +38,13 @@ def args_parser(argv=None):
     parser.add_argument('--device_aug', action='store_true',
                         help='keep the preprocessed cases resident in HBM and run train_transforms (crop, rotation, intensity, flip) '
                              'and the label encoding as one kernel per batch (passion_b200/data.py) instead of on the host')
+    parser.add_argument('--host_crop_only', action='store_true',
+                        help='real data without --device_aug: accept the host loader, which applies the random crop ONLY '
+                             '(no rotation / intensity change / flip); without this flag real-data training uses --device_aug')
     args = parser.parse_args(argv)
+    if not args.synthetic and not args.device_aug and not args.host_crop_only:
+        # the reference trains with the full train_transforms chain (options.py:50); only the device pipeline implements it
+        args.device_aug = True
 
     root = args.datarootPath or os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'datasets'))
     args.datarootPath = root

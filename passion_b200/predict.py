@@ -46,8 +46,9 @@ def _overlap_count(shape, patch, device):
 @torch.no_grad()
 def predict_volume(model, x, mask, patch_size=80):
     """x [B,4,H,W,Z] float32 (CUDA), mask [B,4] bool -> (labels int64 [B,H,W,Z], averaged probabilities [B,C,H,W,Z])."""
-    was = model.is_training
+    was, was_mode = model.is_training, model.training
     model.is_training = False
+    model.eval()                                    # reference utils/predict.py:154 (mmFormer's dropout must be off)
     B = x.shape[0]
     shape = tuple(x.shape[2:])
     weight = _overlap_count(shape, patch_size, x.device)
@@ -59,6 +60,7 @@ def predict_volume(model, x, mask, patch_size=80):
         pred[:, :, h:h + patch_size, w:w + patch_size, z:z + patch_size] += part
     pred = pred / weight
     model.is_training = was
+    model.train(was_mode)
     return torch.argmax(pred, dim=1), pred
 
 
@@ -71,6 +73,8 @@ def predict_all_masks(model, x, masks=None, patch_size=80):
     if model.mask_type == 'pdt':
         raise ValueError("the shared-encoder sweep relies on the idt masking order (rfnet.py:232-242)")
     masks = MASKS_TEST if masks is None else masks
+    was_mode = model.training
+    model.eval()                                    # reference utils/predict.py:154
     mt = torch.tensor(masks, dtype=torch.bool, device=x.device)                        # [M,4]
     M = mt.shape[0]
     shape = tuple(x.shape[2:])
@@ -87,4 +91,5 @@ def predict_all_masks(model, x, masks=None, patch_size=80):
         prob = ops.softmax4(logits).permute(0, 4, 1, 2, 3)                             # [M,C,p,p,p]
         pred[:, :, h:h + patch_size, w:w + patch_size, z:z + patch_size] += prob
     pred = pred / weight
+    model.train(was_mode)
     return torch.argmax(pred, dim=1), pred

@@ -187,3 +187,21 @@ def test_pdt_is_rejected(lib_built):
     model.mask_type = "pdt"
     with pytest.raises(NotImplementedError):
         model(x.cuda(), mask.cuda())
+
+
+def test_inference_sweep_is_deterministic_on_a_fresh_model(lib_built):
+    """predict_volume / evaluate_all_masks put the model in eval mode themselves (reference utils/predict.py:154): a freshly
+    built mmFormer (nn.Module default: training mode, dropout 0.1 in five transformers) must give identical label maps on
+    two sweeps, and its previous mode is restored afterwards."""
+    from passion_b200 import metrics
+    z, model, sd, x, target, mask = _setup("idtU_nopassion", torch.float32)
+    model.train()
+    xs = x[:1].cuda()
+    y = target[:1].argmax(1).to(torch.uint8).cuda()
+    masks = [[True, True, False, True], [False, False, True, False]]
+    names = ["a", "b"]
+    r1 = metrics.evaluate_all_masks(model, xs, y, patch_size=32, masks=masks, mask_names=names)
+    r2 = metrics.evaluate_all_masks(model, xs, y, patch_size=32, masks=masks, mask_names=names)
+    for n in names:
+        assert torch.equal(r1[n], r2[n]), n
+    assert model.training

@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from options import args_parser
+from passion_b200 import ops
 from passion_b200.data import AugmentSampler, DeviceAugment, ResidentCases
 from passion_b200.engine import DevicePrefetcher, Trainer
 from passion_b200.models import build_model
@@ -48,6 +49,18 @@ class Source:
         self.rs = np.random.RandomState(args.seed + rank)
         per_step = args.batch_size * world
         self.iters = args.iters_per_epoch or max(1, len(rows) // per_step)
+        self._perm_epoch, self._perm = -1, None
+
+    def row_index(self, it, b):
+        """Case index of sample b of this rank at global iteration `it`: the rows are re-shuffled every epoch (the
+        reference's DataLoader(shuffle=True), train.py:122-128) with a generator seeded by (seed, epoch) — the same
+        permutation on every rank, each rank takes its own slice of it."""
+        per_step = self.args.batch_size * self.world
+        epoch, i = divmod(it, self.iters)
+        if epoch != self._perm_epoch:
+            self._perm = np.random.RandomState((self.args.seed * 1000003 + epoch) % (2 ** 32)).permutation(len(self.rows))
+            self._perm_epoch = epoch
+        return int(self._perm[(i * per_step + self.rank * self.args.batch_size + b) % len(self.rows)])
 
     def _mask_id(self, row):
         if self.args.mask_type == 'idt':
@@ -60,7 +73,7 @@ class Source:
         B, S = self.args.batch_size, self.args.crop_size
         xs, ys, ms = [], [], []
         for b in range(B):
-            row = self.rows[(it * self.world * B + self.rank * B + b) % len(self.rows)]
+            row = self.rows[self.row_index(it, b)]
             if self.args.synthetic:
                 x = self.rs.standard_normal((4, S, S, S)).astype(np.float32)
                 y = self.rs.randint(0, 4, (S, S, S))
@@ -100,7 +113,7 @@ class ResidentSource(Source):
         B = self.args.batch_size
         ids, ps, ms = [], [], []
         for b in range(B):
-            k = (it * self.world * B + self.rank * B + b) % len(self.rows)
+            k = self.row_index(it, b)
             cid = k % len(self.cases) if self.args.synthetic else k
             ids.append(cid)
             ps.append(self.sampler.sample(tuple(self.cases.vols[cid].shape[:3])))
@@ -132,6 +145,9 @@ def main():
         csv_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tests', 'golden', os.path.basename(args.imbmrpath))
     rows = read_split(csv_path)
     src = ResidentSource(args, rows, rank, world, dev) if args.device_aug else Source(args, rows, rank, world)
+    if not args.device_aug and not args.synthetic:
+        logging.warning('--host_crop_only: the host loader applies the random crop only; RandomRotion / RandomIntensityChange / '
+                        'RandomFlip of args.train_transforms are SKIPPED (use --device_aug for the reference chain)')
     modal_num = torch.tensor(np.sum([eval(r['mask']) for r in rows], 0), dtype=torch.float32)      # train.py:163-166
     logging.info('Training Imperfect Datasets with Mod.Flair-%d, Mod.T1c-%d, Mod.T1-%d, Mod.T2-%d', *modal_num.int().tolist())
     iter_per_epoch = src.iters
@@ -171,6 +187,7 @@ def main():
                 logging.info('Epoch %d/%d, Iter %d/%d, Loss %.4f, fuse_loss:%.4f, prm_loss:%.4f, sep_loss:%.4f, kl_loss:%.4f, proto_loss:%.4f',
                              epoch + 1, args.num_epochs, i + 1, iter_per_epoch, *vals)
         torch.cuda.synchronize()
+        ops.check_tc_errors()                            # a tcgen05 pipeline time-out must not corrupt training silently
         logging.info('train time per epoch: %.2f s (%.2f samples/s)', time.time() - t0,
                      iter_per_epoch * args.batch_size * world / (time.time() - t0))
         if args.use_passion and epoch >= args.region_fusion_start_epoch:                            # train.py:325-335
