@@ -153,9 +153,18 @@ typedef struct {
     float* gw[4];
     float* gb[4];
     int groups, cin, cout, ksize;
+    int accumulate;         /* 0: gw / gb are overwritten; 1: added to (autograd's accumulation into an existing .grad) */
 } pb_weight_unpack_desc;
 int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream);
 int pb_weight_grad_unpack(const pb_weight_unpack_desc* d, pb_stream_t stream);
+/* Batched forms: ALL conv layers of a model in one launch each (the weights change once per step, after the optimizer; the
+ * weight gradients are complete once backward has finished) instead of one launch per layer and direction.
+ * `table` = device scratch of pb_weight_batch_table_bytes(n) bytes.  upload != 0: the n descriptors are packed on the host
+ * and copied into `table` first (a pageable-memory copy: NOT capturable — do it in a warm-up step); upload == 0: the table
+ * written by the previous call is reused as is (same descriptors; capturable into a CUDA graph). */
+size_t pb_weight_batch_table_bytes(int n);
+int pb_weight_prep_batch(const pb_weight_prep_desc* descs, int n, void* table, int upload, pb_stream_t stream);
+int pb_weight_grad_unpack_batch(const pb_weight_unpack_desc* descs, int n, void* table, int upload, pb_stream_t stream);
 
 /* ---- InstanceNorm3d(affine=False, eps) + LeakyReLU(slope) (+ residual) -----------------
  * Replaces norm + activation of general_conv3d (blocks.py:18, :363, :367-369) and the encoder

@@ -36,7 +36,8 @@ class WeightUnpackDesc(ctypes.Structure):
     """Mirror of pb_weight_unpack_desc."""
     _fields_ = [("dw", ctypes.c_void_p), ("db", ctypes.c_void_p), ("dy_stats", ctypes.c_void_p), ("npg", ctypes.c_int32),
                 ("gw", ctypes.c_void_p * 4), ("gb", ctypes.c_void_p * 4),
-                ("groups", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32)]
+                ("groups", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32),
+                ("accumulate", ctypes.c_int32)]
 
 
 class AugmentSample(ctypes.Structure):
@@ -69,6 +70,8 @@ def load():
         raise RuntimeError(f"passion_b200: library is missing symbols {missing}")
     lib.pb_last_error.restype = ctypes.c_char_p
     lib.pb_launch_count.restype = ctypes.c_longlong
+    lib.pb_weight_batch_table_bytes.restype = ctypes.c_size_t
+    lib.pb_weight_batch_table_bytes.argtypes = [ctypes.c_int]
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
     cd = ctypes.POINTER(ConvDesc)
     sig = {
@@ -89,6 +92,8 @@ def load():
         "pb_conv3d_small_wgrad": [cd, vp, vp, vp, vp],
         "pb_weight_prep": [ctypes.POINTER(WeightPrepDesc), vp],
         "pb_weight_grad_unpack": [ctypes.POINTER(WeightUnpackDesc), vp],
+        "pb_weight_prep_batch": [ctypes.POINTER(WeightPrepDesc), i32, vp, i32, vp],
+        "pb_weight_grad_unpack_batch": [ctypes.POINTER(WeightUnpackDesc), i32, vp, i32, vp],
         "pb_channel_stats": [i32, vp, vp, i32, i64, i32, vp],
         "pb_inorm_finalize": [vp, vp, i32, i32, i64, f32, vp],
         "pb_inorm_lrelu_fwd": [i32, vp, vp, vp, vp, i32, i64, i32, f32, vp],

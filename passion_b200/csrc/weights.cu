@@ -8,6 +8,7 @@
 //   imgT bf16 [G][Cin tiles][27][NCH'][NT'][8]     the same for the data gradient: taps flipped, channels transposed
 // Doing this with tensor ops costs ~10 tiny launches per layer and step (permute / stack / zeros / copy / cast); here
 // it is one gather kernel before the layer runs and one scatter kernel after its weight gradient.
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -33,9 +34,8 @@ __device__ __forceinline__ float ref_w(const PrepK& k, int g, int co, int ci, in
     return __ldg(k.w[g] + ((size_t)co * k.cin + ci) * k.taps + tap);
 }
 
-__global__ void weight_prep_kernel(PrepK k) {
-    const long long total = k.n_wk + k.n_wt + k.n_img + k.n_imgT + k.n_bias;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+__device__ __forceinline__ void prep_element(const PrepK& k, const long long t) {
+    {
         long long i = t;
         if (i < k.n_wk) {                                   // [g][tap][ci][co]
             const int co = (int)(i % k.cout); i /= k.cout;
@@ -43,7 +43,7 @@ __global__ void weight_prep_kernel(PrepK k) {
             const int tap = (int)(i % k.taps);
             const int g = (int)(i / k.taps);
             k.wk[t] = ref_w(k, g, co, ci, tap);
-            continue;
+            return;
         }
         i -= k.n_wk;
         if (i < k.n_wt) {                                   // [g][tap][co][ci]
@@ -53,7 +53,7 @@ __global__ void weight_prep_kernel(PrepK k) {
             const int tap = (int)(i % k.taps);
             const int g = (int)(i / k.taps);
             k.wt[o] = ref_w(k, g, co, ci, tap);
-            continue;
+            return;
         }
         i -= k.n_wt;
         if (i < k.n_img) {                                  // [g][tile][9 (kh,kw)][chunk][3 nt rows: kd = 2,1,0][8]
@@ -69,7 +69,7 @@ __global__ void weight_prep_kernel(PrepK k) {
             img_row(k.kws, k.nt, t9, row, tap, col);
             const int ci = chunk * 8 + e, co = tile * k.nt + col;
             k.img[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, tap) : 0.f);
-            continue;
+            return;
         }
         i -= k.n_img;
         if (i < k.n_imgT) {                                 // roles of Cin / Cout swapped, taps mirrored
@@ -85,7 +85,7 @@ __global__ void weight_prep_kernel(PrepK k) {
             img_row(k.kwsT, k.ntT, t9, row, tap, col);
             const int co = chunk * 8 + e, ci = tile * k.ntT + col;
             k.imgT[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, 26 - tap) : 0.f);
-            continue;
+            return;
         }
         i -= k.n_imgT;
         {
@@ -96,17 +96,42 @@ __global__ void weight_prep_kernel(PrepK k) {
     }
 }
 
+__global__ void weight_prep_kernel(PrepK k) {
+    const long long total = k.n_wk + k.n_wt + k.n_img + k.n_imgT + k.n_bias;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+        prep_element(k, t);
+}
+
+// layer of flat element t: prefix[l] <= t < prefix[l+1]
+__device__ __forceinline__ int find_layer(const long long* __restrict__ prefix, int n, long long t) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// every conv layer of the model in ONE launch (weights change once per step): table = [n+1 prefix sums][n PrepK]
+__global__ void weight_prep_batch_kernel(const long long* __restrict__ prefix, const PrepK* __restrict__ tab, int n) {
+    const long long total = __ldg(prefix + n);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int l = find_layer(prefix, n, t);
+        prep_element(tab[l], t - __ldg(prefix + l));
+    }
+}
+
 struct UnpackK {
     const float* dw; const float* db; const double* dy_stats; int npg;
     float* gw[4]; float* gb[4];
     int G, cin, cout, taps;
+    int accumulate;         // 1: add to what gw / gb hold (autograd's accumulation semantics), 0: overwrite
 };
 
-__global__ void weight_unpack_kernel(UnpackK k) {
+__device__ __forceinline__ void unpack_element(const UnpackK& k, const long long t) {
     const long long per = (long long)k.cout * k.cin * k.taps;
     const long long n_w = per * k.G;
-    const long long total = n_w + ((k.db || k.dy_stats) ? (long long)k.G * k.cout : 0);
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    {
         if (t < n_w) {
             const int g = (int)(t / per);
             long long i = t - (long long)g * per;
@@ -114,27 +139,106 @@ __global__ void weight_unpack_kernel(UnpackK k) {
             const int tap = (int)(i % k.taps); i /= k.taps;
             const int ci = (int)(i % k.cin);
             const int co = (int)(i / k.cin);
-            k.gw[g][o] = __ldg(k.dw + (((size_t)g * k.taps + tap) * k.cin + ci) * k.cout + co);
+            const float v = __ldg(k.dw + (((size_t)g * k.taps + tap) * k.cin + ci) * k.cout + co);
+            k.gw[g][o] = k.accumulate ? k.gw[g][o] + v : v;
         } else {
             const long long i = t - n_w;
             const int g = (int)(i / k.cout), co = (int)(i % k.cout);
-            if (k.db) k.gb[g][co] = __ldg(k.db + i);
+            float v;
+            if (k.db) v = __ldg(k.db + i);
             else {
                 double acc = 0.0;
                 for (int n = 0; n < k.npg; ++n) acc += k.dy_stats[(((size_t)g * k.npg + n) * k.cout + co) * 2];
-                k.gb[g][co] = (float)acc;
+                v = (float)acc;
             }
+            k.gb[g][co] = k.accumulate ? k.gb[g][co] + v : v;
         }
+    }
+}
+
+__device__ __forceinline__ long long unpack_total(const UnpackK& k) {
+    return (long long)k.G * k.cout * ((long long)k.cin * k.taps + ((k.db || k.dy_stats) ? 1 : 0));
+}
+
+__global__ void weight_unpack_kernel(UnpackK k) {
+    const long long total = unpack_total(k);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+        unpack_element(k, t);
+}
+
+__global__ void weight_unpack_batch_kernel(const long long* __restrict__ prefix, const UnpackK* __restrict__ tab, int n) {
+    const long long total = __ldg(prefix + n);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int l = find_layer(prefix, n, t);
+        unpack_element(tab[l], t - __ldg(prefix + l));
     }
 }
 
 }  // namespace
 
-extern "C" int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream) {
+namespace {
+int make_prep(const pb_weight_prep_desc* d, PrepK& k, long long& total);
+int make_unpack(const pb_weight_unpack_desc* d, UnpackK& k, long long& total);
+constexpr size_t kEntryBytes = sizeof(PrepK) > sizeof(UnpackK) ? sizeof(PrepK) : sizeof(UnpackK);
+
+template <typename K, typename D, typename F>
+int run_batch(const D* descs, int n, void* table, int upload, cudaStream_t st, F make, void (*kern)(const long long*, const K*, int),
+              const char* what) {
+    static thread_local std::vector<uint8_t> host;
+    const size_t pre = ((size_t)(n + 1) * sizeof(long long) + 15) & ~(size_t)15;
+    long long grand = 0;
+    if (upload) {
+        host.assign(pre + (size_t)n * sizeof(K), 0);
+        long long* prefix = reinterpret_cast<long long*>(host.data());
+        K* tab = reinterpret_cast<K*>(host.data() + pre);
+        for (int i = 0; i < n; ++i) {
+            long long total = 0;
+            if (int e = make(descs + i, tab[i], total)) return e;
+            prefix[i] = grand;
+            grand += total;
+        }
+        prefix[n] = grand;
+        cudaError_t e = cudaMemcpyAsync(table, host.data(), host.size(), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { pb_set_error("%s: table upload: %s", what, cudaGetErrorString(e)); return PB_ECUDA; }
+    } else {
+        for (int i = 0; i < n; ++i) {               // only the element count is needed to size the grid
+            K tmp; long long total = 0;
+            if (int e = make(descs + i, tmp, total)) return e;
+            grand += total;
+        }
+    }
+    if (grand == 0) return PB_OK;
+    long long blocks = (grand + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    kern<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(table),
+                                           reinterpret_cast<const K*>(reinterpret_cast<const uint8_t*>(table) + pre), n);
+    return PB_OK;
+}
+}  // namespace
+
+extern "C" size_t pb_weight_batch_table_bytes(int n) {
+    return (((size_t)(n + 1) * sizeof(long long) + 15) & ~(size_t)15) + (size_t)n * kEntryBytes;
+}
+
+extern "C" int pb_weight_prep_batch(const pb_weight_prep_desc* descs, int n, void* table, int upload, pb_stream_t stream) {
+    PB_CHECK_ARG(descs && n > 0 && table, "bad argument");
+    if (int e = run_batch<PrepK>(descs, n, table, upload, (cudaStream_t)stream, make_prep, weight_prep_batch_kernel, __func__)) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_weight_grad_unpack_batch(const pb_weight_unpack_desc* descs, int n, void* table, int upload, pb_stream_t stream) {
+    PB_CHECK_ARG(descs && n > 0 && table, "bad argument");
+    if (int e = run_batch<UnpackK>(descs, n, table, upload, (cudaStream_t)stream, make_unpack, weight_unpack_batch_kernel, __func__)) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+namespace {
+int make_prep(const pb_weight_prep_desc* d, PrepK& k, long long& total) {
     PB_CHECK_ARG(d && d->groups >= 1 && d->groups <= 4, "1..4 weight groups");
     PB_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "ksize 1 or 3");
     PB_CHECK_ARG(d->cin >= 1 && d->cout >= 1, "bad channels");
-    PrepK k;
     k.G = d->groups; k.cin = d->cin; k.cout = d->cout; k.taps = d->ksize * d->ksize * d->ksize;
     for (int g = 0; g < 4; ++g) {
         k.w[g] = g < k.G ? d->w[g] : nullptr;
@@ -164,7 +268,15 @@ extern "C" int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream) 
         k.n_imgT = (long long)k.G * k.tilesT * 27 * k.nchT * k.ntT * 8;
     }
     k.n_bias = k.bias ? (long long)k.G * k.cout : 0;
-    const long long total = k.n_wk + k.n_wt + k.n_img + k.n_imgT + k.n_bias;
+    total = k.n_wk + k.n_wt + k.n_img + k.n_imgT + k.n_bias;
+    return PB_OK;
+}
+}  // namespace
+
+extern "C" int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream) {
+    PrepK k;
+    long long total = 0;
+    if (int e = make_prep(d, k, total)) return e;
     if (total == 0) return PB_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 8) blocks = 148LL * 8;
@@ -173,9 +285,9 @@ extern "C" int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream) 
     return PB_OK;
 }
 
-extern "C" int pb_weight_grad_unpack(const pb_weight_unpack_desc* d, pb_stream_t stream) {
+namespace {
+int make_unpack(const pb_weight_unpack_desc* d, UnpackK& k, long long& total) {
     PB_CHECK_ARG(d && d->dw && d->groups >= 1 && d->groups <= 4, "1..4 weight groups");
-    UnpackK k;
     k.dw = d->dw; k.db = d->db; k.dy_stats = d->dy_stats; k.npg = d->npg;
     k.G = d->groups; k.cin = d->cin; k.cout = d->cout; k.taps = d->ksize * d->ksize * d->ksize;
     for (int g = 0; g < 4; ++g) {
@@ -184,7 +296,16 @@ extern "C" int pb_weight_grad_unpack(const pb_weight_unpack_desc* d, pb_stream_t
         PB_CHECK_ARG(g >= k.G || k.gw[g], "null gradient pointer");
         PB_CHECK_ARG(g >= k.G || !(d->db || d->dy_stats) || k.gb[g], "null bias-gradient pointer");
     }
-    const long long total = (long long)k.G * k.cout * (k.cin * k.taps + ((k.db || k.dy_stats) ? 1 : 0));
+    k.accumulate = d->accumulate;
+    total = (long long)k.G * k.cout * ((long long)k.cin * k.taps + ((k.db || k.dy_stats) ? 1 : 0));
+    return PB_OK;
+}
+}  // namespace
+
+extern "C" int pb_weight_grad_unpack(const pb_weight_unpack_desc* d, pb_stream_t stream) {
+    UnpackK k;
+    long long total = 0;
+    if (int e = make_unpack(d, k, total)) return e;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 8) blocks = 148LL * 8;
     weight_unpack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k);

@@ -39,6 +39,7 @@ def _side_stream(device):
     st = _side.get(device)
     if st is None:
         st = _side[device] = torch.cuda.Stream(device=device)
+        ops.register_side_stream(device, st)
     return st
 
 

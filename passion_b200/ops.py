@@ -123,8 +123,14 @@ _scratch = _ZeroScratch()
 
 
 def begin_step(device):
-    """Call once at the start of a forward pass: recycles the zero scratch of the previous step."""
-    _scratch.begin_step(torch.device(device))
+    """Call once at the start of a forward pass: recycles the zero scratch of the previous step and refreshes the
+    kernel-layout copies of all registered conv weights in one launch."""
+    device = torch.device(device)
+    _scratch.begin_step(device)
+    if BATCH_WEIGHTS and device.type == "cuda":
+        c = _wcache.get(device)
+        if c is not None:
+            c.refresh(_lib.load(), device)
 
 
 def _conv_work(d, esize):
@@ -362,24 +368,249 @@ class _Conv3d(torch.autograd.Function):
         return dx0, dx1, dw, db, None, None, None, None, None
 
 
+BATCH_WEIGHTS = os.environ.get("PB_BATCH_WEIGHTS", "1") != "0"   # one weight-prep / one weight-grad-unpack launch per step
+
+
+class _WeightCache:
+    """Kernel-layout copies of every conv layer's parameters, kept in persistent buffers and refreshed by ONE batched launch
+    at the start of a step (`begin_step` -> pb_weight_prep_batch) instead of one launch per layer: the weights change once
+    per step, after the optimizer.  An entry is registered the first time a layer runs (that call prepares it alone); it is
+    used only while the parameters' version counters still equal those seen by the last refresh, so weights modified in
+    place outside the step protocol simply take the per-layer path again.  Entries die with their parameters."""
+
+    def __init__(self):
+        self.entries = {}            # key -> entry
+        self.dirty = False
+        self.table = None            # device scratch holding the packed descriptors of the batched launch
+        self.descs = None
+        self.n = 0
+
+    @staticmethod
+    def _versions(e):
+        ps = [r() for r in e["refs"]]
+        if any(p is None for p in ps):
+            return None
+        return tuple(p._version for p in ps)
+
+    def lookup(self, key):
+        e = self.entries.get(key)
+        if e is None:
+            return None
+        v = self._versions(e)
+        if v is None:
+            del self.entries[key]
+            self.dirty = True
+            return None
+        return e if v == e["versions"] else False          # False: registered but stale
+
+    def refresh(self, lib, device):
+        dead = [k for k, e in self.entries.items() if self._versions(e) is None]
+        for k in dead:
+            del self.entries[k]
+            self.dirty = True
+        if not self.entries:
+            return
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.dirty:
+            if capturing:
+                return                                     # cannot upload a new table inside a capture: per-layer path
+            ents = list(self.entries.values())
+            self.n = len(ents)
+            self.descs = (_lib.WeightPrepDesc * self.n)()
+            for d, e in zip(self.descs, ents):
+                ws, bs = e["ws"](), e["bs"]()
+                wk, wt, img, imgT, bias = e["outs"]
+                d.groups, d.cin, d.cout, d.ksize = len(ws), e["cin"], e["cout"], e["ksize"]
+                d.wk, d.wt, d.img, d.imgT, d.bias = (t.data_ptr() if t is not None else None for t in (wk, wt, img, imgT, bias))
+                d.nt, d.ntT = e["nt"], e["ntT"]
+                for g, w in enumerate(ws):
+                    d.w[g] = w.data_ptr()
+                    d.b[g] = bs[g].data_ptr() if bias is not None else None
+            need = int(lib.pb_weight_batch_table_bytes(self.n))
+            if self.table is None or self.table.numel() < need:
+                self.table = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        upload = 1 if self.dirty else 0
+        _run("weight_prep", "batch", 0, 0, lambda: lib.pb_weight_prep_batch(self.descs, self.n, _p(self.table), upload, _stream()))
+        self.dirty = False
+        for e in self.entries.values():
+            e["versions"] = self._versions(e)
+
+
+_wcache = {}
+
+
+def _wcache_for(device):
+    c = _wcache.get(device)
+    if c is None:
+        c = _wcache[device] = _WeightCache()
+    return c
+
+
 def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt=0, ntT=0, want_bias=False):
-    """One pb_weight_prep launch: parameter-layout weights of G groups -> the layouts asked for."""
+    """Parameter-layout weights of G groups -> the layouts asked for.  Served from the step's batched refresh when the layer
+    is registered and fresh, else one pb_weight_prep launch (which also registers the layer)."""
+    import weakref
     G = len(ws)
     dev = ws[0].device
+    cache = _wcache_for(dev) if BATCH_WEIGHTS else None
+    key = (tuple(id(w) for w in ws), bool(want_wk), bool(want_wt), nt, ntT, bool(want_bias))
+    e = cache.lookup(key) if cache is not None else None
+    if e:
+        return e["outs"]
     taps = ksize ** 3
     f32 = dict(dtype=torch.float32, device=dev)
-    wk = torch.empty((G, taps, cin, cout), **f32) if want_wk else None
-    wt = torch.empty((G, taps, cout, cin), **f32) if want_wt else None
-    img = torch.empty((G, (cout + nt - 1) // nt, 9, max(2, cin // 8), 3 * nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
-    imgT = torch.empty((G, (cin + ntT - 1) // ntT, 9, max(2, cout // 8), 3 * ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
-    bias = torch.empty((G, cout), **f32) if want_bias else None
+    if e is False:                                                   # registered but stale: refresh this layer in place
+        ent = cache.entries[key]
+        wk, wt, img, imgT, bias = ent["outs"]
+    else:
+        ent = None
+        wk = torch.empty((G, taps, cin, cout), **f32) if want_wk else None
+        wt = torch.empty((G, taps, cout, cin), **f32) if want_wt else None
+        img = torch.empty((G, (cout + nt - 1) // nt, 9, max(2, cin // 8), 3 * nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
+        imgT = torch.empty((G, (cin + ntT - 1) // ntT, 9, max(2, cout // 8), 3 * ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
+        bias = torch.empty((G, cout), **f32) if want_bias else None
     desc = _lib.WeightPrepDesc(groups=G, cin=cin, cout=cout, ksize=ksize, wk=_p(wk), wt=_p(wt), img=_p(img), nt=nt,
                                imgT=_p(imgT), ntT=ntT, bias=_p(bias))
     for g in range(G):
         desc.w[g] = ws[g].data_ptr()
         desc.b[g] = bs[g].data_ptr() if want_bias else None
     _run("weight_prep", f"c{cin}->{cout} k{ksize} g{G}", 0, 0, lambda: lib.pb_weight_prep(ctypes.byref(desc), _stream()))
+    if cache is not None and all(isinstance(w, torch.nn.Parameter) for w in ws):
+        params = list(ws) + (list(bs) if want_bias else [])
+        if ent is None:
+            # weak references only: the cache must not keep a dead model's parameters alive
+            wrefs, brefs = [weakref.ref(w) for w in ws], [weakref.ref(b) for b in bs] if want_bias else []
+            ent = dict(refs=[weakref.ref(p) for p in params], outs=(wk, wt, img, imgT, bias), cin=cin, cout=cout, ksize=ksize,
+                       nt=nt, ntT=ntT, ws=lambda r=wrefs: [x() for x in r], bs=lambda r=brefs: [x() for x in r])
+            cache.entries[key] = ent
+            cache.dirty = True
+        ent["versions"] = tuple(p._version for p in params)
     return wk, wt, img, imgT, bias
+
+
+def _unpack_desc(item, gws, gbs, accumulate, desc=None):
+    desc = desc if desc is not None else _lib.WeightUnpackDesc()
+    G = len(item["ws"])
+    desc.dw, desc.db = item["dw"].data_ptr(), None
+    desc.dy_stats = item["st"].data_ptr() if gbs is not None else None
+    desc.npg, desc.groups, desc.cin, desc.cout, desc.ksize = item["npg"], G, item["cin"], item["cout"], item["ksize"]
+    desc.accumulate = accumulate
+    for g in range(4):
+        desc.gw[g] = gws[g].data_ptr() if g < G else None
+        desc.gb[g] = gbs[g].data_ptr() if (g < G and gbs is not None) else None
+    return desc
+
+
+class _GradSink:
+    """Weight gradients of the conv layers of one backward pass, scattered into the parameters' .grad by ONE launch
+    (pb_weight_grad_unpack_batch) from an end-of-backward callback, instead of one scatter launch per layer.
+    A parameter without a .grad gets a persistent per-parameter buffer (pointer-stable, so the packed descriptor table is
+    uploaded only when something changed and the launch is CUDA-graph capturable); an existing .grad (DDP bucket views,
+    gradient accumulation) is added to."""
+
+    def __init__(self):
+        self.pending = []
+        self.bufs = {}               # id(param) -> (weakref, buffer)
+        self.table = None
+        self.sig = None
+        self.descs = None
+
+    def _buffer(self, p):
+        import weakref
+        ent = self.bufs.get(id(p))
+        if ent is None or ent[0]() is not p:
+            if len(self.bufs) > 4096:
+                self.bufs = {k: v for k, v in self.bufs.items() if v[0]() is not None}
+            ent = self.bufs[id(p)] = (weakref.ref(p), torch.empty_like(p, memory_format=torch.contiguous_format))
+        return ent[1]
+
+    def _target(self, p):
+        g = p.grad
+        if g is None:
+            p.grad = self._buffer(p)
+            return p.grad, 0
+        if g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape:
+            return g, 1
+        raise RuntimeError("passion_b200: conv parameter .grad must be a contiguous fp32 tensor of the parameter's shape")
+
+    def flush(self, device):
+        items, self.pending = self.pending, []
+        if not items:
+            return
+        lib = _lib.load()
+        rows, seen = [], set()
+        for it in items:
+            ps = list(it["ws"]) + list(it["bs"])
+            if any(id(p) in seen for p in ps):              # a parameter used by two conv calls: scatter what is queued first
+                self._launch(lib, rows, device)
+                rows, seen = [], set()
+            seen.update(id(p) for p in ps)
+            tg = [self._target(w) for w in it["ws"]]
+            tb = [self._target(b) for b in it["bs"]] if it["bs"] else None
+            acc = {a for _, a in tg} | ({a for _, a in tb} if tb else set())
+            if len(acc) != 1:
+                raise RuntimeError("passion_b200: weight and bias .grad of one conv layer must both exist or both be None")
+            rows.append((it, [t for t, _ in tg], [t for t, _ in tb] if tb else None, acc.pop()))
+        self._launch(lib, rows, device)
+
+    def _launch(self, lib, rows, device):
+        if not rows:
+            return
+        n = len(rows)
+        sig = tuple((it["dw"].data_ptr(), it["st"].data_ptr() if gbs is not None else 0, acc, tuple(t.data_ptr() for t in gws),
+                     tuple(t.data_ptr() for t in gbs) if gbs is not None else ()) for it, gws, gbs, acc in rows)
+        changed = sig != self.sig
+        if changed and torch.cuda.is_current_stream_capturing():
+            for it, gws, gbs, acc in rows:                  # a new table cannot be uploaded inside a capture
+                desc = _unpack_desc(it, gws, gbs, acc)
+                _run("weight_grad_unpack", "layer", 0, 0, lambda: lib.pb_weight_grad_unpack(ctypes.byref(desc), _stream()))
+            return
+        if changed:
+            self.descs = (_lib.WeightUnpackDesc * n)()
+            for d, (it, gws, gbs, acc) in zip(self.descs, rows):
+                _unpack_desc(it, gws, gbs, acc, d)
+            need = int(lib.pb_weight_batch_table_bytes(n))
+            if self.table is None or self.table.numel() < need:
+                self.table = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+            self.sig = sig
+        _run("weight_grad_unpack", "batch", 0, 0,
+             lambda: lib.pb_weight_grad_unpack_batch(self.descs, n, _p(self.table), 1 if changed else 0, _stream()))
+
+
+_sinks = {}
+
+
+def _queue_weight_grads(device, item):
+    sink = _sinks.get(device)
+    if sink is None:
+        sink = _sinks[device] = _GradSink()
+    if not sink.pending:
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: flush_weight_grads(device))
+    sink.pending.append(item)
+
+
+def flush_weight_grads(device):
+    """Runs at the end of the backward pass that queued conv weight gradients (autograd final callback, on the caller's
+    stream, after the engine has joined the streams the backward ran on)."""
+    sink = _sinks.get(device)
+    if sink is not None and sink.pending:
+        for st in _side_streams_of(device):
+            torch.cuda.current_stream(device).wait_stream(st)
+        sink.flush(device)
+
+
+_side_stream_registry = {}
+
+
+def register_side_stream(device, stream):
+    """Streams other than the caller's on which conv backward kernels may run (the models' decoder_sep stream)."""
+    _side_stream_registry.setdefault(device, [])
+    if stream not in _side_stream_registry[device]:
+        _side_stream_registry[device].append(stream)
+
+
+def _side_streams_of(device):
+    return _side_stream_registry.get(device, [])
 
 
 class _Conv3dRef(torch.autograd.Function):
@@ -412,7 +643,7 @@ class _Conv3dRef(torch.autograd.Function):
                                                _p(stats), _p(err), _stream())
         _conv_fwd_launch(lib, d, x0, x1, lambda: wk if wk is not None else _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=True)[0],
                          tc_call, bias, y, stats)
-        ctx.save_for_backward(x0, x1, *ws)
+        ctx.save_for_backward(x0, x1, *ws, *bs)
         ctx.bwd_w = (wt, imgT)
         ctx.cfg = (ksize, stride, pad_mode, G, has_bias)
         if want_stats:
@@ -425,7 +656,7 @@ class _Conv3dRef(torch.autograd.Function):
         lib = _lib.load()
         ksize, stride, pad_mode, G, has_bias = ctx.cfg
         x0, x1 = ctx.saved_tensors[:2]
-        ws = ctx.saved_tensors[2:]
+        ws = ctx.saved_tensors[2:2 + G]
         wt, imgT = ctx.bwd_w
         cout, cin = ws[0].shape[0], ws[0].shape[1]
         dy = dy.contiguous()
@@ -438,17 +669,20 @@ class _Conv3dRef(torch.autograd.Function):
         gws = [None] * G
         gbs = [None] * G if has_bias else []
         if need_dw or need_db:
-            gws = [torch.empty_like(w) for w in ws]
-            desc = _lib.WeightUnpackDesc(dw=_p(dw), db=None, dy_stats=None, npg=d.n // G, groups=G, cin=cin, cout=cout, ksize=ksize)
-            if need_db:
-                st = channel_stats(dy)
-                desc.dy_stats = st.data_ptr()
-                gbs = [torch.empty((cout,), dtype=torch.float32, device=dy.device) for _ in range(G)]
-            for g in range(G):
-                desc.gw[g] = gws[g].data_ptr()
-                desc.gb[g] = gbs[g].data_ptr() if need_db else None
-            _run("weight_grad_unpack", f"c{cin}->{cout} k{ksize} g{G}", 0, 0,
-                 lambda: lib.pb_weight_grad_unpack(ctypes.byref(desc), _stream()))
+            bs = ctx.saved_tensors[2 + G:] if has_bias else ()
+            st = channel_stats(dy) if need_db else None
+            item = dict(ws=ws, bs=bs if need_db else (), dw=dw, st=st, npg=d.n // G, cin=cin, cout=cout, ksize=ksize)
+            if (BATCH_WEIGHTS and need_dw and all(w.is_leaf and w.requires_grad for w in ws)
+                    and (not has_bias or (need_db and all(b.is_leaf and b.requires_grad for b in bs)))):
+                # leaf parameters: their .grad is written by ONE batched scatter launch when this backward pass ends
+                _queue_weight_grads(dy.device, item)
+            else:
+                gws = [torch.empty_like(w) for w in ws]
+                if need_db:
+                    gbs = [torch.empty((cout,), dtype=torch.float32, device=dy.device) for _ in range(G)]
+                desc = _unpack_desc(item, gws, gbs if need_db else None, 0)
+                _run("weight_grad_unpack", f"c{cin}->{cout} k{ksize} g{G}", 0, 0,
+                     lambda: lib.pb_weight_grad_unpack(ctypes.byref(desc), _stream()))
         return (dx0, dx1, None, None, None, None, None, *gws, *gbs)
 
 
