@@ -498,15 +498,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    if (warp < 4) {
-#pragma unroll 1
-        for (int c = 0; c < TMEM_COLS; c += 16) tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
-        tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;          // no zero fill: the first MMA into a block overwrites it (accumulate = 0)
 
     if (warp >= 5) {
         // =============================== producers (as conv3_tc_kernel; tiles advance by kKwsStride) ===============================
@@ -592,8 +584,19 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
                     const int nb = od_hi - od_lo + 1;
                     const int row0 = (2 - (pl - od_lo)) * NB;                  // weight rows: kd = 2, 1, 0 blocks of [kw][co]
                     const int blk0 = (int)((j0 + od_lo) % R);
-                    const int n1 = blk0 + nb > R ? R - blk0 : nb;
                     const uint64_t a0 = umma_desc(slab_addr + (k % kSlots) * slot_bytes, (uint32_t)p.slab_e * 16, 128);
+                    // output plane pl (if any) gets its FIRST contribution from this input plane: that block is written with
+                    // accumulate = 0 by the first instruction, so the epilogue never has to zero a block (and hands it back as soon
+                    // as it has been read); every other (block, instruction) accumulates
+                    const bool has_new = pl < nout;
+                    const int nb_old = nb - (has_new ? 1 : 0);
+                    auto issue = [&](uint64_t ad, uint64_t bd, int first_blk, int nblk, uint32_t acc) {     // nblk consecutive ring blocks
+                        const int b0i = (blk0 + first_blk) % R;
+                        const int m1 = b0i + nblk > R ? R - b0i : nblk;
+                        const uint64_t bdd = bd + (uint64_t)(uint32_t)(first_blk * NB);
+                        umma_f16(tmem_base + b0i * NB, ad, bdd, umma_idesc(kTileM, m1 * NB), acc);
+                        if (m1 < nblk) umma_f16(tmem_base, ad, bdd + (uint64_t)(uint32_t)(m1 * NB), umma_idesc(kTileM, (nblk - m1) * NB), acc);
+                    };
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
                         const uint64_t a1 = a0 + (uint64_t)(uint32_t)(kh * p.PW);
@@ -601,8 +604,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
                         for (int ks = 0; ks < KS; ++ks) {
                             const uint64_t ad = a1 + (uint64_t)(uint32_t)(2 * ks * p.slab_e);
                             const uint64_t bd = b0 + (uint64_t)(uint32_t)((kh * NCH + 2 * ks) * 9 * NT + row0);
-                            umma_f16(tmem_base + blk0 * NB, ad, bd, umma_idesc(kTileM, n1 * NB), 1u);
-                            if (n1 < nb) umma_f16(tmem_base, ad, bd + (uint64_t)(uint32_t)(n1 * NB), umma_idesc(kTileM, (nb - n1) * NB), 1u);
+                            if (kh == 0 && ks == 0 && has_new) {
+                                if (nb_old > 0) issue(ad, bd, 0, nb_old, 1u);
+                                issue(ad, bd, nb_old, 1, 0u);
+                            } else {
+                                issue(ad, bd, 0, nb, 1u);
+                            }
                         }
                     }
                     umma_commit(&empty[k % kSlots]);
@@ -617,8 +624,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
         const int cout = p.CO0 + p.CO1;
         const int cb0 = nt * NT;
         const float4* bias4 = bias != nullptr ? reinterpret_cast<const float4*>(bias + (size_t)g * cout + cb0) : nullptr;
-        uint32_t j = 0, prev_blk = 0;
-        bool have_prev = false;
+        uint32_t j = 0;
         const int tl = warp * 32 + lane;
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int dc = it % p.ND, r1 = it / p.ND;
@@ -645,33 +651,37 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
                     tmem_ld8(taddr + c, v0 + c); tmem_ld8(taddr + NT + c, v1 + c); tmem_ld8(taddr + 2 * NT + c, v2 + c);
                 }
                 tmem_wait_ld();
-                if (have_prev) {
-                    tmem_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(&blk_empty[prev_blk]);
-                }
-#pragma unroll
-                for (int c = 0; c < NB; c += 16) tmem_zero16(taddr + c);
-                prev_blk = blk; have_prev = true;
+                tc_fence_before();
+                mbar_arrive(&blk_empty[blk]);                  // the block is in registers: the MMA thread may overwrite it
                 // rows 0 / 1 of this warp are rows 32 / 33 of its left neighbour
-                float* xw = xch + ((j & 1) * 4 + warp) * 3 * NT;
-                if (lane == 0) {
+                if (lane < 2) {
+                    float4* xw = reinterpret_cast<float4*>(xch + ((j & 1) * 4 + warp) * 3 * NT);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int c = 0; c < CRE; ++c) { xw[c] = v1[c]; xw[NT + c] = v2[c]; }
-                } else if (lane == 1) {
+                        for (int c = 0; c < CRE; c += 4) {
+                            xw[c / 4] = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
+                            xw[NT / 4 + c / 4] = make_float4(v2[c], v2[c + 1], v2[c + 2], v2[c + 3]);
+                        }
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < CRE; ++c) xw[2 * NT + c] = v2[c];
+                        for (int c = 0; c < CRE; c += 4) xw[2 * NT / 4 + c / 4] = make_float4(v2[c], v2[c + 1], v2[c + 2], v2[c + 3]);
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                const float* xn = xch + ((j & 1) * 4 + ((warp + 1) & 3)) * 3 * NT;
+                const float4* xn = reinterpret_cast<const float4*>(xch + ((j & 1) * 4 + ((warp + 1) & 3)) * 3 * NT);
                 float y[CRE];
 #pragma unroll
-                for (int c = 0; c < CRE; ++c) {
-                    float a1 = __shfl_down_sync(0xffffffffu, v1[c], 1);
-                    float a2 = __shfl_down_sync(0xffffffffu, v2[c], 2);
-                    if (lane == 31) { a1 = xn[c]; a2 = xn[2 * NT + c]; }
-                    else if (lane == 30) a2 = xn[NT + c];
-                    y[c] = v0[c] + a1 + a2;
+                for (int c = 0; c < CRE; c += 4) {              // broadcast loads, selects instead of branches
+                    const float4 n0 = xn[c / 4], n1 = xn[NT / 4 + c / 4], n2 = xn[2 * NT / 4 + c / 4];
+                    const float e0[4] = {n0.x, n0.y, n0.z, n0.w}, e1[4] = {n1.x, n1.y, n1.z, n1.w}, e2[4] = {n2.x, n2.y, n2.z, n2.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float a1 = __shfl_down_sync(0xffffffffu, v1[c + i], 1);
+                        float a2 = __shfl_down_sync(0xffffffffu, v2[c + i], 2);
+                        a1 = lane == 31 ? e0[i] : a1;
+                        a2 = lane == 31 ? e2[i] : (lane == 30 ? e1[i] : a2);
+                        y[c + i] = v0[c + i] + a1 + a2;
+                    }
                 }
                 if (bias4 != nullptr) {
 #pragma unroll
@@ -712,7 +722,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
                 }
             }
         }
-        if (have_prev) tmem_wait_st();
     }
     tc_fence_before();
     __syncthreads();
@@ -735,7 +744,7 @@ int launch_tc_kws(const TcP& p, const void* x0, const void* x1, const void* wimg
     if (e != cudaSuccess) { pb_set_error("conv3d_tc_kws: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
     const int items = p.npg * p.QT * p.ND;
     int ctas = 148 / (p.groups * p.nt_tiles);
-    if (smem <= 110 * 1024) ctas *= 2;
+    if (smem <= 113 * 1024) ctas *= 2;           // two CTAs per SM: 2 x (smem + 1 KB reserved per CTA) <= 228 KB
     if (ctas < 1) ctas = 1;
     if (ctas > items) ctas = items;
     kern<<<dim3(ctas, p.groups, p.nt_tiles), kTcThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,

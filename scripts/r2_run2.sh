@@ -6,10 +6,13 @@ timeout 900 python -m pytest tests/test_model_gpu.py tests/test_model_full_gpu.p
 PB_DUMP_KERNELS=$OUT/kernels_kws1.txt timeout 600 python bench.py --no-cpu-baseline > $OUT/bench_kws1.json 2> $OUT/bench_kws1.err; echo "bench kws1 rc=$?" >> $OUT/summary.txt
 PB_TC_KWS=0 PB_DUMP_KERNELS=$OUT/kernels_kws0.txt timeout 600 python bench.py --no-cpu-baseline > $OUT/bench_kws0.json 2> $OUT/bench_kws0.err; echo "bench kws0 rc=$?" >> $OUT/summary.txt
 PB_BATCH_WEIGHTS=0 timeout 600 python bench.py --no-cpu-baseline > $OUT/bench_b0.json 2> $OUT/bench_b0.err; echo "bench batch0 rc=$?" >> $OUT/summary.txt
+PB_PW2=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider -k "_k1_" > $OUT/kern_pw2.log 2>&1; echo "kernels(pw2) rc=$?" >> $OUT/summary.txt; tail -3 $OUT/kern_pw2.log >> $OUT/summary.txt
+PB_PW2=1 timeout 600 python bench.py --no-cpu-baseline > $OUT/bench_pw2.json 2> $OUT/bench_pw2.err; echo "bench pw2 rc=$?" >> $OUT/summary.txt
+timeout 300 python scripts/profile_glue.py > $OUT/glue.txt 2> $OUT/glue.err; echo "glue rc=$?" >> $OUT/summary.txt
 cat $OUT/summary.txt
 python - <<'P'
 import json
-for t in ("kws1","kws0","b0"):
+for t in ("kws1","kws0","b0","pw2"):
     try:
         d=json.loads(open(f"gpurun_out/r2b/bench_{t}.json").read()); print(t, d["ms_per_step"], d["gpu_launches"], d["roofline"]["families_ms_per_step"])
     except Exception as e: print(t, "ERR", e)
