@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
     uint64_t* blk_empty = blk_full + R;
     uint64_t* wbar = blk_empty + R;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-    float* xch = reinterpret_cast<float*>(tmem_slot + 4);          // [2][4 warps][3][NT]
+    float* xch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [2][4 warps][3][NT], 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.y, nt = blockIdx.z;
@@ -737,7 +737,7 @@ int launch_tc_kws(const TcP& p, const void* x0, const void* x1, const void* wimg
     constexpr int kSlots = NCHR >= 16 ? 2 : 6;
     const size_t w_bytes = (size_t)27 * NCH * 16 * 16;
     const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 2 * 16 + 1) * 8 + 16
-                        + 2 * 4 * 3 * 16 * sizeof(float);
+                        + 2 * 4 * 3 * 16 * sizeof(float) + 16;
     auto kern = conv3_tc_kws_kernel<NCHR, CR>;
     if (smem > 227 * 1024) { pb_set_error("conv3d_tc_kws: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
