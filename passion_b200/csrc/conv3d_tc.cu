@@ -1388,10 +1388,14 @@ extern "C" int pb_conv3d_tc_ntile(int cin, int cout) {
 }
 
 // 1 = the (cin, cout) class runs on the kw-stacked kernel (conv3_tc_kws_kernel) and its weight image uses that kernel's
-// layout [G][tile][3 kh][chunk][rows: kd = 2,1,0 | kw | 16 co][8]; PB_TC_KWS=0 switches the variant off (A/B measurements).
+// layout [G][tile][3 kh][chunk][rows: kd = 2,1,0 | kw | 16 co][8].  Measured (profiles/r02_conv_tc_kws.txt): faster than
+// conv3_tc_kernel for Cout = 8 (one 8-channel epilogue pass per plane: -16..19 % per launch), slower for Cout = 16 (the
+// shifted sum over 16 channels makes the four epilogue warps the bottleneck), so only Cout = 8 is routed here by default.
+// PB_TC_KWS=0 switches the variant off, PB_TC_KWS=2 also routes Cout = 16 (A/B measurements).
 extern "C" int pb_conv3d_tc_kws(int cin, int cout) {
-    static const bool on = [] { const char* e = getenv("PB_TC_KWS"); return !(e != nullptr && e[0] == '0'); }();
-    return on && pb_conv3d_tc_ntile(cin, cout) == 16 && cout <= 16 ? 1 : 0;
+    static const int mode = [] { const char* e = getenv("PB_TC_KWS"); return e != nullptr && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1; }();
+    if (mode == 0 || pb_conv3d_tc_ntile(cin, cout) != 16) return 0;
+    return cout == 8 || (mode == 2 && cout == 16) ? 1 : 0;
 }
 
 namespace {

@@ -385,7 +385,9 @@ class Model(nn.Module):
             sep_logits = self.decoder_sep.run(*feat)                          # [4B,D,H,W,C], modality-major
         else:
             torch.cuda.current_stream(dev).wait_stream(_rf._side_stream(dev))
-        sep_prob = ops.softmax4(sep_logits).view(4, B, D, H, W, -1) * e[:, :, None, None, None, None]     # :480-483
+        # mmformer.py:480-483 zeroes a missing modality's probabilities; its loss is multiplied by the same 0 below, so the
+        # product over the volume is skipped (see models/rfnet.py)
+        sep_prob = ops.softmax4(sep_logits).view(4, B, D, H, W, -1)
         self.last["sep_prob"] = sep_prob
         labels, cnt, wgt = crit.label_stats(target)
 

@@ -368,8 +368,9 @@ class Model(nn.Module):
             torch.cuda.current_stream(x.device).wait_stream(_side_stream(x.device))
         sep_prob = ops.softmax4(sep_logits).view(4, B, D, H, W, -1)
         e = (fm if idt else torch.ones_like(fm)).t()                          # [4(m),B]
-        if idt:
-            sep_prob = sep_prob * e[:, :, None, None, None, None]             # rfnet.py:259-260
+        # rfnet.py:259-260 multiplies the probabilities of a MISSING modality by 0 before the loss; that sample's loss is then
+        # multiplied by the same 0 below (and again in train.py:260), so value and gradient are exactly 0 either way and the
+        # 131 MB element-wise product (and its backward) is skipped: e * f(p) == e * f(e * p) for e in {0, 1}, f finite
         self.last["sep_prob"] = sep_prob
 
         labels, cnt, wgt = crit.label_stats(target)
