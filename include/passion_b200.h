@@ -144,6 +144,8 @@ typedef struct {
     void* imgT;
     int ntT;
     float* bias;
+    int w_cin_stride;       /* 0 = cin.  > cin: each w[g] points at a cin-SLICE of a wider parameter [cout][w_cin_stride][k][k][k]
+                             * (the single-modality decoder passes read one modality's quarter of a 4C-input 1x1x1 conv) */
 } pb_weight_prep_desc;
 typedef struct {
     const float* dw;
@@ -154,6 +156,7 @@ typedef struct {
     float* gb[4];
     int groups, cin, cout, ksize;
     int accumulate;         /* 0: gw / gb are overwritten; 1: added to (autograd's accumulation into an existing .grad) */
+    int w_cin_stride;       /* as in pb_weight_prep_desc: gw[g] points at a cin-slice of a wider gradient tensor */
 } pb_weight_unpack_desc;
 int pb_weight_prep(const pb_weight_prep_desc* d, pb_stream_t stream);
 int pb_weight_grad_unpack(const pb_weight_unpack_desc* d, pb_stream_t stream);

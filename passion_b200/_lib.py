@@ -29,7 +29,7 @@ class WeightPrepDesc(ctypes.Structure):
     _fields_ = [("w", ctypes.c_void_p * 4), ("b", ctypes.c_void_p * 4),
                 ("groups", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32),
                 ("wk", ctypes.c_void_p), ("wt", ctypes.c_void_p), ("img", ctypes.c_void_p), ("nt", ctypes.c_int32),
-                ("imgT", ctypes.c_void_p), ("ntT", ctypes.c_int32), ("bias", ctypes.c_void_p)]
+                ("imgT", ctypes.c_void_p), ("ntT", ctypes.c_int32), ("bias", ctypes.c_void_p), ("w_cin_stride", ctypes.c_int32)]
 
 
 class WeightUnpackDesc(ctypes.Structure):
@@ -37,7 +37,7 @@ class WeightUnpackDesc(ctypes.Structure):
     _fields_ = [("dw", ctypes.c_void_p), ("db", ctypes.c_void_p), ("dy_stats", ctypes.c_void_p), ("npg", ctypes.c_int32),
                 ("gw", ctypes.c_void_p * 4), ("gb", ctypes.c_void_p * 4),
                 ("groups", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32),
-                ("accumulate", ctypes.c_int32)]
+                ("accumulate", ctypes.c_int32), ("w_cin_stride", ctypes.c_int32)]
 
 
 class AugmentSample(ctypes.Structure):

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ y, cons
 }
 
 // R[n][v][i*C+c] = p_i * sum_k gate[n][i][k] y[n][v][k*C+c]   (K = 4 modalities, 4 classes)
-template <typename T, int VEC>
+template <typename T, int VEC, int K>
 __global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ y, const float* __restrict__ p, const float* __restrict__ gate,
                                                   T* __restrict__ r, long long voxels, int c, long long total) {
     const int cv = c / VEC;
@@ -69,10 +69,10 @@ __global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ y, const
         const int n = (int)(nv / voxels);
         const float4 pv = __ldg(reinterpret_cast<const float4*>(p) + nv);
         const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
-        const float* g = gate + (size_t)n * 16;
-        float yv[4][VEC];
+        const float* g = gate + (size_t)n * 4 * K;
+        float yv[K][VEC];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) VecIO<T, VEC>::load(y + nv * 4 * c + k * c + cl * VEC, yv[k]);
+        for (int k = 0; k < K; ++k) VecIO<T, VEC>::load(y + nv * K * c + k * c + cl * VEC, yv[k]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float o[VEC];
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ y, const
             for (int j = 0; j < VEC; ++j) {
                 float s = 0.f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) s = fmaf(__ldg(g + i * 4 + k), yv[k][j], s);
+                for (int k = 0; k < K; ++k) s = fmaf(__ldg(g + i * K + k), yv[k][j], s);
                 o[j] = s * pp[i];
             }
             VecIO<T, VEC>::store(r + nv * 4 * c + i * c + cl * VEC, o);
@@ -89,60 +89,60 @@ __global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ y, const
 }
 
 // dgate[n][i][k] += sum_{v,c} p_i y[k*C+c] dR[i*C+c].   grid = (blocks_per_sample, n)
-template <typename T, int VEC>
+template <typename T, int VEC, int K>
 __global__ void __launch_bounds__(256) mix_bwd_gate_kernel(const T* __restrict__ y, const float* __restrict__ p, const T* __restrict__ dr,
                                                            double* __restrict__ dgate, long long voxels, int c) {
-    __shared__ float red[8][16];
+    __shared__ float red[8][4 * K];
     const int n = blockIdx.y, cv = c / VEC;
-    float acc[16];
+    float acc[4 * K];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4 * K; ++i) acc[i] = 0.f;
     const long long total = voxels * cv;
     for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
         const int cl = (int)(t % cv);
         const long long nv = (size_t)n * voxels + t / cv;
         const float4 pv = __ldg(reinterpret_cast<const float4*>(p) + nv);
         const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
-        float yv[4][VEC];
+        float yv[K][VEC];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) VecIO<T, VEC>::load(y + nv * 4 * c + k * c + cl * VEC, yv[k]);
+        for (int k = 0; k < K; ++k) VecIO<T, VEC>::load(y + nv * K * c + k * c + cl * VEC, yv[k]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float g[VEC];
             VecIO<T, VEC>::load(dr + nv * 4 * c + i * c + cl * VEC, g);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < K; ++k) {
                 float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) s = fmaf(yv[k][j], g[j], s);
-                acc[i * 4 + k] = fmaf(s, pp[i], acc[i * 4 + k]);
+                acc[i * K + k] = fmaf(s, pp[i], acc[i * K + k]);
             }
         }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 4 * K; ++i) {
         const float s = warp_sum(acc[i]);
         if (lane == 0) red[wid][i] = s;
     }
     __syncthreads();
-    if (threadIdx.x < 16) {
+    if (threadIdx.x < 4 * K) {
         float s = 0.f;
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
-        atomicAdd(&dgate[(size_t)n * 16 + threadIdx.x], (double)s);
+        atomicAdd(&dgate[(size_t)n * 4 * K + threadIdx.x], (double)s);
     }
 }
 
 // dy[n][v][k*C+c] = sum_i p_i (gate[n][i][k] dR[n][v][i*C+c] + dS[n][i][k*C+c]).  grid = (blocks_per_sample, n)
-template <typename T, int VEC>
+template <typename T, int VEC, int K>
 __global__ void __launch_bounds__(256) bwd_y_kernel(const float* __restrict__ p, const float* __restrict__ gate, const T* __restrict__ dr,
                                                     const float* __restrict__ dS, T* __restrict__ dy, long long voxels, int c) {
-    extern __shared__ __align__(16) float sds[];              // dS[n] : [4][4*c], then gate[16]
-    const int n = blockIdx.y, cv = c / VEC, kc = 4 * c;
+    extern __shared__ __align__(16) float sds[];              // dS[n] : [4][K*c], then gate[4*K]
+    const int n = blockIdx.y, cv = c / VEC, kc = K * c;
     for (int i = threadIdx.x; i < 4 * kc; i += 256) sds[i] = dS[(size_t)n * 4 * kc + i];
     float* sg = sds + 4 * kc;
-    if (threadIdx.x < 16) sg[threadIdx.x] = gate[(size_t)n * 16 + threadIdx.x];
+    if (threadIdx.x < 4 * K) sg[threadIdx.x] = gate[(size_t)n * 4 * K + threadIdx.x];
     __syncthreads();
     const long long total = voxels * cv;
     for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
@@ -152,15 +152,15 @@ __global__ void __launch_bounds__(256) bwd_y_kernel(const float* __restrict__ p,
         const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
         float g[4][VEC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) VecIO<T, VEC>::load(dr + nv * kc + i * c + cl * VEC, g[i]);
+        for (int i = 0; i < 4; ++i) VecIO<T, VEC>::load(dr + nv * 4 * c + i * c + cl * VEC, g[i]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < K; ++k) {
             float o[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 float s = 0.f;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s = fmaf(pp[i], fmaf(sg[i * 4 + k], g[i][j], sds[i * kc + k * c + cl * VEC + j]), s);
+                for (int i = 0; i < 4; ++i) s = fmaf(pp[i], fmaf(sg[i * K + k], g[i][j], sds[i * kc + k * c + cl * VEC + j]), s);
                 o[j] = s;
             }
             VecIO<T, VEC>::store(dy + nv * kc + k * c + cl * VEC, o);
@@ -208,13 +208,14 @@ extern "C" int pb_rfm_pool(int dtype, const void* y, const float* p, double* S, 
 
 extern "C" int pb_rfm_mix(int dtype, const void* y, const float* p, const float* gate, void* r, int n, long long voxels, int k,
                           int c, pb_stream_t stream) {
-    PB_CHECK_ARG(y && p && gate && r && n > 0 && voxels > 0 && k == 4 && c > 0, "bad argument (k must be 4)");
+    PB_CHECK_ARG(y && p && gate && r && n > 0 && voxels > 0 && (k == 4 || k == 1) && c > 0, "bad argument (k must be 1 or 4)");
     cudaStream_t st = (cudaStream_t)stream;
     RFM_DISPATCH(c, {
         const long long total = (long long)n * voxels * (c / VEC);
         long long blocks = (total + 255) / 256;
         if (blocks > 148LL * 16) blocks = 148LL * 16;
-        mix_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)y, p, gate, (T*)r, voxels, c, total);
+        if (k == 4) mix_kernel<T, VEC, 4><<<(int)blocks, 256, 0, st>>>((const T*)y, p, gate, (T*)r, voxels, c, total);
+        else        mix_kernel<T, VEC, 1><<<(int)blocks, 256, 0, st>>>((const T*)y, p, gate, (T*)r, voxels, c, total);
     });
     PB_CHECK_LAUNCH();
     return PB_OK;
@@ -222,11 +223,12 @@ extern "C" int pb_rfm_mix(int dtype, const void* y, const float* p, const float*
 
 extern "C" int pb_rfm_mix_bwd_gate(int dtype, const void* y, const float* p, const void* dr, double* dgate, int n,
                                    long long voxels, int k, int c, pb_stream_t stream) {
-    PB_CHECK_ARG(y && p && dr && dgate && n > 0 && voxels > 0 && k == 4 && c > 0, "bad argument (k must be 4)");
+    PB_CHECK_ARG(y && p && dr && dgate && n > 0 && voxels > 0 && (k == 4 || k == 1) && c > 0, "bad argument (k must be 1 or 4)");
     cudaStream_t st = (cudaStream_t)stream;
     RFM_DISPATCH(c, {
         const int bps = blocks_per_sample(voxels * (c / VEC), n);
-        mix_bwd_gate_kernel<T, VEC><<<dim3(bps, n), 256, 0, st>>>((const T*)y, p, (const T*)dr, dgate, voxels, c);
+        if (k == 4) mix_bwd_gate_kernel<T, VEC, 4><<<dim3(bps, n), 256, 0, st>>>((const T*)y, p, (const T*)dr, dgate, voxels, c);
+        else        mix_bwd_gate_kernel<T, VEC, 1><<<dim3(bps, n), 256, 0, st>>>((const T*)y, p, (const T*)dr, dgate, voxels, c);
     });
     PB_CHECK_LAUNCH();
     return PB_OK;
@@ -234,11 +236,13 @@ extern "C" int pb_rfm_mix_bwd_gate(int dtype, const void* y, const float* p, con
 
 extern "C" int pb_rfm_bwd_y(int dtype, const float* p, const float* gate, const void* dr, const float* dS, void* dy, int n,
                             long long voxels, int k, int c, pb_stream_t stream) {
-    PB_CHECK_ARG(p && gate && dr && dS && dy && n > 0 && voxels > 0 && k == 4 && c > 0, "bad argument (k must be 4)");
+    PB_CHECK_ARG(p && gate && dr && dS && dy && n > 0 && voxels > 0 && (k == 4 || k == 1) && c > 0, "bad argument (k must be 1 or 4)");
     cudaStream_t st = (cudaStream_t)stream;
     RFM_DISPATCH(c, {
         const int bps = blocks_per_sample(voxels * (c / VEC), n);
-        bwd_y_kernel<T, VEC><<<dim3(bps, n), 256, (16 * c + 16) * sizeof(float), st>>>(p, gate, (const T*)dr, dS, (T*)dy, voxels, c);
+        const size_t sm = (size_t)(4 * k * c + 16) * sizeof(float);
+        if (k == 4) bwd_y_kernel<T, VEC, 4><<<dim3(bps, n), 256, sm, st>>>(p, gate, (const T*)dr, dS, (T*)dy, voxels, c);
+        else        bwd_y_kernel<T, VEC, 1><<<dim3(bps, n), 256, sm, st>>>(p, gate, (const T*)dr, dS, (T*)dy, voxels, c);
     });
     PB_CHECK_LAUNCH();
     return PB_OK;

@@ -21,6 +21,7 @@ struct PrepK {
     int nt, ntT;
     long long n_wk, n_wt, n_img, n_imgT, n_bias;
     int nch, tiles, nchT, tilesT;
+    int wstride;            // cin extent of the PARAMETER a group reads from (= cin unless the group is a cin-slice of a wider weight)
     int kws, kwsT;          // image layout of the kw-stacked kernel: [g][tile][3 kh][chunk][rows: kd = 2,1,0 | kw | nt co][8]
 };
 
@@ -31,7 +32,7 @@ __device__ __forceinline__ void img_row(int kws, int nt, int t, int row, int& ta
 }
 
 __device__ __forceinline__ float ref_w(const PrepK& k, int g, int co, int ci, int tap) {
-    return __ldg(k.w[g] + ((size_t)co * k.cin + ci) * k.taps + tap);
+    return __ldg(k.w[g] + ((size_t)co * k.wstride + ci) * k.taps + tap);
 }
 
 __device__ __forceinline__ void prep_element(const PrepK& k, const long long t) {
@@ -125,6 +126,7 @@ struct UnpackK {
     const float* dw; const float* db; const double* dy_stats; int npg;
     float* gw[4]; float* gb[4];
     int G, cin, cout, taps;
+    int wstride;            // see PrepK
     int accumulate;         // 1: add to what gw / gb hold (autograd's accumulation semantics), 0: overwrite
 };
 
@@ -140,7 +142,8 @@ __device__ __forceinline__ void unpack_element(const UnpackK& k, const long long
             const int ci = (int)(i % k.cin);
             const int co = (int)(i / k.cin);
             const float v = __ldg(k.dw + (((size_t)g * k.taps + tap) * k.cin + ci) * k.cout + co);
-            k.gw[g][o] = k.accumulate ? k.gw[g][o] + v : v;
+            float* dst = k.gw[g] + ((size_t)co * k.wstride + ci) * k.taps + tap;
+            *dst = k.accumulate ? *dst + v : v;
         } else {
             const long long i = t - n_w;
             const int g = (int)(i / k.cout), co = (int)(i % k.cout);
@@ -240,6 +243,8 @@ int make_prep(const pb_weight_prep_desc* d, PrepK& k, long long& total) {
     PB_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "ksize 1 or 3");
     PB_CHECK_ARG(d->cin >= 1 && d->cout >= 1, "bad channels");
     k.G = d->groups; k.cin = d->cin; k.cout = d->cout; k.taps = d->ksize * d->ksize * d->ksize;
+    k.wstride = d->w_cin_stride > 0 ? d->w_cin_stride : d->cin;
+    PB_CHECK_ARG(k.wstride >= k.cin, "w_cin_stride < cin");
     for (int g = 0; g < 4; ++g) {
         k.w[g] = g < k.G ? d->w[g] : nullptr;
         k.b[g] = g < k.G ? d->b[g] : nullptr;
@@ -290,6 +295,8 @@ int make_unpack(const pb_weight_unpack_desc* d, UnpackK& k, long long& total) {
     PB_CHECK_ARG(d && d->dw && d->groups >= 1 && d->groups <= 4, "1..4 weight groups");
     k.dw = d->dw; k.db = d->db; k.dy_stats = d->dy_stats; k.npg = d->npg;
     k.G = d->groups; k.cin = d->cin; k.cout = d->cout; k.taps = d->ksize * d->ksize * d->ksize;
+    k.wstride = d->w_cin_stride > 0 ? d->w_cin_stride : d->cin;
+    PB_CHECK_ARG(k.wstride >= k.cin, "w_cin_stride < cin");
     for (int g = 0; g < 4; ++g) {
         k.gw[g] = g < k.G ? d->gw[g] : nullptr;
         k.gb[g] = g < k.G ? d->gb[g] : nullptr;

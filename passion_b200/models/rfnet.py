@@ -32,6 +32,7 @@ basic_dims = 8
 num_modals = 4
 SEP_STREAM = os.environ.get("PB_SEP_STREAM", "1") != "0"     # run decoder_sep concurrently with decoder_fuse (measured: -0.9 ms/step)
 SIDE_RECORD = os.environ.get("PB_SIDE_RECORD", "1") != "0"   # debugging switch for _lend_to_stream (keep on)
+SPARSE_SINGLES = os.environ.get("PB_SPARSE_SINGLES", "1") != "0"   # single-modality passes without their 3/4-zero stacks
 _side = {}
 
 
@@ -72,6 +73,18 @@ class general_conv3d(nn.Module):
                                   pad_mode=self.pad_type, res=res)
         # the bias cancels in InstanceNorm: give it an exact-zero gradient (keeps optimizer state shape)
         return _ZeroGradTouch.apply(y, self.conv.bias)
+
+    def run_stack(self, y, enc=None):
+        """A conv over the 4-modality stack: `y` [Nd,...,4C] holds the dense passes; `enc` [4B,...,C] (modality-major encoder
+        output), if given, stands for four further single-modality passes (pass m: modality m in slot m, zeros elsewhere).
+        For those only the m-th cin-quarter of the weight matters, so they run as ONE grouped conv on `enc` itself — a quarter
+        of the bytes and FLOPs, and their 3/4-zero stacks are never built.  Returns the passes concatenated along the batch."""
+        out = self.run(y)
+        if enc is None:
+            return out
+        single = ops.conv_in_lrelu_ref(enc, [self.conv.weight], ksize=self.k_size, stride=self.stride, pad_mode=self.pad_type,
+                                       slices=4)
+        return torch.cat((out, single), 0)
 
 
 class _ZeroGradTouch(torch.autograd.Function):
@@ -171,6 +184,11 @@ def _run_seq(seq, x):
     return x
 
 
+def _run_stack_seq(seq, y, enc):
+    """first layer on the 4-modality stack (dense passes `y` + single-modality passes `enc`), the rest on the joint batch"""
+    return _run_seq(list(seq)[1:], seq[0].run_stack(y, enc))
+
+
 class region_aware_modal_fusion(nn.Module):
     """blocks.py:582-626."""
 
@@ -182,16 +200,23 @@ class region_aware_modal_fusion(nn.Module):
                                        general_conv3d(in_channel, in_channel, k_size=3, padding=1),
                                        general_conv3d(in_channel, in_channel // 2, k_size=1, padding=0))
 
-    def run(self, y, prm):
-        """y [N,D,H,W,4C] masked features (channel = modality*C + c); prm [N,D,H,W,4] fp32 detached probs."""
+    def run(self, y, prm, enc=None):
+        """y [Nd,D,H,W,4C] masked features of the dense passes (channel = modality*C + c); prm [N,D,H,W,4] fp32 detached
+        probs of ALL passes; enc [4B,D,H,W,C]: four further single-modality passes (see general_conv3d.run_stack)."""
         mf = self.modal_fusion
         w0 = torch.stack([m.weight_layer[0].weight.flatten(1) for m in mf])     # [4,128,4C+1]
         b0 = torch.stack([m.weight_layer[0].bias for m in mf])
         w2 = torch.stack([m.weight_layer[2].weight.flatten(1) for m in mf])     # [4,4,128]
         b2 = torch.stack([m.weight_layer[2].bias for m in mf])
-        region = ops.rfm_region(y, prm, w0, b0, w2, b2)
-        r = _run_seq(self.region_fusion.fusion_layer, region)
-        s = _run_seq(self.short_cut, y)
+        nd = y.shape[0]
+        fl = self.region_fusion.fusion_layer
+        r = fl[0].run(ops.rfm_region(y, prm[:nd], w0, b0, w2, b2))
+        if enc is not None:
+            # the class-weighted mix of a single-modality pass reads C channels instead of 4C; its [4B,...,4C] region tensor
+            # goes through the same 1x1x1 conv (weights shared with the dense passes) and only then joins the batch
+            r = torch.cat((r, fl[0].run(ops.rfm_region_single(enc, prm[nd:].contiguous(), w0, b0, w2, b2))), 0)
+        r = _run_seq(list(fl)[1:], r)
+        s = _run_stack_seq(self.short_cut, y, enc)
         return torch.cat((r, s), -1)
 
 
@@ -207,8 +232,8 @@ class prm_generator_pk(nn.Module):
         self.prm_layer = nn.Sequential(general_conv3d(in_channel if laststage else in_channel * 2, 16, k_size=1, padding=0),
                                        nn.Conv3d(16, num_cls, kernel_size=1, padding=0, stride=1, bias=True))
 
-    def run(self, y, upper=None):
-        e = _run_seq(self.embedding_layer, y)
+    def run(self, y, upper=None, enc=None):
+        e = _run_stack_seq(self.embedding_layer, y, enc)
         h = self.prm_layer[0].run(e) if upper is None else self.prm_layer[0].run(upper, e)   # cat((x1, emb))
         return _plain_conv1(self.prm_layer[1], h)
 
@@ -232,24 +257,27 @@ class Decoder_fuse(_DecoderConvs):
     def _probs(logits):
         return torch.softmax(logits.float(), -1).detach()
 
-    def run(self, y1, y2, y3, y4):
-        """y_l [N,D_l,H_l,W_l,4*C_l] masked encoder features.  Returns logits, (prm1..4), (de1..4), all cl."""
-        prm4 = self.prm_generator4.run(y4)
-        de4 = self.RFM4.run(y4, self._probs(prm4))
+    def run(self, y1, y2, y3, y4, enc=None):
+        """y_l [Nd,D_l,H_l,W_l,4*C_l] masked encoder features of the dense passes; enc = the four levels of the modality-major
+        encoder output [4B,...,C_l] when four single-modality passes follow the dense ones in the batch (PASSION training:
+        Nd = B, N = 5B).  Returns logits, (prm1..4), (de1..4) of all N passes, all cl."""
+        e1, e2, e3, e4 = enc if enc is not None else (None,) * 4
+        prm4 = self.prm_generator4.run(y4, None, e4)
+        de4 = self.RFM4.run(y4, self._probs(prm4), e4)
         de4 = self.d3_c1.run(ops.upsample(de4))
 
-        prm3 = self.prm_generator3.run(y3, de4)
-        de3 = self.RFM3.run(y3, self._probs(prm3))
+        prm3 = self.prm_generator3.run(y3, de4, e3)
+        de3 = self.RFM3.run(y3, self._probs(prm3), e3)
         de3 = self.d3_out.run(self.d3_c2.run(de3, de4))
         de3 = self.d2_c1.run(ops.upsample(de3))
 
-        prm2 = self.prm_generator2.run(y2, de3)
-        de2 = self.RFM2.run(y2, self._probs(prm2))
+        prm2 = self.prm_generator2.run(y2, de3, e2)
+        de2 = self.RFM2.run(y2, self._probs(prm2), e2)
         de2 = self.d2_out.run(self.d2_c2.run(de2, de3))
         de2 = self.d1_c1.run(ops.upsample(de2))
 
-        prm1 = self.prm_generator1.run(y1, de2)
-        de1 = self.RFM1.run(y1, self._probs(prm1))
+        prm1 = self.prm_generator1.run(y1, de2, e1)
+        de1 = self.RFM1.run(y1, self._probs(prm1), e1)
         de1 = self.d1_out.run(self.d1_c2.run(de1, de2))
 
         logits = _plain_conv1(self.seg_layer, de1)
@@ -353,8 +381,14 @@ class Model(nn.Module):
             with torch.cuda.stream(side):
                 sep_logits = self.decoder_sep.run(*enc)
                 sep_logits.record_stream(main)
-        ys = self._masked(enc, ms)
-        logits, prms, des = self.decoder_fuse.run(*ys)
+        if train_passion and SPARSE_SINGLES:
+            # passes 1..4 see ONE modality each (ms[1+m] = e_m * mask): they read the encoder output itself (already masked in
+            # idt mode, unmasked in pdt mode — exactly what ms[1:] selects); only the full-mask pass needs a 4-modality stack
+            ys = self._masked(enc, ms[:1])
+            logits, prms, des = self.decoder_fuse.run(*ys, enc=enc)
+        else:
+            ys = self._masked(enc, ms)
+            logits, prms, des = self.decoder_fuse.run(*ys)
         D, H, W = logits.shape[1:4]
         fuse_logits = logits.view(P, B, D, H, W, -1)
         fuse_prob = ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)                  # [B,C,D,H,W]

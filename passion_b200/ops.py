@@ -420,11 +420,13 @@ class _WeightCache:
             for d, e in zip(self.descs, ents):
                 ws, bs = e["ws"](), e["bs"]()
                 wk, wt, img, imgT, bias = e["outs"]
-                d.groups, d.cin, d.cout, d.ksize = len(ws), e["cin"], e["cout"], e["ksize"]
+                S = e["slices"]
+                G = S if S else len(ws)
+                d.groups, d.cin, d.cout, d.ksize = G, e["cin"], e["cout"], e["ksize"]
                 d.wk, d.wt, d.img, d.imgT, d.bias = (t.data_ptr() if t is not None else None for t in (wk, wt, img, imgT, bias))
-                d.nt, d.ntT = e["nt"], e["ntT"]
-                for g, w in enumerate(ws):
-                    d.w[g] = w.data_ptr()
+                d.nt, d.ntT, d.w_cin_stride = e["nt"], e["ntT"], S * e["cin"]
+                for g in range(G):
+                    d.w[g] = ws[0].data_ptr() + 4 * g * e["cin"] * e["ksize"] ** 3 if S else ws[g].data_ptr()
                     d.b[g] = bs[g].data_ptr() if bias is not None else None
             need = int(lib.pb_weight_batch_table_bytes(self.n))
             if self.table is None or self.table.numel() < need:
@@ -446,14 +448,15 @@ def _wcache_for(device):
     return c
 
 
-def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt=0, ntT=0, want_bias=False):
+def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt=0, ntT=0, want_bias=False, slices=0):
     """Parameter-layout weights of G groups -> the layouts asked for.  Served from the step's batched refresh when the layer
-    is registered and fresh, else one pb_weight_prep launch (which also registers the layer)."""
+    is registered and fresh, else one pb_weight_prep launch (which also registers the layer).
+    slices = S > 0: `ws` is ONE parameter [cout, S*cin, k, k, k] and group g reads its cin-slice g."""
     import weakref
-    G = len(ws)
+    G = slices if slices else len(ws)
     dev = ws[0].device
     cache = _wcache_for(dev) if BATCH_WEIGHTS else None
-    key = (tuple(id(w) for w in ws), bool(want_wk), bool(want_wt), nt, ntT, bool(want_bias))
+    key = (tuple(id(w) for w in ws), bool(want_wk), bool(want_wt), nt, ntT, bool(want_bias), slices)
     e = cache.lookup(key) if cache is not None else None
     if e:
         return e["outs"]
@@ -470,9 +473,9 @@ def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt
         imgT = torch.empty((G, (cin + ntT - 1) // ntT, 9, max(2, cout // 8), 3 * ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
         bias = torch.empty((G, cout), **f32) if want_bias else None
     desc = _lib.WeightPrepDesc(groups=G, cin=cin, cout=cout, ksize=ksize, wk=_p(wk), wt=_p(wt), img=_p(img), nt=nt,
-                               imgT=_p(imgT), ntT=ntT, bias=_p(bias))
+                               imgT=_p(imgT), ntT=ntT, bias=_p(bias), w_cin_stride=slices * cin)
     for g in range(G):
-        desc.w[g] = ws[g].data_ptr()
+        desc.w[g] = ws[0].data_ptr() + 4 * g * cin * taps if slices else ws[g].data_ptr()
         desc.b[g] = bs[g].data_ptr() if want_bias else None
     _run("weight_prep", f"c{cin}->{cout} k{ksize} g{G}", 0, 0, lambda: lib.pb_weight_prep(ctypes.byref(desc), _stream()))
     if cache is not None and all(isinstance(w, torch.nn.Parameter) for w in ws):
@@ -481,7 +484,7 @@ def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt
             # weak references only: the cache must not keep a dead model's parameters alive
             wrefs, brefs = [weakref.ref(w) for w in ws], [weakref.ref(b) for b in bs] if want_bias else []
             ent = dict(refs=[weakref.ref(p) for p in params], outs=(wk, wt, img, imgT, bias), cin=cin, cout=cout, ksize=ksize,
-                       nt=nt, ntT=ntT, ws=lambda r=wrefs: [x() for x in r], bs=lambda r=brefs: [x() for x in r])
+                       nt=nt, ntT=ntT, slices=slices, ws=lambda r=wrefs: [x() for x in r], bs=lambda r=brefs: [x() for x in r])
             cache.entries[key] = ent
             cache.dirty = True
         ent["versions"] = tuple(p._version for p in params)
@@ -490,13 +493,17 @@ def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt
 
 def _unpack_desc(item, gws, gbs, accumulate, desc=None):
     desc = desc if desc is not None else _lib.WeightUnpackDesc()
-    G = len(item["ws"])
+    S = item.get("slices", 0)
+    G = S if S else len(item["ws"])
     desc.dw, desc.db = item["dw"].data_ptr(), None
     desc.dy_stats = item["st"].data_ptr() if gbs is not None else None
     desc.npg, desc.groups, desc.cin, desc.cout, desc.ksize = item["npg"], G, item["cin"], item["cout"], item["ksize"]
-    desc.accumulate = accumulate
+    desc.accumulate, desc.w_cin_stride = accumulate, S * item["cin"]
     for g in range(4):
-        desc.gw[g] = gws[g].data_ptr() if g < G else None
+        if S:
+            desc.gw[g] = gws[0].data_ptr() + 4 * g * item["cin"] * item["ksize"] ** 3 if g < G else None
+        else:
+            desc.gw[g] = gws[g].data_ptr() if g < G else None
         desc.gb[g] = gbs[g].data_ptr() if (g < G and gbs is not None) else None
     return desc
 
@@ -511,9 +518,8 @@ class _GradSink:
     def __init__(self):
         self.pending = []
         self.bufs = {}               # id(param) -> (weakref, buffer)
-        self.table = None
-        self.sig = None
-        self.descs = None
+        self.launches = []           # per launch ordinal within a flush: dict(sig, table, descs)
+        self.ordinal = 0
 
     def _buffer(self, p):
         import weakref
@@ -538,43 +544,55 @@ class _GradSink:
         if not items:
             return
         lib = _lib.load()
-        rows, seen = [], set()
+        self.ordinal = 0
+        # a parameter used by several conv calls of this backward (the dense and the single-modality passes share weights) is
+        # written by its r-th use in the r-th launch: no two rows of one launch touch the same gradient
+        rounds, uses = [], {}
         for it in items:
             ps = list(it["ws"]) + list(it["bs"])
-            if any(id(p) in seen for p in ps):              # a parameter used by two conv calls: scatter what is queued first
-                self._launch(lib, rows, device)
-                rows, seen = [], set()
-            seen.update(id(p) for p in ps)
-            tg = [self._target(w) for w in it["ws"]]
-            tb = [self._target(b) for b in it["bs"]] if it["bs"] else None
-            acc = {a for _, a in tg} | ({a for _, a in tb} if tb else set())
-            if len(acc) != 1:
-                raise RuntimeError("passion_b200: weight and bias .grad of one conv layer must both exist or both be None")
-            rows.append((it, [t for t, _ in tg], [t for t, _ in tb] if tb else None, acc.pop()))
-        self._launch(lib, rows, device)
+            r = max(uses.get(id(p), 0) for p in ps)
+            for p in ps:
+                uses[id(p)] = r + 1
+            while len(rounds) <= r:
+                rounds.append([])
+            rounds[r].append(it)
+        for its in rounds:
+            rows = []
+            for it in its:
+                tg = [self._target(w) for w in it["ws"]]
+                tb = [self._target(b) for b in it["bs"]] if it["bs"] else None
+                acc = {a for _, a in tg} | ({a for _, a in tb} if tb else set())
+                if len(acc) != 1:
+                    raise RuntimeError("passion_b200: weight and bias .grad of one conv layer must both exist or both be None")
+                rows.append((it, [t for t, _ in tg], [t for t, _ in tb] if tb else None, acc.pop()))
+            self._launch(lib, rows, device)
 
     def _launch(self, lib, rows, device):
         if not rows:
             return
         n = len(rows)
+        if self.ordinal >= len(self.launches):
+            self.launches.append(dict(sig=None, table=None, descs=None))
+        slot = self.launches[self.ordinal]
+        self.ordinal += 1
         sig = tuple((it["dw"].data_ptr(), it["st"].data_ptr() if gbs is not None else 0, acc, tuple(t.data_ptr() for t in gws),
-                     tuple(t.data_ptr() for t in gbs) if gbs is not None else ()) for it, gws, gbs, acc in rows)
-        changed = sig != self.sig
+                     tuple(t.data_ptr() for t in gbs) if gbs is not None else (), it.get("slices", 0)) for it, gws, gbs, acc in rows)
+        changed = sig != slot["sig"]
         if changed and torch.cuda.is_current_stream_capturing():
             for it, gws, gbs, acc in rows:                  # a new table cannot be uploaded inside a capture
                 desc = _unpack_desc(it, gws, gbs, acc)
                 _run("weight_grad_unpack", "layer", 0, 0, lambda: lib.pb_weight_grad_unpack(ctypes.byref(desc), _stream()))
             return
         if changed:
-            self.descs = (_lib.WeightUnpackDesc * n)()
-            for d, (it, gws, gbs, acc) in zip(self.descs, rows):
+            slot["descs"] = (_lib.WeightUnpackDesc * n)()
+            for d, (it, gws, gbs, acc) in zip(slot["descs"], rows):
                 _unpack_desc(it, gws, gbs, acc, d)
             need = int(lib.pb_weight_batch_table_bytes(n))
-            if self.table is None or self.table.numel() < need:
-                self.table = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
-            self.sig = sig
+            if slot["table"] is None or slot["table"].numel() < need:
+                slot["table"] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+            slot["sig"] = sig
         _run("weight_grad_unpack", "batch", 0, 0,
-             lambda: lib.pb_weight_grad_unpack_batch(self.descs, n, _p(self.table), 1 if changed else 0, _stream()))
+             lambda: lib.pb_weight_grad_unpack_batch(slot["descs"], n, _p(slot["table"]), 1 if changed else 0, _stream()))
 
 
 _sinks = {}
@@ -619,21 +637,24 @@ class _Conv3dRef(torch.autograd.Function):
     and one scatter launch in backward (pb_weight_grad_unpack) instead of ~10 tensor-op launches per layer."""
 
     @staticmethod
-    def forward(ctx, x0, x1, ksize, stride, pad_mode, want_stats, has_bias, *params):
+    def forward(ctx, x0, x1, ksize, stride, pad_mode, want_stats, bias_slices, *params):
         lib = _lib.load()
-        G = len(params) // 2 if has_bias else len(params)
-        ws, bs = params[:G], params[G:]
+        has_bias, slices = bias_slices
+        nw = len(params) // 2 if has_bias else len(params)               # weight PARAMETERS
+        ws, bs = params[:nw], params[nw:]
+        G = slices if slices else nw                                     # weight GROUPS over the modality-major batch
         _chk(x0, x1, *params)
-        cout, cin = ws[0].shape[0], ws[0].shape[1]
+        cout, cin = ws[0].shape[0], ws[0].shape[1] // (slices or 1)
         d = _conv_desc(x0, x1, cout, ksize, stride, pad_mode, G)
-        assert cin == d.c0 + d.c1 and all(w.dtype == torch.float32 and tuple(w.shape) == (cout, cin, ksize, ksize, ksize) for w in ws)
+        assert cin == d.c0 + d.c1 and all(w.dtype == torch.float32 and tuple(w.shape) == (cout, cin * (slices or 1), ksize, ksize, ksize) for w in ws)
+        assert not slices or (nw == 1 and not has_bias), "sliced weights: one parameter, no bias"
         need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
         fwd_tc = _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout)
         dgrad_tc = need_dx and _dgrad_tc_ok(d, x0.dtype, ksize, stride, pad_mode)
         want_wt = need_dx and (not dgrad_tc or (pad_mode == "reflect" and not DGRAD_FOLD))
         wk, wt, img, imgT, bias = _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=not fwd_tc, want_wt=want_wt,
                                                nt=_tc_ntile(cin, cout) if fwd_tc else 0,
-                                               ntT=_tc_ntile(cout, cin) if dgrad_tc else 0, want_bias=has_bias)
+                                               ntT=_tc_ntile(cout, cin) if dgrad_tc else 0, want_bias=has_bias, slices=slices)
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
         stats = _scratch.zeros((d.n, cout, 2), torch.float64, x0.device) if want_stats else None
         tc_call = None
@@ -641,11 +662,11 @@ class _Conv3dRef(torch.autograd.Function):
             err = _tc_err_flag(x0.device)
             tc_call = lambda: lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y), None, cout, 0,
                                                _p(stats), _p(err), _stream())
-        _conv_fwd_launch(lib, d, x0, x1, lambda: wk if wk is not None else _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=True)[0],
+        _conv_fwd_launch(lib, d, x0, x1, lambda: wk if wk is not None else _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=True, slices=slices)[0],
                          tc_call, bias, y, stats)
         ctx.save_for_backward(x0, x1, *ws, *bs)
         ctx.bwd_w = (wt, imgT)
-        ctx.cfg = (ksize, stride, pad_mode, G, has_bias)
+        ctx.cfg = (ksize, stride, pad_mode, G, has_bias, nw, slices)
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -654,24 +675,24 @@ class _Conv3dRef(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dstats):
         lib = _lib.load()
-        ksize, stride, pad_mode, G, has_bias = ctx.cfg
+        ksize, stride, pad_mode, G, has_bias, nw, slices = ctx.cfg
         x0, x1 = ctx.saved_tensors[:2]
-        ws = ctx.saved_tensors[2:2 + G]
+        ws = ctx.saved_tensors[2:2 + nw]
         wt, imgT = ctx.bwd_w
-        cout, cin = ws[0].shape[0], ws[0].shape[1]
+        cout, cin = ws[0].shape[0], ws[0].shape[1] // (slices or 1)
         dy = dy.contiguous()
         d = _conv_desc(x0, x1, cout, ksize, stride, pad_mode, G)
         need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
-        need_dw = any(ctx.needs_input_grad[7:7 + G])
-        need_db = has_bias and any(ctx.needs_input_grad[7 + G:])
-        get_wt = lambda: wt if wt is not None else _weight_prep(lib, ws, (), cin, cout, ksize, want_wt=True)[1]
+        need_dw = any(ctx.needs_input_grad[7:7 + nw])
+        need_db = has_bias and any(ctx.needs_input_grad[7 + nw:])
+        get_wt = lambda: wt if wt is not None else _weight_prep(lib, ws, (), cin, cout, ksize, want_wt=True, slices=slices)[1]
         dx0, dx1, dw = _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, lambda: imgT, pad_mode, need_dx, need_dw or need_db)
-        gws = [None] * G
-        gbs = [None] * G if has_bias else []
+        gws = [None] * nw
+        gbs = [None] * nw if has_bias else []
         if need_dw or need_db:
-            bs = ctx.saved_tensors[2 + G:] if has_bias else ()
+            bs = ctx.saved_tensors[2 + nw:] if has_bias else ()
             st = channel_stats(dy) if need_db else None
-            item = dict(ws=ws, bs=bs if need_db else (), dw=dw, st=st, npg=d.n // G, cin=cin, cout=cout, ksize=ksize)
+            item = dict(ws=ws, bs=bs if need_db else (), dw=dw, st=st, npg=d.n // G, cin=cin, cout=cout, ksize=ksize, slices=slices)
             if (BATCH_WEIGHTS and need_dw and all(w.is_leaf and w.requires_grad for w in ws)
                     and (not has_bias or (need_db and all(b.is_leaf and b.requires_grad for b in bs)))):
                 # leaf parameters: their .grad is written by ONE batched scatter launch when this backward pass ends
@@ -679,18 +700,20 @@ class _Conv3dRef(torch.autograd.Function):
             else:
                 gws = [torch.empty_like(w) for w in ws]
                 if need_db:
-                    gbs = [torch.empty((cout,), dtype=torch.float32, device=dy.device) for _ in range(G)]
+                    gbs = [torch.empty((cout,), dtype=torch.float32, device=dy.device) for _ in range(nw)]
                 desc = _unpack_desc(item, gws, gbs if need_db else None, 0)
                 _run("weight_grad_unpack", f"c{cin}->{cout} k{ksize} g{G}", 0, 0,
                      lambda: lib.pb_weight_grad_unpack(ctypes.byref(desc), _stream()))
         return (dx0, dx1, None, None, None, None, None, *gws, *gbs)
 
 
-def conv3d_ref(x0, weights, biases=None, x1=None, ksize=3, stride=1, pad_mode="reflect", want_stats=False):
+def conv3d_ref(x0, weights, biases=None, x1=None, ksize=3, stride=1, pad_mode="reflect", want_stats=False, slices=0):
     """Conv on the parameters in nn.Conv3d layout: `weights` = list of G tensors [cout, cin, k, k, k] (G weight groups
-    over a modality-major batch), `biases` = list of G tensors [cout] or None.  Returns (y, stats or None)."""
+    over a modality-major batch), `biases` = list of G tensors [cout] or None.  Returns (y, stats or None).
+    slices = S: `weights` is ONE tensor [cout, S*cin, k, k, k]; group g of the batch is convolved with its cin-slice g (the
+    single-modality decoder passes of a conv over the 4-modality stack: only modality g's quarter of the weight matters)."""
     params = list(weights) + (list(biases) if biases is not None else [])
-    return _Conv3dRef.apply(x0, x1, ksize, stride, pad_mode, want_stats, biases is not None, *params)
+    return _Conv3dRef.apply(x0, x1, ksize, stride, pad_mode, want_stats, (biases is not None, int(slices)), *params)
 
 
 def conv3d(x0, w, bias=None, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=1, want_stats=False):
@@ -754,9 +777,9 @@ def conv_in_lrelu(x0, w, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=
     return _InormLrelu.apply(y, mr, res)
 
 
-def conv_in_lrelu_ref(x0, weights, x1=None, ksize=3, stride=1, pad_mode="reflect", res=None):
+def conv_in_lrelu_ref(x0, weights, x1=None, ksize=3, stride=1, pad_mode="reflect", res=None, slices=0):
     """conv_in_lrelu on parameter-layout weights (list of G tensors, see conv3d_ref)."""
-    y, stats = conv3d_ref(x0, weights, None, x1, ksize, stride, pad_mode, True)
+    y, stats = conv3d_ref(x0, weights, None, x1, ksize, stride, pad_mode, True, slices)
     voxels = y.shape[1] * y.shape[2] * y.shape[3]
     return _InormLrelu.apply(y, inorm_finalize(stats, voxels), res)
 
@@ -888,53 +911,74 @@ def masked_stack(enc, ms):
     return _MaskedStack.apply(enc, ms)
 
 
+def _gate_single(S1, Psum, voxels, w0, b0, w2, b2):
+    """Gate of a SINGLE-modality pass: sample n = m*B + b only has modality m, so its pooled vector is S1 [4B,4,C] in slot
+    m of the [4B,4,4C] MLP input (zeros elsewhere, exactly what pooling the masked 4-slot stack gives) and only column m of
+    the [4B,4(class),4(modality)] gate is ever used.  Returns gate1 [4B,4]."""
+    n, _, c = S1.shape
+    B = n // 4
+    eye = torch.eye(4, dtype=S1.dtype, device=S1.device)
+    S_full = torch.einsum("mbic,mk->mbikc", S1.view(4, B, 4, c), eye).reshape(n, 4, 4 * c)
+    gate = _gate_mlp(S_full, Psum, voxels, w0, b0, w2, b2)                       # [4B,4,4]
+    return torch.einsum("mbik,mk->mbi", gate.view(4, B, 4, 4), eye).reshape(n, 4)
+
+
 class _RfmRegion(torch.autograd.Function):
-    """Region-aware modality mixing: y [N,D,H,W,4C] (masked features, channel = k*C+c), p [N,D,H,W,4] fp32
+    """Region-aware modality mixing: y [N,D,H,W,K*C] (masked features, channel = k*C+c), p [N,D,H,W,4] fp32
     (detached class probabilities) -> R [N,D,H,W,4C] (channel = class*C + c).
-    w0 [4,128,4C+1], b0 [4,128], w2 [4,4,128], b2 [4,4] are the four modal_fusion gate MLPs."""
+    w0 [4,128,4C+1], b0 [4,128], w2 [4,4,128], b2 [4,4] are the four modal_fusion gate MLPs.
+    K = 4: the 4-modality stack.  K = 1: y is the modality-major encoder output [4B,...,C] itself — four single-modality
+    passes (pass m sees modality m only) without ever building their 3/4-zero stacks."""
 
     @staticmethod
-    def forward(ctx, y, p, w0, b0, w2, b2):
+    def forward(ctx, y, p, w0, b0, w2, b2, K):
         lib = _lib.load()
         _chk(y, p)
-        assert p.dtype == torch.float32 and p.shape[-1] == 4
+        assert p.dtype == torch.float32 and p.shape[-1] == 4 and K in (1, 4)
         n, kc = y.shape[0], y.shape[-1]
-        c = kc // 4
+        c = kc // K
         voxels = y.numel() // (n * kc)
         S = torch.zeros((n, 4, kc), dtype=torch.float64, device=y.device)
         Ps = torch.zeros((n, 4), dtype=torch.float64, device=y.device)
         _lib.check(lib.pb_rfm_pool(_dt(y), _p(y), _p(p), _p(S), _p(Ps), n, voxels, kc, _stream()), "rfm_pool")
         S, Ps = S.float(), Ps.float()
-        gate = _gate_mlp(S, Ps, voxels, w0, b0, w2, b2).contiguous()
-        r = torch.empty_like(y)
-        _lib.check(lib.pb_rfm_mix(_dt(y), _p(y), _p(p), _p(gate), _p(r), n, voxels, 4, c, _stream()), "rfm_mix")
+        gate = (_gate_mlp if K == 4 else _gate_single)(S, Ps, voxels, w0, b0, w2, b2).contiguous()
+        r = torch.empty(y.shape[:-1] + (4 * c,), dtype=y.dtype, device=y.device)
+        _lib.check(lib.pb_rfm_mix(_dt(y), _p(y), _p(p), _p(gate), _p(r), n, voxels, K, c, _stream()), "rfm_mix")
         ctx.save_for_backward(y, p, S, Ps, gate, w0, b0, w2, b2)
+        ctx.K = K
         return r
 
     @staticmethod
     def backward(ctx, dr):
         lib = _lib.load()
         y, p, S, Ps, gate, w0, b0, w2, b2 = ctx.saved_tensors
+        K = ctx.K
         dr = dr.contiguous()
         n, kc = y.shape[0], y.shape[-1]
-        c = kc // 4
+        c = kc // K
         voxels = y.numel() // (n * kc)
-        dgate = torch.zeros((n, 4, 4), dtype=torch.float64, device=y.device)
-        _lib.check(lib.pb_rfm_mix_bwd_gate(_dt(y), _p(y), _p(p), _p(dr), _p(dgate), n, voxels, 4, c, _stream()),
+        dgate = torch.zeros((n, 4, K) if K == 4 else (n, 4), dtype=torch.float64, device=y.device)
+        _lib.check(lib.pb_rfm_mix_bwd_gate(_dt(y), _p(y), _p(p), _p(dr), _p(dgate), n, voxels, K, c, _stream()),
                    "rfm_mix_bwd_gate")
         with torch.enable_grad():                       # tiny [N, 4C+1] MLP: recompute and let autograd transpose it
             S_ = S.detach().requires_grad_(True)
             params = [t.detach().requires_grad_(True) for t in (w0, b0, w2, b2)]
-            g = _gate_mlp(S_, Ps, voxels, *params)
+            g = (_gate_mlp if K == 4 else _gate_single)(S_, Ps, voxels, *params)
             dS, dw0, db0, dw2, db2 = torch.autograd.grad(g, [S_, *params], dgate.float())
         dy = torch.empty_like(y)
-        _lib.check(lib.pb_rfm_bwd_y(_dt(y), _p(p), _p(gate), _p(dr), _p(dS.contiguous()), _p(dy), n, voxels, 4, c, _stream()),
+        _lib.check(lib.pb_rfm_bwd_y(_dt(y), _p(p), _p(gate), _p(dr), _p(dS.contiguous()), _p(dy), n, voxels, K, c, _stream()),
                    "rfm_bwd_y")
-        return dy, None, dw0, db0, dw2, db2
+        return dy, None, dw0, db0, dw2, db2, None
 
 
 def rfm_region(y, p, w0, b0, w2, b2):
-    return _RfmRegion.apply(y, p, w0, b0, w2, b2)
+    return _RfmRegion.apply(y, p, w0, b0, w2, b2, 4)
+
+
+def rfm_region_single(enc, p, w0, b0, w2, b2):
+    """Four single-modality passes on the modality-major encoder output enc [4B,D,H,W,C]; p [4B,D,H,W,4]."""
+    return _RfmRegion.apply(enc, p, w0, b0, w2, b2, 1)
 
 
 # ---- PASSION objective kernels (csrc/loss.cu) ----------------------------------------------------------------

@@ -284,6 +284,50 @@ def test_rfm_region(lib_built, c, shape, dtype):
         assert rel(a.grad, b.grad) < (2e-4 if dtype == torch.float32 else 2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,shape", [(8, (6, 7, 8)), (16, (4, 5, 6)), (64, (2, 2, 2))])
+def test_single_modality_passes_equal_their_stacks(lib_built, c, shape, dtype):
+    """The four single-modality decoder passes computed on the modality-major encoder output itself (ops.rfm_region_single and
+    the cin-sliced grouped 1x1x1 conv, conv3d_ref(..., slices=4)) must equal the same ops on their explicitly built
+    [4B,...,4C] stacks (modality m in slot m, zeros elsewhere): values, input gradients and parameter gradients."""
+    from passion_b200 import ops
+    g = torch.Generator().manual_seed(100 + c)
+    B, kc = 2, 4 * c
+    enc = torch.randn(4 * B, *shape, c, generator=g).cuda().to(dtype)
+    enc[1 * B + 0] = 0                                                # a missing modality of sample 0
+    p = torch.softmax(torch.randn(4 * B, *shape, 4, generator=g), -1).cuda()
+    w0 = (torch.randn(4, 128, kc + 1, generator=g) / kc ** 0.5).cuda()
+    b0 = (torch.randn(4, 128, generator=g) * 0.1).cuda()
+    w2 = (torch.randn(4, 4, 128, generator=g) / 128 ** 0.5).cuda()
+    b2 = (torch.randn(4, 4, generator=g) * 0.1).cuda()
+    wc = (torch.randn(c, kc, 1, 1, 1, generator=g) / kc ** 0.5).cuda()
+    gr = torch.randn(4 * B, *shape, kc, generator=g).cuda().to(dtype)
+    gc = torch.randn(4 * B, *shape, c, generator=g).cuda().to(dtype)
+    ms = torch.eye(4)[:, None, :].expand(4, B, 4).contiguous().cuda()          # pass m: modality m only
+
+    def run(single):
+        e = enc.clone().requires_grad_(True)
+        ps = [t.clone().requires_grad_(True) for t in (w0, b0, w2, b2, wc)]
+        if single:
+            r = ops.rfm_region_single(e, p, *ps[:4])
+            y, st = ops.conv3d_ref(e, [ps[4]], ksize=1, pad_mode="zeros", want_stats=True, slices=4)
+        else:
+            stack = ops.masked_stack(e, ms)
+            r = ops.rfm_region(stack, p, *ps[:4])
+            y, st = ops.conv3d_ref(stack, [ps[4]], ksize=1, pad_mode="zeros", want_stats=True)
+        (r.float() * gr.float()).sum().backward(retain_graph=True)
+        (y.float() * gc.float()).sum().backward()
+        return r.detach(), y.detach(), st.clone(), e.grad, [t.grad.clone() for t in ps]
+
+    a, b = run(True), run(False)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel(a[0], b[0]) < tol and rel(a[1], b[1]) < tol
+    assert rel(a[2], b[2]) < 1e-4 if dtype == torch.float32 else rel(a[2], b[2]) < 1e-2
+    assert rel(a[3], b[3]) < (1e-5 if dtype == torch.float32 else 2e-2)
+    for ga, gb in zip(a[4], b[4]):
+        assert rel(ga, gb) < (2e-4 if dtype == torch.float32 else 2e-2)
+
+
 # ------------------------------------------------------------------------------------------------ loss kernels
 def _onehot_target(labels, num_cls=4):
     return F.one_hot(labels.long(), num_cls).permute(0, 4, 1, 2, 3).double()
