@@ -44,10 +44,25 @@ def up_probs(p, scale):
 
 
 # ------------------------------------------------------------------ channels-last helpers used by the model
+_label_memo = {}
+
+
 def label_stats(target, num_cls=4):
     """target -> (labels uint8 [B,D,H,W], class voxel counts [B,C] fp32, CE class weights 1 - count/total [B,C]
     (criterions.py:67)).  `target` is the reference's one-hot [B,C,D,H,W] (float64, datasets_nii.py:150-153) or — the
-    compact form passion_b200.data.DeviceAugment produces — the uint8 label map [B,D,H,W] itself (33x fewer bytes)."""
+    compact form passion_b200.data.DeviceAugment produces — the uint8 label map [B,D,H,W] itself (33x fewer bytes).
+    The result for the most recent target OBJECT is kept (identity + version counter): Model.forward and the
+    step's fused-prediction CE / Dice (train.py:228-229) derive it from the same tensor three times per step."""
+    import weakref
+    ref = _label_memo.get("ref")
+    if ref is not None and ref() is target and _label_memo["k"] == (target._version, num_cls):
+        return _label_memo["v"]
+    out = _label_stats(target, num_cls)
+    _label_memo["ref"], _label_memo["k"], _label_memo["v"] = weakref.ref(target), (target._version, num_cls), out
+    return out
+
+
+def _label_stats(target, num_cls=4):
     if target.dtype == torch.uint8 and target.dim() == 4:
         labels = target.contiguous()
         cls = torch.arange(num_cls, device=target.device, dtype=torch.uint8).view(1, num_cls, 1)
@@ -85,6 +100,15 @@ def proto(fs, ft, labels, cnt, eps=1e-5):
 
 
 # ------------------------------------------------------------------ reference-signature wrappers
+def ce_dice_bs(output, target, num_cls=5, eps=1e-7, up_op=None):
+    """softmax_weighted_loss_bs + dice_loss_bs of the same prediction from ONE pass over it (the step's fused-prediction
+    term, train.py:228-229).  Returns ([B,1] CE, [B,1] Dice)."""
+    p = up_probs(_to_cl(output.float()), _scale_of(up_op))
+    labels, cnt, wgt = label_stats(target)
+    ce, dice = cedice(p, labels, cnt, wgt, eps)
+    return ce.unsqueeze(1), dice.unsqueeze(1)
+
+
 def dice_loss_bs(output, target, num_cls=5, eps=1e-7, up_op=None):
     p = up_probs(_to_cl(output.float()), _scale_of(up_op))
     labels, cnt, wgt = label_stats(target)

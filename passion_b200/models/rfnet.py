@@ -32,7 +32,9 @@ basic_dims = 8
 num_modals = 4
 SEP_STREAM = os.environ.get("PB_SEP_STREAM", "1") != "0"     # run decoder_sep concurrently with decoder_fuse (measured: -0.9 ms/step)
 SIDE_RECORD = os.environ.get("PB_SIDE_RECORD", "1") != "0"   # debugging switch for _lend_to_stream (keep on)
-SPARSE_SINGLES = os.environ.get("PB_SPARSE_SINGLES", "1") != "0"   # single-modality passes without their 3/4-zero stacks
+# single-modality passes without their 3/4-zero stacks, at the N finest levels (the coarse levels are launch-bound: splitting
+# their batch into dense + single parts costs more launches than the bytes it saves)
+SPARSE_SINGLES = int(os.environ.get("PB_SPARSE_SINGLES", "2"))
 _side = {}
 
 
@@ -381,11 +383,12 @@ class Model(nn.Module):
             with torch.cuda.stream(side):
                 sep_logits = self.decoder_sep.run(*enc)
                 sep_logits.record_stream(main)
-        if train_passion and SPARSE_SINGLES:
+        if train_passion and SPARSE_SINGLES > 0:
             # passes 1..4 see ONE modality each (ms[1+m] = e_m * mask): they read the encoder output itself (already masked in
             # idt mode, unmasked in pdt mode — exactly what ms[1:] selects); only the full-mask pass needs a 4-modality stack
-            ys = self._masked(enc, ms[:1])
-            logits, prms, des = self.decoder_fuse.run(*ys, enc=enc)
+            sparse = [lvl < SPARSE_SINGLES for lvl in range(4)]
+            ys = [ops.masked_stack(f, ms[:1] if sp else ms) for f, sp in zip(enc, sparse)]
+            logits, prms, des = self.decoder_fuse.run(*ys, enc=[f if sp else None for f, sp in zip(enc, sparse)])
         else:
             ys = self._masked(enc, ms)
             logits, prms, des = self.decoder_fuse.run(*ys)

@@ -13,8 +13,8 @@ def loss_mix(outputs, target, mask, imb_beta, modal_weight, *, mask_type="idt", 
     """outputs = Model.forward tuple.  Returns (loss, parts).  `rp_allreduce`, if given, is applied to the
     4-float rp_iter before thresholding (rp_mask is a GLOBAL-batch statistic, train.py:265-268)."""
     fuse_pred, prm_bs, sep_bs, kl_bs, proto_bs, dist_bs = outputs
-    fuse_loss = (criterions.softmax_weighted_loss_bs(fuse_pred, target, num_cls=num_cls)
-                 + criterions.dice_loss_bs(fuse_pred, target, num_cls=num_cls)).sum()          # :228-229
+    ce_bs, dice_bs = criterions.ce_dice_bs(fuse_pred, target, num_cls=num_cls)                 # one pass for both terms
+    fuse_loss = (ce_bs + dice_bs).sum()          # :228-229
     prm_loss = prm_bs.sum()
     if mask_type == "pdt":
         sep_m, kl_m, proto_m, dist_m = sep_bs.sum(0), kl_bs.sum(0), proto_bs.sum(0), dist_bs.sum(0)
@@ -48,8 +48,8 @@ def loss_mix(outputs, target, mask, imb_beta, modal_weight, *, mask_type="idt", 
 def loss_mix_baseline(outputs, target, mask, *, mask_type="idt", warmup=False, num_cls=4):
     """The non-PASSION loop's loss (train.py:410-437): fuse + sum_m sep_m + prm, no preference gating."""
     fuse_pred, prm_bs, sep_bs = outputs
-    fuse_loss = (criterions.softmax_weighted_loss_bs(fuse_pred, target, num_cls=num_cls)
-                 + criterions.dice_loss_bs(fuse_pred, target, num_cls=num_cls)).sum()
+    ce_bs, dice_bs = criterions.ce_dice_bs(fuse_pred, target, num_cls=num_cls)                 # one pass for both terms
+    fuse_loss = (ce_bs + dice_bs).sum()
     prm_loss = prm_bs.sum()
     sep_m = sep_bs.sum(0) if mask_type == "pdt" else (sep_bs * mask.to(torch.float32)).sum(0)
     sep_loss = sep_m.sum()
