@@ -18,6 +18,8 @@
 //     warp 4 single-thread tcgen05.mma issue + TMEM allocation, warps 5-7 producers.  Two TMEM accumulator stages
 //     overlap the epilogue of plane d with the MMAs of plane d+1.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include "common.cuh"
 
 namespace {
@@ -32,6 +34,8 @@ __host__ __device__ constexpr int max_copies(int nchr) { return nchr >= 8 ? kMax
 constexpr int kWgCopies = 5;            // weight-gradient kernels: slab rows per producer thread (planes up to W = 174)
 constexpr int kTileM = 128;
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p);
+
 struct TcP {
     int N, D, H, W, C0, C1, CO0, CO1;   // inputs x0|x1 (concat), outputs y0|y1 (split)
     int reflect;
@@ -41,7 +45,17 @@ struct TcP {
     int slab_need, slab_e;              // rows needed / padded rows per chunk plane of a slab
     int nt_tiles;
     long long w_tile_bytes;             // bytes of one (group, Cout tile) weight image
+    int tma, tma_rows;                  // 1: the input planes are fetched by TMA (zero padding, one source): per plane and 8-channel
+                                        // chunk one cp.async.bulk.tensor box [tma_rows padded rows][PW][8 ch], out-of-bounds = the zero
+                                        // padding; the slab then starts at padded row r0 = q0 / PW and the tile at offset q0 - r0 * PW
+    int q_stride;                       // positions a tile advances by (128, or 126 for the kw-stacked kernel)
 };
+
+// 5-D tiled tensor map of a dense NDHWC bf16 volume for those boxes: dims (8 ch of a chunk, W, H, chunks, N*D planes)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -95,6 +109,36 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// TMA producer of conv3_tc_kernel / conv3_tc_kws_kernel (one thread): streams the input planes of this CTA's work items into the
+// slot ring.  Zero padding is the tensor map's out-of-bounds fill; a plane outside the volume (padding along d) is fetched with
+// an h coordinate beyond the volume, i.e. as an all-zero box.
+template <int NCHR, int kSlots>
+__device__ __forceinline__ void tma_producer(const TcP& p, const CUtensorMap* map, uint8_t* slab_s, int slot_bytes, uint64_t* full,
+                                             uint64_t* empty, int g, int items, int* err) {
+    const int Di = p.D - 2 * p.inset, Hi = p.H - 2 * p.inset;
+    const uint32_t bytes = (uint32_t)NCHR * 16u * (uint32_t)p.PW * (uint32_t)p.tma_rows;
+    uint32_t k = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int dc = it % p.ND, r1 = it / p.ND;
+        const int qt = r1 % p.QT, n = g * p.npg + r1 / p.QT;
+        const int d0 = dc * p.DCH;
+        const int nout = min(p.DCH, p.D - d0);
+        const int r0 = (qt * p.q_stride) / p.PW;                   // first padded row of the slab
+        for (int pl = 0; pl < nout + 2; ++pl, ++k) {
+            const int slot = k % kSlots;
+            mbar_wait(&empty[slot], ((k / kSlots) & 1) ^ 1, err, 1);
+            const int dp = d0 - 1 + pl - p.inset;
+            const bool plane_ok = dp >= 0 && dp < Di;
+            mbar_expect_tx(&full[slot], bytes);
+            const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
+#pragma unroll
+            for (int ch = 0; ch < NCHR; ++ch)
+                tma_load_5d(sbase + (uint32_t)(ch * p.slab_e) * 16u, map, 0, -1 - p.inset, plane_ok ? r0 - 1 - p.inset : Hi + 8, ch,
+                            plane_ok ? n * Di + dp : 0, &full[slot]);
+        }
+    }
+}
+
 // UMMA shared-memory descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 | [46,48) version
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -143,7 +187,8 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // NCHR = real input chunks of 8 channels (1,2,4,8,16); NT = Cout tile (16 or 32); the 128-channel variant (NCHR = 16) has
 // room for a 2-plane ring only (110 KB of weights + 2 x 40 KB planes, one CTA per SM) — its layers are the small deep ones
 template <int NCHR, int NT>
-__global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+__global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcP p,
+                                                               const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                                const bf16* __restrict__ wimg, const float* __restrict__ bias,
                                                                bf16* __restrict__ y0, bf16* __restrict__ y1, bf16* __restrict__ yext,
                                                                double* __restrict__ stats, int* err) {
@@ -172,7 +217,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kTcProducers); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], p.tma ? 1 : kTcProducers); mbar_init(&empty[i], 1); }
         for (int i = 0; i < R; ++i) { mbar_init(&blk_full[i], 1); mbar_init(&blk_empty[i], 128); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,7 +246,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
     __syncthreads();
     tc_fence_after();
 
-    if (warp >= 5) {
+    if (warp >= 5 && p.tma) {
+        // =============================== producer: one thread, TMA ===============================
+        if (warp == 5 && lane == 0) tma_producer<NCHR, kSlots>(p, &tmap, slab_s, slot_bytes, full, empty, g, items, err);
+    } else if (warp >= 5) {
         // =============================== producers ===============================
         // The (h, w) geometry of a slab row depends only on the q-tile, so each thread resolves its <= kMaxCopies
         // copies (source offset inside a plane, padding, destination) once per work item and then streams planes.
@@ -278,6 +326,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
                 const int nout = min(p.DCH, p.D - dc * p.DCH);
+                // TMA slabs start at a padded-row boundary: the tile begins (q0 mod PW) rows into the slab
+                const uint32_t tile_off = p.tma ? (uint32_t)((((it / p.ND) % p.QT) * p.q_stride) % p.PW) * 16u : 0u;
                 for (int pl = 0; pl < nout + 2; ++pl, ++k) {
                     mbar_wait(&full[k % kSlots], (k / kSlots) & 1, err, 3);
                     if (pl < nout) {                           // output plane pl gets its first contribution: its block must be free
@@ -291,7 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
                     const int row0 = (2 - (pl - od_lo)) * NT;                  // weight rows are ordered kd = 2, 1, 0
                     const int blk0 = (int)((j0 + od_lo) % R);
                     const int n1 = blk0 + nb > R ? R - blk0 : nb;              // blocks before the ring wraps
-                    const uint64_t a0 = umma_desc(slab_addr + (k % kSlots) * slot_bytes, (uint32_t)p.slab_e * 16, 128);
+                    const uint64_t a0 = umma_desc(slab_addr + (k % kSlots) * slot_bytes + tile_off, (uint32_t)p.slab_e * 16, 128);
 #pragma unroll
                     for (int t9 = 0; t9 < 9; ++t9) {
                         const uint64_t a1 = a0 + (uint64_t)toff[t9];           // address field is in 16 B units
@@ -404,8 +454,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(TcP p, const bf
 }
 
 template <int NCHR, int NT>
-int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1, void* yext,
-              double* stats, int* err, cudaStream_t st) {
+int launch_tc(const CUtensorMap& tmap, const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0,
+              void* y1, void* yext, double* stats, int* err, cudaStream_t st) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     constexpr int kSlots = NCHR >= 16 ? 2 : 6;
     const size_t w_bytes = (size_t)27 * NCH * NT * 16;
@@ -419,7 +469,7 @@ int launch_tc(const TcP& p, const void* x0, const void* x1, const void* wimg, co
     if (smem <= 110 * 1024) ctas *= 2;
     if (ctas < 1) ctas = 1;
     if (ctas > items) ctas = items;
-    kern<<<dim3(ctas, p.groups, p.nt_tiles), kTcThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
+    kern<<<dim3(ctas, p.groups, p.nt_tiles), kTcThreads, smem, st>>>(tmap, p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
                                                                     (bf16*)y0, (bf16*)y1, (bf16*)yext, stats, err);
     return 0;
 }
@@ -449,7 +499,8 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int NCHR, int CR>       // CR = real output channels of the tile / 8 (1 or 2)
-__global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+__global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __grid_constant__ CUtensorMap tmap, TcP p,
+                                                                   const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                                    const bf16* __restrict__ wimg, const float* __restrict__ bias,
                                                                    bf16* __restrict__ y0, bf16* __restrict__ y1, bf16* __restrict__ yext,
                                                                    double* __restrict__ stats, int* err) {
@@ -479,7 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], kTcProducers); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], p.tma ? 1 : kTcProducers); mbar_init(&empty[i], 1); }
         for (int i = 0; i < R; ++i) { mbar_init(&blk_full[i], 1); mbar_init(&blk_empty[i], 128); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -500,7 +551,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;          // no zero fill: the first MMA into a block overwrites it (accumulate = 0)
 
-    if (warp >= 5) {
+    if (warp >= 5 && p.tma) {
+        // =============================== producer: one thread, TMA ===============================
+        if (warp == 5 && lane == 0) tma_producer<NCHR, kSlots>(p, &tmap, slab_s, slot_bytes, full, empty, g, items, err);
+    } else if (warp >= 5) {
         // =============================== producers (as conv3_tc_kernel; tiles advance by kKwsStride) ===============================
         const int pt = threadIdx.x - 5 * 32;
         const int c0ch = p.C0 >> 3;
@@ -572,6 +626,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
                 const int nout = min(p.DCH, p.D - dc * p.DCH);
+                // TMA slabs start at a padded-row boundary: the tile begins (q0 mod PW) rows into the slab
+                const uint32_t tile_off = p.tma ? (uint32_t)((((it / p.ND) % p.QT) * p.q_stride) % p.PW) * 16u : 0u;
                 for (int pl = 0; pl < nout + 2; ++pl, ++k) {
                     mbar_wait(&full[k % kSlots], (k / kSlots) & 1, err, 3);
                     if (pl < nout) {
@@ -584,7 +640,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
                     const int nb = od_hi - od_lo + 1;
                     const int row0 = (2 - (pl - od_lo)) * NB;                  // weight rows: kd = 2, 1, 0 blocks of [kw][co]
                     const int blk0 = (int)((j0 + od_lo) % R);
-                    const uint64_t a0 = umma_desc(slab_addr + (k % kSlots) * slot_bytes, (uint32_t)p.slab_e * 16, 128);
+                    const uint64_t a0 = umma_desc(slab_addr + (k % kSlots) * slot_bytes + tile_off, (uint32_t)p.slab_e * 16, 128);
                     // output plane pl (if any) gets its FIRST contribution from this input plane: that block is written with
                     // accumulate = 0 by the first instruction, so the epilogue never has to zero a block (and hands it back as soon
                     // as it has been read); every other (block, instruction) accumulates
@@ -731,8 +787,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(TcP p, cons
 }
 
 template <int NCHR, int CR>
-int launch_tc_kws(const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1, void* yext,
-                  double* stats, int* err, cudaStream_t st) {
+int launch_tc_kws(const CUtensorMap& tmap, const TcP& p, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0,
+                  void* y1, void* yext, double* stats, int* err, cudaStream_t st) {
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     constexpr int kSlots = NCHR >= 16 ? 2 : 6;
     const size_t w_bytes = (size_t)27 * NCH * 16 * 16;
@@ -747,7 +803,7 @@ int launch_tc_kws(const TcP& p, const void* x0, const void* x1, const void* wimg
     if (smem <= 113 * 1024) ctas *= 2;           // two CTAs per SM: 2 x (smem + 1 KB reserved per CTA) <= 228 KB
     if (ctas < 1) ctas = 1;
     if (ctas > items) ctas = items;
-    kern<<<dim3(ctas, p.groups, p.nt_tiles), kTcThreads, smem, st>>>(p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
+    kern<<<dim3(ctas, p.groups, p.nt_tiles), kTcThreads, smem, st>>>(tmap, p, (const bf16*)x0, (const bf16*)x1, (const bf16*)wimg, bias,
                                                                     (bf16*)y0, (bf16*)y1, (bf16*)yext, stats, err);
     return 0;
 }
@@ -1403,6 +1459,44 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
              void* yext, int inset, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
 }
 
+namespace {
+bool tc_tma_enabled() {
+    static const bool on = [] { const char* e = getenv("PB_TC_TMA"); return !(e != nullptr && e[0] == '0'); }();
+    return on;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda: the library must still
+// load on a machine without a driver, where only the symbol check runs)
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return (EncodeTiledFn) nullptr;
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+
+// dense NDHWC bf16 volume [planes][H][W][C] seen as (8 ch of a chunk, W, H, C/8 chunks, planes); box = [rows][PW][8 ch] of one chunk
+int make_plane_map(CUtensorMap* map, const void* base, int C, int W, int H, long long planes, int box_w, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (enc == nullptr) return -1;
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)planes};
+    const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+}  // namespace
+
 extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias,
                             void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
     PB_CHECK_ARG(d && x0 && wimg && y0 && err_flag, "null pointer");
@@ -1522,12 +1616,25 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     p.DCH = (p.D + nd - 1) / nd;
     p.ND = (p.D + p.DCH - 1) / p.DCH;
     p.slab_need = kws ? kTileM + 2 * p.PW : kTileM + 2 * p.PW + 2;
+    p.q_stride = kws ? kKwsStride : kTileM;
     const int nchr = cin / 8, nch = nchr < 2 ? 2 : nchr;
     // pad the plane pitch so that the nch chunk planes start in different shared-memory banks
     const int want = nch >= 8 ? 1 : 8 / nch;
     int se = p.slab_need;
     while (se % 8 != want % 8) ++se;
     p.slab_e = se;
+    // TMA-fed input planes: zero padding (= the tensor map's out-of-bounds fill; reflection cannot be expressed), one source
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    p.tma = 0; p.tma_rows = 0;
+    if (!p.reflect && d->c1 == 0 && tc_tma_enabled()) {
+        const int rows = (p.slab_need + p.PW - 2) / p.PW + 1;               // padded rows a slab of slab_need positions can touch
+        const int se_t = ((rows * p.PW + 7) / 8) * 8;                       // chunk-plane pitch: TMA destinations are 128 B aligned
+        const int Di = p.D - 2 * inset, Hi = p.H - 2 * inset, Wi = p.W - 2 * inset;
+        if (p.PW <= 256 && rows <= 256 && make_plane_map(&tmap, x0, cin, Wi, Hi, (long long)p.N * Di, p.PW, rows) == 0) {
+            p.tma = 1; p.tma_rows = rows; p.slab_e = se_t;
+        }
+    }
     p.w_tile_bytes = (long long)27 * nch * NT * 16;
     if (p.slab_need * nchr > max_copies(nchr) * kTcProducers) {
         pb_set_error("conv3d_tc: plane slab of %d x %d copies exceeds the producer budget", p.slab_need, nchr);
@@ -1535,11 +1642,11 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PB_EUNSUPPORTED;
-#define KWS_CASE(NCHR_, CR_) if (kws && nchr == NCHR_ && cout == 8 * CR_) rc = launch_tc_kws<NCHR_, CR_>(p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
+#define KWS_CASE(NCHR_, CR_) if (kws && nchr == NCHR_ && cout == 8 * CR_) rc = launch_tc_kws<NCHR_, CR_>(tmap, p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
     KWS_CASE(1, 1); KWS_CASE(2, 1); KWS_CASE(4, 1); KWS_CASE(8, 1); KWS_CASE(16, 1);
     KWS_CASE(1, 2); KWS_CASE(2, 2); KWS_CASE(4, 2); KWS_CASE(8, 2); KWS_CASE(16, 2);
 #undef KWS_CASE
-#define TC_CASE(NCHR_, NT_) if (!kws && nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
+#define TC_CASE(NCHR_, NT_) if (!kws && nchr == NCHR_ && NT == NT_) rc = launch_tc<NCHR_, NT_>(tmap, p, x0, x1, wimg, bias, y0, y1, yext, stats, err_flag, st)
     TC_CASE(1, 16); TC_CASE(2, 16); TC_CASE(4, 16); TC_CASE(8, 16); TC_CASE(16, 16);
     TC_CASE(1, 32); TC_CASE(2, 32); TC_CASE(4, 32); TC_CASE(8, 32);
 #undef TC_CASE
