@@ -112,8 +112,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // TMA producer of conv3_tc_kernel / conv3_tc_kws_kernel (one thread): streams the input planes of this CTA's work items into the
 // slot ring, one box [tma_rows padded rows][PW][8 ch] per plane and 8-channel chunk (chunks of the second source of a two-source
 // conv come from its own tensor map).  Zero padding is the tensor map's out-of-bounds fill; a plane outside the volume (zero
-// padding along d) is fetched with an h coordinate beyond the volume, i.e. as an all-zero box.  Reflect padding (p.tma == 2):
-// along d the reflected plane is fetched; the in-plane halo cells arrive as zeros and are patched by halo_patcher below.
+// padding along d) is fetched with an h coordinate beyond the volume, i.e. as an all-zero box.
+// (Reflect padding cannot be expressed as an out-of-bounds fill.  Fetching the same boxes and patching the one-voxel in-plane
+// halo in shared memory by two extra warps was built and measured in round 2: the extra pipeline stage and the larger
+// row-aligned slabs made the forward family 6 % SLOWER than the cp.async producers, so reflect-padded launches keep those.)
 template <int NCHR, int kSlots>
 __device__ __forceinline__ void tma_producer(const TcP& p, const CUtensorMap* map0, const CUtensorMap* map1, uint8_t* slab_s,
                                              int slot_bytes, uint64_t* full, uint64_t* empty, int g, int items, int* err) {
@@ -130,59 +132,14 @@ __device__ __forceinline__ void tma_producer(const TcP& p, const CUtensorMap* ma
         for (int pl = 0; pl < nout + 2; ++pl, ++k) {
             const int slot = k % kSlots;
             mbar_wait(&empty[slot], ((k / kSlots) & 1) ^ 1, err, 1);
-            int dp = d0 - 1 + pl - p.inset;
-            bool plane_ok = true;
-            if (p.reflect) dp = reflect_idx(dp, Di); else plane_ok = dp >= 0 && dp < Di;
+            const int dp = d0 - 1 + pl - p.inset;
+            const bool plane_ok = dp >= 0 && dp < Di;
             mbar_expect_tx(&full[slot], bytes);
             const uint32_t sbase = smem_u32(slab_s + (size_t)slot * slot_bytes);
 #pragma unroll
             for (int ch = 0; ch < NCHR; ++ch)
                 tma_load_5d(sbase + (uint32_t)(ch * p.slab_e) * 16u, ch < c0ch ? map0 : map1, 0, -1 - p.inset,
                             plane_ok ? r0 - 1 - p.inset : Hi + 8, ch < c0ch ? ch : ch - c0ch, plane_ok ? n * Di + dp : 0, &full[slot]);
-        }
-    }
-}
-
-// Reflect padding on top of TMA (p.tma == 2; two warps): the one-voxel in-plane halo of a slab — padded column 0 / W+1 of every
-// row, padded row 0 / H+1 where the slab reaches them — is copied from the interior cell the reflection maps it to (always
-// inside the same slab: -1 -> 1, size -> size-2), shared memory to shared memory, once the plane's box has landed; the MMA
-// thread waits on `ready` instead of `full`.
-constexpr int kPatchThreads = 64, kPatchMax = 4;
-template <int NCHR, int kSlots>
-__device__ __forceinline__ void halo_patcher(const TcP& p, uint8_t* slab_s, int slot_bytes, uint64_t* full, uint64_t* ready, int items,
-                                             int pt, int* err) {
-    uint32_t k = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int dc = it % p.ND, r1 = it / p.ND;
-        const int qt = r1 % p.QT;
-        const int nout = min(p.DCH, p.D - dc * p.DCH);
-        const int r0 = (qt * p.q_stride) / p.PW;
-        int src[kPatchMax], dst[kPatchMax], np = 0;                 // this thread's halo cells of the slab (same for every plane)
-        int seen = 0;
-        const int cells = p.tma_rows * p.PW;
-        for (int idx = 0; idx < cells; ++idx) {                     // enumerate halo cells; cell number `seen` goes to thread seen % 64
-            const int rs = idx / p.PW, wp = idx - rs * p.PW, hp = r0 + rs;
-            if (hp > p.H + 1) break;
-            const bool hr = hp == 0 || hp == p.H + 1, hc = wp == 0 || wp == p.W + 1;
-            if (!(hr || hc)) { if (wp == 1 && !hr) idx += p.W - 1; continue; }     // skip the interior of a non-halo row
-            if (seen % kPatchThreads == pt && np < kPatchMax) {
-                const int sr = hp == 0 ? 2 : (hp == p.H + 1 ? p.H - 1 : hp), sc = wp == 0 ? 2 : (wp == p.W + 1 ? p.W - 1 : wp);
-                src[np] = ((sr - r0) * p.PW + sc) * 16; dst[np] = idx * 16; ++np;
-            }
-            ++seen;
-        }
-        for (int pl = 0; pl < nout + 2; ++pl, ++k) {
-            const int slot = k % kSlots;
-            mbar_wait(&full[slot], (k / kSlots) & 1, err, 6);
-            uint8_t* base = slab_s + (size_t)slot * slot_bytes;
-            for (int i = 0; i < np; ++i)
-#pragma unroll
-                for (int ch = 0; ch < NCHR; ++ch) {
-                    uint8_t* cp = base + (size_t)ch * p.slab_e * 16;
-                    *reinterpret_cast<uint4*>(cp + dst[i]) = *reinterpret_cast<const uint4*>(cp + src[i]);
-                }
-            fence_proxy_async();
-            mbar_arrive(&ready[slot]);
         }
     }
 }
@@ -258,15 +215,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
     uint64_t* blk_full = bars + 2 * kSlots;  // [R]       MMA -> epilogue: output plane complete
     uint64_t* blk_empty = blk_full + R;      // [R]       epilogue -> MMA: block drained and zeroed
     uint64_t* wbar = blk_empty + R;          // weights landed
-    uint64_t* ready = wbar + 1;              // [kSlots]  TMA + reflect padding: halo patched (halo_patcher -> MMA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kSlots);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.y, nt = blockIdx.z;
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], p.tma ? 1 : kTcProducers); mbar_init(&empty[i], 1); mbar_init(&ready[i], kPatchThreads); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], p.tma ? 1 : kTcProducers); mbar_init(&empty[i], 1); }
         for (int i = 0; i < R; ++i) { mbar_init(&blk_full[i], 1); mbar_init(&blk_empty[i], 128); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -298,8 +254,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
     if (warp >= 5 && p.tma) {
         // =============================== producer: one thread, TMA ===============================
         if (warp == 5 && lane == 0) tma_producer<NCHR, kSlots>(p, &tmap, &tmap1, slab_s, slot_bytes, full, empty, g, items, err);
-        else if (p.tma == 2 && (warp == 6 || warp == 7))
-            halo_patcher<NCHR, kSlots>(p, slab_s, slot_bytes, full, ready, items, threadIdx.x - 6 * 32, err);
     } else if (warp >= 5) {
         // =============================== producers ===============================
         // The (h, w) geometry of a slab row depends only on the q-tile, so each thread resolves its <= kMaxCopies
@@ -380,7 +334,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kernel(const __grid_co
                 // TMA slabs start at a padded-row boundary: the tile begins (q0 mod PW) rows into the slab
                 const uint32_t tile_off = p.tma ? (uint32_t)((((it / p.ND) % p.QT) * p.q_stride) % p.PW) * 16u : 0u;
                 for (int pl = 0; pl < nout + 2; ++pl, ++k) {
-                    mbar_wait(p.tma == 2 ? &ready[k % kSlots] : &full[k % kSlots], (k / kSlots) & 1, err, 3);
+                    mbar_wait(&full[k % kSlots], (k / kSlots) & 1, err, 3);
                     if (pl < nout) {                           // output plane pl gets its first contribution: its block must be free
                         const uint32_t jn = j0 + pl;
                         mbar_wait(&blk_empty[jn % R], ((jn / R) & 1) ^ 1, err, 4);
@@ -510,7 +464,7 @@ int launch_tc(const CUtensorMap& tmap, const CUtensorMap& tmap1, const TcP& p, c
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     constexpr int kSlots = NCHR >= 16 ? 2 : 6;
     const size_t w_bytes = (size_t)27 * NCH * NT * 16;
-    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (3 * kSlots + 2 * 16 + 1) * 8 + 16;
+    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 2 * 16 + 1) * 8 + 16;
     auto kern = conv3_tc_kernel<NCHR, NT>;
     if (smem > 227 * 1024) { pb_set_error("conv3d_tc: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -573,8 +527,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __gri
     uint64_t* blk_full = bars + 2 * kSlots;
     uint64_t* blk_empty = blk_full + R;
     uint64_t* wbar = blk_empty + R;
-    uint64_t* ready = wbar + 1;              // [kSlots]  TMA + reflect padding: halo patched (halo_patcher -> MMA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kSlots);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     float* xch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [2][4 warps][3][NT], 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -582,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __gri
     const int items = p.npg * p.QT * p.ND;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], p.tma ? 1 : kTcProducers); mbar_init(&empty[i], 1); mbar_init(&ready[i], kPatchThreads); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], p.tma ? 1 : kTcProducers); mbar_init(&empty[i], 1); }
         for (int i = 0; i < R; ++i) { mbar_init(&blk_full[i], 1); mbar_init(&blk_empty[i], 128); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -606,8 +559,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __gri
     if (warp >= 5 && p.tma) {
         // =============================== producer: one thread, TMA ===============================
         if (warp == 5 && lane == 0) tma_producer<NCHR, kSlots>(p, &tmap, &tmap1, slab_s, slot_bytes, full, empty, g, items, err);
-        else if (p.tma == 2 && (warp == 6 || warp == 7))
-            halo_patcher<NCHR, kSlots>(p, slab_s, slot_bytes, full, ready, items, threadIdx.x - 6 * 32, err);
     } else if (warp >= 5) {
         // =============================== producers (as conv3_tc_kernel; tiles advance by kKwsStride) ===============================
         const int pt = threadIdx.x - 5 * 32;
@@ -683,7 +634,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __gri
                 // TMA slabs start at a padded-row boundary: the tile begins (q0 mod PW) rows into the slab
                 const uint32_t tile_off = p.tma ? (uint32_t)((((it / p.ND) % p.QT) * p.q_stride) % p.PW) * 16u : 0u;
                 for (int pl = 0; pl < nout + 2; ++pl, ++k) {
-                    mbar_wait(p.tma == 2 ? &ready[k % kSlots] : &full[k % kSlots], (k / kSlots) & 1, err, 3);
+                    mbar_wait(&full[k % kSlots], (k / kSlots) & 1, err, 3);
                     if (pl < nout) {
                         const uint32_t jn = j0 + pl;
                         mbar_wait(&blk_empty[jn % R], ((jn / R) & 1) ^ 1, err, 4);
@@ -846,7 +797,7 @@ int launch_tc_kws(const CUtensorMap& tmap, const CUtensorMap& tmap1, const TcP& 
     constexpr int NCH = NCHR < 2 ? 2 : NCHR;
     constexpr int kSlots = NCHR >= 16 ? 2 : 6;
     const size_t w_bytes = (size_t)27 * NCH * 16 * 16;
-    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (3 * kSlots + 2 * 16 + 1) * 8 + 16
+    const size_t smem = ((w_bytes + 127) & ~(size_t)127) + (size_t)kSlots * NCH * p.slab_e * 16 + (2 * kSlots + 2 * 16 + 1) * 8 + 16
                         + 2 * 4 * 3 * 16 * sizeof(float) + 16;
     auto kern = conv3_tc_kws_kernel<NCHR, CR>;
     if (smem > 227 * 1024) { pb_set_error("conv3d_tc_kws: needs %zu B of shared memory", smem); return PB_EUNSUPPORTED; }
@@ -1514,8 +1465,8 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
 }
 
 namespace {
-int tc_tma_mode() {          // 0: cp.async producers, 1: TMA for zero-padded launches, 2 (default): TMA for all launches
-    static const int mode = [] { const char* e = getenv("PB_TC_TMA"); return e != nullptr && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2; }();
+int tc_tma_mode() {          // 0: cp.async producers everywhere, 1 (default): TMA for the zero-padded launches
+    static const int mode = [] { const char* e = getenv("PB_TC_TMA"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
     return mode;
 }
 
@@ -1677,21 +1628,19 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
     int se = p.slab_need;
     while (se % 8 != want % 8) ++se;
     p.slab_e = se;
-    // TMA-fed input planes (PB_TC_TMA=0: cp.async producers; =1: zero-padded launches only).  Zero padding is the tensor map's
-    // out-of-bounds fill; reflect padding fetches the same boxes and patches the one-voxel in-plane halo in shared memory.
+    // TMA-fed input planes for zero-padded launches — every data gradient (PB_TC_TMA=0: cp.async producers everywhere).
+    // Zero padding is the tensor map's out-of-bounds fill; reflect-padded launches keep the cp.async producers (see tma_producer).
     CUtensorMap tmap, tmap1;
     memset(&tmap, 0, sizeof(tmap));
     memset(&tmap1, 0, sizeof(tmap1));
     p.tma = 0; p.tma_rows = 0;
-    const int tma_mode = tc_tma_mode();
-    if (tma_mode >= (p.reflect ? 2 : 1) && d->c0 % 8 == 0 && d->c1 % 8 == 0) {
+    if (tc_tma_mode() >= 1 && !p.reflect && d->c0 % 8 == 0 && d->c1 % 8 == 0) {
         const int rows = (p.slab_need + p.PW - 2) / p.PW + 1;               // padded rows a slab of slab_need positions can touch
         const int se_t = ((rows * p.PW + 7) / 8) * 8;                       // chunk-plane pitch: TMA destinations are 128 B aligned
         const int Di = p.D - 2 * inset, Hi = p.H - 2 * inset, Wi = p.W - 2 * inset;
-        const bool halo_ok = !p.reflect || (rows >= 3 && Hi >= 3 && Wi >= 3 && 2 * rows + 2 * p.PW <= kPatchThreads * kPatchMax);
-        if (halo_ok && p.PW <= 256 && rows <= 256 && make_plane_map(&tmap, x0, d->c0, Wi, Hi, (long long)p.N * Di, p.PW, rows) == 0 &&
+        if (p.PW <= 256 && rows <= 256 && make_plane_map(&tmap, x0, d->c0, Wi, Hi, (long long)p.N * Di, p.PW, rows) == 0 &&
             (d->c1 == 0 || make_plane_map(&tmap1, x1, d->c1, Wi, Hi, (long long)p.N * Di, p.PW, rows) == 0)) {
-            p.tma = p.reflect ? 2 : 1; p.tma_rows = rows; p.slab_e = se_t;
+            p.tma = 1; p.tma_rows = rows; p.slab_e = se_t;
         }
     }
     p.w_tile_bytes = (long long)27 * nch * NT * 16;

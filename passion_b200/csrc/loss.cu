@@ -285,6 +285,155 @@ __global__ void __launch_bounds__(256) proto_bwd2_kernel(const uint8_t* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------ fused logit-level loss pass
+// One pass over the logits of P decoder passes (sample index p*B + b) for the losses that live at the logits' own resolution
+// (reference rfnet.py:284-377 / criterions.py:25-38, 59-76, 92-103), without materialising any probability tensor:
+//   mode 0 (teacher / students): pass 0 -> softmax (T = 1) -> the CE / Dice sums A, L, E (and, optionally, the probabilities
+//           themselves: Model.forward returns them); passes 1..P-1 -> KL(clamp(softmax(l_0 / T)) || clamp(softmax(l_p / T)));
+//   mode 1 (all supervised): every pass -> the CE / Dice sums (the per-modality decoder_sep predictions).
+// The backward kernel reads the logits again and writes d loss / d logits directly (softmax adjoint fused in).
+template <int P> struct LogitLossAcc { static constexpr int kCe0 = 12 + (P - 1), kCeAll = 12 * P; };
+
+__device__ __forceinline__ void softmax4_reg(const float* l, float inv_temp, float* p) {
+    const float a = l[0] * inv_temp, b = l[1] * inv_temp, c = l[2] * inv_temp, d = l[3] * inv_temp;
+    const float m = fmaxf(fmaxf(a, b), fmaxf(c, d));
+    p[0] = expf(a - m); p[1] = expf(b - m); p[2] = expf(c - m); p[3] = expf(d - m);
+    const float r = 1.f / (p[0] + p[1] + p[2] + p[3]);
+    p[0] *= r; p[1] *= r; p[2] *= r; p[3] *= r;
+}
+
+template <typename T, int P, int MODE>
+__global__ void __launch_bounds__(256) logit_loss_fwd_kernel(const T* __restrict__ logits, const uint8_t* __restrict__ labels,
+                                                            float* __restrict__ probs0, double* __restrict__ ce_sums,
+                                                            double* __restrict__ kl_sums, long long voxels, int B, float inv_temp) {
+    constexpr int NA = MODE == 0 ? 12 + (P - 1) : 12 * P;
+    const int b = blockIdx.y;
+    float acc[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+    const uint8_t* lb = labels + (size_t)b * voxels;
+    for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < voxels; v += (long long)gridDim.x * 256) {
+        const int t = lb[v];
+        float l0[4], p[4];
+        load4(logits + ((size_t)b * voxels + v) * 4, l0);
+        softmax4_reg(l0, 1.f, p);
+        if (probs0 != nullptr) reinterpret_cast<float4*>(probs0)[(size_t)b * voxels + v] = make_float4(p[0], p[1], p[2], p[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            acc[4 + c] += p[c];
+            if (t == c) { acc[c] += p[c]; acc[8 + c] += logf(fminf(fmaxf(p[c], kClampMin), 1.f)); }
+        }
+        if (MODE == 0) {
+            float tc[4], ltc[4];
+            softmax4_reg(l0, inv_temp, p);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { tc[c] = fminf(fmaxf(p[c], kClampMin), 1.f); ltc[c] = logf(tc[c]); }
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                float lq[4];
+                load4(logits + (((size_t)q * B + b) * voxels + v) * 4, lq);
+                softmax4_reg(lq, inv_temp, p);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[12 + q - 1] += tc[c] * (ltc[c] - logf(fminf(fmaxf(p[c], kClampMin), 1.f)));
+            }
+        } else {
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                float lq[4];
+                load4(logits + (((size_t)q * B + b) * voxels + v) * 4, lq);
+                softmax4_reg(lq, 1.f, p);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc[q * 12 + 4 + c] += p[c];
+                    if (t == c) { acc[q * 12 + c] += p[c]; acc[q * 12 + 8 + c] += logf(fminf(fmaxf(p[c], kClampMin), 1.f)); }
+                }
+            }
+        }
+    }
+    // block reduction: 12 CE/Dice sums per supervised pass, one KL sum per student pass
+    __shared__ float red[8][NA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const float sv = warp_sum(acc[i]);
+        if (lane == 0) red[wid][i] = sv;
+    }
+    __syncthreads();
+    if (threadIdx.x < NA) {
+        float sv = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sv += red[w][threadIdx.x];
+        const int i = threadIdx.x;
+        if (MODE == 0) {
+            if (i < 12) atomicAdd(ce_sums + (size_t)b * 12 + i, (double)sv);
+            else atomicAdd(kl_sums + (size_t)(i - 12) * B + b, (double)sv);
+        } else {
+            atomicAdd(ce_sums + ((size_t)(i / 12) * B + b) * 12 + (i % 12), (double)sv);
+        }
+    }
+}
+
+// d/d logit of a supervised pass: g_c = coef[4+c] + [t==c] (coef[c] + coef[8+c] / p_c inside the clamp) (+ dprobs_c); dl = p (g - <p, g>)
+__device__ __forceinline__ void cedice_logit_grad(const float* p, int t, const float* cf, const float* extra, float* o) {
+    float g[4], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float gc = cf[4 + c] + (extra != nullptr ? extra[c] : 0.f);
+        if (t == c) gc += cf[c] + ((p[c] >= kClampMin && p[c] <= 1.f) ? cf[8 + c] / p[c] : 0.f);
+        g[c] = gc; dot += p[c] * gc;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[c] = p[c] * (g[c] - dot);
+}
+
+template <typename T, int P, int MODE>
+__global__ void __launch_bounds__(256) logit_loss_bwd_kernel(const T* __restrict__ logits, const uint8_t* __restrict__ labels,
+                                                            const float* __restrict__ ce_coef, const float* __restrict__ kl_coef,
+                                                            const float* __restrict__ dprobs0, T* __restrict__ dlogits,
+                                                            long long voxels, int B, float inv_temp, long long total) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int b = (int)(i / voxels);
+        const long long v = i - (long long)b * voxels;
+        const int t = labels[i];
+        float l0[4], p[4], o[4];
+        load4(logits + (size_t)i * 4, l0);
+        softmax4_reg(l0, 1.f, p);
+        float ex[4];
+        if (dprobs0 != nullptr) { const float4 e4 = __ldg(reinterpret_cast<const float4*>(dprobs0) + i); ex[0] = e4.x; ex[1] = e4.y; ex[2] = e4.z; ex[3] = e4.w; }
+        cedice_logit_grad(p, t, ce_coef + (size_t)b * 12, dprobs0 != nullptr ? ex : nullptr, o);
+        VecIO<T, 4>::store(dlogits + (size_t)i * 4, o);
+        if (MODE == 0) {
+            float tc[4];
+            softmax4_reg(l0, inv_temp, p);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tc[c] = fminf(fmaxf(p[c], kClampMin), 1.f);
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                const size_t row = ((size_t)q * B + b) * voxels + v;
+                float lq[4], g[4], dot = 0.f;
+                load4(logits + row * 4, lq);
+                softmax4_reg(lq, inv_temp, p);
+                const float cf = kl_coef[(size_t)(q - 1) * B + b];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { g[c] = (p[c] >= kClampMin && p[c] <= 1.f) ? -cf * tc[c] / p[c] : 0.f; dot += p[c] * g[c]; }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[c] = inv_temp * p[c] * (g[c] - dot);
+                VecIO<T, 4>::store(dlogits + row * 4, o);
+            }
+        } else {
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                const size_t row = ((size_t)q * B + b) * voxels + v;
+                float lq[4];
+                load4(logits + row * 4, lq);
+                softmax4_reg(lq, 1.f, p);
+                cedice_logit_grad(p, t, ce_coef + ((size_t)q * B + b) * 12, nullptr, o);
+                VecIO<T, 4>::store(dlogits + row * 4, o);
+            }
+        }
+    }
+}
+
 int ew_blocks(long long work) {
     long long bl = (work + 255) / 256;
     if (bl > 148LL * 16) bl = 148LL * 16;
