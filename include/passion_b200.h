@@ -238,6 +238,19 @@ int pb_rfm_bwd_y(int dtype, const float* p, const float* gate, const void* dr, c
 int pb_softmax4(int dtype, const void* logits, float* probs, long long rows, float inv_temp, pb_stream_t stream);
 int pb_softmax4_bwd(int dtype, const float* probs, const float* dprobs, void* dlogits, long long rows,
                     float inv_temp, pb_stream_t stream);
+/* Fused logit-level loss pass (the north_star's "one pass over the logits"): logits [passes*b][voxels][4] (sample = pass*b + sample),
+ * labels uint8 [b][voxels]; no probability tensor is materialised.
+ *   mode 0: pass 0 -> softmax (T = 1) -> ce_sums[b][12] (A, L, E as pb_cedice_fwd) and, if probs0 != NULL, the probabilities
+ *           [b][voxels][4] fp32 (Model.forward's first output); passes 1.. -> kl_sums[(pass-1)*b + sample] =
+ *           sum_{v,c} pt (log pt - log ps), pt / ps = clamp(softmax(logit / T), .005, 1) of pass 0 / pass p (rfnet.py:284-377).
+ *   mode 1: every pass -> ce_sums[pass*b + sample][12] (the four decoder_sep predictions).
+ * pb_logit_loss_bwd writes d/d logits [passes*b][voxels][4] (dtype of the logits) from ce_coef (same shape as ce_sums, fp32),
+ * kl_coef and, optionally, an incoming gradient dprobs0 of the returned probabilities.  (passes, mode) in {(5,0), (1,0), (4,1)}. */
+int pb_logit_loss_fwd(int dtype, const void* logits, const uint8_t* labels, float* probs0, double* ce_sums, double* kl_sums,
+                      int passes, int b, long long voxels, int mode, float inv_temp, pb_stream_t stream);
+int pb_logit_loss_bwd(int dtype, const void* logits, const uint8_t* labels, const float* ce_coef, const float* kl_coef,
+                      const float* dprobs0, void* dlogits, int passes, int b, long long voxels, int mode, float inv_temp,
+                      pb_stream_t stream);
 int pb_cedice_fwd(const float* probs, const uint8_t* labels, double* sums, int n, int b, long long voxels,
                   pb_stream_t stream);
 int pb_cedice_bwd(const float* probs, const uint8_t* labels, const float* coef, float* dprobs, int n, int b,

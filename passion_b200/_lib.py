@@ -103,6 +103,8 @@ def load():
         "pb_upsample_bwd_axis": [i32, vp, vp, i64, i32, i32, i64, i32, vp],
         "pb_softmax4": [i32, vp, vp, i64, f32, vp],
         "pb_softmax4_bwd": [i32, vp, vp, vp, i64, f32, vp],
+        "pb_logit_loss_fwd": [i32, vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, vp],
+        "pb_logit_loss_bwd": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, vp],
         "pb_cedice_fwd": [vp, vp, vp, i32, i32, i64, vp],
         "pb_cedice_bwd": [vp, vp, vp, vp, i32, i32, i64, vp],
         "pb_kl_fwd": [vp, vp, vp, i32, i32, i64, vp],

@@ -85,6 +85,27 @@ def cedice(prob, labels, cnt, wgt, eps=1e-7):
     return ce, dice
 
 
+def ce_dice_from_sums(s, cnt, wgt, voxels, b, eps=1e-7):
+    """(ce [N], dice [N]) from the A / L / E sums [N,3,4] of N = k*B supervised samples (criterions.py:25-38, :59-76)."""
+    n = s.shape[0]
+    cnt_n, wgt_n = cnt.repeat(n // b, 1), wgt.repeat(n // b, 1)
+    dice = 1.0 - (2.0 * s[:, 0] / (s[:, 1] + cnt_n + eps)).sum(1) / s.shape[-1]
+    ce = -(wgt_n * s[:, 2]).sum(1) / voxels
+    return ce, dice
+
+
+def logit_losses(logits, labels, cnt, wgt, passes, mode, temp=1.0, want_probs=False):
+    """The losses that live at the logits' own resolution from ONE fused pass (ops.logit_loss): logits [passes*B,D,H,W,4].
+    mode 0 -> (ce [B], dice [B]) of pass 0, kl [(passes-1)*B] of passes 1.. against pass 0 (T^2 * mean, criterions.py:98-102),
+    probabilities of pass 0 or None; mode 1 -> (ce, dice) [passes*B] of every pass, None, None."""
+    b = labels.shape[0]
+    voxels = labels.numel() // b
+    s, kls, probs = ops.logit_loss(logits.contiguous(), labels, passes, mode, temp, want_probs)
+    ce, dice = ce_dice_from_sums(s, cnt, wgt, voxels, b)
+    klv = (temp * temp / (voxels * 4)) * kls if (mode == 0 and passes > 1) else None
+    return ce, dice, klv, probs
+
+
 def kl(ps, pt, temp):
     """ps [N,D,H,W,4], pt [B,D,H,W,4]: fp32 probabilities at temperature `temp`, same resolution.  Returns [N]
     = T^2 * mean_{c,v} clamp(pt) (log clamp(pt) - log clamp(ps))   (criterions.py:98-102)."""
@@ -103,6 +124,10 @@ def proto(fs, ft, labels, cnt, eps=1e-5):
 def ce_dice_bs(output, target, num_cls=5, eps=1e-7, up_op=None):
     """softmax_weighted_loss_bs + dice_loss_bs of the same prediction from ONE pass over it (the step's fused-prediction
     term, train.py:228-229).  Returns ([B,1] CE, [B,1] Dice)."""
+    stash = getattr(output, "_pb_ce_dice", None)
+    if stash is not None and stash[2]() is target and _scale_of(up_op) == 1:
+        # Model.forward already accumulated these sums in its fused logit pass over the same prediction and target
+        return stash[0].unsqueeze(1), stash[1].unsqueeze(1)
     p = up_probs(_to_cl(output.float()), _scale_of(up_op))
     labels, cnt, wgt = label_stats(target)
     ce, dice = cedice(p, labels, cnt, wgt, eps)

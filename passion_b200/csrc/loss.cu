@@ -448,6 +448,60 @@ int red_blocks(long long voxels, int n) {
 
 }  // namespace
 
+namespace {
+template <typename T, int P, int MODE>
+void launch_logit_loss(bool bwd, const void* logits, const uint8_t* labels, float* probs0, double* ce_sums, double* kl_sums,
+                       const float* ce_coef, const float* kl_coef, const float* dprobs0, void* dlogits, int b, long long voxels,
+                       float inv_temp, cudaStream_t st) {
+    if (!bwd) {
+        logit_loss_fwd_kernel<T, P, MODE><<<dim3(red_blocks(voxels, b), b), 256, 0, st>>>((const T*)logits, labels, probs0, ce_sums, kl_sums,
+                                                                                       voxels, b, inv_temp);
+    } else {
+        const long long total = (long long)b * voxels;
+        logit_loss_bwd_kernel<T, P, MODE><<<ew_blocks(total), 256, 0, st>>>((const T*)logits, labels, ce_coef, kl_coef, dprobs0, (T*)dlogits,
+                                                                          voxels, b, inv_temp, total);
+    }
+}
+
+int dispatch_logit_loss(bool bwd, int dtype, const void* logits, const uint8_t* labels, float* probs0, double* ce_sums, double* kl_sums,
+                        const float* ce_coef, const float* kl_coef, const float* dprobs0, void* dlogits, int passes, int b,
+                        long long voxels, int mode, float inv_temp, cudaStream_t st) {
+#define LL_CASE(P_, M_)                                                                                                                   \
+    if (passes == P_ && mode == M_) {                                                                                                     \
+        if (dtype == PB_BF16) launch_logit_loss<bf16, P_, M_>(bwd, logits, labels, probs0, ce_sums, kl_sums, ce_coef, kl_coef, dprobs0,   \
+                                                              dlogits, b, voxels, inv_temp, st);                                          \
+        else launch_logit_loss<float, P_, M_>(bwd, logits, labels, probs0, ce_sums, kl_sums, ce_coef, kl_coef, dprobs0, dlogits, b,       \
+                                              voxels, inv_temp, st);                                                                      \
+        return 0;                                                                                                                         \
+    }
+    LL_CASE(5, 0) LL_CASE(1, 0) LL_CASE(4, 1)
+#undef LL_CASE
+    pb_set_error("logit_loss: unsupported (passes %d, mode %d): 5/0 (teacher + 4 students), 1/0, 4/1 (4 supervised passes)", passes, mode);
+    return PB_EUNSUPPORTED;
+}
+}  // namespace
+
+extern "C" int pb_logit_loss_fwd(int dtype, const void* logits, const uint8_t* labels, float* probs0, double* ce_sums, double* kl_sums,
+                                 int passes, int b, long long voxels, int mode, float inv_temp, pb_stream_t stream) {
+    PB_CHECK_ARG(logits && labels && ce_sums && passes >= 1 && b > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(mode == 1 || passes == 1 || kl_sums, "kl_sums needed for student passes");
+    if (int e = dispatch_logit_loss(false, dtype, logits, labels, probs0, ce_sums, kl_sums, nullptr, nullptr, nullptr, nullptr, passes, b,
+                                    voxels, mode, inv_temp, (cudaStream_t)stream)) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+extern "C" int pb_logit_loss_bwd(int dtype, const void* logits, const uint8_t* labels, const float* ce_coef, const float* kl_coef,
+                                 const float* dprobs0, void* dlogits, int passes, int b, long long voxels, int mode, float inv_temp,
+                                 pb_stream_t stream) {
+    PB_CHECK_ARG(logits && labels && ce_coef && dlogits && passes >= 1 && b > 0 && voxels > 0, "bad argument");
+    PB_CHECK_ARG(mode == 1 || passes == 1 || kl_coef, "kl_coef needed for student passes");
+    if (int e = dispatch_logit_loss(true, dtype, logits, labels, nullptr, nullptr, nullptr, ce_coef, kl_coef, dprobs0, dlogits, passes, b,
+                                    voxels, mode, inv_temp, (cudaStream_t)stream)) return e;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
 extern "C" int pb_softmax4(int dtype, const void* logits, float* probs, long long rows, float inv_temp, pb_stream_t stream) {
     PB_CHECK_ARG(logits && probs && rows > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;

@@ -18,6 +18,8 @@ The token path (LayerNorm, attention, MLP: ~125-500 tokens of width 512) is plai
 (cuBLAS / SDPA); it is not the hot path and costs well under a millisecond per step.
 The nn.Conv3d / nn.Linear objects below are parameter containers only; their torch forward is never called.
 """
+import weakref
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -376,44 +378,40 @@ class Model(nn.Module):
         logits, preds, des = self.decoder_fuse.run(*ys, x5)
         D, H, W = logits.shape[1:4]
         fuse_logits = logits.view(P, B, D, H, W, -1)
-        fuse_prob = ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)        # [B,C,D,H,W]
         self.last = {"fuse_logits": fuse_logits, "prm_logits": preds, "de_f": des, "passes": P, "enc": enc, "x5": x5}
         if not self.is_training:
-            return fuse_prob
+            return ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)         # [B,C,D,H,W]
 
         if sep_logits is None:
             sep_logits = self.decoder_sep.run(*feat)                          # [4B,D,H,W,C], modality-major
         else:
             torch.cuda.current_stream(dev).wait_stream(_rf._side_stream(dev))
-        # mmformer.py:480-483 zeroes a missing modality's probabilities; its loss is multiplied by the same 0 below, so the
-        # product over the volume is skipped (see models/rfnet.py)
-        sep_prob = ops.softmax4(sep_logits).view(4, B, D, H, W, -1)
-        self.last["sep_prob"] = sep_prob
+        self.last["sep_logits"] = sep_logits
         labels, cnt, wgt = crit.label_stats(target)
+        V = D * H * W
+        # one fused pass over the fused-decoder logits (prediction, its CE / Dice sums, KL of the single-modality passes) and one
+        # over the four decoder_sep predictions; mmformer.py:480-483 zeroes a missing modality's probabilities, but its loss is
+        # multiplied by the same 0 below, so that product over the volume is skipped (see models/rfnet.py)
+        ce_f, dice_f, kl, probs = crit.logit_losses(logits, labels, cnt, wgt, P, 0, temp, want_probs=True)
+        fuse_prob = probs.permute(0, 4, 1, 2, 3)                              # [B,C,D,H,W]
+        fuse_prob._pb_ce_dice = (ce_f, dice_f, weakref.ref(target))
+        ce, dice, _, _ = crit.logit_losses(sep_logits, labels, cnt, wgt, 4, 1)
+        sep_loss = (e * (ce + dice).view(4, B)).t()                           # [B,4]
 
         prm_loss = torch.zeros(B, device=dev)
         wl = 1.0
-        for prm, s in zip(preds, UP_SCALES):                                  # mmformer.py:564-571
+        for prm, s in zip(preds, UP_SCALES):                                  # mmformer.py:564-571, 628-650
             wl /= 2.0
-            p0 = ops.softmax4(prm.view(P, B, *prm.shape[1:])[0])
-            ce, dice = crit.cedice(crit.up_probs(p0, s), labels, cnt, wgt)
+            pr = prm.view(P, B, *prm.shape[1:])
+            ce, dice = crit.cedice(crit.up_probs(ops.softmax4(pr[0]), s), labels, cnt, wgt)
             prm_loss = prm_loss + wl * (ce + dice)
-        ce, dice = crit.cedice(sep_prob.view(4 * B, D, H, W, -1), labels, cnt, wgt)
-        sep_loss = (e * (ce + dice).view(4, B)).t()                           # [B,4]
+            if train_passion:
+                ps_l = crit.up_probs(ops.softmax4(pr[1:].reshape(4 * B, *prm.shape[1:]), temp), s)
+                pt_l = crit.up_probs(ops.softmax4(pr[0].detach(), temp), s)
+                kl = kl + wl * crit.kl(ps_l, pt_l, temp)
         if not self.use_passion:
             return fuse_prob, prm_loss[:, None], sep_loss                     # mmformer.py:586
 
-        V = D * H * W
-        ps = ops.softmax4(fuse_logits[1:].reshape(4 * B, D, H, W, -1), temp)
-        pt = ops.softmax4(fuse_logits[0].detach(), temp)
-        kl = crit.kl(ps, pt, temp)                                            # [4B]
-        wl = 1.0
-        for prm, s in zip(preds, UP_SCALES):
-            wl /= 2.0
-            pr = prm.view(P, B, *prm.shape[1:])
-            ps_l = crit.up_probs(ops.softmax4(pr[1:].reshape(4 * B, *prm.shape[1:]), temp), s)
-            pt_l = crit.up_probs(ops.softmax4(pr[0].detach(), temp), s)
-            kl = kl + wl * crit.kl(ps_l, pt_l, temp)
         kl = kl.view(4, B)
         de1 = des[0].view(P, B, V, -1)
         proto, dist = crit.proto(de1[1:].reshape(4 * B, V, -1), de1[0].detach(), labels.view(B, V), cnt)

@@ -20,6 +20,7 @@ The nn.Conv3d / nn.Sequential objects below are parameter containers only (names
 their torch forward is never called.
 """
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -35,6 +36,7 @@ SIDE_RECORD = os.environ.get("PB_SIDE_RECORD", "1") != "0"   # debugging switch 
 # single-modality passes without their 3/4-zero stacks, at the N finest levels (the coarse levels are launch-bound: splitting
 # their batch into dense + single parts costs more launches than the bytes it saves)
 SPARSE_SINGLES = int(os.environ.get("PB_SPARSE_SINGLES", "2"))
+FUSED_LOSS = os.environ.get("PB_FUSED_LOSS", "1") != "0"     # logit-level losses from one fused pass (csrc/loss.cu logit_loss_*)
 _side = {}
 
 
@@ -394,50 +396,61 @@ class Model(nn.Module):
             logits, prms, des = self.decoder_fuse.run(*ys)
         D, H, W = logits.shape[1:4]
         fuse_logits = logits.view(P, B, D, H, W, -1)
-        fuse_prob = ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)                  # [B,C,D,H,W]
         self.last = {"fuse_logits": fuse_logits, "prm_logits": prms, "de_f": des, "passes": P, "enc": enc}
         if not self.is_training:
-            return fuse_prob
+            return ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)                   # [B,C,D,H,W]
 
         if sep_logits is None:
             sep_logits = self.decoder_sep.run(*enc)                           # [4B,D,H,W,C], modality-major
         else:
             torch.cuda.current_stream(x.device).wait_stream(_side_stream(x.device))
-        sep_prob = ops.softmax4(sep_logits).view(4, B, D, H, W, -1)
+        self.last["sep_logits"] = sep_logits
         e = (fm if idt else torch.ones_like(fm)).t()                          # [4(m),B]
-        # rfnet.py:259-260 multiplies the probabilities of a MISSING modality by 0 before the loss; that sample's loss is then
-        # multiplied by the same 0 below (and again in train.py:260), so value and gradient are exactly 0 either way and the
-        # 131 MB element-wise product (and its backward) is skipped: e * f(p) == e * f(e * p) for e in {0, 1}, f finite
-        self.last["sep_prob"] = sep_prob
-
         labels, cnt, wgt = crit.label_stats(target)
+        V = D * H * W
 
-        # ---- prm loss (rfnet.py:284-288): full-mask pass only
+        if FUSED_LOSS:
+            # ONE pass over the fused-decoder logits: softmax of the full-mask pass (the returned prediction), its CE / Dice sums
+            # (the step's fuse loss, train.py:228-229 — handed to criterions.ce_dice_bs through the tensor) and, with PASSION,
+            # the KL of the four single-modality passes against it; no probability tensor is materialised
+            ce_f, dice_f, kl, probs = crit.logit_losses(logits, labels, cnt, wgt, P, 0, temp, want_probs=True)
+            fuse_prob = probs.permute(0, 4, 1, 2, 3)                                     # [B,C,D,H,W]
+            fuse_prob._pb_ce_dice = (ce_f, dice_f, weakref.ref(target))
+            # rfnet.py:259-260 multiplies the probabilities of a MISSING modality by 0 before the loss; that sample's loss is
+            # then multiplied by the same 0 below (and again in train.py:260): e * f(p) == e * f(e * p) for e in {0, 1}
+            ce, dice, _, _ = crit.logit_losses(sep_logits, labels, cnt, wgt, 4, 1)
+        else:
+            fuse_prob = ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)
+            ce, dice = crit.cedice(ops.softmax4(sep_logits), labels, cnt, wgt)
+            kl = None
+            if train_passion:
+                ps = ops.softmax4(fuse_logits[1:].reshape(4 * B, D, H, W, -1), temp)
+                pt = ops.softmax4(fuse_logits[0].detach(), temp)
+                kl = crit.kl(ps, pt, temp)                                     # [4B]
+        sep_loss = (e * (ce + dice).view(4, B)).t()                           # [B,4]   (rfnet.py:336 ...)
+
+        # ---- prm loss (rfnet.py:284-288, full-mask pass only) and the PRM part of the KL term (rfnet.py:340-344 ...)
         prm_loss = torch.zeros(B, device=x.device)
         wl = 1.0
         for prm, s in zip(prms, UP_SCALES):
             wl /= 2.0
-            p0 = ops.softmax4(prm.view(P, B, *prm.shape[1:])[0])
-            ce, dice = crit.cedice(crit.up_probs(p0, s), labels, cnt, wgt)
+            if FUSED_LOSS and s == 1:                                          # the level at the labels' resolution: same fused pass
+                ce, dice, kl_l, _ = crit.logit_losses(prm, labels, cnt, wgt, P, 0, temp)
+            else:
+                pr = prm.view(P, B, *prm.shape[1:])
+                ce, dice = crit.cedice(crit.up_probs(ops.softmax4(pr[0]), s), labels, cnt, wgt)
+                kl_l = None
+                if train_passion:
+                    ps_l = crit.up_probs(ops.softmax4(pr[1:].reshape(4 * B, *prm.shape[1:]), temp), s)
+                    pt_l = crit.up_probs(ops.softmax4(pr[0].detach(), temp), s)
+                    kl_l = crit.kl(ps_l, pt_l, temp)
             prm_loss = prm_loss + wl * (ce + dice)
-        # ---- sep loss (rfnet.py:336 ...)
-        ce, dice = crit.cedice(sep_prob.view(4 * B, D, H, W, -1), labels, cnt, wgt)
-        sep_loss = (e * (ce + dice).view(4, B)).t()                           # [B,4]
+            if train_passion:
+                kl = kl + wl * kl_l
         if not self.use_passion:
             return fuse_prob, prm_loss[:, None], sep_loss                     # rfnet.py:402
 
         # ---- PASSION terms: single-modality passes 1..4 vs the detached full-mask pass 0
-        V = D * H * W
-        ps = ops.softmax4(fuse_logits[1:].reshape(4 * B, D, H, W, -1), temp)
-        pt = ops.softmax4(fuse_logits[0].detach(), temp)
-        kl = crit.kl(ps, pt, temp)                                             # [4B]
-        wl = 1.0
-        for prm, s in zip(prms, UP_SCALES):
-            wl /= 2.0
-            pr = prm.view(P, B, *prm.shape[1:])
-            ps_l = crit.up_probs(ops.softmax4(pr[1:].reshape(4 * B, *prm.shape[1:]), temp), s)
-            pt_l = crit.up_probs(ops.softmax4(pr[0].detach(), temp), s)
-            kl = kl + wl * crit.kl(ps_l, pt_l, temp)
         kl = kl.view(4, B)
         de1 = des[0].view(P, B, V, -1)
         proto, dist = crit.proto(de1[1:].reshape(4 * B, V, -1), de1[0].detach(), labels.view(B, V), cnt)

@@ -1015,6 +1015,62 @@ def softmax4(logits, temp=1.0):
     return _Softmax4.apply(logits, float(temp))
 
 
+class _LogitLoss(torch.autograd.Function):
+    """Fused logit-level loss pass (csrc/loss.cu logit_loss_*): logits [passes*B, D, H, W, 4], labels uint8 [B, D, H, W].
+    mode 0: pass 0 supervised (CE / Dice sums, optionally its probabilities), passes 1.. distilled from pass 0 (KL sums at
+    temperature `temp`; the teacher is detached as in the reference).  mode 1: every pass supervised.
+    Returns (ce_sums [n,3,4] fp32: A, L, E per supervised sample; kl_sums [(passes-1)*B] fp32; probs [B,D,H,W,4] fp32 or None)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, passes, mode, temp, want_probs):
+        lib = _lib.load()
+        _chk(logits, labels)
+        B = labels.shape[0]
+        voxels = labels.numel() // B
+        assert logits.shape[-1] == 4 and logits.numel() == passes * B * voxels * 4 and labels.dtype == torch.uint8
+        dev = logits.device
+        n_ce = B if mode == 0 else passes * B
+        ce = torch.zeros((n_ce, 12), dtype=torch.float64, device=dev)
+        kl = torch.zeros(((passes - 1) * B,), dtype=torch.float64, device=dev) if mode == 0 and passes > 1 else None
+        probs = torch.empty(tuple(labels.shape) + (4,), dtype=torch.float32, device=dev) if want_probs else None
+        nb = logits.numel() * logits.element_size() + labels.numel() + (probs.numel() * 4 if want_probs else 0)
+        _run("logit_loss_fwd", f"p{passes} m{mode}", nb, 0,
+             lambda: lib.pb_logit_loss_fwd(_dt(logits), _p(logits), _p(labels), _p(probs), _p(ce), _p(kl), passes, B, voxels, mode,
+                                           1.0 / temp, _stream()))
+        ctx.save_for_backward(logits, labels)
+        ctx.set_materialize_grads(False)          # the gradient of an unused output arrives as None instead of a dense zero tensor
+        ctx.meta = (passes, mode, temp, B, voxels, n_ce)
+        klf = kl.float() if kl is not None else torch.zeros((0,), dtype=torch.float32, device=dev)
+        if probs is None:
+            probs = torch.zeros((0,), dtype=torch.float32, device=dev)
+        return ce.float().view(n_ce, 3, 4), klf, probs
+
+    @staticmethod
+    def backward(ctx, dce, dkl, dprobs):
+        lib = _lib.load()
+        logits, labels = ctx.saved_tensors
+        passes, mode, temp, B, voxels, n_ce = ctx.meta
+        dev = logits.device
+        ce_coef = (dce.reshape(n_ce, 12).contiguous().float() if dce is not None
+                   else torch.zeros((n_ce, 12), dtype=torch.float32, device=dev))
+        kl_coef = None
+        if mode == 0 and passes > 1:
+            kl_coef = dkl.contiguous().float() if dkl is not None else torch.zeros(((passes - 1) * B,), dtype=torch.float32, device=dev)
+        # the returned probabilities normally only leave the graph (Model.forward's first output; the step's CE / Dice of it
+        # come from this same pass): a gradient arrives only when a caller differentiates through them
+        dp = dprobs.contiguous().float() if dprobs is not None and dprobs.numel() == B * voxels * 4 else None
+        dlogits = torch.empty_like(logits)
+        _run("logit_loss_bwd", f"p{passes} m{mode}", 2 * logits.numel() * logits.element_size() + labels.numel(), 0,
+             lambda: lib.pb_logit_loss_bwd(_dt(logits), _p(logits), _p(labels), _p(ce_coef), _p(kl_coef), _p(dp), _p(dlogits), passes, B,
+                                           voxels, mode, 1.0 / temp, _stream()))
+        return dlogits, None, None, None, None, None
+
+
+def logit_loss(logits, labels, passes, mode, temp=1.0, want_probs=False):
+    ce, kl, probs = _LogitLoss.apply(logits, labels, passes, mode, float(temp), want_probs)
+    return ce, kl, (probs if want_probs else None)
+
+
 class _CeDiceSums(torch.autograd.Function):
     """probs [N, V.., 4] fp32 at label resolution, labels uint8 [B, V..] -> sums [N, 3, 4] fp32:
     A_c = sum p_c t_c, L_c = sum p_c, E_c = sum t_c log(clamp(p_c, .005, 1)).  Sample n uses labels n % B."""

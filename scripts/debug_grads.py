@@ -28,7 +28,7 @@ def main():
     for l in range(4):
         keep[f"prm{l+1}"] = last["prm_logits"][l]
         keep[f"de{l+1}"] = last["de_f"][l]
-    keep["sep_prob"] = last["sep_prob"]
+    keep["sep_prob"] = torch.softmax(last["sep_logits"].float(), -1)
     for i, e in enumerate(last["enc"]):
         keep[f"enc{i+1}"] = e
     for t in keep.values():

@@ -328,6 +328,51 @@ def test_single_modality_passes_equal_their_stacks(lib_built, c, shape, dtype):
         assert rel(ga, gb) < (2e-4 if dtype == torch.float32 else 2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("passes,mode", [(5, 0), (1, 0), (4, 1)])
+def test_fused_logit_loss_equals_unfused(lib_built, passes, mode, dtype):
+    """ops.logit_loss (one pass over the logits: softmax, CE / Dice sums, temperature KL against the detached first pass) against
+    the separate softmax4 / cedice_sums / kl_sums kernels: sums, returned probabilities and d/d logits."""
+    from passion_b200 import ops
+    g = torch.Generator().manual_seed(10 * passes + mode)
+    B, shape, temp = 2, (6, 7, 8), 4.0
+    logits = (3 * torch.randn(passes * B, *shape, 4, generator=g)).cuda().to(dtype)
+    labels = torch.randint(0, 4, (B, *shape), generator=g).to(torch.uint8).cuda()
+    n_ce = B if mode == 0 else passes * B
+    w_ce = torch.randn(n_ce, 3, 4, generator=g).cuda()
+    w_kl = torch.randn((passes - 1) * B, generator=g).cuda()
+    w_p = torch.randn(B, *shape, 4, generator=g).cuda()
+
+    def fused(use_probs):
+        l = logits.clone().requires_grad_(True)
+        ce, kl, probs = ops.logit_loss(l, labels, passes, mode, temp, want_probs=True)
+        loss = (ce * w_ce).sum() + ((kl * w_kl).sum() if kl.numel() else 0.0) + ((probs * w_p).sum() if use_probs else 0.0)
+        loss.backward()
+        return ce.detach(), kl.detach(), probs.detach(), l.grad
+
+    def unfused(use_probs):
+        l = logits.clone().requires_grad_(True)
+        lv = l.view(passes, B, *shape, 4)
+        p0 = ops.softmax4(lv[0])
+        if mode == 0:
+            ce = ops.cedice_sums(p0, labels)
+            kl = (ops.kl_sums(ops.softmax4(lv[1:].reshape((passes - 1) * B, *shape, 4), temp), ops.softmax4(lv[0].detach(), temp))
+                  if passes > 1 else torch.zeros(0, device="cuda"))
+        else:
+            ce = ops.cedice_sums(ops.softmax4(l), labels)
+            kl = torch.zeros(0, device="cuda")
+        loss = (ce * w_ce).sum() + ((kl * w_kl).sum() if kl.numel() else 0.0) + ((p0 * w_p).sum() if use_probs else 0.0)
+        loss.backward()
+        return ce.detach(), kl.detach(), p0.detach(), l.grad
+
+    for use_probs in (False, True):
+        a, b = fused(use_probs), unfused(use_probs)
+        assert rel(a[0], b[0]) < 1e-5 and rel(a[2], b[2]) < 1e-6
+        if a[1].numel():
+            assert rel(a[1], b[1]) < 1e-4
+        assert rel(a[3], b[3]) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
 # ------------------------------------------------------------------------------------------------ loss kernels
 def _onehot_target(labels, num_cls=4):
     return F.one_hot(labels.long(), num_cls).permute(0, 4, 1, 2, 3).double()
