@@ -359,6 +359,10 @@ def run_ours(args):
     if args.model != "rfnet":
         # SURVEY.md §8d's per-sample flop / byte figures are RFNet's; the secondary backbone reports kernel families only
         roofline.pop("step_hbm_frac"); roofline.pop("step_tc_frac")
+    if world == 1 and args.model == "rfnet" and not args.no_extras:
+        del trainer, model
+        torch.cuda.empty_cache()
+        out["extra_configs"] = extra_configs(dev)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], ref_first = cpu_baseline(budget_s=30.0, model=args.model, S=S)
         try:
@@ -463,6 +467,69 @@ def parity_block(ref_first, model_name, S):
     return out
 
 
+def extra_configs(dev, budget_s=60.0):
+    """BASELINE.json configs[3] and configs[4] as additional, driver-visible figures (N = 1; never part of `value`):
+    mmFormer + PASSION on one 4x128^3 crop per GPU (the per-GPU share of configs[3]'s 8-GPU job) and the 15-mask sliding-window
+    inference sweep over a 240x240x155 volume.  Each is bounded to a few seconds; failures are reported, not raised."""
+    import numpy as np
+    import torch
+    from passion_b200 import ops
+    from passion_b200.engine import Trainer
+    from passion_b200.models import build_model
+    from passion_b200.predict import _windows, predict_all_masks
+    out = {}
+    t_start = time.time()
+    try:
+        torch.manual_seed(1037)
+        model = build_model("mmformer", num_cls=4, crop=128).to(dev)
+        model.compute_dtype = torch.bfloat16
+        tr = Trainer(model, lr=2e-4, weight_decay=1e-4, temp=4.0, mask_type="idt", use_passion=True, modal_weight=modal_weight(), use_graph=True)
+        batch = tuple(t.to(dev) for t in synth_host_batches(0, 1, 1, 128)[0])
+        for _ in range(3):
+            tr.step(*batch)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 5
+        e0.record()
+        for _ in range(n):
+            tr.step(*batch)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out["mmformer_128"] = {"workload": "mmFormer+PASSION train step, B=1/GPU, 4x128^3 crop (configs[3], per-GPU share), bf16, CUDA graph",
+                               "ms_per_step": round(ms, 2), "samples_per_s": round(1e3 / ms, 2), "steps": n}
+        del tr, model, batch
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["mmformer_128"] = {"error": repr(exc)[:300]}
+    try:
+        if time.time() - t_start < budget_s:
+            torch.manual_seed(1037)
+            model = build_model("rfnet", num_cls=4).to(dev)
+            model.compute_dtype = torch.bfloat16
+            rs = np.random.RandomState(7)
+            shape = (240, 240, 155)
+            x = torch.from_numpy(rs.standard_normal((1, 4) + shape).astype(np.float32)).to(dev)
+            predict_all_masks(model, x, patch_size=128)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 2
+            e0.record()
+            for _ in range(reps):
+                predict_all_masks(model, x, patch_size=128)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out["inference_15_masks"] = {"workload": "15 missing-modality subsets, sliding window 128^3 (50 % overlap) over 240x240x155 (configs[4]), "
+                                                     "RFNet bf16, encoders once per window + one batch-15 decoder pass",
+                                         "windows_per_volume": len(_windows(shape, 128)), "ms_per_volume": round(ms, 1),
+                                         "volumes_per_s": round(1e3 / ms, 3), "reps": reps}
+            ops.check_tc_errors()
+    except Exception as exc:
+        out["inference_15_masks"] = {"error": repr(exc)[:300]}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the step on the host cores — the unmodified reference
     model + criterions from baseline/_ref (staged by __graft_entry__.build(); /root/reference itself does not exist on the GPU
@@ -539,6 +606,7 @@ def main():
     ap.add_argument("--model", default="rfnet", choices=["rfnet", "mmformer"],
                     help="backbone; the headline metric (BASELINE.json configs[1]) is rfnet")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the additional configs[3] / configs[4] figures (N = 1)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -44,25 +44,11 @@ def up_probs(p, scale):
 
 
 # ------------------------------------------------------------------ channels-last helpers used by the model
-_label_memo = {}
-
-
 def label_stats(target, num_cls=4):
     """target -> (labels uint8 [B,D,H,W], class voxel counts [B,C] fp32, CE class weights 1 - count/total [B,C]
     (criterions.py:67)).  `target` is the reference's one-hot [B,C,D,H,W] (float64, datasets_nii.py:150-153) or — the
     compact form passion_b200.data.DeviceAugment produces — the uint8 label map [B,D,H,W] itself (33x fewer bytes).
-    The result for the most recent target OBJECT is kept (identity + version counter): Model.forward and the
-    step's fused-prediction CE / Dice (train.py:228-229) derive it from the same tensor three times per step."""
-    import weakref
-    ref = _label_memo.get("ref")
-    if ref is not None and ref() is target and _label_memo["k"] == (target._version, num_cls):
-        return _label_memo["v"]
-    out = _label_stats(target, num_cls)
-    _label_memo["ref"], _label_memo["k"], _label_memo["v"] = weakref.ref(target), (target._version, num_cls), out
-    return out
-
-
-def _label_stats(target, num_cls=4):
+    (Deliberately NOT memoised: a cached result would be baked into a CUDA-graph capture and go stale on replay.)"""
     if target.dtype == torch.uint8 and target.dim() == 4:
         labels = target.contiguous()
         cls = torch.arange(num_cls, device=target.device, dtype=torch.uint8).view(1, num_cls, 1)
