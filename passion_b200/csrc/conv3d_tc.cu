@@ -19,8 +19,7 @@
 //     overlap the epilogue of plane d with the MMAs of plane d+1.
 #include <cstdlib>
 #include <cstring>
-#include <cuda.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -33,8 +32,6 @@ constexpr int kMaxCopiesWide = 20;      // ... and for the 64-channel variants (
 __host__ __device__ constexpr int max_copies(int nchr) { return nchr >= 8 ? kMaxCopiesWide : kMaxCopies; }
 constexpr int kWgCopies = 5;            // weight-gradient kernels: slab rows per producer thread (planes up to W = 174)
 constexpr int kTileM = 128;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p);
 
 struct TcP {
     int N, D, H, W, C0, C1, CO0, CO1;   // inputs x0|x1 (concat), outputs y0|y1 (split)
@@ -51,63 +48,6 @@ struct TcP {
     int q_stride;                       // positions a tile advances by (128, or 126 for the kw-stacked kernel)
 };
 
-// 5-D tiled tensor map of a dense NDHWC bf16 volume for those boxes: dims (8 ch of a chunk, W, H, chunks, N*D planes)
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must never hang the GPU.  On timeout (~2 s) an error code is published and every
-// later wait returns immediately, so the kernel drains (with garbage results) and the host reports the failure.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0) {
-            if (*err != 0) return;
-            if (clock64() - t0 > 4000000000LL) { atomicCAS((int*)err, 0, code); return; }
-        }
-    }
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// arrive on `bar` once all cp.async copies issued so far by this thread have landed (counts as one expected arrival)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // TMA producer of conv3_tc_kernel / conv3_tc_kws_kernel (one thread): streams the input planes of this CTA's work items into the
 // slot ring, one box [tma_rows padded rows][PW][8 ch] per plane and 8-channel chunk (chunks of the second source of a two-source
@@ -144,44 +84,6 @@ __device__ __forceinline__ void tma_producer(const TcP& p, const CUtensorMap* ma
     }
 }
 
-// UMMA shared-memory descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 | [46,48) version
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ULL << 46);
-}
-// instruction descriptor for kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// zero 16 consecutive TMEM columns of this warp's 32 lanes
-__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
-        ::"r"(taddr), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // The three kd taps are stacked along N: the MMAs of INPUT plane pl (9 x K-steps of them, N = 3 NT) add its contribution
 // to the three output planes pl-2, pl-1, pl at once, whose accumulators are adjacent blocks of a ring of TMEM column blocks.
@@ -493,15 +395,6 @@ int launch_tc(const CUtensorMap& tmap, const CUtensorMap& tmap1, const TcP& p, c
 // Ring block of one output plane = 48 columns [kw][16 co]; weight image [3 kh][chunk][rows: kd = 2,1,0 | kw | co][8].
 constexpr int kKwsStride = 126;
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int NCHR, int CR>       // CR = real output channels of the tile / 8 (1 or 2)
 __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, TcP p,
@@ -1468,23 +1361,6 @@ namespace {
 int tc_tma_mode() {          // 0: cp.async producers everywhere, 1 (default): TMA for the zero-padded launches
     static const int mode = [] { const char* e = getenv("PB_TC_TMA"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
     return mode;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda: the library must still
-// load on a machine without a driver, where only the symbol check runs)
-EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            return (EncodeTiledFn) nullptr;
-        return (EncodeTiledFn)ptr;
-    }();
-    return fn;
 }
 
 // dense NDHWC bf16 volume [planes][H][W][C] seen as (8 ch of a chunk, W, H, C/8 chunks, planes); box = [rows][PW][8 ch] of one chunk
