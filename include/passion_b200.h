@@ -107,6 +107,13 @@ int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy, const flo
  *                       straight into y0|y1 [n,di,hi,wi,co0|co1]; all others into yext [n,di+2,hi+2,wi+2,co0+co1].
  *   pb_reflect_fold   : y0|y1[v] = sum of the yext voxels that the reflect padding maps onto v, for the remaining voxels
  *                       (per axis: {i+1} U {0 if i == 1} U {size+1 if i == size-2}).  bf16, sizes >= 4. */
+/* 1x1x1 conv (and, on dy with the transposed image, its data gradient) as a TMA-fed tcgen05 GEMM (csrc/conv1_tc.cu): bf16, channels
+ * multiples of 8 (cout also 2 or 4), voxels per sample >= 128.  `wimg` = [groups][cout tiles][cin/8 rounded up to even][NT][8] bf16
+ * with NT = pb_conv1_tc_ntile(cin, cout) (0 = class not covered; pb_weight_prep writes the image for ksize = 1 when nt is set).
+ * Output split y0 (co0 channels) | y1 (co1 channels) as in pb_conv3d_tc; optional bias and InstanceNorm sums. */
+int pb_conv1_tc_ntile(int cin, int cout);
+int pb_conv1_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
+                int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
 int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, void* y0, void* y1, int co0, int co1,
                       void* yext, int* err_flag, pb_stream_t stream);
 int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int d, int h, int w, int co0, int co1, pb_stream_t stream);

@@ -80,6 +80,8 @@ def load():
         "pb_conv3d_wgrad": [cd, vp, vp, vp, vp, vp],
         "pb_conv3d_tc_ntile": [i32, i32],
         "pb_conv3d_tc_kws": [i32, i32],
+        "pb_conv1_tc_ntile": [i32, i32],
+        "pb_conv1_tc": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_tc": [cd, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_conv3d_tc_full": [cd, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_reflect_fold": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],

@@ -59,6 +59,16 @@ __device__ __forceinline__ void prep_element(const PrepK& k, const long long t) 
         i -= k.n_wt;
         if (i < k.n_img) {                                  // [g][tile][9 (kh,kw)][chunk][3 nt rows: kd = 2,1,0][8]
             const long long o = i;
+            if (k.taps == 1) {                              // 1x1x1 (csrc/conv1_tc.cu): [g][tile][chunk][nt rows][8]
+                const int e = (int)(i % 8); i /= 8;
+                const int row = (int)(i % k.nt); i /= k.nt;
+                const int chunk = (int)(i % k.nch); i /= k.nch;
+                const int tile = (int)(i % k.tiles);
+                const int g = (int)(i / k.tiles);
+                const int ci = chunk * 8 + e, co = tile * k.nt + row;
+                k.img[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, 0) : 0.f);
+                return;
+            }
             const int rows = k.kws ? 9 * k.nt : 3 * k.nt, planes = k.kws ? 3 : 9;
             const int e = (int)(i % 8); i /= 8;
             const int row = (int)(i % rows); i /= rows;
@@ -75,6 +85,16 @@ __device__ __forceinline__ void prep_element(const PrepK& k, const long long t) 
         i -= k.n_img;
         if (i < k.n_imgT) {                                 // roles of Cin / Cout swapped, taps mirrored
             const long long o = i;
+            if (k.taps == 1) {
+                const int e = (int)(i % 8); i /= 8;
+                const int row = (int)(i % k.ntT); i /= k.ntT;
+                const int chunk = (int)(i % k.nchT); i /= k.nchT;
+                const int tile = (int)(i % k.tilesT);
+                const int g = (int)(i / k.tilesT);
+                const int co = chunk * 8 + e, ci = tile * k.ntT + row;
+                k.imgT[o] = __float2bfloat16_rn((ci < k.cin && co < k.cout) ? ref_w(k, g, co, ci, 0) : 0.f);
+                return;
+            }
             const int rows = k.kwsT ? 9 * k.ntT : 3 * k.ntT, planes = k.kwsT ? 3 : 9;
             const int e = (int)(i % 8); i /= 8;
             const int row = (int)(i % rows); i /= rows;
@@ -257,20 +277,32 @@ int make_prep(const pb_weight_prep_desc* d, PrepK& k, long long& total) {
     k.n_wk = k.wk ? nw : 0;
     k.n_wt = k.wt ? nw : 0;
     k.nch = k.tiles = k.nchT = k.tilesT = 1;
-    k.kws = k.img ? pb_conv3d_tc_kws(k.cin, k.cout) : 0;
-    k.kwsT = k.imgT ? pb_conv3d_tc_kws(k.cout, k.cin) : 0;
+    k.kws = (k.img && k.taps == 27) ? pb_conv3d_tc_kws(k.cin, k.cout) : 0;
+    k.kwsT = (k.imgT && k.taps == 27) ? pb_conv3d_tc_kws(k.cout, k.cin) : 0;
     k.n_img = k.n_imgT = 0;
     if (k.img) {
-        PB_CHECK_ARG(k.taps == 27 && k.nt > 0 && k.cin % 8 == 0, "forward image needs a 3x3x3 conv, cin % 8 == 0");
-        k.nch = k.cin / 8 < 2 ? 2 : k.cin / 8;
-        k.tiles = (k.cout + k.nt - 1) / k.nt;
-        k.n_img = (long long)k.G * k.tiles * 27 * k.nch * k.nt * 8;
+        PB_CHECK_ARG(k.nt > 0 && (k.taps == 27 ? k.cin % 8 == 0 : k.cin % 8 == 0), "weight image: nt > 0, cin % 8 == 0");
+        if (k.taps == 27) {
+            k.nch = k.cin / 8 < 2 ? 2 : k.cin / 8;
+            k.tiles = (k.cout + k.nt - 1) / k.nt;
+            k.n_img = (long long)k.G * k.tiles * 27 * k.nch * k.nt * 8;
+        } else {                                            // 1x1x1: chunk planes rounded up to even (K = 16 per MMA)
+            k.nch = (k.cin / 8 + 1) & ~1;
+            k.tiles = (k.cout + k.nt - 1) / k.nt;
+            k.n_img = (long long)k.G * k.tiles * k.nch * k.nt * 8;
+        }
     }
     if (k.imgT) {
-        PB_CHECK_ARG(k.taps == 27 && k.ntT > 0 && k.cout % 8 == 0, "data-gradient image needs a 3x3x3 conv, cout % 8 == 0");
-        k.nchT = k.cout / 8 < 2 ? 2 : k.cout / 8;
-        k.tilesT = (k.cin + k.ntT - 1) / k.ntT;
-        k.n_imgT = (long long)k.G * k.tilesT * 27 * k.nchT * k.ntT * 8;
+        PB_CHECK_ARG(k.ntT > 0 && k.cout % 8 == 0, "data-gradient weight image: ntT > 0, cout % 8 == 0");
+        if (k.taps == 27) {
+            k.nchT = k.cout / 8 < 2 ? 2 : k.cout / 8;
+            k.tilesT = (k.cin + k.ntT - 1) / k.ntT;
+            k.n_imgT = (long long)k.G * k.tilesT * 27 * k.nchT * k.ntT * 8;
+        } else {
+            k.nchT = (k.cout / 8 + 1) & ~1;
+            k.tilesT = (k.cin + k.ntT - 1) / k.ntT;
+            k.n_imgT = (long long)k.G * k.tilesT * k.nchT * k.ntT * 8;
+        }
     }
     k.n_bias = k.bias ? (long long)k.G * k.cout : 0;
     total = k.n_wk + k.n_wt + k.n_img + k.n_imgT + k.n_bias;

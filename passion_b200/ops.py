@@ -189,6 +189,26 @@ def _tc_eligible(dtype, ksize, stride, c0, c1, cout):
             and cout % 8 == 0 and _tc_ntile(c0 + c1, cout) != 0)
 
 
+def _tc1_ntile(cin, cout):
+    return int(_lib.load().pb_conv1_tc_ntile(cin, cout))
+
+
+def _tc1_eligible(dtype, ksize, stride, c0, c1, cout, voxels):
+    """1x1x1 conv on the TMA-fed tcgen05 GEMM (csrc/conv1_tc.cu)."""
+    return (TC_ENABLED and dtype == torch.bfloat16 and ksize == 1 and stride == 1 and c0 % 8 == 0 and c1 % 8 == 0 and c0 >= 8
+            and voxels >= 128 and _tc1_ntile(c0 + c1, cout) != 0)
+
+
+def tc1_weight_image(w, nt):
+    """fp32 [G, 1, cin, cout] -> bf16 image [G, cout tiles, cin/8 rounded up to even, nt, 8] (zero padded)."""
+    G, _, cin, cout = w.shape
+    nch = (cin // 8 + 1) & ~1
+    tiles = (cout + nt - 1) // nt
+    img = torch.zeros((G, nch * 8, tiles * nt), dtype=torch.float32, device=w.device)
+    img[:, :cin, :cout] = w[:, 0]
+    return img.view(G, nch, 8, tiles, nt).permute(0, 3, 1, 4, 2).to(torch.bfloat16).contiguous()
+
+
 def tc_weight_image(w, nt):
     """fp32 [G, 27, cin, cout] -> bf16 image [G, cout tiles, 9, max(2, cin/8), 3 nt, 8] (zero padded); for the classes of
     the kw-stacked kernel (pb_conv3d_tc_kws) [G, cout tiles, 3 (kh), max(2, cin/8), 9 nt (kd = 2,1,0 | kw | co), 8]."""
@@ -245,6 +265,13 @@ def _dgrad_tc_ok(d, dtype, ksize, stride, pad_mode):
             and (pad_mode != "reflect" or min(d.di, d.hi, d.wi) >= 4))
 
 
+def _dgrad_tc1_ok(d, dtype, ksize, stride):
+    """data gradient of a 1x1x1 conv on the tcgen05 GEMM: dy has cout channels (multiple of 8), dx = c0 | c1 channels"""
+    cin = d.c0 + d.c1
+    return (TC_ENABLED and dtype == torch.bfloat16 and ksize == 1 and stride == 1 and d.cout % 8 == 0 and d.di * d.hi * d.wi >= 128
+            and (d.c1 == 0 or (d.c0 % 8 == 0 and d.c1 % 8 == 0)) and _tc1_ntile(d.cout, cin) != 0)
+
+
 def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, need_dw):
     """Data and weight gradient launches.  get_imgT() -> bf16 image of the flipped / transposed weights (None = class
     not on the tensor-core path), get_wt() -> fp32 [G][taps][cout][cin] for the FFMA kernels.
@@ -258,7 +285,15 @@ def _conv_bwd_launch(lib, d, x0, x1, dy, get_wt, get_imgT, pad_mode, need_dx, ne
         dx1 = torch.empty_like(x1) if x1 is not None else None
         done = False
         imgT = get_imgT()
-        if imgT is not None:
+        if imgT is not None and d.ksize == 1:
+            # data gradient of a 1x1x1 conv = the same tcgen05 GEMM on dy with the transposed weight image
+            err = _tc_err_flag(dy.device)
+            dd = ConvDesc(dtype=d.dtype, n=d.n, di=d.di, hi=d.hi, wi=d.wi, dout=d.di, ho=d.hi, wo=d.wi, c0=d.cout, c1=0, cout=cin,
+                          ksize=1, stride=1, pad_mode=PB_PAD_ZERO, groups=groups)
+            done = _run("conv1_dgrad_tc", key, nb, fl,
+                        lambda: lib.pb_conv1_tc(ctypes.byref(dd), _p(dy), None, _p(imgT), None, _p(dx0), _p(dx1), d.c0, d.c1, None,
+                                                _p(err), _stream()), allow_unsupported=True)
+        elif imgT is not None:
             # data gradient = the same implicit GEMM on dy with flipped taps / transposed channels
             err = _tc_err_flag(dy.device)
             if pad_mode == "reflect" and DGRAD_FOLD:
@@ -336,6 +371,11 @@ class _Conv3d(torch.autograd.Function):
         if _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout):
             err = _tc_err_flag(x0.device)
             tc_call = lambda: _tc_conv_call(lib, d, x0, x1, w, y, None, cout, 0, stats, err, bias)
+        elif _tc1_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout, d.di * d.hi * d.wi):
+            err = _tc_err_flag(x0.device)
+            img1 = tc1_weight_image(w, _tc1_ntile(d.c0 + d.c1, cout))
+            tc_call = lambda: lib.pb_conv1_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img1), _p(bias), _p(y), None, cout, 0, _p(stats),
+                                              _p(err), _stream())
         _conv_fwd_launch(lib, d, x0, x1, lambda: w, tc_call, bias, y, stats)
         ctx.save_for_backward(x0, x1, w)
         ctx.cfg = (ksize, stride, pad_mode, groups, bias is not None)
@@ -354,6 +394,8 @@ class _Conv3d(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
 
         def get_imgT():
+            if _dgrad_tc1_ok(d, dy.dtype, ksize, stride):
+                return tc1_weight_image(w.transpose(2, 3), _tc1_ntile(d.cout, d.c0 + d.c1))
             if not _dgrad_tc_ok(d, dy.dtype, ksize, stride, pad_mode):
                 return None
             return tc_weight_image(w.flip(1).transpose(2, 3), _tc_ntile(d.cout, d.c0 + d.c1))
@@ -469,8 +511,12 @@ def _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=False, want_wt=False, nt
         ent = None
         wk = torch.empty((G, taps, cin, cout), **f32) if want_wk else None
         wt = torch.empty((G, taps, cout, cin), **f32) if want_wt else None
-        img = torch.empty((G, (cout + nt - 1) // nt, 9, max(2, cin // 8), 3 * nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
-        imgT = torch.empty((G, (cin + ntT - 1) // ntT, 9, max(2, cout // 8), 3 * ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
+        if ksize == 1:                                               # csrc/conv1_tc.cu: [G][tiles][cin/8 rounded up to even][nt][8]
+            img = torch.empty((G, (cout + nt - 1) // nt, (cin // 8 + 1) & ~1, nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
+            imgT = torch.empty((G, (cin + ntT - 1) // ntT, (cout // 8 + 1) & ~1, ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
+        else:
+            img = torch.empty((G, (cout + nt - 1) // nt, 9, max(2, cin // 8), 3 * nt, 8), dtype=torch.bfloat16, device=dev) if nt else None
+            imgT = torch.empty((G, (cin + ntT - 1) // ntT, 9, max(2, cout // 8), 3 * ntT, 8), dtype=torch.bfloat16, device=dev) if ntT else None
         bias = torch.empty((G, cout), **f32) if want_bias else None
     desc = _lib.WeightPrepDesc(groups=G, cin=cin, cout=cout, ksize=ksize, wk=_p(wk), wt=_p(wt), img=_p(img), nt=nt,
                                imgT=_p(imgT), ntT=ntT, bias=_p(bias), w_cin_stride=slices * cin)
@@ -650,11 +696,14 @@ class _Conv3dRef(torch.autograd.Function):
         assert not slices or (nw == 1 and not has_bias), "sliced weights: one parameter, no bias"
         need_dx = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
         fwd_tc = _tc_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout)
-        dgrad_tc = need_dx and _dgrad_tc_ok(d, x0.dtype, ksize, stride, pad_mode)
-        want_wt = need_dx and (not dgrad_tc or (pad_mode == "reflect" and not DGRAD_FOLD))
-        wk, wt, img, imgT, bias = _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=not fwd_tc, want_wt=want_wt,
-                                               nt=_tc_ntile(cin, cout) if fwd_tc else 0,
-                                               ntT=_tc_ntile(cout, cin) if dgrad_tc else 0, want_bias=has_bias, slices=slices)
+        fwd_tc1 = _tc1_eligible(x0.dtype, ksize, stride, d.c0, d.c1, cout, d.di * d.hi * d.wi)
+        dgrad_tc1 = need_dx and _dgrad_tc1_ok(d, x0.dtype, ksize, stride)
+        dgrad_tc = need_dx and (dgrad_tc1 or _dgrad_tc_ok(d, x0.dtype, ksize, stride, pad_mode))
+        want_wt = need_dx and (not dgrad_tc or (pad_mode == "reflect" and not DGRAD_FOLD and not dgrad_tc1))
+        nt = _tc_ntile(cin, cout) if fwd_tc else (_tc1_ntile(cin, cout) if fwd_tc1 else 0)
+        ntT = (_tc1_ntile(cout, cin) if dgrad_tc1 else _tc_ntile(cout, cin)) if dgrad_tc else 0
+        wk, wt, img, imgT, bias = _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=not (fwd_tc or fwd_tc1), want_wt=want_wt,
+                                               nt=nt, ntT=ntT, want_bias=has_bias, slices=slices)
         y = torch.empty((d.n, d.dout, d.ho, d.wo, cout), dtype=x0.dtype, device=x0.device)
         stats = _scratch.zeros((d.n, cout, 2), torch.float64, x0.device) if want_stats else None
         tc_call = None
@@ -662,6 +711,10 @@ class _Conv3dRef(torch.autograd.Function):
             err = _tc_err_flag(x0.device)
             tc_call = lambda: lib.pb_conv3d_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y), None, cout, 0,
                                                _p(stats), _p(err), _stream())
+        elif fwd_tc1:
+            err = _tc_err_flag(x0.device)
+            tc_call = lambda: lib.pb_conv1_tc(ctypes.byref(d), _p(x0), _p(x1), _p(img), _p(bias), _p(y), None, cout, 0,
+                                              _p(stats), _p(err), _stream())
         _conv_fwd_launch(lib, d, x0, x1, lambda: wk if wk is not None else _weight_prep(lib, ws, bs, cin, cout, ksize, want_wk=True, slices=slices)[0],
                          tc_call, bias, y, stats)
         ctx.save_for_backward(x0, x1, *ws, *bs)

@@ -91,6 +91,16 @@ def main():
     torch.cuda.synchronize()
 
     r_g = float((g_ddp - g_ref).norm() / g_ref.norm())
+    if rank == 0 and r_g > 1e-4:                       # diagnosis: which parameters disagree
+        off, bad = 0, []
+        for name, p_ in ref.named_parameters():
+            k = p_.numel()
+            a, b = g_ddp[off:off + k], g_ref[off:off + k]
+            r = float((a - b).norm() / b.norm().clamp_min(1e-30))
+            if r > 1e-4 and float(b.norm()) > 1e-9:
+                bad.append((name, round(r, 4), round(float(a.norm()), 5), round(float(b.norm()), 5)))
+            off += k
+        print(f"  {len(bad)} parameters disagree; first: {bad[:10]}")
     r_l = abs(float(loss_sum) - float(total)) / abs(float(total))
     flips = [bool(((rp_c[c] > 0) != (rp_sum > 0)).any()) for c in range(world)]
     if rank == 0:
