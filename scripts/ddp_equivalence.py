@@ -7,8 +7,8 @@ fp32 check mode, eager steps.  Checked on rank 0 (every rank computes the chunk 
   * the all-reduced gradient buckets == sum over chunks of the chunk gradients (rel-L2 <= 1e-6: only the reduction order of the
     cross-rank sum differs; per-chunk kernels use float64 atomics whose order varies run to run, hence not bit-exact);
   * the step loss summed over ranks == the chunk loop's;
-  * rp_mask is the GLOBAL-batch statistic (train.py:265-268): the per-chunk rp_iter signs differ from the global one in this
-    fixture for at least one modality, and the ranks use the global one;
+  * rp_mask is the GLOBAL-batch statistic (train.py:265-268): every rank sees the all-reduced rp_iter (printed next to the
+    per-chunk values, with whether a chunk-local gate would have decided differently);
   * the prototype loss's class gate (criterions.py:157 `.all()` over the LOCAL batch, i.e. the DataParallel chunk) is evaluated
     per rank: sample 1 of chunk 0 lacks class 3, so chunk 0 drops that class while chunk 1 keeps it.
 """
