@@ -32,7 +32,8 @@ struct C1P {
     int nch;                            // chunk planes of the weight image: nchr rounded up to a multiple of 2 (K = 16 per MMA)
     int kblocks;                        // ring slots per tile = ceil(nch / kC1KB)
     int slots;                          // ring depth
-    int tiles_per_sample, nt_tiles;
+    int sub;                            // 128-voxel sub-tiles per ring slot ("super-tile"): amortises the per-slot barrier round trips
+    int tiles_per_sample, nt_tiles;     // super-tiles per sample
 };
 
 template <int NT>
@@ -44,7 +45,8 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv1_tc_kernel(const __grid_co
     const int w_bytes = p.nch * NT * 16;
     uint8_t* w_s = smem;
     const int kb_chunks = p.nch < kC1KB ? p.nch : kC1KB;
-    const int slot_bytes = kb_chunks * kC1Tile * 16;
+    const int sub_bytes = kb_chunks * kC1Tile * 16;      // one 128-voxel sub-tile: kb_chunks chunk planes
+    const int slot_bytes = p.sub * sub_bytes;
     uint8_t* a_s = smem + ((w_bytes + 127) & ~127);
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + (size_t)p.slots * slot_bytes);
     uint64_t* full = bars;                               // [slots]   TMA -> MMA
@@ -70,9 +72,9 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv1_tc_kernel(const __grid_co
     }
     if (p.nchr < p.nch) {                                // odd chunk count: the pad chunk plane of every slot stays zero
         const int pad_plane = (p.nchr % kC1KB);
-        for (int i = threadIdx.x; i < p.slots * kC1Tile; i += kC1Threads) {
-            const int s = i / kC1Tile, e = i % kC1Tile;
-            *reinterpret_cast<uint4*>(a_s + (size_t)s * slot_bytes + ((size_t)pad_plane * kC1Tile + e) * 16) = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < p.slots * p.sub * kC1Tile; i += kC1Threads) {
+            const int s = i / kC1Tile, e = i % kC1Tile;               // s = slot * sub + sub-tile
+            *reinterpret_cast<uint4*>(a_s + (size_t)s * sub_bytes + ((size_t)pad_plane * kC1Tile + e) * 16) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async();
     }
@@ -92,19 +94,20 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv1_tc_kernel(const __grid_co
             uint32_t k = 0;
             for (long long t = t_begin; t < t_end; ++t) {
                 const int n = g * p.npg + (int)(t / p.tiles_per_sample);
-                const int v0 = (int)(t % p.tiles_per_sample) * kC1Tile;
+                const int v0 = (int)(t % p.tiles_per_sample) * kC1Tile * p.sub;
                 for (int kb = 0; kb < p.kblocks; ++kb, ++k) {
                     const int slot = k % p.slots;
                     mbar_wait(&empty[slot], ((k / p.slots) & 1) ^ 1, err, 11);
                     const int ch0 = kb * kC1KB;
                     const int nreal = min(kC1KB, p.nchr - ch0);
-                    mbar_expect_tx(&full[slot], (uint32_t)nreal * kC1Tile * 16u);
+                    mbar_expect_tx(&full[slot], (uint32_t)(p.sub * nreal) * kC1Tile * 16u);
                     const uint32_t sbase = smem_u32(a_s + (size_t)slot * slot_bytes);
-                    for (int c = 0; c < nreal; ++c) {
-                        const int ch = ch0 + c;
-                        tma_load_4d(sbase + (uint32_t)c * kC1Tile * 16u, ch < c0ch ? &map0 : &map1, 0, v0, ch < c0ch ? ch : ch - c0ch, n,
-                                    &full[slot]);
-                    }
+                    for (int sb = 0; sb < p.sub; ++sb)
+                        for (int c = 0; c < nreal; ++c) {
+                            const int ch = ch0 + c;
+                            tma_load_4d(sbase + (uint32_t)(sb * sub_bytes) + (uint32_t)c * kC1Tile * 16u, ch < c0ch ? &map0 : &map1, 0,
+                                        v0 + sb * kC1Tile, ch < c0ch ? ch : ch - c0ch, n, &full[slot]);
+                        }
                 }
             }
         }
@@ -119,24 +122,46 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv1_tc_kernel(const __grid_co
             }
             mbar_wait(wbar, 0, err, 12);
             const uint32_t a_addr = smem_u32(a_s), w_addr = smem_u32(w_s);
-            uint32_t k = 0, j = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++j) {
-                const uint32_t stage = j % STAGES;
-                mbar_wait(&tempty[stage], ((j / STAGES) & 1) ^ 1, err, 13);
-                for (int kb = 0; kb < p.kblocks; ++kb, ++k) {
+            uint32_t k = 0, j = 0;                                     // ring-slot / accumulator-stage counters
+            for (long long t = t_begin; t < t_end; ++t) {
+                if (p.sub == 1) {
+                    const uint32_t stage = j % STAGES;
+                    mbar_wait(&tempty[stage], ((j / STAGES) & 1) ^ 1, err, 13);
+                    for (int kb = 0; kb < p.kblocks; ++kb, ++k) {
+                        const int slot = k % p.slots;
+                        mbar_wait(&full[slot], (k / p.slots) & 1, err, 14);
+                        tc_fence_after();
+                        const int ch0 = kb * kC1KB;
+                        const int steps = (min(kC1KB, p.nch - ch0)) / 2;           // K = 16 channels per instruction
+                        for (int ks = 0; ks < steps; ++ks) {
+                            const uint64_t ad = umma_desc(a_addr + slot * slot_bytes + (uint32_t)(2 * ks) * kC1Tile * 16u, kC1Tile * 16u, 128);
+                            const uint64_t bd = umma_desc(w_addr + (uint32_t)(ch0 + 2 * ks) * NT * 16u, NT * 16u, 128);
+                            umma_f16(tmem_base + stage * NT, ad, bd, umma_idesc(kC1Tile, NT), (kb > 0 || ks > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&empty[slot]);
+                    }
+                    umma_commit(&tfull[stage]);
+                    ++j;
+                } else {                                               // one slot = p.sub sub-tiles, one K block (cin <= 128)
                     const int slot = k % p.slots;
                     mbar_wait(&full[slot], (k / p.slots) & 1, err, 14);
                     tc_fence_after();
-                    const int ch0 = kb * kC1KB;
-                    const int steps = (min(kC1KB, p.nch - ch0)) / 2;               // K = 16 channels per instruction
-                    for (int ks = 0; ks < steps; ++ks) {
-                        const uint64_t ad = umma_desc(a_addr + slot * slot_bytes + (uint32_t)(2 * ks) * kC1Tile * 16u, kC1Tile * 16u, 128);
-                        const uint64_t bd = umma_desc(w_addr + (uint32_t)(ch0 + 2 * ks) * NT * 16u, NT * 16u, 128);
-                        umma_f16(tmem_base + stage * NT, ad, bd, umma_idesc(kC1Tile, NT), (kb > 0 || ks > 0) ? 1u : 0u);
+                    const int steps = p.nch / 2;
+                    for (int sb = 0; sb < p.sub; ++sb, ++j) {
+                        const uint32_t stage = j % STAGES;
+                        mbar_wait(&tempty[stage], ((j / STAGES) & 1) ^ 1, err, 13);
+                        tc_fence_after();
+                        for (int ks = 0; ks < steps; ++ks) {
+                            const uint64_t ad = umma_desc(a_addr + slot * slot_bytes + sb * sub_bytes + (uint32_t)(2 * ks) * kC1Tile * 16u,
+                                                          kC1Tile * 16u, 128);
+                            const uint64_t bd = umma_desc(w_addr + (uint32_t)(2 * ks) * NT * 16u, NT * 16u, 128);
+                            umma_f16(tmem_base + stage * NT, ad, bd, umma_idesc(kC1Tile, NT), ks > 0 ? 1u : 0u);
+                        }
+                        umma_commit(&tfull[stage]);
                     }
                     umma_commit(&empty[slot]);
+                    ++k;
                 }
-                umma_commit(&tfull[stage]);
             }
         }
         __syncwarp();
@@ -162,42 +187,44 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv1_tc_kernel(const __grid_co
             }
         };
         uint32_t j = 0;
-        for (long long t = t_begin; t < t_end; ++t, ++j) {
+        for (long long t = t_begin; t < t_end; ++t) {
             const int n = g * p.npg + (int)(t / p.tiles_per_sample);
-            const long long v = (long long)(t % p.tiles_per_sample) * kC1Tile + warp * 32 + lane;
             if (n != cur_n) { flush(cur_n); cur_n = n; }
-            const uint32_t stage = j % STAGES;
-            mbar_wait(&tfull[stage], (j / STAGES) & 1, err, 15);
-            tc_fence_after();
-            float acc[NT];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * NT;
+            for (int sb = 0; sb < p.sub; ++sb, ++j) {
+                const long long v = ((long long)(t % p.tiles_per_sample) * p.sub + sb) * kC1Tile + warp * 32 + lane;
+                const uint32_t stage = j % STAGES;
+                mbar_wait(&tfull[stage], (j / STAGES) & 1, err, 15);
+                tc_fence_after();
+                float acc[NT];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * NT;
 #pragma unroll
-            for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, acc + c);
-            tc_fence_before();
-            mbar_arrive(&tempty[stage]);
-            if (bias != nullptr) {
+                for (int c = 0; c < NT; c += 16) tmem_ld16(taddr + c, acc + c);
+                tc_fence_before();
+                mbar_arrive(&tempty[stage]);
+                if (bias != nullptr) {
 #pragma unroll
-                for (int c = 0; c < NT; ++c)
-                    if (c < creal) acc[c] += __ldg(bias + (size_t)g * cout + cb0 + c);
-            }
-            if (v < p.V) {
-                const size_t vox = (size_t)n * p.V + v;
-                if (creal >= 8) {
-#pragma unroll
-                    for (int c8 = 0; c8 < NT / 8; ++c8) {
-                        if (c8 * 8 < creal) {
-                            const int cb = cb0 + c8 * 8;
-                            bf16* dst = cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0);
-                            VecIO<bf16, 8>::store(dst, acc + c8 * 8);
-                        }
-                    }
-                } else if (creal == 4) {
-                    VecIO<bf16, 4>::store(y0 + vox * 4, acc);
-                } else {
-                    VecIO<bf16, 2>::store(y0 + vox * 2, acc);
+                    for (int c = 0; c < NT; ++c)
+                        if (c < creal) acc[c] += __ldg(bias + (size_t)g * cout + cb0 + c);
                 }
+                if (v < p.V) {
+                    const size_t vox = (size_t)n * p.V + v;
+                    if (creal >= 8) {
 #pragma unroll
-                for (int c = 0; c < NT; ++c) { s1[c] += acc[c]; s2[c] += acc[c] * acc[c]; }
+                        for (int c8 = 0; c8 < NT / 8; ++c8) {
+                            if (c8 * 8 < creal) {
+                                const int cb = cb0 + c8 * 8;
+                                bf16* dst = cb < p.CO0 ? y0 + vox * p.CO0 + cb : y1 + vox * p.CO1 + (cb - p.CO0);
+                                VecIO<bf16, 8>::store(dst, acc + c8 * 8);
+                            }
+                        }
+                    } else if (creal == 4) {
+                        VecIO<bf16, 4>::store(y0 + vox * 4, acc);
+                    } else {
+                        VecIO<bf16, 2>::store(y0 + vox * 2, acc);
+                    }
+#pragma unroll
+                    for (int c = 0; c < NT; ++c) { s1[c] += acc[c]; s2[c] += acc[c] * acc[c]; }
+                }
             }
         }
         flush(cur_n);
@@ -228,7 +255,16 @@ int launch_c1(const CUtensorMap& m0, const CUtensorMap& m1, C1P p, const void* w
               int* err, cudaStream_t st) {
     const size_t w_bytes = (size_t)p.nch * NT * 16;
     const int kb_chunks = p.nch < kC1KB ? p.nch : kC1KB;
-    const size_t slot_bytes = (size_t)kb_chunks * kC1Tile * 16;
+    // sub-tiles per slot: up to half of the accumulator stages, slot <= 16 KB, only for single-K-block classes
+    int sub = 1;
+    if (p.kblocks == 1) {
+        sub = (kC1TmemCols / NT) / 2;
+        while (sub > 1 && (size_t)sub * kb_chunks * kC1Tile * 16 > 16384) sub /= 2;
+        while (sub > 1 && (long long)kC1Tile * sub > p.V) sub /= 2;
+    }
+    p.sub = sub;
+    p.tiles_per_sample = (int)((p.V + (long long)kC1Tile * sub - 1) / ((long long)kC1Tile * sub));
+    const size_t slot_bytes = (size_t)sub * kb_chunks * kC1Tile * 16;
     const size_t fixed = ((w_bytes + 127) & ~(size_t)127) + (2 * kC1MaxSlots + 2 * (kC1TmemCols / NT) + 1) * 8 + 16;
     // ring depth: as many slots as fit next to a second CTA on the SM (113 KB each), at most 8, at least 2 tiles' worth
     int slots = (int)((113 * 1024 - fixed) / slot_bytes);

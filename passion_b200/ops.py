@@ -248,7 +248,7 @@ def _conv_fwd_launch(lib, d, x0, x1, get_wk, tc_call, bias, y, stats):
     key, nb, fl = _conv_work(d, x0.element_size())
     done = False
     if tc_call is not None:
-        done = _run("conv3d_fwd_tc", key, nb, fl, tc_call, allow_unsupported=True)
+        done = _run("conv1_fwd_tc" if d.ksize == 1 else "conv3d_fwd_tc", key, nb, fl, tc_call, allow_unsupported=True)
     if not done and _small_ok(d):
         wk = get_wk()
         done = _run("conv3d_small_fwd", key, nb, fl,

@@ -59,6 +59,10 @@ CONV_CASES = [
     (128, 0, 128, 3, 1, "zeros", 1, 2, (5, 5, 5), True),
     (512, 0, 128, 1, 1, "zeros", 1, 2, (5, 5, 5), True),
     (32, 0, 8, 1, 1, "zeros", 1, 2, (6, 7, 8), True),
+    # 1x1x1 on the TMA-fed tcgen05 GEMM: two K blocks and two Cout tiles, weight groups, ragged last tile, several super-tiles
+    (256, 0, 64, 1, 1, "zeros", 1, 2, (6, 6, 6), True),
+    (16, 0, 16, 1, 1, "zeros", 4, 4, (8, 9, 10), False),
+    (8, 0, 8, 1, 1, "zeros", 1, 2, (20, 18, 22), False),
     # 128-wide planes (128^3 crops): producer budgets of the tcgen05 kernels
     (16, 0, 8, 3, 1, "reflect", 1, 1, (4, 6, 128), False),
     (8, 0, 8, 3, 1, "reflect", 1, 1, (3, 5, 128), True),
@@ -88,7 +92,8 @@ def test_conv3d(lib_built, case, dtype):
     # ---- float64 reference on the same (rounded) inputs
     xr = xq.double().requires_grad_(True)
     # the tcgen05 path multiplies bf16 weights (fp32 accumulate); give the reference the same rounded operands
-    uses_tc = ops._tc_eligible(dtype, k, stride, c0, c1, cout)
+    uses_tc = (ops._tc_eligible(dtype, k, stride, c0, c1, cout)
+               or ops._tc1_eligible(dtype, k, stride, c0, c1, cout, x.shape[2] * x.shape[3] * x.shape[4]))
     wr = (wt.to(torch.bfloat16) if uses_tc else wt).double().requires_grad_(True)
     ys = []
     npg = n // groups
