@@ -285,11 +285,6 @@ int launch_c1(const CUtensorMap& m0, const CUtensorMap& m1, C1P p, const void* w
     return 0;
 }
 
-bool c1_enabled() {
-    static const bool on = [] { const char* e = getenv("PB_C1_TC"); return !(e != nullptr && e[0] == '0'); }();
-    return on;
-}
-
 }  // namespace
 
 // Cout tile of the 1x1x1 tensor-core kernel for (cin, cout) — 16 or 32 (wider outputs run as several tiles, blockIdx.z: the
@@ -297,8 +292,14 @@ bool c1_enabled() {
 // multiple of 8 up to 128.  The weight image pb_weight_prep writes for ksize = 1 is
 // [groups][cout tiles][chunk planes = cin/8 rounded up to even][NT rows][8 ch] bf16, zero padded.
 extern "C" int pb_conv1_tc_ntile(int cin, int cout) {
-    if (!c1_enabled() || cin % 8 || cin < 8 || cin > 512) return 0;
+    static const int mode = [] { const char* e = getenv("PB_C1_TC"); return e != nullptr && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1; }();
+    if (mode == 0 || cin % 8 || cin < 8 || cin > 512) return 0;
     if (cout != 2 && cout != 4 && (cout % 8 || cout < 8 || cout > 128)) return 0;
+    // Routed by measurement (profiles/r02_conv1_tc.txt): the GEMM wins where a voxel carries enough work per 128-row MMA tile —
+    // wide inputs (cin >= 128: the coarse levels, where the FFMA kernel ran 40-120 us launches over a few MB) and the 16..32 ->
+    // 16..32 classes; with fewer channels a tile is 2-4 KB and the per-tile TMEM / barrier round trips dominate, and
+    // pw_conv2_kernel (3.5-4 TB/s there) stays ahead.  PB_C1_TC=2 routes every covered class (A/B runs), =0 none.
+    if (mode == 1 && !(cin >= 128 || (cin >= 16 && cin <= 32 && cout >= 16))) return 0;
     return cout <= 16 ? 16 : 32;
 }
 
