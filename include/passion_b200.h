@@ -190,6 +190,9 @@ int pb_inorm_finalize(const double* stats, float* mr, int n, int c, long long vo
                       pb_stream_t stream);
 int pb_inorm_lrelu_fwd(int dtype, const void* y, const float* mr, const void* res, void* out,
                        int n, long long voxels, int c, float slope, pb_stream_t stream);
+/* finalize + forward apply in one launch (mr is an OUTPUT here: written for the backward pass) */
+int pb_inorm_lrelu_fwd_stats(int dtype, const void* y, const double* stats, float* mr, const void* res, void* out,
+                             int n, long long voxels, int c, float eps, float slope, pb_stream_t stream);
 int pb_inorm_lrelu_bwd(int dtype, const void* dout, const void* y, const float* mr, double* sums,
                        void* dy, int n, long long voxels, int c, float slope, pb_stream_t stream);
 
@@ -212,6 +215,14 @@ int pb_upsample_bwd_axis(int dtype, const void* in, void* out, long long outer, 
  *   mix_bwd_gate : dgate[n][i][k] = sum_{v,c} p_i * y[k*C+c] * dR[i*C+c]   (float64, zero-filled)
  *   bwd_y : dy[n][v][k*C+c] = sum_i p_i * (gate[n][i][k]*dR[n][v][i*C+c] + dS[n][i][k*C+c])
  */
+/* Gate MLP of modal_fusion (blocks.py:507-513) fused: pooled float64 sums of pb_rfm_pool -> gate [n][4][K] (K = 4: all modality
+ * slots; K = 1: single-modality samples, sample n = modality n / b, gate [n][4]) plus the hidden pre-activations z1 [n][4][128]
+ * for the backward pass.  w / dw: 16 device pointers = 4 classes x {w0 [128][4c+1], b0 [128], w2 [4][128], b2 [4]} in that
+ * order (w0 of all classes first).  pb_rfm_gate_bwd ACCUMULATES the parameter gradients into zero-filled dw buffers. */
+int pb_rfm_gate_fwd(const float* const* w, const double* S, const double* Psum, float* z1, float* gate, int n, int b,
+                    long long voxels, int k, int c, pb_stream_t stream);
+int pb_rfm_gate_bwd(const float* const* w, float* const* dw, const double* S, const double* Psum, const float* z1,
+                    const double* dgate, float* dS, int n, int b, long long voxels, int k, int c, pb_stream_t stream);
 /* MaskModal (rfnet.py:154-163, 239-242; mmformer.py:316-326) for `passes` decoder passes in one launch:
  *   out[p*b + i][v][m*c + ch] = enc[m*b + i][v][ch] * ms[p][i][m]     (enc: modality-major output of the grouped encoders)
  * and its adjoint denc[m*b + i][v][ch] = sum_p ms[p][i][m] * dout[p*b + i][v][m*c + ch]. */

@@ -99,6 +99,7 @@ def load():
         "pb_channel_stats": [i32, vp, vp, i32, i64, i32, vp],
         "pb_inorm_finalize": [vp, vp, i32, i32, i64, f32, vp],
         "pb_inorm_lrelu_fwd": [i32, vp, vp, vp, vp, i32, i64, i32, f32, vp],
+        "pb_inorm_lrelu_fwd_stats": [i32, vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, vp],
         "pb_inorm_lrelu_bwd": [i32, vp, vp, vp, vp, vp, i32, i64, i32, f32, vp],
         "pb_upsample_fwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "pb_upsample_bwd": [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
@@ -118,6 +119,8 @@ def load():
         "pb_masked_stack_fwd": [i32, vp, vp, vp, i32, i32, i64, i32, vp],
         "pb_masked_stack_bwd": [i32, vp, vp, vp, i32, i32, i64, i32, vp],
         "pb_rfm_pool": [i32, vp, vp, vp, vp, i32, i64, i32, vp],
+        "pb_rfm_gate_fwd": [vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, vp],
+        "pb_rfm_gate_bwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, vp],
         "pb_rfm_mix": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
         "pb_rfm_mix_bwd_gate": [i32, vp, vp, vp, vp, i32, i64, i32, i32, vp],
         "pb_rfm_bwd_y": [i32, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],

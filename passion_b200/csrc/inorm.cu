@@ -97,7 +97,8 @@ struct Walk {
 template <typename T, int VEC, bool RES>
 __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ mr,
                                                         const T* __restrict__ res, T* __restrict__ out,
-                                                        long long voxels, int c, float slope, int rev) {
+                                                        long long voxels, int c, float slope, int rev,
+                                                        const double* __restrict__ stats, float* __restrict__ mr_out, double inv_v, float eps) {
     constexpr int UNR = 4;
     const int lanes = c / VEC, tpb = (256 / lanes) * lanes, vpb = tpb / lanes;
     if ((int)threadIdx.x >= tpb) return;
@@ -105,9 +106,23 @@ __global__ void __launch_bounds__(256) apply_fwd_kernel(const T* __restrict__ y,
     const int c0 = cl * VEC;
     const Walk wk(voxels, vpb, vl, rev != 0);
     float mean[VEC], rstd[VEC];
+    if (stats != nullptr) {
+        // finalize fused in (same arithmetic as finalize_kernel): mean / rstd straight from the float64 sums of the producing
+        // kernel's epilogue; the first block of the sample also publishes them for the backward pass
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        mean[j] = mr[((size_t)wk.n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)wk.n * c + c0 + j) * 2 + 1];
+        for (int j = 0; j < VEC; ++j) {
+            const size_t i = (size_t)wk.n * c + c0 + j;
+            const double m = stats[2 * i] * inv_v;
+            double var = stats[2 * i + 1] * inv_v - m * m;
+            if (var < 0.0) var = 0.0;
+            mean[j] = (float)m; rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+            if (blockIdx.x == 0 && vl == 0) { mr_out[2 * i] = mean[j]; mr_out[2 * i + 1] = rstd[j]; }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            mean[j] = mr[((size_t)wk.n * c + c0 + j) * 2]; rstd[j] = mr[((size_t)wk.n * c + c0 + j) * 2 + 1];
+        }
     }
     const size_t base = (size_t)wk.n * voxels * c + c0;
     for (int it = 0; it < wk.K; it += UNR) {
@@ -308,7 +323,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 1) bwd_apply_kernel(
 }
 
 template <typename T, int VEC>
-int run_fwd(const void* y, const float* mr, const void* res, void* out, int n, long long voxels, int c, float slope, cudaStream_t st) {
+int run_fwd(const void* y, const float* mr, const void* res, void* out, int n, long long voxels, int c, float slope, cudaStream_t st,
+            const double* stats = nullptr, float* mr_out = nullptr, float eps = 0.f) {
     const int lanes = c / VEC, vpb = 256 / lanes;
     int bps = (int)((voxels + (long long)vpb * 8 - 1) / ((long long)vpb * 8));       // >= 8 voxels per thread
     const int cap = (148 * 8 + n - 1) / n;
@@ -316,10 +332,10 @@ int run_fwd(const void* y, const float* mr, const void* res, void* out, int n, l
     if (bps < 1) bps = 1;
     if (res)
         apply_fwd_kernel<T, VEC, true><<<dim3(bps, n), 256, 0, st>>>((const T*)y, mr, (const T*)res, (T*)out, voxels, c, slope,
-                                                                     inorm_order() & 1);
+                                                                     inorm_order() & 1, stats, mr_out, 1.0 / (double)voxels, eps);
     else
         apply_fwd_kernel<T, VEC, false><<<dim3(bps, n), 256, 0, st>>>((const T*)y, mr, nullptr, (T*)out, voxels, c, slope,
-                                                                      inorm_order() & 1);
+                                                                      inorm_order() & 1, stats, mr_out, 1.0 / (double)voxels, eps);
     return 0;
 }
 
@@ -407,6 +423,20 @@ extern "C" int pb_inorm_lrelu_fwd(int dtype, const void* y, const float* mr, con
 #define CALL_F(T, V) run_fwd<T, V>(y, mr, res, out, n, voxels, c, slope, st)
     if (dtype == PB_BF16) { VEC_SWITCH(bf16, c, CALL_F) } else { VEC_SWITCH(float, c, CALL_F) }
 #undef CALL_F
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+// pb_inorm_finalize + pb_inorm_lrelu_fwd in one launch: mean / rstd are computed from the float64 sums in the kernel prologue
+// and written to `mr` (for the backward pass) by the first block of each sample.
+extern "C" int pb_inorm_lrelu_fwd_stats(int dtype, const void* y, const double* stats, float* mr, const void* res, void* out, int n,
+                                        long long voxels, int c, float eps, float slope, pb_stream_t stream) {
+    PB_CHECK_ARG(y && stats && mr && out && n > 0 && c > 0 && voxels > 0 && voxels < (1LL << 31), "bad argument");
+    PB_CHECK_ARG(c <= 256 * pb_vec_width(c), "too many channels");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL_FS(T, V) run_fwd<T, V>(y, nullptr, res, out, n, voxels, c, slope, st, stats, mr, eps)
+    if (dtype == PB_BF16) { VEC_SWITCH(bf16, c, CALL_FS) } else { VEC_SWITCH(float, c, CALL_FS) }
+#undef CALL_FS
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

@@ -6,6 +6,7 @@
 //     feat_avg_i[k,c] = mean_v(y[k,c] p_i) / (mean_v p_i + 1e-7)        -> pb_rfm_pool (the two sums)
 //     region_i[c]     = p_i * sum_k gate_i[k] y[k,c]                     -> pb_rfm_mix
 // The 4C+1 -> 128 -> 4 gate MLP on the pooled vector is host-side glue on a [B, 4C+1] tensor.
+#include <cstring>
 #include "common.cuh"
 
 namespace {
@@ -168,6 +169,107 @@ __global__ void __launch_bounds__(256) bwd_y_kernel(const float* __restrict__ p,
     }
 }
 
+// ------------------------------------------------------------------------------------ gate MLP of modal_fusion, fused
+// Reference models/blocks.py:507-513 per class i: feat = [ mean_v(y p_i) / (mean_v p_i + 1e-7) (K*C values), mean_v p_i + 1e-7 ]
+//   -> Conv1x1(K*C+1 -> 128) -> LeakyReLU(0.2) -> Conv1x1(128 -> 4) -> sigmoid = gate_i[k].
+// One block per (sample, class): thread h owns hidden unit h.  For the single-modality passes (K = 1) the pooled vector has C
+// values, sitting in slot m = sample / b of the 4C-wide MLP input (zeros elsewhere), and only gate column m is used.
+// The host-side version of this was ~12 tiny tensor-op launches forward and ~40 backward per call (6 calls per step).
+struct GateW {
+    const float* w0[4]; const float* b0[4]; const float* w2[4]; const float* b2[4];     // per class: [128][4C+1], [128], [4][128], [4]
+    float* dw0[4]; float* db0[4]; float* dw2[4]; float* db2[4];                           // gradient accumulators (zero-filled), backward only
+};
+
+constexpr int kGateH = 128;
+
+__global__ void __launch_bounds__(kGateH) rfm_gate_fwd_kernel(GateW gw, const double* __restrict__ S, const double* __restrict__ Ps,
+                                                             float* __restrict__ z1buf, float* __restrict__ gate, int b, double inv_v,
+                                                             int K, int c) {
+    __shared__ float feat[4 * 64 + 1 + 3];
+    __shared__ float red[4][kGateH / 32];
+    const int n = blockIdx.x, i = blockIdx.y, h = threadIdx.x;
+    const int kc = K * c, F = 4 * c + 1;
+    const int slot0 = K == 4 ? 0 : (n / b) * c;                 // first MLP input column fed by S
+    const float pavg = (float)(Ps[(size_t)n * 4 + i] * inv_v) + 1e-7f;
+    for (int f = h; f < kc; f += kGateH) feat[f] = (float)(S[((size_t)n * 4 + i) * kc + f] * inv_v) / pavg;
+    __syncthreads();
+    const float* w = gw.w0[i] + (size_t)h * F;
+    float z = gw.b0[i][h] + w[F - 1] * pavg;
+    for (int f = 0; f < kc; ++f) z = fmaf(feat[f], w[slot0 + f], z);
+    z1buf[((size_t)n * 4 + i) * kGateH + h] = z;
+    const float a = z > 0.f ? z : 0.2f * z;
+    float part[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) part[k] = warp_sum(a * gw.w2[i][k * kGateH + h]);
+    if ((h & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[k][h >> 5] = part[k];
+    }
+    __syncthreads();
+    if (h < 4) {
+        const float zz = gw.b2[i][h] + red[h][0] + red[h][1] + red[h][2] + red[h][3];
+        const float g = 1.f / (1.f + expf(-zz));
+        if (K == 4) gate[((size_t)n * 4 + i) * 4 + h] = g;
+        else if (h == n / b) gate[(size_t)n * 4 + i] = g;
+    }
+}
+
+__global__ void __launch_bounds__(kGateH) rfm_gate_bwd_kernel(GateW gw, const double* __restrict__ S, const double* __restrict__ Ps,
+                                                             const float* __restrict__ z1buf, const double* __restrict__ dgate,
+                                                             float* __restrict__ dS, int b, double inv_v, int K, int c) {
+    __shared__ float feat[4 * 64 + 1 + 3];
+    __shared__ float dz1s[kGateH];
+    __shared__ float dz2[4];
+    __shared__ float red[4][kGateH / 32];
+    const int n = blockIdx.x, i = blockIdx.y, h = threadIdx.x;
+    const int kc = K * c, F = 4 * c + 1;
+    const int slot0 = K == 4 ? 0 : (n / b) * c;
+    const float pavg = (float)(Ps[(size_t)n * 4 + i] * inv_v) + 1e-7f;
+    for (int f = h; f < kc; f += kGateH) feat[f] = (float)(S[((size_t)n * 4 + i) * kc + f] * inv_v) / pavg;
+    const float z = z1buf[((size_t)n * 4 + i) * kGateH + h];
+    const float a = z > 0.f ? z : 0.2f * z;
+    // recompute the gate pre-activations (4 block reductions) to get sigmoid'
+    float part[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) part[k] = warp_sum(a * gw.w2[i][k * kGateH + h]);
+    if ((h & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[k][h >> 5] = part[k];
+    }
+    __syncthreads();
+    if (h < 4) {
+        const float zz = gw.b2[i][h] + red[h][0] + red[h][1] + red[h][2] + red[h][3];
+        const float g = 1.f / (1.f + expf(-zz));
+        float dg;
+        if (K == 4) dg = (float)dgate[((size_t)n * 4 + i) * 4 + h];
+        else dg = h == n / b ? (float)dgate[(size_t)n * 4 + i] : 0.f;
+        const float d = dg * g * (1.f - g);
+        dz2[h] = d;
+        if (d != 0.f) atomicAdd(gw.db2[i] + h, d);
+    }
+    __syncthreads();
+    float dh = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dh = fmaf(dz2[k], gw.w2[i][k * kGateH + h], dh);
+        if (dz2[k] != 0.f) atomicAdd(gw.dw2[i] + k * kGateH + h, dz2[k] * a);
+    }
+    const float dz1 = dh * (z > 0.f ? 1.f : 0.2f);
+    dz1s[h] = dz1;
+    atomicAdd(gw.db0[i] + h, dz1);
+    float* dw = gw.dw0[i] + (size_t)h * F;
+    atomicAdd(dw + F - 1, dz1 * pavg);
+    for (int f = 0; f < kc; ++f) atomicAdd(dw + slot0 + f, dz1 * feat[f]);
+    __syncthreads();
+    // d feat[f] = sum_h dz1[h] w0[h][slot0 + f]  ->  dS = d feat / (voxels * pavg)    (p, hence pavg, is detached)
+    for (int f = h; f < kc; f += kGateH) {
+        float acc = 0.f;
+        const float* w = gw.w0[i] + slot0 + f;
+        for (int hh = 0; hh < kGateH; ++hh) acc = fmaf(dz1s[hh], w[(size_t)hh * F], acc);
+        dS[((size_t)n * 4 + i) * kc + f] = acc * (float)inv_v / pavg;
+    }
+}
+
 int blocks_per_sample(long long work_items, int n) {
     long long b = (work_items + 256 * 4 - 1) / (256 * 4);
     const long long cap = (148LL * 8 + n - 1) / n;
@@ -248,6 +350,36 @@ extern "C" int pb_rfm_bwd_y(int dtype, const float* p, const float* gate, const 
     return PB_OK;
 }
 
+
+// Gate MLP of the four modal_fusion modules (blocks.py:495-513) on the pooled sums of pb_rfm_pool: S [n][4][K*c], Psum [n][4]
+// (float64) -> gate [n][4][K] and the hidden pre-activations z1 [n][4][128] (kept for the backward pass).  `w` = 16 parameter
+// pointers (4 classes x {w0 [128][4c+1], b0 [128], w2 [4][128], b2 [4]}).  K = 1: sample n holds modality n / b only.
+extern "C" int pb_rfm_gate_fwd(const float* const* w, const double* S, const double* Psum, float* z1, float* gate, int n, int b,
+                               long long voxels, int k, int c, pb_stream_t stream) {
+    PB_CHECK_ARG(w && S && Psum && z1 && gate && n > 0 && b > 0 && voxels > 0 && (k == 4 || k == 1) && c > 0 && c <= 64, "bad argument");
+    GateW gw;
+    memset(&gw, 0, sizeof(gw));
+    for (int i = 0; i < 4; ++i) { gw.w0[i] = w[i]; gw.b0[i] = w[4 + i]; gw.w2[i] = w[8 + i]; gw.b2[i] = w[12 + i]; }
+    rfm_gate_fwd_kernel<<<dim3(n, 4), kGateH, 0, (cudaStream_t)stream>>>(gw, S, Psum, z1, gate, b, 1.0 / (double)voxels, k, c);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+// Adjoint: dgate [n][4][K] (float64, from pb_rfm_mix_bwd_gate) -> dS [n][4][K*c] fp32 and the parameter gradients, ACCUMULATED
+// into the 16 zero-filled buffers `dw` (same order as `w`).
+extern "C" int pb_rfm_gate_bwd(const float* const* w, float* const* dw, const double* S, const double* Psum, const float* z1,
+                               const double* dgate, float* dS, int n, int b, long long voxels, int k, int c, pb_stream_t stream) {
+    PB_CHECK_ARG(w && dw && S && Psum && z1 && dgate && dS && n > 0 && b > 0 && voxels > 0 && (k == 4 || k == 1) && c > 0 && c <= 64,
+                 "bad argument");
+    GateW gw;
+    for (int i = 0; i < 4; ++i) {
+        gw.w0[i] = w[i]; gw.b0[i] = w[4 + i]; gw.w2[i] = w[8 + i]; gw.b2[i] = w[12 + i];
+        gw.dw0[i] = dw[i]; gw.db0[i] = dw[4 + i]; gw.dw2[i] = dw[8 + i]; gw.db2[i] = dw[12 + i];
+    }
+    rfm_gate_bwd_kernel<<<dim3(n, 4), kGateH, 0, (cudaStream_t)stream>>>(gw, S, Psum, z1, dgate, dS, b, 1.0 / (double)voxels, k, c);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
 
 // ------------------------------------------------------------------------------------ masked modality stacking
 // MaskModal of the reference (models/rfnet.py:154-163, 239-242; mmformer.py:316-326) for P decoder passes at once:

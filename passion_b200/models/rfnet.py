@@ -208,17 +208,15 @@ class region_aware_modal_fusion(nn.Module):
         """y [Nd,D,H,W,4C] masked features of the dense passes (channel = modality*C + c); prm [N,D,H,W,4] fp32 detached
         probs of ALL passes; enc [4B,D,H,W,C]: four further single-modality passes (see general_conv3d.run_stack)."""
         mf = self.modal_fusion
-        w0 = torch.stack([m.weight_layer[0].weight.flatten(1) for m in mf])     # [4,128,4C+1]
-        b0 = torch.stack([m.weight_layer[0].bias for m in mf])
-        w2 = torch.stack([m.weight_layer[2].weight.flatten(1) for m in mf])     # [4,4,128]
-        b2 = torch.stack([m.weight_layer[2].bias for m in mf])
+        gp = ([m.weight_layer[0].weight for m in mf] + [m.weight_layer[0].bias for m in mf]
+              + [m.weight_layer[2].weight for m in mf] + [m.weight_layer[2].bias for m in mf])      # the 16 gate-MLP parameters
         nd = y.shape[0]
         fl = self.region_fusion.fusion_layer
-        r = fl[0].run(ops.rfm_region(y, prm[:nd], w0, b0, w2, b2))
+        r = fl[0].run(ops.rfm_region(y, prm[:nd], gp))
         if enc is not None:
             # the class-weighted mix of a single-modality pass reads C channels instead of 4C; its [4B,...,4C] region tensor
             # goes through the same 1x1x1 conv (weights shared with the dense passes) and only then joins the batch
-            r = torch.cat((r, fl[0].run(ops.rfm_region_single(enc, prm[nd:].contiguous(), w0, b0, w2, b2))), 0)
+            r = torch.cat((r, fl[0].run(ops.rfm_region_single(enc, prm[nd:].contiguous(), gp, enc.shape[0] // 4))), 0)
         r = _run_seq(list(fl)[1:], r)
         s = _run_stack_seq(self.short_cut, y, enc)
         return torch.cat((r, s), -1)

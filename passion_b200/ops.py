@@ -789,8 +789,9 @@ def inorm_finalize(stats, voxels, eps=IN_EPS):
 
 
 class _InormLrelu(torch.autograd.Function):
-    """out = LeakyReLU(InstanceNorm(y)) (+ res).  `mr` = (mean, rstd) of y; backward is the full
-    InstanceNorm adjoint (the dependence of the statistics on y is accounted for)."""
+    """out = LeakyReLU(InstanceNorm(y)) (+ res).  `mr` = (mean, rstd) of y — or the float64 [N,C,2] sums of y, in which case
+    the finalisation runs inside the apply kernel (one launch instead of two); backward is the full InstanceNorm adjoint
+    (the dependence of the statistics on y is accounted for)."""
 
     @staticmethod
     def forward(ctx, y, mr, res):
@@ -800,8 +801,15 @@ class _InormLrelu(torch.autograd.Function):
         voxels = y.numel() // (n * c)
         out = torch.empty_like(y)
         nb = y.numel() * y.element_size() * (3 if res is not None else 2)
-        _run("inorm_lrelu_fwd", f"c{c}", nb, 0,
-             lambda: lib.pb_inorm_lrelu_fwd(_dt(y), _p(y), _p(mr), _p(res), _p(out), n, voxels, c, LRELU_SLOPE, _stream()))
+        if mr.dtype == torch.float64:
+            stats = mr
+            mr = torch.empty((n, c, 2), dtype=torch.float32, device=y.device)
+            _run("inorm_lrelu_fwd", f"c{c}", nb, 0,
+                 lambda: lib.pb_inorm_lrelu_fwd_stats(_dt(y), _p(y), _p(stats), _p(mr), _p(res), _p(out), n, voxels, c, IN_EPS,
+                                                      LRELU_SLOPE, _stream()))
+        else:
+            _run("inorm_lrelu_fwd", f"c{c}", nb, 0,
+                 lambda: lib.pb_inorm_lrelu_fwd(_dt(y), _p(y), _p(mr), _p(res), _p(out), n, voxels, c, LRELU_SLOPE, _stream()))
         ctx.save_for_backward(y, mr)
         ctx.has_res = res is not None
         return out
@@ -825,16 +833,13 @@ def conv_in_lrelu(x0, w, x1=None, ksize=3, stride=1, pad_mode="reflect", groups=
     """general_conv3d (reference models/blocks.py:354-370): conv -> InstanceNorm -> LeakyReLU(0.2) (+ res).
     The conv bias is dropped: InstanceNorm(affine=False) cancels it exactly."""
     y, stats = conv3d(x0, w, None, x1, ksize, stride, pad_mode, groups, True)
-    voxels = y.shape[1] * y.shape[2] * y.shape[3]
-    mr = inorm_finalize(stats, voxels)
-    return _InormLrelu.apply(y, mr, res)
+    return _InormLrelu.apply(y, stats, res)                 # float64 sums: finalised inside the apply kernel
 
 
 def conv_in_lrelu_ref(x0, weights, x1=None, ksize=3, stride=1, pad_mode="reflect", res=None, slices=0):
     """conv_in_lrelu on parameter-layout weights (list of G tensors, see conv3d_ref)."""
     y, stats = conv3d_ref(x0, weights, None, x1, ksize, stride, pad_mode, True, slices)
-    voxels = y.shape[1] * y.shape[2] * y.shape[3]
-    return _InormLrelu.apply(y, inorm_finalize(stats, voxels), res)
+    return _InormLrelu.apply(y, stats, res)                 # float64 sums: finalised inside the apply kernel
 
 
 _zero_arena = {}
@@ -872,8 +877,7 @@ def prenorm(x, stats=None):
     """InstanceNorm3d(affine=False) -> LeakyReLU(0.2) of an arbitrary cl tensor (the first half of
     general_conv3d_prenorm, reference models/blocks.py:312-314).  `stats`: the float64 [N, C, 2] sums of x when the kernel
     that produced x already accumulated them in its epilogue (conv3d_ref(..., want_stats=True)); else one extra pass."""
-    voxels = x.numel() // (x.shape[0] * x.shape[-1])
-    return _InormLrelu.apply(x, inorm_finalize(stats if stats is not None else channel_stats(x), voxels), None)
+    return _InormLrelu.apply(x, stats if stats is not None else channel_stats(x), None)
 
 
 class _Upsample(torch.autograd.Function):
@@ -917,15 +921,6 @@ def upsample(x, scale=2):
     return _Upsample.apply(x, scale)
 
 
-def _gate_mlp(S, Psum, voxels, w0, b0, w2, b2):
-    """modal_fusion gate (reference models/blocks.py:507-513) on the pooled statistics.
-    S [N,4,KC] = sum_v y p_i, Psum [N,4] = sum_v p_i  ->  gate [N,4(class),4(modality)]."""
-    prm_avg = Psum / voxels + 1e-7                                  # [N,4]
-    feat = torch.cat((S / voxels / prm_avg[..., None], prm_avg[..., None]), -1)        # [N,4,KC+1]
-    h = torch.nn.functional.leaky_relu(torch.einsum("nif,ihf->nih", feat, w0) + b0, LRELU_SLOPE)
-    return torch.sigmoid(torch.einsum("nih,ikh->nik", h, w2) + b2)
-
-
 class _MaskedStack(torch.autograd.Function):
     """out[p*B+b, ..., m*C+c] = enc[m*B+b, ..., c] * ms[p, b, m]  (MaskModal for P decoder passes in one launch)."""
 
@@ -964,74 +959,76 @@ def masked_stack(enc, ms):
     return _MaskedStack.apply(enc, ms)
 
 
-def _gate_single(S1, Psum, voxels, w0, b0, w2, b2):
-    """Gate of a SINGLE-modality pass: sample n = m*B + b only has modality m, so its pooled vector is S1 [4B,4,C] in slot
-    m of the [4B,4,4C] MLP input (zeros elsewhere, exactly what pooling the masked 4-slot stack gives) and only column m of
-    the [4B,4(class),4(modality)] gate is ever used.  Returns gate1 [4B,4]."""
-    n, _, c = S1.shape
-    B = n // 4
-    eye = torch.eye(4, dtype=S1.dtype, device=S1.device)
-    S_full = torch.einsum("mbic,mk->mbikc", S1.view(4, B, 4, c), eye).reshape(n, 4, 4 * c)
-    gate = _gate_mlp(S_full, Psum, voxels, w0, b0, w2, b2)                       # [4B,4,4]
-    return torch.einsum("mbik,mk->mbi", gate.view(4, B, 4, 4), eye).reshape(n, 4)
+def _ptr_array(ts):
+    return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
 class _RfmRegion(torch.autograd.Function):
     """Region-aware modality mixing: y [N,D,H,W,K*C] (masked features, channel = k*C+c), p [N,D,H,W,4] fp32
     (detached class probabilities) -> R [N,D,H,W,4C] (channel = class*C + c).
-    w0 [4,128,4C+1], b0 [4,128], w2 [4,4,128], b2 [4,4] are the four modal_fusion gate MLPs.
+    params = the 16 modal_fusion gate-MLP parameters as the reference stores them: 4 x weight_layer[0].weight [128,4C+1,1,1,1],
+    4 x weight_layer[0].bias [128], 4 x weight_layer[2].weight [4,128,1,1,1], 4 x weight_layer[2].bias [4] (class-major).
     K = 4: the 4-modality stack.  K = 1: y is the modality-major encoder output [4B,...,C] itself — four single-modality
-    passes (pass m sees modality m only) without ever building their 3/4-zero stacks."""
+    passes (pass m sees modality m only) without ever building their 3/4-zero stacks.
+    Three launches forward (pool, gate MLP, mix) and three backward (gate gradient, gate-MLP adjoint, dy)."""
 
     @staticmethod
-    def forward(ctx, y, p, w0, b0, w2, b2, K):
+    def forward(ctx, y, p, K, B, *params):
         lib = _lib.load()
-        _chk(y, p)
-        assert p.dtype == torch.float32 and p.shape[-1] == 4 and K in (1, 4)
+        _chk(y, p, *params)
+        assert p.dtype == torch.float32 and p.shape[-1] == 4 and K in (1, 4) and len(params) == 16
         n, kc = y.shape[0], y.shape[-1]
         c = kc // K
         voxels = y.numel() // (n * kc)
-        S = torch.zeros((n, 4, kc), dtype=torch.float64, device=y.device)
-        Ps = torch.zeros((n, 4), dtype=torch.float64, device=y.device)
+        dev = y.device
+        sums = torch.zeros((n * 4 * kc + n * 4,), dtype=torch.float64, device=dev)       # S | Psum in one zero fill
+        S, Ps = sums[:n * 4 * kc].view(n, 4, kc), sums[n * 4 * kc:].view(n, 4)
         _lib.check(lib.pb_rfm_pool(_dt(y), _p(y), _p(p), _p(S), _p(Ps), n, voxels, kc, _stream()), "rfm_pool")
-        S, Ps = S.float(), Ps.float()
-        gate = (_gate_mlp if K == 4 else _gate_single)(S, Ps, voxels, w0, b0, w2, b2).contiguous()
-        r = torch.empty(y.shape[:-1] + (4 * c,), dtype=y.dtype, device=y.device)
+        z1 = torch.empty((n, 4, 128), dtype=torch.float32, device=dev)
+        gate = torch.empty((n, 4, K), dtype=torch.float32, device=dev)
+        _lib.check(lib.pb_rfm_gate_fwd(_ptr_array(params), _p(S), _p(Ps), _p(z1), _p(gate), n, B, voxels, K, c, _stream()), "rfm_gate_fwd")
+        r = torch.empty(y.shape[:-1] + (4 * c,), dtype=y.dtype, device=dev)
         _lib.check(lib.pb_rfm_mix(_dt(y), _p(y), _p(p), _p(gate), _p(r), n, voxels, K, c, _stream()), "rfm_mix")
-        ctx.save_for_backward(y, p, S, Ps, gate, w0, b0, w2, b2)
-        ctx.K = K
+        ctx.save_for_backward(y, p, S, Ps, z1, gate, *params)
+        ctx.meta = (K, B)
         return r
 
     @staticmethod
     def backward(ctx, dr):
         lib = _lib.load()
-        y, p, S, Ps, gate, w0, b0, w2, b2 = ctx.saved_tensors
-        K = ctx.K
+        y, p, S, Ps, z1, gate = ctx.saved_tensors[:6]
+        params = ctx.saved_tensors[6:]
+        K, B = ctx.meta
         dr = dr.contiguous()
         n, kc = y.shape[0], y.shape[-1]
         c = kc // K
         voxels = y.numel() // (n * kc)
-        dgate = torch.zeros((n, 4, K) if K == 4 else (n, 4), dtype=torch.float64, device=y.device)
+        dev = y.device
+        dgate = torch.zeros((n, 4, K), dtype=torch.float64, device=dev)
         _lib.check(lib.pb_rfm_mix_bwd_gate(_dt(y), _p(y), _p(p), _p(dr), _p(dgate), n, voxels, K, c, _stream()),
                    "rfm_mix_bwd_gate")
-        with torch.enable_grad():                       # tiny [N, 4C+1] MLP: recompute and let autograd transpose it
-            S_ = S.detach().requires_grad_(True)
-            params = [t.detach().requires_grad_(True) for t in (w0, b0, w2, b2)]
-            g = (_gate_mlp if K == 4 else _gate_single)(S_, Ps, voxels, *params)
-            dS, dw0, db0, dw2, db2 = torch.autograd.grad(g, [S_, *params], dgate.float())
+        flat = torch.zeros((sum(t.numel() for t in params),), dtype=torch.float32, device=dev)   # 16 gradient accumulators, one fill
+        grads, off = [], 0
+        for t in params:
+            grads.append(flat[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+        dS = torch.empty((n, 4, kc), dtype=torch.float32, device=dev)
+        _lib.check(lib.pb_rfm_gate_bwd(_ptr_array(params), _ptr_array(grads), _p(S), _p(Ps), _p(z1), _p(dgate), _p(dS), n, B, voxels, K, c,
+                                       _stream()), "rfm_gate_bwd")
         dy = torch.empty_like(y)
-        _lib.check(lib.pb_rfm_bwd_y(_dt(y), _p(p), _p(gate), _p(dr), _p(dS.contiguous()), _p(dy), n, voxels, K, c, _stream()),
+        _lib.check(lib.pb_rfm_bwd_y(_dt(y), _p(p), _p(gate), _p(dr), _p(dS), _p(dy), n, voxels, K, c, _stream()),
                    "rfm_bwd_y")
-        return dy, None, dw0, db0, dw2, db2, None
+        return (dy, None, None, None, *grads)
 
 
-def rfm_region(y, p, w0, b0, w2, b2):
-    return _RfmRegion.apply(y, p, w0, b0, w2, b2, 4)
+def rfm_region(y, p, params, B=1):
+    """params: the 16 gate-MLP parameters (see _RfmRegion)."""
+    return _RfmRegion.apply(y, p, 4, B, *params)
 
 
-def rfm_region_single(enc, p, w0, b0, w2, b2):
+def rfm_region_single(enc, p, params, B):
     """Four single-modality passes on the modality-major encoder output enc [4B,D,H,W,C]; p [4B,D,H,W,4]."""
-    return _RfmRegion.apply(enc, p, w0, b0, w2, b2, 1)
+    return _RfmRegion.apply(enc, p, 1, B, *params)
 
 
 # ---- PASSION objective kernels (csrc/loss.cu) ----------------------------------------------------------------

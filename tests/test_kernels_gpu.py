@@ -246,6 +246,19 @@ def test_upsample(lib_built, c, shape, scale, dtype):
     assert rel(to_nc(x_cl.grad), xr.grad) < tol
 
 
+def _gate_params(w0, b0, w2, b2):
+    """stacked [4, ...] gate-MLP tensors -> the 16 parameters in the reference's nn.Conv3d shapes (ops._RfmRegion order)"""
+    mk = lambda t: t.clone().requires_grad_(True)
+    return ([mk(w0[i][:, :, None, None, None]) for i in range(4)] + [mk(b0[i]) for i in range(4)]
+            + [mk(w2[i][:, :, None, None, None]) for i in range(4)] + [mk(b2[i]) for i in range(4)])
+
+
+def _gate_grads(params):
+    g = [t.grad for t in params]
+    return (torch.stack([t.flatten(1) for t in g[0:4]]), torch.stack(g[4:8]), torch.stack([t.flatten(1) for t in g[8:12]]),
+            torch.stack(g[12:16]))
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("c,shape", [(8, (6, 7, 8)), (16, (4, 5, 6)), (64, (2, 2, 2)), (32, (3, 4, 3))])
 def test_rfm_region(lib_built, c, shape, dtype):
@@ -279,14 +292,15 @@ def test_rfm_region(lib_built, c, shape, dtype):
     refs = [t.double().requires_grad_(True) for t in (y, w0, b0, w2, b2)]
     rr = reference(*refs)
     rr.backward(gr.double())
-    ins = [y.clone().requires_grad_(True)] + [t.clone().requires_grad_(True) for t in (w0, b0, w2, b2)]
-    r = ops.rfm_region(ins[0], p, *ins[1:])
+    yin = y.clone().requires_grad_(True)
+    params = _gate_params(w0, b0, w2, b2)
+    r = ops.rfm_region(yin, p, params)
     r.backward(gr)
     tol = TOL[dtype]
     assert rel(r, rr) < tol
-    assert rel(ins[0].grad, refs[0].grad) < tol
-    for a, b in zip(ins[1:], refs[1:]):
-        assert rel(a.grad, b.grad) < (2e-4 if dtype == torch.float32 else 2e-2)
+    assert rel(yin.grad, refs[0].grad) < tol
+    for a, b in zip(_gate_grads(params), refs[1:]):
+        assert rel(a, b.grad) < (2e-4 if dtype == torch.float32 else 2e-2)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -312,17 +326,18 @@ def test_single_modality_passes_equal_their_stacks(lib_built, c, shape, dtype):
 
     def run(single):
         e = enc.clone().requires_grad_(True)
-        ps = [t.clone().requires_grad_(True) for t in (w0, b0, w2, b2, wc)]
+        gp = _gate_params(w0, b0, w2, b2)
+        wcp = wc.clone().requires_grad_(True)
         if single:
-            r = ops.rfm_region_single(e, p, *ps[:4])
-            y, st = ops.conv3d_ref(e, [ps[4]], ksize=1, pad_mode="zeros", want_stats=True, slices=4)
+            r = ops.rfm_region_single(e, p, gp, B)
+            y, st = ops.conv3d_ref(e, [wcp], ksize=1, pad_mode="zeros", want_stats=True, slices=4)
         else:
             stack = ops.masked_stack(e, ms)
-            r = ops.rfm_region(stack, p, *ps[:4])
-            y, st = ops.conv3d_ref(stack, [ps[4]], ksize=1, pad_mode="zeros", want_stats=True)
+            r = ops.rfm_region(stack, p, gp, B)
+            y, st = ops.conv3d_ref(stack, [wcp], ksize=1, pad_mode="zeros", want_stats=True)
         (r.float() * gr.float()).sum().backward(retain_graph=True)
         (y.float() * gc.float()).sum().backward()
-        return r.detach(), y.detach(), st.clone(), e.grad, [t.grad.clone() for t in ps]
+        return r.detach(), y.detach(), st.clone(), e.grad, list(_gate_grads(gp)) + [wcp.grad.clone()]
 
     a, b = run(True), run(False)
     tol = 1e-5 if dtype == torch.float32 else 1e-2
