@@ -36,7 +36,6 @@ SIDE_RECORD = os.environ.get("PB_SIDE_RECORD", "1") != "0"   # debugging switch 
 # single-modality passes without their 3/4-zero stacks, at the N finest levels (the coarse levels are launch-bound: splitting
 # their batch into dense + single parts costs more launches than the bytes it saves)
 SPARSE_SINGLES = int(os.environ.get("PB_SPARSE_SINGLES", "2"))
-FUSED_LOSS = os.environ.get("PB_FUSED_LOSS", "1") != "0"     # logit-level losses from one fused pass (csrc/loss.cu logit_loss_*)
 _side = {}
 
 
@@ -46,6 +45,17 @@ def _side_stream(device):
         st = _side[device] = torch.cuda.Stream(device=device)
         ops.register_side_stream(device, st)
     return st
+
+
+_consts = {}
+
+
+def _level_weights(device):
+    """[1, 1/2, 1/4, 1/8, 1/16]: weight of the full-resolution term and of the four PRM levels (rfnet.py:285-288)."""
+    t = _consts.get(device)
+    if t is None:
+        t = _consts[device] = torch.tensor([1.0, 0.5, 0.25, 0.125, 0.0625], device=device)
+    return t
 
 
 def _lend_to_stream(tensors, stream):
@@ -407,44 +417,38 @@ class Model(nn.Module):
         labels, cnt, wgt = crit.label_stats(target)
         V = D * H * W
 
-        if FUSED_LOSS:
-            # ONE pass over the fused-decoder logits: softmax of the full-mask pass (the returned prediction), its CE / Dice sums
-            # (the step's fuse loss, train.py:228-229 — handed to criterions.ce_dice_bs through the tensor) and, with PASSION,
-            # the KL of the four single-modality passes against it; no probability tensor is materialised
-            ce_f, dice_f, kl, probs = crit.logit_losses(logits, labels, cnt, wgt, P, 0, temp, want_probs=True)
-            fuse_prob = probs.permute(0, 4, 1, 2, 3)                                     # [B,C,D,H,W]
-            fuse_prob._pb_ce_dice = (ce_f, dice_f, weakref.ref(target))
-            # rfnet.py:259-260 multiplies the probabilities of a MISSING modality by 0 before the loss; that sample's loss is
-            # then multiplied by the same 0 below (and again in train.py:260): e * f(p) == e * f(e * p) for e in {0, 1}
-            ce, dice, _, _ = crit.logit_losses(sep_logits, labels, cnt, wgt, 4, 1)
-        else:
-            fuse_prob = ops.softmax4(fuse_logits[0]).permute(0, 4, 1, 2, 3)
-            ce, dice = crit.cedice(ops.softmax4(sep_logits), labels, cnt, wgt)
-            kl = None
-            if train_passion:
-                ps = ops.softmax4(fuse_logits[1:].reshape(4 * B, D, H, W, -1), temp)
-                pt = ops.softmax4(fuse_logits[0].detach(), temp)
-                kl = crit.kl(ps, pt, temp)                                     # [4B]
-        sep_loss = (e * (ce + dice).view(4, B)).t()                           # [B,4]   (rfnet.py:336 ...)
-
-        # ---- prm loss (rfnet.py:284-288, full-mask pass only) and the PRM part of the KL term (rfnet.py:340-344 ...)
-        prm_loss = torch.zeros(B, device=x.device)
-        wl = 1.0
-        for prm, s in zip(prms, UP_SCALES):
-            wl /= 2.0
-            if FUSED_LOSS and s == 1:                                          # the level at the labels' resolution: same fused pass
-                ce, dice, kl_l, _ = crit.logit_losses(prm, labels, cnt, wgt, P, 0, temp)
+        # ONE pass over the fused-decoder logits: softmax of the full-mask pass (the returned prediction), its CE / Dice sums (the
+        # step's fuse loss, train.py:228-229 — handed to criterions.ce_dice_bs through the tensor) and, with PASSION, the KL of the
+        # four single-modality passes against it; the same pass over the level-1 PRM logits; a four-pass supervised variant over
+        # the decoder_sep predictions.  No probability tensor is materialised at the labels' resolution.
+        # (rfnet.py:259-260 multiplies the probabilities of a MISSING modality by 0 before the loss; that sample's loss is then
+        # multiplied by the same 0 below and again in train.py:260: e * f(p) == e * f(e * p) for e in {0, 1}.)
+        s_fuse, kl_sums, probs = ops.logit_loss(logits, labels, P, 0, temp, want_probs=True)
+        fuse_prob = probs.permute(0, 4, 1, 2, 3)                                         # [B,C,D,H,W]
+        s_sep, _, _ = ops.logit_loss(sep_logits, labels, 4, 1)
+        sums, kls = [s_fuse, s_sep], [kl_sums]                # A / L / E sums of 1 + 4 + 4 supervised predictions per sample
+        for prm, s in zip(prms, UP_SCALES):                   # prm loss (rfnet.py:284-288) and the PRM part of the KL (:340-344 ...)
+            if s == 1:
+                s_l, kl_l, _ = ops.logit_loss(prm, labels, P, 0, temp)
             else:
                 pr = prm.view(P, B, *prm.shape[1:])
-                ce, dice = crit.cedice(crit.up_probs(ops.softmax4(pr[0]), s), labels, cnt, wgt)
+                s_l = ops.cedice_sums(crit.up_probs(ops.softmax4(pr[0]), s), labels)
                 kl_l = None
                 if train_passion:
                     ps_l = crit.up_probs(ops.softmax4(pr[1:].reshape(4 * B, *prm.shape[1:]), temp), s)
                     pt_l = crit.up_probs(ops.softmax4(pr[0].detach(), temp), s)
-                    kl_l = crit.kl(ps_l, pt_l, temp)
-            prm_loss = prm_loss + wl * (ce + dice)
-            if train_passion:
-                kl = kl + wl * kl_l
+                    kl_l = ops.kl_sums(ps_l, pt_l.detach())
+            sums.append(s_l)
+            kls.append(kl_l)
+        # the small arithmetic once for all nine predictions instead of once per prediction
+        ce, dice = crit.ce_dice_from_sums(torch.cat(sums), cnt, wgt, V, B)               # [9B]: fuse | sep x4 | prm x4
+        cd = (ce + dice).view(9, B)
+        fuse_prob._pb_ce_dice = (ce[:B], dice[:B], weakref.ref(target))
+        sep_loss = (e * cd[1:5]).t()                                                     # [B,4]   (rfnet.py:336 ...)
+        lvl_w = _level_weights(x.device)                      # 1, 1/2, 1/4, 1/8, 1/16 (created once per device: no copy in a capture)
+        prm_loss = (lvl_w[1:, None] * cd[5:9]).sum(0)
+        if train_passion:                                     # T^2 * mean over (voxels, classes), criterions.py:98-102
+            kl = (lvl_w[:, None] * torch.stack(kls)).sum(0) * (temp * temp / (V * 4))    # [4B]
         if not self.use_passion:
             return fuse_prob, prm_loss[:, None], sep_loss                     # rfnet.py:402
 
