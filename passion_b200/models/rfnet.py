@@ -267,7 +267,9 @@ class Decoder_fuse(_DecoderConvs):
 
     @staticmethod
     def _probs(logits):
-        return torch.softmax(logits.float(), -1).detach()
+        """detached class probabilities of the PRM logits (rfnet.py:128: `prm_pred.detach()` after the softmax of blocks.py:414)"""
+        with torch.no_grad():
+            return ops.softmax4(logits)
 
     def run(self, y1, y2, y3, y4, enc=None):
         """y_l [Nd,D_l,H_l,W_l,4*C_l] masked encoder features of the dense passes; enc = the four levels of the modality-major
