@@ -10,6 +10,8 @@ typedef __nv_bfloat16 bf16;
 
 void pb_set_error(const char* fmt, ...);
 void pb_count_launch(int n = 1);
+// csrc/conv3d_wgrad_rs.cu: row-stacked tcgen05 weight gradient (PB_EUNSUPPORTED = class not covered)
+int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw, int* err_flag, cudaStream_t st);
 
 #define PB_CHECK_ARG(cond, msg)                                   \
     do { if (!(cond)) { pb_set_error("%s: %s", __func__, msg); return PB_EINVAL; } } while (0)

@@ -1552,6 +1552,11 @@ extern "C" int pb_conv3d_wgrad_tc(const pb_conv_desc* d, const void* x0, const v
     p.N = d->n; p.D = d->di; p.H = d->hi; p.W = d->wi; p.C0 = d->c0; p.C1 = d->c1; p.Cout = d->cout;
     p.reflect = d->pad_mode == PB_PAD_REFLECT;
     PB_CHECK_ARG(!p.reflect || (p.D >= 2 && p.H >= 2 && p.W >= 2), "reflect padding needs size >= 2");
+    {   // row-stacked kernel (conv3d_wgrad_rs.cu): one MMA per 16 voxels and input chunk for all 27 taps
+        const int rc = pb_wgrad_rs_launch(d, x0, x1, dy, dw, err_flag, (cudaStream_t)stream);
+        if (rc == 0) { PB_CHECK_LAUNCH(); return PB_OK; }
+        if (rc != PB_EUNSUPPORTED) return rc;
+    }
     p.PW = p.W + 2;
     p.QT = (p.H * p.PW + kTileM - 1) / kTileM;
     p.npg = d->n / d->groups; p.groups = d->groups;

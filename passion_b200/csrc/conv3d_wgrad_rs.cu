@@ -1,0 +1,398 @@
+// Row-stacked tcgen05 weight gradient of the 3x3x3 stride-1 convs (sm_100a) — round 2 replacement of the kh-stacked kernels of
+// conv3d_tc.cu.  Replaces the weight-gradient half of nn.Conv3d's autograd node (reference models/blocks.py:357, general_conv3d).
+//
+//   dw[kd,kh,kw][ci][co] = sum_{n,d,h,w} xp[n, d+kd-1, h+kh-1, w+kw-1][ci] * dy[n,d,h,w][co]        (xp = reflect / zero padded x)
+//
+// Why a new shape: the old kernels (M = 64, N = 32: six tcgen05.mma per 16 voxels of a c16 -> 8 layer) were bound by the
+// instruction count — an MMA with both operands MN-major costs the pipe max(36, M*N*16 / 2048 [M = 64] or 4096 [M = 128]) cycles
+// and ONE thread cannot issue them faster than one per 61.5 cycles (scripts/microbench/umma_rate_mn*.cu, profiles/r02_wgrad_rs.txt).
+// Here ONE instruction per 16 voxels, 8-channel input chunk and 8-channel output chunk produces all 27 taps:
+//   * K = 16 consecutive w positions of ONE padded input row (d, h); a CTA walks whole rows.
+//   * A (M = 64, MN-major) = that row of xp for one 8-channel chunk; the eight M-groups are the same row shifted by 0..7 positions
+//     (SBO = 16 B), groups 0..2 are the three kw taps, groups 3..7 are don't-care rows that are never read back.
+//   * B (N = 88, MN-major) = the dy rows (d-1..d+1) x (h-1..h+1) that pair with this input row, one 8-channel output chunk.
+//     The dy strip lives in shared memory in a DIAGONAL layout: row h' of the q-th plane of the sweep sits at row index
+//     L = 4 h' + q of one linear buffer.  The nine rows of an input row are then L0 + {0,1,2, 4,5,6, 8,9,10} with L0 moving by one
+//     per plane: ONE descriptor with SBO = row pitch and 11 N-groups addresses them, always in the same order (no rotation of
+//     the accumulator columns); groups 3 and 7 belong to plane q + 3, which is being prefetched while plane q's step runs —
+//     their accumulator columns are garbage and are never read back.  Plane q + 4 overwrites plane q one row further up, so four
+//     planes are live and the load of a plane has a whole step to land (with three planes it sat on the critical path:
+//     measured 198 us vs the 83 us of the MMAs alone for the c16 -> 8, 80^3, n = 10 class).
+// A CTA (one per SM) owns (weight group, up to four input chunks, one output chunk) and a stream of work items (sample, strip of
+// <= 8 input rows, depth chunk of <= 16 planes); the accumulators (96 TMEM columns per input chunk) stay in TMEM for the whole
+// stream and are flushed once with fp32 atomics.
+// Warp roles: warps 0-7 stage the input rows (16-byte cp.async; reflect / zero padding and the two-source concat are resolved
+// in the address computation, the K tail is zero-filled), running up to three steps ahead; warp 8 lane 0 streams the dy rows by
+// TMA (one box [KW positions][8 ch] per row; rows and planes outside the volume and the K tail are the tensor map's zero fill);
+// lanes 0 of warps 9-11 issue the MMAs, all accumulating into the same (zero-initialised) accumulators, K loop unrolled (with
+// the descriptors advanced in a rolled loop one thread needs 119 cycles per MMA instead of 64).  Warps 0 and 1 flush at the end.
+#include <cstdlib>
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kRsThreads = 384;
+constexpr int kRsXProducers = 256;         // warps 0-7
+constexpr int kRsXSlots = 3;
+constexpr int kRsXCopies = 8;              // 16-byte copies per x-producer thread and step
+constexpr int kRsMaxRows = 16;
+constexpr int kRsMaxSteps = 16;            // planes per work item (bounds the diagonal dy buffer)
+constexpr int kRsMaxChunks = 4;            // input chunks per CTA
+constexpr int kRsIssuers = 3;
+constexpr int kRsN = 88;                   // UMMA N: 11 dy row groups x 8 output channels
+constexpr int kRsSetW = 96;                // TMEM columns per input chunk
+
+struct RsP {
+    int N, D, H, W, C0, C1, Cout, reflect;
+    int KW;                                // K extent of a row: W rounded up to 16
+    int nr;                                // input rows per strip
+    int nstrips, ND, npg, groups, nT, nP, TG, ntg;   // TG input chunks per CTA, ntg chunk groups
+    int h_lo, rows_t, d_lo, planes_t;      // padded input rows / planes that contribute: [-1, H] for reflect, [0, H) for zero padding
+    int yrows, nregions;                   // rows of one diagonal dy buffer region; regions (2: the first planes of the next item load while this one computes)
+    int dbg;                               // developer probes: 2 = no MMAs, 3 = no input-row copies (results are garbage)
+    uint32_t tmem_cols;
+    int prefetch;                          // dy planes ahead to prefetch into L2 (0 = off)
+};
+
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+// Producer-side wait: ONE lane polls, with a back-off, and the warp follows.  The MMAs of this kernel read ~108 B of shared memory
+// per clock (4.75 KB per 44-cycle instruction) out of the SM's 128: nine warps spinning on mbarrier.try_wait took a third of it.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane, volatile int* err, int code) {
+    if (lane == 0 && !mbar_try_wait(bar, parity)) {
+        const long long t0 = clock64();
+        uint32_t spins = 0;
+        while (!mbar_try_wait(bar, parity)) {
+            __nanosleep(40);
+            if ((++spins & 255u) == 0) {
+                if (*err != 0) break;
+                if (clock64() - t0 > 4000000000LL) { atomicCAS((int*)err, 0, code); break; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int KS>
+__device__ __forceinline__ void rs_issue(uint32_t d_tmem, uint32_t xrow, uint32_t yrow, int ypitch_b) {
+    constexpr uint32_t IDESC = umma_idesc(64, kRsN) | (1u << 15) | (1u << 16);      // both operands MN-major
+    const uint64_t a0 = umma_desc(xrow, 128, 16);
+    const uint64_t b0 = umma_desc(yrow, 128, (uint32_t)ypitch_b);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b0 + (uint64_t)(16 * ks), IDESC, 1u);
+}
+
+__global__ void __launch_bounds__(kRsThreads, 1)
+conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                      float* __restrict__ dw, int* err) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int ypitch_b = p.KW * 16;
+    const int xpitch_b = (p.KW + 8) * 16;
+    const int yregion_bytes = p.yrows * ypitch_b;
+    const int ybuf_bytes = p.nregions * yregion_bytes;
+    const int xslot_bytes = p.TG * p.nr * xpitch_b;
+    uint8_t* y_s = smem;
+    uint8_t* x_s = smem + ybuf_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + (size_t)kRsXSlots * xslot_bytes);
+    uint64_t* fullx = bars;
+    uint64_t* emptyx = bars + kRsXSlots;
+    uint64_t* fully = bars + 2 * kRsXSlots;
+    uint64_t* emptyy = fully + 4;
+    uint64_t* item_done = emptyy + 4;                  // [2]: one per dy buffer region
+    uint64_t* done = item_done + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int by = blockIdx.y;
+    const int cochunk = by % p.nP, tg = (by / p.nP) % p.ntg, g = by / (p.nP * p.ntg);
+    const int ch0 = tg * p.TG;
+    const int nch = min(p.TG, p.nT - ch0);                    // input chunks of this CTA
+    const int items = p.npg * p.nstrips * p.ND;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRsXSlots; ++i) { mbar_init(&fullx[i], kRsXProducers); mbar_init(&emptyx[i], kRsIssuers); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&fully[i], 1); mbar_init(&emptyy[i], kRsIssuers); }
+        mbar_init(&item_done[0], kRsIssuers);
+        mbar_init(&item_done[1], kRsIssuers);
+        mbar_init(done, kRsIssuers);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp < 4) {
+        // every MMA accumulates (several threads issue into the same accumulators, in no particular order): start from zero
+        for (int c = 0; c < (int)p.tmem_cols; c += 16) tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 8) {
+        // =============================== input-row producers (run ahead of the MMAs by up to kRsXSlots steps) ===============
+        const int pt = threadIdx.x;
+        const int c0ch = p.C0 >> 3;
+        const int xrow_e = p.KW + 8;
+        const int per_chunk = p.nr * xrow_e;
+        uint32_t kx = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int st = r1 % p.nstrips, n = g * p.npg + r1 / p.nstrips;
+            const int hs = p.h_lo + (st * p.rows_t) / p.nstrips;                 // first padded input row of the strip
+            const int nr = p.h_lo + ((st + 1) * p.rows_t) / p.nstrips - hs;
+            const int dx0 = p.d_lo + (dc * p.planes_t) / p.ND;
+            const int dx1 = p.d_lo + ((dc + 1) * p.planes_t) / p.ND;             // exclusive
+            int xoff[kRsXCopies];                                               // -2: nothing to copy, -1: zero fill, else offset in the plane
+            uint32_t xdst[kRsXCopies];
+            uint32_t src1 = 0;                                                  // bit i: copy i reads the second source
+#pragma unroll
+            for (int i = 0; i < kRsXCopies; ++i) {
+                const int e = pt + i * kRsXProducers;
+                xoff[i] = -2;
+                xdst[i] = 0;
+                if (e < nch * per_chunk) {
+                    const int c = e / per_chunk, rem = e - c * per_chunk;
+                    const int r = rem / xrow_e, t = rem - r * xrow_e;
+                    if (r < nr) {
+                        const int ch = ch0 + c;
+                        const bool from1 = ch >= c0ch;
+                        const int cs = from1 ? p.C1 : p.C0, coff = (from1 ? ch - c0ch : ch) * 8;
+                        int h = hs + r, w = t - 1;
+                        bool ok;
+                        if (p.reflect) { ok = w >= -1 && w <= p.W; h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); }
+                        else ok = w >= 0 && w < p.W;
+                        xoff[i] = ok ? (h * p.W + w) * cs + coff : -1;
+                        xdst[i] = (uint32_t)((c * p.nr + r) * xpitch_b + t * 16);
+                        if (from1) src1 |= 1u << i;
+                    }
+                }
+            }
+            for (int dx = dx0; dx < dx1; ++dx, ++kx) {
+                const int slot = kx % kRsXSlots;
+                mbar_wait_warp(&emptyx[slot], ((kx / kRsXSlots) & 1) ^ 1, lane, err, 42);
+                const int dpx = p.reflect ? reflect_idx(dx, p.D) : dx;
+                const size_t pl = ((size_t)n * p.D + dpx) * p.H * p.W;
+                const bf16* pp0 = x0 + pl * p.C0;
+                const bf16* pp1 = x1 + pl * p.C1;
+                const uint32_t sbase = smem_u32(x_s) + (uint32_t)(slot * xslot_bytes);
+#pragma unroll
+                for (int i = 0; i < kRsXCopies; ++i) {
+                    if (xoff[i] != -2 && p.dbg != 3) {
+                        const bool ok = xoff[i] >= 0;
+                        const bf16* src = ((src1 >> i) & 1u) ? pp1 : pp0;
+                        cp_async16(sbase + xdst[i], ok ? src + xoff[i] : x0, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive_noinc(&fullx[slot]);
+            }
+        }
+        cp_async_wait_all();
+    } else if (warp == 8) {
+        // =============================== dy-row producer: one TMA box [KW positions][8 ch] per row, one row per lane ============
+        // (a single thread issuing the rows one after the other made the load of a plane take ~2.8 us — longer than a step)
+        const uint32_t plane_bytes = (uint32_t)((p.nr + 2) * ypitch_b);
+        uint32_t ky = 0, kitem = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x, ++kitem) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int st = r1 % p.nstrips, n = g * p.npg + r1 / p.nstrips;
+            const int hs = p.h_lo + (st * p.rows_t) / p.nstrips;
+            const int dx0 = p.d_lo + (dc * p.planes_t) / p.ND;
+            const int dx1 = p.d_lo + ((dc + 1) * p.planes_t) / p.ND;
+            // the diagonal buffer restarts at q = 0 with every item, alternating between the regions: the MMAs of the item that
+            // used this region last must have drained
+            const uint32_t region = kitem % p.nregions, use = kitem / p.nregions;
+            if (use > 0) mbar_wait_warp(&item_done[region], (use - 1) & 1, lane, err, 40);
+            // planes dx0-1 .. dx1 (q = 0 .. nsteps+1); plane q may land once plane q-4 is dead.  Always nr + 2 rows (a shorter
+            // strip leaves the last rows unused) so that a plane is a fixed number of bytes.
+            for (int dp = dx0 - 1, q = 0; dp <= dx1; ++dp, ++q, ++ky) {
+                const int slot = ky & 3;
+                mbar_wait_warp(&emptyy[slot], ((ky >> 2) & 1) ^ 1, lane, err, 41);
+                const bool plane_ok = dp >= 0 && dp < p.D;
+                const uint32_t ybase = smem_u32(y_s) + region * (uint32_t)yregion_bytes + (uint32_t)(q * ypitch_b);
+                if (lane == 0) mbar_expect_tx(&fully[slot], plane_bytes);
+                __syncwarp();
+                if (lane < p.nr + 2)
+                    tma_load_5d(ybase + (uint32_t)(lane * 4 * ypitch_b), &ymap, 0, 0, plane_ok ? hs - 1 + lane : p.H + 8, cochunk,
+                                plane_ok ? n * p.D + dp : 0, &fully[slot]);
+                const int dpf = dp + p.prefetch, hpf = hs - 1 + lane;
+                if (p.prefetch && lane < p.nr + 2 && dpf >= 0 && dpf < p.D && dpf <= dx1 && hpf >= 0 && hpf < p.H)
+                    tma_prefetch_5d(&ymap, 0, 0, hpf, cochunk, n * p.D + dpf);
+            }
+        }
+    } else if (lane == 0) {
+        // =============================== MMA issuers (warps 9-11) ===============================
+        // One thread cannot issue faster than one MMA per ~62 cycles and the pipe retires one in 44: every issuer walks all steps
+        // (it must see every `full` phase before it may arrive on the matching `empty`) and issues every third (chunk, row) pair.
+        const int issuer = warp - 9;
+        const uint32_t x_addr = smem_u32(x_s), y_addr = smem_u32(y_s);
+        const int ksteps = p.KW >> 4;
+        uint32_t kx = 0, ky = 0, kitem = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x, ++kitem) {
+            const int dc = it % p.ND, r1 = it / p.ND;
+            const int st = r1 % p.nstrips;
+            const int nr = ((st + 1) * p.rows_t) / p.nstrips - (st * p.rows_t) / p.nstrips;
+            const int nsteps = ((dc + 1) * p.planes_t) / p.ND - (dc * p.planes_t) / p.ND;
+            const uint32_t region = kitem % p.nregions;
+            const uint32_t yreg = y_addr + region * (uint32_t)yregion_bytes;
+            for (int s = 0; s < nsteps; ++s, ++kx) {
+                // step s reads planes q = s, s+1, s+2: three new ones at the start of an item, one per step afterwards
+                const int nl = s == 0 ? 3 : 1;
+                for (int l = 0; l < nl; ++l, ++ky) mbar_wait(&fully[ky & 3], (ky >> 2) & 1, err, 43);
+                mbar_wait(&fullx[kx % kRsXSlots], (kx / kRsXSlots) & 1, err, 44);
+                fence_proxy_async();
+                tc_fence_after();
+                const uint32_t xs0 = x_addr + (kx % kRsXSlots) * xslot_bytes;
+                const int npairs = p.dbg == 2 ? 0 : nch * nr;
+                for (int pr = issuer; pr < npairs; pr += kRsIssuers) {
+                    const int c = pr / nr, i = pr - c * nr;
+                    const uint32_t d_tmem = tmem_base + c * kRsSetW;
+                    const uint32_t xrow = xs0 + (c * p.nr + i) * xpitch_b;
+                    const uint32_t yrow = yreg + (4 * i + s) * ypitch_b;
+                    switch (ksteps) {
+                        case 1: rs_issue<1>(d_tmem, xrow, yrow, ypitch_b); break;
+                        case 2: rs_issue<2>(d_tmem, xrow, yrow, ypitch_b); break;
+                        case 3: rs_issue<3>(d_tmem, xrow, yrow, ypitch_b); break;
+                        case 4: rs_issue<4>(d_tmem, xrow, yrow, ypitch_b); break;
+                        case 5: rs_issue<5>(d_tmem, xrow, yrow, ypitch_b); break;
+                        case 6: rs_issue<6>(d_tmem, xrow, yrow, ypitch_b); break;
+                        case 7: rs_issue<7>(d_tmem, xrow, yrow, ypitch_b); break;
+                        default: rs_issue<8>(d_tmem, xrow, yrow, ypitch_b); break;
+                    }
+                }
+                umma_commit(&emptyx[kx % kRsXSlots]);
+                // plane q = s is dead after this step; its barrier slot is the one of load (ky - 3)
+                umma_commit(&emptyy[(ky - 3) & 3]);
+                if (s == nsteps - 1) { umma_commit(&emptyy[(ky - 2) & 3]); umma_commit(&emptyy[(ky - 1) & 3]); umma_commit(&item_done[region]); }
+            }
+        }
+        umma_commit(done);
+    }
+    __syncwarp();
+    if (warp < 2 && blockIdx.x < items) {
+        // =============================== epilogue: TMEM -> fp32 atomics into dw ===============================
+        mbar_wait(done, 0, err, 45);
+        tc_fence_after();
+        // M = 64 accumulator layout: row m lives in lane (m % 16) + 32 * (m / 16); m = kw * 8 + ci
+        const int m = lane < 16 ? warp * 16 + lane : 64;
+        const int kw = m >> 3, ci = m & 7;
+        const int cin = p.C0 + p.C1;
+        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < nch; ++c) {
+            for (int a = 0; a < 3; ++a) {
+                for (int dq = 0; dq < 3; ++dq) {                            // N-group 4a + dq: dy row h-1+a of plane d-1+dq
+                    float v[8];
+                    tmem_ld8(tlane + c * kRsSetW + (4 * a + dq) * 8, v);
+                    tmem_wait_ld();
+                    if (m < 24) {
+                        const int tap = ((2 - dq) * 3 + (2 - a)) * 3 + kw;
+                        float* dst = dw + (((size_t)g * 27 + tap) * cin + (ch0 + c) * 8 + ci) * p.Cout + cochunk * 8;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) atomicAdd(dst + q, v[q]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
+
+}  // namespace
+
+// Internal entry (called by pb_conv3d_wgrad_tc, which has validated the descriptor): PB_EUNSUPPORTED = class not covered, the
+// caller falls back to the kh-stacked kernels.
+int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw, int* err_flag,
+                       cudaStream_t st) {
+    // read per call (a getenv is noise beside a launch) so that a developer script can compare both paths in one process
+    const int mode = env_int("PB_WG_RS", 1);
+    if (mode == 0) return PB_EUNSUPPORTED;
+    RsP p;
+    p.dbg = mode;
+    p.N = d->n; p.D = d->di; p.H = d->hi; p.W = d->wi; p.C0 = d->c0; p.C1 = d->c1; p.Cout = d->cout;
+    p.reflect = d->pad_mode == PB_PAD_REFLECT;
+    p.KW = (p.W + 15) & ~15;
+    if (p.KW > 128) return PB_EUNSUPPORTED;
+    // measured (scripts/bench_wgrad.py, profiles/r02_wgrad_rs.txt): 1.2-1.5x faster than the kh-stacked kernels at 80^3 and 40^3; at 20^3
+    // and below a launch is a few items per CTA and the per-item prologue (three dy planes) dominates: those stay on the old kernels
+    if ((long long)p.D * p.H * p.W < env_int("PB_WG_RS_MIN_VOX", 48000)) return PB_EUNSUPPORTED;
+    p.npg = d->n / d->groups; p.groups = d->groups;
+    p.nT = (d->c0 + d->c1) / 8;
+    p.nP = d->cout / 8;
+    p.TG = p.nT < kRsMaxChunks ? p.nT : kRsMaxChunks;
+    p.ntg = (p.nT + p.TG - 1) / p.TG;
+    p.tmem_cols = 32;
+    while ((int)p.tmem_cols < p.TG * kRsSetW) p.tmem_cols *= 2;
+    p.h_lo = p.reflect ? -1 : 0; p.rows_t = p.reflect ? p.H + 2 : p.H;
+    p.d_lo = p.reflect ? -1 : 0; p.planes_t = p.reflect ? p.D + 2 : p.D;
+    if ((long long)p.H * p.W * (p.C0 > p.C1 ? p.C0 : p.C1) >= (1LL << 30)) return PB_EUNSUPPORTED;          // int offsets within a plane
+    p.prefetch = env_int("PB_WG_RS_PREFETCH", 0);
+    p.nregions = env_int("PB_WG_RS_REGIONS", 2) >= 2 ? 2 : 1;
+    const int gy = p.groups * p.ntg * p.nP;
+    const int ctas_max = 148 / gy < 1 ? 1 : 148 / gy;
+    // rows per strip: bounded by the copy budget of the input-row producers and by shared memory
+    int nr = env_int("PB_WG_RS_ROWS", 8);
+    if (nr > kRsMaxRows) nr = kRsMaxRows;
+    if (nr > p.rows_t) nr = p.rows_t;
+    auto smem_of = [&](int rows, int steps) {
+        return (size_t)p.nregions * (4 * (rows + 2) + steps + 2) * p.KW * 16 + (size_t)kRsXSlots * p.TG * rows * (p.KW + 8) * 16 + 256;
+    };
+    while (nr > 1 && (p.TG * nr * (p.KW + 8) > kRsXCopies * kRsXProducers || smem_of(nr, kRsMaxSteps) > 227 * 1024)) --nr;
+    if (p.TG * nr * (p.KW + 8) > kRsXCopies * kRsXProducers || smem_of(nr, kRsMaxSteps) > 227 * 1024) return PB_EUNSUPPORTED;
+    p.nstrips = (p.rows_t + nr - 1) / nr;
+    p.nr = (p.rows_t + p.nstrips - 1) / p.nstrips;
+    // depth chunks: at most kRsMaxSteps planes per item, at least 6 (the two halo planes of dy are loaded per item); among those the
+    // count that fills whole rounds of CTAs best (an item is ~25 us of work: a ragged last round is the largest loss)
+    int best_nd = 0;
+    double best_eff = -1.0;
+    const int nd_force = env_int("PB_WG_RS_ND", 0);
+    for (int nd = (p.planes_t + kRsMaxSteps - 1) / kRsMaxSteps; nd == (p.planes_t + kRsMaxSteps - 1) / kRsMaxSteps || p.planes_t / nd >= 6; ++nd) {
+        const int it = p.npg * p.nstrips * nd;
+        const int ct = it < ctas_max ? it : ctas_max;
+        const int rounds = (it + ct - 1) / ct;
+        // whole-round efficiency, discounted by the per-item overhead of the two extra dy planes
+        const double steps = (double)p.planes_t / nd;
+        const double eff = (double)it / ((double)rounds * ct) * steps / (steps + 1.0);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_nd = nd; }
+        if (nd > p.planes_t) break;
+    }
+    p.ND = nd_force > 0 ? nd_force : best_nd;
+    const int max_steps = (p.planes_t + p.ND - 1) / p.ND;
+    if (max_steps > kRsMaxSteps) return PB_EUNSUPPORTED;
+    p.yrows = 4 * (p.nr + 2) + max_steps + 2;
+    const int items = p.npg * p.nstrips * p.ND;
+    const int ctas = items < ctas_max ? items : ctas_max;
+    const size_t smem = (size_t)p.nregions * p.yrows * p.KW * 16 + (size_t)kRsXSlots * p.TG * p.nr * (p.KW + 8) * 16 + (2 * kRsXSlots + 11) * 8 + 16;
+    if (smem > 227 * 1024) return PB_EUNSUPPORTED;
+    // dense NDHWC dy seen as (8 ch of a chunk, W, H, Cout/8 chunks, N*D planes); box = one row of KW positions of one chunk
+    CUtensorMap ymap;
+    {
+        EncodeTiledFn enc = encode_tiled();
+        if (enc == nullptr) return PB_EUNSUPPORTED;
+        const cuuint64_t dims[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)(p.Cout / 8), (cuuint64_t)p.N * p.D};
+        const cuuint64_t strides[4] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.W * p.Cout * 2, 16, (cuuint64_t)p.H * p.W * p.Cout * 2};
+        const cuuint32_t box[5] = {8, (cuuint32_t)p.KW, 1, 1, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        if (enc(&ymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return PB_EUNSUPPORTED;
+    }
+    cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pb_set_error("conv3d_wgrad_rs: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
+    conv3_wgrad_rs_kernel<<<dim3(ctas, gy), kRsThreads, smem, st>>>(ymap, p, (const bf16*)x0, (const bf16*)x1, dw, err_flag);
+    return 0;
+}
