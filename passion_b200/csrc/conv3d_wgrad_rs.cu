@@ -51,6 +51,7 @@ struct RsP {
     int yrows, nregions;                   // rows of one diagonal dy buffer region; regions (2: the first planes of the next item load while this one computes)
     int dbg;                               // developer probes: 2 = no MMAs, 3 = no input-row copies (results are garbage)
     uint32_t tmem_cols;
+    int UC;                                // input chunks per MMA ("unit"): 1 = plain rows, 2 = 16-channel rows (SWIZZLE_32B), 4 = 32-channel rows (SWIZZLE_64B)
     int prefetch;                          // dy planes ahead to prefetch into L2 (0 = off)
 };
 
@@ -76,13 +77,41 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
     __syncwarp();
 }
 
-template <int KS>
+// A operand of one input row for a unit of UC chunks, MN-major (cute canonical layouts, T = 8 elements = 16 B):
+//   UC = 1: no swizzle   ((T,1,m),(8,k)) : ((1,T,SBO),(1T,LBO))   m = shift groups at SBO = 16 B (one position), 8 k at LBO = 128 B
+//   UC = 2: SWIZZLE_32B  ((T,2,m),(8,k)) : ((1,T,LBO),(2T,SBO))   16-channel rows of 32 B, m = shift groups at LBO = 32 B, 8 k at SBO = 256 B
+//   UC = 4: SWIZZLE_64B  ((T,4,m),(8,k)) : ((1,T,LBO),(4T,SBO))   32-channel rows of 64 B, LBO = 64 B, SBO = 512 B
+// The swizzle XORs the 16-byte unit index within a row with address bits 7.. (one bit / two bits): the producers store a position's
+// chunks permuted accordingly; row starts are multiples of 256 / 512 B so the pattern is a function of the position alone and one
+// staged row serves all shifts.
+template <int UC>
+__device__ __forceinline__ uint64_t rs_adesc(uint32_t addr) {
+    if constexpr (UC == 1) return umma_desc(addr, 128, 16);
+    else if constexpr (UC == 2) return umma_desc(addr, 32, 256) | (6ULL << 61);
+    else return umma_desc(addr, 64, 512) | (4ULL << 61);
+}
+
+template <int UC, int KS>
 __device__ __forceinline__ void rs_issue(uint32_t d_tmem, uint32_t xrow, uint32_t yrow, int ypitch_b) {
-    constexpr uint32_t IDESC = umma_idesc(64, kRsN) | (1u << 15) | (1u << 16);      // both operands MN-major
-    const uint64_t a0 = umma_desc(xrow, 128, 16);
+    constexpr uint32_t IDESC = umma_idesc(UC == 4 ? 128 : 64, kRsN) | (1u << 15) | (1u << 16);      // both operands MN-major
+    const uint64_t a0 = rs_adesc<UC>(xrow);
     const uint64_t b0 = umma_desc(yrow, 128, (uint32_t)ypitch_b);
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) umma_f16(d_tmem, a0 + (uint64_t)(16 * ks), b0 + (uint64_t)(16 * ks), IDESC, 1u);
+    for (int ks = 0; ks < KS; ++ks) umma_f16(d_tmem, a0 + (uint64_t)(16 * UC * ks), b0 + (uint64_t)(16 * ks), IDESC, 1u);
+}
+
+template <int UC>
+__device__ __forceinline__ void rs_issue_k(int ksteps, uint32_t d_tmem, uint32_t xrow, uint32_t yrow, int ypitch_b) {
+    switch (ksteps) {
+        case 1: rs_issue<UC, 1>(d_tmem, xrow, yrow, ypitch_b); break;
+        case 2: rs_issue<UC, 2>(d_tmem, xrow, yrow, ypitch_b); break;
+        case 3: rs_issue<UC, 3>(d_tmem, xrow, yrow, ypitch_b); break;
+        case 4: rs_issue<UC, 4>(d_tmem, xrow, yrow, ypitch_b); break;
+        case 5: rs_issue<UC, 5>(d_tmem, xrow, yrow, ypitch_b); break;
+        case 6: rs_issue<UC, 6>(d_tmem, xrow, yrow, ypitch_b); break;
+        case 7: rs_issue<UC, 7>(d_tmem, xrow, yrow, ypitch_b); break;
+        default: rs_issue<UC, 8>(d_tmem, xrow, yrow, ypitch_b); break;
+    }
 }
 
 __global__ void __launch_bounds__(kRsThreads, 1)
@@ -94,9 +123,11 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
     const int yregion_bytes = p.yrows * ypitch_b;
     const int ybuf_bytes = p.nregions * yregion_bytes;
     const int xslot_bytes = p.TG * p.nr * xpitch_b;
-    uint8_t* y_s = smem;
-    uint8_t* x_s = smem + ybuf_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(x_s + (size_t)kRsXSlots * xslot_bytes);
+    // input-row slots first, on a 1024-byte boundary of the shared address space (the swizzle patterns are functions of address
+    // bits 4..8); slot, unit and row strides are multiples of 512 B
+    uint8_t* x_s = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    uint8_t* y_s = x_s + (size_t)kRsXSlots * xslot_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(y_s + ybuf_bytes);
     uint64_t* fullx = bars;
     uint64_t* emptyx = bars + kRsXSlots;
     uint64_t* fully = bars + 2 * kRsXSlots;
@@ -171,7 +202,10 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
                         if (p.reflect) { ok = w >= -1 && w <= p.W; h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); }
                         else ok = w >= 0 && w < p.W;
                         xoff[i] = ok ? (h * p.W + w) * cs + coff : -1;
-                        xdst[i] = (uint32_t)((c * p.nr + r) * xpitch_b + t * 16);
+                        // unit u = c / UC holds UC chunks side by side: [row][position][UC x 16 B], 16-byte units swizzled
+                        const int u = c / p.UC, cu = c - u * p.UC;
+                        const int sw = p.UC == 1 ? 0 : (p.UC == 2 ? ((t >> 2) & 1) : ((t >> 1) & 3));
+                        xdst[i] = (uint32_t)(((u * p.nr + r) * xrow_e + t) * 16 * p.UC + ((cu ^ sw) * 16));
                         if (from1) src1 |= 1u << i;
                     }
                 }
@@ -251,22 +285,17 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
                 fence_proxy_async();
                 tc_fence_after();
                 const uint32_t xs0 = x_addr + (kx % kRsXSlots) * xslot_bytes;
-                const int npairs = p.dbg == 2 ? 0 : nch * nr;
+                const int nunits = (nch + p.UC - 1) / p.UC;
+                const int npairs = p.dbg == 2 ? 0 : nunits * nr;
+                const uint32_t upitch = (uint32_t)xpitch_b * p.UC;         // bytes of one row of a unit
                 for (int pr = issuer; pr < npairs; pr += kRsIssuers) {
-                    const int c = pr / nr, i = pr - c * nr;
-                    const uint32_t d_tmem = tmem_base + c * kRsSetW;
-                    const uint32_t xrow = xs0 + (c * p.nr + i) * xpitch_b;
+                    const int u = pr / nr, i = pr - u * nr;
+                    const uint32_t d_tmem = tmem_base + u * kRsSetW;
+                    const uint32_t xrow = xs0 + (u * p.nr + i) * upitch;
                     const uint32_t yrow = yreg + (4 * i + s) * ypitch_b;
-                    switch (ksteps) {
-                        case 1: rs_issue<1>(d_tmem, xrow, yrow, ypitch_b); break;
-                        case 2: rs_issue<2>(d_tmem, xrow, yrow, ypitch_b); break;
-                        case 3: rs_issue<3>(d_tmem, xrow, yrow, ypitch_b); break;
-                        case 4: rs_issue<4>(d_tmem, xrow, yrow, ypitch_b); break;
-                        case 5: rs_issue<5>(d_tmem, xrow, yrow, ypitch_b); break;
-                        case 6: rs_issue<6>(d_tmem, xrow, yrow, ypitch_b); break;
-                        case 7: rs_issue<7>(d_tmem, xrow, yrow, ypitch_b); break;
-                        default: rs_issue<8>(d_tmem, xrow, yrow, ypitch_b); break;
-                    }
+                    if (p.UC == 1) rs_issue_k<1>(ksteps, d_tmem, xrow, yrow, ypitch_b);
+                    else if (p.UC == 2) rs_issue_k<2>(ksteps, d_tmem, xrow, yrow, ypitch_b);
+                    else rs_issue_k<4>(ksteps, d_tmem, xrow, yrow, ypitch_b);
                 }
                 umma_commit(&emptyx[kx % kRsXSlots]);
                 // plane q = s is dead after this step; its barrier slot is the one of load (ky - 3)
@@ -277,24 +306,29 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
         umma_commit(done);
     }
     __syncwarp();
-    if (warp < 2 && blockIdx.x < items) {
+    if (warp < 3 && blockIdx.x < items) {
         // =============================== epilogue: TMEM -> fp32 atomics into dw ===============================
         mbar_wait(done, 0, err, 45);
         tc_fence_after();
-        // M = 64 accumulator layout: row m lives in lane (m % 16) + 32 * (m / 16); m = kw * 8 + ci
-        const int m = lane < 16 ? warp * 16 + lane : 64;
-        const int kw = m >> 3, ci = m & 7;
+        // accumulator row m = kw * (8 UC) + channel within the unit.  M = 64 (UC = 1, 2): row m lives in lane (m % 16) + 32 * (m / 16);
+        // M = 128 (UC = 4): row m lives in lane m.
+        const int m = p.UC == 4 ? warp * 32 + lane : (lane < 16 ? warp * 16 + lane : 64);
+        const int uw = 8 * p.UC;
+        const int kw = m / uw, cc = m - kw * uw;
         const int cin = p.C0 + p.C1;
         const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int c = 0; c < nch; ++c) {
+        const int nunits = (nch + p.UC - 1) / p.UC;
+        for (int u = 0; u < nunits; ++u) {
+            const int ch = ch0 + u * p.UC + (cc >> 3);
+            const bool valid = kw < 3 && ch < ch0 + nch;
             for (int a = 0; a < 3; ++a) {
                 for (int dq = 0; dq < 3; ++dq) {                            // N-group 4a + dq: dy row h-1+a of plane d-1+dq
                     float v[8];
-                    tmem_ld8(tlane + c * kRsSetW + (4 * a + dq) * 8, v);
+                    tmem_ld8(tlane + u * kRsSetW + (4 * a + dq) * 8, v);
                     tmem_wait_ld();
-                    if (m < 24) {
+                    if (valid) {
                         const int tap = ((2 - dq) * 3 + (2 - a)) * 3 + kw;
-                        float* dst = dw + (((size_t)g * 27 + tap) * cin + (ch0 + c) * 8 + ci) * p.Cout + cochunk * 8;
+                        float* dst = dw + (((size_t)g * 27 + tap) * cin + ch * 8 + (cc & 7)) * p.Cout + cochunk * 8;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) atomicAdd(dst + q, v[q]);
                     }
@@ -327,16 +361,19 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     p.reflect = d->pad_mode == PB_PAD_REFLECT;
     p.KW = (p.W + 15) & ~15;
     if (p.KW > 128) return PB_EUNSUPPORTED;
-    // measured (scripts/bench_wgrad.py, profiles/r02_wgrad_rs.txt): 1.2-1.5x faster than the kh-stacked kernels at 80^3 and 40^3; at 20^3
-    // and below a launch is a few items per CTA and the per-item prologue (three dy planes) dominates: those stay on the old kernels
-    if ((long long)p.D * p.H * p.W < env_int("PB_WG_RS_MIN_VOX", 48000)) return PB_EUNSUPPORTED;
+    // measured (scripts/bench_wgrad.py, profiles/r02_wgrad_rs_classes.txt): 1.2-2.1x faster than the kh-stacked kernels from 20^3 up; at
+    // 10^3 a launch is a handful of items and the per-item prologue (three dy planes) dominates: those stay on the old kernels
+    if ((long long)p.D * p.H * p.W < env_int("PB_WG_RS_MIN_VOX", 4000)) return PB_EUNSUPPORTED;
     p.npg = d->n / d->groups; p.groups = d->groups;
     p.nT = (d->c0 + d->c1) / 8;
     p.nP = d->cout / 8;
     p.TG = p.nT < kRsMaxChunks ? p.nT : kRsMaxChunks;
     p.ntg = (p.nT + p.TG - 1) / p.TG;
+    // chunks per MMA: 32- or 16-channel rows when the chunk count allows (PB_WG_RS_UC caps it)
+    p.UC = p.nT % 4 == 0 ? 4 : (p.nT % 2 == 0 ? 2 : 1);
+    { const int cap = env_int("PB_WG_RS_UC", 4); while (p.UC > cap) p.UC /= 2; }
     p.tmem_cols = 32;
-    while ((int)p.tmem_cols < p.TG * kRsSetW) p.tmem_cols *= 2;
+    while ((int)p.tmem_cols < (p.TG / p.UC) * kRsSetW) p.tmem_cols *= 2;
     p.h_lo = p.reflect ? -1 : 0; p.rows_t = p.reflect ? p.H + 2 : p.H;
     p.d_lo = p.reflect ? -1 : 0; p.planes_t = p.reflect ? p.D + 2 : p.D;
     if ((long long)p.H * p.W * (p.C0 > p.C1 ? p.C0 : p.C1) >= (1LL << 30)) return PB_EUNSUPPORTED;          // int offsets within a plane
@@ -345,11 +382,11 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     const int gy = p.groups * p.ntg * p.nP;
     const int ctas_max = 148 / gy < 1 ? 1 : 148 / gy;
     // rows per strip: bounded by the copy budget of the input-row producers and by shared memory
-    int nr = env_int("PB_WG_RS_ROWS", 8);
+    int nr = env_int("PB_WG_RS_ROWS", kRsMaxRows);
     if (nr > kRsMaxRows) nr = kRsMaxRows;
     if (nr > p.rows_t) nr = p.rows_t;
     auto smem_of = [&](int rows, int steps) {
-        return (size_t)p.nregions * (4 * (rows + 2) + steps + 2) * p.KW * 16 + (size_t)kRsXSlots * p.TG * rows * (p.KW + 8) * 16 + 256;
+        return (size_t)p.nregions * (4 * (rows + 2) + steps + 2) * p.KW * 16 + (size_t)kRsXSlots * p.TG * rows * (p.KW + 8) * 16 + 256 + 1024;
     };
     while (nr > 1 && (p.TG * nr * (p.KW + 8) > kRsXCopies * kRsXProducers || smem_of(nr, kRsMaxSteps) > 227 * 1024)) --nr;
     if (p.TG * nr * (p.KW + 8) > kRsXCopies * kRsXProducers || smem_of(nr, kRsMaxSteps) > 227 * 1024) return PB_EUNSUPPORTED;
@@ -376,7 +413,7 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     p.yrows = 4 * (p.nr + 2) + max_steps + 2;
     const int items = p.npg * p.nstrips * p.ND;
     const int ctas = items < ctas_max ? items : ctas_max;
-    const size_t smem = (size_t)p.nregions * p.yrows * p.KW * 16 + (size_t)kRsXSlots * p.TG * p.nr * (p.KW + 8) * 16 + (2 * kRsXSlots + 11) * 8 + 16;
+    const size_t smem = (size_t)p.nregions * p.yrows * p.KW * 16 + (size_t)kRsXSlots * p.TG * p.nr * (p.KW + 8) * 16 + (2 * kRsXSlots + 11) * 8 + 16 + 1024;
     if (smem > 227 * 1024) return PB_EUNSUPPORTED;
     // dense NDHWC dy seen as (8 ch of a chunk, W, H, Cout/8 chunks, N*D planes); box = one row of KW positions of one chunk
     CUtensorMap ymap;
