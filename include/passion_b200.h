@@ -114,6 +114,18 @@ int pb_conv3d_dgrad_reflect_fix(const pb_conv_desc* d, const void* dy, const flo
 int pb_conv1_tc_ntile(int cin, int cout);
 int pb_conv1_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias, void* y0, void* y1,
                 int co0, int co1, double* stats, int* err_flag, pb_stream_t stream);
+/* Token-path GEMM of the mmFormer transformer blocks on tcgen05 (csrc/gemm_tc.cu) — replaces torch.nn.Linear of SelfAttention
+ * (qkv, proj) and FeedForward, reference models/mmformer.py:192-280, forward and both gradients:
+ *     D[m][n] = sum_k A(m,k) * B(n,k) (+ bias[n]),   bf16 operands, fp32 accumulation, D bf16 (d_fp32 = 0) or fp32 (1), ldd elements per row.
+ * a_kmajor = 1: A is stored [M][K] (lda elements between rows); 0: A is stored [K][M] (A(m,k) at a[k*lda + m]); b likewise with N.
+ *     forward  Y = X W^T + b : A = X (1), B = W [N][K] (1);   dX = dY W : A = dY (1), B = W read as [K = N'][K'] (0);
+ *     dW = dY^T X : A = dY read as [K = M][N'] (0), B = X read as [K = M][K'] (0), D fp32.
+ * lda, ldb multiples of 8, operands 16-byte aligned.  err_flag as in pb_conv3d_tc.  Outputs with few tiles and a long K run split-K:
+ * pb_gemm_tc_workspace_floats(M, N, K) > 0 is the size of the ZERO-FILLED fp32 workspace the call then needs (partials are added
+ * with atomics, a second small launch adds the bias and converts); otherwise workspace may be NULL. */
+long long pb_gemm_tc_workspace_floats(int M, int N, int K);
+int pb_gemm_tc(const void* a, const void* b, const float* bias, void* d, float* workspace, int M, int N, int K, int lda, int ldb,
+               int ldd, int a_kmajor, int b_kmajor, int d_fp32, int* err_flag, pb_stream_t stream);
 int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, void* y0, void* y1, int co0, int co1,
                       void* yext, int* err_flag, pb_stream_t stream);
 int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int d, int h, int w, int co0, int co1, pb_stream_t stream);

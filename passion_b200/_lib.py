@@ -71,6 +71,8 @@ def load():
     lib.pb_last_error.restype = ctypes.c_char_p
     lib.pb_launch_count.restype = ctypes.c_longlong
     lib.pb_weight_batch_table_bytes.restype = ctypes.c_size_t
+    lib.pb_gemm_tc_workspace_floats.restype = ctypes.c_longlong
+    lib.pb_gemm_tc_workspace_floats.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.pb_weight_batch_table_bytes.argtypes = [ctypes.c_int]
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
     cd = ctypes.POINTER(ConvDesc)
@@ -86,6 +88,7 @@ def load():
         "pb_conv3d_tc_full": [cd, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pb_reflect_fold": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "pb_conv3d_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
+        "pb_gemm_tc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
         "pb_conv1_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv3d_dgrad_reflect_fix": [cd, vp, vp, vp, vp, vp],
         "pb_conv3d_small_supported": [i32, i32],

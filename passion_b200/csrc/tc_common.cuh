@@ -125,6 +125,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda: the library must still
 // load on a machine without a driver, where only the symbol check runs)
 inline EncodeTiledFn encode_tiled() {
+    // cuTensorMapEncodeTiled is a driver call: it needs the device's primary context to be current in THIS thread.  Autograd runs
+    // backward on its own thread, where no runtime call may have bound it yet (CUDA_ERROR_INVALID_CONTEXT otherwise).
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
     static EncodeTiledFn fn = [] {
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult q;

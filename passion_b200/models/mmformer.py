@@ -238,7 +238,8 @@ class Transformer(nn.Module):
         p = self.dropout_rate if self.training else 0.0
 
         def lin(t, layer):
-            return F.linear(t, layer.weight.to(dt), None if layer.bias is None else layer.bias.to(dt))
+            # nn.Linear of qkv / proj / FFN (mmformer.py:201,214,270-276): tcgen05 GEMM in bf16 (ops.linear), library GEMM in the fp32 check mode
+            return ops.linear(t, layer.weight, layer.bias)
 
         def ln(t, layer):
             return F.layer_norm(t.float(), (t.shape[-1],), layer.weight, layer.bias, layer.eps).to(dt)

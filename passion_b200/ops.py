@@ -1242,3 +1242,70 @@ class _ProtoSums(torch.autograd.Function):
 
 def proto_sums(fs, ft, labels, cnt, eps=1e-5):
     return _ProtoSums.apply(fs, ft.detach(), labels, cnt, eps)
+
+
+# ------------------------------------------------------------------------------------ token-path GEMMs (mmFormer transformer)
+LINEAR_TC = os.environ.get("PB_LINEAR_TC", "1") != "0"
+
+
+def _gemm_tc(name, a, b, bias, out, M, N, K, lda, ldb, a_kmajor, b_kmajor):
+    lib = _lib.load()
+    err = _tc_err_flag(a.device)
+    nws = int(lib.pb_gemm_tc_workspace_floats(M, N, K))
+    ws = _scratch.zeros((nws,), torch.float32, a.device) if nws else None          # split-K partial sums (zero arena)
+    _run(name, f"m{M} n{N} k{K}", (M * K + N * K) * 2 + M * N * out.element_size(), 2.0 * M * N * K,
+         lambda: lib.pb_gemm_tc(_p(a), _p(b), _p(bias), _p(out), _p(ws), M, N, K, lda, ldb, out.stride(0), int(a_kmajor), int(b_kmajor),
+                                int(out.dtype == torch.float32), _p(err), _stream()))
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM (csrc/gemm_tc.cu): x [M, K] bf16, W [N, K] fp32 parameter (multiplied as bf16, like the
+    conv kernels do), b [N] fp32 or None.  Backward: dx = dy W and dW = dy^T x through the same kernel (operands read in place,
+    MN-major where the reduction runs over rows), db = column sums of dy."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        M, K = x.shape
+        N = w.shape[0]
+        wq = w.detach().to(torch.bfloat16).contiguous()
+        y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+        _gemm_tc("linear_fwd", x, wq, None if b is None else b.detach().float().contiguous(), y, M, N, K, K, K, True, True)
+        ctx.save_for_backward(x, wq)
+        ctx.has_bias = b is not None
+        ctx.w_dtype = w.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wq = ctx.saved_tensors
+        M, K = x.shape
+        N = wq.shape[0]
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
+            # D[m][k'] = sum_n dy[m][n] W[n][k']: A = dy K-major, B = W [N][K] read as [reduction = N][rows = K]
+            _gemm_tc("linear_dgrad", dy, wq, None, dx, M, K, N, N, K, True, False)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((N, K), dtype=torch.float32, device=x.device)
+            # D[n][k'] = sum_m dy[m][n] x[m][k']: both operands read as [reduction = M][rows]
+            _gemm_tc("linear_wgrad", dy, x, None, dw, N, K, M, N, K, False, False)
+            dw = dw.to(ctx.w_dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)
+        return dx, dw, db
+
+
+def linear_tc_eligible(x, weight):
+    return (LINEAR_TC and TC_ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
+            and weight.shape[1] % 8 == 0)
+
+
+def linear(x, weight, bias=None):
+    """torch.nn.functional.linear for the transformer token path: bf16 activations run on the tcgen05 GEMM, anything else
+    (the fp32 check mode) on the library GEMM."""
+    if not linear_tc_eligible(x, weight):
+        return torch.nn.functional.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
+    shp = x.shape
+    y = _LinearTC.apply(x.reshape(-1, shp[-1]).contiguous(), weight, bias)
+    return y.view(*shp[:-1], weight.shape[0])
