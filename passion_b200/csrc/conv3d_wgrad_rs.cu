@@ -48,11 +48,12 @@ struct RsP {
     int nr;                                // input rows per strip
     int nstrips, ND, npg, groups, nT, nP, TG, ntg;   // TG input chunks per CTA, ntg chunk groups
     int h_lo, rows_t, d_lo, planes_t;      // padded input rows / planes that contribute: [-1, H] for reflect, [0, H) for zero padding
-    int yrows, nregions;                   // rows of one diagonal dy buffer region; regions (2: the first planes of the next item load while this one computes)
+    int yrows, nregions;                   // rows of one diagonal dy buffer region; regions (2: one per item of a pair)
     int dbg;                               // developer probes: 2 = no MMAs, 3 = no input-row copies (results are garbage)
     uint32_t tmem_cols;
     int UC;                                // input chunks per MMA ("unit"): 1 = plain rows, 2 = 16-channel rows (SWIZZLE_32B), 4 = 32-channel rows (SWIZZLE_64B)
     int prefetch;                          // dy planes ahead to prefetch into L2 (0 = off)
+    int ybulk;                             // 1: dy rows are contiguous (Cout = 8, W % 16 == 0) and fetched by plain bulk copies
 };
 
 __device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
@@ -75,6 +76,21 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
         }
     }
     __syncwarp();
+}
+
+struct RsItem { int n, hs, nr, dx0, nsteps; };       // sample, first padded input row, rows, first padded plane, planes (0 = no such item)
+
+__device__ __forceinline__ RsItem rs_item(const RsP& p, int it, int items, int g) {
+    RsItem r;
+    if (it >= items) { r.n = 0; r.hs = 0; r.nr = 0; r.dx0 = 0; r.nsteps = 0; return r; }
+    const int dc = it % p.ND, r1 = it / p.ND;
+    const int st = r1 % p.nstrips;
+    r.n = g * p.npg + r1 / p.nstrips;
+    r.hs = p.h_lo + (st * p.rows_t) / p.nstrips;
+    r.nr = p.h_lo + ((st + 1) * p.rows_t) / p.nstrips - r.hs;
+    r.dx0 = p.d_lo + (dc * p.planes_t) / p.ND;
+    r.nsteps = p.d_lo + ((dc + 1) * p.planes_t) / p.ND - r.dx0;
+    return r;
 }
 
 // A operand of one input row for a unit of UC chunks, MN-major (cute canonical layouts, T = 8 elements = 16 B):
@@ -116,7 +132,7 @@ __device__ __forceinline__ void rs_issue_k(int ksteps, uint32_t d_tmem, uint32_t
 
 __global__ void __launch_bounds__(kRsThreads, 1)
 conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf16* __restrict__ x0, const bf16* __restrict__ x1,
-                      float* __restrict__ dw, int* err) {
+                      const bf16* __restrict__ dy, float* __restrict__ dw, int* err) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int ypitch_b = p.KW * 16;
     const int xpitch_b = (p.KW + 8) * 16;
@@ -131,8 +147,8 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
     uint64_t* fullx = bars;
     uint64_t* emptyx = bars + kRsXSlots;
     uint64_t* fully = bars + 2 * kRsXSlots;
-    uint64_t* emptyy = fully + 4;
-    uint64_t* item_done = emptyy + 4;                  // [2]: one per dy buffer region
+    uint64_t* emptyy = fully + 8;                       // fully / emptyy: [2 items of a pair][4 plane slots]
+    uint64_t* item_done = emptyy + 8;                  // [2]: one per dy buffer region
     uint64_t* done = item_done + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
@@ -145,7 +161,7 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kRsXSlots; ++i) { mbar_init(&fullx[i], kRsXProducers); mbar_init(&emptyx[i], kRsIssuers); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&fully[i], 1); mbar_init(&emptyy[i], kRsIssuers); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&fully[i], 1); mbar_init(&emptyy[i], kRsIssuers); }
         mbar_init(&item_done[0], kRsIssuers);
         mbar_init(&item_done[1], kRsIssuers);
         mbar_init(done, kRsIssuers);
@@ -168,6 +184,11 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
     __syncthreads();
     tc_fence_after();
 
+    // Work items are taken in PAIRS (items it and it + gridDim.x of this CTA's stream) whose steps are interleaved: A.0, B.0, A.1, B.1, ...
+    // Each of the two has its own dy buffer region and plane barriers.  The copy of a plane can only start when the MMAs of the
+    // step that last read the plane it overwrites have retired; interleaving puts three steps of other work between that moment
+    // and the step that needs the new plane (one step was not enough: ncu showed the issuers spinning on the dy `full` barrier).
+    const int pair_stride = 2 * gridDim.x;
     if (warp < 8) {
         // =============================== input-row producers (run ahead of the MMAs by up to kRsXSlots steps) ===============
         const int pt = threadIdx.x;
@@ -175,132 +196,173 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
         const int xrow_e = p.KW + 8;
         const int per_chunk = p.nr * xrow_e;
         uint32_t kx = 0;
-        for (int it = blockIdx.x; it < items; it += gridDim.x) {
-            const int dc = it % p.ND, r1 = it / p.ND;
-            const int st = r1 % p.nstrips, n = g * p.npg + r1 / p.nstrips;
-            const int hs = p.h_lo + (st * p.rows_t) / p.nstrips;                 // first padded input row of the strip
-            const int nr = p.h_lo + ((st + 1) * p.rows_t) / p.nstrips - hs;
-            const int dx0 = p.d_lo + (dc * p.planes_t) / p.ND;
-            const int dx1 = p.d_lo + ((dc + 1) * p.planes_t) / p.ND;             // exclusive
-            int xoff[kRsXCopies];                                               // -2: nothing to copy, -1: zero fill, else offset in the plane
-            uint32_t xdst[kRsXCopies];
+        for (int it0 = blockIdx.x; it0 < items; it0 += pair_stride) {
+            int xoff[2][kRsXCopies];                                            // -2: nothing to copy, -1: zero fill, else offset in the plane
+            uint32_t xdst[kRsXCopies];                                          // (same for both items: they differ in rows, not in layout)
             uint32_t src1 = 0;                                                  // bit i: copy i reads the second source
+            int nsteps[2], dxs[2], ns[2];
 #pragma unroll
-            for (int i = 0; i < kRsXCopies; ++i) {
-                const int e = pt + i * kRsXProducers;
-                xoff[i] = -2;
-                xdst[i] = 0;
-                if (e < nch * per_chunk) {
-                    const int c = e / per_chunk, rem = e - c * per_chunk;
-                    const int r = rem / xrow_e, t = rem - r * xrow_e;
-                    if (r < nr) {
+            for (int k = 0; k < 2; ++k) {
+                const RsItem im = rs_item(p, it0 + k * (int)gridDim.x, items, g);
+                nsteps[k] = im.nsteps; dxs[k] = im.dx0; ns[k] = im.n;
+#pragma unroll
+                for (int i = 0; i < kRsXCopies; ++i) {
+                    const int e = pt + i * kRsXProducers;
+                    xoff[k][i] = -2;
+                    if (k == 0) xdst[i] = 0;
+                    if (e < nch * per_chunk) {
+                        const int c = e / per_chunk, rem = e - c * per_chunk;
+                        const int r = rem / xrow_e, t = rem - r * xrow_e;
                         const int ch = ch0 + c;
                         const bool from1 = ch >= c0ch;
-                        const int cs = from1 ? p.C1 : p.C0, coff = (from1 ? ch - c0ch : ch) * 8;
-                        int h = hs + r, w = t - 1;
-                        bool ok;
-                        if (p.reflect) { ok = w >= -1 && w <= p.W; h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); }
-                        else ok = w >= 0 && w < p.W;
-                        xoff[i] = ok ? (h * p.W + w) * cs + coff : -1;
                         // unit u = c / UC holds UC chunks side by side: [row][position][UC x 16 B], 16-byte units swizzled
                         const int u = c / p.UC, cu = c - u * p.UC;
                         const int sw = p.UC == 1 ? 0 : (p.UC == 2 ? ((t >> 2) & 1) : ((t >> 1) & 3));
                         xdst[i] = (uint32_t)(((u * p.nr + r) * xrow_e + t) * 16 * p.UC + ((cu ^ sw) * 16));
                         if (from1) src1 |= 1u << i;
+                        if (r < im.nr) {
+                            const int cs = from1 ? p.C1 : p.C0, coff = (from1 ? ch - c0ch : ch) * 8;
+                            int h = im.hs + r, w = t - 1;
+                            bool ok;
+                            if (p.reflect) { ok = w >= -1 && w <= p.W; h = reflect_idx(h, p.H); w = reflect_idx(w, p.W); }
+                            else ok = w >= 0 && w < p.W;
+                            xoff[k][i] = ok ? (h * p.W + w) * cs + coff : -1;
+                        }
                     }
                 }
             }
-            for (int dx = dx0; dx < dx1; ++dx, ++kx) {
-                const int slot = kx % kRsXSlots;
-                mbar_wait_warp(&emptyx[slot], ((kx / kRsXSlots) & 1) ^ 1, lane, err, 42);
-                const int dpx = p.reflect ? reflect_idx(dx, p.D) : dx;
-                const size_t pl = ((size_t)n * p.D + dpx) * p.H * p.W;
-                const bf16* pp0 = x0 + pl * p.C0;
-                const bf16* pp1 = x1 + pl * p.C1;
-                const uint32_t sbase = smem_u32(x_s) + (uint32_t)(slot * xslot_bytes);
+            const int smax = nsteps[0] > nsteps[1] ? nsteps[0] : nsteps[1];
+            for (int s = 0; s < smax; ++s) {
 #pragma unroll
-                for (int i = 0; i < kRsXCopies; ++i) {
-                    if (xoff[i] != -2 && p.dbg != 3) {
-                        const bool ok = xoff[i] >= 0;
-                        const bf16* src = ((src1 >> i) & 1u) ? pp1 : pp0;
-                        cp_async16(sbase + xdst[i], ok ? src + xoff[i] : x0, ok ? 16u : 0u);
+                for (int k = 0; k < 2; ++k) {
+                    if (s >= nsteps[k]) continue;
+                    const int slot = kx % kRsXSlots;
+                    mbar_wait_warp(&emptyx[slot], ((kx / kRsXSlots) & 1) ^ 1, lane, err, 42);
+                    const int dx = dxs[k] + s;
+                    const int dpx = p.reflect ? reflect_idx(dx, p.D) : dx;
+                    const size_t pl = ((size_t)ns[k] * p.D + dpx) * p.H * p.W;
+                    const bf16* pp0 = x0 + pl * p.C0;
+                    const bf16* pp1 = x1 + pl * p.C1;
+                    const uint32_t sbase = smem_u32(x_s) + (uint32_t)(slot * xslot_bytes);
+#pragma unroll
+                    for (int i = 0; i < kRsXCopies; ++i) {
+                        if (xoff[k][i] != -2 && p.dbg != 3) {
+                            const bool ok = xoff[k][i] >= 0;
+                            const bf16* src = ((src1 >> i) & 1u) ? pp1 : pp0;
+                            cp_async16(sbase + xdst[i], ok ? src + xoff[k][i] : x0, ok ? 16u : 0u);
+                        }
                     }
+                    cp_async_arrive_noinc(&fullx[slot]);
+                    ++kx;
                 }
-                cp_async_arrive_noinc(&fullx[slot]);
             }
         }
         cp_async_wait_all();
     } else if (warp == 8) {
-        // =============================== dy-row producer: one TMA box [KW positions][8 ch] per row, one row per lane ============
-        // (a single thread issuing the rows one after the other made the load of a plane take ~2.8 us — longer than a step)
+        // =============================== dy-row producer (one warp, one row per lane) ===============================
         const uint32_t plane_bytes = (uint32_t)((p.nr + 2) * ypitch_b);
-        uint32_t ky = 0, kitem = 0;
-        for (int it = blockIdx.x; it < items; it += gridDim.x, ++kitem) {
-            const int dc = it % p.ND, r1 = it / p.ND;
-            const int st = r1 % p.nstrips, n = g * p.npg + r1 / p.nstrips;
-            const int hs = p.h_lo + (st * p.rows_t) / p.nstrips;
-            const int dx0 = p.d_lo + (dc * p.planes_t) / p.ND;
-            const int dx1 = p.d_lo + ((dc + 1) * p.planes_t) / p.ND;
-            // the diagonal buffer restarts at q = 0 with every item, alternating between the regions: the MMAs of the item that
-            // used this region last must have drained
-            const uint32_t region = kitem % p.nregions, use = kitem / p.nregions;
-            if (use > 0) mbar_wait_warp(&item_done[region], (use - 1) & 1, lane, err, 40);
-            // planes dx0-1 .. dx1 (q = 0 .. nsteps+1); plane q may land once plane q-4 is dead.  Always nr + 2 rows (a shorter
-            // strip leaves the last rows unused) so that a plane is a fixed number of bytes.
-            for (int dp = dx0 - 1, q = 0; dp <= dx1; ++dp, ++q, ++ky) {
-                const int slot = ky & 3;
-                mbar_wait_warp(&emptyy[slot], ((ky >> 2) & 1) ^ 1, lane, err, 41);
-                const bool plane_ok = dp >= 0 && dp < p.D;
-                const uint32_t ybase = smem_u32(y_s) + region * (uint32_t)yregion_bytes + (uint32_t)(q * ypitch_b);
-                if (lane == 0) mbar_expect_tx(&fully[slot], plane_bytes);
-                __syncwarp();
-                if (lane < p.nr + 2)
-                    tma_load_5d(ybase + (uint32_t)(lane * 4 * ypitch_b), &ymap, 0, 0, plane_ok ? hs - 1 + lane : p.H + 8, cochunk,
-                                plane_ok ? n * p.D + dp : 0, &fully[slot]);
-                const int dpf = dp + p.prefetch, hpf = hs - 1 + lane;
-                if (p.prefetch && lane < p.nr + 2 && dpf >= 0 && dpf < p.D && dpf <= dx1 && hpf >= 0 && hpf < p.H)
-                    tma_prefetch_5d(&ymap, 0, 0, hpf, cochunk, n * p.D + dpf);
+        uint32_t ky[2] = {0, 0}, kpair = 0;
+        for (int it0 = blockIdx.x; it0 < items; it0 += pair_stride, ++kpair) {
+            RsItem im[2];
+            im[0] = rs_item(p, it0, items, g);
+            im[1] = rs_item(p, it0 + (int)gridDim.x, items, g);
+            // the diagonal buffer of a region restarts at q = 0 with every item: the MMAs of the item that used it last must have drained
+            const int smax = im[0].nsteps > im[1].nsteps ? im[0].nsteps : im[1].nsteps;
+            // planes dx0-1 .. dx0+nsteps (q = 0 .. nsteps+1) of each item: q = 0, 1, 2 with its step 0, then one per step; plane q
+            // may land once plane q-4 is dead.  Always nr + 2 rows (a shorter strip leaves the last rows unused).
+            for (int s = 0; s < smax; ++s) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (s >= im[k].nsteps) continue;
+                    if (s == 0 && kpair > 0) mbar_wait_warp(&item_done[k], (kpair - 1) & 1, lane, err, 40);
+                    for (int q = (s == 0 ? 0 : s + 2); q <= s + 2; ++q, ++ky[k]) {
+                        const int dp = im[k].dx0 - 1 + q;
+                        const int slot = ky[k] & 3;
+                        uint64_t* full_b = &fully[4 * k + slot];
+                        mbar_wait_warp(&emptyy[4 * k + slot], ((ky[k] >> 2) & 1) ^ 1, lane, err, 41);
+                        const bool plane_ok = dp >= 0 && dp < p.D;
+                        const uint32_t ybase = smem_u32(y_s) + (uint32_t)k * (uint32_t)yregion_bytes + (uint32_t)(q * ypitch_b);
+                        const int n = im[k].n, hs = im[k].hs;
+                        if (p.ybulk) {
+                            // Cout = 8 and W a multiple of 16: a dy row is W * 16 contiguous bytes — one bulk copy per row and lane
+                            // instead of a tensor box of W 16-byte rows.  Rows outside the volume are zero-filled by the warp itself.
+                            const int h = hs - 1 + lane;
+                            const bool row_ok = plane_ok && lane < p.nr + 2 && h >= 0 && h < p.H;
+                            const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+                            unsigned zmask = ~okmask & ((p.nr + 2 >= 32) ? 0xffffffffu : ((1u << (p.nr + 2)) - 1u));
+                            while (zmask) {
+                                const int r = __ffs(zmask) - 1;
+                                zmask &= zmask - 1;
+                                uint4* dst = reinterpret_cast<uint4*>(y_s + k * (size_t)yregion_bytes + (size_t)(q + 4 * r) * ypitch_b);
+                                for (int i = lane; i < p.KW; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
+                            }
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_expect_tx(full_b, (uint32_t)__popc(okmask) * (uint32_t)ypitch_b);
+                            __syncwarp();
+                            if (row_ok)
+                                bulk_g2s(ybase + (uint32_t)(lane * 4 * ypitch_b), dy + (((size_t)n * p.D + dp) * p.H + h) * p.W * 8,
+                                         (uint32_t)ypitch_b, full_b);
+                        } else {
+                            // one TMA box [KW positions][8 ch] per row; rows, planes and the K tail outside the volume are zero fill
+                            if (lane == 0) mbar_expect_tx(full_b, plane_bytes);
+                            __syncwarp();
+                            if (lane < p.nr + 2)
+                                tma_load_5d(ybase + (uint32_t)(lane * 4 * ypitch_b), &ymap, 0, 0, plane_ok ? hs - 1 + lane : p.H + 8, cochunk,
+                                            plane_ok ? n * p.D + dp : 0, full_b);
+                        }
+                    }
+                }
             }
         }
     } else if (lane == 0) {
         // =============================== MMA issuers (warps 9-11) ===============================
         // One thread cannot issue faster than one MMA per ~62 cycles and the pipe retires one in 44: every issuer walks all steps
-        // (it must see every `full` phase before it may arrive on the matching `empty`) and issues every third (chunk, row) pair.
+        // (it must see every `full` phase before it may arrive on the matching `empty`) and issues every third (unit, row) pair.
         const int issuer = warp - 9;
         const uint32_t x_addr = smem_u32(x_s), y_addr = smem_u32(y_s);
         const int ksteps = p.KW >> 4;
-        uint32_t kx = 0, ky = 0, kitem = 0;
-        for (int it = blockIdx.x; it < items; it += gridDim.x, ++kitem) {
-            const int dc = it % p.ND, r1 = it / p.ND;
-            const int st = r1 % p.nstrips;
-            const int nr = ((st + 1) * p.rows_t) / p.nstrips - (st * p.rows_t) / p.nstrips;
-            const int nsteps = ((dc + 1) * p.planes_t) / p.ND - (dc * p.planes_t) / p.ND;
-            const uint32_t region = kitem % p.nregions;
-            const uint32_t yreg = y_addr + region * (uint32_t)yregion_bytes;
-            for (int s = 0; s < nsteps; ++s, ++kx) {
-                // step s reads planes q = s, s+1, s+2: three new ones at the start of an item, one per step afterwards
-                const int nl = s == 0 ? 3 : 1;
-                for (int l = 0; l < nl; ++l, ++ky) mbar_wait(&fully[ky & 3], (ky >> 2) & 1, err, 43);
-                mbar_wait(&fullx[kx % kRsXSlots], (kx / kRsXSlots) & 1, err, 44);
-                fence_proxy_async();
-                tc_fence_after();
-                const uint32_t xs0 = x_addr + (kx % kRsXSlots) * xslot_bytes;
-                const int nunits = (nch + p.UC - 1) / p.UC;
-                const int npairs = p.dbg == 2 ? 0 : nunits * nr;
-                const uint32_t upitch = (uint32_t)xpitch_b * p.UC;         // bytes of one row of a unit
-                for (int pr = issuer; pr < npairs; pr += kRsIssuers) {
-                    const int u = pr / nr, i = pr - u * nr;
-                    const uint32_t d_tmem = tmem_base + u * kRsSetW;
-                    const uint32_t xrow = xs0 + (u * p.nr + i) * upitch;
-                    const uint32_t yrow = yreg + (4 * i + s) * ypitch_b;
-                    if (p.UC == 1) rs_issue_k<1>(ksteps, d_tmem, xrow, yrow, ypitch_b);
-                    else if (p.UC == 2) rs_issue_k<2>(ksteps, d_tmem, xrow, yrow, ypitch_b);
-                    else rs_issue_k<4>(ksteps, d_tmem, xrow, yrow, ypitch_b);
+        uint32_t kx = 0, ky[2] = {0, 0};
+        for (int it0 = blockIdx.x; it0 < items; it0 += pair_stride) {
+            RsItem im[2];
+            im[0] = rs_item(p, it0, items, g);
+            im[1] = rs_item(p, it0 + (int)gridDim.x, items, g);
+            const int smax = im[0].nsteps > im[1].nsteps ? im[0].nsteps : im[1].nsteps;
+            for (int s = 0; s < smax; ++s) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (s >= im[k].nsteps) continue;
+                    // step s reads planes q = s, s+1, s+2: three new ones at the start of an item, one per step afterwards
+                    const int nl = s == 0 ? 3 : 1;
+                    for (int l = 0; l < nl; ++l, ++ky[k]) mbar_wait(&fully[4 * k + (ky[k] & 3)], (ky[k] >> 2) & 1, err, 43);
+                    mbar_wait(&fullx[kx % kRsXSlots], (kx / kRsXSlots) & 1, err, 44);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint32_t xs0 = x_addr + (kx % kRsXSlots) * xslot_bytes;
+                    const uint32_t yreg = y_addr + (uint32_t)k * (uint32_t)yregion_bytes;
+                    const int nr = im[k].nr;
+                    const int nunits = (nch + p.UC - 1) / p.UC;
+                    const int npairs = p.dbg == 2 ? 0 : nunits * nr;
+                    const uint32_t upitch = (uint32_t)xpitch_b * p.UC;         // bytes of one row of a unit
+                    for (int pr = issuer; pr < npairs; pr += kRsIssuers) {
+                        const int u = pr / nr, i = pr - u * nr;
+                        const uint32_t d_tmem = tmem_base + u * kRsSetW;
+                        const uint32_t xrow = xs0 + (u * p.nr + i) * upitch;
+                        const uint32_t yrow = yreg + (4 * i + s) * ypitch_b;
+                        if (p.UC == 1) rs_issue_k<1>(ksteps, d_tmem, xrow, yrow, ypitch_b);
+                        else if (p.UC == 2) rs_issue_k<2>(ksteps, d_tmem, xrow, yrow, ypitch_b);
+                        else rs_issue_k<4>(ksteps, d_tmem, xrow, yrow, ypitch_b);
+                    }
+                    umma_commit(&emptyx[kx % kRsXSlots]);
+                    ++kx;
+                    // plane q = s is dead after this step; its barrier slot is the one of load (ky - 3)
+                    umma_commit(&emptyy[4 * k + ((ky[k] - 3) & 3)]);
+                    if (s == im[k].nsteps - 1) {
+                        umma_commit(&emptyy[4 * k + ((ky[k] - 2) & 3)]);
+                        umma_commit(&emptyy[4 * k + ((ky[k] - 1) & 3)]);
+                        umma_commit(&item_done[k]);
+                    }
                 }
-                umma_commit(&emptyx[kx % kRsXSlots]);
-                // plane q = s is dead after this step; its barrier slot is the one of load (ky - 3)
-                umma_commit(&emptyy[(ky - 3) & 3]);
-                if (s == nsteps - 1) { umma_commit(&emptyy[(ky - 2) & 3]); umma_commit(&emptyy[(ky - 1) & 3]); umma_commit(&item_done[region]); }
             }
         }
         umma_commit(done);
@@ -378,7 +440,8 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     p.d_lo = p.reflect ? -1 : 0; p.planes_t = p.reflect ? p.D + 2 : p.D;
     if ((long long)p.H * p.W * (p.C0 > p.C1 ? p.C0 : p.C1) >= (1LL << 30)) return PB_EUNSUPPORTED;          // int offsets within a plane
     p.prefetch = env_int("PB_WG_RS_PREFETCH", 0);
-    p.nregions = env_int("PB_WG_RS_REGIONS", 2) >= 2 ? 2 : 1;
+    p.ybulk = (p.Cout == 8 && p.KW == p.W && env_int("PB_WG_RS_YBULK", 1)) ? 1 : 0;
+    p.nregions = 2;                                               // one per item of a pair
     const int gy = p.groups * p.ntg * p.nP;
     const int ctas_max = 148 / gy < 1 ? 1 : 148 / gy;
     // rows per strip: bounded by the copy budget of the input-row producers and by shared memory
@@ -413,7 +476,7 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     p.yrows = 4 * (p.nr + 2) + max_steps + 2;
     const int items = p.npg * p.nstrips * p.ND;
     const int ctas = items < ctas_max ? items : ctas_max;
-    const size_t smem = (size_t)p.nregions * p.yrows * p.KW * 16 + (size_t)kRsXSlots * p.TG * p.nr * (p.KW + 8) * 16 + (2 * kRsXSlots + 11) * 8 + 16 + 1024;
+    const size_t smem = (size_t)p.nregions * p.yrows * p.KW * 16 + (size_t)kRsXSlots * p.TG * p.nr * (p.KW + 8) * 16 + (2 * kRsXSlots + 19) * 8 + 16 + 1024;
     if (smem > 227 * 1024) return PB_EUNSUPPORTED;
     // dense NDHWC dy seen as (8 ch of a chunk, W, H, Cout/8 chunks, N*D planes); box = one row of KW positions of one chunk
     CUtensorMap ymap;
@@ -430,6 +493,6 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     }
     cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { pb_set_error("conv3d_wgrad_rs: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
-    conv3_wgrad_rs_kernel<<<dim3(ctas, gy), kRsThreads, smem, st>>>(ymap, p, (const bf16*)x0, (const bf16*)x1, dw, err_flag);
+    conv3_wgrad_rs_kernel<<<dim3(ctas, gy), kRsThreads, smem, st>>>(ymap, p, (const bf16*)x0, (const bf16*)x1, (const bf16*)dy, dw, err_flag);
     return 0;
 }
