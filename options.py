@@ -7,7 +7,7 @@ import os
 
 def args_parser(argv=None):
     parser = argparse.ArgumentParser()
-    parser.add_argument('--model', default='rfnet', type=str, help='model name: rfnet | mmformer (both on the B200-native kernels)')
+    parser.add_argument('--model', default='mmformer', type=str, help='model name: rfnet | mmformer (both on the B200-native kernels); the reference default')
     parser.add_argument('-batch_size', '--batch_size', default=1, type=int, help='Batch size (per GPU)')
     parser.add_argument('--lr', default=2e-4, type=float, help='base learning rate')
     parser.add_argument('--weight_decay', default=1e-4, type=float)
@@ -16,7 +16,7 @@ def args_parser(argv=None):
     parser.add_argument('--region_fusion_start_epoch', default=0, type=int, help='warm-up epochs used in rfnet')
     # system
     parser.add_argument('--seed', default=1037, type=int, help='random seed')
-    parser.add_argument('--gpu', type=str, default='0', help='GPU to use (ignored under torchrun: one rank per GPU)')
+    parser.add_argument('--gpu', type=str, default='0', help="GPU to use (ignored under torchrun: one rank per GPU).  The one default that differs from the reference ('3', its author's box): it must exist on a one-GPU machine")
     # options
     parser.add_argument('--mask_type', default='idt', type=str, help='training settings: pdt idt or idt_drop')
     parser.add_argument('--use_pretrain', action='store_true', default=False, help='whether use pretrained model')
@@ -26,7 +26,7 @@ def args_parser(argv=None):
     parser.add_argument('--dataname', default='BraTS/BRATS2020', type=str)
     parser.add_argument('--datapath', default='BraTS/BRATS2020_Training_none_npy', type=str)
     parser.add_argument('--imbmrpath', default='BraTS/brats_split/Brats2020_imb_split_mr2468.csv', type=str, help='csv path')
-    parser.add_argument('--savepath', default='outputs/idt_mr2468_rfnet_passion', type=str, help='output path')
+    parser.add_argument('--savepath', default='outputs/idt_mr2468_mmformer_passion_bs1_epoch300_lr2e-4_temp4', type=str, help='output path')
     parser.add_argument('--resume', default=None, type=str, help='pretrained model path')
     parser.add_argument('--datarootPath', default=None, type=str, help='dataset root (default: ./datasets)')
     # additions (not in the reference)
