@@ -124,6 +124,8 @@ int pb_conv1_tc(const pb_conv_desc* d, const void* x0, const void* x1, const voi
  * pb_gemm_tc_workspace_floats(M, N, K) > 0 is the size of the ZERO-FILLED fp32 workspace the call then needs (partials are added
  * with atomics, a second small launch adds the bias and converts); otherwise workspace may be NULL. */
 long long pb_gemm_tc_workspace_floats(int M, int N, int K);
+/* developer probe of csrc/conv3d_wgrad_rs.cu (launches made with PB_WG_RS=5): issuer-thread cycle counters, read and cleared */
+int pb_wgrad_rs_debug(unsigned long long* out8);
 int pb_gemm_tc(const void* a, const void* b, const float* bias, void* d, float* workspace, int M, int N, int K, int lda, int ldb,
                int ldd, int a_kmajor, int b_kmajor, int d_fp32, int* err_flag, pb_stream_t stream);
 int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, void* y0, void* y1, int co0, int co1,

@@ -31,14 +31,14 @@
 
 namespace {
 
-constexpr int kRsThreads = 384;
+constexpr int kRsThreads = 416;            // warps 0-7 input rows, 8 dy rows, 9-12 MMA issuers
 constexpr int kRsXProducers = 256;         // warps 0-7
 constexpr int kRsXSlots = 3;
 constexpr int kRsXCopies = 8;              // 16-byte copies per x-producer thread and step
 constexpr int kRsMaxRows = 16;
 constexpr int kRsMaxSteps = 16;            // planes per work item (bounds the diagonal dy buffer)
 constexpr int kRsMaxChunks = 4;            // input chunks per CTA
-constexpr int kRsIssuers = 3;
+constexpr int kRsIssuers = 4;
 constexpr int kRsN = 88;                   // UMMA N: 11 dy row groups x 8 output channels
 constexpr int kRsSetW = 96;                // TMEM columns per input chunk
 
@@ -51,7 +51,9 @@ struct RsP {
     int yrows, nregions;                   // rows of one diagonal dy buffer region; regions (2: one per item of a pair)
     int dbg;                               // developer probes: 2 = no MMAs, 3 = no input-row copies (results are garbage)
     uint32_t tmem_cols;
-    int UC;                                // input chunks per MMA ("unit"): 1 = plain rows, 2 = 16-channel rows (SWIZZLE_32B), 4 = 32-channel rows (SWIZZLE_64B)
+    int UC;                                // 16-byte sub-units per position of a unit = CU chunks x RU rows: 1 plain rows, 2 SWIZZLE_32B, 4 SWIZZLE_64B
+    int CU, RU;                            // input chunks and input ROWS that share one MMA (the RU rows of a group sit side by side like channels)
+    int NN, setw;                          // UMMA N = 8 * (11 + 4 * (RU - 1)); TMEM columns per unit
     int prefetch;                          // dy planes ahead to prefetch into L2 (0 = off)
     int ybulk;                             // 1: dy rows are contiguous (Cout = 8, W % 16 == 0) and fetched by plain bulk copies
 };
@@ -77,6 +79,8 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
     }
     __syncwarp();
 }
+
+__device__ unsigned long long rs_dbg[8];            // developer probe (PB_WG_RS=5): cycles of issuer 0 spent waiting / issuing, summed over CTAs
 
 struct RsItem { int n, hs, nr, dx0, nsteps; };       // sample, first padded input row, rows, first padded plane, planes (0 = no such item)
 
@@ -107,26 +111,43 @@ __device__ __forceinline__ uint64_t rs_adesc(uint32_t addr) {
     else return umma_desc(addr, 64, 512) | (4ULL << 61);
 }
 
-template <int UC, int KS>
+template <int UC, int NN, int KS>
 __device__ __forceinline__ void rs_issue(uint32_t d_tmem, uint32_t xrow, uint32_t yrow, int ypitch_b) {
-    constexpr uint32_t IDESC = umma_idesc(UC == 4 ? 128 : 64, kRsN) | (1u << 15) | (1u << 16);      // both operands MN-major
+    constexpr uint32_t IDESC = umma_idesc(UC == 4 ? 128 : 64, NN) | (1u << 15) | (1u << 16);      // both operands MN-major
     const uint64_t a0 = rs_adesc<UC>(xrow);
     const uint64_t b0 = umma_desc(yrow, 128, (uint32_t)ypitch_b);
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) umma_f16(d_tmem, a0 + (uint64_t)(16 * UC * ks), b0 + (uint64_t)(16 * ks), IDESC, 1u);
 }
 
-template <int UC>
-__device__ __forceinline__ void rs_issue_k(int ksteps, uint32_t d_tmem, uint32_t xrow, uint32_t yrow, int ypitch_b) {
+// All MMAs one issuer contributes to a step: every kRsIssuers-th (unit, row) pair, KS instructions each.  Templated on the unit
+// width and the K-step count and free of divisions: the issuing threads are the bottleneck of this kernel (a thread needs ~65-75
+// cycles per instruction even with the descriptors in registers; with a division, a switch and the descriptor arithmetic per pair
+// ncu / clock64 probes showed 185).
+template <int UC, int NN, int KS>
+__device__ __forceinline__ void rs_issue_step(int issuer, int nunits, int ngr, int ngr_pitch, int ru, int setw, uint32_t tmem_base, uint32_t xs0,
+                                              uint32_t upitch, uint32_t yrow0, int ypitch_b) {
+    int u = 0, i = issuer;                                  // i = row GROUP (ru input rows per instruction)
+    while (i >= ngr) { i -= ngr; ++u; }
+    while (u < nunits) {
+        rs_issue<UC, NN, KS>(tmem_base + u * setw, xs0 + (u * ngr_pitch + i) * upitch, yrow0 + 4 * i * ru * ypitch_b, ypitch_b);
+        i += kRsIssuers;
+        while (i >= ngr) { i -= ngr; ++u; }
+    }
+}
+
+template <int UC, int NN>
+__device__ __forceinline__ void rs_issue_step_k(int ksteps, int issuer, int nunits, int ngr, int ngr_pitch, int ru, int setw, uint32_t tmem_base,
+                                                uint32_t xs0, uint32_t upitch, uint32_t yrow0, int ypitch_b) {
     switch (ksteps) {
-        case 1: rs_issue<UC, 1>(d_tmem, xrow, yrow, ypitch_b); break;
-        case 2: rs_issue<UC, 2>(d_tmem, xrow, yrow, ypitch_b); break;
-        case 3: rs_issue<UC, 3>(d_tmem, xrow, yrow, ypitch_b); break;
-        case 4: rs_issue<UC, 4>(d_tmem, xrow, yrow, ypitch_b); break;
-        case 5: rs_issue<UC, 5>(d_tmem, xrow, yrow, ypitch_b); break;
-        case 6: rs_issue<UC, 6>(d_tmem, xrow, yrow, ypitch_b); break;
-        case 7: rs_issue<UC, 7>(d_tmem, xrow, yrow, ypitch_b); break;
-        default: rs_issue<UC, 8>(d_tmem, xrow, yrow, ypitch_b); break;
+        case 1: rs_issue_step<UC, NN, 1>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
+        case 2: rs_issue_step<UC, NN, 2>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
+        case 3: rs_issue_step<UC, NN, 3>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
+        case 4: rs_issue_step<UC, NN, 4>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
+        case 5: rs_issue_step<UC, NN, 5>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
+        case 6: rs_issue_step<UC, NN, 6>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
+        case 7: rs_issue_step<UC, NN, 7>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
+        default: rs_issue_step<UC, NN, 8>(issuer, nunits, ngr, ngr_pitch, ru, setw, tmem_base, xs0, upitch, yrow0, ypitch_b); break;
     }
 }
 
@@ -215,11 +236,14 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
                         const int r = rem / xrow_e, t = rem - r * xrow_e;
                         const int ch = ch0 + c;
                         const bool from1 = ch >= c0ch;
-                        // unit u = c / UC holds UC chunks side by side: [row][position][UC x 16 B], 16-byte units swizzled
-                        const int u = c / p.UC, cu = c - u * p.UC;
+                        // unit u = c / CU; RU consecutive input rows form a row group whose rows sit side by side like channels:
+                        // [unit][row group][position][(row in group, chunk in unit) x 16 B], the 16-byte sub-units swizzled
+                        const int u = c / p.CU, cu = c - u * p.CU;
+                        const int rg = r / p.RU, rho = r - rg * p.RU;
                         const int sw = p.UC == 1 ? 0 : (p.UC == 2 ? ((t >> 2) & 1) : ((t >> 1) & 3));
-                        xdst[i] = (uint32_t)(((u * p.nr + r) * xrow_e + t) * 16 * p.UC + ((cu ^ sw) * 16));
+                        xdst[i] = (uint32_t)(((u * (p.nr / p.RU) + rg) * xrow_e + t) * 16 * p.UC + (((rho * p.CU + cu) ^ sw) * 16));
                         if (from1) src1 |= 1u << i;
+                        if (r >= im.nr && r < ((im.nr + p.RU - 1) / p.RU) * p.RU) xoff[k][i] = -1;      // pad of the last row group: zeros
                         if (r < im.nr) {
                             const int cs = from1 ? p.C1 : p.C0, coff = (from1 ? ch - c0ch : ch) * 8;
                             int h = im.hs + r, w = t - 1;
@@ -316,13 +340,15 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
             }
         }
     } else if (lane == 0) {
-        // =============================== MMA issuers (warps 9-11) ===============================
+        // =============================== MMA issuers (warps 9-12) ===============================
         // One thread cannot issue faster than one MMA per ~62 cycles and the pipe retires one in 44: every issuer walks all steps
-        // (it must see every `full` phase before it may arrive on the matching `empty`) and issues every third (unit, row) pair.
+        // (it must see every `full` phase before it may arrive on the matching `empty`) and issues every fourth (unit, row) pair.
         const int issuer = warp - 9;
         const uint32_t x_addr = smem_u32(x_s), y_addr = smem_u32(y_s);
         const int ksteps = p.KW >> 4;
         uint32_t kx = 0, ky[2] = {0, 0};
+        long long dbg_y0 = 0, dbg_y = 0, dbg_x = 0, dbg_issue = 0, dbg_steps = 0;
+        const long long dbg_t0 = clock64();
         for (int it0 = blockIdx.x; it0 < items; it0 += pair_stride) {
             RsItem im[2];
             im[0] = rs_item(p, it0, items, g);
@@ -334,25 +360,34 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
                     if (s >= im[k].nsteps) continue;
                     // step s reads planes q = s, s+1, s+2: three new ones at the start of an item, one per step afterwards
                     const int nl = s == 0 ? 3 : 1;
+                    const long long t0 = clock64();
                     for (int l = 0; l < nl; ++l, ++ky[k]) mbar_wait(&fully[4 * k + (ky[k] & 3)], (ky[k] >> 2) & 1, err, 43);
+                    const long long t1 = clock64();
                     mbar_wait(&fullx[kx % kRsXSlots], (kx / kRsXSlots) & 1, err, 44);
+                    const long long t2 = clock64();
                     fence_proxy_async();
                     tc_fence_after();
+                    if (s == 0) dbg_y0 += t1 - t0; else dbg_y += t1 - t0;
+                    dbg_x += t2 - t1;
                     const uint32_t xs0 = x_addr + (kx % kRsXSlots) * xslot_bytes;
                     const uint32_t yreg = y_addr + (uint32_t)k * (uint32_t)yregion_bytes;
                     const int nr = im[k].nr;
-                    const int nunits = (nch + p.UC - 1) / p.UC;
-                    const int npairs = p.dbg == 2 ? 0 : nunits * nr;
-                    const uint32_t upitch = (uint32_t)xpitch_b * p.UC;         // bytes of one row of a unit
-                    for (int pr = issuer; pr < npairs; pr += kRsIssuers) {
-                        const int u = pr / nr, i = pr - u * nr;
-                        const uint32_t d_tmem = tmem_base + u * kRsSetW;
-                        const uint32_t xrow = xs0 + (u * p.nr + i) * upitch;
-                        const uint32_t yrow = yreg + (4 * i + s) * ypitch_b;
-                        if (p.UC == 1) rs_issue_k<1>(ksteps, d_tmem, xrow, yrow, ypitch_b);
-                        else if (p.UC == 2) rs_issue_k<2>(ksteps, d_tmem, xrow, yrow, ypitch_b);
-                        else rs_issue_k<4>(ksteps, d_tmem, xrow, yrow, ypitch_b);
+                    const int nunits = nch / p.CU;
+                    const int ngr = (nr + p.RU - 1) / p.RU, ngr_pitch = p.nr / p.RU;
+                    const uint32_t upitch = (uint32_t)xpitch_b * p.UC;         // bytes of one row group of a unit
+                    const uint32_t yrow0 = yreg + s * ypitch_b;
+                    if (p.dbg != 2) {
+#define RS_GO(UC_, NN_) rs_issue_step_k<UC_, NN_>(ksteps, issuer, nunits, ngr, ngr_pitch, p.RU, p.setw, tmem_base, xs0, upitch, yrow0, ypitch_b)
+                        if (p.UC == 1) RS_GO(1, 88);
+                        else if (p.UC == 2 && p.RU == 1) RS_GO(2, 88);
+                        else if (p.UC == 2) RS_GO(2, 120);
+                        else if (p.RU == 1) RS_GO(4, 88);
+                        else if (p.RU == 2) RS_GO(4, 120);
+                        else RS_GO(4, 184);
+#undef RS_GO
                     }
+                    dbg_issue += clock64() - t2;
+                    ++dbg_steps;
                     umma_commit(&emptyx[kx % kRsXSlots]);
                     ++kx;
                     // plane q = s is dead after this step; its barrier slot is the one of load (ky - 3)
@@ -366,33 +401,44 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
             }
         }
         umma_commit(done);
+        if (p.dbg == 5 && issuer == 0) {
+            atomicAdd(&rs_dbg[0], (unsigned long long)dbg_y0); atomicAdd(&rs_dbg[1], (unsigned long long)dbg_y);
+            atomicAdd(&rs_dbg[2], (unsigned long long)dbg_x); atomicAdd(&rs_dbg[3], (unsigned long long)dbg_issue);
+            atomicAdd(&rs_dbg[4], (unsigned long long)dbg_steps); atomicAdd(&rs_dbg[5], (unsigned long long)(clock64() - dbg_t0));
+            atomicAdd(&rs_dbg[6], 1ULL);
+        }
     }
     __syncwarp();
-    if (warp < 3 && blockIdx.x < items) {
+    if (warp < 4 && blockIdx.x < items) {
         // =============================== epilogue: TMEM -> fp32 atomics into dw ===============================
         mbar_wait(done, 0, err, 45);
         tc_fence_after();
-        // accumulator row m = kw * (8 UC) + channel within the unit.  M = 64 (UC = 1, 2): row m lives in lane (m % 16) + 32 * (m / 16);
-        // M = 128 (UC = 4): row m lives in lane m.
+        // accumulator row m = kw * (8 UC) + (row in group * CU + chunk in unit) * 8 + channel.  M = 64 (UC = 1, 2): row m lives in lane
+        // (m % 16) + 32 * (m / 16); M = 128 (UC = 4): row m lives in lane m.  N-group 4 * rho + 4a + dq of the row with index rho in its
+        // group: dy row h-1+a of plane d-1+dq.
         const int m = p.UC == 4 ? warp * 32 + lane : (lane < 16 ? warp * 16 + lane : 64);
         const int uw = 8 * p.UC;
-        const int kw = m / uw, cc = m - kw * uw;
+        const int kw = m / uw, sub = (m - kw * uw) >> 3;
+        const int rho = sub / p.CU, cu = sub - rho * p.CU;
         const int cin = p.C0 + p.C1;
         const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int nunits = (nch + p.UC - 1) / p.UC;
+        const int nunits = nch / p.CU;
         for (int u = 0; u < nunits; ++u) {
-            const int ch = ch0 + u * p.UC + (cc >> 3);
-            const bool valid = kw < 3 && ch < ch0 + nch;
-            for (int a = 0; a < 3; ++a) {
-                for (int dq = 0; dq < 3; ++dq) {                            // N-group 4a + dq: dy row h-1+a of plane d-1+dq
-                    float v[8];
-                    tmem_ld8(tlane + u * kRsSetW + (4 * a + dq) * 8, v);
-                    tmem_wait_ld();
-                    if (valid) {
-                        const int tap = ((2 - dq) * 3 + (2 - a)) * 3 + kw;
-                        float* dst = dw + (((size_t)g * 27 + tap) * cin + ch * 8 + (cc & 7)) * p.Cout + cochunk * 8;
+            const int ch = ch0 + u * p.CU + cu;
+            const bool valid = kw < 3;
+            // (tcgen05.ld takes one column address per warp: walk the row-in-group index uniformly, the lanes it belongs to store)
+            for (int rr = 0; rr < p.RU; ++rr) {
+                for (int a = 0; a < 3; ++a) {
+                    for (int dq = 0; dq < 3; ++dq) {
+                        float v[8];
+                        tmem_ld8(tlane + u * p.setw + (4 * rr + 4 * a + dq) * 8, v);
+                        tmem_wait_ld();
+                        if (valid && rho == rr) {
+                            const int tap = ((2 - dq) * 3 + (2 - a)) * 3 + kw;
+                            float* dst = dw + (((size_t)g * 27 + tap) * cin + ch * 8 + (m & 7)) * p.Cout + cochunk * 8;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) atomicAdd(dst + q, v[q]);
+                            for (int q = 0; q < 8; ++q) atomicAdd(dst + q, v[q]);
+                        }
                     }
                 }
             }
@@ -409,6 +455,14 @@ conv3_wgrad_rs_kernel(const __grid_constant__ CUtensorMap ymap, RsP p, const bf1
 int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
 
 }  // namespace
+
+// developer probe: reads and clears the issuer-0 cycle counters gathered by launches with PB_WG_RS=5
+extern "C" int pb_wgrad_rs_debug(unsigned long long* out8) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, rs_dbg, sizeof(z)) != cudaSuccess) return PB_ECUDA;
+    if (cudaMemcpyToSymbol(rs_dbg, z, sizeof(z)) != cudaSuccess) return PB_ECUDA;
+    return PB_OK;
+}
 
 // Internal entry (called by pb_conv3d_wgrad_tc, which has validated the descriptor): PB_EUNSUPPORTED = class not covered, the
 // caller falls back to the kh-stacked kernels.
@@ -431,11 +485,21 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     p.nP = d->cout / 8;
     p.TG = p.nT < kRsMaxChunks ? p.nT : kRsMaxChunks;
     p.ntg = (p.nT + p.TG - 1) / p.TG;
-    // chunks per MMA: 32- or 16-channel rows when the chunk count allows (PB_WG_RS_UC caps it)
-    p.UC = p.nT % 4 == 0 ? 4 : (p.nT % 2 == 0 ? 2 : 1);
-    { const int cap = env_int("PB_WG_RS_UC", 4); while (p.UC > cap) p.UC /= 2; }
+    // chunks per MMA: 32- or 16-channel rows when the chunk count allows (PB_WG_RS_UC caps it); narrower units are filled up with
+    // RU consecutive input ROWS side by side (PB_WG_RS_RU caps it), so that an instruction always carries 32 "channels" (M = 128)
+    p.CU = p.nT % 4 == 0 ? 4 : (p.nT % 2 == 0 ? 2 : 1);
+    { const int cap = env_int("PB_WG_RS_UC", 4); while (p.CU > cap) p.CU /= 2; }
+    // (measured: RU > 1 is SLOWER — c16->8 80^3 127 -> 147 us with two rows per M = 128 / N = 120 instruction, c8->8 105 -> 151 us with four rows
+    // per N = 184 instruction: those shapes fetch 7.75 / 9.75 KB of operands per instruction, more than the 128 B per clock the shared memory
+    // delivers in their MAC time, and in the kernel they retire in 94 / 172 cycles.  Kept behind PB_WG_RS_RU, default one row.)
+    p.RU = 4 / p.CU;
+    { const int cap = env_int("PB_WG_RS_RU", 1); while (p.RU > cap) p.RU /= 2; }
+    p.UC = p.CU * p.RU;
+    p.NN = 8 * (11 + 4 * (p.RU - 1));
+    p.setw = (p.NN + 31) & ~31;
     p.tmem_cols = 32;
-    while ((int)p.tmem_cols < (p.TG / p.UC) * kRsSetW) p.tmem_cols *= 2;
+    while ((int)p.tmem_cols < (p.TG / p.CU) * p.setw) p.tmem_cols *= 2;
+    if (p.tmem_cols > 512) return PB_EUNSUPPORTED;
     p.h_lo = p.reflect ? -1 : 0; p.rows_t = p.reflect ? p.H + 2 : p.H;
     p.d_lo = p.reflect ? -1 : 0; p.planes_t = p.reflect ? p.D + 2 : p.D;
     if ((long long)p.H * p.W * (p.C0 > p.C1 ? p.C0 : p.C1) >= (1LL << 30)) return PB_EUNSUPPORTED;          // int offsets within a plane
@@ -448,13 +512,16 @@ int pb_wgrad_rs_launch(const pb_conv_desc* d, const void* x0, const void* x1, co
     int nr = env_int("PB_WG_RS_ROWS", kRsMaxRows);
     if (nr > kRsMaxRows) nr = kRsMaxRows;
     if (nr > p.rows_t) nr = p.rows_t;
+    nr = ((nr + p.RU - 1) / p.RU) * p.RU;                          // whole row groups (pad rows are zero-filled)
     auto smem_of = [&](int rows, int steps) {
         return (size_t)p.nregions * (4 * (rows + 2) + steps + 2) * p.KW * 16 + (size_t)kRsXSlots * p.TG * rows * (p.KW + 8) * 16 + 256 + 1024;
     };
-    while (nr > 1 && (p.TG * nr * (p.KW + 8) > kRsXCopies * kRsXProducers || smem_of(nr, kRsMaxSteps) > 227 * 1024)) --nr;
-    if (p.TG * nr * (p.KW + 8) > kRsXCopies * kRsXProducers || smem_of(nr, kRsMaxSteps) > 227 * 1024) return PB_EUNSUPPORTED;
+    auto too_big = [&](int rows) { return p.TG * rows * (p.KW + 8) > kRsXCopies * kRsXProducers || smem_of(rows, kRsMaxSteps) > 227 * 1024; };
+    while (nr > p.RU && too_big(nr)) nr -= p.RU;
+    if (too_big(nr)) return PB_EUNSUPPORTED;
     p.nstrips = (p.rows_t + nr - 1) / nr;
     p.nr = (p.rows_t + p.nstrips - 1) / p.nstrips;
+    p.nr = ((p.nr + p.RU - 1) / p.RU) * p.RU;                     // <= nr
     // depth chunks: at most kRsMaxSteps planes per item, at least 6 (the two halo planes of dy are loaded per item); among those the
     // count that fills whole rounds of CTAs best (an item is ~25 us of work: a ragged last round is the largest loss)
     int best_nd = 0;

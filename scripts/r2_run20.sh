@@ -8,3 +8,4 @@ import json
 d=json.loads(open("gpurun_out/r2t/bench.json").read()); print(d["ms_per_step"], d["e2e"]["ms_per_step"], d["gpu_launches"]//16, d["roofline"]["families_ms_per_step"])
 P
 MODES=0,1 timeout 300 python scripts/bench_wgrad.py > $OUT/wgrad_classes.txt 2>&1; tail -1 $OUT/wgrad_classes.txt
+PB_WG_RS_MIN_VOX=0 PB_WG_RS_RU=4 timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider -k "test_conv3d" 2>&1 | tail -1
