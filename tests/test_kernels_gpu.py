@@ -503,3 +503,58 @@ def test_linear_tc_3d_and_fallback(lib_built):
     assert y16.shape == (2, 125, 1536) and y16.dtype == torch.bfloat16 and y32.dtype == torch.float32
     assert rel(y16, y32) < 1.5e-2
     ops.check_tc_errors()
+
+
+WGRAD_RS_CASES = [
+    # c0, c1, cout, pad, groups, n, (d, h, w): every unit width of the row-stacked weight gradient (csrc/conv3d_wgrad_rs.cu) — 8-channel
+    # plain rows, 16-channel SWIZZLE_32B rows, 32-channel SWIZZLE_64B rows, several chunk groups / output chunks per launch, two sources
+    # that straddle a unit, zero padding, ragged strips and depth chunks, W = 128 and W not a multiple of 16 (K tail = zero fill)
+    (8, 0, 8, "reflect", 1, 2, (9, 11, 16)),
+    (16, 0, 8, "reflect", 1, 2, (7, 19, 20)),
+    (32, 0, 16, "reflect", 1, 2, (6, 9, 12)),
+    (32, 0, 32, "zeros", 2, 4, (5, 7, 10)),
+    (64, 0, 32, "reflect", 1, 1, (5, 6, 9)),
+    (64, 64, 64, "reflect", 1, 1, (4, 5, 6)),
+    (8, 16, 16, "reflect", 1, 2, (6, 8, 11)),
+    (16, 16, 8, "zeros", 1, 1, (18, 17, 40)),
+    (24, 0, 8, "reflect", 1, 1, (5, 6, 7)),
+    (8, 0, 8, "reflect", 1, 1, (3, 5, 128)),
+    (16, 0, 16, "reflect", 4, 4, (20, 21, 22)),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_RS_CASES, ids=lambda c: "c%d+%d_%d_%s_g%d_n%d" % c[:6])
+def test_wgrad_rs_classes(lib_built, case, monkeypatch):
+    """The row-stacked tcgen05 weight gradient on every unit width and routing branch, forced on for small volumes
+    (PB_WG_RS_MIN_VOX=0; by default volumes below 20^3 stay on the kh-stacked kernels), against a float64 reference of the same
+    bf16-rounded operands; and the same launch through the old kernels (PB_WG_RS=0) as a second opinion."""
+    from passion_b200 import ops
+    c0, c1, cout, pad, groups, n, (d, h, w) = case
+    cin = c0 + c1
+    g = torch.Generator(device="cpu").manual_seed(cin * 131 + cout * 7 + d * h * w)
+    x = torch.randn(n, cin, d, h, w, generator=g).cuda().bfloat16()
+    wt = (torch.randn(groups, cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5).cuda()
+    gy = torch.randn(n, cout, d, h, w, generator=g).cuda().bfloat16()
+    xr = x.double()
+    wr = wt.bfloat16().double().requires_grad_(True)
+    npg = n // groups
+    ys = []
+    for gi in range(groups):
+        xi = F.pad(xr[gi * npg:(gi + 1) * npg], (1,) * 6, mode="reflect" if pad == "reflect" else "constant")
+        ys.append(F.conv3d(xi, wr[gi]))
+    torch.cat(ys, 0).backward(gy.double())
+    dwr = torch.stack([ops.kernel_layout(wr.grad[gi]) for gi in range(groups)])
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PB_WG_RS", mode)
+        monkeypatch.setenv("PB_WG_RS_MIN_VOX", "0")
+        x_cl = to_cl(x)
+        x0 = x_cl[..., :c0].contiguous().requires_grad_(True)
+        x1 = x_cl[..., c0:].contiguous().requires_grad_(True) if c1 else None
+        wk = torch.stack([ops.kernel_layout(wt[gi]) for gi in range(groups)]).contiguous().requires_grad_(True)
+        y, _ = ops.conv3d(x0, wk, None, x1, ksize=3, stride=1, pad_mode=pad, groups=groups, want_stats=False)
+        y.backward(to_cl(gy))
+        got[mode] = wk.grad.clone()
+        assert rel(wk.grad, dwr) < 2e-5, (mode, rel(wk.grad, dwr))      # fp32 accumulation of exact bf16 products
+    assert rel(got["1"], got["0"]) < 2e-5
+    ops.check_tc_errors()
