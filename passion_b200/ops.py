@@ -379,6 +379,7 @@ class _Conv3d(torch.autograd.Function):
         _conv_fwd_launch(lib, d, x0, x1, lambda: w, tc_call, bias, y, stats)
         ctx.save_for_backward(x0, x1, w)
         ctx.cfg = (ksize, stride, pad_mode, groups, bias is not None)
+        ctx.set_materialize_grads(False)         # no zero-filled "gradient" of the statistics output (one fill launch per conv otherwise)
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -386,6 +387,8 @@ class _Conv3d(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        if dy is None:
+            return (None,) * 9
         lib = _lib.load()
         x0, x1, w = ctx.saved_tensors
         ksize, stride, pad_mode, groups, has_bias = ctx.cfg
@@ -720,6 +723,7 @@ class _Conv3dRef(torch.autograd.Function):
         ctx.save_for_backward(x0, x1, *ws, *bs)
         ctx.bwd_w = (wt, imgT)
         ctx.cfg = (ksize, stride, pad_mode, G, has_bias, nw, slices)
+        ctx.set_materialize_grads(False)         # no zero-filled "gradient" of the statistics output (one fill launch per conv otherwise)
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -727,6 +731,8 @@ class _Conv3dRef(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        if dy is None:
+            return (None,) * (7 + len(ctx.saved_tensors) - 2)
         lib = _lib.load()
         ksize, stride, pad_mode, G, has_bias, nw, slices = ctx.cfg
         x0, x1 = ctx.saved_tensors[:2]
