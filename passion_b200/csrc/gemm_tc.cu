@@ -12,6 +12,7 @@
 // MMA-issuing thread (M = 128, N = 64, K = 16), epilogue TMEM -> registers -> (+ bias) -> global.  Outputs with few tiles and a long
 // K (FFN down: 250 x 512 x 4096) run split-K into a zero-filled fp32 workspace (float4 atomics) + a small finalize launch.
 // Warp roles: warps 0-3 epilogue, warp 4 MMA issue + TMEM allocation, warp 5 TMA producer.
+#include <cstdlib>
 #include <cstring>
 #include "tc_common.cuh"
 
@@ -174,6 +175,7 @@ __global__ void gemm_finalize_kernel(const float* __restrict__ ws, const float* 
 
 // split-K factor: enough CTAs to occupy the GPU when the output has few tiles and K is long (FFN down: 250 x 512 x 4096 is 8 tiles)
 int gemm_splits(int M, int N, int K) {
+    { const char* e = getenv("PB_GEMM_SPLITK"); if (e && atoi(e) == 0) return 1; }
     const int tiles = ((M + kGBM - 1) / kGBM) * ((N + kGBN - 1) / kGBN);
     const int kblocks = (K + kGBK - 1) / kGBK;
     if (tiles >= 296 || kblocks < 32) return 1;                 // a CTA keeps only 72 KB in flight: a long K needs many CTAs to fill the HBM pipe

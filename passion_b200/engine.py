@@ -88,9 +88,14 @@ class Trainer:
                 self._eager_step(*self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import ops
+        gen = ops.scratch_generation(self.dev)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             loss, parts = self._eager_step(*self._static)
+        if ops.scratch_generation(self.dev) != gen:
+            # the zero-scratch arena was re-allocated inside the capture: the replayed memset would not cover what the step uses
+            raise RuntimeError("passion_b200: the scratch arena grew while the step was being captured; run one more eager step first")
         self._out = (loss, {k: v.detach() for k, v in parts.items()})
         self._captured_warmup = self.warmup
 

@@ -89,19 +89,33 @@ def _publish_to_all_streams(device):
 
 
 class _ZeroScratch:
-    """Zero-initialised short-lived scratch (statistics / weight-gradient accumulators that kernels fill with atomics and
-    the very next launch consumes).  Slices of one arena per device, handed out linearly; `begin_step()` re-zeroes the
-    used part with ONE memset instead of one fill launch per buffer (~350 per training step)."""
+    """Zero-initialised short-lived scratch (statistics / weight-gradient accumulators / split-K partials that kernels fill with
+    atomics and the very next launch consumes).  Slices of one arena per device, handed out linearly; `begin_step()` re-zeroes the
+    used part with ONE memset instead of one fill launch per buffer (~350 per training step).
+
+    The arena must not grow inside a step that is being captured into a CUDA graph: the replayed memset would then cover only the part
+    used since the last growth, and the accumulators beyond it would start every replay from the previous replay's sums (this is what
+    turned the mmFormer step into NaNs after three replays once the split-K workspaces pushed the demand past the initial 8 MB).
+    `begin_step()` therefore sizes the arena for the TOTAL demand of the previous step, so the step after a growing one never grows,
+    and `generation(device)` lets the trainer verify that a capture saw a stable arena."""
     MIN_BYTES = 8 << 20
 
     def __init__(self):
-        self.arenas = {}
+        self.arenas = {}          # device -> [tensor, used bytes, bytes requested since begin_step, generation]
 
     def begin_step(self, device):
         a = self.arenas.get(device)
-        if a is not None and a[1] > 0:
+        if a is None:
+            return
+        if a[2] > a[0].numel() and not (device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            # the previous step outgrew the arena on its way: give the coming step one that holds all of it
+            self.arenas[device] = [torch.zeros(max(self.MIN_BYTES, 2 * a[2]), dtype=torch.uint8, device=device), 0, 0, a[3] + 1]
+            _publish_to_all_streams(device)
+            return
+        if a[1] > 0:
             a[0][:a[1]].zero_()
-            a[1] = 0
+        a[1] = 0
+        a[2] = 0
 
     def zeros(self, shape, dtype, device):
         n = 1
@@ -111,15 +125,25 @@ class _ZeroScratch:
         a = self.arenas.get(device)
         if a is None or a[1] + nbytes > a[0].numel():
             size = max(self.MIN_BYTES, 2 * nbytes, 2 * (a[0].numel() if a is not None else 0))
-            a = [torch.zeros(size, dtype=torch.uint8, device=device), 0]
+            a = [torch.zeros(size, dtype=torch.uint8, device=device), 0, a[2] if a is not None else 0, (a[3] + 1) if a is not None else 0]
             self.arenas[device] = a
             _publish_to_all_streams(device)
         off = a[1]
         a[1] = off + nbytes
+        a[2] += nbytes
         return a[0][off:off + nbytes].view(dtype)[:n].view(shape)
+
+    def generation(self, device):
+        a = self.arenas.get(torch.device(device))
+        return -1 if a is None else a[3]
 
 
 _scratch = _ZeroScratch()
+
+
+def scratch_generation(device):
+    """Changes whenever the zero-scratch arena of `device` is re-allocated (see _ZeroScratch)."""
+    return _scratch.generation(device)
 
 
 def begin_step(device):

@@ -205,3 +205,35 @@ def test_inference_sweep_is_deterministic_on_a_fresh_model(lib_built):
     for n in names:
         assert torch.equal(r1[n], r2[n]), n
     assert model.training
+
+
+def test_graph_replay_equals_eager_from_a_cold_scratch_arena(lib_built, monkeypatch):
+    """Regression test of the zero-scratch arena under CUDA-graph capture.  The arena (statistics / weight-gradient accumulators /
+    split-K partials) is re-zeroed by ONE memset per step; when it was still growing during the trainer's last warm-up step, the
+    captured memset covered only the part used since the last growth and the accumulators beyond it carried their sums from replay to
+    replay — an mmFormer `train.py` run from a cold process went to NaN after three replays.  Here the arena starts EMPTY and tiny
+    (so that it grows many times during the first step, as in a cold process with large demands), and the replayed steps must
+    reproduce eager steps from the same weights and batch (dropout off): graph step i = eager step i + 2 (two warm-up steps)."""
+    from passion_b200 import ops
+    from passion_b200.engine import Trainer
+    z, _, sd, x, target, mask = _setup("idtU", torch.bfloat16)
+    mw = torch.from_numpy(z["modal_weight"]).float()
+    beta = torch.from_numpy(z["imb_beta"]).float()
+    steps = 6
+    runs = {}
+    for use_graph in (False, True):
+        _, model, _, _, _, _ = _setup("idtU", torch.bfloat16)
+        monkeypatch.setattr(ops._scratch, "arenas", {})
+        monkeypatch.setattr(ops._ZeroScratch, "MIN_BYTES", 1 << 16)
+        tr = Trainer(model, lr=2e-4, weight_decay=1e-4, temp=float(z["temp"]), mask_type="idt", use_passion=True, modal_weight=mw,
+                     imb_beta=beta, use_graph=use_graph)
+        xs, ts, ms = x.cuda(), target.cuda(), mask.cuda()
+        runs[use_graph] = [float(tr.step(xs, ts, ms)[0]) for _ in range(steps + (0 if use_graph else 2))]
+    ops.check_tc_errors()
+    eager, graph = runs[False], runs[True]
+    assert all(np.isfinite(graph)), graph
+    worst = max(abs(g - e) / abs(e) for g, e in zip(graph, eager[2:]))
+    print(f"graph vs eager (cold arena): {graph} vs {eager[2:]}, worst rel dev {worst:.2e}")
+    # two bf16 runs separate by ~2e-3 over these steps on their own (atomic summation order feeds back through the optimizer);
+    # the stale-accumulator bug produced O(1) deviations, then NaN
+    assert worst < 1e-2, (graph, eager)
