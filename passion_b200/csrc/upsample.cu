@@ -171,29 +171,31 @@ __global__ void __launch_bounds__(256) up_bwd_kernel(const T* __restrict__ dy, T
 // One axis of the (separable) adjoint: in [outer][n_big][inner] -> out [outer][n_small][inner],
 // out[i] = sum_o w(o, i) in[o].  The 3-D adjoint is the composition over W, H, D; the intermediates shrink by the
 // scale factor after every pass, so for x4 / x8 this replaces a (2s)^3-term gather per voxel by three 2s-term ones.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256) up_bwd_axis_kernel(const T* __restrict__ in, T* __restrict__ out, long long outer, int n_big,
-                                                          int n_small, long long inner_vec, float ratio, long long total_vec) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total_vec; t += (long long)gridDim.x * blockDim.x) {
-        const long long iv = t % inner_vec;
-        const long long r = t / inner_vec;
-        const int i = (int)(r % n_small);
-        const long long o_idx = r / n_small;
+// I = index type: 32-bit whenever the tensors allow it (two divisions per output vector; as 64-bit divisions they cost as much as the loads)
+template <typename T, int VEC, typename I>
+__global__ void __launch_bounds__(256) up_bwd_axis_kernel(const T* __restrict__ in, T* __restrict__ out, I outer, int n_big,
+                                                          int n_small, I inner_vec, float ratio, I total_vec) {
+    const float inv_ratio = ratio > 0.f ? 1.f / ratio : 0.f;
+    for (I t = (I)blockIdx.x * blockDim.x + threadIdx.x; t < total_vec; t += (I)gridDim.x * blockDim.x) {
+        const I r = t / inner_vec;
+        const I iv = t - r * inner_vec;
+        const I o_idx = r / n_small;
+        const int i = (int)(r - o_idx * n_small);
         int lo = 0, hi = n_big - 1;
-        if (ratio > 0.f) { lo = max(0, (int)floorf((i - 1) / ratio) - 1); hi = min(n_big - 1, (int)ceilf((i + 1) / ratio) + 1); }
+        if (ratio > 0.f) { lo = max(0, (int)floorf((i - 1) * inv_ratio) - 2); hi = min(n_big - 1, (int)ceilf((i + 1) * inv_ratio) + 2); }
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-        const T* base = in + (o_idx * n_big) * inner_vec * VEC + iv * VEC;
+        const T* base = in + ((size_t)o_idx * n_big) * inner_vec * VEC + (size_t)iv * VEC;
         for (int o = lo; o <= hi; ++o) {
             const float wgt = axis_weight(o, i, ratio, n_small);
             if (wgt == 0.f) continue;
             float v[VEC];
-            VecIO<T, VEC>::load(base + (long long)o * inner_vec * VEC, v);
+            VecIO<T, VEC>::load(base + (size_t)o * inner_vec * VEC, v);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
         }
-        VecIO<T, VEC>::store(out + t * VEC, acc);
+        VecIO<T, VEC>::store(out + (size_t)t * VEC, acc);
     }
 }
 
@@ -205,7 +207,12 @@ int run_axis(const void* in, void* out, long long outer, int n_big, int n_small,
     long long blocks = (total_vec + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     if (blocks < 1) blocks = 1;
-    up_bwd_axis_kernel<T, VEC><<<(int)blocks, 256, 0, st>>>((const T*)in, (T*)out, outer, n_big, n_small, inner_vec, ratio, total_vec);
+    if (total_vec + 148LL * 32 * 256 < 0x7fffffffLL)
+        up_bwd_axis_kernel<T, VEC, int><<<(int)blocks, 256, 0, st>>>((const T*)in, (T*)out, (int)outer, n_big, n_small, (int)inner_vec, ratio,
+                                                                    (int)total_vec);
+    else
+        up_bwd_axis_kernel<T, VEC, long long><<<(int)blocks, 256, 0, st>>>((const T*)in, (T*)out, outer, n_big, n_small, inner_vec, ratio,
+                                                                          total_vec);
     return 0;
 }
 
