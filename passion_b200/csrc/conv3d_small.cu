@@ -190,26 +190,43 @@ conv3_small_wgrad_kernel(SmK p, const T* __restrict__ x, const T* __restrict__ d
         const int qt = r % p.tiles_q, dt = r / p.tiles_q;
         const int d0 = dt * kTD, q0 = qt * kTQ;
         const int hb = q0 / p.W;
-        __syncthreads();                                        // previous tile fully consumed
-        load_tile<T, CIN>(p, x, tile, n, d0, hb);
-        __syncthreads();
         const int q = q0 + threadIdx.x;
         const bool valid = q < p.H * p.W;
         const int h = valid ? q / p.W : hb, wq = valid ? q - h * p.W : 0;
-        // One output plane at a time, the next plane's dy vector already in flight: the accumulators plus two dy vectors
-        // fit 128 registers, so two CTAs share an SM (the version that held all kTD dy vectors ran one 8-warp CTA per SM
-        // and was bound by its own load -> sync -> compute latency chain: 0.41 ms for the 73 MB of the 1 -> 8 layer).
         const T* dyp = dy + ((((size_t)n * p.D + d0) * p.H + h) * p.W + wq) * COUT;
         const size_t plane = (size_t)p.H * p.W * COUT;
-        float gc[COUT], gn[COUT];
-        if (valid && d0 < p.D) VecIO<T, COUT>::load(dyp, gc);
-        else {
+        // Few output channels: ALL kTD dy vectors of this thread are requested before the tile is staged, so their latency hides behind
+        // the staging (with one plane of look-ahead the loop was a chain of kTD global-load round trips: ncu showed 60 % of the samples
+        // on the long scoreboard at 0.7 instructions per clock and SM).  Wide outputs keep the one-plane look-ahead (register budget).
+        constexpr bool PRE = COUT * kTD <= 32;
+        float gall[PRE ? kTD : 1][COUT];
+        if constexpr (PRE) {
 #pragma unroll
-            for (int j = 0; j < COUT; ++j) gc[j] = 0.f;
+            for (int o = 0; o < kTD; ++o) {
+                if (valid && d0 + o < p.D) VecIO<T, COUT>::load(dyp + (size_t)o * plane, gall[o]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < COUT; ++j) gall[o][j] = 0.f;
+                }
+            }
+        }
+        __syncthreads();                                        // previous tile fully consumed
+        load_tile<T, CIN>(p, x, tile, n, d0, hb);
+        __syncthreads();
+        float gc[COUT], gn[COUT];
+        if constexpr (!PRE) {
+            if (valid && d0 < p.D) VecIO<T, COUT>::load(dyp, gc);
+            else {
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) gc[j] = 0.f;
+            }
         }
 #pragma unroll
         for (int o = 0; o < kTD; ++o) {
-            if (o + 1 < kTD) {
+            if constexpr (PRE) {
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) gc[j] = gall[o][j];
+            } else if (o + 1 < kTD) {
                 if (valid && d0 + o + 1 < p.D) VecIO<T, COUT>::load(dyp + (size_t)(o + 1) * plane, gn);
                 else {
 #pragma unroll
@@ -231,9 +248,11 @@ conv3_small_wgrad_kernel(SmK p, const T* __restrict__ x, const T* __restrict__ d
                                 acc[((k * 3 + kh) * 3 + kw) * CIN * COUT + ci * COUT + j] =
                                     fmaf(xv[ci], gc[j], acc[((k * 3 + kh) * 3 + kw) * CIN * COUT + ci * COUT + j]);
                     }
-            if (o + 1 < kTD) {
+            if constexpr (!PRE) {
+                if (o + 1 < kTD) {
 #pragma unroll
-                for (int j = 0; j < COUT; ++j) gc[j] = gn[j];
+                    for (int j = 0; j < COUT; ++j) gc[j] = gn[j];
+                }
             }
         }
     }

@@ -1,5 +1,5 @@
 #!/bin/bash
 OUT=gpurun_out/r2u; mkdir -p $OUT
-timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider -k "upsample or test_conv3d" 2>&1 | tail -2
-PB_DUMP_KERNELS=$OUT/kernels.txt timeout 600 python bench.py --no-cpu-baseline --no-extras --steps 16 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); f=d['roofline']['families_ms_per_step']; print(d['ms_per_step'], d['e2e']['ms_per_step'], {k:f[k] for k in ('upsample_bwd','reflect_fold','upsample_fwd')})"
-grep "^upsample_bwd\|^reflect_fold" $OUT/kernels.txt | head -8
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider -k "test_conv3d" 2>&1 | tail -2
+PB_DUMP_KERNELS=$OUT/kernels1.txt timeout 600 python bench.py --no-cpu-baseline --no-extras --steps 16 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); f=d['roofline']['families_ms_per_step']; print(d['ms_per_step'], d['e2e']['ms_per_step'], {k:f[k] for k in f if 'small' in k})"
+grep "^conv3d_small_wgrad" $OUT/kernels1.txt | head -4
