@@ -6,26 +6,32 @@
 // Why a new shape: the old kernels (M = 64, N = 32: six tcgen05.mma per 16 voxels of a c16 -> 8 layer) were bound by the
 // instruction count — an MMA with both operands MN-major costs the pipe max(36, M*N*16 / 2048 [M = 64] or 4096 [M = 128]) cycles
 // and ONE thread cannot issue them faster than one per 61.5 cycles (scripts/microbench/umma_rate_mn*.cu, profiles/r02_wgrad_rs.txt).
-// Here ONE instruction per 16 voxels, 8-channel input chunk and 8-channel output chunk produces all 27 taps:
+// Here ONE instruction per 16 voxels, UNIT of input channels and 8-channel output chunk produces all 27 taps:
 //   * K = 16 consecutive w positions of ONE padded input row (d, h); a CTA walks whole rows.
-//   * A (M = 64, MN-major) = that row of xp for one 8-channel chunk; the eight M-groups are the same row shifted by 0..7 positions
-//     (SBO = 16 B), groups 0..2 are the three kw taps, groups 3..7 are don't-care rows that are never read back.
+//   * A (MN-major) = that row of xp for one unit of 8 / 16 / 32 input channels; its M-groups are the same row shifted by 0, 1, 2, ...
+//     positions (one position per group): groups 0..2 are the three kw taps, the others are don't-care rows that are never read back.
+//     8 channels = plain 16-byte rows (M = 64); 16 / 32 channels = the tensor's own 32- / 64-byte NDHWC rows under SWIZZLE_32B (M = 64) /
+//     SWIZZLE_64B (M = 128) — the producers store each 16-byte chunk at its swizzled position (rs_adesc below).
 //   * B (N = 88, MN-major) = the dy rows (d-1..d+1) x (h-1..h+1) that pair with this input row, one 8-channel output chunk.
 //     The dy strip lives in shared memory in a DIAGONAL layout: row h' of the q-th plane of the sweep sits at row index
 //     L = 4 h' + q of one linear buffer.  The nine rows of an input row are then L0 + {0,1,2, 4,5,6, 8,9,10} with L0 moving by one
 //     per plane: ONE descriptor with SBO = row pitch and 11 N-groups addresses them, always in the same order (no rotation of
 //     the accumulator columns); groups 3 and 7 belong to plane q + 3, which is being prefetched while plane q's step runs —
-//     their accumulator columns are garbage and are never read back.  Plane q + 4 overwrites plane q one row further up, so four
-//     planes are live and the load of a plane has a whole step to land (with three planes it sat on the critical path:
-//     measured 198 us vs the 83 us of the MMAs alone for the c16 -> 8, 80^3, n = 10 class).
+//     their accumulator columns are garbage and are never read back.  Plane q + 4 overwrites plane q one row further up.
 // A CTA (one per SM) owns (weight group, up to four input chunks, one output chunk) and a stream of work items (sample, strip of
-// <= 8 input rows, depth chunk of <= 16 planes); the accumulators (96 TMEM columns per input chunk) stay in TMEM for the whole
-// stream and are flushed once with fp32 atomics.
-// Warp roles: warps 0-7 stage the input rows (16-byte cp.async; reflect / zero padding and the two-source concat are resolved
-// in the address computation, the K tail is zero-filled), running up to three steps ahead; warp 8 lane 0 streams the dy rows by
-// TMA (one box [KW positions][8 ch] per row; rows and planes outside the volume and the K tail are the tensor map's zero fill);
-// lanes 0 of warps 9-11 issue the MMAs, all accumulating into the same (zero-initialised) accumulators, K loop unrolled (with
-// the descriptors advanced in a rolled loop one thread needs 119 cycles per MMA instead of 64).  Warps 0 and 1 flush at the end.
+// <= 16 input rows, depth chunk of <= 16 planes) which it takes in interleaved PAIRS (steps A.0, B.0, A.1, B.1, ...; each item of a pair has
+// its own dy buffer region and plane barriers), so that three steps of other work lie between the retirement of a dy plane and the step
+// that needs the plane loaded in its place.  The accumulators (96 TMEM columns per unit) stay in TMEM for the whole stream and are
+// flushed once with fp32 atomics.
+// Warp roles (13 warps): warps 0-7 stage the input rows (16-byte cp.async; reflect / zero padding and the two-source concat are
+// resolved in the address computation, the K tail is zero-filled), running up to three steps ahead; warp 8 streams the dy rows, one row
+// per lane: plain bulk copies where a dy row is contiguous (Cout = 8, W a multiple of 16; rows outside the volume zero-filled by the
+// warp), else one TMA box [KW positions][8 ch] per row (rows, planes and the K tail outside the volume = the tensor map's zero fill);
+// lanes 0 of warps 9-12 issue the MMAs, all accumulating into the same zero-initialised accumulators, with a division-free issue loop
+// whose K loop is unrolled (one thread needs ~65-75 cycles per instruction; 119 with a rolled loop, 185 with a division per row).
+// Warps 0-3 flush at the end.  PB_WG_RS=0 falls back to the kh-stacked kernels, =2 / 3 / 5 are developer probes (no MMAs / no input
+// copies / issuer cycle counters, scripts/probe_wgrad_issuer.py); PB_WG_RS_RU > 1 puts several input rows side by side in one instruction
+// (built, measured slower, off).
 #include <cstdlib>
 #include "tc_common.cuh"
 
@@ -39,8 +45,6 @@ constexpr int kRsMaxRows = 16;
 constexpr int kRsMaxSteps = 16;            // planes per work item (bounds the diagonal dy buffer)
 constexpr int kRsMaxChunks = 4;            // input chunks per CTA
 constexpr int kRsIssuers = 4;
-constexpr int kRsN = 88;                   // UMMA N: 11 dy row groups x 8 output channels
-constexpr int kRsSetW = 96;                // TMEM columns per input chunk
 
 struct RsP {
     int N, D, H, W, C0, C1, Cout, reflect;
