@@ -127,8 +127,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 inline EncodeTiledFn encode_tiled() {
     // cuTensorMapEncodeTiled is a driver call: it needs the device's primary context to be current in THIS thread.  Autograd runs
     // backward on its own thread, where no runtime call may have bound it yet (CUDA_ERROR_INVALID_CONTEXT otherwise).
+    // cudaSetDevice binds the primary context without being a stream / memory operation (legal while another thread captures a graph).
     static thread_local bool ctx_bound = false;
-    if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+    if (!ctx_bound) { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev); ctx_bound = true; }
     static EncodeTiledFn fn = [] {
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult q;
