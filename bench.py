@@ -7,9 +7,11 @@ A "step" is one forward + PASSION loss + backward + AdamW(amsgrad) update on one
 BraTS-shaped 4x80^3 crops, B = 2 per GPU (BASELINE.json configs[1]); at N > 1 (torchrun, one rank per GPU,
 NCCL) each rank takes its own B = 2 shard of the global batch (weak scaling, configs[2]).
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same metric
-through the public API with pinned HOST buffers (H2D of x / one-hot target / mask and D2H of the loss inside
-the timed region).  `roofline` is the live CUDA-event measurement of the dominant kernel family.
-`--impl reference` times the reference algorithm's CPU port (oracle/, PyTorch fp32 on the host cores).
+through the public API with pinned HOST buffers (H2D of x / uint8 label map / mask every step, the H2D of batch i+1
+overlapping step i, and a D2H read of every step's loss, one step behind, inside the timed region).  `roofline` is the live
+CUDA-event measurement of the dominant kernel family.
+`--impl reference` times the UNMODIFIED reference model + criterions staged under baseline/_ref (PyTorch fp32 on the host
+cores, same config block); where that tree is missing it falls back to the oracle port and says so (`kind`).
 """
 import argparse
 import json
