@@ -1,4 +1,5 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider -k "linear" 2>&1 | tail -1
-timeout 900 python -m pytest tests/test_mmformer_gpu.py tests/test_model_gpu.py -m gpu -q -p no:cacheprovider 2>&1 | tail -1
-timeout 300 python train.py --use_passion --batch_size 2 --synthetic --num_epochs 1 --iters_per_epoch 6 --savepath /tmp/mm 2>&1 | grep -E "Iter 6/6" | cut -c25-170
+OUT=gpurun_out/r2u; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider -k "test_conv3d" 2>&1 | tail -2
+PB_DUMP_KERNELS=$OUT/kernels1.txt timeout 600 python bench.py --no-cpu-baseline --no-extras --steps 16 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); f=d['roofline']['families_ms_per_step']; print(d['ms_per_step'], d['e2e']['ms_per_step'], {k:f[k] for k in ('conv3d_fwd_tc','conv3d_dgrad_tc','conv3d_wgrad_tc')})"
+grep "^conv3d_fwd_tc\|^conv3d_dgrad_tc" $OUT/kernels1.txt | head -10
