@@ -126,6 +126,8 @@ int pb_conv1_tc(const pb_conv_desc* d, const void* x0, const void* x1, const voi
 long long pb_gemm_tc_workspace_floats(int M, int N, int K);
 /* developer probe of csrc/conv3d_wgrad_rs.cu (launches made with PB_WG_RS=5): issuer-thread cycle counters, read and cleared */
 int pb_wgrad_rs_debug(unsigned long long* out8);
+/* same for the kw-stacked forward / data-gradient kernel of csrc/conv3d_tc.cu (launches made with PB_TC_PROBE=1) */
+int pb_conv3d_tc_debug(unsigned long long* out8);
 int pb_gemm_tc(const void* a, const void* b, const float* bias, void* d, float* workspace, int M, int N, int K, int lda, int ldb,
                int ldd, int a_kmajor, int b_kmajor, int d_fp32, int* err_flag, pb_stream_t stream);
 int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, void* y0, void* y1, int co0, int co1,

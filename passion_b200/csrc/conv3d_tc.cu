@@ -46,7 +46,10 @@ struct TcP {
                                         // chunk one cp.async.bulk.tensor box [tma_rows padded rows][PW][8 ch], out-of-bounds = the zero
                                         // padding; the slab then starts at padded row r0 = q0 / PW and the tile at offset q0 - r0 * PW
     int q_stride;                       // positions a tile advances by (128, or 126 for the kw-stacked kernel)
+    int probe;                          // developer probe (PB_TC_PROBE=1): cycle counters of the MMA thread and of epilogue thread 0
 };
+
+__device__ unsigned long long tc_dbg[8];
 
 
 // TMA producer of conv3_tc_kernel / conv3_tc_kws_kernel (one thread): streams the input planes of this CTA's work items into the
@@ -521,17 +524,23 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __gri
             const uint32_t slab_addr = smem_u32(slab_s);
             const uint64_t b0 = umma_desc(smem_u32(w_s), 9 * NT * 16, 128);      // LBO = one chunk plane of 9 NT rows
             uint32_t k = 0, j0 = 0;
+            long long pw_full = 0, pw_blk = 0, p_issue = 0, p_n = 0;
+            const long long p_t0 = clock64();
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int dc = it % p.ND;
                 const int nout = min(p.DCH, p.D - dc * p.DCH);
                 // TMA slabs start at a padded-row boundary: the tile begins (q0 mod PW) rows into the slab
                 const uint32_t tile_off = p.tma ? (uint32_t)((((it / p.ND) % p.QT) * p.q_stride) % p.PW) * 16u : 0u;
                 for (int pl = 0; pl < nout + 2; ++pl, ++k) {
+                    const long long c0 = clock64();
                     mbar_wait(&full[k % kSlots], (k / kSlots) & 1, err, 3);
+                    const long long c1 = clock64();
                     if (pl < nout) {
                         const uint32_t jn = j0 + pl;
                         mbar_wait(&blk_empty[jn % R], ((jn / R) & 1) ^ 1, err, 4);
                     }
+                    const long long c2 = clock64();
+                    pw_full += c1 - c0; pw_blk += c2 - c1; ++p_n;
                     fence_proxy_async();
                     tc_fence_after();
                     const int od_lo = pl >= 2 ? pl - 2 : 0, od_hi = pl < nout ? pl : nout - 1;
@@ -566,10 +575,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __gri
                             }
                         }
                     }
+                    p_issue += clock64() - c2;
                     umma_commit(&empty[k % kSlots]);
                     if (pl >= 2) umma_commit(&blk_full[(j0 + pl - 2) % R]);
                 }
                 j0 += nout;
+            }
+            if (p.probe) {
+                atomicAdd(&tc_dbg[0], (unsigned long long)pw_full); atomicAdd(&tc_dbg[1], (unsigned long long)pw_blk);
+                atomicAdd(&tc_dbg[2], (unsigned long long)p_issue); atomicAdd(&tc_dbg[3], (unsigned long long)p_n);
+                atomicAdd(&tc_dbg[4], (unsigned long long)(clock64() - p_t0)); atomicAdd(&tc_dbg[5], 1ULL);
             }
         }
         __syncwarp();
@@ -596,7 +611,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv3_tc_kws_kernel(const __gri
             for (int c = 0; c < CRE; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
             for (int od = 0; od < nout; ++od, ++j) {
                 const uint32_t blk = j % R;
+                const long long e0 = clock64();
                 mbar_wait(&blk_full[blk], (j / R) & 1, err, 5);
+                if (p.probe && threadIdx.x == 0) atomicAdd(&tc_dbg[6], (unsigned long long)(clock64() - e0));
                 tc_fence_after();
                 float v0[CRE], v1[CRE], v2[CRE];
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + blk * NB;
@@ -1378,6 +1395,14 @@ int make_plane_map(CUtensorMap* map, const void* base, int C, int W, int H, long
 }
 }  // namespace
 
+// developer probe: reads and clears the kw-stacked kernel's cycle counters (launches made with PB_TC_PROBE=1)
+extern "C" int pb_conv3d_tc_debug(unsigned long long* out8) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, tc_dbg, sizeof(z)) != cudaSuccess) return PB_ECUDA;
+    if (cudaMemcpyToSymbol(tc_dbg, z, sizeof(z)) != cudaSuccess) return PB_ECUDA;
+    return PB_OK;
+}
+
 extern "C" int pb_conv3d_tc(const pb_conv_desc* d, const void* x0, const void* x1, const void* wimg, const float* bias,
                             void* y0, void* y1, int co0, int co1, double* stats, int* err_flag, pb_stream_t stream) {
     PB_CHECK_ARG(d && x0 && wimg && y0 && err_flag, "null pointer");
@@ -1529,6 +1554,7 @@ int tc_entry(const pb_conv_desc* d, const void* x0, const void* x1, const void* 
         }
     }
     p.w_tile_bytes = (long long)27 * nch * NT * 16;
+    { const char* e = getenv("PB_TC_PROBE"); p.probe = e ? atoi(e) : 0; }
     if (p.slab_need * nchr > max_copies(nchr) * kTcProducers) {
         pb_set_error("conv3d_tc: plane slab of %d x %d copies exceeds the producer budget", p.slab_need, nchr);
         return PB_EUNSUPPORTED;
