@@ -130,6 +130,31 @@ int pb_wgrad_rs_debug(unsigned long long* out8);
 int pb_conv3d_tc_debug(unsigned long long* out8);
 int pb_gemm_tc(const void* a, const void* b, const float* bias, void* d, float* workspace, int M, int N, int K, int lda, int ldb,
                int ldd, int a_kmajor, int b_kmajor, int d_fp32, int* err_flag, pb_stream_t stream);
+/* The same GEMM once per (b0, b1) — the attention products of SelfAttention.forward (reference models/mmformer.py:203-213), one
+ * problem per (sample, head): S = Q K^T, O = P V and the four gradient products, with Q / K / V read in place as column blocks of the
+ * [tokens][3 * dim] qkv rows.  sa0 / sa1, sb0 / sb1, sd0 / sd1 = element strides of A, B, D over the two batch indices (multiples of
+ * 8 for the operands); rows beyond M / N / K inside one batch entry read as zero, never as the next entry's data.  No bias, no split-K. */
+int pb_gemm_tc_batched(const void* a, const void* b, void* d, int M, int N, int K, int lda, int ldb, int ldd, int a_kmajor, int b_kmajor,
+                       int d_fp32, int nb0, int nb1, long long sa0, long long sa1, long long sb0, long long sb1, long long sd0,
+                       long long sd1, int* err_flag, pb_stream_t stream);
+/* Row kernels of the token path (csrc/attn.cu).
+ * pb_attn_softmax_fwd — reference mmformer.py:206-208: p = softmax(scale * s) over the T keys of each of `rows` fp32 score rows
+ *   (row stride T), written as bf16 with row stride ldp >= T (a multiple of 8 so that p can be a TMA operand; pad columns are
+ *   written as zero); with drop_p > 0 also p_drop = p * keep / (1 - drop_p), keep drawn from a counter hash of the device-side
+ *   int64 *seed (give a fresh one per call), else p_drop = NULL.
+ * pb_attn_softmax_bwd — ds = scale * (p_drop .* dp - p * sum_j(p_drop_j dp_j)) (bf16, row stride ldp) from the fp32 gradient dp
+ *   (row stride T) with respect to p_drop; without dropout pass p for p_drop.
+ * pb_layernorm_fwd / _bwd — nn.LayerNorm over the last dimension (mmformer.py:233-250), C in {256, 512, 1024}, x / y / dy / dx in
+ *   `dtype` (PB_F32 | PB_BF16), affine parameters and statistics fp32; mean / rstd [rows] are written by the forward and read by
+ *   the backward; dw / db [C] fp32 are ACCUMULATED into (zero them first). */
+int pb_attn_softmax_fwd(const float* s, void* p, void* p_drop, long long rows, int T, int ldp, float scale, float drop_p,
+                        const long long* seed, pb_stream_t stream);
+int pb_attn_softmax_bwd(const float* dp, const void* p, const void* p_drop, void* ds, long long rows, int T, int ldp, float scale,
+                        pb_stream_t stream);
+int pb_layernorm_fwd(int dtype, const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, long long rows, int C,
+                     float eps, pb_stream_t stream);
+int pb_layernorm_bwd(int dtype, const void* dy, const void* x, const float* mean, const float* rstd, const float* w, void* dx, float* dw,
+                     float* db, long long rows, int C, pb_stream_t stream);
 int pb_conv3d_tc_full(const pb_conv_desc* d, const void* x, const void* wimg, void* y0, void* y1, int co0, int co1,
                       void* yext, int* err_flag, pb_stream_t stream);
 int pb_reflect_fold(const void* yext, void* y0, void* y1, int n, int d, int h, int w, int co0, int co1, pb_stream_t stream);

@@ -89,6 +89,11 @@ def load():
         "pb_reflect_fold": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "pb_conv3d_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_gemm_tc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
+        "pb_gemm_tc_batched": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, vp],
+        "pb_attn_softmax_fwd": [vp, vp, vp, i64, i32, i32, f32, f32, vp, vp],
+        "pb_attn_softmax_bwd": [vp, vp, vp, vp, i64, i32, i32, f32, vp],
+        "pb_layernorm_fwd": [i32, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp],
+        "pb_layernorm_bwd": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
         "pb_conv1_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],
         "pb_conv3d_dgrad_reflect_fix": [cd, vp, vp, vp, vp, vp],
         "pb_conv3d_small_supported": [i32, i32],

@@ -12,6 +12,9 @@
 // MMA-issuing thread (M = 128, N = 64, K = 16), epilogue TMEM -> registers -> (+ bias) -> global.  Outputs with few tiles and a long
 // K (FFN down: 250 x 512 x 4096) run split-K into a zero-filled fp32 workspace (float4 atomics) + a small finalize launch.
 // Warp roles: warps 0-3 epilogue, warp 4 MMA issue + TMEM allocation, warp 5 TMA producer.
+// Batched form (pb_gemm_tc_batched; the attention products Q K^T, P V and their four gradients, reference mmformer.py:203-213, one
+// problem per (sample, head)): the tensor maps carry the two batch indices as their own dimensions, so operand rows beyond M / N / K
+// are zero fill and never the next head's data; blockIdx.z is the (sample, head) pair, no split-K.
 #include <cstdlib>
 #include <cstring>
 #include "tc_common.cuh"
@@ -29,11 +32,14 @@ struct GemmP {
     int M, N, K, ldd;
     int a_kmajor, b_kmajor, d_fp32;
     int splits;                       // split-K: blockIdx.z takes a range of K blocks and adds its partial tile into the fp32 workspace
+    int nb1;                          // batched: blockIdx.z = b0 * nb1 + b1 (splits == 1); 0 = not batched
+    long long sd0, sd1;               // element strides of D over the two batch indices
 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+// operand maps are 4-D: (inner, outer, batch index 1, batch index 0); the unbatched entry point uses batch extents of 1
+__device__ __forceinline__ void tma_load_op(uint32_t dst, const CUtensorMap* map, int c0, int c1, int b1, int b0, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(b1), "r"(b0), "r"(smem_u32(bar)) : "memory");
 }
 
 // SWIZZLE_128B descriptors (layout type 2).  K-major: 8-row groups of 128-byte rows at SBO = 1024 B (LBO unused); a K = 16 step is
@@ -59,7 +65,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * kGBN, m0 = blockIdx.y * kGBM;
     const int kblocks_all = (p.K + kGBK - 1) / kGBK;
-    const int kb_lo = (int)((long long)blockIdx.z * kblocks_all / p.splits), kb_hi = (int)((long long)(blockIdx.z + 1) * kblocks_all / p.splits);
+    const int zs = p.nb1 ? 0 : (int)blockIdx.z;                                   // split index
+    const int bt0 = p.nb1 ? (int)blockIdx.z / p.nb1 : 0, bt1 = p.nb1 ? (int)blockIdx.z % p.nb1 : 0;
+    const int kb_lo = (int)((long long)zs * kblocks_all / p.splits), kb_hi = (int)((long long)(zs + 1) * kblocks_all / p.splits);
     const int kblocks = kb_hi - kb_lo;
 
     if (threadIdx.x == 0) {
@@ -84,10 +92,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                 mbar_expect_tx(&full[slot], (uint32_t)(kGTileA + kGTileB));
                 const uint32_t ad = smem_u32(a_s) + slot * kGTileA, bd = smem_u32(b_s) + slot * kGTileB;
                 const int k0 = (kb_lo + kb) * kGBK;
-                if (p.a_kmajor) tma_load_2d(ad, &amap, k0, m0, &full[slot]);
-                else { tma_load_2d(ad, &amap, m0, k0, &full[slot]); tma_load_2d(ad + kGTileA / 2, &amap, m0 + 64, k0, &full[slot]); }
-                if (p.b_kmajor) tma_load_2d(bd, &bmap, k0, n0, &full[slot]);
-                else tma_load_2d(bd, &bmap, n0, k0, &full[slot]);                     // 64 rows: one box
+                if (p.a_kmajor) tma_load_op(ad, &amap, k0, m0, bt1, bt0, &full[slot]);
+                else {
+                    tma_load_op(ad, &amap, m0, k0, bt1, bt0, &full[slot]);
+                    tma_load_op(ad + kGTileA / 2, &amap, m0 + 64, k0, bt1, bt0, &full[slot]);
+                }
+                if (p.b_kmajor) tma_load_op(bd, &bmap, k0, n0, bt1, bt0, &full[slot]);
+                else tma_load_op(bd, &bmap, n0, k0, bt1, bt0, &full[slot]);           // 64 rows: one box
             }
         }
     } else if (warp == 4) {
@@ -114,6 +125,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         tc_fence_after();
         const int m = m0 + warp * 32 + lane;                 // accumulator row = TMEM lane
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const long long doff = (long long)bt0 * p.sd0 + (long long)bt1 * p.sd1;      // batch offset of D (elements)
+        const bool vec_ok = p.d_fp32 ? (((p.ldd | doff) & 3) == 0) : (((p.ldd | doff) & 7) == 0);
 #pragma unroll 1
         for (int c = 0; c < kGBN; c += 16) {
             float v[16];
@@ -135,16 +148,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                     for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __ldg(bias + n + j);
                 }
                 if (p.d_fp32) {
-                    float* dst = reinterpret_cast<float*>(dout) + (size_t)m * p.ldd + n;
-                    if (n + 16 <= p.N && (p.ldd & 3) == 0) {
+                    float* dst = reinterpret_cast<float*>(dout) + doff + (size_t)m * p.ldd + n;
+                    if (n + 16 <= p.N && vec_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     } else {
                         for (int j = 0; j < 16 && n + j < p.N; ++j) dst[j] = v[j];
                     }
                 } else {
-                    bf16* dst = reinterpret_cast<bf16*>(dout) + (size_t)m * p.ldd + n;
-                    if (n + 16 <= p.N && (p.ldd & 7) == 0) {
+                    bf16* dst = reinterpret_cast<bf16*>(dout) + doff + (size_t)m * p.ldd + n;
+                    if (n + 16 <= p.N && vec_ok) {
                         VecIO<bf16, 8>::store(dst, v);
                         VecIO<bf16, 8>::store(dst + 8, v + 8);
                     } else {
@@ -184,15 +197,17 @@ int gemm_splits(int M, int N, int K) {
     return s < 1 ? 1 : s;
 }
 
-// operand stored [outer][inner] with `ld` elements between outer rows; box = [box_outer][64 inner]
-int make_operand_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_outer) {
+// operand stored [b0][b1][outer][inner] with `ld` elements between outer rows and s0 / s1 elements between batch entries (any order in
+// memory: a head is a column block of the qkv rows); box = [1][1][box_outer][64 inner]
+int make_operand_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_outer, int nb0 = 1, int nb1 = 1,
+                     long long s0 = 0, long long s1 = 0) {
     EncodeTiledFn enc = encode_tiled();
     if (enc == nullptr) return -1;
-    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    const cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nb1, (cuuint64_t)nb0};
+    const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb1 > 1 ? s1 : ld) * 2, (cuuint64_t)(nb0 > 1 ? s0 : ld) * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_outer, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
@@ -213,6 +228,7 @@ extern "C" int pb_gemm_tc(const void* a, const void* b, const float* bias, void*
     GemmP p;
     p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.a_kmajor = a_kmajor; p.b_kmajor = b_kmajor; p.d_fp32 = d_fp32;
     p.splits = gemm_splits(M, N, K);
+    p.nb1 = 0; p.sd0 = p.sd1 = 0;
     PB_CHECK_ARG(p.splits == 1 || workspace, "this shape runs split-K: pass a zero-filled workspace of pb_gemm_tc_workspace_floats(M, N, K) floats");
     CUtensorMap amap, bmap;
     // K-major: [rows][K] -> inner = K, box [128 rows][64 K];  MN-major: [K][rows] -> inner = rows, box [64 K][64 rows]
@@ -232,5 +248,31 @@ extern "C" int pb_gemm_tc(const void* a, const void* b, const float* bias, void*
         gemm_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ws, bias, d, M, N, ldd, d_fp32);
         PB_CHECK_LAUNCH();
     }
+    return PB_OK;
+}
+
+// one GEMM per (b0, b1): operand / result element strides over the two batch indices are free (a head may be a column block of a row)
+extern "C" int pb_gemm_tc_batched(const void* a, const void* b, void* d, int M, int N, int K, int lda, int ldb, int ldd, int a_kmajor, int b_kmajor,
+                                  int d_fp32, int nb0, int nb1, long long sa0, long long sa1, long long sb0, long long sb1, long long sd0,
+                                  long long sd1, int* err_flag, pb_stream_t stream) {
+    PB_CHECK_ARG(a && b && d && err_flag, "null pointer");
+    PB_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && nb0 >= 1 && nb1 >= 1, "empty problem");
+    PB_CHECK_ARG((long long)nb0 * nb1 <= 65535, "more than 65535 batch entries");
+    PB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && sa0 % 8 == 0 && sa1 % 8 == 0 && sb0 % 8 == 0 && sb1 % 8 == 0,
+                 "operand leading dimensions and batch strides must be multiples of 8 elements (16-byte TMA strides)");
+    PB_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "operands must be 16-byte aligned");
+    GemmP p;
+    p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.a_kmajor = a_kmajor; p.b_kmajor = b_kmajor; p.d_fp32 = d_fp32;
+    p.splits = 1; p.nb1 = nb1; p.sd0 = sd0; p.sd1 = sd1;
+    CUtensorMap amap, bmap;
+    const int ra = a_kmajor ? make_operand_map(&amap, a, K, M, lda, kGBM, nb0, nb1, sa0, sa1) : make_operand_map(&amap, a, M, K, lda, kGBK, nb0, nb1, sa0, sa1);
+    const int rb = b_kmajor ? make_operand_map(&bmap, b, K, N, ldb, kGBN, nb0, nb1, sb0, sb1) : make_operand_map(&bmap, b, N, K, ldb, kGBK, nb0, nb1, sb0, sb1);
+    if (ra || rb) { pb_set_error("pb_gemm_tc_batched: cuTensorMapEncodeTiled failed (a %d, b %d; M %d N %d K %d lda %d ldb %d batch %d x %d)", ra, rb, M, N, K, lda, ldb, nb0, nb1); return PB_EUNSUPPORTED; }
+    const size_t smem = (size_t)kGSlots * (kGTileA + kGTileB) + (2 * kGSlots + 1) * 8 + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pb_set_error("pb_gemm_tc_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
+    const dim3 grid((N + kGBN - 1) / kGBN, (M + kGBM - 1) / kGBM, nb0 * nb1);
+    gemm_tc_kernel<<<grid, kGThreads, smem, (cudaStream_t)stream>>>(amap, bmap, p, nullptr, d, nullptr, err_flag);
+    PB_CHECK_LAUNCH();
     return PB_OK;
 }

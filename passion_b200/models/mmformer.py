@@ -242,16 +242,17 @@ class Transformer(nn.Module):
             return ops.linear(t, layer.weight, layer.bias)
 
         def ln(t, layer):
-            return F.layer_norm(t.float(), (t.shape[-1],), layer.weight, layer.bias, layer.eps).to(dt)
+            # nn.LayerNorm of PreNorm / PreNormDrop (mmformer.py:233-250): csrc/attn.cu
+            return ops.layer_norm(t, layer.weight, layer.bias, layer.eps)
 
         for j in range(self.depth):
             x = x + pos.to(dt)
             pn = self.cross_attention_list[j].fn
             sa = pn.fn
             N, T, C = x.shape
-            qkv = lin(ln(x, pn.norm), sa.qkv).view(N, T, 3, sa.num_heads, C // sa.num_heads).permute(2, 0, 3, 1, 4)
-            h = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], dropout_p=p)
-            h = F.dropout(lin(h.transpose(1, 2).reshape(N, T, C), sa.proj), p, self.training)
+            qkv = lin(ln(x, pn.norm), sa.qkv).view(N, T, 3, sa.num_heads, C // sa.num_heads)
+            # softmax(q k^T / sqrt(d)) v with attention dropout (mmformer.py:203-213): batched tcgen05 GEMMs + row softmax in bf16
+            h = F.dropout(lin(ops.attention(qkv, p), sa.proj), p, self.training)
             x = x + F.dropout(h, p, self.training)
             pf = self.cross_ffn_list[j].fn
             net = pf.fn.net

@@ -1339,3 +1339,137 @@ def linear(x, weight, bias=None):
     shp = x.shape
     y = _LinearTC.apply(x.reshape(-1, shp[-1]).contiguous(), weight, bias)
     return y.view(*shp[:-1], weight.shape[0])
+
+
+# ------------------------------------------------------------------------------------ attention + LayerNorm of the token path
+ATTN_TC = os.environ.get("PB_ATTN_TC", "1") != "0"
+
+
+def _gemm_tc_batched(name, a, b, out, M, N, K, lda, ldb, ldd, a_kmajor, b_kmajor, nb0, nb1, sa, sb, sd):
+    lib = _lib.load()
+    err = _tc_err_flag(a.device)
+    nb = nb0 * nb1
+    _run(name, f"b{nb} m{M} n{N} k{K}", nb * ((M * K + N * K) * 2 + M * N * out.element_size()), 2.0 * nb * M * N * K,
+         lambda: lib.pb_gemm_tc_batched(_p(a), _p(b), _p(out), M, N, K, lda, ldb, ldd, int(a_kmajor), int(b_kmajor),
+                                        int(out.dtype == torch.float32), nb0, nb1, sa[0], sa[1], sb[0], sb[1], sd[0], sd[1], _p(err),
+                                        _stream()))
+
+
+class _AttentionTC(torch.autograd.Function):
+    """softmax(q k^T / sqrt(d)) v per (sample, head) with attention dropout — SelfAttention.forward, reference models/mmformer.py:203-213
+    — on the batched tcgen05 GEMM (csrc/gemm_tc.cu) and the row kernels of csrc/attn.cu.  qkv [N, T, 3, H, d] bf16 as the qkv GEMM
+    wrote it (the heads are read in place as column blocks of its rows); returns [N, T, H * d] bf16, the layout the proj GEMM reads.
+    Scores and their gradient are fp32 [N, H, T, T]; the probabilities are kept as bf16 (P, and with dropout P' = P keep / (1 - p))."""
+
+    @staticmethod
+    def forward(ctx, qkv, drop_p):
+        lib = _lib.load()
+        N, T, _, H, d = qkv.shape
+        C = H * d
+        dev = qkv.device
+        ldp = (T + 7) // 8 * 8
+        scale = float(d) ** -0.5
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]            # views: [N, T, H, d], row stride 3C, head stride d
+        sq = (T * 3 * C, d)
+        s = torch.empty((N, H, T, T), dtype=torch.float32, device=dev)
+        # S[t][u] = sum_c q[t][c] k[u][c]
+        _gemm_tc_batched("attn_qk", q, k, s, T, T, d, 3 * C, 3 * C, T, True, True, N, H, sq, sq, (H * T * T, T * T))
+        p = torch.empty((N, H, T, ldp), dtype=torch.bfloat16, device=dev)
+        if drop_p > 0.0:
+            pd = torch.empty_like(p)
+            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=dev)      # graph-safe: drawn from torch's CUDA generator
+        else:
+            pd, seed = None, None
+        _run("attn_softmax_fwd", f"t{T}", N * H * T * (T * 4 + ldp * (2 if pd is None else 4)), 0.0,
+             lambda: lib.pb_attn_softmax_fwd(_p(s), _p(p), _p(pd), N * H * T, T, ldp, scale, float(drop_p), _p(seed), _stream()))
+        del s
+        pm = p if pd is None else pd
+        o = torch.empty((N, T, C), dtype=torch.bfloat16, device=dev)
+        # O[t][c] = sum_u P'[t][u] v[u][c]: B = v read as [reduction = u][rows = c]
+        _gemm_tc_batched("attn_pv", pm, v, o, T, d, T, ldp, 3 * C, C, True, False, N, H, (H * T * ldp, T * ldp), sq, (T * C, d))
+        ctx.save_for_backward(qkv, p, pm)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        lib = _lib.load()
+        qkv, p, pm = ctx.saved_tensors
+        N, T, _, H, d = qkv.shape
+        C = H * d
+        dev = qkv.device
+        ldp = p.shape[-1]
+        do = do.contiguous()
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        sq, sp, so = (T * 3 * C, d), (H * T * ldp, T * ldp), (T * C, d)
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]
+        # dV[u][c] = sum_t P'[t][u] dO[t][c]: both operands read as [reduction = t][rows]
+        _gemm_tc_batched("attn_dv", pm, do, dv, T, d, T, ldp, C, 3 * C, False, False, N, H, sp, so, sq)
+        # dP'[t][u] = sum_c dO[t][c] v[u][c]
+        dp = torch.empty((N, H, T, T), dtype=torch.float32, device=dev)
+        _gemm_tc_batched("attn_dp", do, v, dp, T, T, d, C, 3 * C, T, True, True, N, H, so, sq, (H * T * T, T * T))
+        ds = torch.empty((N, H, T, ldp), dtype=torch.bfloat16, device=dev)
+        _run("attn_softmax_bwd", f"t{T}", N * H * T * (T * 4 + ldp * 6), 0.0,
+             lambda: lib.pb_attn_softmax_bwd(_p(dp), _p(p), _p(pm), _p(ds), N * H * T, T, ldp, ctx.scale, _stream()))
+        del dp
+        # dQ[t][c] = sum_u dS[t][u] k[u][c];  dK[u][c] = sum_t dS[t][u] q[t][c]
+        _gemm_tc_batched("attn_dq", ds, k, dq, T, d, T, ldp, 3 * C, 3 * C, True, False, N, H, sp, sq, sq)
+        _gemm_tc_batched("attn_dk", ds, q, dk, T, d, T, ldp, 3 * C, 3 * C, False, False, N, H, sp, sq, sq)
+        return dqkv, None
+
+
+def attention_tc_eligible(qkv):
+    return (ATTN_TC and LINEAR_TC and TC_ENABLED and qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.dim() == 5
+            and qkv.shape[-1] % 8 == 0 and qkv.shape[0] * qkv.shape[3] <= 65535)
+
+
+def attention(qkv, drop_p=0.0):
+    """qkv [N, T, 3, H, d] -> [N, T, H * d]: bf16 on the tcgen05 path above; otherwise (fp32 check mode) the library's fused attention."""
+    if attention_tc_eligible(qkv):
+        return _AttentionTC.apply(qkv.contiguous(), float(drop_p))
+    N, T, _, H, d = qkv.shape
+    t = qkv.permute(2, 0, 3, 1, 4)
+    h = torch.nn.functional.scaled_dot_product_attention(t[0], t[1], t[2], dropout_p=drop_p)
+    return h.transpose(1, 2).reshape(N, T, H * d)
+
+
+class _LayerNorm(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension (PreNorm / PreNormDrop, reference models/mmformer.py:233-250): csrc/attn.cu, statistics
+    and affine parameters in fp32, activations in their storage type."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        lib = _lib.load()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
+        _run("layernorm_fwd", f"c{C}", 2 * x.numel() * x.element_size(), 0.0,
+             lambda: lib.pb_layernorm_fwd(_dt(x), _p(x), _p(wf), _p(bf), _p(y), _p(mean), _p(rstd), rows, C, float(eps), _stream()))
+        ctx.save_for_backward(x, wf, mean, rstd)
+        ctx.pdt = (w.dtype, b.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, wf, mean, rstd = ctx.saved_tensors
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        acc = _scratch.zeros((2, C), torch.float32, x.device)
+        _run("layernorm_bwd", f"c{C}", 3 * x.numel() * x.element_size(), 0.0,
+             lambda: lib.pb_layernorm_bwd(_dt(x), _p(dy), _p(x), _p(mean), _p(rstd), _p(wf), _p(dx), _p(acc[0]), _p(acc[1]), rows, C, _stream()))
+        # copies: the accumulators live in the zero-scratch arena, which the next step clears
+        return dx, acc[0].to(ctx.pdt[0], copy=True), acc[1].to(ctx.pdt[1], copy=True), None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    """F.layer_norm over the last dimension on csrc/attn.cu (fp32 or bf16 activations, C in {256, 512, 1024})."""
+    if not (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.shape[-1] in (256, 512, 1024)):
+        return torch.nn.functional.layer_norm(x.float(), (x.shape[-1],), weight, bias, eps).to(x.dtype)
+    return _LayerNorm.apply(x.contiguous(), weight, bias, eps)
