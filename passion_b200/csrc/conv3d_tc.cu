@@ -29,7 +29,9 @@ constexpr int kTcThreads = 288;         // conv3_tc_kernel: 4 epilogue warps, 1 
 constexpr int kTcProducers = 128;
 constexpr int kMaxCopies = 16;          // 16-B copies per producer thread and plane ...
 constexpr int kMaxCopiesWide = 20;      // ... and for the 64-channel variants (NCHR = 8, which have registers to spare)
-__host__ __device__ constexpr int max_copies(int nchr) { return nchr >= 8 ? kMaxCopiesWide : kMaxCopies; }
+constexpr int kMaxCopies128 = 26;       // 128 input channels (NCHR = 16): planes up to W = 37 (mmFormer's 128 -> 64 decoder conv runs at 16^3;
+                                        // with 20 the 16^3 launch fell back to the FFMA kernel: 2 x 1.9 ms per step at 128^3)
+__host__ __device__ constexpr int max_copies(int nchr) { return nchr >= 16 ? kMaxCopies128 : nchr >= 8 ? kMaxCopiesWide : kMaxCopies; }
 constexpr int kWgCopies = 5;            // weight-gradient kernels: slab rows per producer thread (planes up to W = 174)
 constexpr int kTileM = 128;
 

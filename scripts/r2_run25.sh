@@ -1,5 +1,6 @@
 #!/bin/bash
-timeout 300 python train.py --use_passion --batch_size 2 --synthetic --num_epochs 2 --iters_per_epoch 8 --savepath /tmp/mm 2>&1 | grep -E "Iter 8/8|rp_epoch" | cut -c25-190
-timeout 300 python train.py --use_passion --model rfnet --batch_size 2 --synthetic --num_epochs 1 --iters_per_epoch 8 --savepath /tmp/rf 2>&1 | grep -E "Iter 8/8|rp_epoch" | cut -c25-190
-timeout 300 python train.py --use_passion --batch_size 2 --synthetic --num_epochs 1 --iters_per_epoch 8 --device_aug --savepath /tmp/mmd 2>&1 | grep -E "Iter 8/8" | cut -c25-170
-timeout 900 python -m pytest tests/test_model_gpu.py tests/test_mmformer_gpu.py tests/test_augment_gpu.py -m gpu -q -p no:cacheprovider 2>&1 | tail -2
+mkdir -p gpurun_out/r2y
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -p no:cacheprovider -k "stay_on_tcgen05 or c64+64_64_k3 or c128+0_64_k3" 2>&1 | tail -25 | cut -c1-300
+for i in 1 2; do
+timeout 600 python bench.py --model mmformer --size 128 --batch 1 --no-cpu-baseline --no-extras --steps 8 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('mmformer 128^3', d['ms_per_step'], d['value'], 'last_loss', d['e2e']['last_loss'])" | tee -a gpurun_out/r2y/ab2.log
+done

@@ -68,6 +68,9 @@ CONV_CASES = [
     (8, 0, 8, 3, 1, "reflect", 1, 1, (3, 5, 128), True),
     (16, 0, 16, 3, 1, "zeros", 1, 1, (3, 4, 128), True),
     (64, 0, 32, 3, 1, "reflect", 1, 1, (4, 5, 32), True),
+    # 128 input channels on planes wider than RFNet's 10^3: mmFormer's 64 + 64 -> 64 decoder conv at 16^3 (128^3 crop) and a W = 30 plane
+    (64, 64, 64, 3, 1, "reflect", 1, 1, (16, 16, 16), True),
+    (128, 0, 64, 3, 1, "zeros", 1, 1, (3, 20, 30), True),
     # very few channels: shared-memory tiled kernels (several tiles in d and in the plane, ragged edges, zero padding)
     (2, 0, 2, 3, 1, "reflect", 1, 2, (20, 18, 22), False),
     (2, 0, 2, 3, 1, "zeros", 1, 2, (6, 7, 8), True),
@@ -128,6 +131,42 @@ def test_conv3d(lib_built, case, dtype):
         npg_ = n // groups
         ref_db = torch.stack([gy.double()[gi * npg_:(gi + 1) * npg_].sum((0, 2, 3, 4)) for gi in range(groups)])
         assert rel(bk.grad, ref_db) < 1e-3
+    ops.check_tc_errors()
+
+
+# (c0, c1, cout, plane size): the stride-1 3x3x3 classes of RFNet at 80^3 and of mmFormer at 128^3, on the plane sizes they run at
+ROUTED_CLASSES = [(8, 0, 8, 80), (8, 8, 8, 80), (16, 0, 16, 40), (16, 16, 16, 40), (32, 0, 32, 20), (32, 32, 32, 20), (64, 0, 64, 10),
+                  (8, 0, 8, 128), (8, 8, 8, 128), (16, 0, 16, 64), (16, 16, 16, 64), (32, 0, 32, 32), (32, 32, 32, 32), (64, 0, 64, 16),
+                  (64, 64, 64, 16), (128, 0, 128, 8)]
+
+
+@pytest.mark.parametrize("case", ROUTED_CLASSES, ids=lambda c: "c%d+%d_%d_s%d" % c)
+def test_conv3d_bf16_classes_stay_on_tcgen05(lib_built, case):
+    """No silent fall-back: every stride-1 3x3x3 bf16 class of the two backbones, at the plane size it has in the benchmark
+    configurations, must run its forward, data gradient and weight gradient on the tcgen05 kernels.  (ops falls back to the FFMA
+    kernels when a tcgen05 launch reports PB_EUNSUPPORTED; the 64 + 64 -> 64 conv of mmFormer at 16^3 did so for a whole round
+    because its plane exceeded the producer budget sized on RFNet's 10^3 — 3.7 ms of a 36 ms step.)"""
+    from passion_b200 import ops
+    c0, c1, cout, S = case
+    g = torch.Generator(device="cpu").manual_seed(S + cout)
+    d = min(S, 4)
+    x0 = torch.randn(1, d, S, S, c0, generator=g).cuda().bfloat16().requires_grad_(True)
+    x1 = torch.randn(1, d, S, S, c1, generator=g).cuda().bfloat16().requires_grad_(True) if c1 else None
+    wk = (torch.randn(1, 27, c0 + c1, cout, generator=g) / (27 * (c0 + c1)) ** 0.5).cuda().requires_grad_(True)
+    timer = ops.KernelTimer()
+    ops.TIMER = timer
+    try:
+        y, _ = ops.conv3d(x0, wk, None, x1, ksize=3, stride=1, pad_mode="reflect")
+        y.backward(torch.randn(y.shape, generator=g).cuda().bfloat16())
+        torch.cuda.synchronize()
+    finally:
+        ops.TIMER = None
+    names = {r[0] for r in timer.records}
+    generic = names & {"conv3d_fwd", "conv3d_dgrad", "conv3d_wgrad", "conv3d_small_fwd", "conv3d_small_dgrad", "conv3d_small_wgrad"}
+    if cout > 64:
+        generic -= {"conv3d_wgrad"}            # the tcgen05 weight gradients hold Cout <= 64 rows (documented limit; 8^3 volumes only)
+    assert not generic, (names, generic)
+    assert {"conv3d_fwd_tc", "conv3d_dgrad_tc"} <= names
     ops.check_tc_errors()
 
 
