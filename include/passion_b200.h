@@ -151,6 +151,17 @@ int pb_attn_softmax_fwd(const float* s, void* p, void* p_drop, long long rows, i
                         const long long* seed, pb_stream_t stream);
 int pb_attn_softmax_bwd(const float* dp, const void* p, const void* p_drop, void* ds, long long rows, int T, int ldp, float scale,
                         pb_stream_t stream);
+/* The same two softmax steps FUSED with the score products (csrc/gemm_tc.cu attn_rows_kernel; head width d <= 64): no [N][H][T][T] fp32
+ * tensor is written.  q / k / v / d_o are [N][T][H][d] views: ld = elements between tokens, s0 between samples, s1 between heads.
+ *   pb_attn_scores_softmax: p (and p_drop) = softmax(scale * q k^T) per (sample, head), as pb_attn_softmax_fwd would write them;
+ *   pb_attn_delta:          delta[n][h][t] = sum_c d_o[n][t][h][c] * o[n][t][h][c]  (contiguous d_o, o);
+ *   pb_attn_dsoftmax:       ds = scale * (p_drop .* (d_o v^T) - p * delta), as pb_attn_softmax_bwd would write it. */
+int pb_attn_scores_softmax(const void* q, const void* k, void* p, void* p_drop, int N, int H, int T, int d, int ld, long long s0,
+                           long long s1, int ldp, float scale, float drop_p, const long long* seed, int* err_flag, pb_stream_t stream);
+int pb_attn_delta(const void* d_o, const void* o, float* delta, int N, int T, int H, int d, pb_stream_t stream);
+int pb_attn_dsoftmax(const void* d_o, const void* v, const void* p, const void* p_drop, const float* delta, void* ds, int N, int H,
+                     int T, int d, int ld_o, long long so0, long long so1, int ld_v, long long sv0, long long sv1, int ldp,
+                     float scale, int* err_flag, pb_stream_t stream);
 int pb_layernorm_fwd(int dtype, const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, long long rows, int C,
                      float eps, pb_stream_t stream);
 int pb_layernorm_bwd(int dtype, const void* dy, const void* x, const float* mean, const float* rstd, const float* w, void* dx, float* dw,

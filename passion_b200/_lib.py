@@ -92,6 +92,9 @@ def load():
         "pb_gemm_tc_batched": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, vp, vp],
         "pb_attn_softmax_fwd": [vp, vp, vp, i64, i32, i32, f32, f32, vp, vp],
         "pb_attn_softmax_bwd": [vp, vp, vp, vp, i64, i32, i32, f32, vp],
+        "pb_attn_scores_softmax": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i32, f32, f32, vp, vp, vp],
+        "pb_attn_delta": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "pb_attn_dsoftmax": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i32, i64, i64, i32, f32, vp, vp],
         "pb_layernorm_fwd": [i32, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp],
         "pb_layernorm_bwd": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
         "pb_conv1_wgrad_tc": [cd, vp, vp, vp, vp, vp, vp],

@@ -14,16 +14,6 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// 32 uniform bits per (seed, element): splitmix64 finaliser of a counter — the dropout mask only has to be reproducible within one
-// forward (the backward reads P and P', it never regenerates the mask) and independent between steps (a fresh device-side seed).
-__device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned long long idx) {
-    unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z ^= z >> 31;
-    return (uint32_t)(z >> 32);
-}
-
 __global__ void __launch_bounds__(256)
 attn_softmax_fwd_kernel(const float* __restrict__ s, bf16* __restrict__ p, bf16* __restrict__ pd, long long rows, int T, int ldp, float scale,
                         float drop_p, const long long* __restrict__ seed_ptr) {
@@ -47,7 +37,7 @@ attn_softmax_fwd_kernel(const float* __restrict__ s, bf16* __restrict__ p, bf16*
         const float v = j < T ? __expf((sr[j] - mx) * scale) * inv : 0.f;
         pr[j] = __float2bfloat16_rn(v);
         if (pdr) {
-            const bool keep = hash_u32(seed, (unsigned long long)row * (unsigned long long)T + j) >= thresh;
+            const bool keep = pb_dropout_bits(seed, (unsigned long long)row * (unsigned long long)T + j) >= thresh;
             pdr[j] = __float2bfloat16_rn(keep ? v * keep_scale : 0.f);
         }
     }
@@ -70,6 +60,28 @@ attn_softmax_bwd_kernel(const float* __restrict__ dp, const bf16* __restrict__ p
         const float v = j < T ? scale * (__bfloat162float(pdr[j]) * dr[j] - __bfloat162float(pr[j]) * dot) : 0.f;
         dsr[j] = __float2bfloat16_rn(v);
     }
+}
+
+// delta[n][h][t] = sum_c dO[n][t][h][c] * O[n][t][h][c]  (= sum_j P'_j dP'_j, the row term of the softmax backward)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ d_o, const bf16* __restrict__ o, float* __restrict__ delta, int N, int T, int H, int d) {
+    const long long total = (long long)N * T * H;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;             // (n, t, h), h fastest: neighbours read neighbours
+    if (i >= total) return;
+    const int h = (int)(i % H);
+    const long long nt = i / H;
+    const int t = (int)(nt % T), n = (int)(nt / T);
+    const bf16* a = d_o + i * d;
+    const bf16* b = o + i * d;
+    float acc = 0.f;
+    for (int c = 0; c < d; c += 8) {
+        float x[8], y[8];
+        VecIO<bf16, 8>::load(a + c, x);
+        VecIO<bf16, 8>::load(b + c, y);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += x[e] * y[e];
+    }
+    delta[((long long)n * H + h) * T + t] = acc;
 }
 
 // ---- LayerNorm: C = 256 * NV channels, a lane holds NV vectors of 8 ----
@@ -243,6 +255,17 @@ extern "C" int pb_layernorm_bwd(int dtype, const void* dy, const void* x, const 
     const int r = dtype == PB_F32 ? ln_bwd_dispatch<float>(dy, x, mean, rstd, w, dx, dw, db, rows, C, (cudaStream_t)stream)
                                   : ln_bwd_dispatch<bf16>(dy, x, mean, rstd, w, dx, dw, db, rows, C, (cudaStream_t)stream);
     PB_CHECK_ARG(r == 0, "unsupported width");
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+// delta [N][H][T] fp32 from the contiguous bf16 d_o and o [N][T][H][d] (d a multiple of 8): input of pb_attn_dsoftmax
+extern "C" int pb_attn_delta(const void* d_o, const void* o, float* delta, int N, int T, int H, int d, pb_stream_t stream) {
+    PB_CHECK_ARG(d_o && o && delta, "null pointer");
+    PB_CHECK_ARG(N >= 1 && T >= 1 && H >= 1 && d >= 8 && d % 8 == 0, "bad shape");
+    const long long total = (long long)N * T * H;
+    PB_CHECK_ARG((total + 255) / 256 <= 2147483647LL, "too many rows");
+    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)d_o, (const bf16*)o, delta, N, T, H, d);
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

@@ -136,6 +136,17 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// 32 uniform bits per (seed, element counter) for the attention dropout masks (csrc/attn.cu, csrc/gemm_tc.cu): a 32-bit multiply /
+// xor-shift mixer — the mask has to be reproducible within one forward pass (the backward reads the saved P and P', it never regenerates
+// the mask) and independent between steps (a fresh device-side seed per call), not cryptographic.
+__device__ __forceinline__ uint32_t pb_dropout_bits(unsigned long long seed, unsigned long long idx) {
+    uint32_t x = ((uint32_t)idx ^ (uint32_t)seed) + ((uint32_t)(idx >> 32) + (uint32_t)(seed >> 32)) * 0x9E3779B9u;
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
 // largest of {8,4,2,1} dividing c
 static inline int pb_vec_width(int c) { return (c % 8 == 0) ? 8 : (c % 4 == 0) ? 4 : (c % 2 == 0) ? 2 : 1; }
 

@@ -213,6 +213,212 @@ int make_operand_map(CUtensorMap* map, const void* base, long long inner, long l
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+
+// ------------------------------------------------------------------------------------ attention rows: scores fused with their softmax
+// The score products of SelfAttention (reference mmformer.py:205-208) never leave the SM as fp32: one CTA owns 128 query rows of one
+// (sample, head), keeps its A tile (Q, or dO in the backward; [128 rows][d <= 64] K-major) in shared memory and sweeps the key tiles
+// (K, or V; [64 keys][d]) through a 4-slot TMA ring; each 128 x 64 product lands in one of two TMEM buffers (4 MMAs, K = 64) and the
+// four epilogue warps — thread = accumulator row, so all row statistics are thread-local — consume it while the next one is computed:
+//   MODE 0 (forward), two sweeps: (1) running max and sum of exp(scale (s - max)) per row; (2) the products again (recomputing a
+//           K = 64 product is cheaper than storing 4 T^2 bytes of fp32 scores), p = exp(scale (s - max)) / sum -> bf16 P and, with
+//           dropout, P' = P keep / (1 - p_drop) (same counter hash as attn_softmax_fwd_kernel in attn.cu);
+//   MODE 1 (backward), one sweep: dP' = dO V^T per tile, dS = scale (P' .* dP' - P * delta[row]) -> bf16, with
+//           delta[row] = sum_j P'_j dP'_j = sum_c dO[row][c] O[row][c] computed beforehand from the outputs (attn_delta_kernel).
+// Against the unfused pb_gemm_tc_batched + row-kernel path this removes the write and the read of two [N, H, T, T] fp32 tensors.
+constexpr int kARows = 128, kAKeys = 64, kASlots = 4;
+constexpr int kATileA = kARows * 128, kATileB = kAKeys * 128;        // 128-byte rows (d <= 64 bf16; the tensor map zero-fills d..63)
+
+struct AttnP {
+    int T, ldp, H, ntiles;
+    float scale, keep_scale;
+    uint32_t thresh;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGThreads, 3)
+attn_rows_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, AttnP p, bf16* __restrict__ out0,
+                 bf16* __restrict__ out1, const bf16* __restrict__ pin, const bf16* __restrict__ pdin, const float* __restrict__ delta,
+                 const long long* __restrict__ seed_ptr, int* err) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a_s = smem;
+    uint8_t* b_s = smem + kATileA;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + kASlots * kATileB);
+    uint64_t* a_full = bars;
+    uint64_t* b_full = bars + 1;
+    uint64_t* b_empty = b_full + kASlots;
+    uint64_t* t_full = b_empty + kASlots;
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kARows, hh = blockIdx.y, nn = blockIdx.z;
+    const int total = (MODE == 0 ? 2 : 1) * p.ntiles;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int i = 0; i < kASlots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 5) {
+        if (lane == 0) {
+            mbar_expect_tx(a_full, (uint32_t)kATileA);
+            tma_load_op(smem_u32(a_s), &amap, 0, m0, hh, nn, a_full);
+            for (int i = 0; i < total; ++i) {
+                const int slot = i % kASlots;
+                mbar_wait(&b_empty[slot], ((i / kASlots) & 1) ^ 1, err, 64);
+                mbar_expect_tx(&b_full[slot], (uint32_t)kATileB);
+                tma_load_op(smem_u32(b_s) + slot * kATileB, &bmap, 0, (i % p.ntiles) * kAKeys, hh, nn, &b_full[slot]);
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(kARows, kAKeys);
+            mbar_wait(a_full, 0, err, 65);
+            const uint64_t a0 = gemm_desc(smem_u32(a_s), true);
+            for (int i = 0; i < total; ++i) {
+                const int slot = i % kASlots, buf = i & 1;
+                mbar_wait(&b_full[slot], (i / kASlots) & 1, err, 66);
+                mbar_wait(&t_empty[buf], ((i >> 1) & 1) ^ 1, err, 67);
+                tc_fence_after();
+                const uint64_t b0 = gemm_desc(smem_u32(b_s) + slot * kATileB, true);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_f16(tmem_base + buf * kAKeys, a0 + (uint64_t)(2 * ks), b0 + (uint64_t)(2 * ks), idesc, ks ? 1u : 0u);
+                umma_commit(&b_empty[slot]);
+                umma_commit(&t_full[buf]);
+            }
+        }
+    }
+    __syncwarp();
+    if (warp < 4) {
+        const int m = m0 + warp * 32 + lane;                          // accumulator row = TMEM lane = query
+        const bool row_ok = m < p.T;
+        const long long rowg = ((long long)nn * p.H + hh) * p.T + m;  // row of P / dS / delta
+        const float sc2 = p.scale * 1.4426950408889634f;              // exp(scale x) = 2^(sc2 x)
+        float nb = 0.f;                                               // -max * sc2 once the maximum is known
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float mx = -INFINITY, l = 0.f, inv = 0.f;
+        const float dl = (MODE == 1 && row_ok) ? __ldg(delta + rowg) : 0.f;
+        const unsigned long long seed = (MODE == 0 && out1 != nullptr) ? (unsigned long long)*seed_ptr : 0ULL;
+#pragma unroll 1
+        for (int i = 0; i < total; ++i) {
+            const int buf = i & 1;
+            mbar_wait(&t_full[buf], (i >> 1) & 1, err, 68);
+            tc_fence_after();
+            float v[kAKeys];
+#pragma unroll
+            for (int c = 0; c < kAKeys; c += 16) tmem_ld16(taddr + buf * kAKeys + c, v + c);
+            tc_fence_before();
+            mbar_arrive(&t_empty[buf]);
+            const int j = i % p.ntiles, c0 = j * kAKeys;
+            if (MODE == 0) {
+                // keys beyond T (last tile only) are -inf scores: they drop out of the maximum and come out as p = 0 without a
+                // per-element predicate in the common path
+                if (c0 + kAKeys > p.T) {
+#pragma unroll
+                    for (int c = 0; c < kAKeys; ++c) if (c0 + c >= p.T) v[c] = -INFINITY;
+                }
+                if (i < p.ntiles) {
+                    float tm = v[0];
+#pragma unroll
+                    for (int c = 1; c < kAKeys; ++c) tm = fmaxf(tm, v[c]);
+                    const float mn = fmaxf(mx, tm);
+                    const float b2 = -mn * sc2;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < kAKeys; ++c) acc += ex2_approx(fmaf(v[c], sc2, b2));
+                    l = l * ex2_approx(fmaf(mx, sc2, b2)) + acc;
+                    mx = mn;
+                    if (i == p.ntiles - 1) { inv = 1.f / l; nb = b2; }
+                    continue;
+                }
+            }
+            if (!row_ok) continue;
+            bf16* o0 = out0 + rowg * p.ldp + c0;
+            if (MODE == 0) {
+#pragma unroll
+                for (int c = 0; c < kAKeys; ++c) v[c] = ex2_approx(fmaf(v[c], sc2, nb)) * inv;
+#pragma unroll
+                for (int c8 = 0; c8 < kAKeys; c8 += 8) {
+                    if (c0 + c8 >= p.ldp) break;                      // ldp is a multiple of 8: a chunk of 8 is inside the row or beyond it
+                    VecIO<bf16, 8>::store(o0 + c8, v + c8);
+                }
+                if (out1 != nullptr) {
+                    const unsigned long long e0 = (unsigned long long)rowg * (unsigned long long)p.T + c0;
+                    bf16* o1 = out1 + rowg * p.ldp + c0;
+#pragma unroll
+                    for (int c8 = 0; c8 < kAKeys; c8 += 8) {
+                        if (c0 + c8 >= p.ldp) break;
+                        float r[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) r[e] = pb_dropout_bits(seed, e0 + c8 + e) >= p.thresh ? v[c8 + e] * p.keep_scale : 0.f;
+                        VecIO<bf16, 8>::store(o1 + c8, r);
+                    }
+                }
+            } else {
+                // keys beyond T: dP' = 0 (zero-filled V rows) and P = P' = 0 (pad columns), so dS = 0 without a predicate
+                const bf16* pi = pin + rowg * p.ldp + c0;
+                const bf16* pdi = pdin + rowg * p.ldp + c0;
+                const float sdl = p.scale * dl;
+#pragma unroll
+                for (int c8 = 0; c8 < kAKeys; c8 += 8) {
+                    if (c0 + c8 >= p.ldp) break;
+                    float r0[8], r1[8];
+                    VecIO<bf16, 8>::load(pi + c8, r0);
+                    if (pin != pdin) {
+                        VecIO<bf16, 8>::load(pdi + c8, r1);
+                    } else {                                          // no dropout: P' is P
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) r1[e] = r0[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) r0[e] = p.scale * r1[e] * v[c8 + e] - sdl * r0[e];
+                    VecIO<bf16, 8>::store(o0 + c8, r0);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    }
+}
+
+template <int MODE>
+int launch_attn_rows(const void* a, const void* b, int N, int H, int T, int d, int lda, long long sa0, long long sa1, int ldb, long long sb0,
+                     long long sb1, const AttnP& p, bf16* out0, bf16* out1, const bf16* pin, const bf16* pdin, const float* delta,
+                     const long long* seed, int* err, cudaStream_t st) {
+    CUtensorMap amap, bmap;
+    const int ra = make_operand_map(&amap, a, d, T, lda, kARows, N, H, sa0, sa1);
+    const int rb = make_operand_map(&bmap, b, d, T, ldb, kAKeys, N, H, sb0, sb1);
+    if (ra || rb) { pb_set_error("attn_rows: cuTensorMapEncodeTiled failed (a %d, b %d)", ra, rb); return PB_EUNSUPPORTED; }
+    const size_t smem = (size_t)kATileA + kASlots * kATileB + (1 + 2 * kASlots + 4) * 8 + 16 + 1024;
+    auto kern = attn_rows_kernel<MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pb_set_error("attn_rows: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
+    kern<<<dim3((T + kARows - 1) / kARows, H, N), kGThreads, smem, st>>>(amap, bmap, p, out0, out1, pin, pdin, delta, seed, err);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" long long pb_gemm_tc_workspace_floats(int M, int N, int K) {
@@ -273,6 +479,48 @@ extern "C" int pb_gemm_tc_batched(const void* a, const void* b, void* d, int M, 
     if (e != cudaSuccess) { pb_set_error("pb_gemm_tc_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PB_ECUDA; }
     const dim3 grid((N + kGBN - 1) / kGBN, (M + kGBM - 1) / kGBM, nb0 * nb1);
     gemm_tc_kernel<<<grid, kGThreads, smem, (cudaStream_t)stream>>>(amap, bmap, p, nullptr, d, nullptr, err_flag);
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+// P = softmax(scale * Q K^T) (and P' with dropout) without materialising the scores; see attn_rows_kernel.  q / k: [N][T][H][d] views
+// (ld = elements between tokens, s0 = between samples, s1 = between heads), d <= 64 and a multiple of 8; p / p_drop [N][H][T][ldp] bf16.
+extern "C" int pb_attn_scores_softmax(const void* q, const void* k, void* p, void* p_drop, int N, int H, int T, int d, int ld, long long s0,
+                                      long long s1, int ldp, float scale, float drop_p, const long long* seed, int* err_flag,
+                                      pb_stream_t stream) {
+    PB_CHECK_ARG(q && k && p && err_flag, "null pointer");
+    PB_CHECK_ARG(N >= 1 && H >= 1 && T >= 1 && H <= 65535 && N <= 65535, "bad batch");
+    PB_CHECK_ARG(d >= 8 && d <= 64 && d % 8 == 0, "head width must be a multiple of 8 up to 64");
+    PB_CHECK_ARG(ld % 8 == 0 && s0 % 8 == 0 && s1 % 8 == 0 && ldp % 8 == 0 && ldp >= T && ldp < T + 8, "strides: multiples of 8, ldp = T rounded up to 8");
+    PB_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)p & 15) == 0 && ((uintptr_t)p_drop & 15) == 0, "16-byte alignment");
+    PB_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (p_drop == nullptr) == (drop_p == 0.f) && (p_drop == nullptr || seed), "dropout arguments");
+    AttnP ap;
+    ap.T = T; ap.ldp = ldp; ap.H = H; ap.ntiles = (T + kAKeys - 1) / kAKeys; ap.scale = scale; ap.keep_scale = 1.f / (1.f - drop_p);
+    { const float t = drop_p * 4294967296.f; ap.thresh = (uint32_t)(t < 4294967040.f ? t : 4294967040.f); }
+    const int rc = launch_attn_rows<0>(q, k, N, H, T, d, ld, s0, s1, ld, s0, s1, ap, (bf16*)p, (bf16*)p_drop, nullptr, nullptr, nullptr, seed,
+                                       err_flag, (cudaStream_t)stream);
+    if (rc) return rc;
+    PB_CHECK_LAUNCH();
+    return PB_OK;
+}
+
+// dS = scale * (P' .* (dO V^T) - P * delta) without materialising dO V^T.  d_o [N][T][H][d] (ld_o, so0, so1), v likewise (ld_v, sv0, sv1),
+// p / p_drop / ds [N][H][T][ldp] bf16 (without dropout pass p for p_drop), delta [N][H][T] fp32 from pb_attn_delta.
+extern "C" int pb_attn_dsoftmax(const void* d_o, const void* v, const void* p, const void* p_drop, const float* delta, void* ds, int N, int H,
+                                int T, int d, int ld_o, long long so0, long long so1, int ld_v, long long sv0, long long sv1, int ldp,
+                                float scale, int* err_flag, pb_stream_t stream) {
+    PB_CHECK_ARG(d_o && v && p && p_drop && delta && ds && err_flag, "null pointer");
+    PB_CHECK_ARG(N >= 1 && H >= 1 && T >= 1 && H <= 65535 && N <= 65535, "bad batch");
+    PB_CHECK_ARG(d >= 8 && d <= 64 && d % 8 == 0, "head width must be a multiple of 8 up to 64");
+    PB_CHECK_ARG(ld_o % 8 == 0 && so0 % 8 == 0 && so1 % 8 == 0 && ld_v % 8 == 0 && sv0 % 8 == 0 && sv1 % 8 == 0 && ldp % 8 == 0 && ldp >= T && ldp < T + 8,
+                 "strides: multiples of 8, ldp = T rounded up to 8");
+    PB_CHECK_ARG(((uintptr_t)d_o & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)p & 15) == 0 && ((uintptr_t)p_drop & 15) == 0 && ((uintptr_t)ds & 15) == 0,
+                 "16-byte alignment");
+    AttnP ap;
+    ap.T = T; ap.ldp = ldp; ap.H = H; ap.ntiles = (T + kAKeys - 1) / kAKeys; ap.scale = scale; ap.keep_scale = 1.f; ap.thresh = 0;
+    const int rc = launch_attn_rows<1>(d_o, v, N, H, T, d, ld_o, so0, so1, ld_v, sv0, sv1, ap, (bf16*)ds, nullptr, (const bf16*)p, (const bf16*)p_drop,
+                                       delta, nullptr, err_flag, (cudaStream_t)stream);
+    if (rc) return rc;
     PB_CHECK_LAUNCH();
     return PB_OK;
 }

@@ -1343,6 +1343,7 @@ def linear(x, weight, bias=None):
 
 # ------------------------------------------------------------------------------------ attention + LayerNorm of the token path
 ATTN_TC = os.environ.get("PB_ATTN_TC", "1") != "0"
+ATTN_FUSED = os.environ.get("PB_ATTN_FUSED", "1") != "0"      # scores fused with their softmax (head width <= 64); 0: GEMM + row kernels
 
 
 def _gemm_tc_batched(name, a, b, out, M, N, K, lda, ldb, ldd, a_kmajor, b_kmajor, nb0, nb1, sa, sb, sd):
@@ -1371,30 +1372,38 @@ class _AttentionTC(torch.autograd.Function):
         scale = float(d) ** -0.5
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]            # views: [N, T, H, d], row stride 3C, head stride d
         sq = (T * 3 * C, d)
-        s = torch.empty((N, H, T, T), dtype=torch.float32, device=dev)
-        # S[t][u] = sum_c q[t][c] k[u][c]
-        _gemm_tc_batched("attn_qk", q, k, s, T, T, d, 3 * C, 3 * C, T, True, True, N, H, sq, sq, (H * T * T, T * T))
         p = torch.empty((N, H, T, ldp), dtype=torch.bfloat16, device=dev)
         if drop_p > 0.0:
             pd = torch.empty_like(p)
             seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=dev)      # graph-safe: drawn from torch's CUDA generator
         else:
             pd, seed = None, None
-        _run("attn_softmax_fwd", f"t{T}", N * H * T * (T * 4 + ldp * (2 if pd is None else 4)), 0.0,
-             lambda: lib.pb_attn_softmax_fwd(_p(s), _p(p), _p(pd), N * H * T, T, ldp, scale, float(drop_p), _p(seed), _stream()))
-        del s
+        fused = ATTN_FUSED and d <= 64
+        if fused:
+            # scores and their softmax in one kernel: no fp32 [N, H, T, T] tensor (csrc/gemm_tc.cu attn_rows_kernel)
+            err = _tc_err_flag(dev)
+            _run("attn_scores_softmax", f"b{N * H} t{T} d{d}", N * H * T * (2 * d * 2 + ldp * (2 if pd is None else 4)), 4.0 * N * H * T * T * d,
+                 lambda: lib.pb_attn_scores_softmax(_p(q), _p(k), _p(p), _p(pd), N, H, T, d, 3 * C, sq[0], sq[1], ldp, scale, float(drop_p),
+                                                    _p(seed), _p(err), _stream()))
+        else:
+            s = torch.empty((N, H, T, T), dtype=torch.float32, device=dev)
+            # S[t][u] = sum_c q[t][c] k[u][c]
+            _gemm_tc_batched("attn_qk", q, k, s, T, T, d, 3 * C, 3 * C, T, True, True, N, H, sq, sq, (H * T * T, T * T))
+            _run("attn_softmax_fwd", f"t{T}", N * H * T * (T * 4 + ldp * (2 if pd is None else 4)), 0.0,
+                 lambda: lib.pb_attn_softmax_fwd(_p(s), _p(p), _p(pd), N * H * T, T, ldp, scale, float(drop_p), _p(seed), _stream()))
+            del s
         pm = p if pd is None else pd
         o = torch.empty((N, T, C), dtype=torch.bfloat16, device=dev)
         # O[t][c] = sum_u P'[t][u] v[u][c]: B = v read as [reduction = u][rows = c]
         _gemm_tc_batched("attn_pv", pm, v, o, T, d, T, ldp, 3 * C, C, True, False, N, H, (H * T * ldp, T * ldp), sq, (T * C, d))
-        ctx.save_for_backward(qkv, p, pm)
-        ctx.scale = scale
+        ctx.save_for_backward(qkv, p, pm, o)
+        ctx.scale, ctx.fused = scale, fused
         return o
 
     @staticmethod
     def backward(ctx, do):
         lib = _lib.load()
-        qkv, p, pm = ctx.saved_tensors
+        qkv, p, pm, o = ctx.saved_tensors
         N, T, _, H, d = qkv.shape
         C = H * d
         dev = qkv.device
@@ -1406,13 +1415,22 @@ class _AttentionTC(torch.autograd.Function):
         dq, dk, dv = dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]
         # dV[u][c] = sum_t P'[t][u] dO[t][c]: both operands read as [reduction = t][rows]
         _gemm_tc_batched("attn_dv", pm, do, dv, T, d, T, ldp, C, 3 * C, False, False, N, H, sp, so, sq)
-        # dP'[t][u] = sum_c dO[t][c] v[u][c]
-        dp = torch.empty((N, H, T, T), dtype=torch.float32, device=dev)
-        _gemm_tc_batched("attn_dp", do, v, dp, T, T, d, C, 3 * C, T, True, True, N, H, so, sq, (H * T * T, T * T))
         ds = torch.empty((N, H, T, ldp), dtype=torch.bfloat16, device=dev)
-        _run("attn_softmax_bwd", f"t{T}", N * H * T * (T * 4 + ldp * 6), 0.0,
-             lambda: lib.pb_attn_softmax_bwd(_p(dp), _p(p), _p(pm), _p(ds), N * H * T, T, ldp, ctx.scale, _stream()))
-        del dp
+        if ctx.fused:
+            # dS = scale (P' .* (dO V^T) - P * delta), delta = rowsum(dO .* O): the fp32 dP' never leaves the SM
+            err = _tc_err_flag(dev)
+            delta = torch.empty((N, H, T), dtype=torch.float32, device=dev)
+            _run("attn_delta", f"t{T}", 2 * do.numel() * 2, 0.0, lambda: lib.pb_attn_delta(_p(do), _p(o), _p(delta), N, T, H, d, _stream()))
+            _run("attn_dsoftmax", f"b{N * H} t{T} d{d}", N * H * T * (2 * d * 2 + ldp * 6), 2.0 * N * H * T * T * d,
+                 lambda: lib.pb_attn_dsoftmax(_p(do), _p(v), _p(p), _p(pm), _p(delta), _p(ds), N, H, T, d, C, so[0], so[1], 3 * C, sq[0], sq[1],
+                                              ldp, ctx.scale, _p(err), _stream()))
+        else:
+            # dP'[t][u] = sum_c dO[t][c] v[u][c]
+            dp = torch.empty((N, H, T, T), dtype=torch.float32, device=dev)
+            _gemm_tc_batched("attn_dp", do, v, dp, T, T, d, C, 3 * C, T, True, True, N, H, so, sq, (H * T * T, T * T))
+            _run("attn_softmax_bwd", f"t{T}", N * H * T * (T * 4 + ldp * 6), 0.0,
+                 lambda: lib.pb_attn_softmax_bwd(_p(dp), _p(p), _p(pm), _p(ds), N * H * T, T, ldp, ctx.scale, _stream()))
+            del dp
         # dQ[t][c] = sum_u dS[t][u] k[u][c];  dK[u][c] = sum_t dS[t][u] q[t][c]
         _gemm_tc_batched("attn_dq", ds, k, dq, T, d, T, ldp, 3 * C, 3 * C, True, False, N, H, sp, sq, sq)
         _gemm_tc_batched("attn_dk", ds, q, dk, T, d, T, ldp, 3 * C, 3 * C, False, False, N, H, sp, sq, sq)

@@ -28,10 +28,14 @@ ATTN_CASES = [(2, 125, 8, 64), (1, 500, 8, 64), (1, 512, 8, 64), (1, 2048, 2, 64
               (2, 130, 8, 8)]
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "gemm+rows"])
 @pytest.mark.parametrize("case", ATTN_CASES, ids=lambda c: "n%d_t%d_h%d_d%d" % c)
-def test_attention_tc(lib_built, case):
+def test_attention_tc(lib_built, case, fused, monkeypatch):
+    """fused: scores and softmax (forward) / dO V^T and the softmax backward in one kernel, no fp32 [N, H, T, T] tensor (head width <= 64);
+    gemm+rows: the same products through pb_gemm_tc_batched with fp32 scores and the row kernels of csrc/attn.cu."""
     from passion_b200 import ops
     N, T, H, d = case
+    monkeypatch.setattr(ops, "ATTN_FUSED", fused)
     g = torch.Generator(device="cpu").manual_seed(T * 13 + H * 5 + d)
     qkv = (torch.randn(N, T, 3, H, d, generator=g) * 1.5).cuda().bfloat16().requires_grad_(True)
     assert ops.attention_tc_eligible(qkv)
@@ -63,11 +67,13 @@ def test_attention_tc_matches_library(lib_built):
     assert o32.dtype == torch.float32 and rel(o32, ref) < 1e-5
 
 
-def test_attention_dropout(lib_built):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "gemm+rows"])
+def test_attention_dropout(lib_built, fused, monkeypatch):
     """Attention dropout (mmformer.py:208, p = 0.1 in train mode): the kept set is a fresh Bernoulli(1 - p) draw per call, kept
     probabilities are scaled by 1 / (1 - p), and forward and backward use the SAME mask (checked against float64 with the mask read
     back from the saved P')."""
     from passion_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_FUSED", fused)
     N, T, H, d, p = 2, 250, 8, 64, 0.1
     g = torch.Generator(device="cpu").manual_seed(4)
     qkv = torch.randn(N, T, 3, H, d, generator=g).cuda().bfloat16().requires_grad_(True)
@@ -93,6 +99,10 @@ def test_attention_dropout(lib_built):
     torch.manual_seed(11)
     o3 = ops.attention(qkv.detach(), p)                      # same generator state: same mask
     assert torch.equal(o3, o.detach())
+    monkeypatch.setattr(ops, "ATTN_FUSED", not fused)        # both paths draw the same mask from the same seed
+    torch.manual_seed(11)
+    o4 = ops.attention(qkv.detach(), p)
+    assert rel(o4, o) < 4e-3
     ops.check_tc_errors()
 
 
