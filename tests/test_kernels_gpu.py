@@ -597,3 +597,31 @@ def test_wgrad_rs_classes(lib_built, case, monkeypatch):
         assert rel(wk.grad, dwr) < 2e-5, (mode, rel(wk.grad, dwr))      # fp32 accumulation of exact bf16 products
     assert rel(got["1"], got["0"]) < 2e-5
     ops.check_tc_errors()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 5, 6, 7, 4), (3, 9, 10, 11, 8), (1, 33, 20, 17, 16), (2, 8, 8, 8, 64), (2, 4, 4, 4, 128),
+                                   (1, 2, 2, 2, 512), (5, 24, 24, 24, 8), (2, 6, 5, 3, 2)], ids=lambda s: "x".join(map(str, s)))
+def test_channel_stats_and_prenorm(lib_built, dtype, shape):
+    """ops.channel_stats (per-(n, c) sum and sum of squares of an arbitrary tensor: the statistics of a PRE-norm block, reference
+    models/blocks.py:312-316) against float64, and ops.prenorm (InstanceNorm -> LeakyReLU(0.2)) built on it, forward and backward."""
+    from passion_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = (torch.randn(*shape, generator=g) * 1.5 + 0.3).cuda().to(dtype)
+    ops.begin_step(torch.device("cuda", 0))
+    st = ops.channel_stats(x)
+    xd = x.double()
+    assert st.dtype == torch.float64 and st.shape == (shape[0], shape[-1], 2)
+    assert rel(st[..., 0], xd.sum((1, 2, 3))) < 1e-6 + (0 if dtype == torch.float32 else 1e-5)
+    assert rel(st[..., 1], (xd * xd).sum((1, 2, 3))) < 1e-6 + (0 if dtype == torch.float32 else 1e-5)
+    xq = x.clone().requires_grad_(True)
+    y = ops.prenorm(xq)
+    gy = torch.randn(*shape, generator=g).cuda().to(dtype)
+    y.backward(gy)
+    xr = xd.clone().requires_grad_(True)
+    xn = xr.permute(0, 4, 1, 2, 3)
+    yr = F.leaky_relu(F.instance_norm(xn, eps=1e-5), 0.2).permute(0, 2, 3, 4, 1)
+    yr.backward(gy.double())
+    tol = TOL[dtype]
+    assert rel(y, yr) < tol
+    assert rel(xq.grad, xr.grad) < (tol if dtype == torch.bfloat16 else 1e-4)
