@@ -11,6 +11,7 @@
 //                  (output = input grown by one voxel per side) followed by small_fold_kernel (see conv3d_tc.cu)
 //   weight grad.   every thread keeps the (kd x) 9 x Cin x Cout partial sums of its voxels in registers across all the
 //                  tiles of a persistent CTA; one block reduction and one atomicAdd per element at the end
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -275,6 +276,141 @@ conv3_small_wgrad_kernel(SmK p, const T* __restrict__ x, const T* __restrict__ d
     }
 }
 
+// ---- bf16 weight gradient with the NEXT tile's halo in flight while the current one is consumed (round 2) ----
+// ncu on the kernel above (c2->2, 80^3, n = 10: 288 us for 41 MB): one CTA of 8 warps per SM (the 108 partial sums take 255 registers),
+// 60 % of the stall samples on the long scoreboard — the CTA stages a tile, waits, computes, and nothing else is resident to hide the wait.
+// Here the halo is copied RAW (bf16, no conversion pass, no registers) by cp.async into the other half of a double buffer while the
+// threads accumulate from the current half; out-of-volume elements are the copy's zero fill, reflection is resolved in the source
+// address.  Needs Cin * 2 bytes >= 4 per copy, i.e. Cin >= 2.
+template <int BYTES> __device__ __forceinline__ void cp_async_small(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(BYTES), "r"(src_bytes) : "memory");
+}
+
+template <int CIN>
+__device__ __forceinline__ void stage_tile_async(const SmK& p, const bf16* __restrict__ x, bf16* __restrict__ tile, int n, int d0, int hb) {
+    const int WP = p.W + 2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nrows = (kTD + 2) * p.rows;
+    for (int row = wid; row < nrows; row += kTQ / 32) {
+        const int dz = row / p.rows, r = row - dz * p.rows;
+        int id = d0 + dz - p.pad, ih = hb + r - p.pad;
+        if (p.reflect) { id = reflect_idx(id, p.Di); ih = reflect_idx(ih, p.Hi); }
+        const bool ok_row = id >= 0 && id < p.Di && ih >= 0 && ih < p.Hi;
+        const bf16* src = x + (((size_t)n * p.Di + (ok_row ? id : 0)) * p.Hi + (ok_row ? ih : 0)) * p.Wi * CIN;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + (size_t)row * WP * CIN);
+        for (int c = lane; c < WP; c += 32) {
+            int iw = c - p.pad;
+            bool ok = ok_row;
+            if (p.reflect) iw = reflect_idx(iw, p.Wi); else ok = ok && iw >= 0 && iw < p.Wi;
+            cp_async_small<CIN * 2>(dst + (uint32_t)c * CIN * 2, ok ? src + (size_t)iw * CIN : x, ok ? CIN * 2u : 0u);
+        }
+    }
+}
+
+template <int CIN> __device__ __forceinline__ void lds_bf16N(const bf16* p, float* o) {
+    if constexpr (CIN == 2) {
+        bf2_unpack(*reinterpret_cast<const uint32_t*>(p), o[0], o[1]);
+    } else if constexpr (CIN == 4) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        bf2_unpack(u.x, o[0], o[1]); bf2_unpack(u.y, o[2], o[3]);
+    } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        bf2_unpack(u.x, o[0], o[1]); bf2_unpack(u.y, o[2], o[3]); bf2_unpack(u.z, o[4], o[5]); bf2_unpack(u.w, o[6], o[7]);
+    }
+}
+
+template <int CIN, int COUT, int KDS>
+__global__ void __launch_bounds__(kTQ, (KDS * 9 * CIN * COUT <= 80) ? 2 : 1)
+conv3_small_wgrad_async_kernel(SmK p, const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NACC = KDS * 9 * CIN * COUT;
+    const int g = blockIdx.z, kd0 = blockIdx.y * KDS;
+    const int WP = p.W + 2;
+    const size_t tile_elems = (((size_t)(kTD + 2) * p.rows * WP * CIN + 7) / 8) * 8;           // 16-byte aligned halves
+    bf16* tiles = reinterpret_cast<bf16*>(smem);
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    const int per_sample = p.tiles_q * p.tiles_d;
+    const int items = p.npg * per_sample;
+    int buf = 0;
+    if ((int)blockIdx.x < items) {
+        const int it = blockIdx.x, r = it % per_sample;
+        stage_tile_async<CIN>(p, x, tiles, g * p.npg + it / per_sample, (r / p.tiles_q) * kTD, ((r % p.tiles_q) * kTQ) / p.W);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int n = g * p.npg + it / per_sample;
+        const int r = it % per_sample;
+        const int qt = r % p.tiles_q, dt = r / p.tiles_q;
+        const int d0 = dt * kTD, q0 = qt * kTQ;
+        const int hb = q0 / p.W;
+        const int q = q0 + threadIdx.x;
+        const bool valid = q < p.H * p.W;
+        const int h = valid ? q / p.W : hb, wq = valid ? q - h * p.W : 0;
+        const bf16* dyp = dy + ((((size_t)n * p.D + d0) * p.H + h) * p.W + wq) * COUT;
+        const size_t plane = (size_t)p.H * p.W * COUT;
+        float gall[kTD][COUT];
+#pragma unroll
+        for (int o = 0; o < kTD; ++o) {
+            if (valid && d0 + o < p.D) VecIO<bf16, COUT>::load(dyp + (size_t)o * plane, gall[o]);
+            else {
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) gall[o][j] = 0.f;
+            }
+        }
+        {   // next tile of this CTA into the other half (its previous readers passed the barrier at the end of the last iteration)
+            const int nx = it + gridDim.x;
+            if (nx < items) {
+                const int rn = nx % per_sample;
+                stage_tile_async<CIN>(p, x, tiles + (size_t)(buf ^ 1) * tile_elems, g * p.npg + nx / per_sample, (rn / p.tiles_q) * kTD,
+                                      ((rn % p.tiles_q) * kTQ) / p.W);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the group just committed: the current tile has landed
+        __syncthreads();
+        const bf16* tile = tiles + (size_t)buf * tile_elems;
+#pragma unroll
+        for (int o = 0; o < kTD; ++o) {
+#pragma unroll
+            for (int k = 0; k < KDS; ++k)
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        float xv[CIN];
+                        lds_bf16N<CIN>(tile + (((size_t)(o + kd0 + k) * p.rows + (h - hb + kh)) * WP + wq + kw) * CIN, xv);
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                            for (int j = 0; j < COUT; ++j)
+                                acc[((k * 3 + kh) * 3 + kw) * CIN * COUT + ci * COUT + j] =
+                                    fmaf(xv[ci], gall[o][j], acc[((k * 3 + kh) * 3 + kw) * CIN * COUT + ci * COUT + j]);
+                    }
+        }
+        __syncthreads();                                        // this half may be overwritten by the copies of the next iteration
+        buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float* red = smem;                                          // [8][NACC]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        const float sres = warp_sum(acc[i]);
+        if (lane == 0) red[wid * NACC + i] = sres;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NACC; i += kTQ) {
+        float sres = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sres += red[k * NACC + i];
+        const int k = i / (9 * CIN * COUT), rest = i % (9 * CIN * COUT);
+        atomicAdd(dw + ((size_t)g * 27 + (kd0 + k) * 9) * CIN * COUT + rest, sres);
+    }
+}
+
 // dx[v] = sum of the extended-domain values that the reflect padding maps onto v (every voxel; C channels, C <= 8)
 template <typename T, int C>
 __global__ void __launch_bounds__(256) small_fold_kernel(const T* __restrict__ ext, T* __restrict__ dx, int N, int D, int H, int W) {
@@ -371,8 +507,36 @@ int dispatch_fwd(const SmK& p, int cin, int cout, const void* x, const float* w,
     return PB_EUNSUPPORTED;
 }
 
+template <int CIN, int COUT, int KDS>
+int launch_wgrad_async(const SmK& p, int groups, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    constexpr int NACC = KDS * 9 * CIN * COUT;
+    const size_t tile_elems = (((size_t)(kTD + 2) * p.rows * (p.W + 2) * CIN + 7) / 8) * 8;
+    size_t smem = 2 * tile_elems * sizeof(bf16);
+    if (smem < (size_t)8 * NACC * sizeof(float)) smem = (size_t)8 * NACC * sizeof(float);
+    auto kern = conv3_small_wgrad_async_kernel<CIN, COUT, KDS>;
+    if (int e = set_smem_small(kern, smem)) return e;
+    const int items = p.npg * p.tiles_q * p.tiles_d;
+    const int per_sm = (NACC <= 80) ? 2 : 1;                    // resident CTAs (register budget of the partial sums)
+    int ctas = 148 * per_sm / (groups * (3 / KDS));
+    if (ctas < 1) ctas = 1;
+    if (ctas > items) ctas = items;
+    kern<<<dim3(ctas, 3 / KDS, groups), kTQ, smem, st>>>(p, (const bf16*)x, (const bf16*)dy, dw);
+    return 0;
+}
+
+int small_wgrad_async_mode() {          // PB_SMALL_WGRAD_ASYNC=0: the single-buffer kernel everywhere (A/B measurements)
+    static const int mode = [] { const char* e = getenv("PB_SMALL_WGRAD_ASYNC"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
+    return mode;
+}
+
 template <typename T>
 int dispatch_wgrad(const SmK& p, int groups, int cin, int cout, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    if constexpr (sizeof(T) == 2) {
+        if (small_wgrad_async_mode()) {
+            if (cin == 2 && cout == 2) return launch_wgrad_async<2, 2, 3>(p, groups, x, dy, dw, st);
+            if (cin == 4 && cout == 4) return launch_wgrad_async<4, 4, 1>(p, groups, x, dy, dw, st);
+        }
+    }
     if (cin == 1 && cout == 8) return launch_wgrad<T, 1, 8, 1>(p, groups, x, dy, dw, st);
     if (cin == 2 && cout == 2) return launch_wgrad<T, 2, 2, 3>(p, groups, x, dy, dw, st);
     if (cin == 4 && cout == 4) return launch_wgrad<T, 4, 4, 1>(p, groups, x, dy, dw, st);
