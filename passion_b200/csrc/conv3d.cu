@@ -636,6 +636,146 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(ConvK p, WgK q, const T
     }
 }
 
+// ------------------------------------------------------------------------------------ wgrad, 3x3x3 stride 2, bf16 (round 2)
+// The two longest launches of the RFNet step were the stride-2 data and weight gradients (ncu launch list: 319 / 309 us on the
+// 8 -> 16 encoder conv).  The tiled kernel above stages a tile, waits, accumulates, and pays two integer divisions per voxel and
+// accumulator row; this variant keeps its work split (thread = (tap, 4 input channels) x 16 output channels for a slice of the
+// tile's voxels) but
+//   * copies the NEXT tile's input halo and dy tile RAW (bf16) by 16-byte cp.async into the other half of a double buffer while the
+//     current tile is consumed (out-of-volume elements are the copy's zero fill, reflection is resolved in the source address);
+//   * has compile-time tile extents (2 x 4 x 8 outputs, 5 x 9 x 17 inputs), so voxel -> halo offsets are shifts and adds;
+//   * converts the 64 x 16 dy values of a tile to fp32 once per tile instead of once per (thread, voxel).
+// Single source (the encoder's down-sampling convs), CIC in {8, 16} input channels per CTA, 16 output channels per CTA.
+constexpr int kS2Td = 2, kS2Th = 4, kS2Tw = 8, kS2Tv = kS2Td * kS2Th * kS2Tw;              // output tile
+constexpr int kS2Hd = 5, kS2Hh = 9, kS2Hw = 17, kS2Halo = kS2Hd * kS2Hh * kS2Hw;          // input halo = (t - 1) * 2 + 3
+
+template <int CIC>
+__device__ __forceinline__ void s2_stage(const ConvK& p, const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ xraw,
+                                         bf16* __restrict__ dyraw, int n, int od0, int oh0, int ow0, int ci0, int co0) {
+    constexpr int CPV = CIC / 8;                                  // 16-byte copies per halo voxel
+    for (int idx = threadIdx.x; idx < kS2Halo * CPV; idx += 256) {
+        const int hv = idx / CPV, part = idx - hv * CPV;
+        const int hw_i = hv % kS2Hw, r2 = hv / kS2Hw;
+        const int hh_i = r2 % kS2Hh, hd_i = r2 / kS2Hh;
+        int id = od0 * 2 - 1 + hd_i, ih = oh0 * 2 - 1 + hh_i, iw = ow0 * 2 - 1 + hw_i;
+        if (p.reflect) { id = reflect_idx(id, p.Di); ih = reflect_idx(ih, p.Hi); iw = reflect_idx(iw, p.Wi); }
+        const bool ok = id >= 0 && id < p.Di && ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi;
+        const bf16* src = ok ? x + ((((size_t)n * p.Di + id) * p.Hi + ih) * p.Wi + iw) * p.C0 + ci0 + part * 8 : x;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xraw + (size_t)hv * CIC + part * 8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+    }
+    for (int idx = threadIdx.x; idx < kS2Tv * 2; idx += 256) {
+        const int v = idx >> 1, part = idx & 1;
+        const int od = od0 + (v >> 5), oh = oh0 + ((v >> 3) & 3), ow = ow0 + (v & 7);
+        const bool ok = od < p.Do && oh < p.Ho && ow < p.Wo;
+        const bf16* src = ok ? dy + ((((size_t)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + co0 + part * 8 : dy;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dyraw + v * 16 + part * 8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+    }
+}
+
+template <int CIC>
+__global__ void __launch_bounds__(256, 2) conv_wgrad_s2_kernel(ConvK p, int tiles_d, int tiles_h, int tiles_w, int n_cic,
+                                                               const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw) {
+    extern __shared__ __align__(16) uint8_t s2_smem[];
+    constexpr int NQ = CIC / 4, NITEMS = 27 * NQ, SLICES = 256 / NITEMS;
+    constexpr size_t XBYTES = (size_t)kS2Halo * CIC * 2, DBYTES = (size_t)kS2Tv * 16 * 2;
+    auto xraw = [&](int b) { return reinterpret_cast<bf16*>(s2_smem + (size_t)b * XBYTES); };
+    auto dyraw = [&](int b) { return reinterpret_cast<bf16*>(s2_smem + 2 * XBYTES + (size_t)b * DBYTES); };
+    float* dyf = reinterpret_cast<float*>(s2_smem + 2 * XBYTES + 2 * DBYTES);               // [64][16] fp32
+    const int g = blockIdx.z;
+    const int cic_i = blockIdx.y % n_cic, coc = blockIdx.y / n_cic;
+    const int ci0 = cic_i * CIC, co0 = coc * 16;
+    const int tid = threadIdx.x;
+    const int item = tid % NITEMS, slice = tid / NITEMS;
+    const bool active = slice < SLICES;
+    const int tap = item / NQ, ciq = item - tap * NQ;
+    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    const int tapoff = ((kd * kS2Hh + kh) * kS2Hw + kw) * CIC + ciq * 4;                  // element offset inside the halo tile
+
+    float acc[4][16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+
+    const int tiles_ps = tiles_d * tiles_h * tiles_w;
+    const long long ntiles = (long long)p.npg * tiles_ps;
+    auto coords = [&](long long t, int& n, int& od0, int& oh0, int& ow0) {
+        n = g * p.npg + (int)(t / tiles_ps);
+        int r = (int)(t % tiles_ps);
+        const int tw_i = r % tiles_w; r /= tiles_w;
+        od0 = (r / tiles_h) * kS2Td; oh0 = (r % tiles_h) * kS2Th; ow0 = tw_i * kS2Tw;
+    };
+    int buf = 0;
+    if ((long long)blockIdx.x < ntiles) {
+        int n, od0, oh0, ow0;
+        coords(blockIdx.x, n, od0, oh0, ow0);
+        s2_stage<CIC>(p, x, dy, xraw(0), dyraw(0), n, od0, oh0, ow0, ci0, co0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (t + gridDim.x < ntiles) {
+            int n, od0, oh0, ow0;
+            coords(t + gridDim.x, n, od0, oh0, ow0);
+            s2_stage<CIC>(p, x, dy, xraw(buf ^ 1), dyraw(buf ^ 1), n, od0, oh0, ow0, ci0, co0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");          // the current tile has landed
+        __syncthreads();
+        {   // dy tile -> fp32, once per tile (64 x 16 values, 4 per thread)
+            const uint2 u = *reinterpret_cast<const uint2*>(dyraw(buf) + tid * 4);
+            float4 f;
+            bf2_unpack(u.x, f.x, f.y); bf2_unpack(u.y, f.z, f.w);
+            reinterpret_cast<float4*>(dyf)[tid] = f;
+        }
+        __syncthreads();
+        if (active) {
+            const bf16* xb = xraw(buf) + tapoff;
+#pragma unroll 2
+            for (int v = slice; v < kS2Tv; v += SLICES) {
+                const int hv = (((v >> 5) * 2) * kS2Hh + ((v >> 3) & 3) * 2) * kS2Hw + (v & 7) * 2;
+                const uint2 xu = *reinterpret_cast<const uint2*>(xb + hv * CIC);
+                float xv[4];
+                bf2_unpack(xu.x, xv[0], xv[1]); bf2_unpack(xu.y, xv[2], xv[3]);
+                float gv[16];
+                lds_vec<16>(dyf + v * 16, gv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();                                                // both halves of the next iteration's writes are free now
+        buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // the SLICES partial sums of an item are combined in shared memory first (slice after slice into one [item][4][16] buffer that
+    // reuses the tile storage), so a CTA sends NITEMS x 64 atomics instead of 256 x 64 — with ~300 persistent CTAs adding into the
+    // same 27 x CIC x 16 addresses, the atomics were a visible tail of the launch
+    float* red = reinterpret_cast<float*>(s2_smem);
+    static_assert((size_t)NITEMS * 64 * sizeof(float) <= 2 * XBYTES + 2 * DBYTES + (size_t)kS2Tv * 16 * sizeof(float), "reduction buffer");
+    for (int sl = 0; sl < SLICES; ++sl) {
+        if (active && slice == sl) {
+            float4* r4 = reinterpret_cast<float4*>(red + (size_t)item * 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 a = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+                    if (sl > 0) { const float4 b = r4[i * 4 + j / 4]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+                    r4[i * 4 + j / 4] = a;
+                }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < NITEMS * 64; e += 256) {
+        const int it2 = e >> 6, i = (e >> 4) & 3, j = e & 15;
+        const int tap2 = it2 / NQ, ciq2 = it2 - tap2 * NQ;
+        atomicAdd(dw + (((size_t)g * 27 + tap2) * p.Cin + ci0 + ciq2 * 4 + i) * p.Cout + co0 + j, red[e]);
+    }
+}
+
 // ------------------------------------------------------------------------------------ wgrad, 1x1x1
 // dw[ci][co] = sum_v x[v][ci] * dy[v][co]: every thread streams a strided set of voxels and keeps a CI_B x CO_B
 // register tile; one shuffle + smem reduction per block, then fp32 atomics.  grid = (voxel blocks, ci/co tiles, groups)
@@ -1071,9 +1211,37 @@ int dispatch_wgrad1(const ConvK& k, const void* x0, const void* x1, const void* 
 #undef W1
 }
 
+template <int CIC>
+int launch_wgrad_s2(const ConvK& k, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    const int tiles_d = (k.Do + kS2Td - 1) / kS2Td, tiles_h = (k.Ho + kS2Th - 1) / kS2Th, tiles_w = (k.Wo + kS2Tw - 1) / kS2Tw;
+    const size_t smem = 2 * ((size_t)kS2Halo * CIC * 2 + (size_t)kS2Tv * 16 * 2) + (size_t)kS2Tv * 16 * sizeof(float);
+    auto kern = conv_wgrad_s2_kernel<CIC>;
+    if (int e = set_smem(kern, smem)) return e;
+    const int n_cic = k.Cin / CIC, pairs = n_cic * (k.Cout / 16);
+    const long long ntiles = (long long)k.npg * tiles_d * tiles_h * tiles_w;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 2;
+    long long nblk = (148LL * occ) / ((long long)pairs * k.groups);
+    if (nblk < 1) nblk = 1;
+    if (nblk > ntiles) nblk = ntiles;
+    kern<<<dim3((unsigned)nblk, pairs, k.groups), 256, smem, st>>>(k, tiles_d, tiles_h, tiles_w, n_cic, (const bf16*)x, (const bf16*)dy, dw);
+    return 0;
+}
+
+int wgrad_s2_mode() {          // PB_WGRAD_S2=0: the generic tiled kernel for the stride-2 weight gradients (A/B measurements)
+    static const int mode = [] { const char* e = getenv("PB_WGRAD_S2"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
+    return mode;
+}
+
 template <typename T>
 int dispatch_wgrad(const ConvK& k, const void* x0, const void* x1, const void* dy, float* dw, cudaStream_t st) {
     if (k.K == 1) return dispatch_wgrad1<T>(k, x0, x1, dy, dw, st);
+    if constexpr (sizeof(T) == 2) {
+        if (k.K == 3 && k.S == 2 && k.C1 == 0 && k.Cin % 8 == 0 && k.Cout % 16 == 0 && wgrad_s2_mode()) {
+            if (k.Cin % 16 == 0) return launch_wgrad_s2<16>(k, x0, dy, dw, st);
+            return launch_wgrad_s2<8>(k, x0, dy, dw, st);
+        }
+    }
     WgK q;
     if (k.S == 1) { q.td = 4; q.th = 4; q.tw = 8; } else { q.td = 2; q.th = 4; q.tw = 8; }
     q.hd = (q.td - 1) * k.S + k.K; q.hh = (q.th - 1) * k.S + k.K; q.hw = (q.tw - 1) * k.S + k.K;
