@@ -430,6 +430,20 @@ __global__ void __launch_bounds__(128) conv_dgrad_kernel(ConvK p, const T* __res
 __device__ __forceinline__ int axis_pairs(int i, int Din, int Dout, int K, int S, int pad, int reflect, unsigned long long& packed) {
     int n = 0;
     packed = 0ull;
+    // 3-tap, stride 2, pad 1 away from the two indices that have a reflected twin (1 and Din - 2): closed form — an odd index is
+    // reached by taps 0 and 2, an even one by tap 1.  (The general enumeration below costs ~250 instructions per axis, with
+    // divisions by a run-time stride: more than the FMAs of an average voxel of the stride-2 data gradients.)
+    if (K == 3 && S == 2 && pad == 1 && !(reflect && (i == 1 || i == Din - 2))) {
+        if (i & 1) {
+            const int o0 = (i + 1) >> 1, o1 = (i - 1) >> 1;
+            if (o0 < Dout) { packed |= (unsigned long long)((o0 << 2) | 0) << (10 * n); ++n; }
+            if (o1 < Dout) { packed |= (unsigned long long)((o1 << 2) | 2) << (10 * n); ++n; }
+        } else {
+            const int o = i >> 1;
+            if (o < Dout) { packed = (unsigned long long)((o << 2) | 1); n = 1; }
+        }
+        return n;
+    }
     const int nc = reflect ? 3 : 1;
     for (int c = 0; c < nc; ++c) {
         bool ok;
@@ -448,7 +462,7 @@ __device__ __forceinline__ int axis_pairs(int i, int Din, int Dout, int K, int S
 }
 
 template <typename T, int CO_V, int CI_T>
-__global__ void __launch_bounds__(128) conv_dgrad_pairs_kernel(ConvK p, const T* __restrict__ dy, const float* __restrict__ wt,
+__global__ void __launch_bounds__(256) conv_dgrad_pairs_kernel(ConvK p, const T* __restrict__ dy, const float* __restrict__ wt,
                                                                T* __restrict__ dx0, T* __restrict__ dx1) {
     extern __shared__ __align__(16) float wsm[];              // [taps][Cout][CI_T]
     const int n = blockIdx.z, cic = blockIdx.y, g = n / p.npg;
@@ -456,12 +470,12 @@ __global__ void __launch_bounds__(128) conv_dgrad_pairs_kernel(ConvK p, const T*
     const float* wg = wt + (size_t)g * taps * p.Cout * p.Cin + cic * CI_T;
     if constexpr (CI_T % 4 == 0) {                            // rows of CI_T floats, 16-byte aligned on both sides
         constexpr int Q = CI_T / 4;
-        for (int i = threadIdx.x; i < taps * p.Cout * Q; i += 128) {
+        for (int i = threadIdx.x; i < taps * p.Cout * Q; i += blockDim.x) {
             const int j = i % Q, r = i / Q;
             reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(wg + (size_t)r * p.Cin) + j);
         }
     } else {
-        for (int i = threadIdx.x; i < taps * p.Cout * CI_T; i += 128) {
+        for (int i = threadIdx.x; i < taps * p.Cout * CI_T; i += blockDim.x) {
             int j = i % CI_T, r = i / CI_T;
             wsm[i] = wg[(size_t)r * p.Cin + j];
         }
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(128) conv_dgrad_pairs_kernel(ConvK p, const T*
     const int qd = by_parity ? (p.Di + 1) / 2 : p.Di, qh = by_parity ? (p.Hi + 1) / 2 : p.Hi, qw = by_parity ? (p.Wi + 1) / 2 : p.Wi;
     const long long cls_sz = (long long)qd * qh * qw;
     const long long n_virtual = by_parity ? 8 * cls_sz : p.Vi;
-    for (long long jv = (long long)blockIdx.x * 128 + threadIdx.x; jv < n_virtual; jv += (long long)gridDim.x * 128) {
+    for (long long jv = (long long)blockIdx.x * blockDim.x + threadIdx.x; jv < n_virtual; jv += (long long)gridDim.x * blockDim.x) {
     int iw, ih, id;
     if (by_parity) {
         const int cls = 7 - (int)(jv / cls_sz);
@@ -1009,6 +1023,8 @@ int launch_dgrad(const ConvK& k, const void* dy, const float* wt, void* dx0, voi
         const long long cap = (148LL * resident + (long long)(k.Cin / CI_T) * k.N - 1) / ((long long)(k.Cin / CI_T) * k.N);
         if (bx > cap) bx = cap;
         dim3 gridp((unsigned)bx, k.Cin / CI_T, k.N);
+        // (256 threads per CTA for the layers whose weight slice leaves one or two CTAs per SM were measured: 16 -> 32 at 20^3 0.168 ->
+        // 0.201 ms, 32 -> 64 at 10^3 unchanged — the same grid then has half the voxels per thread behind the same staging prologue)
         kp<<<gridp, 128, smem, st>>>(k, (const T*)dy, wt, (T*)dx0, (T*)dx1);
         return 0;
     }
