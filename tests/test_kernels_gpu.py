@@ -71,6 +71,10 @@ CONV_CASES = [
     # 128 input channels on planes wider than RFNet's 10^3: mmFormer's 64 + 64 -> 64 decoder conv at 16^3 (128^3 crop) and a W = 30 plane
     (64, 64, 64, 3, 1, "reflect", 1, 1, (16, 16, 16), True),
     (128, 0, 64, 3, 1, "zeros", 1, 1, (3, 20, 30), True),
+    # stride 2 with odd extents and with zero padding (parity-class data gradient, double-buffered weight gradient: ragged tiles)
+    (8, 0, 16, 3, 2, "zeros", 1, 2, (7, 9, 6), False),
+    (16, 0, 32, 3, 2, "reflect", 2, 2, (9, 7, 11), True),
+    (8, 0, 16, 3, 2, "reflect", 1, 1, (20, 18, 22), False),
     # very few channels: shared-memory tiled kernels (several tiles in d and in the plane, ragged edges, zero padding)
     (2, 0, 2, 3, 1, "reflect", 1, 2, (20, 18, 22), False),
     (2, 0, 2, 3, 1, "zeros", 1, 2, (6, 7, 8), True),
